@@ -1,0 +1,226 @@
+/*
+ * vrdd.h — C ABI of libvrdd.so: B200-native distribution decode (P1) and volume ray
+ * casting (P2).  Plain pointers, sizes and ints only; no C++ or torch types.
+ *
+ * The library replaces the device side of ykou/Volume-Rendering-Based-on-Distribution-Data
+ * behind the reference's own host-facing surface.  Two layers are exported:
+ *
+ *   1. the handle-based vrdd_* API below — size-generic, explicit stream, error codes,
+ *      multi-GPU partitions — which is what new host code binds; and
+ *   2. the seven legacy `extern "C"` symbols with the reference's exact signatures
+ *      (include/vrdd_legacy.h), implemented on one default handle, so the unmodified
+ *      /root/reference/volumeRender.cpp links against libvrdd.so instead of
+ *      volumeRender_kernel.cu.
+ *
+ * Each entry point names the reference interface it replaces (file:line in
+ * /root/reference).  All functions return VRDD_OK (0) or a negative vrdd_status; the
+ * reference aborts the process on any CUDA error (checkCudaErrors), this library never
+ * does.  There is no CPU fallback: without a CUDA device every compute call fails with
+ * VRDD_ERR_NO_DEVICE.
+ *
+ * Threading: a handle is not re-entrant (the reference keeps all state in file-scope
+ * globals, volumeRender_kernel.cu:22-43); distinct handles may be used from distinct
+ * threads.  All work is enqueued on the handle's stream and is asynchronous unless a
+ * function is documented to copy to host memory.
+ */
+#ifndef VRDD_H_
+#define VRDD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRDD_VERSION 100
+
+typedef struct vrdd_context* vrdd_handle;
+
+typedef enum vrdd_status {
+    VRDD_OK = 0,
+    VRDD_ERR_INVALID = -1,      /* bad argument / call order */
+    VRDD_ERR_CUDA = -2,         /* CUDA runtime error; see vrdd_last_error() */
+    VRDD_ERR_NO_DEVICE = -3,    /* no usable CUDA device (no CPU fallback exists) */
+    VRDD_ERR_RANGE = -4,        /* input violates the reference's run-time guards
+                                   (volumeRender_kernel.cu:781-816, volumeRender.cpp:611-614) */
+    VRDD_ERR_UNSUPPORTED = -5   /* valid in the reference but outside this build's scope */
+} vrdd_status;
+
+/* Which decoded volume: the reference keeps two float4 arrays
+ * (originalHistogramData / fractalHistogramData, volumeRender_kernel.cu:719-720). */
+typedef enum vrdd_source { VRDD_SRC_ORIGINAL = 0, VRDD_SRC_FRACTAL = 1 } vrdd_source;
+
+/* Ray-caster sampling path (both must agree with the oracle within +-1 LSB). */
+typedef enum vrdd_sampler {
+    VRDD_SAMPLER_TEXTURE = 0,   /* decoded planes live in 3-D cudaArrays; the texture unit
+                                   filters (the reference's own path, :601-651) */
+    VRDD_SAMPLER_BRICKED = 1    /* decoded planes live in a bricked linear layout; manual
+                                   trilinear with the texture unit's 8-bit weights */
+} vrdd_sampler;
+
+/* Ray-marching parameters.  Defaults = the reference's compile-time constants
+ * (volumeRender_kernel.cu:276-278) and run-time defaults (volumeRender.cpp:130-133). */
+typedef struct vrdd_render_params {
+    float density;            /* 0.05f  */
+    float brightness;         /* 1.0f   */
+    float transfer_offset;    /* 0.0f   */
+    float transfer_scale;     /* 1.0f   */
+    float tstep;              /* 0.01f  */
+    int max_steps;            /* 500    */
+    float opacity_threshold;  /* 0.95f  */
+    int query_method;         /* 1,2,3 = mean/variance/entropy of the original histograms,
+                                 4,5,6 = same of the fractal-decoded ones (volumeRender.cpp:129) */
+} vrdd_render_params;
+
+/* Image-space partition for multi-GPU rendering: the image is cut into tile_w x tile_h
+ * tiles, numbered row-major, and this call renders tiles with index % parts == part.
+ * parts = 1 renders everything.  Pixels of other parts are not touched. */
+typedef struct vrdd_tile_partition {
+    int tile_w, tile_h;
+    int part, parts;
+} vrdd_tile_partition;
+
+/* ---- lifetime ----------------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device` (-1 = current device).  Replaces the
+ * file-scope globals of volumeRender_kernel.cu:22-43 and chooseCudaDevice
+ * (volumeRender.cpp:1000-1014). */
+int vrdd_create(int device, vrdd_handle* out);
+/* Releases every device allocation.  Replaces freeCudaBuffers (volumeRender_kernel.cu:2360). */
+int vrdd_destroy(vrdd_handle h);
+/* Work is enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream,
+ * which is what the reference uses everywhere). */
+int vrdd_set_stream(vrdd_handle h, void* cuda_stream);
+int vrdd_synchronize(vrdd_handle h);
+/* Human-readable description of the last error on this handle (never NULL). */
+const char* vrdd_last_error(vrdd_handle h);
+/* Number of kernels this library has launched on this handle since creation. */
+int64_t vrdd_kernel_launches(vrdd_handle h);
+
+/* ---- volume geometry and inputs (replaces initCuda, volumeRender_kernel.cu:1893) ----- */
+
+/* Size of the distribution volume in voxels ("blocks" in the reference, 50x50x10 there,
+ * volumeRender.cpp:86) and bins per histogram (32, volumeRender_kernel.cu:91; this build
+ * supports bins == 32 only).  Drops any previously decoded data. */
+int vrdd_set_volume(vrdd_handle h, int width, int height, int depth, int bins);
+
+/* Raw histograms, float hist[depth*height*width][bins], x fastest
+ * (the h_volume argument of initCuda; layout volumeRender_kernel.cu:740-745).
+ * _host copies synchronously from host memory like the reference does
+ * (volumeRender_kernel.cu:1893-2158); the pointer is not retained.
+ * _device borrows a device pointer covering z-slices [z0, z0+nz) only — slab-wise
+ * streaming of volumes that do not fit (a 1024^3 volume is 137 GB).  The caller keeps the
+ * memory alive until the slab has been decoded. */
+int vrdd_set_histograms_host(vrdd_handle h, const float* hist);
+int vrdd_set_histograms_device(vrdd_handle h, const float* d_hist, int z0, int nz);
+
+/* Fractal codes (h_codebook, h_templates, h_errorsbook of initCuda).
+ *   codebook:  int32[V][4] = (templateId, shift, flip, NE)     volumeRender.cpp:617
+ *   errors_dense: float[V][bins][2] = (binId, value), first NE entries of each row valid
+ *                                                              volumeRender.cpp:582, 625-635
+ *   templates: float[num_templates][bins]                      volumeRender.cpp:661-681
+ * The dense error table is compacted on upload to 8*NE bytes per voxel.  Codes are
+ * validated against the reference's guards; VRDD_ERR_RANGE reports a violation. */
+int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* errors_dense,
+                          const float* templates, int num_templates);
+/* Compact device-resident form for slab streaming:
+ *   d_codebook: int32[nvox][4];  d_errors: float[total_ne][2] in voxel order;
+ *   d_chunk_offsets: uint64[ceil(nvox/256)+1], entry c = index into d_errors of the first
+ *   error of voxel 256*c (exclusive prefix sum of NE taken every 256 voxels);
+ *   d_templates: float[num_templates][bins].  Covers z-slices [z0, z0+nz). */
+int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const float* d_errors,
+                            const uint64_t* d_chunk_offsets, const float* d_templates,
+                            int num_templates, int z0, int nz);
+
+/* ---- P1: decode (replaces basicDataProcessing, volumeRender_kernel.cu:1798-1887) ----- */
+
+/* Selects where decoded volumes are kept; call before decoding.  Default TEXTURE. */
+int vrdd_set_sampler(vrdd_handle h, int sampler /* vrdd_sampler */);
+
+/* Decodes z-slices [z0, z0+nz) of `source` into the (mean, variance, entropy) volume the
+ * ray caster samples.  Stays on the device: the reference's D->H->D round trip
+ * (volumeRender_kernel.cu:1805-1862) is gone.  nz <= 0 decodes the slab most recently
+ * attached for that source. */
+int vrdd_decode(vrdd_handle h, int source /* vrdd_source */, int z0, int nz);
+
+/* Copies the decoded volume of `source` to host memory as float4[V] = (mean, variance,
+ * entropy, 0), x fastest — the layout of originalHistogramData / fractalHistogramData
+ * (volumeRender_kernel.cu:719-720, 771-773).  Synchronous. */
+int vrdd_get_decoded_host(vrdd_handle h, int source, float* out4);
+/* Device pointers of the three decoded planes (float[V] each, x fastest), or NULL when the
+ * handle keeps them only in cudaArrays (TEXTURE sampler without linear planes).  For
+ * NCCL all-gather of z-slabs across ranks. */
+int vrdd_get_decoded_planes_device(vrdd_handle h, int source, float** mean, float** variance,
+                                   float** entropy);
+/* Keep linear planes next to the texture arrays (needed for the call above and for
+ * vrdd_commit_planes).  Off by default: the decode then writes the arrays directly. */
+int vrdd_keep_linear_planes(vrdd_handle h, int keep);
+/* After writing z-slices [z0, z0+nz) of the linear planes from outside (e.g. an NCCL
+ * all-gather), republish them to the sampler's layout. */
+int vrdd_commit_planes(vrdd_handle h, int source, int z0, int nz);
+
+/* Bit-comparable view of the integer part of the fractal decode: the reconstructed
+ * histogram float[nvox][bins] after template lookup, flip, shift, error merge and clamp,
+ * BEFORE normalisation (volumeRender_kernel.cu:798-825), for the attached slab.
+ * d_out is device memory. */
+int vrdd_reconstruct_fractal_device(vrdd_handle h, float* d_out);
+
+/* ---- P2: ray casting ------------------------------------------------------------------ */
+
+/* 1-D RGBA transfer function, float[n][4], linear, normalised, clamp
+ * (baked into initCuda in the reference, volumeRender_kernel.cu:2322-2344).
+ * tf == NULL restores the reference's nine-entry rainbow. */
+int vrdd_set_transfer_function(vrdd_handle h, const float* tf, int n);
+/* Inverse view matrix, row-major 3x4 (copyInvViewMatrix, volumeRender_kernel.cu:2403). */
+int vrdd_set_view(vrdd_handle h, const float* m12);
+void vrdd_default_render_params(vrdd_render_params* p);
+
+/* Renders into device memory d_output = uint32[image_h][image_w], packed
+ * A<<24|B<<16|G<<8|R, row 0 at the bottom (render_kernel, volumeRender_kernel.cu:2387;
+ * d_render :272-717).  Like the reference only pixels whose ray hits the volume are
+ * written; with clear_misses != 0 missed pixels of this call's partition are written as 0,
+ * which folds the caller's cudaMemset (volumeRender.cpp:208) into the kernel.
+ * part == NULL renders the whole image.  Asynchronous. */
+int vrdd_render(vrdd_handle h, uint32_t* d_output, int image_w, int image_h,
+                const vrdd_render_params* params, const vrdd_tile_partition* part,
+                int clear_misses);
+/* Same, then copies the image to host memory and synchronises: the end-to-end call
+ * (render() + the read-back of runSingleTest, volumeRender.cpp:194-217, 1073-1074). */
+int vrdd_render_host(vrdd_handle h, uint32_t* h_output, int image_w, int image_h,
+                     const vrdd_render_params* params);
+/* Enables counting of transfer-function lookups (the S of Gsamples/s) in vrdd_render and
+ * reads / resets the counter.  Reading synchronises. */
+int vrdd_count_samples(vrdd_handle h, int enable);
+int vrdd_get_sample_count(vrdd_handle h, int64_t* out, int reset);
+
+/* Host helper: the inverse view matrix the reference builds with OpenGL
+ * (volumeRender.cpp:224-246): M = Rx(-rot_x) * Ry(-rot_y) * T(-trans), top three rows,
+ * row-major.  Angles in degrees.  (0, 0, (0,0,-4)) is the self-test view (:1024-1043). */
+void vrdd_view_matrix(float rot_x_deg, float rot_y_deg, float tx, float ty, float tz, float* m12);
+
+/* ---- synthetic inputs, generated on the device (include/vrdd_synth.h) ------------------ */
+
+/* Fills d_hist = float[nz*height*width][bins] with the seeded synthetic histograms of
+ * z-slices [z0, z0+nz) of the handle's volume; bit-identical to the host generator. */
+int vrdd_synth_histograms_device(vrdd_handle h, uint32_t seed, int z0, int nz, float* d_hist);
+/* Fractal counterpart.  d_errors must hold max_ne*nvox entries; *total_ne (host) receives
+ * the number actually written.  Synchronises. */
+int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, int max_ne, int z0,
+                              int nz, int32_t* d_codebook, float* d_errors,
+                              uint64_t* d_chunk_offsets, float* d_templates, uint64_t* total_ne);
+
+/* ---- diagnostics ------------------------------------------------------------------------ */
+
+/* Selects a kernel variant by name for A/B measurement ("decode_hist" -> "tma" | "ldg";
+ * "raycast_tf" -> "texture" | "smem").  Unknown names return VRDD_ERR_INVALID. */
+int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);
+/* Samples the texture unit: out[i] = tex3D(plane `comp` of `source`, u[i], v[i], w[i]) with
+ * the ray caster's texture object.  For the filter-model conformance test.  Device ptrs. */
+int vrdd_debug_sample_texture(vrdd_handle h, int source, int comp, const float* d_uvw, int n,
+                              float* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRDD_H_ */

@@ -1,0 +1,433 @@
+/*
+ * vrdd_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain C++/OpenMP restatement of the two hot paths of
+ * ykou/Volume-Rendering-Based-on-Distribution-Data:
+ *   P1  distribution decode   (volumeRender_kernel.cu:195-222, 722-872)
+ *   P2  volume ray casting    (volumeRender_kernel.cu:136-193, 272-717)
+ * plus the texture-unit semantics those kernels lean on (modes set at
+ * volumeRender_kernel.cu:1865-1876, 2161-2171, 2337-2339) and the view matrix the host
+ * builds with OpenGL (volumeRender.cpp:224-246, 1024-1043).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+ * may load this library, and only as the checker or the timed CPU baseline.  The product
+ * (libvrdd.so) never links, loads or calls it.
+ *
+ * PARITY UNPINNED.  The reference cannot be compiled with CUDA 12.9 (texture references
+ * were removed; helper_math.h / helper_cuda.h / GL headers are not vendored) and ships no
+ * input data, no reference image and no unit tests.  Nothing from the
+ * reference pins this restatement; it is checked against hand-computed known answers and
+ * its own invariants in tests/test_oracle.py, and the texture-filter model is checked
+ * against the B200 texture unit in tests/test_texture_model.py (gpu).
+ *
+ * Arithmetic that lives outside /root/reference and is restated from its public definition:
+ *   helper_math.h (CUDA Samples common/inc, CUDA 5.0 era, no pin file):
+ *       dot = a.x*b.x + a.y*b.y + a.z*b.z (+ a.w*b.w), left to right;
+ *       normalize(v) = v * rsqrtf(dot(v,v))  -> restated as v * (1/sqrtf(dot)), IEEE;
+ *       float3/float4 operators are componentwise.
+ *   Texture filtering (CUDA C Programming Guide, "Texture Fetching"):
+ *       point:  T[floor(x)];
+ *       linear: xB = x - 0.5, i = floor(xB), a = frac(xB) held in 9-bit fixed point with
+ *       8 fractional bits; normalised coordinates are multiplied by the extent first;
+ *       clamp addressing clamps i and i+1 into [0, N-1].
+ *
+ * Build with -ffp-contract=off: every float operation below rounds once, in source
+ * order, so the oracle is a fixed point of itself on any host.
+ */
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/vrdd_synth.h"
+
+namespace {
+
+struct f3 { float x, y, z; };
+struct f4 { float x, y, z, w; };
+
+/* ---- texture-unit emulation ---------------------------------------------------- */
+
+enum WeightQuant { WQ_EXACT = 0, WQ_ROUND8 = 1, WQ_TRUNC8 = 2 };
+
+/* Split an unnormalised linear-filter coordinate into (i, alpha).  CUDA Programming
+ * Guide "Linear Filtering": xB = x - 0.5; i = floor(xB); alpha = frac(xB) in 1.8 fixed point. */
+inline void split_linear(float x_unnorm, int wq, int* i, float* a) {
+    float xb = x_unnorm - 0.5f;
+    if (wq == WQ_EXACT) {
+        float fl = std::floor(xb);
+        *i = (int)fl;
+        *a = xb - fl;
+        return;
+    }
+    /* fixed-point coordinate with 8 fractional bits */
+    float scaled = xb * 256.0f;
+    float q = (wq == WQ_ROUND8) ? std::floor(scaled + 0.5f) : std::floor(scaled);
+    long long qi = (long long)q;
+    long long ii = qi >> 8;                     /* arithmetic shift == floor division */
+    *i = (int)ii;
+    *a = (float)(qi - (ii << 8)) * (1.0f / 256.0f);
+}
+
+inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* tex3D on a float4 volume, linear, normalised, clamp (originalQueryTex/fractalQueryTex,
+ * volumeRender_kernel.cu:1865-1876), returning one component. */
+struct Volume4 {
+    const float* data;   /* float4[V], x fastest (volumeRender_kernel.cu:740, 771-773) */
+    int W, H, D;
+};
+
+inline float tex3d_linear_comp(const Volume4& v, int comp, float u, float vv, float w, int wq) {
+    int i, j, k; float a, b, c;
+    split_linear(u * (float)v.W, wq, &i, &a);
+    split_linear(vv * (float)v.H, wq, &j, &b);
+    split_linear(w * (float)v.D, wq, &k, &c);
+    int i0 = clampi(i, 0, v.W - 1), i1 = clampi(i + 1, 0, v.W - 1);
+    int j0 = clampi(j, 0, v.H - 1), j1 = clampi(j + 1, 0, v.H - 1);
+    int k0 = clampi(k, 0, v.D - 1), k1 = clampi(k + 1, 0, v.D - 1);
+    auto T = [&](int x, int y, int z) -> float {
+        return v.data[4 * ((size_t)x + (size_t)v.W * ((size_t)y + (size_t)v.H * (size_t)z)) + comp];
+    };
+    /* (1-a)(1-b)(1-c) T000 + ... evaluated as nested lerps, x then y then z */
+    float oa = 1.0f - a, ob = 1.0f - b, oc = 1.0f - c;
+    float x00 = oa * T(i0, j0, k0) + a * T(i1, j0, k0);
+    float x10 = oa * T(i0, j1, k0) + a * T(i1, j1, k0);
+    float x01 = oa * T(i0, j0, k1) + a * T(i1, j0, k1);
+    float x11 = oa * T(i0, j1, k1) + a * T(i1, j1, k1);
+    float y0 = ob * x00 + b * x10;
+    float y1 = ob * x01 + b * x11;
+    return oc * y0 + c * y1;
+}
+
+/* tex1D on the float4 transfer function, linear, normalised, clamp
+ * (transferTex, volumeRender_kernel.cu:2337-2339) */
+inline f4 tex1d_linear4(const float* tf, int n, float u, int wq) {
+    int i; float a;
+    split_linear(u * (float)n, wq, &i, &a);
+    int i0 = clampi(i, 0, n - 1), i1 = clampi(i + 1, 0, n - 1);
+    float oa = 1.0f - a;
+    f4 r;
+    r.x = oa * tf[4 * i0 + 0] + a * tf[4 * i1 + 0];
+    r.y = oa * tf[4 * i0 + 1] + a * tf[4 * i1 + 1];
+    r.z = oa * tf[4 * i0 + 2] + a * tf[4 * i1 + 2];
+    r.w = oa * tf[4 * i0 + 3] + a * tf[4 * i1 + 3];
+    return r;
+}
+
+/* ---- P1: decode ------------------------------------------------------------------ */
+
+/* Statistics of a raw histogram, volumeRender_kernel.cu:736-769.
+ * Types follow the reference expression by expression:
+ *   mean     += p * (binWidth*i + binWidth/2.0)        -> double term, float accumulator   (:746)
+ *   variance += p * ((i/B)*Max - mean) * (...)         -> all float, bin LEFT edge         (:753-754)
+ *   mean /= 0.0217; variance /= 0.000021               -> double divide                    (:758-759)
+ *   entropy  += p * (p<=0 ? 0 : log(p)/log(2.0))       -> logf, double divide              (:765-766)
+ *   entropy   = -entropy / (logf(B)/logf(2))                                               (:768-769) */
+inline void stats_original(const float* p, int B, float* out3) {
+    float MaxHistogram = 0.0217;
+    float MinHistogram = 0.0;
+    float binWidth = (MaxHistogram - MinHistogram) / (float)B;
+    float mean = 0;
+    for (int i = 0; i < B; ++i)
+        mean = (float)((double)mean + (double)p[i] * ((double)(binWidth * (float)i) + (double)binWidth / 2.0));
+    float variance = 0;
+    for (int i = 0; i < B; ++i) {
+        float d = ((float)i / (float)B) * MaxHistogram - mean;
+        variance = variance + (p[i] * d) * d;
+    }
+    mean = (float)((double)mean / 0.0217);
+    variance = (float)((double)variance / 0.000021);
+    float entropy = 0;
+    for (int i = 0; i < B; ++i) {
+        double term = (p[i] <= 0) ? 0.0 : ((double)logf(p[i]) / std::log(2.0));
+        entropy = (float)((double)entropy + (double)p[i] * term);
+    }
+    entropy = -entropy;
+    entropy = entropy / (logf((float)B) / logf(2.0f));
+    out3[0] = mean; out3[1] = variance; out3[2] = entropy;
+}
+
+/* Optional reversal then circular right shift, volumeRender_kernel.cu:195-222.
+ * Single wrap only: valid for 0 <= shift <= B (the reference indexes out of bounds
+ * otherwise); callers validate. */
+inline void fractal_transform(const float* tmpl, int B, int flip, int shift, float* cur) {
+    for (int i = 0; i < B; ++i) {
+        int m = i + shift;
+        if (m >= B) m -= B;
+        cur[m] = (flip == 0) ? tmpl[i] : tmpl[B - 1 - i];
+    }
+}
+
+/* Statistics of a reconstructed histogram, volumeRender_kernel.cu:841-867.  Here the
+ * variance uses the bin CENTRE in double (:851-853), unlike stats_original. */
+inline void stats_fractal(const float* cur, int B, float* out3) {
+    float MaxHistogram1 = 0.0217;
+    float MinHistogram1 = 0.0;
+    float mean1 = 0;
+    float binWidth1 = (MaxHistogram1 - MinHistogram1) / (float)B;
+    for (int i = 0; i < B; ++i)
+        mean1 = (float)((double)mean1 + (double)cur[i] * ((double)(binWidth1 * (float)i) + (double)binWidth1 / 2.0));
+    float variance1 = 0;
+    for (int i = 0; i < B; ++i) {
+        double d = ((double)(binWidth1 * (float)i) + (double)binWidth1 / 2.0) - (double)mean1;
+        variance1 = (float)((double)variance1 + ((double)cur[i] * d) * d);
+    }
+    mean1 = (float)((double)mean1 / 0.0217);
+    variance1 = (float)((double)variance1 / 0.000021);
+    float entropy1 = 0;
+    for (int i = 0; i < B; ++i) {
+        double term = (cur[i] <= 0) ? 0.0 : ((double)logf(cur[i]) / std::log(2.0));
+        entropy1 = (float)((double)entropy1 + (double)cur[i] * term);
+    }
+    entropy1 = -entropy1;
+    entropy1 = entropy1 / (logf((float)B) / logf(2.0f));
+    out3[0] = mean1; out3[1] = variance1; out3[2] = entropy1;
+}
+
+/* ---- P2: ray casting -------------------------------------------------------------- */
+
+inline float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+/* slab test, volumeRender_kernel.cu:136-156 */
+inline int intersect_box(f3 o, f3 d, f3 bmin, f3 bmax, float* tnear, float* tfar) {
+    f3 invR = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    f3 tbot = {invR.x * (bmin.x - o.x), invR.y * (bmin.y - o.y), invR.z * (bmin.z - o.z)};
+    f3 ttop = {invR.x * (bmax.x - o.x), invR.y * (bmax.y - o.y), invR.z * (bmax.z - o.z)};
+    f3 tmin = {fminf(ttop.x, tbot.x), fminf(ttop.y, tbot.y), fminf(ttop.z, tbot.z)};
+    f3 tmax = {fmaxf(ttop.x, tbot.x), fmaxf(ttop.y, tbot.y), fmaxf(ttop.z, tbot.z)};
+    float largest_tmin = fmaxf(fmaxf(tmin.x, tmin.y), fmaxf(tmin.x, tmin.z));
+    float smallest_tmax = fminf(fminf(tmax.x, tmax.y), fminf(tmax.x, tmax.z));
+    *tnear = largest_tmin;
+    *tfar = smallest_tmax;
+    return smallest_tmax > largest_tmin;
+}
+
+inline float saturate(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }  /* NaN -> 0 like __saturatef */
+
+/* volumeRender_kernel.cu:186-193: saturate, x255, truncate, pack A<<24|B<<16|G<<8|R */
+inline uint32_t pack_rgba(f4 c) {
+    float r = saturate(c.x), g = saturate(c.y), b = saturate(c.z), a = saturate(c.w);
+    return ((uint32_t)(a * 255) << 24) | ((uint32_t)(b * 255) << 16) | ((uint32_t)(g * 255) << 8) |
+           (uint32_t)(r * 255);
+}
+
+}  // namespace
+
+extern "C" {
+
+struct vrdd_oracle_render_params {
+    int image_w, image_h;
+    float density, brightness, transfer_offset, transfer_scale;
+    int query_method;        /* 1,2,3: component 0,1,2 of vol_original; 4,5,6: of vol_fractal */
+    float tstep;             /* reference: 0.01f      (volumeRender_kernel.cu:277) */
+    int max_steps;           /* reference: 500        (:276) */
+    float opacity_threshold; /* reference: 0.95f      (:278) */
+    int weight_quant;        /* 0 exact fp32 weights, 1 round to 8 bits, 2 truncate to 8 bits */
+    int y0, y1;              /* rows [y0, y1) to render (whole image: 0, image_h) */
+};
+
+int vrdd_oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void vrdd_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* a1 — raw-histogram half of d_basicDataProcessing (volumeRender_kernel.cu:722-773).
+ * hist: float[V][B]; out: float4[V] = (mean, variance, entropy, 0). */
+void vrdd_oracle_decode_hist(const float* hist, int64_t V, int B, float* out4) {
+#pragma omp parallel for schedule(static)
+    for (int64_t v = 0; v < V; ++v) {
+        float s[3];
+        stats_original(hist + v * B, B, s);
+        out4[4 * v + 0] = s[0]; out4[4 * v + 1] = s[1]; out4[4 * v + 2] = s[2]; out4[4 * v + 3] = 0.0f;
+    }
+}
+
+/* a2 — fractal half of d_basicDataProcessing (volumeRender_kernel.cu:775-871).
+ * codebook: int4[V] = (templateId, shift, flip, NE)           (:777-786)
+ * errors:   float2[V][B] dense, first NE entries valid        (:806-825, volumeRender.cpp:582)
+ * templates: float[T][B]; the reference fetches layer 1 of a 1-layer array, which the
+ *            hardware clamps to layer 0 (:792-793)
+ * recon (optional): float[V][B], the histogram after errors+clamp and BEFORE
+ *            normalisation — every value is a permuted template entry plus exactly the
+ *            additions the reference performs in order, so it is bit-comparable.
+ * Returns the number of voxels whose code violates the reference's run-time guards. */
+int64_t vrdd_oracle_decode_fractal(const int32_t* codebook, const float* errors, const float* templates,
+                                   int T, int64_t V, int B, float* out4, float* recon) {
+    int64_t bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (int64_t v = 0; v < V; ++v) {
+        float cur[VRDD_SYNTH_MAX_BINS];
+        int id = codebook[4 * v + 0], shift = codebook[4 * v + 1], flip = codebook[4 * v + 2],
+            ne = codebook[4 * v + 3];
+        if (id < 0 || id >= T || shift < 0 || shift > B || ne < 0 || ne > B) {
+            bad += 1;
+            out4[4 * v + 0] = out4[4 * v + 1] = out4[4 * v + 2] = out4[4 * v + 3] = 0.0f;
+            if (recon) std::memset(recon + v * B, 0, sizeof(float) * B);
+            continue;
+        }
+        fractal_transform(templates + (size_t)id * B, B, flip, shift, cur);
+        for (int k = 0; k < ne; ++k) {                                    /* :806-825 */
+            int bin = (int)errors[2 * (v * B + k) + 0];
+            float val = errors[2 * (v * B + k) + 1];
+            if (bin < 0 || bin >= B) { bad += 1; continue; }
+            cur[bin] = cur[bin] + val;
+            if (cur[bin] < 0) cur[bin] = 0;
+        }
+        if (recon) std::memcpy(recon + v * B, cur, sizeof(float) * B);
+        float tot = 0;                                                    /* :828-839 */
+        for (int i = 0; i < B; ++i) tot = tot + cur[i];
+        if (tot > 0)
+            for (int i = 0; i < B; ++i) cur[i] = cur[i] / tot;
+        float s[3];
+        stats_fractal(cur, B, s);
+        out4[4 * v + 0] = s[0]; out4[4 * v + 1] = s[1]; out4[4 * v + 2] = s[2]; out4[4 * v + 3] = 0.0f;
+    }
+    return bad;
+}
+
+/* The hard-coded nine-entry rainbow, volumeRender_kernel.cu:2323-2326 */
+void vrdd_oracle_default_transfer_function(float* tf4 /* [9*4] */) {
+    static const float k[9][4] = {{0, 0, 0, 0}, {1, 0, 0, 1}, {1, 0.5f, 0, 1}, {1, 1, 0, 1}, {0, 1, 0, 1},
+                                  {0, 1, 1, 1}, {0, 0, 1, 1}, {1, 0, 1, 1}, {0, 0, 0, 0}};
+    std::memcpy(tf4, k, sizeof(k));
+}
+
+/* Inverse view matrix without OpenGL (volumeRender.cpp:224-246).
+ * GL post-multiplies: M = Rx(-rot.x) * Ry(-rot.y) * T(-trans); the host keeps the top
+ * three rows of M row-major with the translation in the 4th column.  Angles in degrees.
+ * rot = 0, trans = (0,0,-4) gives the self-test matrix of volumeRender.cpp:1024-1043. */
+void vrdd_oracle_view_matrix(float rot_x_deg, float rot_y_deg, float tx, float ty, float tz, float* m12) {
+    const double d2r = 3.14159265358979323846 / 180.0;
+    double ax = -(double)rot_x_deg * d2r, ay = -(double)rot_y_deg * d2r;
+    float cx = (float)std::cos(ax), sx = (float)std::sin(ax), cy = (float)std::cos(ay), sy = (float)std::sin(ay);
+    /* Rx = [1 0 0; 0 cx -sx; 0 sx cx],  Ry = [cy 0 sy; 0 1 0; -sy 0 cy] */
+    float R[3][3] = {{cy, 0.0f, sy}, {sx * sy, cx, -(sx * cy)}, {-(cx * sy), sx, cx * cy}};
+    float t[3] = {-tx, -ty, -tz};
+    for (int r = 0; r < 3; ++r) {
+        m12[4 * r + 0] = R[r][0]; m12[4 * r + 1] = R[r][1]; m12[4 * r + 2] = R[r][2];
+        m12[4 * r + 3] = R[r][0] * t[0] + R[r][1] * t[1] + R[r][2] * t[2];
+    }
+}
+
+/* d_render for queryMethod 1..6 (volumeRender_kernel.cu:272-312, 381-387, 601-651, 683-716).
+ * The unconditional 8x33-fetch prologue (:354-367) and the per-step mean loop (:605-612)
+ * have no effect on the output for these modes and are not restated.
+ * out: uint32[image_h][image_w]; only hit pixels are written (:302-303) — the caller
+ * pre-clears (volumeRender.cpp:208, 1022).  Returns the number of loop iterations that
+ * performed a transfer-function lookup (the S of "Gsamples/s"). */
+int64_t vrdd_oracle_render(const float* vol_original4, const float* vol_fractal4, int W, int H, int D,
+                           const float* tf4, int tf_n, const float* m12, uint32_t* out,
+                           const vrdd_oracle_render_params* P) {
+    const f3 boxMin = {-1.0f, -1.0f, -1.0f}, boxMax = {1.0f, 1.0f, 1.0f};
+    const int qm = P->query_method;
+    const int comp = (qm - 1) % 3;
+    Volume4 vol = {(qm >= 4) ? vol_fractal4 : vol_original4, W, H, D};
+    const int imageW = P->image_w, imageH = P->image_h;
+    int64_t samples = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : samples)
+    for (int y = P->y0; y < P->y1; ++y) {
+        for (int x = 0; x < imageW; ++x) {
+            float u = ((float)x / (float)imageW) * 2.0f - 1.0f;                    /* :288 */
+            float v = ((float)y / (float)imageH) * 2.0f - 1.0f;                    /* :289 */
+            /* mul(M, (0,0,0,1)) == the translation column exactly (:293-294) */
+            f3 o = {m12[3], m12[7], m12[11]};
+            f3 dv = {u, v, -2.0f};                                                 /* :295 */
+            float inv_len = 1.0f / sqrtf(dot3(dv, dv));
+            dv.x = dv.x * inv_len; dv.y = dv.y * inv_len; dv.z = dv.z * inv_len;
+            f3 r0 = {m12[0], m12[1], m12[2]}, r1 = {m12[4], m12[5], m12[6]}, r2 = {m12[8], m12[9], m12[10]};
+            f3 d = {dot3(dv, r0), dot3(dv, r1), dot3(dv, r2)};                     /* :296, 168-174 */
+            float tnear, tfar;
+            if (!intersect_box(o, d, boxMin, boxMax, &tnear, &tfar)) continue;    /* :300-303 */
+            if (tnear < 0.0f) tnear = 0.0f;                                        /* :305-306 */
+            f4 sum = {0, 0, 0, 0};
+            float t = tnear;
+            f3 pos = {o.x + d.x * tnear, o.y + d.y * tnear, o.z + d.z * tnear};    /* :311 */
+            f3 step = {d.x * P->tstep, d.y * P->tstep, d.z * P->tstep};            /* :312 */
+            for (int i = 0; i < P->max_steps; ++i) {                              /* :381 */
+                float sample = tex3d_linear_comp(vol, comp, pos.x * 0.5f + 0.5f, pos.y * 0.5f + 0.5f,
+                                                 pos.z * 0.5f + 0.5f, P->weight_quant);
+                samples += 1;
+                f4 col = tex1d_linear4(tf4, tf_n, (sample - P->transfer_offset) * P->transfer_scale,
+                                       P->weight_quant);                           /* :683-684 */
+                col.w = col.w * P->density;                                        /* :685 */
+                col.x = col.x * col.w; col.y = col.y * col.w; col.z = col.z * col.w; /* :691-693 */
+                float k = 1.0f - sum.w;                                            /* :695 */
+                sum.x = sum.x + col.x * k; sum.y = sum.y + col.y * k;
+                sum.z = sum.z + col.z * k; sum.w = sum.w + col.w * k;
+                if (sum.w > P->opacity_threshold) break;                           /* :698 */
+                t = t + P->tstep;                                                  /* :701 */
+                if (t > tfar) break;                                               /* :703 */
+                pos.x = pos.x + step.x; pos.y = pos.y + step.y; pos.z = pos.z + step.z; /* :706 */
+            }
+            sum.x = sum.x * P->brightness; sum.y = sum.y * P->brightness;          /* :713 */
+            sum.z = sum.z * P->brightness; sum.w = sum.w * P->brightness;
+            out[(size_t)y * imageW + x] = pack_rgba(sum);                          /* :716 */
+        }
+    }
+    return samples;
+}
+
+/* Direct access to the filter model, for the texture-unit conformance test. */
+float vrdd_oracle_tex3d(const float* vol4, int W, int H, int D, int comp, float u, float v, float w, int wq) {
+    Volume4 vol = {vol4, W, H, D};
+    return tex3d_linear_comp(vol, comp, u, v, w, wq);
+}
+void vrdd_oracle_tex1d4(const float* tf4, int n, float u, int wq, float* out4) {
+    f4 r = tex1d_linear4(tf4, n, u, wq);
+    out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+
+/* ---- synthetic inputs (include/vrdd_synth.h), host side --------------------------- */
+
+/* hist[(z-z0)*H*W + y*W + x][B] for z in [z0, z0+nz) of a W x H x D volume */
+void vrdd_oracle_synth_histograms(uint32_t seed, int W, int H, int D, int B, int z0, int nz, float* hist) {
+#pragma omp parallel for schedule(static) collapse(2)
+    for (int z = z0; z < z0 + nz; ++z)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                size_t v = (size_t)x + (size_t)W * ((size_t)y + (size_t)H * (size_t)(z - z0));
+                vrdd_synth_histogram(seed, x, y, z, W, H, D, B, hist + v * B);
+            }
+}
+
+void vrdd_oracle_synth_templates(uint32_t seed, int T, int B, float* templates) {
+    for (int k = 0; k < T; ++k) vrdd_synth_template(seed, k, T, B, templates + (size_t)k * B);
+}
+
+/* codebook int4[V]; errors float2[V][B] dense like the reference's errorsbook, entries
+ * beyond NE zero-filled (the reference leaves them uninitialised, volumeRender.cpp:582) */
+void vrdd_oracle_synth_fractal(uint32_t seed, int W, int H, int D, int B, int T, int max_ne, int z0, int nz,
+                               int32_t* codebook, float* errors) {
+#pragma omp parallel for schedule(static) collapse(2)
+    for (int z = z0; z < z0 + nz; ++z)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                size_t v = (size_t)x + (size_t)W * ((size_t)y + (size_t)H * (size_t)(z - z0));
+                int code[4], eb[VRDD_SYNTH_MAX_BINS];
+                float ev[VRDD_SYNTH_MAX_BINS];
+                vrdd_synth_fractal_code(seed, x, y, z, W, H, D, B, T, max_ne, code, eb, ev);
+                for (int k = 0; k < 4; ++k) codebook[4 * v + k] = code[k];
+                for (int k = 0; k < B; ++k) {
+                    errors[2 * (v * B + k) + 0] = (k < code[3]) ? (float)eb[k] : 0.0f;
+                    errors[2 * (v * B + k) + 1] = (k < code[3]) ? ev[k] : 0.0f;
+                }
+            }
+}
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+"""ctypes binding of the CPU oracle (oracle/vrdd_oracle.cpp).
+
+TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs
+may import this module; the product package never does.  PARITY UNPINNED: the reference
+ships no fixtures and does not compile with CUDA 12.9 (see the header of vrdd_oracle.cpp).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class RenderParams(C.Structure):
+    """struct vrdd_oracle_render_params; defaults are the reference's constants
+    (volumeRender.cpp:121, 130-133; volumeRender_kernel.cu:276-278)."""
+    _fields_ = [("image_w", C.c_int), ("image_h", C.c_int),
+                ("density", C.c_float), ("brightness", C.c_float),
+                ("transfer_offset", C.c_float), ("transfer_scale", C.c_float),
+                ("query_method", C.c_int), ("tstep", C.c_float), ("max_steps", C.c_int),
+                ("opacity_threshold", C.c_float), ("weight_quant", C.c_int),
+                ("y0", C.c_int), ("y1", C.c_int)]
+
+
+def build(force=False):
+    """Compile both flavours of the oracle with oracle/Makefile (g++ only, no CUDA)."""
+    need = force or not all(os.path.exists(os.path.join(_HERE, n))
+                            for n in ("libvrdd_oracle.so", "libvrdd_oracle_fast.so"))
+    if need:
+        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []),
+                              stdout=subprocess.DEVNULL)
+
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+
+
+class Oracle:
+    def __init__(self, fast=False):
+        build()
+        self.lib = C.CDLL(os.path.join(_HERE, "libvrdd_oracle_fast.so" if fast else "libvrdd_oracle.so"))
+        L = self.lib
+        L.vrdd_oracle_num_threads.restype = C.c_int
+        L.vrdd_oracle_set_num_threads.argtypes = [C.c_int]
+        L.vrdd_oracle_decode_hist.argtypes = [_f32p, C.c_int64, C.c_int, _f32p]
+        L.vrdd_oracle_decode_fractal.argtypes = [_i32p, _f32p, _f32p, C.c_int, C.c_int64, C.c_int, _f32p,
+                                                 C.c_void_p]
+        L.vrdd_oracle_decode_fractal.restype = C.c_int64
+        L.vrdd_oracle_default_transfer_function.argtypes = [_f32p]
+        L.vrdd_oracle_view_matrix.argtypes = [C.c_float] * 5 + [_f32p]
+        L.vrdd_oracle_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int,
+                                         _f32p, _u32p, C.POINTER(RenderParams)]
+        L.vrdd_oracle_render.restype = C.c_int64
+        L.vrdd_oracle_tex3d.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                        C.c_float, C.c_int]
+        L.vrdd_oracle_tex3d.restype = C.c_float
+        L.vrdd_oracle_tex1d4.argtypes = [_f32p, C.c_int, C.c_float, C.c_int, _f32p]
+        L.vrdd_oracle_synth_histograms.argtypes = [C.c_uint32] + [C.c_int] * 6 + [_f32p]
+        L.vrdd_oracle_synth_templates.argtypes = [C.c_uint32, C.c_int, C.c_int, _f32p]
+        L.vrdd_oracle_synth_fractal.argtypes = [C.c_uint32] + [C.c_int] * 8 + [_i32p, _f32p]
+
+    # -- threads ------------------------------------------------------------------
+    def num_threads(self):
+        return int(self.lib.vrdd_oracle_num_threads())
+
+    def set_num_threads(self, n):
+        self.lib.vrdd_oracle_set_num_threads(int(n))
+
+    # -- synthetic inputs -----------------------------------------------------------
+    def synth_histograms(self, seed, dims, bins=32, z0=0, nz=None):
+        W, H, D = dims
+        nz = D - z0 if nz is None else nz
+        out = np.empty((nz * H * W, bins), np.float32)
+        self.lib.vrdd_oracle_synth_histograms(seed, W, H, D, bins, z0, nz, out)
+        return out
+
+    def synth_templates(self, seed, T=622, bins=32):
+        out = np.empty((T, bins), np.float32)
+        self.lib.vrdd_oracle_synth_templates(seed, T, bins, out)
+        return out
+
+    def synth_fractal(self, seed, dims, bins=32, T=622, max_ne=8, z0=0, nz=None):
+        W, H, D = dims
+        nz = D - z0 if nz is None else nz
+        V = nz * H * W
+        codebook = np.empty((V, 4), np.int32)
+        errors = np.empty((V, bins, 2), np.float32)
+        self.lib.vrdd_oracle_synth_fractal(seed, W, H, D, bins, T, max_ne, z0, nz, codebook, errors)
+        return codebook, errors
+
+    # -- P1 -------------------------------------------------------------------------
+    def decode_hist(self, hist):
+        hist = np.ascontiguousarray(hist, np.float32)
+        V, B = hist.shape
+        out = np.empty((V, 4), np.float32)
+        self.lib.vrdd_oracle_decode_hist(hist, V, B, out)
+        return out
+
+    def decode_fractal(self, codebook, errors, templates, want_recon=False):
+        codebook = np.ascontiguousarray(codebook, np.int32)
+        errors = np.ascontiguousarray(errors, np.float32)
+        templates = np.ascontiguousarray(templates, np.float32)
+        V = codebook.shape[0]
+        T, B = templates.shape
+        out = np.empty((V, 4), np.float32)
+        recon = np.empty((V, B), np.float32) if want_recon else None
+        bad = self.lib.vrdd_oracle_decode_fractal(codebook, errors, templates, T, V, B, out,
+                                                  recon.ctypes.data if want_recon else None)
+        return (out, recon, int(bad)) if want_recon else (out, int(bad))
+
+    # -- P2 -------------------------------------------------------------------------
+    def default_transfer_function(self):
+        tf = np.empty((9, 4), np.float32)
+        self.lib.vrdd_oracle_default_transfer_function(tf)
+        return tf
+
+    def view_matrix(self, rot_x=0.0, rot_y=0.0, trans=(0.0, 0.0, -4.0)):
+        m = np.empty(12, np.float32)
+        self.lib.vrdd_oracle_view_matrix(rot_x, rot_y, trans[0], trans[1], trans[2], m)
+        return m
+
+    def render(self, vol4, dims, view, image=(512, 512), query_method=1, tf=None, density=0.05,
+               brightness=1.0, transfer_offset=0.0, transfer_scale=1.0, tstep=0.01, max_steps=500,
+               opacity_threshold=0.95, weight_quant=1, vol_fractal4=None, rows=None):
+        """Returns (uint32 image[h][w] pre-cleared to 0, sample count)."""
+        W, H, D = dims
+        iw, ih = image
+        tf = self.default_transfer_function() if tf is None else np.ascontiguousarray(tf, np.float32)
+        vo = None if vol4 is None else np.ascontiguousarray(vol4, np.float32)
+        vf = None if vol_fractal4 is None else np.ascontiguousarray(vol_fractal4, np.float32)
+        out = np.zeros((ih, iw), np.uint32)
+        y0, y1 = (0, ih) if rows is None else rows
+        P = RenderParams(iw, ih, density, brightness, transfer_offset, transfer_scale, query_method, tstep,
+                         max_steps, opacity_threshold, weight_quant, y0, y1)
+        s = self.lib.vrdd_oracle_render(None if vo is None else vo.ctypes.data,
+                                        None if vf is None else vf.ctypes.data, W, H, D, tf, tf.shape[0],
+                                        np.ascontiguousarray(view, np.float32), out, C.byref(P))
+        return out, int(s)
+
+    def tex3d(self, vol4, dims, comp, u, v, w, weight_quant=1):
+        W, H, D = dims
+        return float(self.lib.vrdd_oracle_tex3d(np.ascontiguousarray(vol4, np.float32), W, H, D, comp, u, v, w,
+                                                weight_quant))
+
+    def tex1d4(self, tf, u, weight_quant=1):
+        tf = np.ascontiguousarray(tf, np.float32)
+        out = np.empty(4, np.float32)
+        self.lib.vrdd_oracle_tex1d4(tf, tf.shape[0], u, weight_quant, out)
+        return out

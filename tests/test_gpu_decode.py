@@ -1,0 +1,227 @@
+"""GPU parity tests of P1 (decode) through the C ABI, against the CPU oracle and the golden
+vectors.  Tolerances: the decode kernels compute in fp32 with MUFU.LG2 where the reference
+promotes single terms to double (see csrc/decode_hist.cu); decoded values are O(1) after the
+reference's normalisation, and the bound below is ~10 fp32 ulps of that scale:
+        |gpu - oracle| <= 2e-6 + 2e-5 * |oracle|
+The integer part of the fractal decode (template row, flip/shift permutation, error placement
+and order, clamp) is compared BIT-EXACTLY through the reconstructed histogram."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 2e-5, 2e-6
+
+
+def _decode_hist(r, V, dims, hist, variant):
+    r.set_volume(*dims)
+    r.set_variant("decode_hist", variant)
+    r.set_histograms_host(hist)
+    r.decode(V.SRC_ORIGINAL)
+    return r.get_decoded_host(V.SRC_ORIGINAL, np.empty((hist.shape[0], 4), np.float32))
+
+
+@pytest.mark.parametrize("variant", ["tma", "ldg"])
+def test_hist_decode_matches_golden(renderer, golden, variant):
+    import vrdd_b200 as V
+    dims = tuple(int(v) for v in golden["dims"])
+    got = _decode_hist(renderer, V, dims, golden["hist"], variant)
+    np.testing.assert_allclose(got, golden["decoded_original"], rtol=RTOL, atol=ATOL)
+    assert np.all(got[:, 3] == 0)
+    assert np.all(got[3] == 0)                       # the all-zero histogram (p <= 0 branch)
+
+
+@pytest.mark.parametrize("variant", ["tma", "ldg"])
+@pytest.mark.parametrize("dims", [(1, 1, 1), (5, 3, 2), (31, 17, 3), (64, 8, 1), (33, 16, 1), (50, 50, 10), (64, 64, 48)])
+def test_hist_decode_matches_oracle_ragged_sizes(renderer, oracle, variant, dims):
+    """Sizes around the 512-voxel tile / 32-voxel warp-tile boundaries, the reference's own
+    50x50x10, and a multi-tile volume."""
+    import vrdd_b200 as V
+    hist = oracle.synth_histograms(99, dims)
+    got = _decode_hist(renderer, V, dims, hist, variant)
+    np.testing.assert_allclose(got, oracle.decode_hist(hist), rtol=RTOL, atol=ATOL)
+
+
+def test_hist_decode_random_and_degenerate_rows(renderer, oracle):
+    import vrdd_b200 as V
+    rng = np.random.default_rng(3)
+    dims = (40, 13, 3)
+    n = dims[0] * dims[1] * dims[2]
+    hist = rng.random((n, 32)).astype(np.float32)
+    hist[hist < 0.5] = 0
+    hist[5] = 0
+    hist /= np.maximum(hist.sum(1, keepdims=True), 1e-30)
+    hist[7] = 0; hist[7, 0] = 1
+    hist[8] = 0; hist[8, 31] = 1
+    hist[9] = 1e-30                                  # denormal-scale frequencies
+    for variant in ("tma", "ldg"):
+        got = _decode_hist(renderer, V, dims, hist, variant)
+        np.testing.assert_allclose(got, oracle.decode_hist(hist), rtol=RTOL, atol=ATOL)
+
+
+def test_slab_decode_from_device_memory(renderer, oracle):
+    """Slab-wise streaming (vrdd_set_histograms_device) writes the same volume as one decode."""
+    import torch
+    import vrdd_b200 as V
+    dims = (24, 20, 9)
+    hist = oracle.synth_histograms(5, dims)
+    r = renderer
+    r.set_volume(*dims)
+    slice_vox = dims[0] * dims[1]
+    for z0, nz in ((0, 4), (4, 3), (7, 2)):
+        d = torch.from_numpy(hist[z0 * slice_vox:(z0 + nz) * slice_vox]).cuda()
+        r.set_histograms_device(d, z0, nz)
+        r.decode(V.SRC_ORIGINAL, z0, nz)
+        r.synchronize()
+    got = r.get_decoded_host(V.SRC_ORIGINAL, np.empty((hist.shape[0], 4), np.float32))
+    np.testing.assert_allclose(got, oracle.decode_hist(hist), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("sampler", ["texture", "bricked"])
+def test_decoded_layouts_agree(renderer, oracle, sampler):
+    """cudaArray planes, bricked planes and linear planes all hold the same decoded values."""
+    import vrdd_b200 as V
+    dims = (21, 10, 7)                               # not a multiple of the 4^3 brick
+    hist = oracle.synth_histograms(8, dims)
+    r = renderer
+    r.set_sampler(V.SAMPLER_TEXTURE if sampler == "texture" else V.SAMPLER_BRICKED)
+    r.keep_linear_planes(True)
+    r.set_volume(*dims)
+    r.set_histograms_host(hist)
+    r.decode(V.SRC_ORIGINAL)
+    n = hist.shape[0]
+    ref = oracle.decode_hist(hist)
+    planes = r.get_decoded_planes_device(V.SRC_ORIGINAL)
+    assert all(planes)
+    r.synchronize()
+    for c, p in enumerate(planes):
+        np.testing.assert_allclose(_from_device_ptr(p, n), ref[:, c], rtol=RTOL, atol=ATOL)
+    # drop the linear planes: get_decoded_host now reads the sampler layout itself
+    r2 = V.Renderer(0)
+    r2.set_sampler(V.SAMPLER_TEXTURE if sampler == "texture" else V.SAMPLER_BRICKED)
+    r2.set_volume(*dims)
+    r2.set_histograms_host(hist)
+    r2.decode(V.SRC_ORIGINAL)
+    got = r2.get_decoded_host(V.SRC_ORIGINAL, np.empty((n, 4), np.float32))
+    r2.close()
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
+
+
+def _from_device_ptr(ptr, n):
+    """n floats behind a raw device pointer, as numpy."""
+    import vrdd_b200 as V
+    return V.as_torch(ptr, (n,)).cpu().numpy()
+
+
+def test_fractal_decode_matches_golden_and_is_bit_exact_in_its_integer_part(renderer, golden):
+    import torch
+    import vrdd_b200 as V
+    dims = tuple(int(v) for v in golden["dims"])
+    n = dims[0] * dims[1] * dims[2]
+    r = renderer
+    r.set_volume(*dims)
+    r.set_fractal_host(golden["codebook"], golden["errors"], golden["templates"])
+    recon = torch.empty(n, 32, dtype=torch.float32, device="cuda")
+    r.reconstruct_fractal_device(recon)
+    r.synchronize()
+    assert np.array_equal(recon.cpu().numpy(), golden["recon"])          # BIT-exact
+    r.decode(V.SRC_FRACTAL)
+    got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
+    np.testing.assert_allclose(got, golden["decoded_fractal"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("dims,T,max_ne", [((1, 1, 1), 3, 8), ((30, 9, 2), 622, 8), ((50, 50, 10), 622, 8),
+                                            ((64, 32, 5), 100, 32), ((16, 16, 4), 1500, 0)])
+def test_fractal_decode_matches_oracle(renderer, oracle, dims, T, max_ne):
+    """Ragged sizes, the reference's 50x50x10 / 622 templates, NE up to 32 (error staging
+    overflow path), NE == 0, and a template table too large for shared memory."""
+    import torch
+    import vrdd_b200 as V
+    tmpl = oracle.synth_templates(4, T)
+    cb, err = oracle.synth_fractal(4, dims, T=T, max_ne=max_ne)
+    ref, ref_recon, bad = oracle.decode_fractal(cb, err, tmpl, want_recon=True)
+    assert bad == 0
+    n = cb.shape[0]
+    r = renderer
+    r.set_volume(*dims)
+    r.set_fractal_host(cb, err, tmpl)
+    recon = torch.empty(n, 32, dtype=torch.float32, device="cuda")
+    r.reconstruct_fractal_device(recon)
+    r.synchronize()
+    assert np.array_equal(recon.cpu().numpy(), ref_recon)
+    r.decode(V.SRC_FRACTAL)
+    got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_fractal_upload_applies_the_reference_guards(renderer, oracle):
+    """volumeRender_kernel.cu:781-816 / volumeRender.cpp:611-614: out-of-range codes are an error
+    here (VRDD_ERR_RANGE), not a printf."""
+    import vrdd_b200 as V
+    dims = (4, 4, 2)
+    tmpl = oracle.synth_templates(1, 10)
+    cb, err = oracle.synth_fractal(1, dims, T=10)
+    r = renderer
+    r.set_volume(*dims)
+    for field, bad in ((0, 10), (0, -1), (1, 33), (3, 33), (3, -2)):
+        c2 = cb.copy(); c2[5, field] = bad
+        with pytest.raises(V.VrddError) as e:
+            r.set_fractal_host(c2, err, tmpl)
+        assert e.value.code == V.ERR_RANGE
+    c2 = cb.copy(); c2[5, 3] = 1
+    e2 = err.copy(); e2[5, 0, 0] = 32.0
+    with pytest.raises(V.VrddError) as e:
+        r.set_fractal_host(c2, e2, tmpl)
+    assert e.value.code == V.ERR_RANGE
+    t2 = tmpl.copy(); t2[3, 3] = 1.5
+    with pytest.raises(V.VrddError):
+        r.set_fractal_host(cb, err, t2)
+
+
+def test_call_order_errors(renderer):
+    import vrdd_b200 as V
+    with pytest.raises(V.VrddError) as e:
+        renderer.decode(V.SRC_ORIGINAL)
+    assert e.value.code == V.ERR_INVALID
+    with pytest.raises(V.VrddError) as e:
+        renderer.set_volume(8, 8, 8, bins=64)
+    assert e.value.code == V.ERR_UNSUPPORTED
+    renderer.set_volume(8, 8, 8)
+    with pytest.raises(V.VrddError):
+        renderer.decode(V.SRC_FRACTAL)
+
+
+def test_device_synth_is_bit_identical_to_host_synth(renderer, oracle):
+    """include/vrdd_synth.h gives the same bits under nvcc (device) and g++ (host)."""
+    import torch
+    dims, seed, T = (37, 21, 9), 1234, 622
+    r = renderer
+    r.set_volume(*dims)
+    n_slab = dims[0] * dims[1] * 4
+    d = torch.empty(n_slab, 32, dtype=torch.float32, device="cuda")
+    r.synth_histograms_device(seed, 3, 4, d)
+    r.synchronize()
+    assert np.array_equal(d.cpu().numpy(), oracle.synth_histograms(seed, dims, z0=3, nz=4))
+    n = dims[0] * dims[1] * dims[2]
+    nch = (n + 255) // 256
+    cb = torch.empty(n, 4, dtype=torch.int32, device="cuda")
+    er = torch.empty(n * 8, 2, dtype=torch.float32, device="cuda")
+    off = torch.empty(nch + 1, dtype=torch.int64, device="cuda")
+    tm = torch.empty(T, 32, dtype=torch.float32, device="cuda")
+    tot = r.synth_fractal_device(seed, T, 8, 0, dims[2], cb, er, off, tm)
+    hcb, herr = oracle.synth_fractal(seed, dims, T=T, max_ne=8)
+    assert np.array_equal(cb.cpu().numpy(), hcb)
+    assert np.array_equal(tm.cpu().numpy(), oracle.synth_templates(seed, T))
+    assert tot == int(hcb[:, 3].sum())
+    compact = np.concatenate([herr[v, :hcb[v, 3]] for v in range(n)])
+    assert np.array_equal(er.cpu().numpy()[:tot], compact)
+    offs = off.cpu().numpy()
+    cum = np.concatenate([[0], np.cumsum(hcb[:, 3])])
+    assert np.array_equal(offs[:-1], cum[0:n:256]) and offs[-1] == tot
+    # and the compact device form decodes to the oracle's answer
+    import vrdd_b200 as V
+    r.set_fractal_device(cb, er, off, tm, T, 0, dims[2])
+    r.decode(V.SRC_FRACTAL)
+    got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
+    ref, _ = oracle.decode_fractal(hcb, herr, oracle.synth_templates(seed, T))
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)

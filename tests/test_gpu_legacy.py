@@ -1,0 +1,42 @@
+"""The reference's seven entry points (volumeRender.cpp:156-170), called the way
+volumeRender.cpp calls them (main :1200-1221, runSingleTest :1016-1075, cleanup :462)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_call_sequence(oracle):
+    import torch
+    import vrdd_b200 as V
+    L = V.legacy
+    dims = (50, 50, 10)                                           # volumeRender.cpp:86
+    hist = oracle.synth_histograms(42, dims)
+    tmpl = oracle.synth_templates(42, 622)                       # volumeRender.cpp:89
+    cb, err = oracle.synth_fractal(42, dims)
+    L.initCuda(hist, dims, cb, tmpl, err)                        # main :1200
+    L.dataProcessing()                                           # main :1220 (flexible chain: not built, no-op)
+    L.basicDataProcessing()                                      # main :1221
+    assert L.handle()
+    w = h = 512                                                  # volumeRender.cpp:121
+    view = V.view_matrix()                                       # runSingleTest :1024-1043
+    L.copyInvViewMatrix(view)
+    L.setTextureFilterMode(True)
+    d_out = torch.zeros(h, w, dtype=torch.int32, device="cuda")  # cudaMalloc + cudaMemset :1021-1022
+    ref_o = oracle.decode_hist(hist)
+    ref_f, _ = oracle.decode_fractal(cb, err, tmpl)
+    for qm in (1, 2, 3, 4, 5, 6):
+        d_out.zero_()
+        L.render_kernel(d_out, w, h, query_method=qm, volume_size=dims)    # :1059
+        torch.cuda.synchronize()
+        got = d_out.cpu().numpy().view(np.uint8).astype(np.int16)
+        ref, _ = oracle.render(ref_o, dims, np.array(view, np.float32), image=(w, h), query_method=qm,
+                               vol_fractal4=ref_f)
+        d = np.abs(got - ref.view(np.uint8).reshape(got.shape).astype(np.int16))
+        # the volumes were decoded on the GPU here, so a texel may differ from the oracle's by
+        # an fp32 rounding; the +-1 LSB bar still holds
+        assert d.max() <= 1, (qm, int(d.max()), int((d > 1).sum()))
+        assert (ref != 0).sum() == 116281                        # rays that hit at this view
+    L.freeCudaBuffers()                                          # cleanup :462
+    assert not L.handle()
+    L.freeCudaBuffers()                                          # idempotent, unlike the reference (:2360-2385)

@@ -1,0 +1,319 @@
+"""CPU tests of the oracle (oracle/vrdd_oracle.cpp).
+
+The reference ships no fixtures (parity unpinned), so the oracle is pinned by
+  * closed-form known answers worked out by hand from the reference's formulas,
+  * an independent numpy restatement of one ray of d_render,
+  * the ray statistics SURVEY.md §6 derives for the reference's self-test view,
+  * the frozen golden vectors (tests/golden/make_golden.py).
+"""
+import numpy as np
+import pytest
+
+BW = np.float32(np.float32(0.0217) / np.float32(32))
+
+
+# ---- P1a: raw histograms (volumeRender_kernel.cu:736-769) -----------------------------------
+
+def test_decode_hist_delta_bins(oracle):
+    """All mass in bin k: mean = (k + 1/2)/32 of full scale, entropy 0, and the variance is the
+    squared half bin width (mean uses the bin centre, variance the left edge: :746 vs :753)."""
+    hist = np.zeros((32, 32), np.float32)
+    hist[np.arange(32), np.arange(32)] = 1.0
+    out = oracle.decode_hist(hist)
+    k = np.arange(32, dtype=np.float64)
+    np.testing.assert_allclose(out[:, 0], float(BW) * (k + 0.5) / 0.0217, rtol=3e-7)
+    np.testing.assert_allclose(out[:, 1], (float(BW) / 2) ** 2 / 0.000021, rtol=2e-5)
+    assert np.all(out[:, 2] == 0.0) and np.all(out[:, 3] == 0.0)
+
+
+def test_decode_hist_uniform(oracle):
+    hist = np.full((1, 32), 1.0 / 32, np.float32)
+    out = oracle.decode_hist(hist)[0]
+    i = np.arange(32, dtype=np.float64)
+    mean_raw = np.sum((float(BW) * i + float(BW) / 2) / 32)
+    var = np.sum(((i / 32) * float(np.float32(0.0217)) - mean_raw) ** 2 / 32) / 0.000021
+    assert out[0] == pytest.approx(mean_raw / 0.0217, rel=1e-6)
+    assert out[1] == pytest.approx(var, rel=1e-5)
+    assert out[2] == pytest.approx(1.0, rel=1e-6)          # maximal entropy, normalised by log2(32)
+
+
+def test_decode_hist_zero_and_matches_float64(oracle):
+    rng = np.random.default_rng(0)
+    hist = rng.random((200, 32)).astype(np.float32)
+    hist[hist < 0.3] = 0.0                                 # exercises the `p <= 0` branch (:765-766)
+    hist /= hist.sum(1, keepdims=True)
+    hist[0] = 0.0
+    out = oracle.decode_hist(hist)
+    assert np.all(out[0] == 0.0)
+    p = hist.astype(np.float64)
+    i = np.arange(32)
+    mean_raw = (p * (float(BW) * i + float(BW) / 2)).sum(1)
+    var = (p * ((i / 32.0) * float(np.float32(0.0217)) - mean_raw[:, None]) ** 2).sum(1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ent = -np.where(p > 0, p * np.log2(np.where(p > 0, p, 1.0)), 0.0).sum(1) / 5.0
+    np.testing.assert_allclose(out[:, 0], mean_raw / 0.0217, rtol=2e-6)
+    np.testing.assert_allclose(out[:, 1], var / 0.000021, rtol=2e-5)
+    np.testing.assert_allclose(out[:, 2], ent, rtol=2e-6, atol=1e-7)
+
+
+# ---- P1b: fractal codes (volumeRender_kernel.cu:195-222, 775-871) ---------------------------
+
+def _fr(oracle, tmpl, code, errs=()):
+    cb = np.array([code], np.int32)
+    e = np.zeros((1, 32, 2), np.float32)
+    for k, (b, v) in enumerate(errs):
+        e[0, k] = (b, v)
+    out, recon, bad = oracle.decode_fractal(cb, e, tmpl, want_recon=True)
+    return out[0], recon[0], bad
+
+
+def test_fractal_shift_flip_permutation(oracle):
+    tmpl = np.arange(32, dtype=np.float32)[None, :] / np.float32(496.0)       # sums to 1
+    t = tmpl[0]
+    _, r, _ = _fr(oracle, tmpl, (0, 0, 0, 0));  assert np.array_equal(r, t)
+    _, r, _ = _fr(oracle, tmpl, (0, 5, 0, 0));  assert np.array_equal(r, np.roll(t, 5))
+    _, r, _ = _fr(oracle, tmpl, (0, 32, 0, 0)); assert np.array_equal(r, t)       # single wrap: B == identity
+    _, r, _ = _fr(oracle, tmpl, (0, 0, 1, 0));  assert np.array_equal(r, t[::-1])
+    _, r, _ = _fr(oracle, tmpl, (0, 3, 1, 0));  assert np.array_equal(r, np.roll(t[::-1], 3))  # flip, then shift
+
+
+def test_fractal_errors_clamp_and_order(oracle):
+    tmpl = np.full((1, 32), 1.0 / 32, np.float32)
+    # +0.1 then -0.5 (clamps to 0) then +0.2 on the same bin: order matters, result 0.2
+    out, r, bad = _fr(oracle, tmpl, (0, 0, 0, 3), [(4, 0.1), (4, -0.5), (4, 0.2)])
+    assert bad == 0
+    exp = tmpl[0].copy()
+    exp[4] = np.float32(0.2)
+    assert np.array_equal(r, exp)
+    p = exp.astype(np.float64) / exp.astype(np.float64).sum()
+    i = np.arange(32)
+    c = float(BW) * i + float(BW) / 2
+    m = (p * c).sum()
+    assert out[0] == pytest.approx(m / 0.0217, rel=2e-6)
+    assert out[1] == pytest.approx((p * (c - m) ** 2).sum() / 0.000021, rel=2e-5)   # bin CENTRE here (:851)
+    assert out[2] == pytest.approx(-(p * np.log2(p)).sum() / 5.0, rel=2e-6)
+
+
+def test_fractal_identity_code_matches_raw_path_except_variance(oracle):
+    """Same histogram through both halves: mean and entropy agree; variances differ by design
+    (left edge vs centre), by exactly bw*(mean_c - ...) -> check the closed form."""
+    h = oracle.synth_histograms(3, (4, 4, 2))
+    a = oracle.decode_hist(h)
+    cb = np.zeros((32, 4), np.int32); cb[:, 0] = np.arange(32)
+    b, _ = oracle.decode_fractal(cb, np.zeros((32, 32, 2), np.float32), h)
+    np.testing.assert_allclose(a[:, 0], b[:, 0], rtol=2e-6)
+    np.testing.assert_allclose(a[:, 2], b[:, 2], rtol=2e-6, atol=1e-7)
+    # var_left = var_centre + (bw/2)^2 for a normalised histogram
+    np.testing.assert_allclose(a[:, 1], b[:, 1] + (float(BW) / 2) ** 2 / 0.000021, rtol=5e-5)
+
+
+def test_fractal_guards(oracle):
+    tmpl = np.full((2, 32), 1.0 / 32, np.float32)
+    for code in ((2, 0, 0, 0), (-1, 0, 0, 0), (0, 33, 0, 0), (0, 0, 0, 33)):
+        _, _, bad = _fr(oracle, tmpl, code)
+        assert bad == 1
+
+
+# ---- texture model ---------------------------------------------------------------------------
+
+def test_texture_model_known_answers(oracle):
+    vol = np.zeros((2 * 2 * 2, 4), np.float32)
+    vol[:, 0] = [0, 1, 0, 1, 0, 1, 0, 1]                     # value == x index
+    dims = (2, 2, 2)
+    assert oracle.tex3d(vol, dims, 0, 0.25, 0.25, 0.25) == 0.0          # texel centre 0
+    assert oracle.tex3d(vol, dims, 0, 0.75, 0.5, 0.5) == 1.0            # texel centre 1
+    assert oracle.tex3d(vol, dims, 0, 0.5, 0.5, 0.5) == 0.5             # halfway
+    assert oracle.tex3d(vol, dims, 0, 0.0, 0.5, 0.5) == 0.0             # clamp
+    assert oracle.tex3d(vol, dims, 0, 1.5, 0.5, 0.5) == 1.0             # clamp
+    # weights live on a 1/256 grid: 0.25 + 0.3/256/2 (0.3 of a weight step) rounds to weight 0
+    u = 0.25 + 0.3 / 512
+    assert oracle.tex3d(vol, dims, 0, u, 0.5, 0.5, weight_quant=1) == 0.0
+    assert oracle.tex3d(vol, dims, 0, u, 0.5, 0.5, weight_quant=0) == pytest.approx(0.3 / 256, rel=1e-4)
+    u = 0.25 + 0.7 / 512
+    assert oracle.tex3d(vol, dims, 0, u, 0.5, 0.5, weight_quant=1) == 1.0 / 256
+    assert oracle.tex3d(vol, dims, 0, u, 0.5, 0.5, weight_quant=2) == 0.0
+
+
+def test_transfer_function_model(oracle):
+    tf = oracle.default_transfer_function()                 # volumeRender_kernel.cu:2323-2326
+    assert tf.shape == (9, 4) and np.array_equal(tf[2], [1, 0.5, 0, 1]) and np.all(tf[0] == 0) and np.all(tf[8] == 0)
+    for k in range(9):                                      # texel centres are at (k + 1/2)/9
+        np.testing.assert_array_equal(oracle.tex1d4(tf, (k + 0.5) / 9), tf[k])
+    np.testing.assert_array_equal(oracle.tex1d4(tf, -3.0), tf[0])
+    np.testing.assert_array_equal(oracle.tex1d4(tf, 7.0), tf[8])
+    np.testing.assert_allclose(oracle.tex1d4(tf, 2.0 / 9), 0.5 * (tf[1] + tf[2]))
+
+
+# ---- view matrix (volumeRender.cpp:224-246, 1024-1043) ----------------------------------------
+
+def test_view_matrix_selftest_view(oracle):
+    m = oracle.view_matrix(0.0, 0.0, (0.0, 0.0, -4.0))
+    np.testing.assert_array_equal(m, [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 4])
+
+
+def test_view_matrix_matches_gl_composition(oracle):
+    def rot(axis, deg):
+        a = np.deg2rad(deg); c, s = np.cos(a), np.sin(a)
+        return {"x": np.array([[1, 0, 0, 0], [0, c, -s, 0], [0, s, c, 0], [0, 0, 0, 1]]),
+                "y": np.array([[c, 0, s, 0], [0, 1, 0, 0], [-s, 0, c, 0], [0, 0, 0, 1]])}[axis]
+    rx, ry, t = 31.0, -112.5, (0.3, -0.2, -3.5)
+    T = np.eye(4); T[:3, 3] = [-t[0], -t[1], -t[2]]
+    M = rot("x", -rx) @ rot("y", -ry) @ T                   # glRotatef, glRotatef, glTranslatef
+    np.testing.assert_allclose(oracle.view_matrix(rx, ry, t).reshape(3, 4), M[:3], atol=1e-6)
+
+
+# ---- P2: ray casting ---------------------------------------------------------------------------
+
+def test_selftest_view_ray_statistics(oracle):
+    """SURVEY.md §6 / BASELINE.md: at the reference's self-test view (eye z=+4, 512x512,
+    tstep 0.01) 116 281 of 262 144 rays hit the box and, with nothing terminating early, a
+    frame takes 14.37 M samples, at most 208 on one ray."""
+    dims = (4, 4, 4)
+    vol = np.zeros((64, 4), np.float32)
+    vol[:, 0] = 0.5
+    m = oracle.view_matrix()
+    img, s = oracle.render(vol, dims, m, image=(512, 512), density=0.0)
+    assert s == pytest.approx(14.37e6, rel=2e-3)
+    # density 0 leaves every hit pixel 0 too, so count hits with an opaque volume instead
+    img, s2 = oracle.render(vol, dims, m, image=(512, 512), density=1.0, opacity_threshold=0.5)
+    assert int((img != 0).sum()) == 116281
+    one, smax = oracle.render(vol, dims, m, image=(512, 512), density=0.0, rows=(256, 257))
+    assert smax <= 208 * 512
+
+
+def _ray_numpy(vol, dims, tf, m, x, y, iw, ih, density, brightness, off, scale, tstep, max_steps, thr):
+    """Independent float32 restatement of one d_render thread (volumeRender_kernel.cu:282-312,
+    381-387, 601-603, 683-716) with numpy scalars; filter weights rounded to 8 bits."""
+    f = np.float32
+    W, H, D = dims
+    u = f(f(f(x) / f(iw)) * f(2)) - f(1); v = f(f(f(y) / f(ih)) * f(2)) - f(1)
+    o = np.array([m[3], m[7], m[11]], f)
+    d0 = np.array([u, v, f(-2)], f)
+    inv = f(1) / np.sqrt(f(f(d0[0] * d0[0] + d0[1] * d0[1]) + d0[2] * d0[2]))
+    d0 = d0 * inv
+    R = np.asarray(m, f).reshape(3, 4)[:, :3]
+    d = np.array([f(f(d0[0] * R[r, 0] + d0[1] * R[r, 1]) + d0[2] * R[r, 2]) for r in range(3)], f)
+    with np.errstate(divide="ignore"):
+        invr = f(1) / d
+    tb = invr * (f(-1) - o); tt = invr * (f(1) - o)
+    tmin = np.minimum(tt, tb); tmax = np.maximum(tt, tb)
+    tnear = max(max(tmin[0], tmin[1]), max(tmin[0], tmin[2])); tfar = min(min(tmax[0], tmax[1]), min(tmax[0], tmax[2]))
+    if not tfar > tnear:
+        return None, 0
+    tnear = max(tnear, f(0))
+    pos = o + d * tnear; step = d * f(tstep); t = f(tnear)
+    acc = np.zeros(4, f); n = 0
+
+    def split(xn, N):
+        q = np.floor(f(f(xn * f(N)) - f(0.5)) * f(256) + f(0.5)); i = int(q) >> 8
+        return i, f(int(q) - (i << 8)) / f(256)
+
+    def tex3(p):
+        (i, a), (j, b), (k, c) = split(p[0], W), split(p[1], H), split(p[2], D)
+        cl = lambda q, N: min(max(q, 0), N - 1)
+        T = lambda xx, yy, zz: vol[cl(xx, W) + W * (cl(yy, H) + H * cl(zz, D)), 0]
+        lx = lambda yy, zz: f(f(f(1) - a) * T(i, yy, zz)) + f(a * T(i + 1, yy, zz))
+        ly = lambda zz: f(f(f(1) - b) * lx(j, zz)) + f(b * lx(j + 1, zz))
+        return f(f(f(1) - c) * ly(k)) + f(c * ly(k + 1))
+
+    for _ in range(max_steps):
+        s = tex3(pos * f(0.5) + f(0.5)); n += 1
+        i, a = split(f(f(s - f(off)) * f(scale)), tf.shape[0])
+        c0 = tf[min(max(i, 0), tf.shape[0] - 1)]; c1 = tf[min(max(i + 1, 0), tf.shape[0] - 1)]
+        col = (f(1) - a) * c0 + a * c1
+        col = col.astype(f); col[3] = col[3] * f(density); col[:3] = col[:3] * col[3]
+        acc = acc + col * (f(1) - acc[3])
+        if acc[3] > f(thr):
+            break
+        t = f(t + f(tstep))
+        if t > tfar:
+            break
+        pos = pos + step
+    acc = acc * f(brightness)
+    c8 = (np.clip(acc, 0, 1) * f(255)).astype(np.uint32)
+    return int(c8[3] << 24 | c8[2] << 16 | c8[1] << 8 | c8[0]), n
+
+
+def test_render_matches_independent_numpy_ray(oracle):
+    dims = (9, 7, 5)
+    h = oracle.synth_histograms(11, dims)
+    vol = oracle.decode_hist(h)
+    tf = oracle.default_transfer_function()
+    m = oracle.view_matrix(15.0, -30.0)
+    iw, ih = 40, 32
+    img, total = oracle.render(vol, dims, m, image=(iw, ih))
+    checked = 0
+    for (x, y) in [(20, 16), (13, 9), (27, 22), (0, 0), (21, 3), (8, 25)]:
+        px, n = _ray_numpy(vol, dims, tf, m, x, y, iw, ih, 0.05, 1.0, 0.0, 1.0, 0.01, 500, 0.95)
+        if px is None:
+            assert img[y, x] == 0
+        else:
+            assert img[y, x] == px, (x, y, hex(int(img[y, x])), hex(px))
+            checked += 1
+    assert checked >= 3
+
+
+def test_render_uniform_volume_closed_form(oracle):
+    """Constant sample s -> constant colour c and alpha a per step: after n steps
+    alpha = 1 - (1-a)^n; the centre ray of the self-test view crosses t in [3,5] (201 steps)."""
+    dims = (3, 3, 3)
+    vol = np.zeros((27, 4), np.float32); vol[:, 0] = 2.5 / 9      # exactly TF texel 2: (1, .5, 0, 1)
+    img, _ = oracle.render(vol, dims, oracle.view_matrix(), image=(64, 64), density=0.01, opacity_threshold=2.0)
+    px = int(img[32, 32])
+    a = 1 - (1 - 0.01) ** 201
+    assert (px >> 24) == int(a * 255) or (px >> 24) == int(a * 255) - 1
+    assert (px & 255) in (int(a * 255), int(a * 255) - 1)         # red == alpha (premultiplied, colour 1)
+    assert ((px >> 8) & 255) in (int(0.5 * a * 255), int(0.5 * a * 255) - 1)
+    assert ((px >> 16) & 255) == 0
+
+
+def test_early_termination_and_misses(oracle):
+    dims = (3, 3, 3)
+    vol = np.zeros((27, 4), np.float32); vol[:, 0] = 0.5
+    img, s = oracle.render(vol, dims, oracle.view_matrix(), image=(64, 64), density=1.0)
+    assert img[0, 0] == 0 and img[63, 63] == 0                    # corner rays miss: never written
+    hit = img[32, 32]
+    assert (int(hit) >> 24) == 255                                # saturated after one opaque sample
+    assert s == int((img != 0).sum())                             # exactly one sample per hit ray
+
+
+# ---- golden vectors ---------------------------------------------------------------------------
+
+def test_oracle_reproduces_golden(oracle, golden):
+    g = golden
+    dims = tuple(int(v) for v in g["dims"]); img = tuple(int(v) for v in g["img"])
+    dec_o = oracle.decode_hist(g["hist"])
+    dec_f, recon, bad = oracle.decode_fractal(g["codebook"], g["errors"], g["templates"], want_recon=True)
+    assert bad == 0
+    assert np.array_equal(recon, g["recon"])
+    np.testing.assert_allclose(dec_o, g["decoded_original"], rtol=1e-6, atol=1e-7)   # libm logf may differ by 1 ulp
+    np.testing.assert_allclose(dec_f, g["decoded_fractal"], rtol=1e-6, atol=1e-7)
+    for k, (vi, qm, s) in enumerate(g["image_index"]):
+        im, ss = oracle.render(g["decoded_original"], dims, g["views"][vi], image=img, query_method=int(qm),
+                               vol_fractal4=g["decoded_fractal"])
+        assert ss == s
+        assert np.array_equal(im, g["images"][k])
+
+
+def test_synth_invariants(oracle):
+    """The generator honours the reference's run-time guards (volumeRender_kernel.cu:781-838)."""
+    dims = (20, 16, 12)
+    h = oracle.synth_histograms(5, dims)
+    assert h.min() >= 0 and h.max() <= 1
+    np.testing.assert_allclose(h.sum(1), 1.0, atol=1e-6)
+    assert (h == 0).mean() > 0.2
+    t = oracle.synth_templates(5, 622)
+    assert t.min() >= 0 and t.max() <= 1
+    cb, err = oracle.synth_fractal(5, dims)
+    assert cb[:, 0].min() >= 0 and cb[:, 0].max() < 622
+    assert cb[:, 1].min() >= 0 and cb[:, 1].max() < 32
+    assert set(np.unique(cb[:, 2])) <= {0, 1}
+    assert cb[:, 3].min() == 0 and cb[:, 3].max() == 8
+    for v in range(0, cb.shape[0], 97):
+        ne = cb[v, 3]
+        bins = err[v, :ne, 0]
+        assert len(set(bins.tolist())) == ne and bins.min(initial=0) >= 0 and bins.max(initial=0) < 32
+        assert np.all(np.abs(err[v, :ne, 1]) <= 0.05)
+    # slabs of a volume are the volume
+    part = oracle.synth_histograms(5, dims, z0=4, nz=3)
+    assert np.array_equal(part, h.reshape(12, -1, 32)[4:7].reshape(-1, 32))

@@ -1,0 +1,345 @@
+"""vrdd_b200 — Python binding of libvrdd.so (include/vrdd.h), the B200-native distribution
+decode and volume ray caster behind the host-facing surface of
+ykou/Volume-Rendering-Based-on-Distribution-Data.
+
+This module is plumbing: it loads the in-tree CUDA library with ctypes and mirrors the C ABI
+one to one (`Renderer` methods are named after the vrdd_* functions; the legacy names
+initCuda / basicDataProcessing / copyInvViewMatrix / render_kernel / freeCudaBuffers are
+exposed through `legacy`).  There is NO CPU fallback and nothing here imports oracle/: if
+libvrdd.so is missing or no B200 is present, calls raise.
+
+The directory name contains hyphens, so import it through the `vrdd_b200` shim at the
+repository root.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvrdd.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_RANGE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+SRC_ORIGINAL, SRC_FRACTAL = 0, 1
+SAMPLER_TEXTURE, SAMPLER_BRICKED = 0, 1
+ERR_CHUNK = 256
+
+EXPORTS = [
+    "vrdd_create", "vrdd_destroy", "vrdd_set_stream", "vrdd_synchronize", "vrdd_last_error",
+    "vrdd_kernel_launches", "vrdd_set_volume", "vrdd_set_histograms_host", "vrdd_set_histograms_device",
+    "vrdd_set_fractal_host", "vrdd_set_fractal_device", "vrdd_set_sampler", "vrdd_decode",
+    "vrdd_get_decoded_host", "vrdd_get_decoded_planes_device", "vrdd_keep_linear_planes", "vrdd_commit_planes",
+    "vrdd_reconstruct_fractal_device", "vrdd_set_transfer_function", "vrdd_set_view",
+    "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_count_samples",
+    "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
+    "vrdd_set_variant", "vrdd_debug_sample_texture",
+]
+LEGACY_EXPORTS = ["initCuda", "basicDataProcessing", "dataProcessing", "copyInvViewMatrix", "render_kernel",
+                  "setTextureFilterMode", "freeCudaBuffers", "vrdd_legacy_handle"]
+
+
+class VrddError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vrdd error {code}: {msg}")
+        self.code = code
+
+
+class RenderParams(C.Structure):
+    """struct vrdd_render_params (include/vrdd.h)."""
+    _fields_ = [("density", C.c_float), ("brightness", C.c_float), ("transfer_offset", C.c_float),
+                ("transfer_scale", C.c_float), ("tstep", C.c_float), ("max_steps", C.c_int),
+                ("opacity_threshold", C.c_float), ("query_method", C.c_int)]
+
+
+class TilePartition(C.Structure):
+    """struct vrdd_tile_partition (include/vrdd.h)."""
+    _fields_ = [("tile_w", C.c_int), ("tile_h", C.c_int), ("part", C.c_int), ("parts", C.c_int)]
+
+
+class Extent(C.Structure):
+    """cudaExtent"""
+    _fields_ = [("width", C.c_size_t), ("height", C.c_size_t), ("depth", C.c_size_t)]
+
+
+class Dim3(C.Structure):
+    _fields_ = [("x", C.c_uint), ("y", C.c_uint), ("z", C.c_uint)]
+
+
+def build(force=False, verbose=False):
+    """Compile libvrdd.so for sm_100a with csrc/Makefile (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j8"] + (["-B"] if force else [])
+    subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, f32, u32 = C.c_void_p, C.c_int, C.c_float, C.c_uint32
+        sig = {
+            "vrdd_create": (i32, [i32, C.POINTER(vp)]),
+            "vrdd_destroy": (i32, [vp]),
+            "vrdd_set_stream": (i32, [vp, vp]),
+            "vrdd_synchronize": (i32, [vp]),
+            "vrdd_last_error": (C.c_char_p, [vp]),
+            "vrdd_kernel_launches": (C.c_int64, [vp]),
+            "vrdd_set_volume": (i32, [vp, i32, i32, i32, i32]),
+            "vrdd_set_histograms_host": (i32, [vp, vp]),
+            "vrdd_set_histograms_device": (i32, [vp, vp, i32, i32]),
+            "vrdd_set_fractal_host": (i32, [vp, vp, vp, vp, i32]),
+            "vrdd_set_fractal_device": (i32, [vp, vp, vp, vp, vp, i32, i32, i32]),
+            "vrdd_set_sampler": (i32, [vp, i32]),
+            "vrdd_decode": (i32, [vp, i32, i32, i32]),
+            "vrdd_get_decoded_host": (i32, [vp, i32, vp]),
+            "vrdd_get_decoded_planes_device": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+            "vrdd_keep_linear_planes": (i32, [vp, i32]),
+            "vrdd_commit_planes": (i32, [vp, i32, i32, i32]),
+            "vrdd_reconstruct_fractal_device": (i32, [vp, vp]),
+            "vrdd_set_transfer_function": (i32, [vp, vp, i32]),
+            "vrdd_set_view": (i32, [vp, vp]),
+            "vrdd_default_render_params": (None, [C.POINTER(RenderParams)]),
+            "vrdd_render": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(TilePartition), i32]),
+            "vrdd_render_host": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams)]),
+            "vrdd_count_samples": (i32, [vp, i32]),
+            "vrdd_get_sample_count": (i32, [vp, C.POINTER(C.c_int64), i32]),
+            "vrdd_view_matrix": (None, [f32, f32, f32, f32, f32, vp]),
+            "vrdd_synth_histograms_device": (i32, [vp, u32, i32, i32, vp]),
+            "vrdd_synth_fractal_device": (i32, [vp, u32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(C.c_uint64)]),
+            "vrdd_set_variant": (i32, [vp, C.c_char_p, C.c_char_p]),
+            "vrdd_debug_sample_texture": (i32, [vp, i32, i32, vp, i32, vp]),
+            # legacy surface (include/vrdd_legacy.h)
+            "initCuda": (None, [vp, Extent, Extent, vp, Extent, vp, Extent, vp, Extent] + [vp] * 9),
+            "basicDataProcessing": (None, []),
+            "dataProcessing": (None, []),
+            "copyInvViewMatrix": (None, [vp, C.c_size_t]),
+            "render_kernel": (None, [Dim3, Dim3, vp, C.c_uint, C.c_uint, f32, f32, f32, f32, i32, Extent]),
+            "setTextureFilterMode": (None, [C.c_bool]),
+            "freeCudaBuffers": (None, []),
+            "vrdd_legacy_handle": (vp, []),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def default_render_params(**over):
+    p = RenderParams()
+    lib().vrdd_default_render_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+def view_matrix(rot_x=0.0, rot_y=0.0, trans=(0.0, 0.0, -4.0)):
+    """vrdd_view_matrix: the inverse view matrix of volumeRender.cpp:224-246 as 12 floats."""
+    m = (C.c_float * 12)()
+    lib().vrdd_view_matrix(rot_x, rot_y, trans[0], trans[1], trans[2], m)
+    return list(m)
+
+
+def _ptr(x):
+    """Address of a numpy array / torch tensor / ctypes array / int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    return C.addressof(x)
+
+
+class DeviceArray:
+    """Raw device pointer published through __cuda_array_interface__, so memory owned by the
+    library (e.g. the decoded planes) can be handed to torch.distributed without a copy."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3}
+
+
+def as_torch(ptr, shape, typestr="<f4", device="cuda"):
+    import torch
+    return torch.as_tensor(DeviceArray(ptr, shape, typestr), device=device)
+
+
+class Renderer:
+    """One vrdd handle.  Methods map 1:1 onto the vrdd_* C functions."""
+
+    def __init__(self, device=-1):
+        self._h = C.c_void_p()
+        rc = lib().vrdd_create(device, C.byref(self._h))
+        if rc != OK:
+            raise VrddError(rc, "vrdd_create failed: no usable sm_100 CUDA device (there is no CPU fallback)"
+                            if rc == ERR_NO_DEVICE else "vrdd_create failed")
+
+    def _ck(self, rc):
+        if rc != OK:
+            raise VrddError(rc, lib().vrdd_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().vrdd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # lifetime / stream
+    def set_stream(self, cuda_stream):
+        self._ck(lib().vrdd_set_stream(self._h, cuda_stream))
+
+    def synchronize(self):
+        self._ck(lib().vrdd_synchronize(self._h))
+
+    def kernel_launches(self):
+        return int(lib().vrdd_kernel_launches(self._h))
+
+    # inputs
+    def set_volume(self, w, h, d, bins=32):
+        self._ck(lib().vrdd_set_volume(self._h, w, h, d, bins))
+
+    def set_histograms_host(self, hist):
+        self._ck(lib().vrdd_set_histograms_host(self._h, _ptr(hist)))
+
+    def set_histograms_device(self, d_hist, z0, nz):
+        self._ck(lib().vrdd_set_histograms_device(self._h, _ptr(d_hist), z0, nz))
+
+    def set_fractal_host(self, codebook, errors_dense, templates):
+        self._ck(lib().vrdd_set_fractal_host(self._h, _ptr(codebook), _ptr(errors_dense), _ptr(templates),
+                                             templates.shape[0]))
+
+    def set_fractal_device(self, d_codebook, d_errors, d_chunk_offsets, d_templates, num_templates, z0, nz):
+        self._ck(lib().vrdd_set_fractal_device(self._h, _ptr(d_codebook), _ptr(d_errors), _ptr(d_chunk_offsets),
+                                               _ptr(d_templates), num_templates, z0, nz))
+
+    # decode
+    def set_sampler(self, sampler):
+        self._ck(lib().vrdd_set_sampler(self._h, sampler))
+
+    def keep_linear_planes(self, keep=True):
+        self._ck(lib().vrdd_keep_linear_planes(self._h, int(keep)))
+
+    def decode(self, source=SRC_ORIGINAL, z0=0, nz=0):
+        self._ck(lib().vrdd_decode(self._h, source, z0, nz))
+
+    def get_decoded_host(self, source, out4):
+        self._ck(lib().vrdd_get_decoded_host(self._h, source, _ptr(out4)))
+        return out4
+
+    def get_decoded_planes_device(self, source):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(lib().vrdd_get_decoded_planes_device(self._h, source, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def commit_planes(self, source, z0, nz):
+        self._ck(lib().vrdd_commit_planes(self._h, source, z0, nz))
+
+    def reconstruct_fractal_device(self, d_out):
+        self._ck(lib().vrdd_reconstruct_fractal_device(self._h, _ptr(d_out)))
+
+    # render
+    def set_transfer_function(self, tf=None):
+        if tf is None:
+            self._ck(lib().vrdd_set_transfer_function(self._h, None, 0))
+        else:
+            self._ck(lib().vrdd_set_transfer_function(self._h, _ptr(tf), tf.shape[0]))
+
+    def set_view(self, m12):
+        arr = (C.c_float * 12)(*[float(v) for v in m12])
+        self._ck(lib().vrdd_set_view(self._h, arr))
+
+    def render(self, d_output, w, h, params=None, part=None, clear_misses=False):
+        self._ck(lib().vrdd_render(self._h, _ptr(d_output), w, h, C.byref(params) if params is not None else None,
+                                   C.byref(part) if part is not None else None, int(clear_misses)))
+
+    def render_host(self, h_output, w, h, params=None):
+        self._ck(lib().vrdd_render_host(self._h, _ptr(h_output), w, h,
+                                        C.byref(params) if params is not None else None))
+        return h_output
+
+    def count_samples(self, enable=True):
+        self._ck(lib().vrdd_count_samples(self._h, int(enable)))
+
+    def get_sample_count(self, reset=True):
+        v = C.c_int64()
+        self._ck(lib().vrdd_get_sample_count(self._h, C.byref(v), int(reset)))
+        return int(v.value)
+
+    # synthetic inputs
+    def synth_histograms_device(self, seed, z0, nz, d_hist):
+        self._ck(lib().vrdd_synth_histograms_device(self._h, seed, z0, nz, _ptr(d_hist)))
+
+    def synth_fractal_device(self, seed, num_templates, max_ne, z0, nz, d_codebook, d_errors, d_chunk_offsets,
+                             d_templates):
+        tot = C.c_uint64()
+        self._ck(lib().vrdd_synth_fractal_device(self._h, seed, num_templates, max_ne, z0, nz, _ptr(d_codebook),
+                                                 _ptr(d_errors), _ptr(d_chunk_offsets), _ptr(d_templates),
+                                                 C.byref(tot)))
+        return int(tot.value)
+
+    # diagnostics
+    def set_variant(self, what, variant):
+        self._ck(lib().vrdd_set_variant(self._h, what.encode(), variant.encode()))
+
+    def debug_sample_texture(self, source, comp, d_uvw, n, d_out):
+        self._ck(lib().vrdd_debug_sample_texture(self._h, source, comp, _ptr(d_uvw), n, _ptr(d_out)))
+
+
+class legacy:
+    """The reference's seven entry points (volumeRender.cpp:156-170), bound as its host code
+    would bind them."""
+
+    @staticmethod
+    def initCuda(h_volume, volume_size, h_codebook=None, h_templates=None, h_errorsbook=None, bins=32):
+        w, h, d = volume_size
+        nt = 0 if h_templates is None else h_templates.shape[0]
+        lib().initCuda(_ptr(h_volume), Extent(w, h, d), Extent(bins, w * h, d), _ptr(h_codebook), Extent(w, h, d),
+                       _ptr(h_templates), Extent(bins, nt, 1), _ptr(h_errorsbook), Extent(bins, w * h, d),
+                       *([None] * 9))
+
+    @staticmethod
+    def basicDataProcessing():
+        lib().basicDataProcessing()
+
+    @staticmethod
+    def dataProcessing():
+        lib().dataProcessing()
+
+    @staticmethod
+    def copyInvViewMatrix(m12):
+        arr = (C.c_float * 12)(*[float(v) for v in m12])
+        lib().copyInvViewMatrix(arr, C.sizeof(arr))
+
+    @staticmethod
+    def render_kernel(d_output, w, h, density=0.05, brightness=1.0, transfer_offset=0.0, transfer_scale=1.0,
+                      query_method=1, volume_size=(50, 50, 10), block=(16, 16)):
+        grid = Dim3((w + block[0] - 1) // block[0], (h + block[1] - 1) // block[1], 1)
+        lib().render_kernel(grid, Dim3(block[0], block[1], 1), _ptr(d_output), w, h, density, brightness,
+                            transfer_offset, transfer_scale, query_method, Extent(*volume_size))
+
+    @staticmethod
+    def setTextureFilterMode(linear):
+        lib().setTextureFilterMode(bool(linear))
+
+    @staticmethod
+    def freeCudaBuffers():
+        lib().freeCudaBuffers()
+
+    @staticmethod
+    def handle():
+        return lib().vrdd_legacy_handle()

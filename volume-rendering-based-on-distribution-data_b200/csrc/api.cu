@@ -1,0 +1,601 @@
+// api.cu — the handle-based C ABI of include/vrdd.h: context, device storage, uploads,
+// decode / render orchestration.  Host code only; kernels live in the sibling files.
+#include "common.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace vrdd {
+
+int fail(vrdd_context* c, int code, const char* what) {
+    if (c) c->err = what;
+    return code;
+}
+int fail_cuda(vrdd_context* c, cudaError_t e, const char* what) {
+    if (c) c->err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return VRDD_ERR_CUDA;
+}
+
+namespace {
+
+// The hard-coded rainbow of the reference (volumeRender_kernel.cu:2323-2326)
+const float kDefaultTf[9][4] = {{0, 0, 0, 0}, {1, 0, 0, 1}, {1, 0.5f, 0, 1}, {1, 1, 0, 1}, {0, 1, 0, 1},
+                                {0, 1, 1, 1}, {0, 0, 1, 1}, {1, 0, 1, 1}, {0, 0, 0, 0}};
+
+void free_volume(vrdd_decoded_volume& v) {
+    for (int i = 0; i < 3; ++i) {
+        if (v.tex[i]) cudaDestroyTextureObject(v.tex[i]);
+        if (v.surf[i]) cudaDestroySurfaceObject(v.surf[i]);
+        if (v.arr[i]) cudaFreeArray(v.arr[i]);
+        if (v.lin[i]) cudaFree(v.lin[i]);
+        if (v.brick[i]) cudaFree(v.brick[i]);
+    }
+    v = vrdd_decoded_volume();
+}
+
+void free_inputs(vrdd_context* c) {
+    if (c->hist_owned) cudaFree(c->hist_owned);
+    if (c->cb_owned) cudaFree(c->cb_owned);
+    if (c->err_owned) cudaFree(c->err_owned);
+    if (c->off_owned) cudaFree(c->off_owned);
+    if (c->tmpl_owned) cudaFree(c->tmpl_owned);
+    c->hist_owned = nullptr; c->cb_owned = nullptr; c->err_owned = nullptr; c->off_owned = nullptr;
+    c->tmpl_owned = nullptr;
+    c->hist = nullptr; c->cb = nullptr; c->errs = nullptr; c->err_off = nullptr; c->tmpl = nullptr;
+    c->hist_nz = 0; c->fr_nz = 0; c->num_templates = 0;
+}
+
+void free_tf(vrdd_context* c) {
+    if (c->tf_tex) cudaDestroyTextureObject(c->tf_tex);
+    if (c->tf_arr) cudaFreeArray(c->tf_arr);
+    if (c->tf_dev) cudaFree(c->tf_dev);
+    c->tf_tex = 0; c->tf_arr = nullptr; c->tf_dev = nullptr; c->tf_n = 0;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+size_t brick_elems(const vrdd_context* c) {
+    return (size_t)c->bW * c->bH * c->bD * (VRDD_BRICK * VRDD_BRICK * VRDD_BRICK);
+}
+
+}  // namespace
+
+// Allocate whatever the current sampler / keep_linear setting needs for `source`.
+int ensure_volume_storage(vrdd_context* c, int source) {
+    vrdd_decoded_volume& v = c->vol[source];
+    const bool want_tex = c->sampler == VRDD_SAMPLER_TEXTURE;
+    const bool want_brick = c->sampler == VRDD_SAMPLER_BRICKED;
+    const bool want_lin = c->keep_linear;
+    for (int i = 0; i < 3; ++i) {
+        if (want_tex && !v.arr[i]) {
+            cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+            VRDD_CUDA(c, cudaMalloc3DArray(&v.arr[i], &desc, make_cudaExtent(c->W, c->H, c->D),
+                                           cudaArraySurfaceLoadStore));
+            cudaResourceDesc rd;
+            std::memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = v.arr[i];
+            // linear, normalised, clamp: originalQueryTex / fractalQueryTex
+            // (volumeRender_kernel.cu:1865-1876; the third axis keeps the default clamp)
+            cudaTextureDesc td;
+            std::memset(&td, 0, sizeof(td));
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 1;
+            VRDD_CUDA(c, cudaCreateTextureObject(&v.tex[i], &rd, &td, nullptr));
+            VRDD_CUDA(c, cudaCreateSurfaceObject(&v.surf[i], &rd));
+        }
+        if (want_lin && !v.lin[i]) VRDD_CUDA(c, cudaMalloc(&v.lin[i], sizeof(float) * c->V));
+        if (want_brick && !v.brick[i]) {
+            VRDD_CUDA(c, cudaMalloc(&v.brick[i], sizeof(float) * brick_elems(c)));
+            VRDD_CUDA(c, cudaMemsetAsync(v.brick[i], 0, sizeof(float) * brick_elems(c), c->stream));
+        }
+    }
+    return VRDD_OK;
+}
+
+DecodeOut make_decode_out(vrdd_context* c, int source, long long v_base) {
+    vrdd_decoded_volume& v = c->vol[source];
+    DecodeOut o;
+    for (int i = 0; i < 3; ++i) {
+        o.lin[i] = v.lin[i];
+        o.surf[i] = v.surf[i];
+        o.brick[i] = v.brick[i];
+    }
+    o.use_surf = v.surf[0] != 0;
+    o.W = c->W; o.H = c->H; o.D = c->D;
+    o.v_base = v_base;
+    o.bW = c->bW; o.bH = c->bH;
+    return o;
+}
+
+}  // namespace vrdd
+
+// linear plane slab -> sampler layout
+__global__ void commit_brick_kernel(const float* __restrict__ lin, float* __restrict__ brick, int W, int H, int bW,
+                                    int bH, long long v0, long long nvox) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvox) return;
+    const long long gv = v0 + i, wh = (long long)W * H;
+    const int z = (int)(gv / wh);
+    const int r = (int)(gv - (long long)z * wh);
+    const int y = r / W, x = r - y * W;
+    brick[vrdd::brick_index(x, y, z, bW, bH)] = lin[gv];
+}
+
+__global__ void gather_brick_kernel(const float* __restrict__ brick, float* __restrict__ lin, int W, int H, int bW,
+                                    int bH, long long nvox) {
+    const long long gv = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gv >= nvox) return;
+    const long long wh = (long long)W * H;
+    const int z = (int)(gv / wh);
+    const int r = (int)(gv - (long long)z * wh);
+    const int y = r / W, x = r - y * W;
+    lin[gv] = brick[vrdd::brick_index(x, y, z, bW, bH)];
+}
+
+using namespace vrdd;
+
+#define CHECK_HANDLE(h)                      \
+    if (!(h)) return VRDD_ERR_INVALID;       \
+    vrdd_context* c = (h);                   \
+    DeviceGuard guard__(c->device)
+
+extern "C" {
+
+int vrdd_create(int device, vrdd_handle* out) {
+    if (!out) return VRDD_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return VRDD_ERR_NO_DEVICE;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return VRDD_ERR_NO_DEVICE;
+    if (device >= n) return VRDD_ERR_INVALID;
+    vrdd_context* c = new vrdd_context();
+    c->device = device;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return VRDD_ERR_NO_DEVICE; }
+    c->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        std::fprintf(stderr, "libvrdd: device %d is sm_%d%d; this library is built for sm_100a only\n", device,
+                     prop.major, prop.minor);
+        delete c;
+        return VRDD_ERR_NO_DEVICE;
+    }
+    if (cudaMalloc(&c->d_samples, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(c->d_samples, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        delete c;
+        return VRDD_ERR_CUDA;
+    }
+    *out = c;
+    int rc = vrdd_set_transfer_function(c, nullptr, 0);
+    if (rc != VRDD_OK) { vrdd_destroy(c); *out = nullptr; return rc; }
+    return VRDD_OK;
+}
+
+int vrdd_destroy(vrdd_handle h) {
+    CHECK_HANDLE(h);
+    cudaStreamSynchronize(c->stream);
+    free_volume(c->vol[0]);
+    free_volume(c->vol[1]);
+    free_inputs(c);
+    free_tf(c);
+    if (c->d_samples) cudaFree(c->d_samples);
+    delete c;
+    return VRDD_OK;
+}
+
+int vrdd_set_stream(vrdd_handle h, void* cuda_stream) {
+    CHECK_HANDLE(h);
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    return VRDD_OK;
+}
+
+int vrdd_synchronize(vrdd_handle h) {
+    CHECK_HANDLE(h);
+    VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VRDD_OK;
+}
+
+const char* vrdd_last_error(vrdd_handle h) { return h ? h->err.c_str() : "null handle"; }
+int64_t vrdd_kernel_launches(vrdd_handle h) { return h ? h->launches : 0; }
+
+int vrdd_set_volume(vrdd_handle h, int width, int height, int depth, int bins) {
+    CHECK_HANDLE(h);
+    if (width <= 0 || height <= 0 || depth <= 0) return fail(c, VRDD_ERR_INVALID, "set_volume: bad size");
+    if (bins != VRDD_BINS) return fail(c, VRDD_ERR_UNSUPPORTED, "set_volume: this build supports bins == 32 only");
+    VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_volume(c->vol[0]);
+    free_volume(c->vol[1]);
+    free_inputs(c);
+    c->W = width; c->H = height; c->D = depth; c->B = bins;
+    c->V = (size_t)width * height * depth;
+    c->bW = (width + VRDD_BRICK - 1) / VRDD_BRICK;
+    c->bH = (height + VRDD_BRICK - 1) / VRDD_BRICK;
+    c->bD = (depth + VRDD_BRICK - 1) / VRDD_BRICK;
+    return VRDD_OK;
+}
+
+int vrdd_set_histograms_host(vrdd_handle h, const float* hist) {
+    CHECK_HANDLE(h);
+    if (!c->V || !hist) return fail(c, VRDD_ERR_INVALID, "set_histograms_host: set_volume first");
+    const size_t bytes = c->V * c->B * sizeof(float);
+    if (!c->hist_owned) VRDD_CUDA(c, cudaMalloc(&c->hist_owned, bytes));
+    VRDD_CUDA(c, cudaMemcpyAsync(c->hist_owned, hist, bytes, cudaMemcpyHostToDevice, c->stream));
+    VRDD_CUDA(c, cudaStreamSynchronize(c->stream));      // the caller frees right after (volumeRender.cpp:1205)
+    c->hist = c->hist_owned; c->hist_z0 = 0; c->hist_nz = c->D;
+    return VRDD_OK;
+}
+
+int vrdd_set_histograms_device(vrdd_handle h, const float* d_hist, int z0, int nz) {
+    CHECK_HANDLE(h);
+    if (!c->V || !d_hist || z0 < 0 || nz <= 0 || z0 + nz > c->D)
+        return fail(c, VRDD_ERR_INVALID, "set_histograms_device: bad slab");
+    if ((reinterpret_cast<uintptr_t>(d_hist) & 15u) != 0)
+        return fail(c, VRDD_ERR_INVALID, "set_histograms_device: pointer must be 16-byte aligned");
+    c->hist = d_hist; c->hist_z0 = z0; c->hist_nz = nz;
+    return VRDD_OK;
+}
+
+int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* errors_dense, const float* templates,
+                          int num_templates) {
+    CHECK_HANDLE(h);
+    if (!c->V || !codebook || !errors_dense || !templates || num_templates <= 0)
+        return fail(c, VRDD_ERR_INVALID, "set_fractal_host: bad arguments");
+    const int B = c->B;
+    const size_t V = c->V;
+    // validate with the reference's guards (volumeRender_kernel.cu:781-816) and compact
+    const size_t nchunks = (V + VRDD_ERR_CHUNK - 1) / VRDD_ERR_CHUNK;
+    std::vector<uint64_t> off(nchunks + 1);
+    uint64_t total = 0;
+    for (size_t v = 0; v < V; ++v) {
+        if (v % VRDD_ERR_CHUNK == 0) off[v / VRDD_ERR_CHUNK] = total;
+        const int32_t* e = codebook + 4 * v;
+        if (e[0] < 0 || e[0] >= num_templates || e[1] < 0 || e[1] > B || e[3] < 0 || e[3] > B)
+            return fail(c, VRDD_ERR_RANGE, "set_fractal_host: codebook entry out of range");
+        total += (uint64_t)e[3];
+    }
+    off[nchunks] = total;
+    std::vector<float> compact(2 * (total ? total : 1));
+    uint64_t w = 0;
+    for (size_t v = 0; v < V; ++v) {
+        const int ne = codebook[4 * v + 3];
+        const float* row = errors_dense + 2 * (v * B);
+        for (int k = 0; k < ne; ++k) {
+            const int bin = (int)row[2 * k];
+            if (bin < 0 || bin >= B) return fail(c, VRDD_ERR_RANGE, "set_fractal_host: error bin out of range");
+            compact[2 * w] = row[2 * k]; compact[2 * w + 1] = row[2 * k + 1];
+            ++w;
+        }
+    }
+    for (int i = 0; i < num_templates * B; ++i)
+        if (!(templates[i] >= 0.0f && templates[i] <= 1.0f))
+            return fail(c, VRDD_ERR_RANGE, "set_fractal_host: template frequency outside [0,1]");
+    if (c->cb_owned) cudaFree(c->cb_owned);
+    if (c->err_owned) cudaFree(c->err_owned);
+    if (c->off_owned) cudaFree(c->off_owned);
+    if (c->tmpl_owned) cudaFree(c->tmpl_owned);
+    c->cb_owned = nullptr; c->err_owned = nullptr; c->off_owned = nullptr; c->tmpl_owned = nullptr;
+    VRDD_CUDA(c, cudaMalloc(&c->cb_owned, sizeof(int32_t) * 4 * V));
+    VRDD_CUDA(c, cudaMalloc(&c->err_owned, sizeof(float) * compact.size()));
+    VRDD_CUDA(c, cudaMalloc(&c->off_owned, sizeof(uint64_t) * (nchunks + 1)));
+    VRDD_CUDA(c, cudaMalloc(&c->tmpl_owned, sizeof(float) * num_templates * B));
+    VRDD_CUDA(c, cudaMemcpyAsync(c->cb_owned, codebook, sizeof(int32_t) * 4 * V, cudaMemcpyHostToDevice, c->stream));
+    VRDD_CUDA(c, cudaMemcpyAsync(c->err_owned, compact.data(), sizeof(float) * compact.size(),
+                                 cudaMemcpyHostToDevice, c->stream));
+    VRDD_CUDA(c, cudaMemcpyAsync(c->off_owned, off.data(), sizeof(uint64_t) * (nchunks + 1), cudaMemcpyHostToDevice,
+                                 c->stream));
+    VRDD_CUDA(c, cudaMemcpyAsync(c->tmpl_owned, templates, sizeof(float) * num_templates * B, cudaMemcpyHostToDevice,
+                                 c->stream));
+    VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->cb = c->cb_owned; c->errs = c->err_owned; c->err_off = c->off_owned; c->tmpl = c->tmpl_owned;
+    c->num_templates = num_templates; c->fr_z0 = 0; c->fr_nz = c->D;
+    return VRDD_OK;
+}
+
+int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const float* d_errors,
+                            const uint64_t* d_chunk_offsets, const float* d_templates, int num_templates, int z0,
+                            int nz) {
+    CHECK_HANDLE(h);
+    if (!c->V || !d_codebook || !d_errors || !d_chunk_offsets || !d_templates || num_templates <= 0 || z0 < 0 ||
+        nz <= 0 || z0 + nz > c->D)
+        return fail(c, VRDD_ERR_INVALID, "set_fractal_device: bad arguments");
+    if (((reinterpret_cast<uintptr_t>(d_codebook) | reinterpret_cast<uintptr_t>(d_templates)) & 15u) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_errors) & 7u) != 0)
+        return fail(c, VRDD_ERR_INVALID, "set_fractal_device: misaligned pointer");
+    c->cb = d_codebook; c->errs = d_errors; c->err_off = d_chunk_offsets; c->tmpl = d_templates;
+    c->num_templates = num_templates; c->fr_z0 = z0; c->fr_nz = nz;
+    return VRDD_OK;
+}
+
+int vrdd_set_sampler(vrdd_handle h, int sampler) {
+    CHECK_HANDLE(h);
+    if (sampler != VRDD_SAMPLER_TEXTURE && sampler != VRDD_SAMPLER_BRICKED)
+        return fail(c, VRDD_ERR_INVALID, "set_sampler: unknown sampler");
+    c->sampler = sampler;
+    return VRDD_OK;
+}
+
+int vrdd_keep_linear_planes(vrdd_handle h, int keep) {
+    CHECK_HANDLE(h);
+    c->keep_linear = keep != 0;
+    return VRDD_OK;
+}
+
+int vrdd_decode(vrdd_handle h, int source, int z0, int nz) {
+    CHECK_HANDLE(h);
+    if (source != VRDD_SRC_ORIGINAL && source != VRDD_SRC_FRACTAL) return fail(c, VRDD_ERR_INVALID, "decode: bad source");
+    if (!c->V) return fail(c, VRDD_ERR_INVALID, "decode: set_volume first");
+    const bool orig = source == VRDD_SRC_ORIGINAL;
+    const int az0 = orig ? c->hist_z0 : c->fr_z0, anz = orig ? c->hist_nz : c->fr_nz;
+    if (anz <= 0) return fail(c, VRDD_ERR_INVALID, "decode: no input attached for this source");
+    if (nz <= 0) { z0 = az0; nz = anz; }
+    if (z0 < az0 || z0 + nz > az0 + anz) return fail(c, VRDD_ERR_INVALID, "decode: slab outside the attached input");
+    int rc = ensure_volume_storage(c, source);
+    if (rc != VRDD_OK) return rc;
+    const long long slice = (long long)c->W * c->H;
+    const long long local0 = (long long)(z0 - az0) * slice;     // first voxel inside the attached slab
+    const long long nvox = (long long)nz * slice;
+    DecodeOut out = make_decode_out(c, source, (long long)z0 * slice);
+    if (orig) {
+        rc = launch_decode_hist(c, c->hist + local0 * c->B, nvox, out);
+    } else {
+        if (local0 % VRDD_ERR_CHUNK != 0)
+            return fail(c, VRDD_ERR_INVALID, "decode: fractal sub-slab must start on a 256-voxel boundary");
+        rc = launch_decode_fractal(c, c->cb + 4 * local0, c->errs, c->err_off + local0 / VRDD_ERR_CHUNK, c->tmpl,
+                                   c->num_templates, nvox, out, nullptr);
+    }
+    if (rc == VRDD_OK) c->vol[source].decoded = true;
+    return rc;
+}
+
+int vrdd_reconstruct_fractal_device(vrdd_handle h, float* d_out) {
+    CHECK_HANDLE(h);
+    if (c->fr_nz <= 0 || !d_out) return fail(c, VRDD_ERR_INVALID, "reconstruct_fractal: no fractal input attached");
+    int rc = ensure_volume_storage(c, VRDD_SRC_FRACTAL);
+    if (rc != VRDD_OK) return rc;
+    const long long slice = (long long)c->W * c->H;
+    DecodeOut out = make_decode_out(c, VRDD_SRC_FRACTAL, (long long)c->fr_z0 * slice);
+    rc = launch_decode_fractal(c, c->cb, c->errs, c->err_off, c->tmpl, c->num_templates, (long long)c->fr_nz * slice,
+                               out, d_out);
+    if (rc == VRDD_OK) c->vol[VRDD_SRC_FRACTAL].decoded = true;
+    return rc;
+}
+
+int vrdd_get_decoded_planes_device(vrdd_handle h, int source, float** mean, float** variance, float** entropy) {
+    CHECK_HANDLE(h);
+    if (source < 0 || source > 1) return fail(c, VRDD_ERR_INVALID, "get_decoded_planes_device: bad source");
+    if (c->keep_linear && c->V) {
+        int rc = ensure_volume_storage(c, source);
+        if (rc != VRDD_OK) return rc;
+    }
+    if (mean) *mean = c->vol[source].lin[0];
+    if (variance) *variance = c->vol[source].lin[1];
+    if (entropy) *entropy = c->vol[source].lin[2];
+    return VRDD_OK;
+}
+
+int vrdd_commit_planes(vrdd_handle h, int source, int z0, int nz) {
+    CHECK_HANDLE(h);
+    if (source < 0 || source > 1 || z0 < 0 || nz <= 0 || z0 + nz > c->D)
+        return fail(c, VRDD_ERR_INVALID, "commit_planes: bad arguments");
+    vrdd_decoded_volume& v = c->vol[source];
+    if (!v.lin[0]) return fail(c, VRDD_ERR_INVALID, "commit_planes: linear planes are not kept");
+    int rc = ensure_volume_storage(c, source);
+    if (rc != VRDD_OK) return rc;
+    const long long slice = (long long)c->W * c->H;
+    for (int i = 0; i < 3; ++i) {
+        if (v.arr[i]) {
+            cudaMemcpy3DParms p;
+            std::memset(&p, 0, sizeof(p));
+            p.srcPtr = make_cudaPitchedPtr(v.lin[i] + (size_t)z0 * slice, c->W * sizeof(float), c->W, c->H);
+            p.dstArray = v.arr[i];
+            p.dstPos = make_cudaPos(0, 0, z0);
+            p.extent = make_cudaExtent(c->W, c->H, nz);
+            p.kind = cudaMemcpyDeviceToDevice;
+            VRDD_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
+        }
+        if (v.brick[i]) {
+            const long long nvox = (long long)nz * slice;
+            commit_brick_kernel<<<(unsigned)((nvox + 255) / 256), 256, 0, c->stream>>>(
+                v.lin[i], v.brick[i], c->W, c->H, c->bW, c->bH, (long long)z0 * slice, nvox);
+            c->launches += 1;
+            VRDD_CUDA(c, cudaGetLastError());
+        }
+    }
+    v.decoded = true;
+    return VRDD_OK;
+}
+
+int vrdd_get_decoded_host(vrdd_handle h, int source, float* out4) {
+    CHECK_HANDLE(h);
+    if (source < 0 || source > 1 || !out4) return fail(c, VRDD_ERR_INVALID, "get_decoded_host: bad arguments");
+    vrdd_decoded_volume& v = c->vol[source];
+    if (!v.decoded) return fail(c, VRDD_ERR_INVALID, "get_decoded_host: nothing decoded");
+    std::vector<float> plane(c->V);
+    float* d_tmp = nullptr;
+    for (int i = 0; i < 3; ++i) {
+        if (v.lin[i]) {
+            VRDD_CUDA(c, cudaMemcpyAsync(plane.data(), v.lin[i], sizeof(float) * c->V, cudaMemcpyDeviceToHost, c->stream));
+        } else if (v.arr[i]) {
+            cudaMemcpy3DParms p;
+            std::memset(&p, 0, sizeof(p));
+            p.srcArray = v.arr[i];
+            p.dstPtr = make_cudaPitchedPtr(plane.data(), c->W * sizeof(float), c->W, c->H);
+            p.extent = make_cudaExtent(c->W, c->H, c->D);
+            p.kind = cudaMemcpyDeviceToHost;
+            VRDD_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
+        } else if (v.brick[i]) {
+            if (!d_tmp) VRDD_CUDA(c, cudaMalloc(&d_tmp, sizeof(float) * c->V));
+            gather_brick_kernel<<<(unsigned)((c->V + 255) / 256), 256, 0, c->stream>>>(v.brick[i], d_tmp, c->W, c->H,
+                                                                                      c->bW, c->bH, (long long)c->V);
+            c->launches += 1;
+            VRDD_CUDA(c, cudaMemcpyAsync(plane.data(), d_tmp, sizeof(float) * c->V, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            return fail(c, VRDD_ERR_INVALID, "get_decoded_host: no storage");
+        }
+        VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (size_t k = 0; k < c->V; ++k) out4[4 * k + i] = plane[k];
+    }
+    if (d_tmp) cudaFree(d_tmp);
+    for (size_t k = 0; k < c->V; ++k) out4[4 * k + 3] = 0.0f;   // the reference never writes .w (:771-773)
+    return VRDD_OK;
+}
+
+int vrdd_set_transfer_function(vrdd_handle h, const float* tf, int n) {
+    CHECK_HANDLE(h);
+    if (!tf) { tf = &kDefaultTf[0][0]; n = 9; }
+    if (n < 1 || n > VRDD_MAX_TF) return fail(c, VRDD_ERR_INVALID, "set_transfer_function: 1..1024 entries");
+    VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
+    free_tf(c);
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+    VRDD_CUDA(c, cudaMallocArray(&c->tf_arr, &desc, n, 1));
+    VRDD_CUDA(c, cudaMemcpy2DToArray(c->tf_arr, 0, 0, tf, n * sizeof(float4), n * sizeof(float4), 1,
+                                     cudaMemcpyHostToDevice));
+    cudaResourceDesc rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->tf_arr;
+    cudaTextureDesc td;                                   // volumeRender_kernel.cu:2337-2339
+    std::memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    VRDD_CUDA(c, cudaCreateTextureObject(&c->tf_tex, &rd, &td, nullptr));
+    VRDD_CUDA(c, cudaMalloc(&c->tf_dev, n * sizeof(float4)));
+    VRDD_CUDA(c, cudaMemcpy(c->tf_dev, tf, n * sizeof(float4), cudaMemcpyHostToDevice));
+    c->tf_n = n;
+    return VRDD_OK;
+}
+
+int vrdd_set_view(vrdd_handle h, const float* m12) {
+    if (!h || !m12) return VRDD_ERR_INVALID;
+    std::memcpy(h->view, m12, sizeof(float) * 12);      // travels as a kernel parameter
+    return VRDD_OK;
+}
+
+void vrdd_default_render_params(vrdd_render_params* p) {
+    if (!p) return;
+    p->density = 0.05f; p->brightness = 1.0f; p->transfer_offset = 0.0f; p->transfer_scale = 1.0f;
+    p->tstep = 0.01f; p->max_steps = 500; p->opacity_threshold = 0.95f; p->query_method = 1;
+}
+
+int vrdd_render(vrdd_handle h, uint32_t* d_output, int image_w, int image_h, const vrdd_render_params* params,
+                const vrdd_tile_partition* part, int clear_misses) {
+    CHECK_HANDLE(h);
+    vrdd_render_params p;
+    if (params) p = *params; else vrdd_default_render_params(&p);
+    vrdd_tile_partition tp;
+    if (part) tp = *part; else { tp.tile_w = image_w; tp.tile_h = image_h; tp.part = 0; tp.parts = 1; }
+    return launch_raycast(c, d_output, image_w, image_h, p, tp, clear_misses);
+}
+
+int vrdd_render_host(vrdd_handle h, uint32_t* h_output, int image_w, int image_h, const vrdd_render_params* params) {
+    CHECK_HANDLE(h);
+    if (!h_output || image_w <= 0 || image_h <= 0) return fail(c, VRDD_ERR_INVALID, "render_host: bad image");
+    uint32_t* d_img = nullptr;
+    const size_t bytes = sizeof(uint32_t) * (size_t)image_w * image_h;
+    VRDD_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&d_img), bytes, c->stream));
+    int rc = vrdd_render(h, d_img, image_w, image_h, params, nullptr, 1);
+    if (rc == VRDD_OK) {
+        cudaError_t e = cudaMemcpyAsync(h_output, d_img, bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) rc = fail_cuda(c, e, "render_host: read-back");
+    }
+    cudaFreeAsync(d_img, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (rc == VRDD_OK && e != cudaSuccess) rc = fail_cuda(c, e, "render_host: synchronize");
+    return rc;
+}
+
+int vrdd_count_samples(vrdd_handle h, int enable) {
+    if (!h) return VRDD_ERR_INVALID;
+    h->count_samples = enable != 0;
+    return VRDD_OK;
+}
+
+int vrdd_get_sample_count(vrdd_handle h, int64_t* out, int reset) {
+    CHECK_HANDLE(h);
+    if (!out) return fail(c, VRDD_ERR_INVALID, "get_sample_count: null");
+    unsigned long long v = 0;
+    VRDD_CUDA(c, cudaMemcpyAsync(&v, c->d_samples, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    if (reset) VRDD_CUDA(c, cudaMemsetAsync(c->d_samples, 0, sizeof(v), c->stream));
+    VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = (int64_t)v;
+    return VRDD_OK;
+}
+
+// volumeRender.cpp:224-246 without OpenGL.  glRotatef(-rot.x, 1,0,0); glRotatef(-rot.y, 0,1,0);
+// glTranslatef(-trans): GL post-multiplies, so M = Rx * Ry * T and the stored 3x4 is the
+// top three rows of M (rotation | rotation * (-trans)).
+void vrdd_view_matrix(float rot_x_deg, float rot_y_deg, float tx, float ty, float tz, float* m12) {
+    const double k = 3.14159265358979323846 / 180.0;
+    const double ax = -(double)rot_x_deg * k, ay = -(double)rot_y_deg * k;
+    const float cx = (float)std::cos(ax), sx = (float)std::sin(ax);
+    const float cy = (float)std::cos(ay), sy = (float)std::sin(ay);
+    const float R[3][3] = {{cy, 0.0f, sy}, {sx * sy, cx, -(sx * cy)}, {-(cx * sy), sx, cx * cy}};
+    const float t[3] = {-tx, -ty, -tz};
+    for (int r = 0; r < 3; ++r) {
+        for (int q = 0; q < 3; ++q) m12[4 * r + q] = R[r][q];
+        m12[4 * r + 3] = R[r][0] * t[0] + R[r][1] * t[1] + R[r][2] * t[2];
+    }
+}
+
+int vrdd_synth_histograms_device(vrdd_handle h, uint32_t seed, int z0, int nz, float* d_hist) {
+    CHECK_HANDLE(h);
+    if (!c->V || !d_hist || z0 < 0 || nz <= 0 || z0 + nz > c->D)
+        return fail(c, VRDD_ERR_INVALID, "synth_histograms_device: bad arguments");
+    return launch_synth_hist(c, seed, z0, nz, d_hist);
+}
+
+int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, int max_ne, int z0, int nz,
+                              int32_t* d_codebook, float* d_errors, uint64_t* d_chunk_offsets, float* d_templates,
+                              uint64_t* total_ne) {
+    CHECK_HANDLE(h);
+    if (!c->V || !d_codebook || !d_errors || !d_chunk_offsets || !d_templates || num_templates <= 0 || max_ne < 0 ||
+        max_ne > VRDD_BINS || z0 < 0 || nz <= 0 || z0 + nz > c->D)
+        return fail(c, VRDD_ERR_INVALID, "synth_fractal_device: bad arguments");
+    return launch_synth_fractal(c, seed, num_templates, max_ne, z0, nz, d_codebook, d_errors, d_chunk_offsets,
+                                d_templates, total_ne);
+}
+
+int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
+    if (!h || !what || !variant) return VRDD_ERR_INVALID;
+    vrdd_context* c = h;
+    const std::string w(what), v(variant);
+    if (w == "decode_hist") {
+        if (v == "tma") c->var_decode_hist = 0;
+        else if (v == "ldg") c->var_decode_hist = 1;
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_hist is tma|ldg");
+    } else if (w == "raycast_tf") {
+        if (v == "texture") c->var_tf = 0;
+        else if (v == "smem") c->var_tf = 1;
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_tf is texture|smem");
+    } else {
+        return fail(c, VRDD_ERR_INVALID, "set_variant: unknown kernel");
+    }
+    return VRDD_OK;
+}
+
+int vrdd_debug_sample_texture(vrdd_handle h, int source, int comp, const float* d_uvw, int n, float* d_out) {
+    CHECK_HANDLE(h);
+    if (source < 0 || source > 1 || comp < 0 || comp > 2 || !c->vol[source].tex[comp])
+        return fail(c, VRDD_ERR_INVALID, "debug_sample_texture: no texture volume");
+    return launch_debug_sample(c, c->vol[source].tex[comp], d_uvw, n, d_out);
+}
+
+}  // extern "C"

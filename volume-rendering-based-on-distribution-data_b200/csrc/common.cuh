@@ -1,0 +1,216 @@
+// common.cuh — internal declarations shared by the translation units of libvrdd.so.
+// sm_100a only.  Nothing here is part of the ABI (see include/vrdd.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/vrdd.h"
+
+#define VRDD_BINS 32                 // volumeRender_kernel.cu:91 (nBins); the only supported value
+#define VRDD_ERR_CHUNK 256           // voxels per entry of the fractal error-offset table
+#define VRDD_MAX_TF 1024             // transfer-function entries kept in shared memory
+
+// Dataset scale constants of the reference (volumeRender_kernel.cu:736, 758-759)
+#define VRDD_MAX_HISTOGRAM 0.0217f
+#define VRDD_MEAN_NORM 0.0217        // double in the reference
+#define VRDD_VAR_NORM 0.000021       // double in the reference
+
+namespace vrdd {
+
+// ---- decoded-volume sink -----------------------------------------------------------------
+// Where a decode kernel puts (mean, variance, entropy) of global voxel gv.  Any subset of
+// the three destinations may be active.
+struct DecodeOut {
+    float* lin[3];                   // linear planes float[V], x fastest (or nullptr)
+    cudaSurfaceObject_t surf[3];     // 3-D cudaArray planes (valid iff use_surf)
+    float* brick[3];                 // bricked planes (or nullptr)
+    int W, H, D;
+    int use_surf;
+    long long v_base;                // global index of local voxel 0
+    int bW, bH;                      // bricks per row / per slice (bricked layout)
+};
+
+// Bricked layout for the manual sampler: 4x4x4-texel bricks, 256 B each (two 128-B lines),
+// bricks stored x-fastest.  The volume is padded up to a multiple of 4 in each axis.
+#define VRDD_BRICK 4
+#define VRDD_BRICK_SHIFT 2
+__host__ __device__ __forceinline__ size_t brick_index(int x, int y, int z, int bW, int bH) {
+    size_t b = (size_t)(x >> VRDD_BRICK_SHIFT) +
+               (size_t)bW * ((size_t)(y >> VRDD_BRICK_SHIFT) + (size_t)bH * (size_t)(z >> VRDD_BRICK_SHIFT));
+    return (b << (3 * VRDD_BRICK_SHIFT)) + (size_t)(((z & 3) << 4) | ((y & 3) << 2) | (x & 3));
+}
+
+__device__ __forceinline__ void emit_decoded(const DecodeOut& o, long long v_local, float mean, float var,
+                                             float ent) {
+    const long long gv = o.v_base + v_local;
+    if (o.lin[0]) {
+        o.lin[0][gv] = mean; o.lin[1][gv] = var; o.lin[2][gv] = ent;
+    }
+    if (o.use_surf || o.brick[0]) {
+        const long long wh = (long long)o.W * o.H;
+        const int z = (int)(gv / wh);
+        const int r = (int)(gv - (long long)z * wh);
+        const int y = r / o.W;
+        const int x = r - y * o.W;
+        if (o.use_surf) {
+            surf3Dwrite(mean, o.surf[0], x * 4, y, z);
+            surf3Dwrite(var, o.surf[1], x * 4, y, z);
+            surf3Dwrite(ent, o.surf[2], x * 4, y, z);
+        }
+        if (o.brick[0]) {
+            const size_t bi = brick_index(x, y, z, o.bW, o.bH);
+            o.brick[0][bi] = mean; o.brick[1][bi] = var; o.brick[2][bi] = ent;
+        }
+    }
+}
+
+// ---- mbarrier / bulk-copy (TMA 1-D) PTX wrappers ------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    // make the initialised barriers visible to the async (TMA) proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (SASS: UBLKCP), completion signalled on `bar` in bytes.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// streaming loads that do not pollute L1
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int4 ldg_stream_i4(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// p * log2(p) with the reference's `p <= 0 ? 0` guard (volumeRender_kernel.cu:765-766):
+// log2(max(p, tiny)) is finite, and 0 * finite == 0.  MUFU.LG2 replaces logf(p)/log(2.0).
+__device__ __forceinline__ float plog2p(float p) { return p * __log2f(fmaxf(p, 1.0e-37f)); }
+
+}  // namespace vrdd
+
+// ---- the context behind vrdd_handle --------------------------------------------------------
+struct vrdd_decoded_volume {
+    float* lin[3] = {nullptr, nullptr, nullptr};
+    cudaArray_t arr[3] = {nullptr, nullptr, nullptr};
+    cudaTextureObject_t tex[3] = {0, 0, 0};
+    cudaSurfaceObject_t surf[3] = {0, 0, 0};
+    float* brick[3] = {nullptr, nullptr, nullptr};
+    bool decoded = false;
+};
+
+struct vrdd_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int num_sms = 148;
+
+    int W = 0, H = 0, D = 0, B = VRDD_BINS;
+    size_t V = 0;
+    int bW = 0, bH = 0, bD = 0;      // bricks per axis
+
+    // raw histograms (attached slab)
+    float* hist_owned = nullptr;
+    const float* hist = nullptr;
+    int hist_z0 = 0, hist_nz = 0;
+
+    // fractal codes (attached slab)
+    int32_t* cb_owned = nullptr;
+    float* err_owned = nullptr;
+    uint64_t* off_owned = nullptr;
+    float* tmpl_owned = nullptr;
+    const int32_t* cb = nullptr;
+    const float* errs = nullptr;
+    const uint64_t* err_off = nullptr;
+    const float* tmpl = nullptr;
+    int num_templates = 0;
+    int fr_z0 = 0, fr_nz = 0;
+
+    vrdd_decoded_volume vol[2];
+    int sampler = VRDD_SAMPLER_TEXTURE;
+    bool keep_linear = false;
+
+    // transfer function
+    cudaArray_t tf_arr = nullptr;
+    cudaTextureObject_t tf_tex = 0;
+    float* tf_dev = nullptr;         // float4[tf_n]
+    int tf_n = 0;
+
+    float view[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 4};
+    bool legacy_linear_filter = true;
+
+    unsigned long long* d_samples = nullptr;
+    bool count_samples = false;
+
+    // kernel variants (vrdd_set_variant)
+    int var_decode_hist = 0;         // 0 tma, 1 ldg
+    int var_tf = 0;                  // 0 texture, 1 smem
+    int var_fractal = 0;             // 0 dense
+};
+
+namespace vrdd {
+
+int fail(vrdd_context* c, int code, const char* what);
+int fail_cuda(vrdd_context* c, cudaError_t e, const char* what);
+#define VRDD_CUDA(c, call)                                                      \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) return ::vrdd::fail_cuda((c), e__, #call);      \
+    } while (0)
+
+DecodeOut make_decode_out(vrdd_context* c, int source, long long v_base);
+int ensure_volume_storage(vrdd_context* c, int source);
+
+// kernels' host launchers (one per .cu)
+int launch_decode_hist(vrdd_context* c, const float* d_hist, long long nvox, const DecodeOut& out);
+int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const float* errs, const uint64_t* off,
+                          const float* tmpl, int T, long long nvox, const DecodeOut& out, float* d_recon);
+int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
+                   const vrdd_tile_partition& part, int clear_misses);
+int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_hist);
+int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int z0, int nz, int32_t* d_cb,
+                         float* d_err, uint64_t* d_off, float* d_tmpl, uint64_t* total_ne);
+int launch_debug_sample(vrdd_context* c, cudaTextureObject_t tex, const float* d_uvw, int n, float* d_out);
+
+}  // namespace vrdd

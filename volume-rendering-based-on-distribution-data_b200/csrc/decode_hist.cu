@@ -1,0 +1,224 @@
+// decode_hist.cu — P1a: raw histogram -> (mean, variance, entropy), sm_100a.
+//
+// Replaces the original-histogram half of d_basicDataProcessing
+// (/root/reference/volumeRender_kernel.cu:722-773).  The reference reads every histogram
+// three times through the texture path with 25 000 threads; here the volume is streamed
+// exactly once from HBM.
+//
+// Per voxel (B = 32 bins, p_i the stored frequencies, bw = 0.0217/32):
+//   mean_raw = sum p_i * (bw*i + bw/2)             bin CENTRE            (:742-747)
+//   variance = sum p_i * (i*bw - mean_raw)^2       bin LEFT EDGE         (:749-755)
+//   mean     = mean_raw / 0.0217,  variance /= 0.000021                  (:758-759)
+//   entropy  = -sum p_i * (p_i <= 0 ? 0 : log2 p_i) / log2(32)           (:761-769)
+// The reference promotes single terms to double; this kernel computes in fp32 with
+// MUFU.LG2 for the logarithm.  A literal transcription would issue 32 fp64 divides per
+// voxel and be fp64-bound; the result differs from the oracle by rounding only
+// (tests/test_decode.py states the tolerance).
+//
+// Algorithmic bytes per voxel: 128 read + 12 written (three fp32 planes; the reference's
+// float4 carries a dead fourth lane that is never written, :771-773).
+//
+// Two variants, selected with vrdd_set_variant("decode_hist", ...):
+//   "tma": persistent CTAs; a producer warp streams 64-KB tiles (512 voxel rows) into a
+//          3-stage shared-memory ring with cp.async.bulk (UBLKCP) + mbarrier; 16 consumer
+//          warps take one voxel row per thread, reading the row's eight 16-B chunks in a
+//          rotated order that is bank-conflict-free.
+//   "ldg": no shared-memory staging; eight lanes share a voxel, each lane loads one 16-B
+//          chunk with a streaming LDG.128 (a warp reads 512 contiguous bytes per load,
+//          eight loads in flight per lane) and partial sums are combined with shuffles.
+#include "common.cuh"
+
+namespace vrdd {
+
+namespace {
+
+constexpr int kTileVox = 512;                       // voxel rows per pipeline stage
+constexpr int kStages = 3;
+constexpr int kConsumerWarps = kTileVox / 32;       // 16
+constexpr int kTmaThreads = kTileVox + 32;          // + one producer warp
+constexpr int kRowBytes = VRDD_BINS * 4;            // 128
+constexpr int kTileBytes = kTileVox * kRowBytes;    // 65536
+constexpr size_t kTmaSmem = (size_t)kStages * kTileBytes + 2 * kStages * sizeof(uint64_t);
+
+__device__ __forceinline__ void finish_and_emit(const DecodeOut& out, long long v, float mean_raw, float var_raw,
+                                                float plogp) {
+    const float inv_mean_norm = (float)(1.0 / VRDD_MEAN_NORM);
+    const float inv_var_norm = (float)(1.0 / VRDD_VAR_NORM);
+    const float inv_log2_bins = 1.0f / 5.0f;        // 1 / log2(32)
+    emit_decoded(out, v, mean_raw * inv_mean_norm, var_raw * inv_var_norm, -plogp * inv_log2_bins);
+}
+
+__global__ void __launch_bounds__(kTmaThreads, 1)
+decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* tiles = reinterpret_cast<float4*>(smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kTileBytes);
+    uint64_t* empty = full + kStages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long ntiles = (nvox + kTileVox - 1) / kTileVox;
+
+    if (warp == kConsumerWarps) {
+        // ---- producer: one lane issues the bulk copies ---------------------------------
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                mbar_wait(&empty[s], phase ^ 1u);
+                const long long v0 = t * kTileVox;
+                const long long rows = (nvox - v0 < kTileVox) ? (nvox - v0) : kTileVox;
+                const uint32_t bytes = (uint32_t)rows * kRowBytes;
+                mbar_arrive_expect_tx(&full[s], bytes);
+                // four copies per stage so the copy engine works on several requests at once
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(hist) + (size_t)v0 * kRowBytes;
+                unsigned char* dst = smem + (size_t)s * kTileBytes;
+                const uint32_t quarter = kTileBytes / 4;
+                for (uint32_t off = 0; off < bytes; off += quarter) {
+                    const uint32_t n = (bytes - off < quarter) ? (bytes - off) : quarter;
+                    bulk_g2s(dst + off, src + off, n, &full[s]);
+                }
+                if (++s == kStages) { s = 0; phase ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: thread `tid` owns voxel row `tid` of each tile -------------------------
+    const float bw = VRDD_MAX_HISTOGRAM / (float)VRDD_BINS;     // bin width           (:738)
+    const float hb = 0.5f * bw;
+    int s = 0;
+    uint32_t phase = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(&full[s], phase);
+        const float4* row = tiles + ((size_t)s * kTileVox + tid) * (VRDD_BINS / 4);
+        const long long v = t * kTileVox + tid;
+        float4 q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = row[(j + tid) & 7];   // rotated: conflict-free LDS.128
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);                   // slot may be refilled now
+        if (++s == kStages) { s = 0; phase ^= 1u; }
+        if (v >= nvox) continue;
+
+        float S0 = 0.f, S1 = 0.f, E = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float fc = (float)(((j + tid) & 7) << 2);      // first bin index of this chunk
+            const float sum4 = (q[j].x + q[j].y) + (q[j].z + q[j].w);
+            const float t1 = fmaf(3.f, q[j].w, fmaf(2.f, q[j].z, q[j].y));
+            S0 += sum4;
+            S1 += fmaf(fc, sum4, t1);
+            E += (plog2p(q[j].x) + plog2p(q[j].y)) + (plog2p(q[j].z) + plog2p(q[j].w));
+        }
+        const float mean_raw = fmaf(bw, S1, hb * S0);
+        float var_a = 0.f, var_b = 0.f;                          // two chains: halves the FFMA latency
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float fc = (float)(((j + tid) & 7) << 2);
+            const float d0 = fmaf(fc, bw, -mean_raw);            // left edge of bin fc minus mean
+            const float d1 = d0 + bw, d2 = d0 + 2.f * bw, d3 = d0 + 3.f * bw;
+            var_a = fmaf(q[j].x * d0, d0, var_a);
+            var_b = fmaf(q[j].y * d1, d1, var_b);
+            var_a = fmaf(q[j].z * d2, d2, var_a);
+            var_b = fmaf(q[j].w * d3, d3, var_b);
+        }
+        finish_and_emit(out, v, mean_raw, var_a + var_b, E);
+    }
+}
+
+// ---- "ldg" variant -------------------------------------------------------------------------
+constexpr int kLdgThreads = 256;
+
+__global__ void __launch_bounds__(kLdgThreads)
+decode_hist_ldg_kernel(const float4* __restrict__ hist4, long long nvox, DecodeOut out) {
+    __shared__ float stage[kLdgThreads / 32][3][32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int g = lane >> 3;                       // voxel within the 4-voxel load
+    const int c = lane & 7;                        // 16-B chunk of the row
+    const float bw = VRDD_MAX_HISTOGRAM / (float)VRDD_BINS;
+    const float hb = 0.5f * bw;
+    const float fc = (float)(c << 2);
+
+    const long long nwt = (nvox + 31) / 32;        // warp tiles of 32 voxels
+    const long long wstride = (long long)gridDim.x * (kLdgThreads / 32);
+    for (long long wt = (long long)blockIdx.x * (kLdgThreads / 32) + warp; wt < nwt; wt += wstride) {
+        const long long v0 = wt * 32;
+        float4 q[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const long long v = v0 + it * 4 + g;
+            q[it] = (v < nvox) ? ldg_stream_f4(hist4 + v * 8 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const float sum4 = (q[it].x + q[it].y) + (q[it].z + q[it].w);
+            float S0 = sum4;
+            float S1 = fmaf(fc, sum4, fmaf(3.f, q[it].w, fmaf(2.f, q[it].z, q[it].y)));
+            float E = (plog2p(q[it].x) + plog2p(q[it].y)) + (plog2p(q[it].z) + plog2p(q[it].w));
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+                S0 += __shfl_xor_sync(0xffffffffu, S0, m);
+                S1 += __shfl_xor_sync(0xffffffffu, S1, m);
+            }
+            const float mean_raw = fmaf(bw, S1, hb * S0);
+            const float d0 = fmaf(fc, bw, -mean_raw);
+            const float d1 = d0 + bw, d2 = d0 + 2.f * bw, d3 = d0 + 3.f * bw;
+            float var = (q[it].x * d0) * d0;
+            var = fmaf(q[it].y * d1, d1, var);
+            var = fmaf(q[it].z * d2, d2, var);
+            var = fmaf(q[it].w * d3, d3, var);
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+                var += __shfl_xor_sync(0xffffffffu, var, m);
+                E += __shfl_xor_sync(0xffffffffu, E, m);
+            }
+            if (c == 0) {
+                stage[warp][0][it * 4 + g] = mean_raw;
+                stage[warp][1][it * 4 + g] = var;
+                stage[warp][2][it * 4 + g] = E;
+            }
+        }
+        __syncwarp();
+        const long long v = v0 + lane;
+        const float m_ = stage[warp][0][lane], v_ = stage[warp][1][lane], e_ = stage[warp][2][lane];
+        __syncwarp();
+        if (v < nvox) finish_and_emit(out, v, m_, v_, e_);
+    }
+}
+
+}  // namespace
+
+int launch_decode_hist(vrdd_context* c, const float* d_hist, long long nvox, const DecodeOut& out) {
+    if (nvox <= 0) return VRDD_OK;
+    if (c->var_decode_hist == 0) {
+        VRDD_CUDA(c, cudaFuncSetAttribute(decode_hist_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kTmaSmem));
+        const long long ntiles = (nvox + kTileVox - 1) / kTileVox;
+        const int grid = (int)((ntiles < c->num_sms) ? ntiles : c->num_sms);
+        decode_hist_tma_kernel<<<grid, kTmaThreads, kTmaSmem, c->stream>>>(d_hist, nvox, out);
+    } else {
+        const long long nblk = (nvox + kLdgThreads - 1) / kLdgThreads;
+        const long long cap = (long long)c->num_sms * 8;       // 8 x 256 threads resident per SM
+        const int grid = (int)((nblk < cap) ? nblk : cap);
+        decode_hist_ldg_kernel<<<grid, kLdgThreads, 0, c->stream>>>(reinterpret_cast<const float4*>(d_hist), nvox,
+                                                                    out);
+    }
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+}  // namespace vrdd

@@ -1,0 +1,259 @@
+// raycast.cu — P2: volume ray caster, sm_100a.
+//
+// Replaces d_render (/root/reference/volumeRender_kernel.cu:272-717), intersectBox
+// (:136-156), mul (:168-184) and rgbaFloatToInt (:186-193) for queryMethod 1..6.
+//
+// One thread per pixel, as in the reference, but
+//   * a warp covers an 8x4 pixel tile (the reference's 16x16 block puts a warp on 16x2),
+//     so the eight texels around the 32 samples of one step share cache lines;
+//   * the sampled volume is ONE fp32 plane (mean, variance or entropy), 4 B per texel,
+//     instead of the reference's float4 volume of which one lane is used (16 B per texel);
+//   * the unconditional 8x33-fetch prologue (:354-367) and the dead 32-fetch per-step loop
+//     (:605-612) are not reproduced — they cannot affect the image in these modes;
+//   * image-space partitions (tiles, round-robin over ranks) and an optional fused clear
+//     of missed pixels are part of the launch.
+//
+// Ray set-up (eye ray, slab test, first position, step) and the t / pos recurrences use
+// explicitly rounded operations (__fmul_rn / __fadd_rn / __fdiv_rn / __fsqrt_rn) in the
+// oracle's order, so tnear, tfar and every sample position are bit-identical to the
+// oracle's and both sides take the same number of steps.  Compositing is plain fp32 and
+// may contract to FMA; images agree with the oracle within +-1 LSB per channel.
+//
+// Samplers:
+//   texture — tex3D<float> on a 3-D cudaArray, linear / normalised / clamp: the texture
+//             unit applies the same 8-bit-weight trilinear filter the reference relies on.
+//   bricked — manual trilinear on 4x4x4-texel bricks with the same weight quantisation.
+// Transfer function: tex1D<float4> (the reference's path, :683) or a shared-memory table
+// with the same filter, chosen with vrdd_set_variant("raycast_tf", ...).
+#include "common.cuh"
+
+namespace vrdd {
+
+namespace {
+
+struct RayArgs {
+    cudaTextureObject_t vol_tex;
+    const float* vol_brick;
+    int W, H, D, bW, bH;
+    cudaTextureObject_t tf_tex;
+    const float4* tf_tab;
+    int tf_n;
+    uint32_t* out;
+    int iw, ih;
+    float m[12];
+    float density, brightness, t_offset, t_scale, tstep, thresh;
+    int max_steps;
+    int tile_w, tile_h, tiles_x, part, parts, n_my_tiles;
+    int blocks_x, blocks_per_tile;   // 16x16-pixel blocks inside a tile
+    int clear_misses;
+    unsigned long long* samples;
+};
+
+constexpr int kBlock = 256;          // 8 warps = 16x16 pixels, each warp an 8x4 sub-tile
+
+// 1.8 fixed-point split of an unnormalised linear-filter coordinate (CUDA Programming
+// Guide, "Linear Filtering"): xB = x - 0.5, i = floor(xB), a = frac(xB) to 8 bits.
+__device__ __forceinline__ void split_linear(float x, int& i, float& a) {
+    const float q = floorf(fmaf(x - 0.5f, 256.0f, 0.5f));
+    const int qi = (int)q;
+    i = qi >> 8;
+    a = (float)(qi & 255) * (1.0f / 256.0f);
+}
+
+__device__ __forceinline__ float4 tf_lookup_smem(const float4* tab, int n, float u) {
+    int i; float a;
+    split_linear(u * (float)n, i, a);
+    const int i0 = min(max(i, 0), n - 1), i1 = min(max(i + 1, 0), n - 1);
+    const float4 c0 = tab[i0], c1 = tab[i1];
+    const float oa = 1.0f - a;
+    return make_float4(oa * c0.x + a * c1.x, oa * c0.y + a * c1.y, oa * c0.z + a * c1.z, oa * c0.w + a * c1.w);
+}
+
+__device__ __forceinline__ float sample_bricked(const RayArgs& A, float u, float v, float w) {
+    int i, j, k; float a, b, c;
+    split_linear(u * (float)A.W, i, a);
+    split_linear(v * (float)A.H, j, b);
+    split_linear(w * (float)A.D, k, c);
+    const int i0 = min(max(i, 0), A.W - 1), i1 = min(max(i + 1, 0), A.W - 1);
+    const int j0 = min(max(j, 0), A.H - 1), j1 = min(max(j + 1, 0), A.H - 1);
+    const int k0 = min(max(k, 0), A.D - 1), k1 = min(max(k + 1, 0), A.D - 1);
+    const float* B = A.vol_brick;
+    const float t000 = __ldg(B + brick_index(i0, j0, k0, A.bW, A.bH));
+    const float t100 = __ldg(B + brick_index(i1, j0, k0, A.bW, A.bH));
+    const float t010 = __ldg(B + brick_index(i0, j1, k0, A.bW, A.bH));
+    const float t110 = __ldg(B + brick_index(i1, j1, k0, A.bW, A.bH));
+    const float t001 = __ldg(B + brick_index(i0, j0, k1, A.bW, A.bH));
+    const float t101 = __ldg(B + brick_index(i1, j0, k1, A.bW, A.bH));
+    const float t011 = __ldg(B + brick_index(i0, j1, k1, A.bW, A.bH));
+    const float t111 = __ldg(B + brick_index(i1, j1, k1, A.bW, A.bH));
+    const float oa = 1.0f - a, ob = 1.0f - b, oc = 1.0f - c;
+    const float x00 = oa * t000 + a * t100, x10 = oa * t010 + a * t110;
+    const float x01 = oa * t001 + a * t101, x11 = oa * t011 + a * t111;
+    const float y0 = ob * x00 + b * x10, y1 = ob * x01 + b * x11;
+    return oc * y0 + c * y1;
+}
+
+__device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a) {
+    // saturate, scale, truncate, pack (volumeRender_kernel.cu:186-193)
+    return ((uint32_t)(__saturatef(a) * 255.0f) << 24) | ((uint32_t)(__saturatef(b) * 255.0f) << 16) |
+           ((uint32_t)(__saturatef(g) * 255.0f) << 8) | (uint32_t)(__saturatef(r) * 255.0f);
+}
+
+template <int SAMPLER, int TFMODE, bool COUNT>
+__global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
+    __shared__ float4 tf_s[TFMODE == 1 ? VRDD_MAX_TF : 1];
+    if (TFMODE == 1) {
+        for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
+        __syncthreads();
+    }
+
+    // ---- which pixel ----------------------------------------------------------------
+    const int lt = blockIdx.x / A.blocks_per_tile;                 // my tile number
+    const int bt = blockIdx.x - lt * A.blocks_per_tile;            // block inside the tile
+    const int gt = A.part + lt * A.parts;                          // global tile index
+    const int ty = gt / A.tiles_x, tx = gt - ty * A.tiles_x;
+    const int by = bt / A.blocks_x, bx = bt - by * A.blocks_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int ly = by * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const int x = tx * A.tile_w + lx, y = ty * A.tile_h + ly;
+    unsigned long long nsamp = 0;
+
+    if (lx < A.tile_w && ly < A.tile_h && x < A.iw && y < A.ih) {
+        // ---- eye ray (volumeRender_kernel.cu:288-296), explicitly rounded --------------
+        const float u = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)A.iw), 2.0f), 1.0f);
+        const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)A.ih), 2.0f), 1.0f);
+        const float ox = A.m[3], oy = A.m[7], oz = A.m[11];
+        float dx0 = u, dy0 = v, dz0 = -2.0f;
+        const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
+        const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+        dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
+        const float dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[0]), __fmul_rn(dy0, A.m[1])), __fmul_rn(dz0, A.m[2]));
+        const float dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[4]), __fmul_rn(dy0, A.m[5])), __fmul_rn(dz0, A.m[6]));
+        const float dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[8]), __fmul_rn(dy0, A.m[9])), __fmul_rn(dz0, A.m[10]));
+        // ---- slab test against [-1,1]^3 (:136-156) --------------------------------------
+        const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+        const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, ox));
+        const float by0 = __fmul_rn(iy, __fsub_rn(-1.0f, oy)), by1 = __fmul_rn(iy, __fsub_rn(1.0f, oy));
+        const float bz0 = __fmul_rn(iz, __fsub_rn(-1.0f, oz)), bz1 = __fmul_rn(iz, __fsub_rn(1.0f, oz));
+        const float tminx = fminf(bx1, bx0), tminy = fminf(by1, by0), tminz = fminf(bz1, bz0);
+        const float tmaxx = fmaxf(bx1, bx0), tmaxy = fmaxf(by1, by0), tmaxz = fmaxf(bz1, bz0);
+        float tnear = fmaxf(fmaxf(tminx, tminy), fmaxf(tminx, tminz));
+        const float tfar = fminf(fminf(tmaxx, tmaxy), fminf(tmaxx, tmaxz));
+
+        if (tfar > tnear) {
+            if (tnear < 0.0f) tnear = 0.0f;                                          // :305-306
+            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
+            float t = tnear;
+            float px = __fadd_rn(ox, __fmul_rn(dx, tnear));                          // :311
+            float py = __fadd_rn(oy, __fmul_rn(dy, tnear));
+            float pz = __fadd_rn(oz, __fmul_rn(dz, tnear));
+            const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
+            for (int i = 0; i < A.max_steps; ++i) {                                  // :381
+                // pos*0.5 is exact, so fma == mul-then-add here
+                const float cu = fmaf(px, 0.5f, 0.5f), cv = fmaf(py, 0.5f, 0.5f), cw = fmaf(pz, 0.5f, 0.5f);
+                float s;
+                if (SAMPLER == 0) s = tex3D<float>(A.vol_tex, cu, cv, cw);           // :601-651
+                else s = sample_bricked(A, cu, cv, cw);
+                const float tu = (s - A.t_offset) * A.t_scale;                       // :683-684
+                float4 col;
+                if (TFMODE == 0) col = tex1D<float4>(A.tf_tex, tu);
+                else col = tf_lookup_smem(tf_s, A.tf_n, tu);
+                if (COUNT) ++nsamp;
+                col.w *= A.density;                                                  // :685
+                col.x *= col.w; col.y *= col.w; col.z *= col.w;                      // :691-693
+                const float k = 1.0f - sa;                                           // :695
+                sr += col.x * k; sg += col.y * k; sb += col.z * k; sa += col.w * k;
+                if (sa > A.thresh) break;                                            // :698
+                t = __fadd_rn(t, A.tstep);                                           // :701
+                if (t > tfar) break;                                                 // :703
+                px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);  // :706
+            }
+            A.out[(size_t)y * A.iw + x] =
+                pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);  // :713-716
+        } else if (A.clear_misses) {
+            A.out[(size_t)y * A.iw + x] = 0u;                                        // volumeRender.cpp:208
+        }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, d);
+        if (lane == 0 && nsamp) atomicAdd(A.samples, nsamp);
+    }
+}
+
+__global__ void debug_sample_kernel(cudaTextureObject_t tex, const float* __restrict__ uvw, int n,
+                                    float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tex3D<float>(tex, uvw[3 * i], uvw[3 * i + 1], uvw[3 * i + 2]);
+}
+
+template <int SAMPLER, int TFMODE>
+void launch_variant(bool count, int grid, cudaStream_t st, const RayArgs& A) {
+    if (count) raycast_kernel<SAMPLER, TFMODE, true><<<grid, kBlock, 0, st>>>(A);
+    else raycast_kernel<SAMPLER, TFMODE, false><<<grid, kBlock, 0, st>>>(A);
+}
+
+}  // namespace
+
+int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
+                   const vrdd_tile_partition& part, int clear_misses) {
+    const int qm = p.query_method;
+    if (qm < 1 || qm > 6)
+        return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod must be 1..6 (7 and the flexible-block "
+                                             "modes 8/9/0 are not built; SURVEY.md §8f)");
+    const int source = (qm >= 4) ? VRDD_SRC_FRACTAL : VRDD_SRC_ORIGINAL;
+    const int comp = (qm - 1) % 3;
+    vrdd_decoded_volume& vol = c->vol[source];
+    if (!vol.decoded) return fail(c, VRDD_ERR_INVALID, "render: the requested volume has not been decoded");
+    if (iw <= 0 || ih <= 0 || !d_out) return fail(c, VRDD_ERR_INVALID, "render: bad image");
+    if (part.parts < 1 || part.part < 0 || part.part >= part.parts || part.tile_w < 1 || part.tile_h < 1)
+        return fail(c, VRDD_ERR_INVALID, "render: bad tile partition");
+
+    RayArgs A;
+    A.vol_tex = vol.tex[comp];
+    A.vol_brick = vol.brick[comp];
+    A.W = c->W; A.H = c->H; A.D = c->D; A.bW = c->bW; A.bH = c->bH;
+    A.tf_tex = c->tf_tex; A.tf_tab = reinterpret_cast<const float4*>(c->tf_dev); A.tf_n = c->tf_n;
+    A.out = d_out; A.iw = iw; A.ih = ih;
+    for (int i = 0; i < 12; ++i) A.m[i] = c->view[i];
+    A.density = p.density; A.brightness = p.brightness; A.t_offset = p.transfer_offset;
+    A.t_scale = p.transfer_scale; A.tstep = p.tstep; A.thresh = p.opacity_threshold; A.max_steps = p.max_steps;
+    A.tile_w = part.tile_w; A.tile_h = part.tile_h;
+    A.tiles_x = (iw + part.tile_w - 1) / part.tile_w;
+    const int tiles_y = (ih + part.tile_h - 1) / part.tile_h;
+    const int ntiles = A.tiles_x * tiles_y;
+    A.part = part.part; A.parts = part.parts;
+    A.n_my_tiles = (ntiles - part.part + part.parts - 1) / part.parts;
+    A.blocks_x = (part.tile_w + 15) / 16;
+    A.blocks_per_tile = A.blocks_x * ((part.tile_h + 15) / 16);
+    A.clear_misses = clear_misses;
+    A.samples = c->d_samples;
+    if (A.n_my_tiles <= 0) return VRDD_OK;
+    const long long grid = (long long)A.n_my_tiles * A.blocks_per_tile;
+    if (grid > 0x7fffffffLL) return fail(c, VRDD_ERR_INVALID, "render: image too large");
+
+    const bool count = c->count_samples && c->d_samples;
+    const int sampler = c->sampler, tfm = (c->sampler == VRDD_SAMPLER_BRICKED) ? 1 : c->var_tf;
+    if (sampler == VRDD_SAMPLER_TEXTURE && !A.vol_tex) return fail(c, VRDD_ERR_INVALID, "render: no texture volume");
+    if (sampler == VRDD_SAMPLER_BRICKED && !A.vol_brick) return fail(c, VRDD_ERR_INVALID, "render: no bricked volume");
+    if (sampler == VRDD_SAMPLER_TEXTURE) {
+        if (tfm == 0) launch_variant<0, 0>(count, (int)grid, c->stream, A);
+        else launch_variant<0, 1>(count, (int)grid, c->stream, A);
+    } else {
+        launch_variant<1, 1>(count, (int)grid, c->stream, A);
+    }
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+int launch_debug_sample(vrdd_context* c, cudaTextureObject_t tex, const float* d_uvw, int n, float* d_out) {
+    if (n <= 0) return VRDD_OK;
+    debug_sample_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(tex, d_uvw, n, d_out);
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+}  // namespace vrdd
