@@ -1,0 +1,524 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the two hot paths on B200 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload), all inputs synthetic and generated on the device
+(include/vrdd_synth.h):
+  * decode: a VOL^3 distribution volume (default 1024^3 x 32 bins = 137 GB of raw
+    histograms) is decoded z-slab by z-slab; every slab is resident in HBM before its timed
+    region starts.  Reported in `decode` (GB/s against the measured HBM peak) together with
+    the fractal-code decode of the same volume.
+  * ray cast (the `metric`): a "step" renders one IMG x IMG view (default 1024^2) of the
+    decoded volume with the reference's constants (tstep 0.01, 500 steps, threshold 0.95,
+    density 0.05, rainbow transfer function, queryMethod 1), cycling through the 64-view orbit
+    of BASELINE.json configs[1].  Gsamples/s = transfer-function lookups / time; the lookups
+    are counted exactly by the kernel in an untimed pass over the same views.
+  * N > 1: image-space tiles (64x64, round-robin over ranks) of a frame that grows with N so
+    every GPU keeps IMG^2 pixels (weak scaling); every rank decodes VOL/N z-slices and the
+    decoded planes are all-gathered (NCCL); partial frames are reduced to rank 0 (NCCL).
+Timing: CUDA events on the launching stream, >= 3 warm-up steps, barrier + synchronize on
+both sides, max over ranks.  The sampled volume (4.3 GB) and every decode slab (>= 8 GB) are
+far larger than the 126 MB L2, so no L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HIST_BYTES_PER_VOXEL = 128 + 12          # 32 fp32 bins read, three fp32 planes written
+SAMPLE_BYTES = 32                        # 8 fp32 texels per trilinear sample
+ORBIT_VIEWS = 64
+HBM_FALLBACK_GBS = 6650.0                # /opt/skills/guides/B200_PROFILING.md
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); out["sm_max_mhz"] = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def orbit_view(V, k):
+    """View k of the 64-view orbit: viewRotation.y = k * 5.625 deg, translation (0,0,-4)
+    (volumeRender.cpp:126, 229-246)."""
+    return V.view_matrix(0.0, k * (360.0 / ORBIT_VIEWS), (0.0, 0.0, -4.0))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (oracle).  bench.py may execute oracle/ only here: as the timed CPU baseline.
+# ---------------------------------------------------------------------------------------------
+
+def cpu_decode_baseline(seed):
+    """Raw-histogram decode on the host cores: a 256x256x64 slab of the same synthetic volume."""
+    from oracle.vrdd_oracle import Oracle
+    o = Oracle(fast=True)
+    dims = (256, 256, 256)
+    hist = o.synth_histograms(seed, dims, z0=96, nz=64)
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter(); o.decode_hist(hist); best = min(best, time.perf_counter() - t0)
+    nvox = hist.shape[0]
+    return {"value": nvox * HIST_BYTES_PER_VOXEL / best / 1e9, "unit": "GB/s", "cores": o.num_threads(),
+            "kind": "port", "sample": "256x256x64 slab (4.2 M voxels) of the synthetic volume, best of 3, "
+            "OpenMP oracle -O3 -march=x86-64-v3", "mvoxels_per_s": nvox / best / 1e6}
+
+
+class CpuRaycaster:
+    """The oracle ray caster on a bounded volume: 256^3 decoded on the host, IMG^2 views of the
+    same orbit with the reference's constants (the sample count per view does not depend on
+    the volume resolution because tstep is fixed)."""
+
+    def __init__(self, seed, img):
+        import numpy as np
+        from oracle.vrdd_oracle import Oracle
+        self.o = Oracle(fast=True)
+        self.dims = (256, 256, 256)
+        self.img = img
+        vol = np.empty((256 ** 3, 4), np.float32)
+        sl = 256 * 256
+        for z0 in range(0, 256, 32):
+            vol[z0 * sl:(z0 + 32) * sl] = self.o.decode_hist(self.o.synth_histograms(seed, self.dims, z0=z0, nz=32))
+        self.vol = vol
+
+    def step(self, k):
+        view = self.o.view_matrix(0.0, k * (360.0 / ORBIT_VIEWS))
+        _, s = self.o.render(self.vol, self.dims, view, image=self.img)
+        return s
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The reference itself cannot be compiled
+    (CUDA 12.9 removed texture references), so this is the OpenMP oracle port
+    with all host threads, on the same metric/config as our arm.  One step = one view."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    img = (args.image, args.image)
+    rc = CpuRaycaster(args.seed, img)
+    for k in range(min(args.warmup, 2)):
+        rc.step(k)
+    steps = max(1, min(args.steps, 16))
+    t0 = time.perf_counter()
+    samples = sum(rc.step(k) for k in range(steps))
+    dt = time.perf_counter() - t0
+    val = samples / dt / 1e9
+    sample = f"{img[0]}x{img[1]} views of the 64-view orbit on a 256^3 decoded volume, {steps} views"
+    line = {"impl": "reference", "metric": "raycast_throughput", "value": val, "unit": "Gsamples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt / steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "fps": steps / dt,
+            "config": {"workload": f"ray cast {img[0]}x{img[1]} orbit views, reference constants (tstep 0.01, 500 steps, "
+                                   "threshold 0.95), CPU oracle on a bounded 256^3 volume"},
+            "cpu_baseline": {"value": val, "unit": "Gsamples/s", "cores": rc.o.num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import vrdd_b200 as V
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU leg)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+
+    vol = args.volume
+    W = H = D = vol
+    r = V.Renderer(local)
+    r.set_stream(torch.cuda.current_stream().cuda_stream)
+    r.set_sampler(V.SAMPLER_TEXTURE if args.sampler == "texture" else V.SAMPLER_BRICKED)
+    if args.tf:
+        r.set_variant("raycast_tf", args.tf)
+    r.set_variant("decode_hist", args.decode_variant)
+    if world > 1:
+        r.keep_linear_planes(True)
+    r.set_volume(W, H, D)
+    slice_vox = W * H
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = r.kernel_launches()
+
+    # ---- P1: decode my z-range slab by slab -------------------------------------------------
+    z_lo, z_hi = D * rank // world, D * (rank + 1) // world
+    slab = max(1, min(args.slab_z, z_hi - z_lo))
+    hist_buf = torch.empty(slab * slice_vox * 32, dtype=torch.float32, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    dec_ms, dec_launches, dec_vox = 0.0, 0, 0
+    reps = max(1, args.decode_reps)
+    for z0 in range(z_lo, z_hi, slab):
+        nz = min(slab, z_hi - z0)
+        r.synth_histograms_device(args.seed, z0, nz, hist_buf)
+        r.set_histograms_device(hist_buf, z0, nz)
+        r.decode(V.SRC_ORIGINAL, z0, nz)                       # warm-up (also creates the arrays)
+        barrier()
+        e0, e1 = ev(), ev()
+        l0 = r.kernel_launches()
+        e0.record()
+        for _ in range(reps):
+            r.decode(V.SRC_ORIGINAL, z0, nz)
+        e1.record()
+        torch.cuda.synchronize()
+        dec_launches += r.kernel_launches() - l0
+        dec_ms += e0.elapsed_time(e1) / reps
+        dec_vox += nz * slice_vox
+    dec_ms = max_over_ranks(dec_ms)
+    total_vox = W * H * D
+    dec_gbs = total_vox * HIST_BYTES_PER_VOXEL / (dec_ms * 1e-3) / 1e9
+    decode = {"kernel": "decode_hist_" + args.decode_variant, "voxels": total_vox, "ms": dec_ms,
+              "gbs": dec_gbs, "gvoxels_per_s": total_vox / (dec_ms * 1e-3) / 1e9,
+              "bytes_per_voxel": HIST_BYTES_PER_VOXEL, "slab_z": slab, "launch_ms": dec_ms * world / max(1, (D + slab - 1) // slab)}
+
+    # ---- P1b: fractal decode of the same volume (compact codes) -----------------------------
+    fr = None
+    if args.fractal and world == 1:
+        T, max_ne = 622, 8
+        del hist_buf
+        torch.cuda.empty_cache()
+        fslab = slab
+        nvs = fslab * slice_vox
+        cb = torch.empty(nvs * 4, dtype=torch.int32, device=dev)
+        er = torch.empty(nvs * max_ne * 2, dtype=torch.float32, device=dev)
+        off = torch.empty((nvs + 255) // 256 + 1, dtype=torch.int64, device=dev)
+        tm = torch.empty(T * 32, dtype=torch.float32, device=dev)
+        fr_ms, fr_bytes = 0.0, 0
+        for z0 in range(0, D, fslab):
+            nz = min(fslab, D - z0)
+            tot = r.synth_fractal_device(args.seed, T, max_ne, z0, nz, cb, er, off, tm)
+            r.set_fractal_device(cb, er, off, tm, T, z0, nz)
+            r.decode(V.SRC_FRACTAL, z0, nz)
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(reps):
+                r.decode(V.SRC_FRACTAL, z0, nz)
+            e1.record()
+            torch.cuda.synchronize()
+            fr_ms += e0.elapsed_time(e1) / reps
+            fr_bytes += nz * slice_vox * (16 + 12) + tot * 8
+        fr = {"kernel": "decode_fractal_dense", "ms": fr_ms, "gbs": fr_bytes / (fr_ms * 1e-3) / 1e9,
+              "frac_of_hbm_peak": fr_bytes / (fr_ms * 1e-3) / 1e9 / hbm_peak,
+              "gvoxels_per_s": total_vox / (fr_ms * 1e-3) / 1e9, "bytes_per_voxel": fr_bytes / total_vox,
+              "templates": T, "mean_ne": (fr_bytes / total_vox - 28) / 8}
+        del cb, er, off, tm
+    else:
+        del hist_buf
+    torch.cuda.empty_cache()
+
+    # ---- replicate the decoded planes (N > 1): all-gather of z-slabs over NCCL ---------------
+    gather_ms = None
+    if world > 1:
+        planes = r.get_decoded_planes_device(V.SRC_ORIGINAL)
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for p in planes[:1] if args.gather_planes == 1 else planes:
+            full = V.as_torch(p, (D * slice_vox,))
+            mine = full[z_lo * slice_vox:z_hi * slice_vox]
+            if D % world == 0:
+                dist.all_gather_into_tensor(full, mine.clone())
+            else:
+                parts = [full[(D * q // world) * slice_vox:(D * (q + 1) // world) * slice_vox] for q in range(world)]
+                dist.all_gather(parts, mine.clone())
+        r.commit_planes(V.SRC_ORIGINAL, 0, D)
+        e1.record()
+        torch.cuda.synchronize()
+        gather_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- P2: ray casting ---------------------------------------------------------------------
+    # weak scaling: every GPU keeps IMG^2 pixels; the frame grows with N
+    fw = args.image * (2 if world in (2, 8) else 1) * (2 if world >= 4 else 1)
+    fh = args.image * (2 if world >= 4 else 1)
+    if world not in (1, 2, 4, 8):
+        fw, fh = args.image * world, args.image
+    part = V.TilePartition(64, 64, rank, world)
+    params = V.default_render_params(query_method=1)
+    img = torch.zeros(fh, fw, dtype=torch.int32, device=dev)
+    red = torch.zeros_like(img) if world > 1 else None
+
+    def render_step(k, e2e_host=None):
+        r.set_view(orbit_view(V, k % ORBIT_VIEWS))
+        r.render(img, fw, fh, params, part=part if world > 1 else None, clear_misses=True)
+        if world > 1:
+            red.copy_(img)
+            dist.reduce(red, dst=0, op=dist.ReduceOp.SUM)
+
+    # exact sample counts per view (untimed)
+    r.count_samples(True)
+    counts = []
+    for k in range(ORBIT_VIEWS if args.steps >= ORBIT_VIEWS else min(ORBIT_VIEWS, args.warmup + args.steps)):
+        render_step(k)
+        counts.append(r.get_sample_count())
+    r.count_samples(False)
+    if world > 1:
+        t = torch.tensor(counts, dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        counts = [int(x) for x in t.tolist()]
+
+    for k in range(args.warmup):
+        render_step(k)
+    barrier()
+    l0 = r.kernel_launches()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(args.warmup, args.warmup + args.steps):
+        render_step(k)
+    e1.record()
+    barrier()
+    ray_launches = r.kernel_launches() - l0
+    ray_ms = max_over_ranks(e0.elapsed_time(e1))
+    samples = sum(counts[k % len(counts)] for k in range(args.warmup, args.warmup + args.steps))
+    gsamples = samples / (ray_ms * 1e-3) / 1e9
+    ms_per_step = ray_ms / args.steps
+
+    # kernel-only duration of the ray caster (no reduce), for the roofline block
+    barrier()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(args.warmup, args.warmup + args.steps):
+        r.set_view(orbit_view(V, k % ORBIT_VIEWS))
+        r.render(img, fw, fh, params, part=part if world > 1 else None, clear_misses=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ray_kernel_ms = e0.elapsed_time(e1) / args.steps
+
+    # ---- end to end through the C ABI with host buffers (rank-local frame) -------------------
+    host_img = torch.empty(fh, fw, dtype=torch.int32).pin_memory()
+    e2e = None
+    if world == 1:
+        for k in range(min(3, args.warmup)):
+            r.set_view(orbit_view(V, k)); r.render_host(host_img, fw, fh, params)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(args.warmup, args.warmup + args.steps):
+            r.set_view(orbit_view(V, k % ORBIT_VIEWS))          # copyInvViewMatrix: 48 B host -> kernel parameters
+            r.render_host(host_img, fw, fh, params)             # render + D2H of the frame + synchronize
+        dt = time.perf_counter() - t0
+        e2e = {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48 + 32,
+               "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt,
+               "call": "vrdd_set_view + vrdd_render_host (render, device->pinned-host frame copy, synchronize)"}
+    else:
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.warmup, args.warmup + args.steps):
+            render_step(k)
+            if rank == 0:
+                host_img.copy_(red, non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48 + 32,
+               "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt,
+               "call": "vrdd_set_view + vrdd_render (tiles) + NCCL reduce to rank 0 + device->pinned-host frame copy"}
+
+    # ---- decode end to end from HOST memory (upload inside the timed region) ------------------
+    dec_e2e = None
+    if world == 1 and args.e2e_decode_z > 0:
+        r2 = V.Renderer(local)
+        ez = args.e2e_decode_z
+        r2.set_volume(W, H, ez)
+        tmp = torch.empty(ez * slice_vox * 32, dtype=torch.float32, device=dev)
+        r2.synth_histograms_device(args.seed, 0, ez, tmp)
+        r2.synchronize()
+        h_hist = torch.empty(ez * slice_vox * 32, dtype=torch.float32).pin_memory()
+        h_hist.copy_(tmp)
+        del tmp
+        h_out = np.empty((ez * slice_vox, 4), np.float32)
+        best = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r2.set_histograms_host(h_hist)                      # initCuda: H2D of the histograms
+            r2.decode(V.SRC_ORIGINAL)                           # basicDataProcessing
+            r2.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        nv = ez * slice_vox
+        dec_e2e = {"value": nv * HIST_BYTES_PER_VOXEL / best / 1e9, "unit": "GB/s", "h2d_bytes": nv * 128,
+                   "sample": f"{W}x{H}x{ez} slab from pinned host memory: vrdd_set_histograms_host + vrdd_decode + sync"}
+        r2.close()
+        del h_hist, h_out
+
+    clk = clocks.stop()
+    total_launches = r.kernel_launches() - launches0
+
+    # ---- CPU baselines (rank 0, N = 1) ---------------------------------------------------------
+    cpu_ray = cpu_dec = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu_dec = cpu_decode_baseline(args.seed)
+        rc = CpuRaycaster(args.seed, (args.image, args.image))
+        rc.step(0)
+        t0 = time.perf_counter()
+        s_cpu = sum(rc.step(k) for k in range(3))
+        dt = time.perf_counter() - t0
+        cpu_ray = {"value": s_cpu / dt / 1e9, "unit": "Gsamples/s", "cores": rc.o.num_threads(), "kind": "port",
+                   "sample": f"3 {args.image}x{args.image} orbit views on a 256^3 decoded volume (same constants; "
+                             "sample count per view is independent of volume resolution)", "fps": 3 / dt}
+
+    if rank == 0:
+        decode["frac_of_hbm_peak"] = dec_gbs / (hbm_peak * world)
+        decode["peak_gbs"] = hbm_peak * world
+        if cpu_dec:
+            decode["cpu_baseline"] = cpu_dec
+        if dec_e2e:
+            decode["e2e"] = dec_e2e
+        if fr:
+            decode["fractal"] = fr
+        per_launch_vox = (slab * slice_vox)
+        per_launch_ms = dec_ms * world / max(1, ((z_hi - z_lo) + slab - 1) // slab) / world if world == 1 else None
+        n_slabs = ((z_hi - z_lo) + slab - 1) // slab
+        launch_ms = dec_ms / n_slabs
+        roofline = {"kernel": decode["kernel"], "bound": "hbm",
+                    "achieved": per_launch_vox * HIST_BYTES_PER_VOXEL / (launch_ms * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"
+                    if peak_kind == "measured" else "fallback (B200_PROFILING.md)",
+                    "traffic": None, "launch_ms": launch_ms, "bytes_per_launch": per_launch_vox * HIST_BYTES_PER_VOXEL}
+        roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        my_samples = samples / world
+        roofline_ray = {"kernel": "raycast_kernel", "bound": "l1tex",
+                        "achieved": my_samples / args.steps * SAMPLE_BYTES / (ray_kernel_ms * 1e-3) / 1e9,
+                        "unit": "GB/s", "launch_ms": ray_kernel_ms,
+                        "hbm_frac_if_every_sample_missed": my_samples / args.steps * SAMPLE_BYTES /
+                        (ray_kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                        "note": "algorithmic 32 B per trilinear sample (8 fp32 texels) / kernel time; served by "
+                                "L1TEX/L2, see profiles/ for dram bytes"}
+        line = {"metric": "raycast_throughput", "value": gsamples, "unit": "Gsamples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "fps": 1e3 / ms_per_step, "samples_per_frame": samples / args.steps,
+                "config": {"workload": f"{vol}^3 distribution volume (32 bins) decoded on device, ray cast "
+                                       f"{fw}x{fh} per step over the 64-view orbit, reference constants "
+                                       "(tstep 0.01, 500 steps, threshold 0.95, density 0.05, queryMethod 1)",
+                           "volume": [W, H, D], "image": [fw, fh], "sampler": args.sampler,
+                           "partition": "single GPU" if world == 1 else f"64x64 image tiles round-robin over {world} ranks; "
+                           "z-slab decode + NCCL all-gather of planes; NCCL reduce of frames to rank 0",
+                           "l2": "inputs larger than L2 (4.3 GB sampled plane, >= 8 GB decode slabs); no flush"},
+                "decode": decode, "roofline": roofline, "roofline_raycast": roofline_ray,
+                "e2e": e2e, "gpu_launches": int(ray_launches), "gpu_launches_total": int(total_launches),
+                "clocks": clk}
+        if gather_ms is not None:
+            line["allgather_planes_ms"] = gather_ms
+        if cpu_ray:
+            line["cpu_baseline"] = cpu_ray
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--volume", type=int, default=1024, help="distribution volume edge (voxels)")
+    ap.add_argument("--image", type=int, default=1024, help="pixels per GPU edge")
+    ap.add_argument("--slab-z", type=int, default=256, help="z-slices decoded per launch (256 -> 34 GB of histograms)")
+    ap.add_argument("--decode-reps", type=int, default=3)
+    ap.add_argument("--decode-variant", default="tma", choices=["tma", "ldg"])
+    ap.add_argument("--sampler", default="texture", choices=["texture", "bricked"])
+    ap.add_argument("--tf", default=None, choices=[None, "texture", "smem"])
+    ap.add_argument("--fractal", type=int, default=1)
+    ap.add_argument("--gather-planes", type=int, default=3)
+    ap.add_argument("--e2e-decode-z", type=int, default=8, help="z-slices of the host-memory decode leg (0 = skip)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--seed", type=int, default=1234)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -219,6 +219,8 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);
  * the ray caster's texture object.  For the filter-model conformance test.  Device ptrs. */
 int vrdd_debug_sample_texture(vrdd_handle h, int source, int comp, const float* d_uvw, int n,
                               float* d_out);
+/* Same for the transfer-function texture: out4[i] = tex1D(transferTex, u[i]).  Device ptrs. */
+int vrdd_debug_sample_transfer_function(vrdd_handle h, const float* d_u, int n, float* d_out4);
 
 #ifdef __cplusplus
 }

@@ -124,7 +124,7 @@ class Oracle:
 
     def render(self, vol4, dims, view, image=(512, 512), query_method=1, tf=None, density=0.05,
                brightness=1.0, transfer_offset=0.0, transfer_scale=1.0, tstep=0.01, max_steps=500,
-               opacity_threshold=0.95, weight_quant=1, vol_fractal4=None, rows=None):
+               opacity_threshold=0.95, weight_quant=3, vol_fractal4=None, rows=None):
         """Returns (uint32 image[h][w] pre-cleared to 0, sample count)."""
         W, H, D = dims
         iw, ih = image
@@ -140,12 +140,12 @@ class Oracle:
                                         np.ascontiguousarray(view, np.float32), out, C.byref(P))
         return out, int(s)
 
-    def tex3d(self, vol4, dims, comp, u, v, w, weight_quant=1):
+    def tex3d(self, vol4, dims, comp, u, v, w, weight_quant=3):
         W, H, D = dims
         return float(self.lib.vrdd_oracle_tex3d(np.ascontiguousarray(vol4, np.float32), W, H, D, comp, u, v, w,
                                                 weight_quant))
 
-    def tex1d4(self, tf, u, weight_quant=1):
+    def tex1d4(self, tf, u, weight_quant=3):
         tf = np.ascontiguousarray(tf, np.float32)
         out = np.empty(4, np.float32)
         self.lib.vrdd_oracle_tex1d4(tf, tf.shape[0], u, weight_quant, out)

@@ -32,7 +32,7 @@ EXPORTS = [
     "vrdd_reconstruct_fractal_device", "vrdd_set_transfer_function", "vrdd_set_view",
     "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_count_samples",
     "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
-    "vrdd_set_variant", "vrdd_debug_sample_texture",
+    "vrdd_set_variant", "vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function",
 ]
 LEGACY_EXPORTS = ["initCuda", "basicDataProcessing", "dataProcessing", "copyInvViewMatrix", "render_kernel",
                   "setTextureFilterMode", "freeCudaBuffers", "vrdd_legacy_handle"]
@@ -115,6 +115,7 @@ def lib():
             "vrdd_synth_fractal_device": (i32, [vp, u32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(C.c_uint64)]),
             "vrdd_set_variant": (i32, [vp, C.c_char_p, C.c_char_p]),
             "vrdd_debug_sample_texture": (i32, [vp, i32, i32, vp, i32, vp]),
+            "vrdd_debug_sample_transfer_function": (i32, [vp, vp, i32, vp]),
             # legacy surface (include/vrdd_legacy.h)
             "initCuda": (None, [vp, Extent, Extent, vp, Extent, vp, Extent, vp, Extent] + [vp] * 9),
             "basicDataProcessing": (None, []),
@@ -298,6 +299,10 @@ class Renderer:
 
     def debug_sample_texture(self, source, comp, d_uvw, n, d_out):
         self._ck(lib().vrdd_debug_sample_texture(self._h, source, comp, _ptr(d_uvw), n, _ptr(d_out)))
+
+
+    def debug_sample_transfer_function(self, d_u, n, d_out4):
+        self._ck(lib().vrdd_debug_sample_transfer_function(self._h, _ptr(d_u), n, _ptr(d_out4)))
 
 
 class legacy:

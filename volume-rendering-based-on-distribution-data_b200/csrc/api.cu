@@ -598,4 +598,10 @@ int vrdd_debug_sample_texture(vrdd_handle h, int source, int comp, const float* 
     return launch_debug_sample(c, c->vol[source].tex[comp], d_uvw, n, d_out);
 }
 
+int vrdd_debug_sample_transfer_function(vrdd_handle h, const float* d_u, int n, float* d_out4) {
+    CHECK_HANDLE(h);
+    if (!c->tf_tex || !d_u || !d_out4) return fail(c, VRDD_ERR_INVALID, "debug_sample_transfer_function: bad arguments");
+    return launch_debug_sample_tf(c, d_u, n, d_out4);
+}
+
 }  // extern "C"

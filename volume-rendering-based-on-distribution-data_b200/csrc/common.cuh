@@ -212,5 +212,6 @@ int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_h
 int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int z0, int nz, int32_t* d_cb,
                          float* d_err, uint64_t* d_off, float* d_tmpl, uint64_t* total_ne);
 int launch_debug_sample(vrdd_context* c, cudaTextureObject_t tex, const float* d_uvw, int n, float* d_out);
+int launch_debug_sample_tf(vrdd_context* c, const float* d_u, int n, float* d_out4);
 
 }  // namespace vrdd

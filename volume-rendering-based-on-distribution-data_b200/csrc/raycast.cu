@@ -22,7 +22,8 @@
 // Samplers:
 //   texture — tex3D<float> on a 3-D cudaArray, linear / normalised / clamp: the texture
 //             unit applies the same 8-bit-weight trilinear filter the reference relies on.
-//   bricked — manual trilinear on 4x4x4-texel bricks with the same weight quantisation.
+//   bricked — manual trilinear on 4x4x4-texel bricks with the texture unit's exact integer
+//             weight scheme (split_hw / sample_bricked below).
 // Transfer function: tex1D<float4> (the reference's path, :683) or a shared-memory table
 // with the same filter, chosen with vrdd_set_variant("raycast_tf", ...).
 #include "common.cuh"
@@ -51,46 +52,60 @@ struct RayArgs {
 
 constexpr int kBlock = 256;          // 8 warps = 16x16 pixels, each warp an 8x4 sub-tile
 
-// 1.8 fixed-point split of an unnormalised linear-filter coordinate (CUDA Programming
-// Guide, "Linear Filtering"): xB = x - 0.5, i = floor(xB), a = frac(xB) to 8 bits.
-__device__ __forceinline__ void split_linear(float x, int& i, float& a) {
-    const float q = floorf(fmaf(x - 0.5f, 256.0f, 0.5f));
-    const int qi = (int)q;
-    i = qi >> 8;
-    a = (float)(qi & 255) * (1.0f / 256.0f);
+// The texture unit's linear filter, restated in integer arithmetic (measured on B200 with
+// one-hot / ramp volumes, tools/probe_texture*.py; the oracle carries the same scheme):
+//   U = trunc(sat(u) * 2^21);  q = ((U * N * 256 + 2^20) >> 21) - 128, clamped to [0,(N-1)*256];
+//   texel i = q >> 8, weight A = q & 255 (out of 256).
+__device__ __forceinline__ void split_hw(float u, int n256, int& i, int& a) {
+    const unsigned U = (unsigned)(__saturatef(u) * 2097152.0f);
+    const unsigned long long p = (unsigned long long)U * (unsigned)n256 + (1u << 20);
+    int q = (int)(p >> 21) - 128;
+    q = min(max(q, 0), n256 - 256);
+    i = q >> 8;
+    a = q & 255;
 }
 
 __device__ __forceinline__ float4 tf_lookup_smem(const float4* tab, int n, float u) {
-    int i; float a;
-    split_linear(u * (float)n, i, a);
-    const int i0 = min(max(i, 0), n - 1), i1 = min(max(i + 1, 0), n - 1);
-    const float4 c0 = tab[i0], c1 = tab[i1];
-    const float oa = 1.0f - a;
-    return make_float4(oa * c0.x + a * c1.x, oa * c0.y + a * c1.y, oa * c0.z + a * c1.z, oa * c0.w + a * c1.w);
+    int i, a;
+    split_hw(u, n << 8, i, a);
+    const float4 c0 = tab[i], c1 = tab[min(i + 1, n - 1)];
+    const float w0 = (float)(256 - a) * (1.0f / 256.0f), w1 = (float)a * (1.0f / 256.0f);
+    return make_float4(w0 * c0.x + w1 * c1.x, w0 * c0.y + w1 * c1.y, w0 * c0.z + w1 * c1.z, w0 * c0.w + w1 * c1.w);
 }
 
+// Manual trilinear sample with the texture unit's eight integer weights (they always sum to
+// 256): split z, then x, then y, rounding half up on the branches the hardware rounds.
 __device__ __forceinline__ float sample_bricked(const RayArgs& A, float u, float v, float w) {
-    int i, j, k; float a, b, c;
-    split_linear(u * (float)A.W, i, a);
-    split_linear(v * (float)A.H, j, b);
-    split_linear(w * (float)A.D, k, c);
-    const int i0 = min(max(i, 0), A.W - 1), i1 = min(max(i + 1, 0), A.W - 1);
-    const int j0 = min(max(j, 0), A.H - 1), j1 = min(max(j + 1, 0), A.H - 1);
-    const int k0 = min(max(k, 0), A.D - 1), k1 = min(max(k + 1, 0), A.D - 1);
+    int i, j, k, a, b, c;
+    split_hw(u, A.W << 8, i, a);
+    split_hw(v, A.H << 8, j, b);
+    split_hw(w, A.D << 8, k, c);
+    const int i1 = min(i + 1, A.W - 1), j1 = min(j + 1, A.H - 1), k1 = min(k + 1, A.D - 1);
     const float* B = A.vol_brick;
-    const float t000 = __ldg(B + brick_index(i0, j0, k0, A.bW, A.bH));
-    const float t100 = __ldg(B + brick_index(i1, j0, k0, A.bW, A.bH));
-    const float t010 = __ldg(B + brick_index(i0, j1, k0, A.bW, A.bH));
-    const float t110 = __ldg(B + brick_index(i1, j1, k0, A.bW, A.bH));
-    const float t001 = __ldg(B + brick_index(i0, j0, k1, A.bW, A.bH));
-    const float t101 = __ldg(B + brick_index(i1, j0, k1, A.bW, A.bH));
-    const float t011 = __ldg(B + brick_index(i0, j1, k1, A.bW, A.bH));
+    const float t000 = __ldg(B + brick_index(i, j, k, A.bW, A.bH));
+    const float t100 = __ldg(B + brick_index(i1, j, k, A.bW, A.bH));
+    const float t010 = __ldg(B + brick_index(i, j1, k, A.bW, A.bH));
+    const float t110 = __ldg(B + brick_index(i1, j1, k, A.bW, A.bH));
+    const float t001 = __ldg(B + brick_index(i, j, k1, A.bW, A.bH));
+    const float t101 = __ldg(B + brick_index(i1, j, k1, A.bW, A.bH));
+    const float t011 = __ldg(B + brick_index(i, j1, k1, A.bW, A.bH));
     const float t111 = __ldg(B + brick_index(i1, j1, k1, A.bW, A.bH));
-    const float oa = 1.0f - a, ob = 1.0f - b, oc = 1.0f - c;
-    const float x00 = oa * t000 + a * t100, x10 = oa * t010 + a * t110;
-    const float x01 = oa * t001 + a * t101, x11 = oa * t011 + a * t111;
-    const float y0 = ob * x00 + b * x10, y1 = ob * x01 + b * x11;
-    return oc * y0 + c * y1;
+    const int z1 = c, z0 = 256 - c;
+    const int x10 = (z0 * a + 128) >> 8, x00 = z0 - x10;          // x-split of the lower z slice
+    const int x11 = (z1 * a + 128) >> 8, x01 = z1 - x11;          // ... and of the upper one
+    const int w000 = (x00 * (256 - b) + 128) >> 8, w010 = x00 - w000;
+    const int w110 = (x10 * b + 128) >> 8, w100 = x10 - w110;
+    const int w001 = (x01 * (256 - b) + 128) >> 8, w011 = x01 - w001;
+    const int w111 = (x11 * b + 128) >> 8, w101 = x11 - w111;
+    float acc = (float)w000 * t000;
+    acc = fmaf((float)w010, t010, acc);
+    acc = fmaf((float)w100, t100, acc);
+    acc = fmaf((float)w110, t110, acc);
+    acc = fmaf((float)w001, t001, acc);
+    acc = fmaf((float)w011, t011, acc);
+    acc = fmaf((float)w101, t101, acc);
+    acc = fmaf((float)w111, t111, acc);
+    return acc * (1.0f / 256.0f);
 }
 
 __device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a) {
@@ -188,6 +203,12 @@ __global__ void debug_sample_kernel(cudaTextureObject_t tex, const float* __rest
     if (i < n) out[i] = tex3D<float>(tex, uvw[3 * i], uvw[3 * i + 1], uvw[3 * i + 2]);
 }
 
+__global__ void debug_sample_tf_kernel(cudaTextureObject_t tex, const float* __restrict__ u, int n,
+                                       float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = tex1D<float4>(tex, u[i]);
+}
+
 template <int SAMPLER, int TFMODE>
 void launch_variant(bool count, int grid, cudaStream_t st, const RayArgs& A) {
     if (count) raycast_kernel<SAMPLER, TFMODE, true><<<grid, kBlock, 0, st>>>(A);
@@ -251,6 +272,14 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
 int launch_debug_sample(vrdd_context* c, cudaTextureObject_t tex, const float* d_uvw, int n, float* d_out) {
     if (n <= 0) return VRDD_OK;
     debug_sample_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(tex, d_uvw, n, d_out);
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+int launch_debug_sample_tf(vrdd_context* c, const float* d_u, int n, float* d_out4) {
+    if (n <= 0) return VRDD_OK;
+    debug_sample_tf_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->tf_tex, d_u, n, reinterpret_cast<float4*>(d_out4));
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;
