@@ -212,8 +212,10 @@ int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, i
 
 /* ---- diagnostics ------------------------------------------------------------------------ */
 
-/* Selects a kernel variant by name for A/B measurement ("decode_hist" -> "tma" | "ldg";
- * "raycast_tf" -> "texture" | "smem").  Unknown names return VRDD_ERR_INVALID. */
+/* Selects a kernel variant by name for A/B measurement: "decode_hist" -> "tma" | "ldg";
+ * "decode_order" -> "chunked" | "interleaved"; "raycast_tf" -> "texture" | "smem";
+ * "raycast_unroll" -> "1" | "2" | "4" | "8" (ray-march steps whose fetches are in flight
+ * together).  Results do not depend on the variant.  Unknown names return VRDD_ERR_INVALID. */
 int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);
 /* Samples the texture unit: out[i] = tex3D(plane `comp` of `source`, u[i], v[i], w[i]) with
  * the ray caster's texture object.  For the filter-model conformance test.  Device ptrs. */

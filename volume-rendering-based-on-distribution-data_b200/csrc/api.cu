@@ -195,6 +195,7 @@ int vrdd_destroy(vrdd_handle h) {
     free_inputs(c);
     free_tf(c);
     if (c->d_samples) cudaFree(c->d_samples);
+    if (c->frame) cudaFree(c->frame);
     delete c;
     return VRDD_OK;
 }
@@ -508,15 +509,18 @@ int vrdd_render(vrdd_handle h, uint32_t* d_output, int image_w, int image_h, con
 int vrdd_render_host(vrdd_handle h, uint32_t* h_output, int image_w, int image_h, const vrdd_render_params* params) {
     CHECK_HANDLE(h);
     if (!h_output || image_w <= 0 || image_h <= 0) return fail(c, VRDD_ERR_INVALID, "render_host: bad image");
-    uint32_t* d_img = nullptr;
     const size_t bytes = sizeof(uint32_t) * (size_t)image_w * image_h;
-    VRDD_CUDA(c, cudaMallocAsync(reinterpret_cast<void**>(&d_img), bytes, c->stream));
-    int rc = vrdd_render(h, d_img, image_w, image_h, params, nullptr, 1);
+    if (c->frame_bytes < bytes) {                       // the frame buffer lives as long as the handle
+        if (c->frame) cudaFree(c->frame);
+        c->frame = nullptr; c->frame_bytes = 0;
+        VRDD_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->frame), bytes));
+        c->frame_bytes = bytes;
+    }
+    int rc = vrdd_render(h, c->frame, image_w, image_h, params, nullptr, 1);
     if (rc == VRDD_OK) {
-        cudaError_t e = cudaMemcpyAsync(h_output, d_img, bytes, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaMemcpyAsync(h_output, c->frame, bytes, cudaMemcpyDeviceToHost, c->stream);
         if (e != cudaSuccess) rc = fail_cuda(c, e, "render_host: read-back");
     }
-    cudaFreeAsync(d_img, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (rc == VRDD_OK && e != cudaSuccess) rc = fail_cuda(c, e, "render_host: synchronize");
     return rc;
@@ -581,6 +585,13 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         if (v == "tma") c->var_decode_hist = 0;
         else if (v == "ldg") c->var_decode_hist = 1;
         else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_hist is tma|ldg");
+    } else if (w == "decode_order") {
+        if (v == "interleaved") c->var_decode_order = 0;
+        else if (v == "chunked") c->var_decode_order = 1;
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_order is interleaved|chunked");
+    } else if (w == "raycast_unroll") {
+        if (v == "1" || v == "2" || v == "4" || v == "8") c->var_unroll = v[0] - '0';
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_unroll is 1|2|4|8");
     } else if (w == "raycast_tf") {
         if (v == "texture") c->var_tf = 0;
         else if (v == "smem") c->var_tf = 1;

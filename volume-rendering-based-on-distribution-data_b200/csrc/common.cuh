@@ -183,9 +183,14 @@ struct vrdd_context {
     unsigned long long* d_samples = nullptr;
     bool count_samples = false;
 
+    uint32_t* frame = nullptr;       // device frame of vrdd_render_host, kept between calls
+    size_t frame_bytes = 0;
+
     // kernel variants (vrdd_set_variant)
     int var_decode_hist = 0;         // 0 tma, 1 ldg
-    int var_tf = 0;                  // 0 texture, 1 smem
+    int var_decode_order = 1;        // tma tile order: 0 interleaved over CTAs, 1 one contiguous run per CTA (TLB-friendly, default)
+    int var_tf = 1;                  // 0 texture unit, 1 shared-memory table (default: frees the TEX pipe)
+    int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
     int var_fractal = 0;             // 0 dense
 };
 

@@ -49,7 +49,7 @@ __device__ __forceinline__ void finish_and_emit(const DecodeOut& out, long long 
 }
 
 __global__ void __launch_bounds__(kTmaThreads, 1)
-decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut out) {
+decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut out, int chunked) {
     extern __shared__ __align__(128) unsigned char smem[];
     float4* tiles = reinterpret_cast<float4*>(smem);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kTileBytes);
@@ -69,13 +69,21 @@ decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut
     __syncthreads();
 
     const long long ntiles = (nvox + kTileVox - 1) / kTileVox;
+    // tile order: interleaved (tile = cta + k*grid) or one contiguous run of tiles per CTA
+    long long t_begin = blockIdx.x, t_end = ntiles, t_step = gridDim.x;
+    if (chunked) {
+        const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+        t_begin = per * blockIdx.x;
+        t_end = (t_begin + per < ntiles) ? t_begin + per : ntiles;
+        t_step = 1;
+    }
 
     if (warp == kConsumerWarps) {
         // ---- producer: one lane issues the bulk copies ---------------------------------
         if (lane == 0) {
             int s = 0;
             uint32_t phase = 0;
-            for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (long long t = t_begin; t < t_end; t += t_step) {
                 mbar_wait(&empty[s], phase ^ 1u);
                 const long long v0 = t * kTileVox;
                 const long long rows = (nvox - v0 < kTileVox) ? (nvox - v0) : kTileVox;
@@ -100,7 +108,7 @@ decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut
     const float hb = 0.5f * bw;
     int s = 0;
     uint32_t phase = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (long long t = t_begin; t < t_end; t += t_step) {
         mbar_wait(&full[s], phase);
         const float4* row = tiles + ((size_t)s * kTileVox + tid) * (VRDD_BINS / 4);
         const long long v = t * kTileVox + tid;
@@ -208,7 +216,7 @@ int launch_decode_hist(vrdd_context* c, const float* d_hist, long long nvox, con
                                           (int)kTmaSmem));
         const long long ntiles = (nvox + kTileVox - 1) / kTileVox;
         const int grid = (int)((ntiles < c->num_sms) ? ntiles : c->num_sms);
-        decode_hist_tma_kernel<<<grid, kTmaThreads, kTmaSmem, c->stream>>>(d_hist, nvox, out);
+        decode_hist_tma_kernel<<<grid, kTmaThreads, kTmaSmem, c->stream>>>(d_hist, nvox, out, c->var_decode_order);
     } else {
         const long long nblk = (nvox + kLdgThreads - 1) / kLdgThreads;
         const long long cap = (long long)c->num_sms * 8;       // 8 x 256 threads resident per SM

@@ -114,7 +114,15 @@ __device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a
            ((uint32_t)(__saturatef(g) * 255.0f) << 8) | (uint32_t)(__saturatef(r) * 255.0f);
 }
 
-template <int SAMPLER, int TFMODE, bool COUNT>
+// The march is software-pipelined in batches of U steps.  A ray's sample positions follow
+// from geometry alone (pos += step, t += tstep, stop when t > tfar or after max_steps), so
+// the U volume fetches of a batch are issued back to back, then the U transfer-function
+// lookups, and only the compositing — with the reference's early exit at alpha > threshold
+// (:698) — is sequential.  Samples fetched beyond an early exit are discarded and never
+// counted, so images and sample counts are those of the step-by-step loop; what changes is
+// that U texture requests per thread are in flight instead of one (ncu: the one-step loop
+// idles on long-scoreboard stalls with the L1TEX pipe at 41 %).
+template <int SAMPLER, int TFMODE, bool COUNT, int U>
 __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
     __shared__ float4 tf_s[TFMODE == 1 ? VRDD_MAX_TF : 1];
     if (TFMODE == 1) {
@@ -164,25 +172,58 @@ __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
             float py = __fadd_rn(oy, __fmul_rn(dy, tnear));
             float pz = __fadd_rn(oz, __fmul_rn(dz, tnear));
             const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
-            for (int i = 0; i < A.max_steps; ++i) {                                  // :381
-                // pos*0.5 is exact, so fma == mul-then-add here
-                const float cu = fmaf(px, 0.5f, 0.5f), cv = fmaf(py, 0.5f, 0.5f), cw = fmaf(pz, 0.5f, 0.5f);
-                float s;
-                if (SAMPLER == 0) s = tex3D<float>(A.vol_tex, cu, cv, cw);           // :601-651
-                else s = sample_bricked(A, cu, cv, cw);
-                const float tu = (s - A.t_offset) * A.t_scale;                       // :683-684
-                float4 col;
-                if (TFMODE == 0) col = tex1D<float4>(A.tf_tex, tu);
-                else col = tf_lookup_smem(tf_s, A.tf_n, tu);
-                if (COUNT) ++nsamp;
-                col.w *= A.density;                                                  // :685
-                col.x *= col.w; col.y *= col.w; col.z *= col.w;                      // :691-693
-                const float k = 1.0f - sa;                                           // :695
-                sr += col.x * k; sg += col.y * k; sb += col.z * k; sa += col.w * k;
-                if (sa > A.thresh) break;                                            // :698
-                t = __fadd_rn(t, A.tstep);                                           // :701
-                if (t > tfar) break;                                                 // :703
-                px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);  // :706
+            int i = 0;
+            bool alive = A.max_steps > 0;                 // the geometric state (i, t, p) is a live step
+            while (alive) {
+                // -- geometry of the next U steps (:381, :701-706), exactly as the one-step loop
+                float cu[U], cv[U], cw[U];
+                bool valid[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    valid[k] = alive;
+                    // pos*0.5 is exact, so fma == mul-then-add here
+                    cu[k] = fmaf(px, 0.5f, 0.5f); cv[k] = fmaf(py, 0.5f, 0.5f); cw[k] = fmaf(pz, 0.5f, 0.5f);
+                    const float tn = __fadd_rn(t, A.tstep);
+                    const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
+                    if (cont) {
+                        t = tn; ++i;
+                        px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+                    }
+                    alive = cont;
+                }
+                // -- U volume fetches in flight (:601-651)
+                float s[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    s[k] = 0.f;
+                    if (valid[k]) {
+                        if (SAMPLER == 0) s[k] = tex3D<float>(A.vol_tex, cu[k], cv[k], cw[k]);
+                        else s[k] = sample_bricked(A, cu[k], cv[k], cw[k]);
+                    }
+                }
+                // -- U transfer-function lookups (:683-684)
+                float4 col[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    col[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid[k]) {
+                        const float tu = (s[k] - A.t_offset) * A.t_scale;
+                        if (TFMODE == 0) col[k] = tex1D<float4>(A.tf_tex, tu);
+                        else col[k] = tf_lookup_smem(tf_s, A.tf_n, tu);
+                    }
+                }
+                // -- front-to-back compositing, in order, with the early exit (:685-699)
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    if (!valid[k]) { alive = false; break; }
+                    if (COUNT) ++nsamp;
+                    float4 c = col[k];
+                    c.w *= A.density;
+                    c.x *= c.w; c.y *= c.w; c.z *= c.w;
+                    const float kk = 1.0f - sa;
+                    sr += c.x * kk; sg += c.y * kk; sb += c.z * kk; sa += c.w * kk;
+                    if (sa > A.thresh) { alive = false; break; }
+                }
             }
             A.out[(size_t)y * A.iw + x] =
                 pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);  // :713-716
@@ -209,10 +250,20 @@ __global__ void debug_sample_tf_kernel(cudaTextureObject_t tex, const float* __r
     if (i < n) out[i] = tex1D<float4>(tex, u[i]);
 }
 
+template <int SAMPLER, int TFMODE, int U>
+void launch_u(bool count, int grid, cudaStream_t st, const RayArgs& A) {
+    if (count) raycast_kernel<SAMPLER, TFMODE, true, U><<<grid, kBlock, 0, st>>>(A);
+    else raycast_kernel<SAMPLER, TFMODE, false, U><<<grid, kBlock, 0, st>>>(A);
+}
+
 template <int SAMPLER, int TFMODE>
-void launch_variant(bool count, int grid, cudaStream_t st, const RayArgs& A) {
-    if (count) raycast_kernel<SAMPLER, TFMODE, true><<<grid, kBlock, 0, st>>>(A);
-    else raycast_kernel<SAMPLER, TFMODE, false><<<grid, kBlock, 0, st>>>(A);
+void launch_variant(bool count, int grid, cudaStream_t st, const RayArgs& A, int unroll) {
+    switch (unroll) {
+        case 1: launch_u<SAMPLER, TFMODE, 1>(count, grid, st, A); break;
+        case 2: launch_u<SAMPLER, TFMODE, 2>(count, grid, st, A); break;
+        case 8: launch_u<SAMPLER, TFMODE, 8>(count, grid, st, A); break;
+        default: launch_u<SAMPLER, TFMODE, 4>(count, grid, st, A); break;
+    }
 }
 
 }  // namespace
@@ -259,10 +310,10 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
     if (sampler == VRDD_SAMPLER_TEXTURE && !A.vol_tex) return fail(c, VRDD_ERR_INVALID, "render: no texture volume");
     if (sampler == VRDD_SAMPLER_BRICKED && !A.vol_brick) return fail(c, VRDD_ERR_INVALID, "render: no bricked volume");
     if (sampler == VRDD_SAMPLER_TEXTURE) {
-        if (tfm == 0) launch_variant<0, 0>(count, (int)grid, c->stream, A);
-        else launch_variant<0, 1>(count, (int)grid, c->stream, A);
+        if (tfm == 0) launch_variant<0, 0>(count, (int)grid, c->stream, A, c->var_unroll);
+        else launch_variant<0, 1>(count, (int)grid, c->stream, A, c->var_unroll);
     } else {
-        launch_variant<1, 1>(count, (int)grid, c->stream, A);
+        launch_variant<1, 1>(count, (int)grid, c->stream, A, c->var_unroll);
     }
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
