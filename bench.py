@@ -7,9 +7,10 @@
 Workload (config.workload), all inputs synthetic and generated on the device
 (include/vrdd_synth.h):
   * decode: a VOL^3 distribution volume (default 1024^3 x 32 bins = 137 GB of raw
-    histograms) is decoded z-slab by z-slab; every slab is resident in HBM before its timed
-    region starts.  Reported in `decode` (GB/s against the measured HBM peak) together with
-    the fractal-code decode of the same volume.
+    histograms) is decoded z-slab by z-slab (default 256 slices = 34 GB per launch); every
+    slab is resident in HBM before its timed region starts.  Reported in `decode` and in
+    `roofline` (GB/s against the measured HBM peak), with the fractal-code decode of the same
+    volume next to it.
   * ray cast (the `metric`): a "step" renders one IMG x IMG view (default 1024^2) of the
     decoded volume with the reference's constants (tstep 0.01, 500 steps, threshold 0.95,
     density 0.05, rainbow transfer function, queryMethod 1), cycling through the 64-view orbit
@@ -19,23 +20,23 @@ Workload (config.workload), all inputs synthetic and generated on the device
     every GPU keeps IMG^2 pixels (weak scaling); every rank decodes VOL/N z-slices and the
     decoded planes are all-gathered (NCCL); partial frames are reduced to rank 0 (NCCL).
 Timing: CUDA events on the launching stream, >= 3 warm-up steps, barrier + synchronize on
-both sides, max over ranks.  The sampled volume (4.3 GB) and every decode slab (>= 8 GB) are
+both sides, max over ranks.  The sampled plane (4.3 GB) and every decode slab (>= 8 GB) are
 far larger than the 126 MB L2, so no L2 flush is needed between iterations.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-HIST_BYTES_PER_VOXEL = 128 + 12          # DESIGN.md: 32 fp32 bins read, three fp32 planes written
-SAMPLE_BYTES = 32                        # DESIGN.md: 8 fp32 texels per trilinear sample
+HIST_BYTES_PER_VOXEL = 128 + 12          # DESIGN.md §4: 32 fp32 bins read, three fp32 planes written
+SAMPLE_BYTES = 32                        # DESIGN.md §4: 8 fp32 texels per trilinear sample
 ORBIT_VIEWS = 64
 HBM_FALLBACK_GBS = 6650.0                # /opt/skills/guides/B200_PROFILING.md
 
@@ -43,9 +44,22 @@ HBM_FALLBACK_GBS = 6650.0                # /opt/skills/guides/B200_PROFILING.md
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return json.load(f), "measured"
+            return json.load(f), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
-        return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback"
+        return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel, bytes_per_launch):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json),
+    if that capture was taken on the same launch shape; else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(kernel)
+        if t and abs(t["algorithmic_bytes_per_launch"] - bytes_per_launch) < 1e-6 * bytes_per_launch:
+            return t["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -103,7 +117,7 @@ class ClockSampler:
 def orbit_view(V, k):
     """View k of the 64-view orbit: viewRotation.y = k * 5.625 deg, translation (0,0,-4)
     (volumeRender.cpp:126, 229-246)."""
-    return V.view_matrix(0.0, k * (360.0 / ORBIT_VIEWS), (0.0, 0.0, -4.0))
+    return V.view_matrix(0.0, (k % ORBIT_VIEWS) * (360.0 / ORBIT_VIEWS), (0.0, 0.0, -4.0))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -114,8 +128,7 @@ def cpu_decode_baseline(seed):
     """Raw-histogram decode on the host cores: a 256x256x64 slab of the same synthetic volume."""
     from oracle.vrdd_oracle import Oracle
     o = Oracle(fast=True)
-    dims = (256, 256, 256)
-    hist = o.synth_histograms(seed, dims, z0=96, nz=64)
+    hist = o.synth_histograms(seed, (256, 256, 256), z0=96, nz=64)
     best = 1e30
     for _ in range(3):
         t0 = time.perf_counter(); o.decode_hist(hist); best = min(best, time.perf_counter() - t0)
@@ -127,7 +140,7 @@ def cpu_decode_baseline(seed):
 
 class CpuRaycaster:
     """The oracle ray caster on a bounded volume: 256^3 decoded on the host, IMG^2 views of the
-    same orbit with the reference's constants (the sample count per view does not depend on
+    same orbit with the reference's constants (the sample count per view hardly depends on
     the volume resolution because tstep is fixed)."""
 
     def __init__(self, seed, img):
@@ -143,7 +156,7 @@ class CpuRaycaster:
         self.vol = vol
 
     def step(self, k):
-        view = self.o.view_matrix(0.0, k * (360.0 / ORBIT_VIEWS))
+        view = self.o.view_matrix(0.0, (k % ORBIT_VIEWS) * (360.0 / ORBIT_VIEWS))
         _, s = self.o.render(self.vol, self.dims, view, image=self.img)
         return s
 
@@ -152,25 +165,25 @@ def run_reference(args):
     """--impl reference: the reference's CPU path.  The reference itself cannot be compiled
     (CUDA 12.9 removed texture references), so this is the OpenMP oracle port
     with all host threads, on the same metric/config as our arm.  One step = one view."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     img = (args.image, args.image)
     rc = CpuRaycaster(args.seed, img)
-    for k in range(min(args.warmup, 2)):
+    warm = min(args.warmup, 2)
+    for k in range(warm):
         rc.step(k)
     steps = max(1, min(args.steps, 16))
     t0 = time.perf_counter()
-    samples = sum(rc.step(k) for k in range(steps))
+    samples = sum(rc.step(warm + k) for k in range(steps))
     dt = time.perf_counter() - t0
     val = samples / dt / 1e9
-    sample = f"{img[0]}x{img[1]} views of the 64-view orbit on a 256^3 decoded volume, {steps} views"
+    sample = f"{steps} {img[0]}x{img[1]} views of the 64-view orbit on a 256^3 volume decoded on the host"
     line = {"impl": "reference", "metric": "raycast_throughput", "value": val, "unit": "Gsamples/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt / steps * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": steps / dt,
             "config": {"workload": f"ray cast {img[0]}x{img[1]} orbit views, reference constants (tstep 0.01, 500 steps, "
-                                   "threshold 0.95), CPU oracle on a bounded 256^3 volume"},
+                                   "threshold 0.95), OpenMP port of the reference's d_render on a bounded 256^3 volume"},
             "cpu_baseline": {"value": val, "unit": "Gsamples/s", "cores": rc.o.num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": val, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -187,6 +200,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import vrdd_b200 as V
+    import vrdd_b200.dist as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -197,21 +211,25 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    peaks, peak_kind = measured_peaks()
+    peaks, peak_src = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
 
-    vol = args.volume
-    W = H = D = vol
+    W = H = Dz = args.volume
+    slice_vox = W * H
+    total_vox = slice_vox * Dz
     r = V.Renderer(local)
     r.set_stream(torch.cuda.current_stream().cuda_stream)
     r.set_sampler(V.SAMPLER_TEXTURE if args.sampler == "texture" else V.SAMPLER_BRICKED)
     if args.tf:
         r.set_variant("raycast_tf", args.tf)
+    if args.unroll:
+        r.set_variant("raycast_unroll", str(args.unroll))
     r.set_variant("decode_hist", args.decode_variant)
     if world > 1:
         r.keep_linear_planes(True)
-    r.set_volume(W, H, D)
-    slice_vox = W * H
+    r.set_volume(W, H, Dz)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if world > 1:
@@ -229,51 +247,53 @@ def run_ours(args):
     clocks.start()
     launches0 = r.kernel_launches()
 
-    # ---- P1: decode my z-range slab by slab -------------------------------------------------
-    z_lo, z_hi = D * rank // world, D * (rank + 1) // world
+    # ---- P1a: raw-histogram decode of my z-range, slab by slab -------------------------------
+    z_lo, z_hi = D.slab_range(Dz, rank, world)
     slab = max(1, min(args.slab_z, z_hi - z_lo))
-    hist_buf = torch.empty(slab * slice_vox * 32, dtype=torch.float32, device=dev)
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    dec_ms, dec_launches, dec_vox = 0.0, 0, 0
+    n_slabs = (z_hi - z_lo + slab - 1) // slab
     reps = max(1, args.decode_reps)
+    hist_buf = torch.empty(slab * slice_vox * 32, dtype=torch.float32, device=dev)
+    dec_ms = 0.0
     for z0 in range(z_lo, z_hi, slab):
         nz = min(slab, z_hi - z0)
-        r.synth_histograms_device(args.seed, z0, nz, hist_buf)
+        r.synth_histograms_device(args.seed, z0, nz, hist_buf)     # untimed: the slab is resident before timing
         r.set_histograms_device(hist_buf, z0, nz)
-        r.decode(V.SRC_ORIGINAL, z0, nz)                       # warm-up (also creates the arrays)
+        r.decode(V.SRC_ORIGINAL, z0, nz)                           # warm-up (also creates the arrays)
         barrier()
         e0, e1 = ev(), ev()
-        l0 = r.kernel_launches()
         e0.record()
         for _ in range(reps):
             r.decode(V.SRC_ORIGINAL, z0, nz)
         e1.record()
         torch.cuda.synchronize()
-        dec_launches += r.kernel_launches() - l0
         dec_ms += e0.elapsed_time(e1) / reps
-        dec_vox += nz * slice_vox
+    del hist_buf
+    torch.cuda.empty_cache()
+    my_dec_ms = dec_ms
     dec_ms = max_over_ranks(dec_ms)
-    total_vox = W * H * D
     dec_gbs = total_vox * HIST_BYTES_PER_VOXEL / (dec_ms * 1e-3) / 1e9
-    decode = {"kernel": "decode_hist_" + args.decode_variant, "voxels": total_vox, "ms": dec_ms,
+    decode = {"kernel": "decode_hist_" + args.decode_variant + "_kernel", "voxels": total_vox, "ms": dec_ms,
               "gbs": dec_gbs, "gvoxels_per_s": total_vox / (dec_ms * 1e-3) / 1e9,
-              "bytes_per_voxel": HIST_BYTES_PER_VOXEL, "slab_z": slab, "launch_ms": dec_ms * world / max(1, (D + slab - 1) // slab)}
+              "bytes_per_voxel": HIST_BYTES_PER_VOXEL, "slab_z": slab, "launches": n_slabs * world,
+              "peak_gbs": hbm_peak * world, "frac_of_hbm_peak": dec_gbs / (hbm_peak * world)}
+    launch_bytes = min(slab, z_hi - z_lo) * slice_vox * HIST_BYTES_PER_VOXEL
+    launch_ms = my_dec_ms * (min(slab, z_hi - z_lo) / (z_hi - z_lo))
+    roofline = {"kernel": decode["kernel"], "bound": "hbm", "achieved": launch_bytes / (launch_ms * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "launch_ms": launch_ms,
+                "bytes_per_launch": launch_bytes, "traffic": ncu_traffic(decode["kernel"], launch_bytes)}
+    roofline["frac"] = roofline["achieved"] / roofline["peak"]
 
-    # ---- P1b: fractal decode of the same volume (compact codes) -----------------------------
-    fr = None
+    # ---- P1b: fractal-code decode of the same volume (compact codes) --------------------------
     if args.fractal and world == 1:
         T, max_ne = 622, 8
-        del hist_buf
-        torch.cuda.empty_cache()
-        fslab = slab
-        nvs = fslab * slice_vox
+        nvs = slab * slice_vox
         cb = torch.empty(nvs * 4, dtype=torch.int32, device=dev)
         er = torch.empty(nvs * max_ne * 2, dtype=torch.float32, device=dev)
         off = torch.empty((nvs + 255) // 256 + 1, dtype=torch.int64, device=dev)
         tm = torch.empty(T * 32, dtype=torch.float32, device=dev)
         fr_ms, fr_bytes = 0.0, 0
-        for z0 in range(0, D, fslab):
-            nz = min(fslab, D - z0)
+        for z0 in range(0, Dz, slab):
+            nz = min(slab, Dz - z0)
             tot = r.synth_fractal_device(args.seed, T, max_ne, z0, nz, cb, er, off, tm)
             r.set_fractal_device(cb, er, off, tm, T, z0, nz)
             r.decode(V.SRC_FRACTAL, z0, nz)
@@ -285,124 +305,123 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize()
             fr_ms += e0.elapsed_time(e1) / reps
-            fr_bytes += nz * slice_vox * (16 + 12) + tot * 8
-        fr = {"kernel": "decode_fractal_dense", "ms": fr_ms, "gbs": fr_bytes / (fr_ms * 1e-3) / 1e9,
-              "frac_of_hbm_peak": fr_bytes / (fr_ms * 1e-3) / 1e9 / hbm_peak,
-              "gvoxels_per_s": total_vox / (fr_ms * 1e-3) / 1e9, "bytes_per_voxel": fr_bytes / total_vox,
-              "templates": T, "mean_ne": (fr_bytes / total_vox - 28) / 8}
+            fr_bytes += nz * slice_vox * (16 + 12) + tot * 8      # codebook + planes + 8 B per error
+        decode["fractal"] = {"kernel": "decode_fractal_" + args.fractal_variant + "_kernel", "ms": fr_ms,
+                             "gbs": fr_bytes / (fr_ms * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": fr_bytes / (fr_ms * 1e-3) / 1e9 / hbm_peak,
+                             "gvoxels_per_s": total_vox / (fr_ms * 1e-3) / 1e9, "bytes_per_voxel": fr_bytes / total_vox,
+                             "templates": T, "mean_ne": (fr_bytes / total_vox - 28) / 8}
         del cb, er, off, tm
-    else:
-        del hist_buf
-    torch.cuda.empty_cache()
+        torch.cuda.empty_cache()
 
-    # ---- replicate the decoded planes (N > 1): all-gather of z-slabs over NCCL ---------------
+    # ---- N > 1: replicate the decoded planes, one in-place all-gather per plane (NCCL) --------
     gather_ms = None
     if world > 1:
         planes = r.get_decoded_planes_device(V.SRC_ORIGINAL)
         barrier()
         e0, e1 = ev(), ev()
         e0.record()
-        for p in planes[:1] if args.gather_planes == 1 else planes:
-            full = V.as_torch(p, (D * slice_vox,))
-            mine = full[z_lo * slice_vox:z_hi * slice_vox]
-            if D % world == 0:
-                dist.all_gather_into_tensor(full, mine.clone())
-            else:
-                parts = [full[(D * q // world) * slice_vox:(D * (q + 1) // world) * slice_vox] for q in range(world)]
-                dist.all_gather(parts, mine.clone())
-        r.commit_planes(V.SRC_ORIGINAL, 0, D)
+        for p in planes:
+            D.allgather_plane(V.as_torch(p, (Dz * slice_vox,), device=dev), Dz, slice_vox, rank, world)
+        r.commit_planes(V.SRC_ORIGINAL, 0, Dz)
         e1.record()
         torch.cuda.synchronize()
         gather_ms = max_over_ranks(e0.elapsed_time(e1))
 
-    # ---- P2: ray casting ---------------------------------------------------------------------
-    # weak scaling: every GPU keeps IMG^2 pixels; the frame grows with N
-    fw = args.image * (2 if world in (2, 8) else 1) * (2 if world >= 4 else 1)
-    fh = args.image * (2 if world >= 4 else 1)
-    if world not in (1, 2, 4, 8):
-        fw, fh = args.image * world, args.image
-    part = V.TilePartition(64, 64, rank, world)
-    params = V.default_render_params(query_method=1)
+    # ---- P2: ray casting -----------------------------------------------------------------------
+    fw, fh = D.frame_size(args.image, world)
+    part = V.TilePartition(D.TILE, D.TILE, rank, world) if world > 1 else None
     img = torch.zeros(fh, fw, dtype=torch.int32, device=dev)
     red = torch.zeros_like(img) if world > 1 else None
 
-    def render_step(k, e2e_host=None):
-        r.set_view(orbit_view(V, k % ORBIT_VIEWS))
-        r.render(img, fw, fh, params, part=part if world > 1 else None, clear_misses=True)
+    def render_step(k, params):
+        r.set_view(orbit_view(V, k))
+        r.render(img, fw, fh, params, part=part, clear_misses=True)
         if world > 1:
-            red.copy_(img)
-            dist.reduce(red, dst=0, op=dist.ReduceOp.SUM)
+            D.reduce_frame(img, red, dst=0)
 
-    # exact sample counts per view (untimed)
-    r.count_samples(True)
-    counts = []
-    for k in range(ORBIT_VIEWS if args.steps >= ORBIT_VIEWS else min(ORBIT_VIEWS, args.warmup + args.steps)):
-        render_step(k)
-        counts.append(r.get_sample_count())
-    r.count_samples(False)
-    if world > 1:
-        t = torch.tensor(counts, dtype=torch.int64, device=dev)
-        dist.all_reduce(t)
-        counts = [int(x) for x in t.tolist()]
+    def count_samples(params, nviews):
+        r.count_samples(True)
+        counts = []
+        for k in range(nviews):
+            r.set_view(orbit_view(V, k))
+            r.render(img, fw, fh, params, part=part, clear_misses=True)
+            counts.append(r.get_sample_count())
+        r.count_samples(False)
+        if world > 1:
+            t = torch.tensor(counts, dtype=torch.int64, device=dev)
+            dist.all_reduce(t)
+            counts = [int(x) for x in t.tolist()]
+        return counts
 
-    for k in range(args.warmup):
-        render_step(k)
-    barrier()
-    l0 = r.kernel_launches()
-    e0, e1 = ev(), ev()
-    e0.record()
-    for k in range(args.warmup, args.warmup + args.steps):
-        render_step(k)
-    e1.record()
-    barrier()
-    ray_launches = r.kernel_launches() - l0
-    ray_ms = max_over_ranks(e0.elapsed_time(e1))
-    samples = sum(counts[k % len(counts)] for k in range(args.warmup, args.warmup + args.steps))
+    def time_render(params, steps, warmup, with_reduce=True):
+        for k in range(warmup):
+            render_step(k, params) if with_reduce else (r.set_view(orbit_view(V, k)),
+                                                        r.render(img, fw, fh, params, part=part, clear_misses=True))
+        barrier()
+        l0 = r.kernel_launches()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for k in range(warmup, warmup + steps):
+            if with_reduce:
+                render_step(k, params)
+            else:
+                r.set_view(orbit_view(V, k))
+                r.render(img, fw, fh, params, part=part, clear_misses=True)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), r.kernel_launches() - l0
+
+    params = V.default_render_params(query_method=1)
+    nviews = min(ORBIT_VIEWS, args.warmup + args.steps)
+    counts = count_samples(params, nviews)
+    steps_samples = lambda c, w, s: sum(c[k % len(c)] for k in range(w, w + s))
+    ray_ms, ray_launches = time_render(params, args.steps, args.warmup)
+    samples = steps_samples(counts, args.warmup, args.steps)
     gsamples = samples / (ray_ms * 1e-3) / 1e9
     ms_per_step = ray_ms / args.steps
+    kernel_ms, _ = time_render(params, args.steps, 0, with_reduce=False)      # ray-cast kernel alone
+    kernel_ms /= args.steps
 
-    # kernel-only duration of the ray caster (no reduce), for the roofline block
-    barrier()
-    e0, e1 = ev(), ev()
-    e0.record()
-    for k in range(args.warmup, args.warmup + args.steps):
-        r.set_view(orbit_view(V, k % ORBIT_VIEWS))
-        r.render(img, fw, fh, params, part=part if world > 1 else None, clear_misses=True)
-    e1.record()
-    torch.cuda.synchronize()
-    ray_kernel_ms = e0.elapsed_time(e1) / args.steps
+    # resolution-matched step: tstep = 2/N so the volume is sampled once per voxel
+    matched = None
+    if args.matched and world == 1:
+        mp_ = V.default_render_params(query_method=1, tstep=2.0 / args.volume,
+                                      max_steps=int(math.ceil(math.sqrt(3.0) * args.volume)) + 1)
+        msteps = min(args.steps, 16)
+        mcounts = count_samples(mp_, min(ORBIT_VIEWS, args.warmup + msteps))
+        m_ms, _ = time_render(mp_, msteps, args.warmup)
+        ms_ = steps_samples(mcounts, args.warmup, msteps)
+        matched = {"tstep": 2.0 / args.volume, "max_steps": mp_.max_steps, "gsamples_per_s": ms_ / (m_ms * 1e-3) / 1e9,
+                   "ms_per_step": m_ms / msteps, "fps": msteps / (m_ms * 1e-3), "samples_per_frame": ms_ / msteps}
 
-    # ---- end to end through the C ABI with host buffers (rank-local frame) -------------------
+    # ---- end to end through the C ABI with host buffers --------------------------------------
     host_img = torch.empty(fh, fw, dtype=torch.int32).pin_memory()
-    e2e = None
     if world == 1:
-        for k in range(min(3, args.warmup)):
+        for k in range(3):
             r.set_view(orbit_view(V, k)); r.render_host(host_img, fw, fh, params)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for k in range(args.warmup, args.warmup + args.steps):
-            r.set_view(orbit_view(V, k % ORBIT_VIEWS))          # copyInvViewMatrix: 48 B host -> kernel parameters
-            r.render_host(host_img, fw, fh, params)             # render + D2H of the frame + synchronize
+            r.set_view(orbit_view(V, k))                         # copyInvViewMatrix: 48 B host -> kernel parameters
+            r.render_host(host_img, fw, fh, params)              # render + D2H of the frame + synchronize
         dt = time.perf_counter() - t0
-        e2e = {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48 + 32,
-               "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt,
-               "call": "vrdd_set_view + vrdd_render_host (render, device->pinned-host frame copy, synchronize)"}
+        call = "vrdd_set_view + vrdd_render_host (render, device->pinned-host frame copy, synchronize)"
     else:
         barrier()
         t0 = time.perf_counter()
         for k in range(args.warmup, args.warmup + args.steps):
-            render_step(k)
+            render_step(k, params)
             if rank == 0:
                 host_img.copy_(red, non_blocking=True)
             torch.cuda.synchronize()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48 + 32,
-               "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt,
-               "call": "vrdd_set_view + vrdd_render (tiles) + NCCL reduce to rank 0 + device->pinned-host frame copy"}
+        call = "vrdd_set_view + vrdd_render (my tiles) + NCCL reduce to rank 0 + device->pinned-host frame copy"
+    e2e = {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48 + 32,
+           "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt, "call": call}
 
     # ---- decode end to end from HOST memory (upload inside the timed region) ------------------
-    dec_e2e = None
     if world == 1 and args.e2e_decode_z > 0:
         r2 = V.Renderer(local)
         ez = args.e2e_decode_z
@@ -413,77 +432,62 @@ def run_ours(args):
         h_hist = torch.empty(ez * slice_vox * 32, dtype=torch.float32).pin_memory()
         h_hist.copy_(tmp)
         del tmp
-        h_out = np.empty((ez * slice_vox, 4), np.float32)
         best = 1e30
-        for _ in range(2):
+        for _ in range(3):
             t0 = time.perf_counter()
             r2.set_histograms_host(h_hist)                      # initCuda: H2D of the histograms
             r2.decode(V.SRC_ORIGINAL)                           # basicDataProcessing
             r2.synchronize()
             best = min(best, time.perf_counter() - t0)
         nv = ez * slice_vox
-        dec_e2e = {"value": nv * HIST_BYTES_PER_VOXEL / best / 1e9, "unit": "GB/s", "h2d_bytes": nv * 128,
-                   "sample": f"{W}x{H}x{ez} slab from pinned host memory: vrdd_set_histograms_host + vrdd_decode + sync"}
+        decode["e2e"] = {"value": nv * HIST_BYTES_PER_VOXEL / best / 1e9, "unit": "GB/s", "h2d_bytes": nv * 128,
+                         "sample": f"{W}x{H}x{ez} slab from pinned host memory: vrdd_set_histograms_host + "
+                                   "vrdd_decode + synchronize, best of 3"}
         r2.close()
-        del h_hist, h_out
+        del h_hist
 
     clk = clocks.stop()
     total_launches = r.kernel_launches() - launches0
 
     # ---- CPU baselines (rank 0, N = 1) ---------------------------------------------------------
-    cpu_ray = cpu_dec = None
+    cpu_ray = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu_dec = cpu_decode_baseline(args.seed)
+        decode["cpu_baseline"] = cpu_decode_baseline(args.seed)
         rc = CpuRaycaster(args.seed, (args.image, args.image))
         rc.step(0)
         t0 = time.perf_counter()
-        s_cpu = sum(rc.step(k) for k in range(3))
+        s_cpu = sum(rc.step(k) for k in range(1, 4))
         dt = time.perf_counter() - t0
         cpu_ray = {"value": s_cpu / dt / 1e9, "unit": "Gsamples/s", "cores": rc.o.num_threads(), "kind": "port",
-                   "sample": f"3 {args.image}x{args.image} orbit views on a 256^3 decoded volume (same constants; "
-                             "sample count per view is independent of volume resolution)", "fps": 3 / dt}
+                   "sample": f"3 {args.image}x{args.image} orbit views on a 256^3 volume decoded on the host (same "
+                             "constants), OpenMP oracle -O3 -march=x86-64-v3", "fps": 3 / dt}
 
     if rank == 0:
-        decode["frac_of_hbm_peak"] = dec_gbs / (hbm_peak * world)
-        decode["peak_gbs"] = hbm_peak * world
-        if cpu_dec:
-            decode["cpu_baseline"] = cpu_dec
-        if dec_e2e:
-            decode["e2e"] = dec_e2e
-        if fr:
-            decode["fractal"] = fr
-        per_launch_vox = (slab * slice_vox)
-        per_launch_ms = dec_ms * world / max(1, ((z_hi - z_lo) + slab - 1) // slab) / world if world == 1 else None
-        n_slabs = ((z_hi - z_lo) + slab - 1) // slab
-        launch_ms = dec_ms / n_slabs
-        roofline = {"kernel": decode["kernel"], "bound": "hbm",
-                    "achieved": per_launch_vox * HIST_BYTES_PER_VOXEL / (launch_ms * 1e-3) / 1e9,
-                    "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"
-                    if peak_kind == "measured" else "fallback (B200_PROFILING.md)",
-                    "traffic": None, "launch_ms": launch_ms, "bytes_per_launch": per_launch_vox * HIST_BYTES_PER_VOXEL}
-        roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        my_samples = samples / world
+        my_samples = samples / world / args.steps
         roofline_ray = {"kernel": "raycast_kernel", "bound": "l1tex",
-                        "achieved": my_samples / args.steps * SAMPLE_BYTES / (ray_kernel_ms * 1e-3) / 1e9,
-                        "unit": "GB/s", "launch_ms": ray_kernel_ms,
-                        "hbm_frac_if_every_sample_missed": my_samples / args.steps * SAMPLE_BYTES /
-                        (ray_kernel_ms * 1e-3) / 1e9 / hbm_peak,
-                        "note": "algorithmic 32 B per trilinear sample (8 fp32 texels) / kernel time; served by "
-                                "L1TEX/L2, see profiles/ for dram bytes"}
+                        "achieved": my_samples * SAMPLE_BYTES / (kernel_ms * 1e-3) / 1e9, "unit": "GB/s",
+                        "launch_ms": kernel_ms, "gsamples_per_s_kernel_only": my_samples / (kernel_ms * 1e-3) / 1e9,
+                        "vs_hbm_peak": my_samples * SAMPLE_BYTES / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                        "note": "algorithmic 32 B per trilinear sample (8 fp32 texels) / kernel time; the texels are "
+                                "served by L1TEX/L2 (ncu: profiles/), so this is not an HBM fraction"}
         line = {"metric": "raycast_throughput", "value": gsamples, "unit": "Gsamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "fps": 1e3 / ms_per_step, "samples_per_frame": samples / args.steps,
-                "config": {"workload": f"{vol}^3 distribution volume (32 bins) decoded on device, ray cast "
+                "config": {"workload": f"{args.volume}^3 distribution volume (32 bins) decoded on device, ray cast "
                                        f"{fw}x{fh} per step over the 64-view orbit, reference constants "
                                        "(tstep 0.01, 500 steps, threshold 0.95, density 0.05, queryMethod 1)",
-                           "volume": [W, H, D], "image": [fw, fh], "sampler": args.sampler,
-                           "partition": "single GPU" if world == 1 else f"64x64 image tiles round-robin over {world} ranks; "
-                           "z-slab decode + NCCL all-gather of planes; NCCL reduce of frames to rank 0",
-                           "l2": "inputs larger than L2 (4.3 GB sampled plane, >= 8 GB decode slabs); no flush"},
+                           "volume": [W, H, Dz], "image": [fw, fh], "sampler": args.sampler,
+                           "partition": "single GPU" if world == 1 else
+                           f"64x64 image tiles round-robin over {world} ranks; z-slab decode + NCCL all-gather of the "
+                           "decoded planes; NCCL reduce of frames to rank 0",
+                           "l2": f"inputs larger than L2 ({total_vox * 4 / 1e9:.1f} GB sampled plane, "
+                                 f"{launch_bytes / 1e9:.1f} GB per decode launch); no flush"},
                 "decode": decode, "roofline": roofline, "roofline_raycast": roofline_ray,
                 "e2e": e2e, "gpu_launches": int(ray_launches), "gpu_launches_total": int(total_launches),
                 "clocks": clk}
+        if matched:
+            line["raycast_resolution_matched"] = matched
         if gather_ms is not None:
             line["allgather_planes_ms"] = gather_ms
         if cpu_ray:
@@ -501,22 +505,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--volume", type=int, default=1024, help="distribution volume edge (voxels)")
-    ap.add_argument("--image", type=int, default=1024, help="pixels per GPU edge")
+    ap.add_argument("--image", type=int, default=1024, help="frame edge per GPU (pixels)")
     ap.add_argument("--slab-z", type=int, default=256, help="z-slices decoded per launch (256 -> 34 GB of histograms)")
     ap.add_argument("--decode-reps", type=int, default=3)
     ap.add_argument("--decode-variant", default="tma", choices=["tma", "ldg"])
+    ap.add_argument("--fractal-variant", default="dense")
     ap.add_argument("--sampler", default="texture", choices=["texture", "bricked"])
     ap.add_argument("--tf", default=None, choices=[None, "texture", "smem"])
+    ap.add_argument("--unroll", type=int, default=0, choices=[0, 1, 2, 4, 8])
     ap.add_argument("--fractal", type=int, default=1)
-    ap.add_argument("--gather-planes", type=int, default=3)
+    ap.add_argument("--matched", type=int, default=1)
     ap.add_argument("--e2e-decode-z", type=int, default=8, help="z-slices of the host-memory decode leg (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     else:
+        args.warmup = max(args.warmup, 3)
         run_ours(args)
 
 
