@@ -225,6 +225,7 @@ def run_ours(args):
     if args.unroll:
         r.set_variant("raycast_unroll", str(args.unroll))
     r.set_variant("decode_hist", args.decode_variant)
+    r.set_variant("decode_fractal", args.fractal_variant)
     if world > 1:
         r.keep_linear_planes(True)
     r.set_volume(W, H, Dz)
@@ -289,7 +290,7 @@ def run_ours(args):
         nvs = slab * slice_vox
         cb = torch.empty(nvs * 4, dtype=torch.int32, device=dev)
         er = torch.empty(nvs * max_ne * 2, dtype=torch.float32, device=dev)
-        off = torch.empty((nvs + 255) // 256 + 1, dtype=torch.int64, device=dev)
+        off = torch.empty((nvs + V.ERR_CHUNK - 1) // V.ERR_CHUNK + 1, dtype=torch.int64, device=dev)
         tm = torch.empty(T * 32, dtype=torch.float32, device=dev)
         fr_ms, fr_bytes = 0.0, 0
         for z0 in range(0, Dz, slab):
@@ -509,7 +510,7 @@ def main():
     ap.add_argument("--slab-z", type=int, default=256, help="z-slices decoded per launch (256 -> 34 GB of histograms)")
     ap.add_argument("--decode-reps", type=int, default=3)
     ap.add_argument("--decode-variant", default="tma", choices=["tma", "ldg"])
-    ap.add_argument("--fractal-variant", default="dense")
+    ap.add_argument("--fractal-variant", default="moments", choices=["moments", "dense"])
     ap.add_argument("--sampler", default="texture", choices=["texture", "bricked"])
     ap.add_argument("--tf", default=None, choices=[None, "texture", "smem"])
     ap.add_argument("--unroll", type=int, default=0, choices=[0, 1, 2, 4, 8])

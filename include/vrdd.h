@@ -126,8 +126,8 @@ int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* e
                           const float* templates, int num_templates);
 /* Compact device-resident form for slab streaming:
  *   d_codebook: int32[nvox][4];  d_errors: float[total_ne][2] in voxel order;
- *   d_chunk_offsets: uint64[ceil(nvox/256)+1], entry c = index into d_errors of the first
- *   error of voxel 256*c (exclusive prefix sum of NE taken every 256 voxels);
+ *   d_chunk_offsets: uint64[ceil(nvox/32)+1], entry c = index into d_errors of the first
+ *   error of voxel 32*c (exclusive prefix sum of NE taken every 32 voxels, one per warp);
  *   d_templates: float[num_templates][bins].  Covers z-slices [z0, z0+nz). */
 int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const float* d_errors,
                             const uint64_t* d_chunk_offsets, const float* d_templates,
@@ -213,7 +213,8 @@ int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, i
 /* ---- diagnostics ------------------------------------------------------------------------ */
 
 /* Selects a kernel variant by name for A/B measurement: "decode_hist" -> "tma" | "ldg";
- * "decode_order" -> "chunked" | "interleaved"; "raycast_tf" -> "texture" | "smem";
+ * "decode_order" -> "chunked" | "interleaved"; "decode_fractal" -> "moments" | "dense";
+ * "raycast_tf" -> "texture" | "smem";
  * "raycast_unroll" -> "1" | "2" | "4" | "8" (ray-march steps whose fetches are in flight
  * together).  Results do not depend on the variant.  Unknown names return VRDD_ERR_INVALID. */
 int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);

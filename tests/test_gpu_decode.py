@@ -113,12 +113,16 @@ def _from_device_ptr(ptr, n):
     return V.as_torch(ptr, (n,)).cpu().numpy()
 
 
-def test_fractal_decode_matches_golden_and_is_bit_exact_in_its_integer_part(renderer, golden):
+@pytest.mark.parametrize("variant", ["moments", "dense"])
+def test_fractal_decode_matches_golden_and_is_bit_exact_in_its_integer_part(renderer, golden, variant):
+    """The golden codes include shift == 32, flip + shift, NE == 0, a clamp to zero and a bin hit
+    three times (the moments variant must fall back to the ordered dense route there)."""
     import torch
     import vrdd_b200 as V
     dims = tuple(int(v) for v in golden["dims"])
     n = dims[0] * dims[1] * dims[2]
     r = renderer
+    r.set_variant("decode_fractal", variant)
     r.set_volume(*dims)
     r.set_fractal_host(golden["codebook"], golden["errors"], golden["templates"])
     recon = torch.empty(n, 32, dtype=torch.float32, device="cuda")
@@ -130,19 +134,27 @@ def test_fractal_decode_matches_golden_and_is_bit_exact_in_its_integer_part(rend
     np.testing.assert_allclose(got, golden["decoded_fractal"], rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("variant", ["moments", "dense"])
 @pytest.mark.parametrize("dims,T,max_ne", [((1, 1, 1), 3, 8), ((30, 9, 2), 622, 8), ((50, 50, 10), 622, 8),
                                             ((64, 32, 5), 100, 32), ((16, 16, 4), 1500, 0)])
-def test_fractal_decode_matches_oracle(renderer, oracle, dims, T, max_ne):
+def test_fractal_decode_matches_oracle(renderer, oracle, dims, T, max_ne, variant):
     """Ragged sizes, the reference's 50x50x10 / 622 templates, NE up to 32 (error staging
     overflow path), NE == 0, and a template table too large for shared memory."""
     import torch
     import vrdd_b200 as V
     tmpl = oracle.synth_templates(4, T)
     cb, err = oracle.synth_fractal(4, dims, T=T, max_ne=max_ne)
+    rng = np.random.default_rng(11)
+    cb[:, 1] = rng.integers(0, 33, cb.shape[0])                       # every legal shift, 32 included
+    if max_ne >= 2:                                                   # a few voxels hit one bin twice
+        for v in range(0, cb.shape[0], 37):
+            if cb[v, 3] >= 2:
+                err[v, 1, 0] = err[v, 0, 0]
     ref, ref_recon, bad = oracle.decode_fractal(cb, err, tmpl, want_recon=True)
     assert bad == 0
     n = cb.shape[0]
     r = renderer
+    r.set_variant("decode_fractal", variant)
     r.set_volume(*dims)
     r.set_fractal_host(cb, err, tmpl)
     recon = torch.empty(n, 32, dtype=torch.float32, device="cuda")
@@ -203,7 +215,8 @@ def test_device_synth_is_bit_identical_to_host_synth(renderer, oracle):
     r.synchronize()
     assert np.array_equal(d.cpu().numpy(), oracle.synth_histograms(seed, dims, z0=3, nz=4))
     n = dims[0] * dims[1] * dims[2]
-    nch = (n + 255) // 256
+    import vrdd_b200 as V
+    nch = (n + V.ERR_CHUNK - 1) // V.ERR_CHUNK
     cb = torch.empty(n, 4, dtype=torch.int32, device="cuda")
     er = torch.empty(n * 8, 2, dtype=torch.float32, device="cuda")
     off = torch.empty(nch + 1, dtype=torch.int64, device="cuda")
@@ -217,9 +230,8 @@ def test_device_synth_is_bit_identical_to_host_synth(renderer, oracle):
     assert np.array_equal(er.cpu().numpy()[:tot], compact)
     offs = off.cpu().numpy()
     cum = np.concatenate([[0], np.cumsum(hcb[:, 3])])
-    assert np.array_equal(offs[:-1], cum[0:n:256]) and offs[-1] == tot
+    assert np.array_equal(offs[:-1], cum[0:n:V.ERR_CHUNK]) and offs[-1] == tot
     # and the compact device form decodes to the oracle's answer
-    import vrdd_b200 as V
     r.set_fractal_device(cb, er, off, tm, T, 0, dims[2])
     r.decode(V.SRC_FRACTAL)
     got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))

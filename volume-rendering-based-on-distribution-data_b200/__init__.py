@@ -22,7 +22,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_RANGE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 SRC_ORIGINAL, SRC_FRACTAL = 0, 1
 SAMPLER_TEXTURE, SAMPLER_BRICKED = 0, 1
-ERR_CHUNK = 256
+ERR_CHUNK = 32
 
 EXPORTS = [
     "vrdd_create", "vrdd_destroy", "vrdd_set_stream", "vrdd_synchronize", "vrdd_last_error",

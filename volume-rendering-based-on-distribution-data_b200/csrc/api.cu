@@ -45,6 +45,8 @@ void free_inputs(vrdd_context* c) {
     c->tmpl_owned = nullptr;
     c->hist = nullptr; c->cb = nullptr; c->errs = nullptr; c->err_off = nullptr; c->tmpl = nullptr;
     c->hist_nz = 0; c->fr_nz = 0; c->num_templates = 0;
+    if (c->tmpl_mom) cudaFree(c->tmpl_mom);
+    c->tmpl_mom = nullptr;
 }
 
 void free_tf(vrdd_context* c) {
@@ -117,6 +119,7 @@ DecodeOut make_decode_out(vrdd_context* c, int source, long long v_base) {
     o.W = c->W; o.H = c->H; o.D = c->D;
     o.v_base = v_base;
     o.bW = c->bW; o.bH = c->bH;
+    o.inv_wh = 1.0f / ((float)c->W * (float)c->H);
     return o;
 }
 
@@ -305,7 +308,7 @@ int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* e
     VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
     c->cb = c->cb_owned; c->errs = c->err_owned; c->err_off = c->off_owned; c->tmpl = c->tmpl_owned;
     c->num_templates = num_templates; c->fr_z0 = 0; c->fr_nz = c->D;
-    return VRDD_OK;
+    return build_template_moments(c, c->tmpl, num_templates);
 }
 
 int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const float* d_errors,
@@ -318,9 +321,12 @@ int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const floa
     if (((reinterpret_cast<uintptr_t>(d_codebook) | reinterpret_cast<uintptr_t>(d_templates)) & 15u) != 0 ||
         (reinterpret_cast<uintptr_t>(d_errors) & 7u) != 0)
         return fail(c, VRDD_ERR_INVALID, "set_fractal_device: misaligned pointer");
+    const bool same_table = c->tmpl == d_templates && c->num_templates == num_templates && c->tmpl_mom;
     c->cb = d_codebook; c->errs = d_errors; c->err_off = d_chunk_offsets; c->tmpl = d_templates;
     c->num_templates = num_templates; c->fr_z0 = z0; c->fr_nz = nz;
-    return VRDD_OK;
+    // slabs of one volume share the template table: its prefix moments are built once per pointer;
+    // call vrdd_set_fractal_device again with a different pointer (or after vrdd_set_volume) to rebuild
+    return same_table ? VRDD_OK : build_template_moments(c, d_templates, num_templates);
 }
 
 int vrdd_set_sampler(vrdd_handle h, int sampler) {
@@ -356,7 +362,7 @@ int vrdd_decode(vrdd_handle h, int source, int z0, int nz) {
         rc = launch_decode_hist(c, c->hist + local0 * c->B, nvox, out);
     } else {
         if (local0 % VRDD_ERR_CHUNK != 0)
-            return fail(c, VRDD_ERR_INVALID, "decode: fractal sub-slab must start on a 256-voxel boundary");
+            return fail(c, VRDD_ERR_INVALID, "decode: fractal sub-slab must start on a 32-voxel boundary");
         rc = launch_decode_fractal(c, c->cb + 4 * local0, c->errs, c->err_off + local0 / VRDD_ERR_CHUNK, c->tmpl,
                                    c->num_templates, nvox, out, nullptr);
     }
@@ -585,6 +591,10 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         if (v == "tma") c->var_decode_hist = 0;
         else if (v == "ldg") c->var_decode_hist = 1;
         else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_hist is tma|ldg");
+    } else if (w == "decode_fractal") {
+        if (v == "dense") c->var_fractal = 0;
+        else if (v == "moments") c->var_fractal = 1;
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal is dense|moments");
     } else if (w == "decode_order") {
         if (v == "interleaved") c->var_decode_order = 0;
         else if (v == "chunked") c->var_decode_order = 1;

@@ -9,7 +9,7 @@
 #include "../../include/vrdd.h"
 
 #define VRDD_BINS 32                 // volumeRender_kernel.cu:91 (nBins); the only supported value
-#define VRDD_ERR_CHUNK 256           // voxels per entry of the fractal error-offset table
+#define VRDD_ERR_CHUNK 32            // voxels per entry of the fractal error-offset table (one warp)
 #define VRDD_MAX_TF 1024             // transfer-function entries kept in shared memory
 
 // Dataset scale constants of the reference (volumeRender_kernel.cu:736, 758-759)
@@ -30,6 +30,7 @@ struct DecodeOut {
     int use_surf;
     long long v_base;                // global index of local voxel 0
     int bW, bH;                      // bricks per row / per slice (bricked layout)
+    float inv_wh;                    // 1 / (W*H), for the index split in emit_decoded
 };
 
 // Bricked layout for the manual sampler: 4x4x4-texel bricks, 256 B each (two 128-B lines),
@@ -49,9 +50,16 @@ __device__ __forceinline__ void emit_decoded(const DecodeOut& o, long long v_loc
         o.lin[0][gv] = mean; o.lin[1][gv] = var; o.lin[2][gv] = ent;
     }
     if (o.use_surf || o.brick[0]) {
+        // (x, y, z) of the voxel.  A 64-bit divide costs ~100 instructions per voxel, so z comes
+        // from a float estimate of gv / (W*H) corrected by at most one (exact for gv < 2^47).
         const long long wh = (long long)o.W * o.H;
-        const int z = (int)(gv / wh);
-        const int r = (int)(gv - (long long)z * wh);
+        int z = (int)((float)gv * o.inv_wh);
+        long long rem = gv - (long long)z * wh;
+        if (rem < 0) { --z; rem += wh; }
+        else if (rem >= wh) { ++z; rem -= wh; }
+        if (rem < 0) { --z; rem += wh; }
+        else if (rem >= wh) { ++z; rem -= wh; }
+        const int r = (int)rem;
         const int y = r / o.W;
         const int x = r - y * o.W;
         if (o.use_surf) {
@@ -166,6 +174,7 @@ struct vrdd_context {
     const float* tmpl = nullptr;
     int num_templates = 0;
     int fr_z0 = 0, fr_nz = 0;
+    double* tmpl_mom = nullptr;      // per-template prefix moments (decode_fractal "moments" variant)
 
     vrdd_decoded_volume vol[2];
     int sampler = VRDD_SAMPLER_TEXTURE;
@@ -191,7 +200,7 @@ struct vrdd_context {
     int var_decode_order = 1;        // tma tile order: 0 interleaved over CTAs, 1 one contiguous run per CTA (TLB-friendly, default)
     int var_tf = 1;                  // 0 texture unit, 1 shared-memory table (default: frees the TEX pipe)
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
-    int var_fractal = 0;             // 0 dense
+    int var_fractal = 1;             // 0 dense (O(B) per voxel), 1 moments (O(NE) per voxel, default)
 };
 
 namespace vrdd {
@@ -211,6 +220,7 @@ int ensure_volume_storage(vrdd_context* c, int source);
 int launch_decode_hist(vrdd_context* c, const float* d_hist, long long nvox, const DecodeOut& out);
 int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const float* errs, const uint64_t* off,
                           const float* tmpl, int T, long long nvox, const DecodeOut& out, float* d_recon);
+int build_template_moments(vrdd_context* c, const float* d_tmpl, int T);
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses);
 int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_hist);

@@ -36,12 +36,12 @@ __global__ void synth_templates_kernel(uint32_t seed, int T, float* out) {
     for (int i = 0; i < VRDD_BINS; ++i) out[(size_t)k * VRDD_BINS + i] = p[i];
 }
 
-// pass 1: codebook + number of errors per 256-voxel chunk
-__global__ void __launch_bounds__(VRDD_ERR_CHUNK)
+// pass 1: codebook + number of errors per 32-voxel chunk (one warp)
+constexpr int kSynthThreads = 256;
+__global__ void __launch_bounds__(kSynthThreads)
 synth_fractal_codes_kernel(uint32_t seed, int W, int H, int D, int T, int max_ne, int z0, long long nvox,
                            int4* codebook, unsigned int* chunk_ne) {
-    __shared__ int wsum[VRDD_ERR_CHUNK / 32];
-    const long long v = (long long)blockIdx.x * VRDD_ERR_CHUNK + threadIdx.x;
+    const long long v = (long long)blockIdx.x * kSynthThreads + threadIdx.x;
     int ne = 0;
     if (v < nvox) {
         const long long wh = (long long)W * H;
@@ -56,22 +56,16 @@ synth_fractal_codes_kernel(uint32_t seed, int W, int H, int D, int T, int max_ne
     }
     int s = ne;
     for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int w = 0; w < VRDD_ERR_CHUNK / 32; ++w) tot += wsum[w];
-        chunk_ne[blockIdx.x] = (unsigned int)tot;
-    }
+    const long long chunk = v / VRDD_ERR_CHUNK;
+    if ((threadIdx.x & 31) == 0 && chunk * VRDD_ERR_CHUNK < nvox) chunk_ne[chunk] = (unsigned int)s;
 }
 
 // pass 2: errors, compact, in voxel order
-__global__ void __launch_bounds__(VRDD_ERR_CHUNK)
+__global__ void __launch_bounds__(kSynthThreads)
 synth_fractal_errors_kernel(uint32_t seed, int W, int H, int D, int T, int max_ne, int z0, long long nvox,
                             const unsigned long long* chunk_off, float2* errs) {
-    __shared__ int wsum[VRDD_ERR_CHUNK / 32];
-    const long long v = (long long)blockIdx.x * VRDD_ERR_CHUNK + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long v = (long long)blockIdx.x * kSynthThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     int code[4] = {0, 0, 0, 0}, eb[VRDD_BINS];
     float ev[VRDD_BINS];
     if (v < nvox) {
@@ -87,11 +81,8 @@ synth_fractal_errors_kernel(uint32_t seed, int W, int H, int D, int T, int max_n
         const int n = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += n;
     }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += wsum[w];
-    const unsigned long long base = chunk_off[blockIdx.x] + (unsigned long long)(wbase + incl - ne);
+    if (v - lane >= nvox) return;
+    const unsigned long long base = chunk_off[v / VRDD_ERR_CHUNK] + (unsigned long long)(incl - ne);
     for (int k = 0; k < ne; ++k) errs[base + k] = make_float2((float)eb[k], ev[k]);
 }
 
@@ -116,7 +107,8 @@ int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int 
     synth_templates_kernel<<<(T + 127) / 128, 128, 0, c->stream>>>(seed, T, d_tmpl);
     unsigned int* d_chunk_ne = nullptr;
     VRDD_CUDA(c, cudaMalloc(&d_chunk_ne, sizeof(unsigned int) * nchunks));
-    synth_fractal_codes_kernel<<<(unsigned)nchunks, VRDD_ERR_CHUNK, 0, c->stream>>>(
+    const unsigned nblk = (unsigned)((nvox + kSynthThreads - 1) / kSynthThreads);
+    synth_fractal_codes_kernel<<<nblk, kSynthThreads, 0, c->stream>>>(
         seed, c->W, c->H, c->D, T, max_ne, z0, nvox, reinterpret_cast<int4*>(d_cb), d_chunk_ne);
     c->launches += 2;
     // exclusive scan of the per-chunk counts on the host (set-up path, not timed)
@@ -133,7 +125,7 @@ int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int 
     if (total_ne) *total_ne = run;
     VRDD_CUDA(c, cudaMemcpyAsync(d_off, off.data(), sizeof(uint64_t) * (nchunks + 1), cudaMemcpyHostToDevice,
                                  c->stream));
-    synth_fractal_errors_kernel<<<(unsigned)nchunks, VRDD_ERR_CHUNK, 0, c->stream>>>(
+    synth_fractal_errors_kernel<<<nblk, kSynthThreads, 0, c->stream>>>(
         seed, c->W, c->H, c->D, T, max_ne, z0, nvox, reinterpret_cast<const unsigned long long*>(d_off),
         reinterpret_cast<float2*>(d_err));
     c->launches += 1;
