@@ -55,8 +55,10 @@ typedef enum vrdd_source { VRDD_SRC_ORIGINAL = 0, VRDD_SRC_FRACTAL = 1 } vrdd_so
 typedef enum vrdd_sampler {
     VRDD_SAMPLER_TEXTURE = 0,   /* decoded planes live in 3-D cudaArrays; the texture unit
                                    filters (the reference's own path, :601-651) */
-    VRDD_SAMPLER_BRICKED = 1    /* decoded planes live in a bricked linear layout; manual
+    VRDD_SAMPLER_BRICKED = 1,   /* decoded planes live in a bricked linear layout; manual
                                    trilinear with the texture unit's 8-bit weights */
+    VRDD_SAMPLER_LINEAR = 2     /* decoded planes are kept as linear fp32 planes only (x fastest):
+                                   what the sort-last brick renderer samples */
 } vrdd_sampler;
 
 /* Ray-marching parameters.  Defaults = the reference's compile-time constants
@@ -194,6 +196,32 @@ int vrdd_render_host(vrdd_handle h, uint32_t* h_output, int image_w, int image_h
 int vrdd_count_samples(vrdd_handle h, int enable);
 int vrdd_get_sample_count(vrdd_handle h, int64_t* out, int reset);
 
+/* ---- sort-last rendering of a brick-decomposed volume (volumes larger than one GPU's HBM;
+ *      new work, the reference is single-GPU; scheme in csrc/sortlast.cu) ------------------------- */
+
+/* This handle's volume (vrdd_set_volume dims, VRDD_SAMPLER_LINEAR) is one brick of a larger one. */
+typedef struct vrdd_brick {
+    int gw, gh, gd;           /* size of the GLOBAL volume in voxels                                   */
+    int ox, oy, oz;           /* global voxel coordinate of this handle's voxel (0,0,0), ghost included */
+    float lo[3], hi[3];       /* this brick owns the samples with lo <= texture coordinate < hi per axis;
+                                 use -INFINITY / +INFINITY at the faces of the global volume.  The stored
+                                 voxels must cover [lo*N - 1.5, hi*N + 0.5] (one ghost voxel each side) */
+} vrdd_brick;
+
+/* Pass 1: alpha accumulated by this brick's own samples, float[image_h][image_w]. */
+int vrdd_render_brick_alpha(vrdd_handle h, float* d_alpha_seg, int image_w, int image_h,
+                            const vrdd_render_params* params, const vrdd_brick* brick);
+/* Alpha entering brick (qx,qy,qz) of a gx x gy x gz grid, from the gathered pass-1 images
+ * d_alpha_seg_all = float[gz][gy][gx][image_h][image_w] (brick index x fastest). */
+int vrdd_compose_alpha_in(vrdd_handle h, const float* d_alpha_seg_all, int gx, int gy, int gz, int qx, int qy,
+                          int qz, float* d_alpha_in, int image_w, int image_h);
+/* Pass 2: colour increments (dR, dG, dB, dA) of this brick, float4[image_h][image_w], starting
+ * from d_alpha_in with the reference's early exit on the global alpha. */
+int vrdd_render_brick_color(vrdd_handle h, const float* d_alpha_in, float* d_partial4, int image_w, int image_h,
+                            const vrdd_render_params* params, const vrdd_brick* brick);
+/* Sum of all bricks' increments -> RGBA8 frame (brightness, saturate, truncate, pack: :713-716). */
+int vrdd_pack_frame(vrdd_handle h, const float* d_sum4, uint32_t* d_output, int image_w, int image_h, float brightness);
+
 /* Host helper: the inverse view matrix the reference builds with OpenGL
  * (volumeRender.cpp:224-246): M = Rx(-rot_x) * Ry(-rot_y) * T(-trans), top three rows,
  * row-major.  Angles in degrees.  (0, 0, (0,0,-4)) is the self-test view (:1024-1043). */
@@ -204,6 +232,10 @@ void vrdd_view_matrix(float rot_x_deg, float rot_y_deg, float tx, float ty, floa
 /* Fills d_hist = float[nz*height*width][bins] with the seeded synthetic histograms of
  * z-slices [z0, z0+nz) of the handle's volume; bit-identical to the host generator. */
 int vrdd_synth_histograms_device(vrdd_handle h, uint32_t seed, int z0, int nz, float* d_hist);
+/* Same for a brick: the handle's volume is the sub-box at global voxel offset (ox,oy,oz) of a
+ * gw x gh x gd volume; fills local z-slices [z0, z0+nz) with the histograms of the GLOBAL voxels. */
+int vrdd_synth_histograms_region_device(vrdd_handle h, uint32_t seed, int gw, int gh, int gd, int ox, int oy,
+                                        int oz, int z0, int nz, float* d_hist);
 /* Fractal counterpart.  d_errors must hold max_ne*nvox entries; *total_ne (host) receives
  * the number actually written.  Synchronises. */
 int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, int max_ne, int z0,

@@ -1,0 +1,109 @@
+"""Sort-last rendering of a brick-decomposed volume (csrc/sortlast.cu), emulated on ONE GPU: the
+bricks of a 2x2x2 (and 2x1x1, 3x2x1) decomposition are rendered one after the other by separate
+handles, the collectives are played by torch ops, and the assembled frame must match the
+single-volume render and the oracle within +-1 LSB — including rays that terminate early."""
+import numpy as np
+import pytest
+
+gpu = pytest.mark.gpu
+
+
+def _lsb(a, b):
+    return np.abs(np.ascontiguousarray(a).view(np.uint8).astype(np.int16) -
+                  np.ascontiguousarray(b).view(np.uint8).astype(np.int16))
+
+
+def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full):
+    import torch
+    w, h = img
+    nb = grid[0] * grid[1] * grid[2]
+    handles, bricks = [], []
+    for b in range(nb):
+        q = (b % grid[0], (b // grid[0]) % grid[1], b // (grid[0] * grid[1]))
+        origin, size, lo, hi = D.brick_geometry(gdims, grid, q)
+        r = V.Renderer(0)
+        r.set_sampler(V.SAMPLER_LINEAR)
+        r.set_volume(*size)
+        # the brick's histograms: generated on the device from GLOBAL voxel coordinates
+        d_hist = torch.empty(size[0] * size[1] * size[2], 32, dtype=torch.float32, device="cuda")
+        r.synth_histograms_region_device(seed, gdims, origin, 0, size[2], d_hist)
+        r.synchronize()
+        sub = hist_full.reshape(gdims[2], gdims[1], gdims[0], 32)[origin[2]:origin[2] + size[2],
+                                                                 origin[1]:origin[1] + size[1],
+                                                                 origin[0]:origin[0] + size[0]].reshape(-1, 32)
+        assert np.array_equal(d_hist.cpu().numpy(), sub)          # brick == sub-box of the whole, bit for bit
+        r.set_histograms_device(d_hist, 0, size[2])
+        r.decode(V.SRC_ORIGINAL)
+        r.synchronize()
+        r.set_view(view)
+        br = V.Brick(gdims[0], gdims[1], gdims[2], origin[0], origin[1], origin[2], (V.C.c_float * 3)(*lo),
+                     (V.C.c_float * 3)(*hi))
+        handles.append((r, q)); bricks.append(br)
+    seg_all = torch.zeros(nb, h, w, dtype=torch.float32, device="cuda")
+    for b, (r, q) in enumerate(handles):
+        r.render_brick_alpha(seg_all[b], w, h, params, bricks[b])            # pass 1 (+ "all-gather")
+    total = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
+    samples = 0
+    for b, (r, q) in enumerate(handles):
+        a_in = torch.empty(h, w, dtype=torch.float32, device="cuda")
+        part = torch.empty(h, w, 4, dtype=torch.float32, device="cuda")
+        r.synchronize()
+        r.compose_alpha_in(seg_all, grid, q, a_in, w, h)
+        r.count_samples(True)
+        r.render_brick_color(a_in, part, w, h, params, bricks[b])            # pass 2
+        r.synchronize()
+        samples += r.get_sample_count()
+        total += part                                                        # "reduce (SUM)"
+    out = torch.zeros(h, w, dtype=torch.int32, device="cuda")
+    handles[0][0].pack_frame(total, out, w, h, params.brightness)
+    handles[0][0].synchronize()
+    for r, _ in handles:
+        r.close()
+    return out.cpu().numpy().view(np.uint32), samples
+
+
+@gpu
+@pytest.mark.parametrize("grid", [(2, 2, 2), (2, 1, 1), (3, 2, 1)])
+@pytest.mark.parametrize("rot", [(0.0, 0.0), (25.0, 40.0), (-35.0, 200.0), (90.0, 0.0)])
+def test_sortlast_matches_single_volume_and_oracle(oracle, grid, rot):
+    import vrdd_b200 as V
+    import vrdd_b200.dist as D
+    gdims, img, seed = (24, 20, 16), (96, 80), 31
+    hist = oracle.synth_histograms(seed, gdims)
+    vol = oracle.decode_hist(hist)
+    view = oracle.view_matrix(*rot)
+    for over in ({}, {"density": 0.3, "opacity_threshold": 0.8, "brightness": 1.3}):     # default, and heavy early exit
+        params = V.default_render_params(query_method=1, **over)
+        ref, ref_s = oracle.render(vol, gdims, view, image=img, density=params.density, brightness=params.brightness,
+                                   opacity_threshold=params.opacity_threshold)
+        got, s = _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist)
+        d = _lsb(got, ref)
+        assert d.max() <= 1, (grid, rot, over, int(d.max()), int((d > 1).sum()))
+        assert abs(s - ref_s) <= max(2, ref_s // 5000), (s, ref_s)
+        # single-volume GPU render of the same thing
+        r = V.Renderer(0)
+        r.set_volume(*gdims); r.set_histograms_host(hist); r.decode(V.SRC_ORIGINAL); r.set_view(view)
+        import torch
+        one = torch.zeros(img[1], img[0], dtype=torch.int32, device="cuda")
+        r.render(one, img[0], img[1], params, clear_misses=True); r.synchronize()
+        assert _lsb(got, one.cpu().numpy().view(np.uint32)).max() <= 1
+        r.close()
+
+
+def test_brick_geometry_partitions_the_volume():
+    import vrdd_b200.dist as D
+    for gdims, grid in (((24, 20, 16), (2, 2, 2)), ((2048, 2048, 2048), (2, 2, 2)), ((50, 50, 10), (3, 2, 1))):
+        owned = 0
+        for b in range(grid[0] * grid[1] * grid[2]):
+            q = (b % grid[0], (b // grid[0]) % grid[1], b // (grid[0] * grid[1]))
+            origin, size, lo, hi = D.brick_geometry(gdims, grid, q)
+            n = 1
+            for ax in range(3):
+                b0 = gdims[ax] * q[ax] // grid[ax]; b1 = gdims[ax] * (q[ax] + 1) // grid[ax]
+                assert origin[ax] == max(b0 - 1, 0) and origin[ax] + size[ax] == min(b1 + 1, gdims[ax])
+                assert (lo[ax] == float("-inf")) == (q[ax] == 0) and (hi[ax] == float("inf")) == (q[ax] == grid[ax] - 1)
+                n *= b1 - b0
+            owned += n
+        assert owned == gdims[0] * gdims[1] * gdims[2]
+    assert [D.brick_grid(n) for n in (1, 2, 4, 8)] == [(1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 2, 2)]
+    assert [D.brick_of_rank(r, (2, 2, 2)) for r in (0, 1, 2, 5, 7)] == [(0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 0, 1), (1, 1, 1)]

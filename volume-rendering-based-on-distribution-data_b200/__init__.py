@@ -21,7 +21,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_RANGE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 SRC_ORIGINAL, SRC_FRACTAL = 0, 1
-SAMPLER_TEXTURE, SAMPLER_BRICKED = 0, 1
+SAMPLER_TEXTURE, SAMPLER_BRICKED, SAMPLER_LINEAR = 0, 1, 2
 ERR_CHUNK = 32
 
 EXPORTS = [
@@ -33,6 +33,8 @@ EXPORTS = [
     "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_count_samples",
     "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
     "vrdd_set_variant", "vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function",
+    "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_render_brick_color", "vrdd_pack_frame",
+    "vrdd_synth_histograms_region_device",
 ]
 LEGACY_EXPORTS = ["initCuda", "basicDataProcessing", "dataProcessing", "copyInvViewMatrix", "render_kernel",
                   "setTextureFilterMode", "freeCudaBuffers", "vrdd_legacy_handle"]
@@ -54,6 +56,12 @@ class RenderParams(C.Structure):
 class TilePartition(C.Structure):
     """struct vrdd_tile_partition (include/vrdd.h)."""
     _fields_ = [("tile_w", C.c_int), ("tile_h", C.c_int), ("part", C.c_int), ("parts", C.c_int)]
+
+
+class Brick(C.Structure):
+    """struct vrdd_brick (include/vrdd.h)."""
+    _fields_ = [("gw", C.c_int), ("gh", C.c_int), ("gd", C.c_int), ("ox", C.c_int), ("oy", C.c_int), ("oz", C.c_int),
+                ("lo", C.c_float * 3), ("hi", C.c_float * 3)]
 
 
 class Extent(C.Structure):
@@ -116,6 +124,11 @@ def lib():
             "vrdd_set_variant": (i32, [vp, C.c_char_p, C.c_char_p]),
             "vrdd_debug_sample_texture": (i32, [vp, i32, i32, vp, i32, vp]),
             "vrdd_debug_sample_transfer_function": (i32, [vp, vp, i32, vp]),
+            "vrdd_render_brick_alpha": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
+            "vrdd_compose_alpha_in": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, i32]),
+            "vrdd_render_brick_color": (i32, [vp, vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
+            "vrdd_pack_frame": (i32, [vp, vp, vp, i32, i32, f32]),
+            "vrdd_synth_histograms_region_device": (i32, [vp, u32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
             # legacy surface (include/vrdd_legacy.h)
             "initCuda": (None, [vp, Extent, Extent, vp, Extent, vp, Extent, vp, Extent] + [vp] * 9),
             "basicDataProcessing": (None, []),
@@ -292,6 +305,25 @@ class Renderer:
                                                  _ptr(d_errors), _ptr(d_chunk_offsets), _ptr(d_templates),
                                                  C.byref(tot)))
         return int(tot.value)
+
+    # sort-last bricks
+    def synth_histograms_region_device(self, seed, gdims, origin, z0, nz, d_hist):
+        self._ck(lib().vrdd_synth_histograms_region_device(self._h, seed, gdims[0], gdims[1], gdims[2], origin[0],
+                                                           origin[1], origin[2], z0, nz, _ptr(d_hist)))
+
+    def render_brick_alpha(self, d_alpha_seg, w, h, params, brick):
+        self._ck(lib().vrdd_render_brick_alpha(self._h, _ptr(d_alpha_seg), w, h, C.byref(params), C.byref(brick)))
+
+    def compose_alpha_in(self, d_alpha_seg_all, grid, q, d_alpha_in, w, h):
+        self._ck(lib().vrdd_compose_alpha_in(self._h, _ptr(d_alpha_seg_all), grid[0], grid[1], grid[2], q[0], q[1], q[2],
+                                             _ptr(d_alpha_in), w, h))
+
+    def render_brick_color(self, d_alpha_in, d_partial4, w, h, params, brick):
+        self._ck(lib().vrdd_render_brick_color(self._h, _ptr(d_alpha_in), _ptr(d_partial4), w, h, C.byref(params),
+                                               C.byref(brick)))
+
+    def pack_frame(self, d_sum4, d_output, w, h, brightness=1.0):
+        self._ck(lib().vrdd_pack_frame(self._h, _ptr(d_sum4), _ptr(d_output), w, h, brightness))
 
     # diagnostics
     def set_variant(self, what, variant):

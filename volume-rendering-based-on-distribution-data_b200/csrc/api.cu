@@ -77,7 +77,7 @@ int ensure_volume_storage(vrdd_context* c, int source) {
     vrdd_decoded_volume& v = c->vol[source];
     const bool want_tex = c->sampler == VRDD_SAMPLER_TEXTURE;
     const bool want_brick = c->sampler == VRDD_SAMPLER_BRICKED;
-    const bool want_lin = c->keep_linear;
+    const bool want_lin = c->keep_linear || c->sampler == VRDD_SAMPLER_LINEAR;
     for (int i = 0; i < 3; ++i) {
         if (want_tex && !v.arr[i]) {
             cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
@@ -331,7 +331,7 @@ int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const floa
 
 int vrdd_set_sampler(vrdd_handle h, int sampler) {
     CHECK_HANDLE(h);
-    if (sampler != VRDD_SAMPLER_TEXTURE && sampler != VRDD_SAMPLER_BRICKED)
+    if (sampler != VRDD_SAMPLER_TEXTURE && sampler != VRDD_SAMPLER_BRICKED && sampler != VRDD_SAMPLER_LINEAR)
         return fail(c, VRDD_ERR_INVALID, "set_sampler: unknown sampler");
     c->sampler = sampler;
     return VRDD_OK;
@@ -581,6 +581,54 @@ int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, i
         return fail(c, VRDD_ERR_INVALID, "synth_fractal_device: bad arguments");
     return launch_synth_fractal(c, seed, num_templates, max_ne, z0, nz, d_codebook, d_errors, d_chunk_offsets,
                                 d_templates, total_ne);
+}
+
+int vrdd_synth_histograms_region_device(vrdd_handle h, uint32_t seed, int gw, int gh, int gd, int ox, int oy, int oz,
+                                        int z0, int nz, float* d_hist) {
+    CHECK_HANDLE(h);
+    if (!c->V || !d_hist || z0 < 0 || nz <= 0 || z0 + nz > c->D || ox < 0 || oy < 0 || oz < 0 || ox + c->W > gw ||
+        oy + c->H > gh || oz + c->D > gd)
+        return fail(c, VRDD_ERR_INVALID, "synth_histograms_region_device: the brick must lie inside the global volume");
+    return launch_synth_hist_region(c, seed, gw, gh, gd, ox, oy, oz, z0, nz, d_hist);
+}
+
+static int check_brick(vrdd_context* c, const vrdd_brick* b) {
+    if (!b) return fail(c, VRDD_ERR_INVALID, "render_brick: null brick");
+    if (b->ox < 0 || b->oy < 0 || b->oz < 0 || b->ox + c->W > b->gw || b->oy + c->H > b->gh || b->oz + c->D > b->gd)
+        return fail(c, VRDD_ERR_INVALID, "render_brick: the brick must lie inside the global volume");
+    return VRDD_OK;
+}
+
+int vrdd_render_brick_alpha(vrdd_handle h, float* d_alpha_seg, int image_w, int image_h, const vrdd_render_params* params,
+                            const vrdd_brick* brick) {
+    CHECK_HANDLE(h);
+    int rc = check_brick(c, brick);
+    if (rc != VRDD_OK) return rc;
+    vrdd_render_params p;
+    if (params) p = *params; else vrdd_default_render_params(&p);
+    return launch_brick_pass(c, 1, nullptr, d_alpha_seg, image_w, image_h, p, *brick);
+}
+
+int vrdd_render_brick_color(vrdd_handle h, const float* d_alpha_in, float* d_partial4, int image_w, int image_h,
+                            const vrdd_render_params* params, const vrdd_brick* brick) {
+    CHECK_HANDLE(h);
+    int rc = check_brick(c, brick);
+    if (rc != VRDD_OK) return rc;
+    vrdd_render_params p;
+    if (params) p = *params; else vrdd_default_render_params(&p);
+    return launch_brick_pass(c, 2, d_alpha_in, d_partial4, image_w, image_h, p, *brick);
+}
+
+int vrdd_compose_alpha_in(vrdd_handle h, const float* d_alpha_seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
+                          float* d_alpha_in, int image_w, int image_h) {
+    CHECK_HANDLE(h);
+    return launch_compose_alpha_in(c, d_alpha_seg_all, gx, gy, gz, qx, qy, qz, d_alpha_in, image_w, image_h);
+}
+
+int vrdd_pack_frame(vrdd_handle h, const float* d_sum4, uint32_t* d_output, int image_w, int image_h, float brightness) {
+    CHECK_HANDLE(h);
+    if (!d_sum4 || !d_output || image_w <= 0 || image_h <= 0) return fail(c, VRDD_ERR_INVALID, "pack_frame: bad arguments");
+    return launch_pack_frame(c, d_sum4, d_output, image_w, image_h, brightness);
 }
 
 int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {

@@ -226,6 +226,13 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
 int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_hist);
 int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int z0, int nz, int32_t* d_cb,
                          float* d_err, uint64_t* d_off, float* d_tmpl, uint64_t* total_ne);
+int launch_synth_hist_region(vrdd_context* c, uint32_t seed, int gw, int gh, int gd, int ox, int oy, int oz, int z0,
+                             int nz, float* d_hist);
+int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float* d_out, int iw, int ih,
+                      const vrdd_render_params& p, const vrdd_brick& b);
+int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
+                            float* d_alpha_in, int iw, int ih);
+int launch_pack_frame(vrdd_context* c, const float* d_sum4, uint32_t* d_out, int iw, int ih, float brightness);
 int launch_debug_sample(vrdd_context* c, cudaTextureObject_t tex, const float* d_uvw, int n, float* d_out);
 int launch_debug_sample_tf(vrdd_context* c, const float* d_u, int n, float* d_out4);
 

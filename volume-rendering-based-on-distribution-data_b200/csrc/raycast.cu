@@ -305,6 +305,8 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
     const long long grid = (long long)A.n_my_tiles * A.blocks_per_tile;
     if (grid > 0x7fffffffLL) return fail(c, VRDD_ERR_INVALID, "render: image too large");
 
+    if (c->sampler == VRDD_SAMPLER_LINEAR)
+        return fail(c, VRDD_ERR_INVALID, "render: VRDD_SAMPLER_LINEAR volumes are rendered with vrdd_render_brick_*");
     const bool count = c->count_samples && c->d_samples;
     const int sampler = c->sampler, tfm = (c->sampler == VRDD_SAMPLER_BRICKED) ? 1 : c->var_tf;
     if (sampler == VRDD_SAMPLER_TEXTURE && !A.vol_tex) return fail(c, VRDD_ERR_INVALID, "render: no texture volume");

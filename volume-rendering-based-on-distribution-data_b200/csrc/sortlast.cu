@@ -1,0 +1,276 @@
+// sortlast.cu — sort-last rendering of a volume that is brick-decomposed over GPUs
+// (BASELINE.json configs[4]).  New work: the reference is single-GPU.
+//
+// Each handle stores ONE brick of the global volume (its voxels plus a one-voxel ghost
+// layer) as linear fp32 planes.  The reference stops a ray when the accumulated alpha
+// exceeds 0.95 (volumeRender_kernel.cu:698); plain "over" compositing of independently
+// rendered bricks cannot reproduce that (the dropped tail is worth up to 12 LSB), so the
+// accumulated alpha is forwarded exactly, but without serialising the bricks:
+//
+//   pass 1  vrdd_render_brick_alpha   every rank marches its own samples and accumulates
+//                                     alpha only                         -> A_seg[H][W]
+//           all-gather of A_seg over ranks (host side, NCCL)
+//   compose vrdd_compose_alpha_in     per pixel, the alpha entering this brick is the
+//                                     front-to-back composite of the A_seg of the bricks the
+//                                     ray crossed before it              -> A_in[H][W]
+//   pass 2  vrdd_render_brick_color   marches again from A_in, with the reference's early
+//                                     exit, and emits the increments (dR, dG, dB, dA)
+//           SUM reduction of the increments over ranks (NCCL), then vrdd_pack_frame.
+//
+// A sample belongs to the brick whose half-open texture-coordinate box contains it; every
+// rank walks the SAME ray recurrence from the global box entry (pos += step is not
+// restarted mid-ray, cf. SURVEY.md §7 "incremental stepping"), and filters with the texture
+// unit's integer weight scheme evaluated on GLOBAL coordinates, so each sample value is the
+// one the single-GPU manual sampler produces.  What differs from the single-GPU image is
+// fp32 rounding in A_in and in the final sum: within +-1 LSB (tests/test_gpu_sortlast.py).
+#include "common.cuh"
+
+namespace vrdd {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+struct BrickArgs {
+    const float* plane;             // this brick's plane of the sampled component, linear, x fastest
+    int sx, sy, sz;                 // local (stored) size in voxels, ghost included
+    int gw, gh, gd;                 // global volume size
+    int ox, oy, oz;                 // global voxel coordinate of local (0,0,0)
+    float lo[3], hi[3];             // owned samples: lo <= texcoord < hi
+    const float4* tf_tab;
+    int tf_n;
+    int iw, ih;
+    float m[12];
+    float density, t_offset, t_scale, tstep, thresh;
+    int max_steps;
+    const float* alpha_in;          // pass 2
+    float* alpha_seg;               // pass 1 out
+    float4* partial;                // pass 2 out
+    unsigned long long* samples;
+};
+
+__device__ __forceinline__ void split_hw(float u, int n256, int& i, int& a) {
+    const unsigned U = (unsigned)(__saturatef(u) * 2097152.0f);
+    const unsigned long long p = (unsigned long long)U * (unsigned)n256 + (1u << 20);
+    int q = (int)(p >> 21) - 128;
+    q = min(max(q, 0), n256 - 256);
+    i = q >> 8;
+    a = q & 255;
+}
+
+// the texture unit's trilinear filter on GLOBAL coordinates, texels read from the local brick
+__device__ __forceinline__ float sample_brick(const BrickArgs& A, float u, float v, float w) {
+    int i, j, k, a, b, c;
+    split_hw(u, A.gw << 8, i, a);
+    split_hw(v, A.gh << 8, j, b);
+    split_hw(w, A.gd << 8, k, c);
+    const int i1 = min(i + 1, A.gw - 1), j1 = min(j + 1, A.gh - 1), k1 = min(k + 1, A.gd - 1);
+    // local indices; clamped so that a weight-0 neighbour outside the ghost layer stays in bounds
+    const int x0 = min(max(i - A.ox, 0), A.sx - 1), x1 = min(max(i1 - A.ox, 0), A.sx - 1);
+    const int y0 = min(max(j - A.oy, 0), A.sy - 1), y1 = min(max(j1 - A.oy, 0), A.sy - 1);
+    const int z0 = min(max(k - A.oz, 0), A.sz - 1), z1 = min(max(k1 - A.oz, 0), A.sz - 1);
+    const float* P = A.plane;
+    const size_t r00 = ((size_t)z0 * A.sy + y0) * A.sx, r10 = ((size_t)z0 * A.sy + y1) * A.sx;
+    const size_t r01 = ((size_t)z1 * A.sy + y0) * A.sx, r11 = ((size_t)z1 * A.sy + y1) * A.sx;
+    const float t000 = __ldg(P + r00 + x0), t100 = __ldg(P + r00 + x1);
+    const float t010 = __ldg(P + r10 + x0), t110 = __ldg(P + r10 + x1);
+    const float t001 = __ldg(P + r01 + x0), t101 = __ldg(P + r01 + x1);
+    const float t011 = __ldg(P + r11 + x0), t111 = __ldg(P + r11 + x1);
+    const int zz1 = c, zz0 = 256 - c;
+    const int x10 = (zz0 * a + 128) >> 8, x00 = zz0 - x10;
+    const int x11 = (zz1 * a + 128) >> 8, x01 = zz1 - x11;
+    const int w000 = (x00 * (256 - b) + 128) >> 8, w010 = x00 - w000;
+    const int w110 = (x10 * b + 128) >> 8, w100 = x10 - w110;
+    const int w001 = (x01 * (256 - b) + 128) >> 8, w011 = x01 - w001;
+    const int w111 = (x11 * b + 128) >> 8, w101 = x11 - w111;
+    float acc = (float)w000 * t000;
+    acc = fmaf((float)w010, t010, acc);
+    acc = fmaf((float)w100, t100, acc);
+    acc = fmaf((float)w110, t110, acc);
+    acc = fmaf((float)w001, t001, acc);
+    acc = fmaf((float)w011, t011, acc);
+    acc = fmaf((float)w101, t101, acc);
+    acc = fmaf((float)w111, t111, acc);
+    return acc * (1.0f / 256.0f);
+}
+
+__device__ __forceinline__ float4 tf_lookup(const float4* tab, int n, float u) {
+    int i, a;
+    split_hw(u, n << 8, i, a);
+    const float4 c0 = tab[i], c1 = tab[min(i + 1, n - 1)];
+    const float w0 = (float)(256 - a) * (1.0f / 256.0f), w1 = (float)a * (1.0f / 256.0f);
+    return make_float4(w0 * c0.x + w1 * c1.x, w0 * c0.y + w1 * c1.y, w0 * c0.z + w1 * c1.z, w0 * c0.w + w1 * c1.w);
+}
+
+// Eye ray of pixel (x, y): the same explicitly rounded operations as raycast.cu, so every rank
+// and the single-GPU kernel agree bit for bit on direction, tnear and tfar.
+struct RaySetup { float ox, oy, oz, dx, dy, dz, tnear, tfar; bool hit; };
+__device__ __forceinline__ RaySetup make_ray(const float* m, int x, int y, int iw, int ih) {
+    RaySetup R;
+    const float u = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)iw), 2.0f), 1.0f);
+    const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)ih), 2.0f), 1.0f);
+    R.ox = m[3]; R.oy = m[7]; R.oz = m[11];
+    float dx0 = u, dy0 = v, dz0 = -2.0f;
+    const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
+    const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+    dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
+    R.dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, m[0]), __fmul_rn(dy0, m[1])), __fmul_rn(dz0, m[2]));
+    R.dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, m[4]), __fmul_rn(dy0, m[5])), __fmul_rn(dz0, m[6]));
+    R.dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, m[8]), __fmul_rn(dy0, m[9])), __fmul_rn(dz0, m[10]));
+    const float ix = __fdiv_rn(1.0f, R.dx), iy = __fdiv_rn(1.0f, R.dy), iz = __fdiv_rn(1.0f, R.dz);
+    const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, R.ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, R.ox));
+    const float by0 = __fmul_rn(iy, __fsub_rn(-1.0f, R.oy)), by1 = __fmul_rn(iy, __fsub_rn(1.0f, R.oy));
+    const float bz0 = __fmul_rn(iz, __fsub_rn(-1.0f, R.oz)), bz1 = __fmul_rn(iz, __fsub_rn(1.0f, R.oz));
+    const float tminx = fminf(bx1, bx0), tminy = fminf(by1, by0), tminz = fminf(bz1, bz0);
+    const float tmaxx = fmaxf(bx1, bx0), tmaxy = fmaxf(by1, by0), tmaxz = fmaxf(bz1, bz0);
+    R.tnear = fmaxf(fmaxf(tminx, tminy), fmaxf(tminx, tminz));
+    R.tfar = fminf(fminf(tmaxx, tmaxy), fminf(tmaxx, tmaxz));
+    R.hit = R.tfar > R.tnear;
+    if (R.tnear < 0.0f) R.tnear = 0.0f;
+    return R;
+}
+
+// PASS 1: alpha of this brick's segment.  PASS 2: colour increments from the incoming alpha.
+template <int PASS, bool COUNT>
+__global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A) {
+    __shared__ float4 tf_s[VRDD_MAX_TF];
+    for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
+    __syncthreads();
+    const int blocks_x = (A.iw + 15) / 16;
+    const int by = blockIdx.x / blocks_x, bx = blockIdx.x - by * blocks_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int y = by * 16 + (warp >> 1) * 4 + (lane >> 3);
+    unsigned long long nsamp = 0;
+    if (x < A.iw && y < A.ih) {
+        const size_t pix = (size_t)y * A.iw + x;
+        const RaySetup R = make_ray(A.m, x, y, A.iw, A.ih);
+        float sr = 0.f, sg = 0.f, sb = 0.f;
+        const float a_in = (PASS == 2) ? A.alpha_in[pix] : 0.f;
+        float sa = a_in;
+        if (R.hit && !(sa > A.thresh)) {
+            float t = R.tnear;
+            float px = __fadd_rn(R.ox, __fmul_rn(R.dx, R.tnear));
+            float py = __fadd_rn(R.oy, __fmul_rn(R.dy, R.tnear));
+            float pz = __fadd_rn(R.oz, __fmul_rn(R.dz, R.tnear));
+            const float stx = __fmul_rn(R.dx, A.tstep), sty = __fmul_rn(R.dy, A.tstep), stz = __fmul_rn(R.dz, A.tstep);
+            for (int i = 0; i < A.max_steps; ++i) {
+                const float cu = fmaf(px, 0.5f, 0.5f), cv = fmaf(py, 0.5f, 0.5f), cw = fmaf(pz, 0.5f, 0.5f);
+                const bool mine = cu >= A.lo[0] && cu < A.hi[0] && cv >= A.lo[1] && cv < A.hi[1] &&
+                                  cw >= A.lo[2] && cw < A.hi[2];
+                if (mine) {
+                    const float s = sample_brick(A, cu, cv, cw);
+                    float4 col = tf_lookup(tf_s, A.tf_n, (s - A.t_offset) * A.t_scale);
+                    if (COUNT) ++nsamp;
+                    col.w *= A.density;
+                    const float kk = 1.0f - sa;
+                    if (PASS == 2) {
+                        col.x *= col.w; col.y *= col.w; col.z *= col.w;
+                        sr += col.x * kk; sg += col.y * kk; sb += col.z * kk;
+                    }
+                    sa += col.w * kk;
+                    if (sa > A.thresh) break;                              // :698, on the GLOBAL alpha in pass 2
+                }
+                t = __fadd_rn(t, A.tstep);
+                if (t > R.tfar) break;
+                px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+            }
+        }
+        if (PASS == 1) A.alpha_seg[pix] = sa;
+        else A.partial[pix] = make_float4(sr, sg, sb, sa - a_in);
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, d);
+        if (lane == 0 && nsamp) atomicAdd(A.samples, nsamp);
+    }
+}
+
+// alpha entering brick (qx,qy,qz): composite, front to back, of the segment alphas of every brick
+// that precedes it along the ray in all three axes.  Bricks the ray does not cross hold 0 and
+// leave the accumulator untouched, so any linear extension of the axis-wise order is exact.
+struct ViewMatrix { float m[12]; };
+__global__ void compose_alpha_in_kernel(const float* __restrict__ seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
+                                        float* __restrict__ alpha_in, int iw, int ih, const ViewMatrix M) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= iw || y >= ih) return;
+    const RaySetup R = make_ray(M.m, x, y, iw, ih);
+    const size_t pix = (size_t)y * iw + x, npix = (size_t)iw * ih;
+    const bool fx = R.dx >= 0.f, fy = R.dy >= 0.f, fz = R.dz >= 0.f;
+    const int rqx = fx ? qx : gx - 1 - qx, rqy = fy ? qy : gy - 1 - qy, rqz = fz ? qz : gz - 1 - qz;
+    float a = 0.f;
+    for (int rz = 0; rz <= rqz; ++rz)
+        for (int ry = 0; ry <= rqy; ++ry)
+            for (int rx = 0; rx <= rqx; ++rx) {
+                if (rx == rqx && ry == rqy && rz == rqz) continue;
+                const int bx = fx ? rx : gx - 1 - rx, by = fy ? ry : gy - 1 - ry, bz = fz ? rz : gz - 1 - rz;
+                const float s = seg_all[((size_t)(bz * gy + by) * gx + bx) * npix + pix];
+                a += s * (1.0f - a);
+            }
+    alpha_in[pix] = a;
+}
+
+__global__ void pack_frame_kernel(const float4* __restrict__ sum, uint32_t* __restrict__ out, size_t n, float brightness) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = sum[i];
+    out[i] = ((uint32_t)(__saturatef(c.w * brightness) * 255.0f) << 24) | ((uint32_t)(__saturatef(c.z * brightness) * 255.0f) << 16) |
+             ((uint32_t)(__saturatef(c.y * brightness) * 255.0f) << 8) | (uint32_t)(__saturatef(c.x * brightness) * 255.0f);
+}
+
+}  // namespace
+
+int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float* d_out, int iw, int ih,
+                      const vrdd_render_params& p, const vrdd_brick& b) {
+    const int qm = p.query_method;
+    if (qm < 1 || qm > 6) return fail(c, VRDD_ERR_UNSUPPORTED, "render_brick: queryMethod must be 1..6");
+    const int source = (qm >= 4) ? VRDD_SRC_FRACTAL : VRDD_SRC_ORIGINAL, comp = (qm - 1) % 3;
+    vrdd_decoded_volume& vol = c->vol[source];
+    if (!vol.decoded || !vol.lin[comp]) return fail(c, VRDD_ERR_INVALID, "render_brick: decode with linear planes kept first");
+    if (iw <= 0 || ih <= 0 || !d_out || (pass == 2 && !d_alpha_in)) return fail(c, VRDD_ERR_INVALID, "render_brick: bad arguments");
+    BrickArgs A;
+    A.plane = vol.lin[comp];
+    A.sx = c->W; A.sy = c->H; A.sz = c->D;
+    A.gw = b.gw; A.gh = b.gh; A.gd = b.gd; A.ox = b.ox; A.oy = b.oy; A.oz = b.oz;
+    for (int i = 0; i < 3; ++i) { A.lo[i] = b.lo[i]; A.hi[i] = b.hi[i]; }
+    A.tf_tab = reinterpret_cast<const float4*>(c->tf_dev); A.tf_n = c->tf_n;
+    A.iw = iw; A.ih = ih;
+    for (int i = 0; i < 12; ++i) A.m[i] = c->view[i];
+    A.density = p.density; A.t_offset = p.transfer_offset; A.t_scale = p.transfer_scale; A.tstep = p.tstep;
+    A.thresh = p.opacity_threshold; A.max_steps = p.max_steps;
+    A.alpha_in = d_alpha_in; A.alpha_seg = d_out; A.partial = reinterpret_cast<float4*>(d_out);
+    A.samples = c->d_samples;
+    const int grid = ((iw + 15) / 16) * ((ih + 15) / 16);
+    const bool count = c->count_samples && pass == 2;
+    if (pass == 1) raycast_brick_kernel<1, false><<<grid, kBlock, 0, c->stream>>>(A);
+    else if (count) raycast_brick_kernel<2, true><<<grid, kBlock, 0, c->stream>>>(A);
+    else raycast_brick_kernel<2, false><<<grid, kBlock, 0, c->stream>>>(A);
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
+                            float* d_alpha_in, int iw, int ih) {
+    if (!d_seg_all || !d_alpha_in || iw <= 0 || ih <= 0 || gx < 1 || gy < 1 || gz < 1 || qx < 0 || qx >= gx || qy < 0 ||
+        qy >= gy || qz < 0 || qz >= gz)
+        return fail(c, VRDD_ERR_INVALID, "compose_alpha_in: bad arguments");
+    ViewMatrix M;
+    for (int i = 0; i < 12; ++i) M.m[i] = c->view[i];
+    dim3 grid((iw + 127) / 128, ih);
+    compose_alpha_in_kernel<<<grid, 128, 0, c->stream>>>(d_seg_all, gx, gy, gz, qx, qy, qz, d_alpha_in, iw, ih, M);
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+int launch_pack_frame(vrdd_context* c, const float* d_sum4, uint32_t* d_out, int iw, int ih, float brightness) {
+    const size_t n = (size_t)iw * ih;
+    pack_frame_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const float4*>(d_sum4), d_out, n,
+                                                                         brightness);
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+}  // namespace vrdd

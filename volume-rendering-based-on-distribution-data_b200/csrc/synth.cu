@@ -28,6 +28,22 @@ __global__ void synth_hist_kernel(uint32_t seed, int W, int H, int D, int z0, lo
         out[v * (VRDD_BINS / 4) + j] = make_float4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
 }
 
+// brick of a larger volume: local voxel (x,y,z) is global voxel (ox+x, oy+y, oz+z)
+__global__ void synth_hist_region_kernel(uint32_t seed, int gw, int gh, int gd, int ox, int oy, int oz, int W, int H,
+                                         int z0, long long nvox, float4* out) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvox) return;
+    const long long wh = (long long)W * H;
+    const int z = (int)(v / wh);
+    const int r = (int)(v - (long long)z * wh);
+    const int y = r / W, x = r - y * W;
+    float p[VRDD_BINS];
+    vrdd_synth_histogram(seed, ox + x, oy + y, oz + z0 + z, gw, gh, gd, VRDD_BINS, p);
+#pragma unroll
+    for (int j = 0; j < VRDD_BINS / 4; ++j)
+        out[v * (VRDD_BINS / 4) + j] = make_float4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+}
+
 __global__ void synth_templates_kernel(uint32_t seed, int T, float* out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= T) return;
@@ -94,6 +110,17 @@ int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_h
     const long long grid = (nvox + 127) / 128;
     synth_hist_kernel<<<(unsigned)grid, 128, 0, c->stream>>>(seed, c->W, c->H, c->D, z0, nvox,
                                                               reinterpret_cast<float4*>(d_hist));
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+int launch_synth_hist_region(vrdd_context* c, uint32_t seed, int gw, int gh, int gd, int ox, int oy, int oz, int z0,
+                             int nz, float* d_hist) {
+    const long long nvox = (long long)c->W * c->H * nz;
+    if (nvox <= 0) return VRDD_OK;
+    synth_hist_region_kernel<<<(unsigned)((nvox + 127) / 128), 128, 0, c->stream>>>(
+        seed, gw, gh, gd, ox, oy, oz, c->W, c->H, z0, nvox, reinterpret_cast<float4*>(d_hist));
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;

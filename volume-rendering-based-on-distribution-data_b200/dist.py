@@ -64,3 +64,34 @@ def reduce_frame(partial, scratch, dst=0, group=None):
     scratch.copy_(partial)
     dist.reduce(scratch, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return scratch
+
+
+# ---- sort-last bricks (volumes larger than one GPU's HBM) -------------------------------------
+
+def brick_grid(world):
+    """Brick grid (gx, gy, gz) for `world` ranks: 8 -> 2x2x2, 4 -> 2x2x1, 2 -> 2x1x1."""
+    g = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(world)
+    if g is None:
+        raise ValueError("sort-last bricks need 1, 2, 4 or 8 ranks")
+    return g
+
+
+def brick_of_rank(rank, grid):
+    gx, gy, gz = grid
+    return rank % gx, (rank // gx) % gy, rank // (gx * gy)
+
+
+def brick_geometry(gdims, grid, q):
+    """Geometry of brick q = (qx,qy,qz): returns (origin, size, lo, hi).
+    Owned voxels are [b0, b1) per axis (balanced split); owned samples are those whose texture
+    coordinate lies in [b0/N, b1/N) (faces of the volume: -inf / +inf); the stored box adds one
+    ghost voxel on each side, clamped to the volume (a sample at coordinate u touches texels
+    floor(u*N - 0.5) and the next one)."""
+    origin, size, lo, hi = [], [], [], []
+    for n, g, k in zip(gdims, grid, q):
+        b0, b1 = n * k // g, n * (k + 1) // g
+        s0, s1 = max(b0 - 1, 0), min(b1 + 1, n)
+        origin.append(s0); size.append(s1 - s0)
+        lo.append(float("-inf") if k == 0 else b0 / n)
+        hi.append(float("inf") if k == g - 1 else b1 / n)
+    return tuple(origin), tuple(size), tuple(lo), tuple(hi)
