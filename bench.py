@@ -499,6 +499,157 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_sortlast(args):
+    """--workload sortlast (BASELINE.json configs[4]): every rank owns one VOL^3 brick (plus a one-voxel
+    ghost layer) of a volume too large for one GPU — 8 ranks: 2x2x2 bricks of a (2*VOL)^3 volume, 1.1 TB of
+    histograms at VOL = 1024.  Per step: alpha pre-pass -> NCCL all-gather of the segment alphas ->
+    incoming alpha -> colour pass -> NCCL SUM reduction of the float4 increments -> pack on rank 0."""
+    import torch
+    import torch.distributed as dist
+    import vrdd_b200 as V
+    import vrdd_b200.dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks, peak_src = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+    grid = D.brick_grid(world)
+    q = D.brick_of_rank(rank, grid)
+    E = args.volume
+    gdims = (E * grid[0], E * grid[1], E * grid[2])
+    origin, size, lo, hi = D.brick_geometry(gdims, grid, q)
+    r = V.Renderer(local)
+    r.set_stream(torch.cuda.current_stream().cuda_stream)
+    r.set_sampler(V.SAMPLER_LINEAR)
+    r.set_volume(*size)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    # ---- decode my brick slab by slab -----------------------------------------------------------
+    slice_vox = size[0] * size[1]
+    slab = max(1, min(args.slab_z, size[2]))
+    buf = torch.empty(slab * slice_vox * 32, dtype=torch.float32, device=dev)
+    dec_ms = 0.0
+    for z0 in range(0, size[2], slab):
+        nz = min(slab, size[2] - z0)
+        r.synth_histograms_region_device(args.seed, gdims, origin, z0, nz, buf)
+        r.set_histograms_device(buf, z0, nz)
+        r.decode(V.SRC_ORIGINAL, z0, nz)
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record(); r.decode(V.SRC_ORIGINAL, z0, nz); e1.record()
+        torch.cuda.synchronize()
+        dec_ms += e0.elapsed_time(e1)
+    del buf
+    torch.cuda.empty_cache()
+    dec_ms = max_over_ranks(dec_ms)
+    brick_vox = size[0] * size[1] * size[2]
+    tv = torch.tensor([brick_vox], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tv)
+    decoded_vox = float(tv.item())
+
+    # ---- render ------------------------------------------------------------------------------------
+    fw = fh = args.image_sortlast
+    params = V.default_render_params(query_method=1)
+    br = V.Brick(gdims[0], gdims[1], gdims[2], origin[0], origin[1], origin[2], (V.C.c_float * 3)(*lo), (V.C.c_float * 3)(*hi))
+    seg = torch.zeros(fh, fw, dtype=torch.float32, device=dev)
+    seg_all = torch.zeros(world, fh, fw, dtype=torch.float32, device=dev)
+    a_in = torch.zeros(fh, fw, dtype=torch.float32, device=dev)
+    part = torch.zeros(fh, fw, 4, dtype=torch.float32, device=dev)
+    frame = torch.zeros(fh, fw, dtype=torch.int32, device=dev)
+
+    def step(k):
+        r.set_view(orbit_view(V, k))
+        r.render_brick_alpha(seg, fw, fh, params, br)
+        if world > 1:
+            dist.all_gather_into_tensor(seg_all, seg)
+        else:
+            seg_all[0].copy_(seg)
+        r.compose_alpha_in(seg_all, grid, q, a_in, fw, fh)
+        r.render_brick_color(a_in, part, fw, fh, params, br)
+        if world > 1:
+            dist.reduce(part, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            r.pack_frame(part, frame, fw, fh, params.brightness)
+
+    nviews = min(ORBIT_VIEWS, args.warmup + args.steps)
+    r.count_samples(True)
+    counts = []
+    for k in range(nviews):
+        step(k)
+        counts.append(r.get_sample_count())
+    r.count_samples(False)
+    if world > 1:
+        t = torch.tensor(counts, dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        counts = [int(x) for x in t.tolist()]
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    l0 = r.kernel_launches()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for k in range(args.warmup, args.warmup + args.steps):
+        step(k)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = r.kernel_launches() - l0
+    samples = sum(counts[k % len(counts)] for k in range(args.warmup, args.warmup + args.steps))
+    host = torch.empty(fh, fw, dtype=torch.int32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.warmup, args.warmup + args.steps):
+        step(k)
+        if rank == 0:
+            host.copy_(frame, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop()
+    if rank == 0:
+        dec_gbs = decoded_vox * HIST_BYTES_PER_VOXEL / (dec_ms * 1e-3) / 1e9
+        line = {"metric": "raycast_throughput", "value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "fps": args.steps / (ms * 1e-3),
+                "samples_per_frame": samples / args.steps,
+                "config": {"workload": f"sort-last: {gdims[0]}x{gdims[1]}x{gdims[2]} distribution volume in {grid[0]}x{grid[1]}x{grid[2]} "
+                                       f"bricks of {E}^3 (+1 ghost) over {world} GPUs, {fw}x{fh} frames of the 64-view orbit, reference "
+                                       "constants; alpha pre-pass, NCCL all-gather of segment alphas, colour pass, NCCL SUM "
+                                       "reduction of float4 increments, pack on rank 0",
+                           "volume": list(gdims), "image": [fw, fh], "histogram_bytes_total": decoded_vox * 128,
+                           "l2": "inputs larger than L2; no flush"},
+                "decode": {"kernel": "decode_hist_tma_kernel", "voxels": decoded_vox, "ms": dec_ms, "gbs": dec_gbs,
+                           "frac_of_hbm_peak": dec_gbs / (hbm_peak * world), "peak_gbs": hbm_peak * world},
+                "e2e": {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 80,
+                        "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt,
+                        "call": "vrdd_render_brick_alpha/compose/color + NCCL + vrdd_pack_frame + device->pinned-host frame copy"},
+                "gpu_launches": int(launches), "clocks": clk}
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -519,12 +670,18 @@ def main():
     ap.add_argument("--e2e-decode-z", type=int, default=8, help="z-slices of the host-memory decode leg (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--workload", default="tiles", choices=["tiles", "sortlast"],
+                    help="tiles: volume replicated, image-space tiles (default); sortlast: one VOL^3 brick per GPU")
+    ap.add_argument("--image-sortlast", type=int, default=2048)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
         args.warmup = max(args.warmup, 3)
-        run_ours(args)
+        if args.workload == "sortlast":
+            run_sortlast(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":
