@@ -21,12 +21,12 @@ def _declared(header):
 def test_every_declared_symbol_is_exported():
     import vrdd_b200 as V
     L = C.CDLL(V.LIB_PATH)
-    names = _declared("vrdd.h") | _declared("vrdd_legacy.h")
+    names = _declared("vrdd.h") | _declared("vrdd_legacy.h") | _declared("vrdd_io.h")
     assert {"vrdd_create", "vrdd_decode", "vrdd_render", "initCuda", "basicDataProcessing", "render_kernel",
             "copyInvViewMatrix", "setTextureFilterMode", "freeCudaBuffers", "dataProcessing"} <= names
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
-    assert names == set(V.EXPORTS) | set(V.LEGACY_EXPORTS)
+    assert names == set(V.EXPORTS) | set(V.LEGACY_EXPORTS) | set(V.IO_EXPORTS)
 
 
 def test_legacy_signatures_match_reference_declarations():

@@ -36,6 +36,10 @@ EXPORTS = [
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
+IO_EXPORTS = ["vrdd_io_read_histograms", "vrdd_io_codebook_blocks", "vrdd_io_read_codebook", "vrdd_io_template_count",
+              "vrdd_io_read_templates", "vrdd_io_write_histograms", "vrdd_io_write_codebook", "vrdd_io_write_templates",
+              "vrdd_io_write_ppm", "vrdd_io_read_ppm"]
+HEADLESS_PATH = os.path.join(_HERE, "vrdd_headless")
 LEGACY_EXPORTS = ["initCuda", "basicDataProcessing", "dataProcessing", "copyInvViewMatrix", "render_kernel",
                   "setTextureFilterMode", "freeCudaBuffers", "vrdd_legacy_handle"]
 
@@ -129,6 +133,17 @@ def lib():
             "vrdd_render_brick_color": (i32, [vp, vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_pack_frame": (i32, [vp, vp, vp, i32, i32, f32]),
             "vrdd_synth_histograms_region_device": (i32, [vp, u32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+            # on-disk formats (include/vrdd_io.h)
+            "vrdd_io_read_histograms": (i32, [C.c_char_p, C.c_size_t, i32, vp]),
+            "vrdd_io_codebook_blocks": (C.c_int64, [C.c_char_p]),
+            "vrdd_io_read_codebook": (i32, [C.c_char_p, i32, C.c_int64, vp, vp]),
+            "vrdd_io_template_count": (i32, [C.c_char_p, i32]),
+            "vrdd_io_read_templates": (i32, [C.c_char_p, i32, i32, vp]),
+            "vrdd_io_write_histograms": (i32, [C.c_char_p, C.c_size_t, i32, vp]),
+            "vrdd_io_write_codebook": (i32, [C.c_char_p, i32, C.c_int64, vp, vp]),
+            "vrdd_io_write_templates": (i32, [C.c_char_p, i32, i32, vp]),
+            "vrdd_io_write_ppm": (i32, [C.c_char_p, vp, i32, i32]),
+            "vrdd_io_read_ppm": (i32, [C.c_char_p, vp, i32, i32]),
             # legacy surface (include/vrdd_legacy.h)
             "initCuda": (None, [vp, Extent, Extent, vp, Extent, vp, Extent, vp, Extent] + [vp] * 9),
             "basicDataProcessing": (None, []),
