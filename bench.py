@@ -525,7 +525,7 @@ def run_sortlast(args):
     origin, size, lo, hi = D.brick_geometry(gdims, grid, q)
     r = V.Renderer(local)
     r.set_stream(torch.cuda.current_stream().cuda_stream)
-    r.set_sampler(V.SAMPLER_LINEAR)
+    r.set_sampler(V.SAMPLER_LINEAR if args.sortlast_layout == "linear" else V.SAMPLER_BRICKED)
     r.set_volume(*size)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -673,6 +673,7 @@ def main():
     ap.add_argument("--workload", default="tiles", choices=["tiles", "sortlast"],
                     help="tiles: volume replicated, image-space tiles (default); sortlast: one VOL^3 brick per GPU")
     ap.add_argument("--image-sortlast", type=int, default=2048)
+    ap.add_argument("--sortlast-layout", default="bricked", choices=["bricked", "linear"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -199,7 +199,8 @@ int vrdd_get_sample_count(vrdd_handle h, int64_t* out, int reset);
 /* ---- sort-last rendering of a brick-decomposed volume (volumes larger than one GPU's HBM;
  *      new work, the reference is single-GPU; scheme in csrc/sortlast.cu) ------------------------- */
 
-/* This handle's volume (vrdd_set_volume dims, VRDD_SAMPLER_LINEAR) is one brick of a larger one. */
+/* This handle's volume (vrdd_set_volume dims; VRDD_SAMPLER_BRICKED, or VRDD_SAMPLER_LINEAR) is one
+ * brick of a larger one. */
 typedef struct vrdd_brick {
     int gw, gh, gd;           /* size of the GLOBAL volume in voxels                                   */
     int ox, oy, oz;           /* global voxel coordinate of this handle's voxel (0,0,0), ghost included */

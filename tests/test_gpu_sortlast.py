@@ -13,7 +13,7 @@ def _lsb(a, b):
                   np.ascontiguousarray(b).view(np.uint8).astype(np.int16))
 
 
-def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full):
+def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full, layout):
     import torch
     w, h = img
     nb = grid[0] * grid[1] * grid[2]
@@ -22,7 +22,7 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
         q = (b % grid[0], (b // grid[0]) % grid[1], b // (grid[0] * grid[1]))
         origin, size, lo, hi = D.brick_geometry(gdims, grid, q)
         r = V.Renderer(0)
-        r.set_sampler(V.SAMPLER_LINEAR)
+        r.set_sampler(layout)
         r.set_volume(*size)
         # the brick's histograms: generated on the device from GLOBAL voxel coordinates
         d_hist = torch.empty(size[0] * size[1] * size[2], 32, dtype=torch.float32, device="cuda")
@@ -76,7 +76,8 @@ def test_sortlast_matches_single_volume_and_oracle(oracle, grid, rot):
         params = V.default_render_params(query_method=1, **over)
         ref, ref_s = oracle.render(vol, gdims, view, image=img, density=params.density, brightness=params.brightness,
                                    opacity_threshold=params.opacity_threshold)
-        got, s = _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist)
+        layout = V.SAMPLER_BRICKED if over else V.SAMPLER_LINEAR            # both plane layouts
+        got, s = _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist, layout)
         d = _lsb(got, ref)
         assert d.max() <= 1, (grid, rot, over, int(d.max()), int((d > 1).sum()))
         assert abs(s - ref_s) <= max(2, ref_s // 5000), (s, ref_s)

@@ -43,6 +43,40 @@ __host__ __device__ __forceinline__ size_t brick_index(int x, int y, int z, int 
     return (b << (3 * VRDD_BRICK_SHIFT)) + (size_t)(((z & 3) << 4) | ((y & 3) << 2) | (x & 3));
 }
 
+// (x, y, z) of a global voxel index.  A 64-bit divide costs ~100 instructions, so z comes from a
+// float estimate of gv / (W*H) corrected by at most two (exact for gv < 2^47).
+__device__ __forceinline__ void split_voxel(const DecodeOut& o, long long gv, int& x, int& y, int& z) {
+    const long long wh = (long long)o.W * o.H;
+    z = (int)((float)gv * o.inv_wh);
+    long long rem = gv - (long long)z * wh;
+    if (rem < 0) { --z; rem += wh; }
+    else if (rem >= wh) { ++z; rem -= wh; }
+    if (rem < 0) { --z; rem += wh; }
+    else if (rem >= wh) { ++z; rem -= wh; }
+    const int r = (int)rem;
+    y = r / o.W;
+    x = r - y * o.W;
+}
+
+// Same sink with the voxel coordinate supplied by the caller (kernels that walk consecutive
+// tiles advance (x, y, z) incrementally instead of dividing per voxel).
+__device__ __forceinline__ void emit_decoded_xyz(const DecodeOut& o, long long v_local, int x, int y, int z, float mean,
+                                                 float var, float ent) {
+    const long long gv = o.v_base + v_local;
+    if (o.lin[0]) {
+        o.lin[0][gv] = mean; o.lin[1][gv] = var; o.lin[2][gv] = ent;
+    }
+    if (o.use_surf) {
+        surf3Dwrite(mean, o.surf[0], x * 4, y, z);
+        surf3Dwrite(var, o.surf[1], x * 4, y, z);
+        surf3Dwrite(ent, o.surf[2], x * 4, y, z);
+    }
+    if (o.brick[0]) {
+        const size_t bi = brick_index(x, y, z, o.bW, o.bH);
+        o.brick[0][bi] = mean; o.brick[1][bi] = var; o.brick[2][bi] = ent;
+    }
+}
+
 __device__ __forceinline__ void emit_decoded(const DecodeOut& o, long long v_local, float mean, float var,
                                              float ent) {
     const long long gv = o.v_base + v_local;
@@ -50,18 +84,8 @@ __device__ __forceinline__ void emit_decoded(const DecodeOut& o, long long v_loc
         o.lin[0][gv] = mean; o.lin[1][gv] = var; o.lin[2][gv] = ent;
     }
     if (o.use_surf || o.brick[0]) {
-        // (x, y, z) of the voxel.  A 64-bit divide costs ~100 instructions per voxel, so z comes
-        // from a float estimate of gv / (W*H) corrected by at most one (exact for gv < 2^47).
-        const long long wh = (long long)o.W * o.H;
-        int z = (int)((float)gv * o.inv_wh);
-        long long rem = gv - (long long)z * wh;
-        if (rem < 0) { --z; rem += wh; }
-        else if (rem >= wh) { ++z; rem -= wh; }
-        if (rem < 0) { --z; rem += wh; }
-        else if (rem >= wh) { ++z; rem -= wh; }
-        const int r = (int)rem;
-        const int y = r / o.W;
-        const int x = r - y * o.W;
+        int x, y, z;
+        split_voxel(o, gv, x, y, z);
         if (o.use_surf) {
             surf3Dwrite(mean, o.surf[0], x * 4, y, z);
             surf3Dwrite(var, o.surf[1], x * 4, y, z);

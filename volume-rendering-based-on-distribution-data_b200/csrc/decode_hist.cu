@@ -47,6 +47,11 @@ __device__ __forceinline__ void finish_and_emit(const DecodeOut& out, long long 
     const float inv_log2_bins = 1.0f / 5.0f;        // 1 / log2(32)
     emit_decoded(out, v, mean_raw * inv_mean_norm, var_raw * inv_var_norm, -plogp * inv_log2_bins);
 }
+__device__ __forceinline__ void finish_and_emit_xyz(const DecodeOut& out, long long v, int x, int y, int z, float mean_raw,
+                                                    float var_raw, float plogp) {
+    emit_decoded_xyz(out, v, x, y, z, mean_raw * (float)(1.0 / VRDD_MEAN_NORM), var_raw * (float)(1.0 / VRDD_VAR_NORM),
+                     -plogp * (1.0f / 5.0f));
+}
 
 __global__ void __launch_bounds__(kTmaThreads, 1)
 decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut out, int chunked) {
@@ -108,6 +113,11 @@ decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut
     const float hb = 0.5f * bw;
     int s = 0;
     uint32_t phase = 0;
+    // voxel coordinate of this thread's row, advanced by one tile per iteration (consecutive tiles):
+    // one division per thread instead of one per voxel
+    const bool need_xyz = out.use_surf || out.brick[0] != nullptr;
+    int vx = 0, vy = 0, vz = 0;
+    if (need_xyz && t_begin < t_end) split_voxel(out, out.v_base + t_begin * kTileVox + tid, vx, vy, vz);
     for (long long t = t_begin; t < t_end; t += t_step) {
         mbar_wait(&full[s], phase);
         const float4* row = tiles + ((size_t)s * kTileVox + tid) * (VRDD_BINS / 4);
@@ -118,6 +128,16 @@ decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);                   // slot may be refilled now
         if (++s == kStages) { s = 0; phase ^= 1u; }
+        const int cx = vx, cy = vy, cz = vz;                     // this tile's coordinate; then step to the next tile
+        if (need_xyz) {
+            if (t_step == 1) {
+                vx += kTileVox;
+                while (vx >= out.W) { vx -= out.W; ++vy; }
+                while (vy >= out.H) { vy -= out.H; ++vz; }
+            } else if (t + t_step < t_end) {
+                split_voxel(out, out.v_base + (t + t_step) * kTileVox + tid, vx, vy, vz);
+            }
+        }
         if (v >= nvox) continue;
 
         float S0 = 0.f, S1 = 0.f, E = 0.f;
@@ -142,7 +162,7 @@ decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut
             var_a = fmaf(q[j].z * d2, d2, var_a);
             var_b = fmaf(q[j].w * d3, d3, var_b);
         }
-        finish_and_emit(out, v, mean_raw, var_a + var_b, E);
+        finish_and_emit_xyz(out, v, cx, cy, cz, mean_raw, var_a + var_b, E);
     }
 }
 

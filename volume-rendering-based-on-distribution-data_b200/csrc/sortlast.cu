@@ -32,7 +32,8 @@ namespace {
 constexpr int kBlock = 256;
 
 struct BrickArgs {
-    const float* plane;             // this brick's plane of the sampled component, linear, x fastest
+    const float* plane;             // this brick's plane of the sampled component
+    int bricked, bW, bH;            // layout of `plane`: 4x4x4-bricked (common.cuh) or linear, x fastest
     int sx, sy, sz;                 // local (stored) size in voxels, ghost included
     int gw, gh, gd;                 // global volume size
     int ox, oy, oz;                 // global voxel coordinate of local (0,0,0)
@@ -70,12 +71,20 @@ __device__ __forceinline__ float sample_brick(const BrickArgs& A, float u, float
     const int y0 = min(max(j - A.oy, 0), A.sy - 1), y1 = min(max(j1 - A.oy, 0), A.sy - 1);
     const int z0 = min(max(k - A.oz, 0), A.sz - 1), z1 = min(max(k1 - A.oz, 0), A.sz - 1);
     const float* P = A.plane;
-    const size_t r00 = ((size_t)z0 * A.sy + y0) * A.sx, r10 = ((size_t)z0 * A.sy + y1) * A.sx;
-    const size_t r01 = ((size_t)z1 * A.sy + y0) * A.sx, r11 = ((size_t)z1 * A.sy + y1) * A.sx;
-    const float t000 = __ldg(P + r00 + x0), t100 = __ldg(P + r00 + x1);
-    const float t010 = __ldg(P + r10 + x0), t110 = __ldg(P + r10 + x1);
-    const float t001 = __ldg(P + r01 + x0), t101 = __ldg(P + r01 + x1);
-    const float t011 = __ldg(P + r11 + x0), t111 = __ldg(P + r11 + x1);
+    float t000, t100, t010, t110, t001, t101, t011, t111;
+    if (A.bricked) {
+        t000 = __ldg(P + brick_index(x0, y0, z0, A.bW, A.bH)); t100 = __ldg(P + brick_index(x1, y0, z0, A.bW, A.bH));
+        t010 = __ldg(P + brick_index(x0, y1, z0, A.bW, A.bH)); t110 = __ldg(P + brick_index(x1, y1, z0, A.bW, A.bH));
+        t001 = __ldg(P + brick_index(x0, y0, z1, A.bW, A.bH)); t101 = __ldg(P + brick_index(x1, y0, z1, A.bW, A.bH));
+        t011 = __ldg(P + brick_index(x0, y1, z1, A.bW, A.bH)); t111 = __ldg(P + brick_index(x1, y1, z1, A.bW, A.bH));
+    } else {
+        const size_t r00 = ((size_t)z0 * A.sy + y0) * A.sx, r10 = ((size_t)z0 * A.sy + y1) * A.sx;
+        const size_t r01 = ((size_t)z1 * A.sy + y0) * A.sx, r11 = ((size_t)z1 * A.sy + y1) * A.sx;
+        t000 = __ldg(P + r00 + x0); t100 = __ldg(P + r00 + x1);
+        t010 = __ldg(P + r10 + x0); t110 = __ldg(P + r10 + x1);
+        t001 = __ldg(P + r01 + x0); t101 = __ldg(P + r01 + x1);
+        t011 = __ldg(P + r11 + x0); t111 = __ldg(P + r11 + x1);
+    }
     const int zz1 = c, zz0 = 256 - c;
     const int x10 = (zz0 * a + 128) >> 8, x00 = zz0 - x10;
     const int x11 = (zz1 * a + 128) >> 8, x01 = zz1 - x11;
@@ -154,7 +163,40 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
             float py = __fadd_rn(R.oy, __fmul_rn(R.dy, R.tnear));
             float pz = __fadd_rn(R.oz, __fmul_rn(R.dz, R.tnear));
             const float stx = __fmul_rn(R.dx, A.tstep), sty = __fmul_rn(R.dy, A.tstep), stz = __fmul_rn(R.dz, A.tstep);
-            for (int i = 0; i < A.max_steps; ++i) {
+            // Steps that can fall into this brick: slab test of the ray against the brick's box in
+            // world coordinates (texcoord c <-> world 2c-1), widened by two steps.  Outside that range
+            // only the recurrence itself is replayed (it must not be restarted, see the header), so a
+            // rank pays for the samples it owns rather than for every step of every ray.
+            int i_first = 0, i_last = A.max_steps - 1;
+            {
+                float t0 = -INFINITY, t1 = INFINITY;
+                const float o3[3] = {R.ox, R.oy, R.oz}, d3[3] = {R.dx, R.dy, R.dz};
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    const float wlo = 2.0f * A.lo[ax] - 1.0f, whi = 2.0f * A.hi[ax] - 1.0f;   // +-inf at the volume faces
+                    if (fabsf(d3[ax]) > 1e-12f) {
+                        const float a = (wlo - o3[ax]) / d3[ax], b = (whi - o3[ax]) / d3[ax];
+                        t0 = fmaxf(t0, fminf(a, b)); t1 = fminf(t1, fmaxf(a, b));
+                    } else if (o3[ax] < wlo - 1e-3f || o3[ax] > whi + 1e-3f) {
+                        t1 = -INFINITY;
+                    }
+                }
+                if (t1 >= t0) {
+                    const float k0 = floorf((t0 - R.tnear) / A.tstep) - 2.0f, k1 = ceilf((t1 - R.tnear) / A.tstep) + 2.0f;
+                    i_first = (int)fminf(fmaxf(k0, 0.0f), (float)A.max_steps);
+                    i_last = (int)fminf(fmaxf(k1, -1.0f), (float)(A.max_steps - 1));
+                } else {
+                    i_last = -1;                                   // the ray never enters this brick
+                }
+            }
+            int i = 0;
+            bool alive = i_last >= 0;
+            for (; alive && i < i_first; ++i) {                    // replay the recurrence up to the brick (:701-706)
+                t = __fadd_rn(t, A.tstep);
+                if (t > R.tfar) { alive = false; break; }
+                px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+            }
+            for (; alive && i <= i_last; ++i) {
                 const float cu = fmaf(px, 0.5f, 0.5f), cv = fmaf(py, 0.5f, 0.5f), cw = fmaf(pz, 0.5f, 0.5f);
                 const bool mine = cu >= A.lo[0] && cu < A.hi[0] && cv >= A.lo[1] && cv < A.hi[1] &&
                                   cw >= A.lo[2] && cw < A.hi[2];
@@ -226,10 +268,13 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
     if (qm < 1 || qm > 6) return fail(c, VRDD_ERR_UNSUPPORTED, "render_brick: queryMethod must be 1..6");
     const int source = (qm >= 4) ? VRDD_SRC_FRACTAL : VRDD_SRC_ORIGINAL, comp = (qm - 1) % 3;
     vrdd_decoded_volume& vol = c->vol[source];
-    if (!vol.decoded || !vol.lin[comp]) return fail(c, VRDD_ERR_INVALID, "render_brick: decode with linear planes kept first");
+    if (!vol.decoded || !(vol.lin[comp] || vol.brick[comp]))
+        return fail(c, VRDD_ERR_INVALID, "render_brick: decode with VRDD_SAMPLER_BRICKED or VRDD_SAMPLER_LINEAR first");
     if (iw <= 0 || ih <= 0 || !d_out || (pass == 2 && !d_alpha_in)) return fail(c, VRDD_ERR_INVALID, "render_brick: bad arguments");
     BrickArgs A;
-    A.plane = vol.lin[comp];
+    A.bricked = vol.brick[comp] != nullptr;
+    A.plane = A.bricked ? vol.brick[comp] : vol.lin[comp];
+    A.bW = c->bW; A.bH = c->bH;
     A.sx = c->W; A.sy = c->H; A.sz = c->D;
     A.gw = b.gw; A.gh = b.gh; A.gd = b.gd; A.ox = b.ox; A.oy = b.oy; A.oz = b.oz;
     for (int i = 0; i < 3; ++i) { A.lo[i] = b.lo[i]; A.hi[i] = b.hi[i]; }
