@@ -72,7 +72,8 @@ typedef struct vrdd_render_params {
     int max_steps;            /* 500    */
     float opacity_threshold;  /* 0.95f  */
     int query_method;         /* 1,2,3 = mean/variance/entropy of the original histograms,
-                                 4,5,6 = same of the fractal-decoded ones (volumeRender.cpp:129) */
+                                 4,5,6 = same of the fractal-decoded ones, 7 = interpolated mean
+                                 (volumeRender.cpp:129); 8/9/0 (flexible blocks) are not built */
 } vrdd_render_params;
 
 /* Image-space partition for multi-GPU rendering: the image is cut into tile_w x tile_h
@@ -155,6 +156,9 @@ int vrdd_get_decoded_host(vrdd_handle h, int source, float* out4);
  * NCCL all-gather of z-slabs across ranks. */
 int vrdd_get_decoded_planes_device(vrdd_handle h, int source, float** mean, float** variance,
                                    float** entropy);
+/* queryMethod 7 (the reference's "interpolated mean", volumeRender_kernel.cu:320-367, 395-480) blends
+ * the UN-normalised block means.  Enable before decoding the raw histograms to keep them (4 B/voxel). */
+int vrdd_enable_interpolated_mean(vrdd_handle h, int enable);
 /* Keep linear planes next to the texture arrays (needed for the call above and for
  * vrdd_commit_planes).  Off by default: the decode then writes the arrays directly. */
 int vrdd_keep_linear_planes(vrdd_handle h, int keep);
@@ -255,6 +259,10 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);
  * the ray caster's texture object.  For the filter-model conformance test.  Device ptrs. */
 int vrdd_debug_sample_texture(vrdd_handle h, int source, int comp, const float* d_uvw, int n,
                               float* d_out);
+/* Same with a POINT-filtered view of the same array (what the reference's block-index texture `tex`
+ * is, volumeRender_kernel.cu:2161-2165): used to measure the unit's nearest-texel rule. */
+int vrdd_debug_sample_texture_point(vrdd_handle h, int source, int comp, const float* d_uvw, int n,
+                                    float* d_out);
 /* Same for the transfer-function texture: out4[i] = tex1D(transferTex, u[i]).  Device ptrs. */
 int vrdd_debug_sample_transfer_function(vrdd_handle h, const float* d_u, int n, float* d_out4);
 

@@ -54,6 +54,11 @@ class Oracle:
         L.vrdd_oracle_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int,
                                          _f32p, _u32p, C.POINTER(RenderParams)]
         L.vrdd_oracle_render.restype = C.c_int64
+        L.vrdd_oracle_render_mode7.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _f32p, _u32p,
+                                               C.POINTER(RenderParams)]
+        L.vrdd_oracle_render_mode7.restype = C.c_int64
+        L.vrdd_oracle_point_index.argtypes = [C.c_float, C.c_int]
+        L.vrdd_oracle_point_index.restype = C.c_int
         L.vrdd_oracle_tex3d.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                         C.c_float, C.c_int]
         L.vrdd_oracle_tex3d.restype = C.c_float
@@ -139,6 +144,23 @@ class Oracle:
                                         None if vf is None else vf.ctypes.data, W, H, D, tf, tf.shape[0],
                                         np.ascontiguousarray(view, np.float32), out, C.byref(P))
         return out, int(s)
+
+    def render_mode7(self, hist, dims, view, image=(512, 512), tf=None, density=0.05, brightness=1.0,
+                     transfer_offset=0.0, transfer_scale=1.0, tstep=0.01, max_steps=500, opacity_threshold=0.95):
+        """queryMethod 7 (interpolated mean) straight from the raw histograms."""
+        W, H, D = dims
+        iw, ih = image
+        hist = np.ascontiguousarray(hist, np.float32)
+        tf = self.default_transfer_function() if tf is None else np.ascontiguousarray(tf, np.float32)
+        out = np.zeros((ih, iw), np.uint32)
+        P = RenderParams(iw, ih, density, brightness, transfer_offset, transfer_scale, 7, tstep, max_steps,
+                         opacity_threshold, 3, 0, ih)
+        s = self.lib.vrdd_oracle_render_mode7(hist, W, H, D, hist.shape[1], tf, tf.shape[0],
+                                              np.ascontiguousarray(view, np.float32), out, C.byref(P))
+        return out, int(s)
+
+    def point_index(self, u, n):
+        return int(self.lib.vrdd_oracle_point_index(u, n))
 
     def tex3d(self, vol4, dims, comp, u, v, w, weight_quant=3):
         W, H, D = dims

@@ -37,6 +37,12 @@ def test_reference_call_sequence(oracle):
         # an fp32 rounding; the +-1 LSB bar still holds
         assert d.max() <= 1, (qm, int(d.max()), int((d > 1).sum()))
         assert 0.3 * ref.size < (ref != 0).sum() <= 116281        # 116 281 rays hit the box at this view
+    d_out.zero_()
+    L.render_kernel(d_out, w, h, query_method=7, volume_size=dims)           # interpolated mean (:395-480)
+    torch.cuda.synchronize()
+    ref7, _ = oracle.render_mode7(hist, dims, np.array(view, np.float32), image=(w, h))
+    got = d_out.cpu().numpy().view(np.uint8).astype(np.int16)
+    assert np.abs(got - ref7.view(np.uint8).reshape(got.shape).astype(np.int16)).max() <= 1
     L.freeCudaBuffers()                                          # cleanup :462
     assert not L.handle()
     L.freeCudaBuffers()                                          # idempotent, unlike the reference (:2360-2385)

@@ -214,7 +214,10 @@ def test_unsupported_modes_are_errors(renderer, golden):
     r = renderer
     _load_golden_volume(r, V, golden)
     out = torch.zeros(8, 8, dtype=torch.int32, device="cuda")
-    for qm in (0, 7, 8, 9, 12):
+    with pytest.raises(V.VrddError) as e:                              # mode 7 needs the un-normalised means
+        r.render(out, 8, 8, V.default_render_params(query_method=7))
+    assert e.value.code == V.ERR_INVALID
+    for qm in (0, 8, 9, 12):
         with pytest.raises(V.VrddError) as e:
             r.render(out, 8, 8, V.default_render_params(query_method=qm))
         assert e.value.code == V.ERR_UNSUPPORTED
@@ -272,3 +275,30 @@ def test_transfer_function_texture_matches_the_filter_model(renderer, oracle):
         hw = d_out.cpu().numpy()
         model = np.stack([oracle.tex1d4(tab, float(x)) for x in u])
         assert np.abs(hw - model).max() <= 2e-7, (n, float(np.abs(hw - model).max()))
+
+
+@pytest.mark.parametrize("dims,img,rot", [((50, 50, 10), (512, 512), (0.0, 0.0)), ((12, 10, 8), (160, 120), (25.0, 40.0)),
+                                          ((33, 17, 9), (200, 150), (-35.0, 200.0))])
+def test_interpolated_mean_mode7(renderer, oracle, dims, img, rot):
+    """queryMethod 7 (volumeRender_kernel.cu:320-367, 395-480) incl. its division-by-zero artefact and the
+    texture unit's nearest-texel rule at coordinates that sit exactly on texel boundaries."""
+    import vrdd_b200 as V
+    hist = oracle.synth_histograms(21, dims)
+    r = renderer
+    r.enable_interpolated_mean(True)
+    r.set_volume(*dims)
+    r.set_histograms_host(hist)
+    r.decode(V.SRC_ORIGINAL)
+    view = oracle.view_matrix(*rot)
+    r.set_view(view)
+    r.count_samples(True)
+    ref, s = oracle.render_mode7(hist, dims, view, image=img)
+    got = _render(r, V, img[0], img[1], query_method=7)
+    assert _close_counts(r.get_sample_count(), s)
+    d = _lsb_diff(got, ref)
+    assert d.max() <= 1, (int(d.max()), int((d > 1).sum()))
+    assert (ref != 0).mean() > 0.1
+    # modes 1..6 are untouched by the extra plane
+    vol = oracle.decode_hist(hist)
+    ref1, _ = oracle.render(vol, dims, view, image=img, query_method=1)
+    assert _lsb_diff(_render(r, V, img[0], img[1], query_method=1), ref1).max() <= 1

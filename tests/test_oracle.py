@@ -358,3 +358,27 @@ def test_synth_invariants(oracle):
     # slabs of a volume are the volume
     part = oracle.synth_histograms(5, dims, z0=4, nz=3)
     assert np.array_equal(part, h.reshape(12, -1, 32)[4:7].reshape(-1, 32))
+
+
+def test_point_sampling_rule_known_answers(oracle):
+    """Nearest-texel rule measured on the B200 texture unit (tools/probe_texture3.py): the coordinate is
+    truncated to 21 fractional bits, so u = fl(k/N) usually reads texel k-1.  Recorded hardware answers."""
+    assert [oracle.point_index(np.float32(k) / np.float32(50), 50) for k in range(13)] == [0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]
+    assert [oracle.point_index(np.float32(k) / np.float32(10), 10) for k in range(11)] == [0, 0, 1, 2, 3, 5, 5, 6, 7, 8, 9]
+    assert oracle.point_index(float("nan"), 7) == 0 and oracle.point_index(2.0, 7) == 6 and oracle.point_index(-1.0, 7) == 0
+
+
+def test_mode7_uniform_volume_and_artefact(oracle):
+    """All blocks equal -> every blend of equal means is that mean (or NaN where the cell degenerates):
+    hit pixels carry TF(50 * mean_raw) composited along the ray, or less where NaN samples (TF texel 0) fell."""
+    dims = (4, 4, 4)
+    hist = np.zeros((64, 32), np.float32); hist[:, 8] = 1.0         # mean_raw = bw * 8.5
+    img, s = oracle.render_mode7(hist, dims, oracle.view_matrix(), image=(64, 64), density=0.01, opacity_threshold=2.0)
+    bw = float(np.float32(np.float32(0.0217) / np.float32(32)))
+    sample = 50 * bw * 8.5                                          # 0.288 -> between TF texels 2 and 3
+    px = int(img[30, 30])
+    assert px != 0 and (px & 255) > 0                               # red channel present (rainbow texels 1..3 are red-ish)
+    assert s > 0 and 0.25 < sample < 0.33
+    # the reference's artefact: rays whose x or y texture coordinate is exactly a cell boundary (the image
+    # centre row/column here, pos01 = 0.5 -> 0.5*4 = 2) blend with 0/0 and stay transparent
+    assert img[32, 32] == 0 and img[32, 40] == 0 and img[40, 32] == 0 and img[40, 40] != 0

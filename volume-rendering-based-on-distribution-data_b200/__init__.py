@@ -33,6 +33,7 @@ EXPORTS = [
     "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_count_samples",
     "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
     "vrdd_set_variant", "vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function",
+    "vrdd_debug_sample_texture_point", "vrdd_enable_interpolated_mean",
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
@@ -113,6 +114,7 @@ def lib():
             "vrdd_get_decoded_host": (i32, [vp, i32, vp]),
             "vrdd_get_decoded_planes_device": (i32, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
             "vrdd_keep_linear_planes": (i32, [vp, i32]),
+            "vrdd_enable_interpolated_mean": (i32, [vp, i32]),
             "vrdd_commit_planes": (i32, [vp, i32, i32, i32]),
             "vrdd_reconstruct_fractal_device": (i32, [vp, vp]),
             "vrdd_set_transfer_function": (i32, [vp, vp, i32]),
@@ -128,6 +130,7 @@ def lib():
             "vrdd_set_variant": (i32, [vp, C.c_char_p, C.c_char_p]),
             "vrdd_debug_sample_texture": (i32, [vp, i32, i32, vp, i32, vp]),
             "vrdd_debug_sample_transfer_function": (i32, [vp, vp, i32, vp]),
+            "vrdd_debug_sample_texture_point": (i32, [vp, i32, i32, vp, i32, vp]),
             "vrdd_render_brick_alpha": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_compose_alpha_in": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, i32]),
             "vrdd_render_brick_color": (i32, [vp, vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
@@ -260,6 +263,9 @@ class Renderer:
     def set_sampler(self, sampler):
         self._ck(lib().vrdd_set_sampler(self._h, sampler))
 
+    def enable_interpolated_mean(self, enable=True):
+        self._ck(lib().vrdd_enable_interpolated_mean(self._h, int(enable)))
+
     def keep_linear_planes(self, keep=True):
         self._ck(lib().vrdd_keep_linear_planes(self._h, int(keep)))
 
@@ -347,6 +353,9 @@ class Renderer:
     def debug_sample_texture(self, source, comp, d_uvw, n, d_out):
         self._ck(lib().vrdd_debug_sample_texture(self._h, source, comp, _ptr(d_uvw), n, _ptr(d_out)))
 
+
+    def debug_sample_texture_point(self, source, comp, d_uvw, n, d_out):
+        self._ck(lib().vrdd_debug_sample_texture_point(self._h, source, comp, _ptr(d_uvw), n, _ptr(d_out)))
 
     def debug_sample_transfer_function(self, d_u, n, d_out4):
         self._ck(lib().vrdd_debug_sample_transfer_function(self._h, _ptr(d_u), n, _ptr(d_out4)))

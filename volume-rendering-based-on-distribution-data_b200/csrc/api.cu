@@ -32,6 +32,7 @@ void free_volume(vrdd_decoded_volume& v) {
         if (v.lin[i]) cudaFree(v.lin[i]);
         if (v.brick[i]) cudaFree(v.brick[i]);
     }
+    if (v.mean_raw) cudaFree(v.mean_raw);
     v = vrdd_decoded_volume();
 }
 
@@ -104,6 +105,8 @@ int ensure_volume_storage(vrdd_context* c, int source) {
             VRDD_CUDA(c, cudaMemsetAsync(v.brick[i], 0, sizeof(float) * brick_elems(c), c->stream));
         }
     }
+    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw)
+        VRDD_CUDA(c, cudaMalloc(&v.mean_raw, sizeof(float) * c->V));
     return VRDD_OK;
 }
 
@@ -115,6 +118,7 @@ DecodeOut make_decode_out(vrdd_context* c, int source, long long v_base) {
         o.surf[i] = v.surf[i];
         o.brick[i] = v.brick[i];
     }
+    o.mean_raw = (source == VRDD_SRC_ORIGINAL) ? v.mean_raw : nullptr;
     o.use_surf = v.surf[0] != 0;
     o.W = c->W; o.H = c->H; o.D = c->D;
     o.v_base = v_base;
@@ -334,6 +338,12 @@ int vrdd_set_sampler(vrdd_handle h, int sampler) {
     if (sampler != VRDD_SAMPLER_TEXTURE && sampler != VRDD_SAMPLER_BRICKED && sampler != VRDD_SAMPLER_LINEAR)
         return fail(c, VRDD_ERR_INVALID, "set_sampler: unknown sampler");
     c->sampler = sampler;
+    return VRDD_OK;
+}
+
+int vrdd_enable_interpolated_mean(vrdd_handle h, int enable) {
+    CHECK_HANDLE(h);
+    c->keep_mean_raw = enable != 0;
     return VRDD_OK;
 }
 
@@ -665,6 +675,28 @@ int vrdd_debug_sample_texture(vrdd_handle h, int source, int comp, const float* 
     if (source < 0 || source > 1 || comp < 0 || comp > 2 || !c->vol[source].tex[comp])
         return fail(c, VRDD_ERR_INVALID, "debug_sample_texture: no texture volume");
     return launch_debug_sample(c, c->vol[source].tex[comp], d_uvw, n, d_out);
+}
+
+int vrdd_debug_sample_texture_point(vrdd_handle h, int source, int comp, const float* d_uvw, int n, float* d_out) {
+    CHECK_HANDLE(h);
+    if (source < 0 || source > 1 || comp < 0 || comp > 2 || !c->vol[source].arr[comp])
+        return fail(c, VRDD_ERR_INVALID, "debug_sample_texture_point: no texture volume");
+    cudaResourceDesc rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->vol[source].arr[comp];
+    cudaTextureDesc td;
+    std::memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    cudaTextureObject_t tex = 0;
+    VRDD_CUDA(c, cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    int rc = launch_debug_sample(c, tex, d_uvw, n, d_out);
+    cudaStreamSynchronize(c->stream);
+    cudaDestroyTextureObject(tex);
+    return rc;
 }
 
 int vrdd_debug_sample_transfer_function(vrdd_handle h, const float* d_u, int n, float* d_out4) {

@@ -26,6 +26,7 @@ struct DecodeOut {
     float* lin[3];                   // linear planes float[V], x fastest (or nullptr)
     cudaSurfaceObject_t surf[3];     // 3-D cudaArray planes (valid iff use_surf)
     float* brick[3];                 // bricked planes (or nullptr)
+    float* mean_raw;                 // un-normalised block means, linear (queryMethod 7), or nullptr
     int W, H, D;
     int use_surf;
     long long v_base;                // global index of local voxel 0
@@ -168,6 +169,7 @@ struct vrdd_decoded_volume {
     cudaTextureObject_t tex[3] = {0, 0, 0};
     cudaSurfaceObject_t surf[3] = {0, 0, 0};
     float* brick[3] = {nullptr, nullptr, nullptr};
+    float* mean_raw = nullptr;       // un-normalised bin-centre mean per block, linear (queryMethod 7)
     bool decoded = false;
 };
 
@@ -203,6 +205,7 @@ struct vrdd_context {
     vrdd_decoded_volume vol[2];
     int sampler = VRDD_SAMPLER_TEXTURE;
     bool keep_linear = false;
+    bool keep_mean_raw = false;      // vrdd_enable_interpolated_mean
 
     // transfer function
     cudaArray_t tf_arr = nullptr;

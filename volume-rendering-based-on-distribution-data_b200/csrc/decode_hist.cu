@@ -45,10 +45,12 @@ __device__ __forceinline__ void finish_and_emit(const DecodeOut& out, long long 
     const float inv_mean_norm = (float)(1.0 / VRDD_MEAN_NORM);
     const float inv_var_norm = (float)(1.0 / VRDD_VAR_NORM);
     const float inv_log2_bins = 1.0f / 5.0f;        // 1 / log2(32)
+    if (out.mean_raw) out.mean_raw[out.v_base + v] = mean_raw;
     emit_decoded(out, v, mean_raw * inv_mean_norm, var_raw * inv_var_norm, -plogp * inv_log2_bins);
 }
 __device__ __forceinline__ void finish_and_emit_xyz(const DecodeOut& out, long long v, int x, int y, int z, float mean_raw,
                                                     float var_raw, float plogp) {
+    if (out.mean_raw) out.mean_raw[out.v_base + v] = mean_raw;
     emit_decoded_xyz(out, v, x, y, z, mean_raw * (float)(1.0 / VRDD_MEAN_NORM), var_raw * (float)(1.0 / VRDD_VAR_NORM),
                      -plogp * (1.0f / 5.0f));
 }

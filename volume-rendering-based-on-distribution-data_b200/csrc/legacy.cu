@@ -37,6 +37,7 @@ void initCuda(void* h_volume, cudaExtent volumeSize, cudaExtent histogramSize, i
                              (int)histogramSize.width);
     report("initCuda/set_volume", rc);
     if (rc != VRDD_OK) return;
+    vrdd_enable_interpolated_mean(g_handle, 1);                                  // queryMethod 7 stays available
     if (h_volume) report("initCuda/histograms", vrdd_set_histograms_host(g_handle, static_cast<const float*>(h_volume)));
     g_have_fractal = false;
     if (h_codebook && h_templates && h_errorsbook) {

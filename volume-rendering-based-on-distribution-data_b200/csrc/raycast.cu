@@ -238,6 +238,119 @@ __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
     }
 }
 
+// ---- queryMethod 7: interpolated mean (volumeRender_kernel.cu:253-270, 320-367, 395-480) ---------------
+// The eight corners of the cell around the sample are floor/ceil(pos01*dim)/dim; each corner point-samples
+// the block-index texture (nearest-texel rule of the texture unit: idx = (trunc(sat(u)*2^21) * N) >> 21,
+// measured with tools/probe_texture3.py) and takes that block's un-normalised mean; the sample is their
+// trilinear blend in double precision times 50.  The corner cache is refreshed when the sample leaves the
+// cell.  When pos01*dim is an integer the blend divides by zero and the sample is NaN — the reference's
+// "vertical and horizontal line" artefact (ver1.9.6.txt:166); a NaN transfer-function coordinate reads
+// texel 0, as on the hardware.  The reference runs this mode below 5 fps (ver1.9.6.txt:168) because it
+// re-reads 8x32 histogram bins at every refresh; here the means are decoded once.
+__device__ __forceinline__ int point_index_hw(float u, int n) {
+    const unsigned U = (unsigned)(__saturatef(u) * 2097152.0f);
+    const unsigned long long i = ((unsigned long long)U * (unsigned)n) >> 21;
+    return (int)min(i, (unsigned long long)(n - 1));
+}
+
+struct Mode7Args {
+    const float* mean_raw;
+    int W, H, D;
+    const float4* tf_tab;
+    int tf_n;
+    uint32_t* out;
+    int iw, ih;
+    float m[12];
+    float density, brightness, t_offset, t_scale, tstep, thresh;
+    int max_steps, clear_misses;
+    unsigned long long* samples;
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) raycast_mode7_kernel(const Mode7Args A) {
+    __shared__ float4 tf_s[VRDD_MAX_TF];
+    for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
+    __syncthreads();
+    const int blocks_x = (A.iw + 15) / 16;
+    const int by = blockIdx.x / blocks_x, bx = blockIdx.x - by * blocks_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = bx * 16 + (warp & 1) * 8 + (lane & 7), y = by * 16 + (warp >> 1) * 4 + (lane >> 3);
+    unsigned long long nsamp = 0;
+    if (x < A.iw && y < A.ih) {
+        const float u = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)A.iw), 2.0f), 1.0f);
+        const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)A.ih), 2.0f), 1.0f);
+        const float ox = A.m[3], oy = A.m[7], oz = A.m[11];
+        float dx0 = u, dy0 = v, dz0 = -2.0f;
+        const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
+        const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+        dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
+        const float dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[0]), __fmul_rn(dy0, A.m[1])), __fmul_rn(dz0, A.m[2]));
+        const float dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[4]), __fmul_rn(dy0, A.m[5])), __fmul_rn(dz0, A.m[6]));
+        const float dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[8]), __fmul_rn(dy0, A.m[9])), __fmul_rn(dz0, A.m[10]));
+        const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
+        const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, ox));
+        const float by0 = __fmul_rn(iy, __fsub_rn(-1.0f, oy)), by1 = __fmul_rn(iy, __fsub_rn(1.0f, oy));
+        const float bz0 = __fmul_rn(iz, __fsub_rn(-1.0f, oz)), bz1 = __fmul_rn(iz, __fsub_rn(1.0f, oz));
+        float tnear = fmaxf(fmaxf(fminf(bx1, bx0), fminf(by1, by0)), fmaxf(fminf(bx1, bx0), fminf(bz1, bz0)));
+        const float tfar = fminf(fminf(fmaxf(bx1, bx0), fmaxf(by1, by0)), fminf(fmaxf(bx1, bx0), fmaxf(bz1, bz0)));
+        if (tfar > tnear) {
+            if (tnear < 0.0f) tnear = 0.0f;
+            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, t = tnear;
+            float px = __fadd_rn(ox, __fmul_rn(dx, tnear)), py = __fadd_rn(oy, __fmul_rn(dy, tnear)),
+                  pz = __fadd_rn(oz, __fmul_rn(dz, tnear));
+            const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
+            const float fW = (float)A.W, fH = (float)A.H, fD = (float)A.D;
+            float botx, boty, botz, topx, topy, topz, mean[8];
+            auto refresh = [&](float cx, float cy, float cz) {                       // :322-367, :398-463
+                botx = __fdiv_rn(floorf(__fmul_rn(cx, fW)), fW); topx = __fdiv_rn(ceilf(__fmul_rn(cx, fW)), fW);
+                boty = __fdiv_rn(floorf(__fmul_rn(cy, fH)), fH); topy = __fdiv_rn(ceilf(__fmul_rn(cy, fH)), fH);
+                botz = __fdiv_rn(floorf(__fmul_rn(cz, fD)), fD); topz = __fdiv_rn(ceilf(__fmul_rn(cz, fD)), fD);
+                const int x0 = point_index_hw(botx, A.W), x1 = point_index_hw(topx, A.W);
+                const int y0 = point_index_hw(boty, A.H), y1 = point_index_hw(topy, A.H);
+                const int z0 = point_index_hw(botz, A.D), z1 = point_index_hw(topz, A.D);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const size_t idx = (size_t)((j & 1) ? x1 : x0) + (size_t)A.W * (((j & 2) ? y1 : y0) + (size_t)A.H * ((j & 4) ? z1 : z0));
+                    mean[j] = __ldg(A.mean_raw + idx);
+                }
+            };
+            refresh(fmaf(px, 0.5f, 0.5f), fmaf(py, 0.5f, 0.5f), fmaf(pz, 0.5f, 0.5f));
+            for (int i = 0; i < A.max_steps; ++i) {
+                const float cx = fmaf(px, 0.5f, 0.5f), cy = fmaf(py, 0.5f, 0.5f), cz = fmaf(pz, 0.5f, 0.5f);
+                if (cx < botx || cy < boty || cz < botz || cx > topx || cy > topy || cz > topz) refresh(cx, cy, cz);   // :396
+                const double xd = (double)__fdiv_rn(__fsub_rn(cx, botx), __fsub_rn(topx, botx));     // :466-471
+                const double yd = (double)__fdiv_rn(__fsub_rn(cy, boty), __fsub_rn(topy, boty));
+                const double zd = (double)__fdiv_rn(__fsub_rn(cz, botz), __fsub_rn(topz, botz));
+                const float m00 = (float)((double)mean[0] * (1.0 - xd) + (double)mean[1] * xd);       // :472-478
+                const float m10 = (float)((double)mean[2] * (1.0 - xd) + (double)mean[3] * xd);
+                const float m01 = (float)((double)mean[4] * (1.0 - xd) + (double)mean[5] * xd);
+                const float m11 = (float)((double)mean[6] * (1.0 - xd) + (double)mean[7] * xd);
+                const float m0 = (float)((double)m00 * (1.0 - yd) + (double)m10 * yd);
+                const float m1 = (float)((double)m01 * (1.0 - yd) + (double)m11 * yd);
+                const float s = (float)((double)m0 * (1.0 - zd) + (double)m1 * zd) * 50.0f;          // :479
+                if (COUNT) ++nsamp;
+                float4 col = tf_lookup_smem(tf_s, A.tf_n, (s - A.t_offset) * A.t_scale);
+                col.w *= A.density;
+                col.x *= col.w; col.y *= col.w; col.z *= col.w;
+                const float kk = 1.0f - sa;
+                sr += col.x * kk; sg += col.y * kk; sb += col.z * kk; sa += col.w * kk;
+                if (sa > A.thresh) break;
+                t = __fadd_rn(t, A.tstep);
+                if (t > tfar) break;
+                px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+            }
+            A.out[(size_t)y * A.iw + x] = pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);
+        } else if (A.clear_misses) {
+            A.out[(size_t)y * A.iw + x] = 0u;
+        }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, d);
+        if (lane == 0 && nsamp) atomicAdd(A.samples, nsamp);
+    }
+}
+
 __global__ void debug_sample_kernel(cudaTextureObject_t tex, const float* __restrict__ uvw, int n,
                                     float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,9 +384,30 @@ void launch_variant(bool count, int grid, cudaStream_t st, const RayArgs& A, int
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses) {
     const int qm = p.query_method;
+    if (qm == 7) {
+        vrdd_decoded_volume& v0 = c->vol[VRDD_SRC_ORIGINAL];
+        if (!v0.decoded || !v0.mean_raw)
+            return fail(c, VRDD_ERR_INVALID, "render: queryMethod 7 needs vrdd_enable_interpolated_mean before the decode");
+        if (iw <= 0 || ih <= 0 || !d_out) return fail(c, VRDD_ERR_INVALID, "render: bad image");
+        if (part.parts != 1) return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod 7 does not take a tile partition");
+        Mode7Args A;
+        A.mean_raw = v0.mean_raw; A.W = c->W; A.H = c->H; A.D = c->D;
+        A.tf_tab = reinterpret_cast<const float4*>(c->tf_dev); A.tf_n = c->tf_n;
+        A.out = d_out; A.iw = iw; A.ih = ih;
+        for (int i = 0; i < 12; ++i) A.m[i] = c->view[i];
+        A.density = p.density; A.brightness = p.brightness; A.t_offset = p.transfer_offset; A.t_scale = p.transfer_scale;
+        A.tstep = p.tstep; A.thresh = p.opacity_threshold; A.max_steps = p.max_steps; A.clear_misses = clear_misses;
+        A.samples = c->d_samples;
+        const int grid7 = ((iw + 15) / 16) * ((ih + 15) / 16);
+        if (c->count_samples && c->d_samples) raycast_mode7_kernel<true><<<grid7, kBlock, 0, c->stream>>>(A);
+        else raycast_mode7_kernel<false><<<grid7, kBlock, 0, c->stream>>>(A);
+        c->launches += 1;
+        VRDD_CUDA(c, cudaGetLastError());
+        return VRDD_OK;
+    }
     if (qm < 1 || qm > 6)
-        return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod must be 1..6 (7 and the flexible-block "
-                                             "modes 8/9/0 are not built; SURVEY.md §8f)");
+        return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod must be 1..7 (the flexible-block modes 8/9/0 "
+                                             "are not built; SURVEY.md §8f)");
     const int source = (qm >= 4) ? VRDD_SRC_FRACTAL : VRDD_SRC_ORIGINAL;
     const int comp = (qm - 1) % 3;
     vrdd_decoded_volume& vol = c->vol[source];
