@@ -334,12 +334,27 @@ def run_ours(args):
     part = V.TilePartition(D.TILE, D.TILE, rank, world) if world > 1 else None
     img = torch.zeros(fh, fw, dtype=torch.int32, device=dev)
     red = torch.zeros_like(img) if world > 1 else None
+    # N > 1, --assemble p2p: rank 0 owns two frames (double buffer); every other rank maps them (CUDA IPC) and
+    # its ray-cast kernel stores its tiles straight into rank 0's HBM over NVLink; one barrier orders a frame.
+    p2p = world > 1 and args.assemble == "p2p"
+    frames = None
+    if p2p:
+        nbytes = fw * fh * 4
+        mine = [r.frame_alloc(nbytes), r.frame_alloc(nbytes)] if rank == 0 else None
+        box = [[r.frame_export(p) for p in mine]] if rank == 0 else [None]
+        dist.broadcast_object_list(box, src=0)
+        frames = mine if rank == 0 else [r.frame_open(hb) for hb in box[0]]
+        red = V.as_torch(frames[0], (fh, fw), typestr="<i4", device=dev) if rank == 0 else None
 
     def render_step(k, params):
         r.set_view(orbit_view(V, k))
-        r.render(img, fw, fh, params, part=part, clear_misses=True)
-        if world > 1:
-            D.reduce_frame(img, red, dst=0)
+        if p2p:
+            r.render(frames[k & 1], fw, fh, params, part=part, clear_misses=True)
+            dist.barrier()                                    # frame k is complete on rank 0
+        else:
+            r.render(img, fw, fh, params, part=part, clear_misses=True)
+            if world > 1:
+                D.reduce_frame(img, red, dst=0)
 
     def count_samples(params, nviews):
         r.count_samples(True)
@@ -414,11 +429,14 @@ def run_ours(args):
         for k in range(args.warmup, args.warmup + args.steps):
             render_step(k, params)
             if rank == 0:
-                host_img.copy_(red, non_blocking=True)
+                src = V.as_torch(frames[k & 1], (fh, fw), typestr="<i4", device=dev) if p2p else red
+                host_img.copy_(src, non_blocking=True)
             torch.cuda.synchronize()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        call = "vrdd_set_view + vrdd_render (my tiles) + NCCL reduce to rank 0 + device->pinned-host frame copy"
+        call = ("vrdd_set_view + vrdd_render (my tiles, stored into rank 0's frame over NVLink) + barrier + "
+                "device->pinned-host frame copy") if p2p else \
+               "vrdd_set_view + vrdd_render (my tiles) + NCCL reduce to rank 0 + device->pinned-host frame copy"
     e2e = {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48 + 32,
            "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt, "call": call}
 
@@ -481,7 +499,9 @@ def run_ours(args):
                            "volume": [W, H, Dz], "image": [fw, fh], "sampler": args.sampler,
                            "partition": "single GPU" if world == 1 else
                            f"64x64 image tiles round-robin over {world} ranks; z-slab decode + NCCL all-gather of the "
-                           "decoded planes; NCCL reduce of frames to rank 0",
+                           "decoded planes; " + ("tiles stored by the ray-cast kernels into rank 0's frame over NVLink "
+                                                 "(CUDA IPC), one barrier per frame" if p2p else
+                                                 "NCCL reduce of frames to rank 0"),
                            "l2": f"inputs larger than L2 ({total_vox * 4 / 1e9:.1f} GB sampled plane, "
                                  f"{launch_bytes / 1e9:.1f} GB per decode launch); no flush"},
                 "decode": decode, "roofline": roofline, "roofline_raycast": roofline_ray,
@@ -494,6 +514,10 @@ def run_ours(args):
         if cpu_ray:
             line["cpu_baseline"] = cpu_ray
         print(json.dumps(line), flush=True)
+    if p2p:
+        barrier()
+        for p in frames:
+            (r.frame_free if rank == 0 else r.frame_close)(p)
     r.close()
     if world > 1:
         dist.destroy_process_group()
@@ -673,6 +697,8 @@ def main():
     ap.add_argument("--workload", default="tiles", choices=["tiles", "sortlast"],
                     help="tiles: volume replicated, image-space tiles (default); sortlast: one VOL^3 brick per GPU")
     ap.add_argument("--image-sortlast", type=int, default=2048)
+    ap.add_argument("--assemble", default="p2p", choices=["p2p", "reduce"],
+                    help="N > 1 tiles: p2p = kernels store tiles into rank 0's frame over NVLink; reduce = NCCL reduce")
     ap.add_argument("--sortlast-layout", default="bricked", choices=["bricked", "linear"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -200,6 +200,19 @@ int vrdd_render_host(vrdd_handle h, uint32_t* h_output, int image_w, int image_h
 int vrdd_count_samples(vrdd_handle h, int enable);
 int vrdd_get_sample_count(vrdd_handle h, int64_t* out, int reset);
 
+/* ---- peer-visible frames: image-space partitions assembled by the ray-cast kernels themselves ------------
+ * A frame allocated here can be exported to the other ranks of the node (CUDA IPC).  A rank that opens it
+ * gets a device pointer into the owner's HBM and passes it to vrdd_render as d_output together with its
+ * vrdd_tile_partition: the kernel then stores its tiles straight into the owner's frame over NVLink — the
+ * gather of tiles costs no extra pass and no collective.  The caller orders frames (e.g. one barrier per
+ * frame) before the owner reads them. */
+#define VRDD_IPC_HANDLE_BYTES 64
+int vrdd_frame_alloc(vrdd_handle h, size_t bytes, void** d_frame);
+int vrdd_frame_free(vrdd_handle h, void* d_frame);
+int vrdd_frame_export(vrdd_handle h, const void* d_frame, unsigned char* ipc_handle /* [64] */);
+int vrdd_frame_open(vrdd_handle h, const unsigned char* ipc_handle /* [64] */, void** d_peer_frame);
+int vrdd_frame_close(vrdd_handle h, void* d_peer_frame);
+
 /* ---- sort-last rendering of a brick-decomposed volume (volumes larger than one GPU's HBM;
  *      new work, the reference is single-GPU; scheme in csrc/sortlast.cu) ------------------------- */
 

@@ -302,3 +302,20 @@ def test_interpolated_mean_mode7(renderer, oracle, dims, img, rot):
     vol = oracle.decode_hist(hist)
     ref1, _ = oracle.render(vol, dims, view, image=img, query_method=1)
     assert _lsb_diff(_render(r, V, img[0], img[1], query_method=1), ref1).max() <= 1
+
+
+def test_peer_visible_frame_roundtrip(renderer, golden):
+    """vrdd_frame_alloc / export: a library-owned frame is a valid render target, and its IPC handle is
+    64 bytes (opening it needs a second process: covered by bench.py --gpus 2, profiles/)."""
+    import vrdd_b200 as V
+    r = renderer
+    _load_golden_volume(r, V, golden)
+    w, h = (int(v) for v in golden["img"])
+    r.set_view(golden["views"][0])
+    p = r.frame_alloc(w * h * 4)
+    assert len(r.frame_export(p)) == 64
+    r.render(p, w, h, V.default_render_params(query_method=1), clear_misses=True)
+    r.synchronize()
+    got = V.as_torch(p, (h, w), typestr="<i4").cpu().numpy().view(np.uint32)
+    assert _lsb_diff(got, golden["images"][0]).max() <= 1
+    r.frame_free(p)

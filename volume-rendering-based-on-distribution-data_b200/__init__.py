@@ -34,6 +34,7 @@ EXPORTS = [
     "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
     "vrdd_set_variant", "vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function",
     "vrdd_debug_sample_texture_point", "vrdd_enable_interpolated_mean",
+    "vrdd_frame_alloc", "vrdd_frame_free", "vrdd_frame_export", "vrdd_frame_open", "vrdd_frame_close",
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
@@ -136,6 +137,11 @@ def lib():
             "vrdd_render_brick_color": (i32, [vp, vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_pack_frame": (i32, [vp, vp, vp, i32, i32, f32]),
             "vrdd_synth_histograms_region_device": (i32, [vp, u32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+            "vrdd_frame_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
+            "vrdd_frame_free": (i32, [vp, vp]),
+            "vrdd_frame_export": (i32, [vp, vp, vp]),
+            "vrdd_frame_open": (i32, [vp, vp, C.POINTER(vp)]),
+            "vrdd_frame_close": (i32, [vp, vp]),
             # on-disk formats (include/vrdd_io.h)
             "vrdd_io_read_histograms": (i32, [C.c_char_p, C.c_size_t, i32, vp]),
             "vrdd_io_codebook_blocks": (C.c_int64, [C.c_char_p]),
@@ -326,6 +332,29 @@ class Renderer:
                                                  _ptr(d_errors), _ptr(d_chunk_offsets), _ptr(d_templates),
                                                  C.byref(tot)))
         return int(tot.value)
+
+    # peer-visible frames
+    def frame_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(lib().vrdd_frame_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def frame_free(self, ptr):
+        self._ck(lib().vrdd_frame_free(self._h, ptr))
+
+    def frame_export(self, ptr):
+        buf = (C.c_ubyte * 64)()
+        self._ck(lib().vrdd_frame_export(self._h, ptr, buf))
+        return bytes(buf)
+
+    def frame_open(self, handle_bytes):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle_bytes)
+        p = C.c_void_p()
+        self._ck(lib().vrdd_frame_open(self._h, buf, C.byref(p)))
+        return p.value
+
+    def frame_close(self, ptr):
+        self._ck(lib().vrdd_frame_close(self._h, ptr))
 
     # sort-last bricks
     def synth_histograms_region_device(self, seed, gdims, origin, z0, nz, d_hist):

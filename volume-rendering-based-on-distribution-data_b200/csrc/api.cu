@@ -593,6 +593,45 @@ int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, i
                                 d_templates, total_ne);
 }
 
+int vrdd_frame_alloc(vrdd_handle h, size_t bytes, void** d_frame) {
+    CHECK_HANDLE(h);
+    if (!d_frame || !bytes) return fail(c, VRDD_ERR_INVALID, "frame_alloc: bad arguments");
+    VRDD_CUDA(c, cudaMalloc(d_frame, bytes));            // a plain cudaMalloc block: exportable as a whole
+    VRDD_CUDA(c, cudaMemset(*d_frame, 0, bytes));
+    return VRDD_OK;
+}
+
+int vrdd_frame_free(vrdd_handle h, void* d_frame) {
+    CHECK_HANDLE(h);
+    VRDD_CUDA(c, cudaFree(d_frame));
+    return VRDD_OK;
+}
+
+int vrdd_frame_export(vrdd_handle h, const void* d_frame, unsigned char* ipc_handle) {
+    CHECK_HANDLE(h);
+    static_assert(sizeof(cudaIpcMemHandle_t) == VRDD_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!d_frame || !ipc_handle) return fail(c, VRDD_ERR_INVALID, "frame_export: bad arguments");
+    cudaIpcMemHandle_t hnd;
+    VRDD_CUDA(c, cudaIpcGetMemHandle(&hnd, const_cast<void*>(d_frame)));
+    std::memcpy(ipc_handle, &hnd, sizeof(hnd));
+    return VRDD_OK;
+}
+
+int vrdd_frame_open(vrdd_handle h, const unsigned char* ipc_handle, void** d_peer_frame) {
+    CHECK_HANDLE(h);
+    if (!d_peer_frame || !ipc_handle) return fail(c, VRDD_ERR_INVALID, "frame_open: bad arguments");
+    cudaIpcMemHandle_t hnd;
+    std::memcpy(&hnd, ipc_handle, sizeof(hnd));
+    VRDD_CUDA(c, cudaIpcOpenMemHandle(d_peer_frame, hnd, cudaIpcMemLazyEnablePeerAccess));
+    return VRDD_OK;
+}
+
+int vrdd_frame_close(vrdd_handle h, void* d_peer_frame) {
+    CHECK_HANDLE(h);
+    VRDD_CUDA(c, cudaIpcCloseMemHandle(d_peer_frame));
+    return VRDD_OK;
+}
+
 int vrdd_synth_histograms_region_device(vrdd_handle h, uint32_t seed, int gw, int gh, int gd, int ox, int oy, int oz,
                                         int z0, int nz, float* d_hist) {
     CHECK_HANDLE(h);

@@ -191,7 +191,7 @@ __global__ void build_moments_kernel(const float* __restrict__ tmpl, int T, doub
     m[68] = m[69] = m[70] = m[71] = 0.0;
 }
 
-__device__ __forceinline__ float xlog2x(float x) { return x * __log2f(fmaxf(x, 1.0e-37f)); }
+__device__ __forceinline__ float xlog2x(float x) { return x * fast_log2(fmaxf(x, 1.0e-37f)); }
 
 // Warps are independent: a warp owns 32 consecutive voxels (one entry of the error-offset
 // table), scans their NE with shuffles, stages its own errors in its own slice of shared
