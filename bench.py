@@ -343,8 +343,21 @@ def run_ours(args):
         mine = [r.frame_alloc(nbytes), r.frame_alloc(nbytes)] if rank == 0 else None
         box = [[r.frame_export(p) for p in mine]] if rank == 0 else [None]
         dist.broadcast_object_list(box, src=0)
-        frames = mine if rank == 0 else [r.frame_open(hb) for hb in box[0]]
-        red = V.as_torch(frames[0], (fh, fw), typestr="<i4", device=dev) if rank == 0 else None
+        ok = 1
+        try:
+            frames = mine if rank == 0 else [r.frame_open(hb) for hb in box[0]]
+        except V.VrddError:
+            ok = 0
+        t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:                      # some rank cannot map the frame: NCCL reduce instead
+            if rank == 0:
+                for p_ in mine:
+                    r.frame_free(p_)
+            elif ok:
+                for p_ in frames:
+                    r.frame_close(p_)
+            p2p, frames = False, None
 
     def render_step(k, params):
         r.set_view(orbit_view(V, k))
@@ -389,6 +402,15 @@ def run_ours(args):
         return max_over_ranks(e0.elapsed_time(e1)), r.kernel_launches() - l0
 
     params = V.default_render_params(query_method=1)
+    if p2p:
+        # the frame the kernels assemble in rank 0's HBM must be, bit for bit, the NCCL-reduced one
+        r.set_view(orbit_view(V, 7))
+        r.render(img, fw, fh, params, part=part, clear_misses=True)
+        D.reduce_frame(img, red, dst=0)
+        r.render(frames[0], fw, fh, params, part=part, clear_misses=True)
+        barrier()
+        if rank == 0 and not torch.equal(V.as_torch(frames[0], (fh, fw), typestr="<i4", device=dev), red):
+            raise SystemExit("bench.py: peer-assembled frame differs from the NCCL-reduced frame")
     nviews = min(ORBIT_VIEWS, args.warmup + args.steps)
     counts = count_samples(params, nviews)
     steps_samples = lambda c, w, s: sum(c[k % len(c)] for k in range(w, w + s))

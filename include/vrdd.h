@@ -260,6 +260,20 @@ int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, i
                               int nz, int32_t* d_codebook, float* d_errors,
                               uint64_t* d_chunk_offsets, float* d_templates, uint64_t* total_ne);
 
+/* ---- flexible-block chain, host stages only --------------------------------------
+ * The reference's dataProcessing() chain (volumeRender_kernel.cu:892-1796) is not built: its span tables are
+ * defined only by data files that do not ship.  The two stages the reference pins with known answers are:
+ *
+ * vrdd_flex_divide_blocks — d_divideBlock (:892-1031): partition a vx x vy x vz raw volume into blocks of
+ *   edge `block`; spans are 1-based and inclusive, the last block of an axis is clipped; blocks are numbered
+ *   x fastest.  spans = int32[n][6] = (lowX, lowY, lowZ, highX, highY, highZ); returns n (or the count
+ *   needed when spans == NULL), negative on bad arguments.
+ * vrdd_flex_prefix_spans — the decomposition inside d_queryBlockNew (:1248-1259): the prefix [1, x] as
+ *   power-of-two-aligned pieces, peeled from the least significant set bit: 25 -> [25,25], [17,24], [1,16].
+ *   spans = int32[n][2] = (low, high); returns n <= 32. */
+int vrdd_flex_divide_blocks(int vx, int vy, int vz, int block, int32_t* spans, int capacity);
+int vrdd_flex_prefix_spans(int x, int32_t* spans);
+
 /* ---- diagnostics ------------------------------------------------------------------------ */
 
 /* Selects a kernel variant by name for A/B measurement: "decode_hist" -> "tma" | "ldg";

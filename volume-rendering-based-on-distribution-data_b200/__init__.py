@@ -34,6 +34,7 @@ EXPORTS = [
     "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
     "vrdd_set_variant", "vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function",
     "vrdd_debug_sample_texture_point", "vrdd_enable_interpolated_mean",
+    "vrdd_flex_divide_blocks", "vrdd_flex_prefix_spans",
     "vrdd_frame_alloc", "vrdd_frame_free", "vrdd_frame_export", "vrdd_frame_open", "vrdd_frame_close",
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
@@ -137,6 +138,8 @@ def lib():
             "vrdd_render_brick_color": (i32, [vp, vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_pack_frame": (i32, [vp, vp, vp, i32, i32, f32]),
             "vrdd_synth_histograms_region_device": (i32, [vp, u32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+            "vrdd_flex_divide_blocks": (i32, [i32, i32, i32, i32, vp, i32]),
+            "vrdd_flex_prefix_spans": (i32, [i32, vp]),
             "vrdd_frame_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
             "vrdd_frame_free": (i32, [vp, vp]),
             "vrdd_frame_export": (i32, [vp, vp, vp]),

@@ -123,6 +123,41 @@ int vrdd_io_write_templates(const char* path, int bins, int n, const float* temp
     return VRDD_OK;
 }
 
+// d_divideBlock, volumeRender_kernel.cu:892-1031 (per-axis; the reference mixes the axes up for
+// non-cubic volumes, :949-1013, which only its cubic 64^3 data set never notices)
+int vrdd_flex_divide_blocks(int vx, int vy, int vz, int block, int32_t* spans, int capacity) {
+    if (vx <= 0 || vy <= 0 || vz <= 0 || block <= 0) return VRDD_ERR_INVALID;
+    const int nx = (vx + block - 1) / block, ny = (vy + block - 1) / block, nz = (vz + block - 1) / block;
+    const long long n = (long long)nx * ny * nz;
+    if (n > 0x7fffffff) return VRDD_ERR_INVALID;
+    if (!spans) return (int)n;
+    if (capacity < n) return VRDD_ERR_INVALID;
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                int32_t* s = spans + 6 * ((size_t)z * nx * ny + (size_t)y * nx + x);
+                s[0] = 1 + x * block; s[1] = 1 + y * block; s[2] = 1 + z * block;          // :937, 1-based
+                s[3] = (x == nx - 1) ? vx : (x + 1) * block;                               // :940-946, clipped
+                s[4] = (y == ny - 1) ? vy : (y + 1) * block;
+                s[5] = (z == nz - 1) ? vz : (z + 1) * block;
+            }
+    return (int)n;
+}
+
+// the bit trick of d_queryBlockNew, volumeRender_kernel.cu:1248-1259
+int vrdd_flex_prefix_spans(int x, int32_t* spans) {
+    if (x < 0 || !spans) return VRDD_ERR_INVALID;
+    int n = 0;
+    for (int i = 0; i < 31 && x != 0; ++i)
+        if (x & (1 << i)) {
+            spans[2 * n + 1] = x;
+            x &= ~(1 << i);
+            spans[2 * n] = x + 1;
+            ++n;
+        }
+    return n;
+}
+
 int vrdd_io_write_ppm(const char* path, const uint32_t* rgba, int width, int height) {
     File fp(path, "wb");
     if (!fp.f || !rgba || width <= 0 || height <= 0) return VRDD_ERR_INVALID;
