@@ -93,7 +93,8 @@ tj = {}
 if os.path.exists(bench) and "decode_hist" in traffic:
     b = json.loads(open(bench).read().strip().splitlines()[-1])
     t = traffic["decode_hist"]
-    tj[b["roofline"]["kernel"]] = {"algorithmic_bytes_per_launch": b["roofline"]["bytes_per_launch"],
+    rd = b.get("roofline_decode", b["roofline"])
+    tj[rd["kernel"]] = {"algorithmic_bytes_per_launch": rd["bytes_per_launch"],
                                    "dram_bytes_per_launch": t["dram_bytes_per_launch"], "dram_read": t["dram_read"],
                                    "dram_write": t["dram_write"], "source": f"profiles/ncu_raw_decode_hist_{tag}.csv"}
     if "raycast" in traffic:
