@@ -72,8 +72,8 @@ typedef struct vrdd_render_params {
     int max_steps;            /* 500    */
     float opacity_threshold;  /* 0.95f  */
     int query_method;         /* 1,2,3 = mean/variance/entropy of the original histograms,
-                                 4,5,6 = same of the fractal-decoded ones, 7 = interpolated mean
-                                 (volumeRender.cpp:129); 8/9/0 (flexible blocks) are not built */
+                                 4,5,6 = same of the fractal-decoded ones, 7 = interpolated mean,
+                                 8/9/0 = entropy/mean/variance of the flexible blocks (volumeRender.cpp:129) */
 } vrdd_render_params;
 
 /* Image-space partition for multi-GPU rendering: the image is cut into tile_w x tile_h
@@ -260,17 +260,47 @@ int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, i
                               int nz, int32_t* d_codebook, float* d_errors,
                               uint64_t* d_chunk_offsets, float* d_templates, uint64_t* total_ne);
 
-/* ---- flexible-block chain, host stages only --------------------------------------
- * The reference's dataProcessing() chain (volumeRender_kernel.cu:892-1796) is not built: its span tables are
- * defined only by data files that do not ship.  The two stages the reference pins with known answers are:
- *
+/* ---- flexible-block-size query chain (csrc/flex.cu) -----------------------------------
+ * Replaces dataProcessing() (volumeRender_kernel.cu:1735-1796) and the queryMethod 8/9/0 sampling of d_render.
+ * The span tables are the last nine arguments of initCuda (volumeRender_kernel.cu:1896-1900); the reference
+ * hard-codes their sizes (131 072 spans, 469 templates, 64 bins, 64^3 raw volume, :96-101), here they are explicit. */
+typedef struct vrdd_flex_tables {
+    int raw_w, raw_h, raw_d;        /* raw volume the spans refer to (rawVolumeDim, :104); each <= 1023           */
+    int bins;                       /* flexNBin = 64 (:97); the only supported value                              */
+    int n_fractal;                  /* spans of >= 8 voxels, fractal-coded                                        */
+    const int32_t* span_low;        /* int32[n_fractal][4] = (x, y, z, 0), 1-based inclusive   (h_codebookSpanLow)  */
+    const int32_t* span_high;       /* int32[n_fractal][4]                                     (h_codebookSpanHigh) */
+    const int32_t* codebook;        /* int32[n_fractal][4] = (templateId, shift, flip, NE)     (h_flexibleCodebook) */
+    const float* errors;            /* float[n_fractal][bins][2] = (binId, value), NE valid    (h_flexibleErrorsbook) */
+    int n_simple;                   /* spans of < 8 voxels, sparse histograms                                      */
+    const int32_t* simple_low;      /* int32[n_simple][4], 0-BASED inclusive (:1464-1471)      (h_simpleLow)        */
+    const int32_t* simple_high;     /* int32[n_simple][4]                                      (h_simpleHigh)       */
+    const int32_t* simple_count;    /* int32[n_simple]                                         (h_simpleCount)      */
+    const float* simple_hist;       /* float[n_simple][bins][2] = (binId, frequency)           (h_simpleHistogram)  */
+    int n_templates;
+    const float* templates;         /* float[n_templates][bins]                                (h_flexibleTemplates) */
+} vrdd_flex_tables;
+
+/* Copies and indexes the tables (hash on (low, high) instead of the reference's linear scans); rows whose
+ * span_low.x < 0 are padding.  Codes are checked against the loader's guards (VRDD_ERR_RANGE). */
+int vrdd_flex_set_tables_host(vrdd_handle h, const vrdd_flex_tables* tables);
+/* dataProcessing(): partitions the raw volume into blocks of edge block_size (the reference hard-codes 6, :1737),
+ * builds every block's histogram from the spans and leaves (mean, variance, entropy) per block ready for
+ * queryMethod 8 (entropy) / 9 (mean) / 0 (variance).  *spans_not_found (may be NULL; reading it synchronises)
+ * counts sub-spans missing from the tables (the reference prints "didn't find ..."). */
+int vrdd_flex_process(vrdd_handle h, int block_size, int64_t* spans_not_found);
+/* float4[nx*ny*nz] = (mean, variance, entropy, 0), blocks x fastest (flexBlockData, :890); dims3 = (nx, ny, nz).
+ * out4 may be NULL to query the dimensions. */
+int vrdd_flex_get_blocks_host(vrdd_handle h, float* out4, int* dims3);
+
+/* Host stages of the chain, usable on their own:
  * vrdd_flex_divide_blocks — d_divideBlock (:892-1031): partition a vx x vy x vz raw volume into blocks of
  *   edge `block`; spans are 1-based and inclusive, the last block of an axis is clipped; blocks are numbered
  *   x fastest.  spans = int32[n][6] = (lowX, lowY, lowZ, highX, highY, highZ); returns n (or the count
- *   needed when spans == NULL), negative on bad arguments.
+ *   needed when spans == NULL), negative on bad arguments.  Known answer: ver1.9.6.txt:77.
  * vrdd_flex_prefix_spans — the decomposition inside d_queryBlockNew (:1248-1259): the prefix [1, x] as
- *   power-of-two-aligned pieces, peeled from the least significant set bit: 25 -> [25,25], [17,24], [1,16].
- *   spans = int32[n][2] = (low, high); returns n <= 32. */
+ *   power-of-two-aligned pieces, peeled from the least significant set bit: 25 -> [25,25], [17,24], [1,16]
+ *   (presentation.pdf p.14).  spans = int32[n][2] = (low, high); returns n <= 32. */
 int vrdd_flex_divide_blocks(int vx, int vy, int vz, int block, int32_t* spans, int capacity);
 int vrdd_flex_prefix_spans(int x, int32_t* spans);
 
@@ -290,6 +320,10 @@ int vrdd_debug_sample_texture(vrdd_handle h, int source, int comp, const float* 
  * is, volumeRender_kernel.cu:2161-2165): used to measure the unit's nearest-texel rule. */
 int vrdd_debug_sample_texture_point(vrdd_handle h, int source, int comp, const float* d_uvw, int n,
                                     float* d_out);
+/* Same with UN-normalised coordinates and linear filtering (what flexBlockTex is,
+ * volumeRender_kernel.cu:1680-1686): d_uvw holds texel-space coordinates. */
+int vrdd_debug_sample_texture_unnorm(vrdd_handle h, int source, int comp, const float* d_uvw, int n,
+                                     float* d_out);
 /* Same for the transfer-function texture: out4[i] = tex1D(transferTex, u[i]).  Device ptrs. */
 int vrdd_debug_sample_transfer_function(vrdd_handle h, const float* d_u, int n, float* d_out4);
 

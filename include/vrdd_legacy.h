@@ -14,10 +14,10 @@
  *     instead of exit() inside checkCudaErrors;
  *   - freeCudaBuffers frees only what was allocated (the reference frees a never-allocated
  *     array and a shadowed global, volumeRender_kernel.cu:2362, 2366);
- *   - the flexible-block tables (last nine arguments of initCuda) are accepted and ignored,
- *     and dataProcessing() is a no-op that says so: the flexible-block chain
- *     (volumeRender_kernel.cu:892-1796) is SURVEY.md §8f row 1, not built yet; queryMethod
- *     8/9/0 render nothing.
+ *   - the flexible-block tables (last nine arguments of initCuda) may be NULL; then
+ *     dataProcessing() says so and queryMethod 8/9/0 are unavailable.  When given they must have
+ *     the sizes the reference hard-codes (131 072 spans each, 469 templates of 64 bins,
+ *     volumeRender_kernel.cu:96-101); rows with span_low.x < 0 are padding.
  */
 #ifndef VRDD_LEGACY_H_
 #define VRDD_LEGACY_H_

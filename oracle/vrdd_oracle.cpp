@@ -52,6 +52,8 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#include <array>
+#include <map>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -557,6 +559,205 @@ int64_t vrdd_oracle_render_mode7(const float* hist, int W, int H, int D, int B, 
 }
 
 int vrdd_oracle_point_index(float u, int N) { return point_index_hw(u, N); }
+
+/* ---- flexible-block-size query chain (volumeRender_kernel.cu:892-1796), SURVEY.md §8f row 1 --------------
+ * dataProcessing() = d_divideBlock -> d_queryBlockNew -> d_querySpanNew -> d_computeBlock -> bindToTex.
+ * The raw volume (64^3 in the reference) is described by 64-bin histograms of power-of-two-aligned boxes
+ * ("spans", 1-based inclusive); boxes of >= 8 voxels are fractal-coded, smaller ones are sparse "simple"
+ * histograms with 0-based coordinates (:1464-1471).  A block's histogram is the 8-corner inclusion-exclusion
+ * of prefix-box histograms (integral histogram), each prefix box being the weighted sum of the spans its
+ * corner decomposes into (:1248-1315).  Quirks kept: the lower corners use `low`, not `low - 1` (:1157-1227),
+ * so a block covers (low, high]; statistics use MaxHistogram = 255 and are not normalised (:1084-1098). */
+struct vrdd_oracle_flex_tables {
+    int raw_w, raw_h, raw_d, bins;
+    int n_fractal; const int32_t* span_low; const int32_t* span_high; const int32_t* codebook; const float* errors;
+    int n_simple;  const int32_t* simple_low; const int32_t* simple_high; const int32_t* simple_count; const float* simple_hist;
+    int n_templates; const float* templates;
+};
+
+static int prefix_pieces(int x, int (*out)[2]) {                  /* :1248-1259 */
+    int n = 0;
+    for (int i = 0; i < 31 && x != 0; ++i)
+        if (x & (1 << i)) { out[n][1] = x; x &= ~(1 << i); out[n][0] = x + 1; ++n; }
+    return n;
+}
+
+/* out4: float4[nx*ny*nz] = (mean, variance, entropy, 0), blocks x fastest; dims3 receives (nx, ny, nz).
+ * Returns the number of spans that were not found in the tables (the reference prints and reads garbage;
+ * here they contribute nothing). */
+int64_t vrdd_oracle_flex_process(const vrdd_oracle_flex_tables* T, int block, float* out4, int* dims3) {
+    const int B = T->bins;
+    typedef std::array<int, 6> Key;
+    std::map<Key, int> fr, si;
+    for (int i = 0; i < T->n_fractal; ++i)
+        fr.emplace(Key{T->span_low[4 * i], T->span_low[4 * i + 1], T->span_low[4 * i + 2], T->span_high[4 * i],
+                       T->span_high[4 * i + 1], T->span_high[4 * i + 2]}, i);      /* first match wins, like the linear scan */
+    for (int i = 0; i < T->n_simple; ++i)
+        si.emplace(Key{T->simple_low[4 * i], T->simple_low[4 * i + 1], T->simple_low[4 * i + 2], T->simple_high[4 * i],
+                       T->simple_high[4 * i + 1], T->simple_high[4 * i + 2]}, i);
+    const int vd[3] = {T->raw_w, T->raw_h, T->raw_d};
+    int nb[3];
+    for (int a = 0; a < 3; ++a) nb[a] = (vd[a] + block - 1) / block;              /* d_divideBlock, :892-1031 */
+    dims3[0] = nb[0]; dims3[1] = nb[1]; dims3[2] = nb[2];
+    const int64_t nblocks = (int64_t)nb[0] * nb[1] * nb[2];
+    int64_t missing = 0;
+    std::vector<float> corner_sum((size_t)nblocks * 8 * B);
+    for (int64_t b = 0; b < nblocks; ++b) {
+        const int bx = (int)(b % nb[0]), by = (int)((b / nb[0]) % nb[1]), bz = (int)(b / ((int64_t)nb[0] * nb[1]));
+        const int bi[3] = {bx, by, bz};
+        int lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) { lo[a] = 1 + bi[a] * block; hi[a] = (bi[a] == nb[a] - 1) ? vd[a] : (bi[a] + 1) * block; }
+        for (int j = 0; j < 8; ++j) {                                              /* d_queryBlockNew, :1142-1315 */
+            const int c[3] = {(j & 1) ? hi[0] : lo[0], (j & 2) ? hi[1] : lo[1], (j & 4) ? hi[2] : lo[2]};
+            int px[32][2], py[32][2], pz[32][2];
+            const int nx = prefix_pieces(c[0], px), ny = prefix_pieces(c[1], py), nz = prefix_pieces(c[2], pz);
+            float* sum = &corner_sum[((size_t)b * 8 + j) * B];
+            for (int k = 0; k < B; ++k) sum[k] = 0.0f;
+            for (int ix = 0; ix < nx; ++ix)
+                for (int iy = 0; iy < ny; ++iy)
+                    for (int iz = 0; iz < nz; ++iz) {                             /* d_querySpanNew, :1318-1544 */
+                        const int weight = (px[ix][1] - px[ix][0] + 1) * (py[iy][1] - py[iy][0] + 1) * (pz[iz][1] - pz[iz][0] + 1);
+                        float cur[VRDD_SYNTH_MAX_BINS];
+                        if (weight >= 8) {
+                            auto it = fr.find(Key{px[ix][0], py[iy][0], pz[iz][0], px[ix][1], py[iy][1], pz[iz][1]});
+                            if (it == fr.end()) { ++missing; continue; }
+                            const int idx = it->second;
+                            const int id = T->codebook[4 * idx], shift = T->codebook[4 * idx + 1], flip = T->codebook[4 * idx + 2],
+                                      ne = T->codebook[4 * idx + 3];
+                            if (id < 0 || id >= T->n_templates || shift < 0 || shift > B || ne < 0 || ne > B) { ++missing; continue; }
+                            fractal_transform(T->templates + (size_t)id * B, B, flip, shift, cur);      /* :225-251 */
+                            for (int e = 0; e < ne; ++e) {
+                                const int bin = (int)T->errors[2 * ((size_t)idx * B + e)];
+                                const float val = T->errors[2 * ((size_t)idx * B + e) + 1];
+                                if (bin < 0 || bin >= B) continue;
+                                cur[bin] = cur[bin] + val;
+                                if (cur[bin] < 0) cur[bin] = 0;
+                            }
+                            float tot = 0;
+                            for (int k = 0; k < B; ++k) tot = tot + cur[k];
+                            for (int k = 0; k < B; ++k) cur[k] = cur[k] / tot;                             /* no guard, :1437-1439 */
+                        } else {
+                            auto it = si.find(Key{px[ix][0] - 1, py[iy][0] - 1, pz[iz][0] - 1, px[ix][1] - 1, py[iy][1] - 1, pz[iz][1] - 1});
+                            if (it == si.end()) { ++missing; continue; }
+                            const int idx = it->second;
+                            for (int k = 0; k < B; ++k) cur[k] = 0;
+                            for (int e = 0; e < T->simple_count[idx] && e < B; ++e) {
+                                const int bin = (int)T->simple_hist[2 * ((size_t)idx * B + e)];
+                                if (bin >= 0 && bin < B) cur[bin] = T->simple_hist[2 * ((size_t)idx * B + e) + 1];
+                            }
+                        }
+                        for (int k = 0; k < B; ++k) sum[k] = sum[k] + cur[k] * (float)weight;            /* :1449, 1517 */
+                    }
+        }
+    }
+    for (int64_t b = 0; b < nblocks; ++b) {                                      /* d_computeBlock, :1033-1126 */
+        const float* c = &corner_sum[(size_t)b * 8 * B];
+        float h[VRDD_SYNTH_MAX_BINS];
+        for (int s = 0; s < B; ++s) {
+            h[s] = c[0 * B + s] + c[3 * B + s] + c[4 * B + s] + c[7 * B + s] - c[1 * B + s] - c[2 * B + s] - c[5 * B + s] - c[6 * B + s];
+            if (h[s] < 0) h[s] = 0;
+        }
+        float total = 0;
+        for (int s = 0; s < B; ++s) total = total + h[s];
+        if (total > 0)
+            for (int s = 0; s < B; ++s) { h[s] = h[s] / total; if (h[s] < 0) h[s] = 0; if (h[s] > 1) h[s] = 1; }
+        float MaxHistogram = 255.0, MinHistogram = 0.0, mean = 0;
+        float binWidth = (MaxHistogram - MinHistogram) / (float)B;
+        for (int i = 0; i < B; ++i)
+            mean = (float)((double)mean + (double)h[i] * ((double)(binWidth * (float)i) + (double)binWidth / 2.0));
+        float variance = 0;
+        for (int i = 0; i < B; ++i) {
+            double d = ((double)(binWidth * (float)i) + (double)binWidth / 2.0) - (double)mean;
+            variance = (float)((double)variance + ((double)h[i] * d) * d);
+        }
+        float entropy = 0;
+        for (int i = 0; i < B; ++i) {
+            double term = (h[i] <= 0) ? 0.0 : ((double)logf(h[i]) / std::log(2.0));
+            entropy = (float)((double)entropy + (double)h[i] * term);
+        }
+        entropy = -entropy;
+        entropy = entropy / (logf((float)B) / logf(2.0f));
+        out4[4 * b] = mean; out4[4 * b + 1] = variance; out4[4 * b + 2] = entropy; out4[4 * b + 3] = 0.0f;
+    }
+    return missing;
+}
+
+/* tex3D(flexBlockTex, x, y, z): float4 volume of nx*ny*nz blocks inside a zero-filled 500^3 array
+ * (bindToTex, :1572-1696), linear, UN-normalised, clamp.  Un-normalised coordinates are not truncated to
+ * 21 bits: q = floor(x*256 + 0.5) - 128 (measured, tools/probe_texture4.py); weights as in weights_hw. */
+static float tex3d_flex(const float* blocks4, int nx, int ny, int nz, int comp, float x, float y, float z) {
+    const int N = 500;
+    int ii[3], aa[3];
+    const float xyz[3] = {x, y, z};
+    for (int a = 0; a < 3; ++a) {
+        float v = xyz[a];
+        if (!(v == v)) v = 0.0f;
+        double q = std::floor((double)v * 256.0 + 0.5) - 128.0;
+        if (q < 0) q = 0;
+        if (q > (double)(N - 1) * 256) q = (double)(N - 1) * 256;
+        long long qi = (long long)q;
+        ii[a] = (int)(qi >> 8); aa[a] = (int)(qi & 255);
+    }
+    int wt[8];
+    weights_hw(aa[0], aa[1], aa[2], wt);
+    float acc = 0.0f;
+    for (int n = 0; n < 8; ++n) {
+        if (wt[n] == 0) continue;
+        int tx = ii[0] + (n & 1), ty = ii[1] + ((n >> 1) & 1), tz = ii[2] + (n >> 2);
+        float t = (tx < nx && ty < ny && tz < nz) ? blocks4[4 * ((size_t)tx + (size_t)nx * ((size_t)ty + (size_t)ny * (size_t)tz)) + comp] : 0.0f;
+        acc = acc + ((float)wt[n] * (1.0f / 256.0f)) * t;
+    }
+    return acc;
+}
+
+/* d_render for queryMethod 8 / 9 / 0: entropy / mean / variance of the flexible blocks (:654-680). */
+int64_t vrdd_oracle_render_flex(const float* blocks4, int nx, int ny, int nz, const float* tf4, int tf_n,
+                                const float* m12, uint32_t* out, const vrdd_oracle_render_params* P) {
+    const f3 boxMin = {-1.0f, -1.0f, -1.0f}, boxMax = {1.0f, 1.0f, 1.0f};
+    const int qm = P->query_method;
+    const int comp = (qm == 8) ? 2 : (qm == 9) ? 0 : 1;
+    const int imageW = P->image_w, imageH = P->image_h;
+    int64_t samples = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : samples)
+    for (int y = P->y0; y < P->y1; ++y) {
+        for (int x = 0; x < imageW; ++x) {
+            float u = ((float)x / (float)imageW) * 2.0f - 1.0f;
+            float v = ((float)y / (float)imageH) * 2.0f - 1.0f;
+            f3 o = {m12[3], m12[7], m12[11]};
+            f3 dv = {u, v, -2.0f};
+            float inv_len = 1.0f / sqrtf(dot3(dv, dv));
+            dv.x = dv.x * inv_len; dv.y = dv.y * inv_len; dv.z = dv.z * inv_len;
+            f3 r0 = {m12[0], m12[1], m12[2]}, r1 = {m12[4], m12[5], m12[6]}, r2 = {m12[8], m12[9], m12[10]};
+            f3 d = {dot3(dv, r0), dot3(dv, r1), dot3(dv, r2)};
+            float tnear, tfar;
+            if (!intersect_box(o, d, boxMin, boxMax, &tnear, &tfar)) continue;
+            if (tnear < 0.0f) tnear = 0.0f;
+            f4 sum = {0, 0, 0, 0};
+            float t = tnear;
+            f3 pos = {o.x + d.x * tnear, o.y + d.y * tnear, o.z + d.z * tnear};
+            f3 step = {d.x * P->tstep, d.y * P->tstep, d.z * P->tstep};
+            for (int i = 0; i < P->max_steps; ++i) {
+                float sample = tex3d_flex(blocks4, nx, ny, nz, comp, (pos.x * 0.5f + 0.5f) * (float)nx,
+                                          (pos.y * 0.5f + 0.5f) * (float)ny, (pos.z * 0.5f + 0.5f) * (float)nz);
+                samples += 1;
+                f4 col = tex1d_linear4(tf4, tf_n, (sample - P->transfer_offset) * P->transfer_scale, WQ_HW);
+                col.w = col.w * P->density;
+                col.x = col.x * col.w; col.y = col.y * col.w; col.z = col.z * col.w;
+                float k = 1.0f - sum.w;
+                sum.x = sum.x + col.x * k; sum.y = sum.y + col.y * k;
+                sum.z = sum.z + col.z * k; sum.w = sum.w + col.w * k;
+                if (sum.w > P->opacity_threshold) break;
+                t = t + P->tstep;
+                if (t > tfar) break;
+                pos.x = pos.x + step.x; pos.y = pos.y + step.y; pos.z = pos.z + step.z;
+            }
+            sum.x = sum.x * P->brightness; sum.y = sum.y * P->brightness;
+            sum.z = sum.z * P->brightness; sum.w = sum.w * P->brightness;
+            out[(size_t)y * imageW + x] = pack_rgba(sum);
+        }
+    }
+    return samples;
+}
 
 /* Direct access to the filter model, for the texture-unit conformance test. */
 float vrdd_oracle_tex3d(const float* vol4, int W, int H, int D, int comp, float u, float v, float w, int wq) {

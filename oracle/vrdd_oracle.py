@@ -24,6 +24,34 @@ class RenderParams(C.Structure):
                 ("y0", C.c_int), ("y1", C.c_int)]
 
 
+class FlexTables(C.Structure):
+    """struct vrdd_oracle_flex_tables / struct vrdd_flex_tables (same layout)."""
+    _fields_ = [("raw_w", C.c_int), ("raw_h", C.c_int), ("raw_d", C.c_int), ("bins", C.c_int),
+                ("n_fractal", C.c_int), ("span_low", C.c_void_p), ("span_high", C.c_void_p), ("codebook", C.c_void_p),
+                ("errors", C.c_void_p),
+                ("n_simple", C.c_int), ("simple_low", C.c_void_p), ("simple_high", C.c_void_p),
+                ("simple_count", C.c_void_p), ("simple_hist", C.c_void_p),
+                ("n_templates", C.c_int), ("templates", C.c_void_p)]
+
+
+def flex_tables_struct(t, cls=FlexTables):
+    """dict of numpy arrays (tests/flex_synth.py) -> ctypes struct; keeps the arrays alive on the struct."""
+    s = cls()
+    s.raw_w, s.raw_h, s.raw_d = t["raw_dims"]
+    s.bins = t["bins"]
+    s.n_fractal = t["span_low"].shape[0]
+    s.n_simple = t["simple_low"].shape[0]
+    s.n_templates = t["templates"].shape[0]
+    keep = []
+    for name in ("span_low", "span_high", "codebook", "errors", "simple_low", "simple_high", "simple_count",
+                 "simple_hist", "templates"):
+        a = np.ascontiguousarray(t[name])
+        keep.append(a)
+        setattr(s, name, a.ctypes.data)
+    s._keep = keep
+    return s
+
+
 def build(force=False):
     """Compile both flavours of the oracle with oracle/Makefile (g++ only, no CUDA)."""
     need = force or not all(os.path.exists(os.path.join(_HERE, n))
@@ -59,6 +87,11 @@ class Oracle:
         L.vrdd_oracle_render_mode7.restype = C.c_int64
         L.vrdd_oracle_point_index.argtypes = [C.c_float, C.c_int]
         L.vrdd_oracle_point_index.restype = C.c_int
+        L.vrdd_oracle_flex_process.argtypes = [C.POINTER(FlexTables), C.c_int, _f32p, C.POINTER(C.c_int * 3)]
+        L.vrdd_oracle_flex_process.restype = C.c_int64
+        L.vrdd_oracle_render_flex.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, _f32p, C.c_int, _f32p, _u32p,
+                                              C.POINTER(RenderParams)]
+        L.vrdd_oracle_render_flex.restype = C.c_int64
         L.vrdd_oracle_tex3d.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                         C.c_float, C.c_int]
         L.vrdd_oracle_tex3d.restype = C.c_float
@@ -157,6 +190,26 @@ class Oracle:
                          opacity_threshold, 3, 0, ih)
         s = self.lib.vrdd_oracle_render_mode7(hist, W, H, D, hist.shape[1], tf, tf.shape[0],
                                               np.ascontiguousarray(view, np.float32), out, C.byref(P))
+        return out, int(s)
+
+    def flex_process(self, tables, block):
+        """dataProcessing(): returns (float4 blocks [n][4], (nx, ny, nz), spans not found)."""
+        st = flex_tables_struct(tables)
+        nb = [(d + block - 1) // block for d in tables["raw_dims"]]
+        out = np.zeros((nb[0] * nb[1] * nb[2], 4), np.float32)
+        dims = (C.c_int * 3)()
+        missing = self.lib.vrdd_oracle_flex_process(C.byref(st), block, out, C.byref(dims))
+        return out, tuple(dims), int(missing)
+
+    def render_flex(self, blocks4, nb, view, image=(512, 512), query_method=8, tf=None, density=0.05, brightness=1.0,
+                    transfer_offset=0.0, transfer_scale=1.0, tstep=0.01, max_steps=500, opacity_threshold=0.95):
+        iw, ih = image
+        tf = self.default_transfer_function() if tf is None else np.ascontiguousarray(tf, np.float32)
+        out = np.zeros((ih, iw), np.uint32)
+        P = RenderParams(iw, ih, density, brightness, transfer_offset, transfer_scale, query_method, tstep, max_steps,
+                         opacity_threshold, 3, 0, ih)
+        s = self.lib.vrdd_oracle_render_flex(np.ascontiguousarray(blocks4, np.float32), nb[0], nb[1], nb[2], tf,
+                                             tf.shape[0], np.ascontiguousarray(view, np.float32), out, C.byref(P))
         return out, int(s)
 
     def point_index(self, u, n):

@@ -217,7 +217,11 @@ def test_unsupported_modes_are_errors(renderer, golden):
     with pytest.raises(V.VrddError) as e:                              # mode 7 needs the un-normalised means
         r.render(out, 8, 8, V.default_render_params(query_method=7))
     assert e.value.code == V.ERR_INVALID
-    for qm in (0, 8, 9, 12):
+    for qm in (0, 8, 9):                                               # flexible blocks need vrdd_flex_process
+        with pytest.raises(V.VrddError) as e:
+            r.render(out, 8, 8, V.default_render_params(query_method=qm))
+        assert e.value.code == V.ERR_INVALID
+    for qm in (-1, 10, 12):
         with pytest.raises(V.VrddError) as e:
             r.render(out, 8, 8, V.default_render_params(query_method=qm))
         assert e.value.code == V.ERR_UNSUPPORTED

@@ -33,15 +33,18 @@ EXPORTS = [
     "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_count_samples",
     "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
     "vrdd_set_variant", "vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function",
-    "vrdd_debug_sample_texture_point", "vrdd_enable_interpolated_mean",
-    "vrdd_flex_divide_blocks", "vrdd_flex_prefix_spans",
+    "vrdd_debug_sample_texture_point", "vrdd_debug_sample_texture_unnorm", "vrdd_enable_interpolated_mean",
+    "vrdd_flex_divide_blocks", "vrdd_flex_prefix_spans", "vrdd_flex_set_tables_host", "vrdd_flex_process",
+    "vrdd_flex_get_blocks_host",
     "vrdd_frame_alloc", "vrdd_frame_free", "vrdd_frame_export", "vrdd_frame_open", "vrdd_frame_close",
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
 IO_EXPORTS = ["vrdd_io_read_histograms", "vrdd_io_codebook_blocks", "vrdd_io_read_codebook", "vrdd_io_template_count",
               "vrdd_io_read_templates", "vrdd_io_write_histograms", "vrdd_io_write_codebook", "vrdd_io_write_templates",
-              "vrdd_io_write_ppm", "vrdd_io_read_ppm"]
+              "vrdd_io_write_ppm", "vrdd_io_read_ppm", "vrdd_io_span_count", "vrdd_io_read_span_list",
+              "vrdd_io_read_flex_codebook", "vrdd_io_simple_count", "vrdd_io_read_simple", "vrdd_io_write_span_list",
+              "vrdd_io_write_flex_codebook", "vrdd_io_write_simple"]
 HEADLESS_PATH = os.path.join(_HERE, "vrdd_headless")
 LEGACY_EXPORTS = ["initCuda", "basicDataProcessing", "dataProcessing", "copyInvViewMatrix", "render_kernel",
                   "setTextureFilterMode", "freeCudaBuffers", "vrdd_legacy_handle"]
@@ -69,6 +72,16 @@ class Brick(C.Structure):
     """struct vrdd_brick (include/vrdd.h)."""
     _fields_ = [("gw", C.c_int), ("gh", C.c_int), ("gd", C.c_int), ("ox", C.c_int), ("oy", C.c_int), ("oz", C.c_int),
                 ("lo", C.c_float * 3), ("hi", C.c_float * 3)]
+
+
+class FlexTables(C.Structure):
+    """struct vrdd_flex_tables (include/vrdd.h)."""
+    _fields_ = [("raw_w", C.c_int), ("raw_h", C.c_int), ("raw_d", C.c_int), ("bins", C.c_int),
+                ("n_fractal", C.c_int), ("span_low", C.c_void_p), ("span_high", C.c_void_p), ("codebook", C.c_void_p),
+                ("errors", C.c_void_p),
+                ("n_simple", C.c_int), ("simple_low", C.c_void_p), ("simple_high", C.c_void_p),
+                ("simple_count", C.c_void_p), ("simple_hist", C.c_void_p),
+                ("n_templates", C.c_int), ("templates", C.c_void_p)]
 
 
 class Extent(C.Structure):
@@ -133,11 +146,15 @@ def lib():
             "vrdd_debug_sample_texture": (i32, [vp, i32, i32, vp, i32, vp]),
             "vrdd_debug_sample_transfer_function": (i32, [vp, vp, i32, vp]),
             "vrdd_debug_sample_texture_point": (i32, [vp, i32, i32, vp, i32, vp]),
+            "vrdd_debug_sample_texture_unnorm": (i32, [vp, i32, i32, vp, i32, vp]),
             "vrdd_render_brick_alpha": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_compose_alpha_in": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, i32]),
             "vrdd_render_brick_color": (i32, [vp, vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_pack_frame": (i32, [vp, vp, vp, i32, i32, f32]),
             "vrdd_synth_histograms_region_device": (i32, [vp, u32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+            "vrdd_flex_set_tables_host": (i32, [vp, C.POINTER(FlexTables)]),
+            "vrdd_flex_process": (i32, [vp, i32, C.POINTER(C.c_int64)]),
+            "vrdd_flex_get_blocks_host": (i32, [vp, vp, C.POINTER(C.c_int * 3)]),
             "vrdd_flex_divide_blocks": (i32, [i32, i32, i32, i32, vp, i32]),
             "vrdd_flex_prefix_spans": (i32, [i32, vp]),
             "vrdd_frame_alloc": (i32, [vp, C.c_size_t, C.POINTER(vp)]),
@@ -155,6 +172,14 @@ def lib():
             "vrdd_io_write_codebook": (i32, [C.c_char_p, i32, C.c_int64, vp, vp]),
             "vrdd_io_write_templates": (i32, [C.c_char_p, i32, i32, vp]),
             "vrdd_io_write_ppm": (i32, [C.c_char_p, vp, i32, i32]),
+            "vrdd_io_span_count": (i32, [C.c_char_p]),
+            "vrdd_io_read_span_list": (i32, [C.c_char_p, i32, vp, vp]),
+            "vrdd_io_read_flex_codebook": (i32, [C.c_char_p, i32, C.c_int64, vp, vp, vp]),
+            "vrdd_io_simple_count": (i32, [C.c_char_p]),
+            "vrdd_io_read_simple": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, vp, vp, vp, vp]),
+            "vrdd_io_write_span_list": (i32, [C.c_char_p, i32, vp, vp]),
+            "vrdd_io_write_flex_codebook": (i32, [C.c_char_p, i32, C.c_int64, vp, vp, vp]),
+            "vrdd_io_write_simple": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, vp, vp, vp, vp]),
             "vrdd_io_read_ppm": (i32, [C.c_char_p, vp, i32, i32]),
             # legacy surface (include/vrdd_legacy.h)
             "initCuda": (None, [vp, Extent, Extent, vp, Extent, vp, Extent, vp, Extent] + [vp] * 9),
@@ -336,6 +361,35 @@ class Renderer:
                                                  C.byref(tot)))
         return int(tot.value)
 
+    # flexible-block chain
+    def flex_set_tables_host(self, t):
+        """t: dict with raw_dims, bins and the nine tables as C-contiguous numpy arrays."""
+        import numpy as np
+        s = FlexTables()
+        s.raw_w, s.raw_h, s.raw_d = t["raw_dims"]
+        s.bins = t["bins"]
+        s.n_fractal, s.n_simple, s.n_templates = t["span_low"].shape[0], t["simple_low"].shape[0], t["templates"].shape[0]
+        keep = []
+        for name in ("span_low", "span_high", "codebook", "errors", "simple_low", "simple_high", "simple_count",
+                     "simple_hist", "templates"):
+            a = np.ascontiguousarray(t[name])
+            keep.append(a)
+            setattr(s, name, a.ctypes.data)
+        self._ck(lib().vrdd_flex_set_tables_host(self._h, C.byref(s)))
+
+    def flex_process(self, block_size, want_missing=True):
+        m = C.c_int64(0)
+        self._ck(lib().vrdd_flex_process(self._h, block_size, C.byref(m) if want_missing else None))
+        return int(m.value)
+
+    def flex_get_blocks_host(self):
+        import numpy as np
+        dims = (C.c_int * 3)()
+        self._ck(lib().vrdd_flex_get_blocks_host(self._h, None, C.byref(dims)))
+        out = np.empty((dims[0] * dims[1] * dims[2], 4), np.float32)
+        self._ck(lib().vrdd_flex_get_blocks_host(self._h, out.ctypes.data, C.byref(dims)))
+        return out, tuple(dims)
+
     # peer-visible frames
     def frame_alloc(self, nbytes):
         p = C.c_void_p()
@@ -388,6 +442,9 @@ class Renderer:
 
     def debug_sample_texture_point(self, source, comp, d_uvw, n, d_out):
         self._ck(lib().vrdd_debug_sample_texture_point(self._h, source, comp, _ptr(d_uvw), n, _ptr(d_out)))
+
+    def debug_sample_texture_unnorm(self, source, comp, d_uvw, n, d_out):
+        self._ck(lib().vrdd_debug_sample_texture_unnorm(self._h, source, comp, _ptr(d_uvw), n, _ptr(d_out)))
 
     def debug_sample_transfer_function(self, d_u, n, d_out4):
         self._ck(lib().vrdd_debug_sample_transfer_function(self._h, _ptr(d_u), n, _ptr(d_out4)))

@@ -203,6 +203,7 @@ int vrdd_destroy(vrdd_handle h) {
     free_tf(c);
     if (c->d_samples) cudaFree(c->d_samples);
     if (c->frame) cudaFree(c->frame);
+    destroy_flex(c);
     delete c;
     return VRDD_OK;
 }
@@ -730,6 +731,28 @@ int vrdd_debug_sample_texture_point(vrdd_handle h, int source, int comp, const f
     td.filterMode = cudaFilterModePoint;
     td.readMode = cudaReadModeElementType;
     td.normalizedCoords = 1;
+    cudaTextureObject_t tex = 0;
+    VRDD_CUDA(c, cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    int rc = launch_debug_sample(c, tex, d_uvw, n, d_out);
+    cudaStreamSynchronize(c->stream);
+    cudaDestroyTextureObject(tex);
+    return rc;
+}
+
+int vrdd_debug_sample_texture_unnorm(vrdd_handle h, int source, int comp, const float* d_uvw, int n, float* d_out) {
+    CHECK_HANDLE(h);
+    if (source < 0 || source > 1 || comp < 0 || comp > 2 || !c->vol[source].arr[comp])
+        return fail(c, VRDD_ERR_INVALID, "debug_sample_texture_unnorm: no texture volume");
+    cudaResourceDesc rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->vol[source].arr[comp];
+    cudaTextureDesc td;
+    std::memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
     cudaTextureObject_t tex = 0;
     VRDD_CUDA(c, cudaCreateTextureObject(&tex, &rd, &td, nullptr));
     int rc = launch_debug_sample(c, tex, d_uvw, n, d_out);

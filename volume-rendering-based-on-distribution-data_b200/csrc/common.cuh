@@ -169,6 +169,8 @@ __device__ __forceinline__ float plog2p(float p) { return p * fast_log2(fmaxf(p,
 
 }  // namespace vrdd
 
+struct vrdd_flex_state;                  // flexible-block chain (flex.cu)
+
 // ---- the context behind vrdd_handle --------------------------------------------------------
 struct vrdd_decoded_volume {
     float* lin[3] = {nullptr, nullptr, nullptr};
@@ -226,6 +228,8 @@ struct vrdd_context {
     unsigned long long* d_samples = nullptr;
     bool count_samples = false;
 
+    vrdd_flex_state* flex = nullptr; // span store + block volume of the flexible-block chain
+
     uint32_t* frame = nullptr;       // device frame of vrdd_render_host, kept between calls
     size_t frame_bytes = 0;
 
@@ -267,6 +271,8 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
 int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
                             float* d_alpha_in, int iw, int ih);
 int launch_pack_frame(vrdd_context* c, const float* d_sum4, uint32_t* d_out, int iw, int ih, float brightness);
+void destroy_flex(vrdd_context* c);
+int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p, int clear_misses);
 int launch_debug_sample(vrdd_context* c, cudaTextureObject_t tex, const float* d_uvw, int n, float* d_out);
 int launch_debug_sample_tf(vrdd_context* c, const float* d_u, int n, float* d_out4);
 

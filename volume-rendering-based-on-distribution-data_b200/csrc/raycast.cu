@@ -384,6 +384,10 @@ void launch_variant(bool count, int grid, cudaStream_t st, const RayArgs& A, int
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses) {
     const int qm = p.query_method;
+    if (qm == 8 || qm == 9 || qm == 0) {                           // flexible blocks (:654-680)
+        if (part.parts != 1) return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod 8/9/0 does not take a tile partition");
+        return launch_raycast_flex(c, d_out, iw, ih, p, clear_misses);
+    }
     if (qm == 7) {
         vrdd_decoded_volume& v0 = c->vol[VRDD_SRC_ORIGINAL];
         if (!v0.decoded || !v0.mean_raw)
@@ -406,8 +410,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         return VRDD_OK;
     }
     if (qm < 1 || qm > 6)
-        return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod must be 1..7 (the flexible-block modes 8/9/0 "
-                                             "are not built; SURVEY.md §8f)");
+        return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod must be 0..9 (volumeRender.cpp:129)");
     const int source = (qm >= 4) ? VRDD_SRC_FRACTAL : VRDD_SRC_ORIGINAL;
     const int comp = (qm - 1) % 3;
     vrdd_decoded_volume& vol = c->vol[source];
