@@ -39,6 +39,7 @@ struct vrdd_flex_state {
     int nb[3] = {0, 0, 0};
     float4* blocks = nullptr;
     float* corner_sum = nullptr;
+    long long capacity = 0;          // blocks the two buffers above were allocated for
     unsigned long long* d_missing = nullptr;
 };
 
@@ -451,11 +452,15 @@ int vrdd_flex_process(vrdd_handle h, int block_size, int64_t* spans_not_found) {
         if (A.nb[0] > VRDD_FLEX_PAD || A.nb[1] > VRDD_FLEX_PAD || A.nb[2] > VRDD_FLEX_PAD) {
             rc = fail(c, VRDD_ERR_INVALID, "flex_process: more than 500 blocks per axis (nMaxBlockDim)"); break;
         }
-        if (f->blocks) cudaFree(f->blocks);
-        if (f->corner_sum) cudaFree(f->corner_sum);
-        f->blocks = nullptr; f->corner_sum = nullptr;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&f->blocks), sizeof(float4) * nblocks);
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&f->corner_sum), sizeof(float) * nblocks * 8 * VRDD_FLEX_BINS);
+        cudaError_t e = cudaSuccess;
+        if (f->capacity < nblocks) {                                   // the result buffers are kept between calls
+            if (f->blocks) cudaFree(f->blocks);
+            if (f->corner_sum) cudaFree(f->corner_sum);
+            f->blocks = nullptr; f->corner_sum = nullptr; f->capacity = 0;
+            e = cudaMalloc(reinterpret_cast<void**>(&f->blocks), sizeof(float4) * nblocks);
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&f->corner_sum), sizeof(float) * nblocks * 8 * VRDD_FLEX_BINS);
+            if (e == cudaSuccess) f->capacity = nblocks;
+        }
         if (e == cudaSuccess) e = cudaMemsetAsync(f->d_missing, 0, sizeof(unsigned long long), c->stream);
         if (e != cudaSuccess) { rc = fail_cuda(c, e, "flex_process: allocate"); break; }
         A.fkeys = f->fkeys; A.fvals = f->fvals; A.fmask = f->fmask; A.skeys = f->skeys; A.svals = f->svals; A.smask = f->smask;
