@@ -534,10 +534,14 @@ def run_ours(args):
         my_samples = samples / world / args.steps
         # the dominant kernel of the timed step is the ray caster; at 1024^3 with the reference's fixed step ncu
         # shows it DRAM-bound (profiles/README.md), so its roofline is HBM with 32 algorithmic bytes per sample
-        ray_traffic = None
+        ray_traffic, traffic_what = None, "no ncu capture for this configuration"
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                ray_traffic = json.load(f)["raycast_kernel"]["dram_bytes_per_launch"] if args.volume == 1024 else None
+                tj = json.load(f)["raycast_kernel"]
+            if args.volume == 1024 and world == 1 and args.image == 1024:
+                ray_traffic = tj["dram_bytes_per_launch"]
+                traffic_what = ("mean DRAM bytes of the %d orbit launches under ncu (cold L2 before each)" % tj["launches"]
+                                if "launches" in tj else "DRAM bytes of one ncu-captured launch (an orbit side view)")
         except Exception:
             pass
         roofline = {"kernel": "raycast_kernel", "bound": "hbm",
@@ -545,8 +549,8 @@ def run_ours(args):
                     "peak_source": peak_src, "launch_ms": kernel_ms, "bytes_per_launch": my_samples * SAMPLE_BYTES,
                     "gsamples_per_s_kernel_only": my_samples / (kernel_ms * 1e-3) / 1e9, "traffic": ray_traffic,
                     "note": "algorithmic bytes = 32 B per trilinear sample (8 fp32 texels) x samples of the average launch; "
-                            "traffic = DRAM bytes of one ncu-captured launch (an orbit side view, profiles/): sector "
-                            "over-fetch, not re-reads, separates the two"}
+                            "traffic = " + traffic_what + ", profiles/traffic.json; sector over-fetch, not re-reads, "
+                            "separates the two"}
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
         line = {"metric": "raycast_throughput", "value": gsamples, "unit": "Gsamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

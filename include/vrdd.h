@@ -127,12 +127,26 @@ int vrdd_set_histograms_device(vrdd_handle h, const float* d_hist, int z0, int n
  * validated against the reference's guards; VRDD_ERR_RANGE reports a violation. */
 int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* errors_dense,
                           const float* templates, int num_templates);
+/* Compact form of the errors: one 8-byte entry per error, grouped per chunk of 32 consecutive
+ * voxels (one warp) and stored ROUND-MAJOR inside a chunk: round k holds the k-th error of every
+ * voxel of the chunk with NE > k, in voxel order; round k+1 follows round k.  In round k the
+ * lanes that still have an error read consecutive entries, so the decode kernels take the table
+ * with one coalesced load per round and no staging. */
+typedef struct vrdd_error_entry {
+    int32_t bin;        /* (int)binId of the reference's float2, 0 <= bin < bins */
+    float value;
+} vrdd_error_entry;
+/* Host-side packer from the reference's dense table to the compact form (what vrdd_set_fractal_host
+ * does internally).  chunk_offsets has ceil(nvox/32)+1 entries; entries may be NULL to only count
+ * (*total_ne = sum of NE).  VRDD_ERR_RANGE for NE/shift/bin outside the reference's guards. */
+int vrdd_pack_fractal_errors(const int32_t* codebook, const float* errors_dense, int64_t nvox, int bins,
+                             vrdd_error_entry* entries, uint64_t* chunk_offsets, uint64_t* total_ne);
 /* Compact device-resident form for slab streaming:
- *   d_codebook: int32[nvox][4];  d_errors: float[total_ne][2] in voxel order;
+ *   d_codebook: int32[nvox][4];  d_errors: vrdd_error_entry[total_ne], round-major per chunk;
  *   d_chunk_offsets: uint64[ceil(nvox/32)+1], entry c = index into d_errors of the first
- *   error of voxel 32*c (exclusive prefix sum of NE taken every 32 voxels, one per warp);
+ *   entry of chunk c (exclusive prefix sum of NE taken every 32 voxels);
  *   d_templates: float[num_templates][bins].  Covers z-slices [z0, z0+nz). */
-int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const float* d_errors,
+int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const vrdd_error_entry* d_errors,
                             const uint64_t* d_chunk_offsets, const float* d_templates,
                             int num_templates, int z0, int nz);
 
@@ -254,10 +268,10 @@ int vrdd_synth_histograms_device(vrdd_handle h, uint32_t seed, int z0, int nz, f
  * gw x gh x gd volume; fills local z-slices [z0, z0+nz) with the histograms of the GLOBAL voxels. */
 int vrdd_synth_histograms_region_device(vrdd_handle h, uint32_t seed, int gw, int gh, int gd, int ox, int oy,
                                         int oz, int z0, int nz, float* d_hist);
-/* Fractal counterpart.  d_errors must hold max_ne*nvox entries; *total_ne (host) receives
+/* Fractal counterpart, in the compact form of vrdd_set_fractal_device.  d_errors must hold max_ne*nvox entries; *total_ne (host) receives
  * the number actually written.  Synchronises. */
 int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, int max_ne, int z0,
-                              int nz, int32_t* d_codebook, float* d_errors,
+                              int nz, int32_t* d_codebook, vrdd_error_entry* d_errors,
                               uint64_t* d_chunk_offsets, float* d_templates, uint64_t* total_ne);
 
 /* ---- flexible-block-size query chain (csrc/flex.cu) -----------------------------------

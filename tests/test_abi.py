@@ -77,3 +77,28 @@ def test_default_render_params_are_the_reference_constants():
         pytest.approx(0.05), 1.0, 0.0, 1.0)                          # volumeRender.cpp:130-133
     assert (p.max_steps, p.query_method) == (500, 1)                 # volumeRender_kernel.cu:276
     assert p.tstep == pytest.approx(0.01) and p.opacity_threshold == pytest.approx(0.95)
+
+
+def test_pack_fractal_errors_matches_the_documented_layout(oracle):
+    """vrdd_pack_fractal_errors (host code, no GPU): round-major entries and per-chunk offsets, against an
+    independent numpy restatement; ragged tail chunk, voxels with NE = 0 and NE = bins included."""
+    import vrdd_b200 as V
+    from packing import round_major, chunk_offsets
+    dims = (13, 7, 5)                                           # 455 voxels: 14 full chunks + 7
+    cb, err = oracle.synth_fractal(77, dims, T=50, max_ne=8)
+    cb = cb.copy(); err = err.copy()
+    cb[3, 3] = 0
+    cb[40, 3] = 32
+    err[40, :, 0] = np.arange(32)[::-1]
+    err[40, :, 1] = np.linspace(-0.01, 0.01, 32)
+    ent, off = V.pack_fractal_errors(cb, err)
+    want = round_major(cb, err)
+    assert ent.shape == want.shape and np.array_equal(ent["bin"], want["bin"]) and np.array_equal(ent["value"], want["value"])
+    assert np.array_equal(off, chunk_offsets(cb))
+    bad = cb.copy(); bad[5, 3] = 33
+    with pytest.raises(V.VrddError):
+        V.pack_fractal_errors(bad, err)
+    bad_e = err.copy(); bad_e[0, 0, 0] = 32.0
+    if cb[0, 3] > 0:
+        with pytest.raises(V.VrddError):
+            V.pack_fractal_errors(cb, bad_e)

@@ -113,7 +113,7 @@ def _from_device_ptr(ptr, n):
     return V.as_torch(ptr, (n,)).cpu().numpy()
 
 
-@pytest.mark.parametrize("variant", ["moments", "dense"])
+@pytest.mark.parametrize("variant", ["moments", "moments_global", "dense"])
 def test_fractal_decode_matches_golden_and_is_bit_exact_in_its_integer_part(renderer, golden, variant):
     """The golden codes include shift == 32, flip + shift, NE == 0, a clamp to zero and a bin hit
     three times (the moments variant must fall back to the ordered dense route there)."""
@@ -134,12 +134,13 @@ def test_fractal_decode_matches_golden_and_is_bit_exact_in_its_integer_part(rend
     np.testing.assert_allclose(got, golden["decoded_fractal"], rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("variant", ["moments", "dense"])
+@pytest.mark.parametrize("variant", ["moments", "moments768", "moments_global", "dense"])
 @pytest.mark.parametrize("dims,T,max_ne", [((1, 1, 1), 3, 8), ((30, 9, 2), 622, 8), ((50, 50, 10), 622, 8),
-                                            ((64, 32, 5), 100, 32), ((16, 16, 4), 1500, 0)])
+                                            ((64, 32, 5), 100, 32), ((16, 16, 4), 1500, 0), ((96, 64, 40), 622, 8)])
 def test_fractal_decode_matches_oracle(renderer, oracle, dims, T, max_ne, variant):
-    """Ragged sizes, the reference's 50x50x10 / 622 templates, NE up to 32 (error staging
-    overflow path), NE == 0, and a template table too large for shared memory."""
+    """Ragged sizes, the reference's 50x50x10 / 622 templates, NE up to 32, NE == 0, a template table too
+    large for shared memory, and a volume of more than one sweep of the persistent grid with rows that are
+    a multiple of 32 voxels (the incremental-coordinate path of the shared-table kernel)."""
     import torch
     import vrdd_b200 as V
     tmpl = oracle.synth_templates(4, T)
@@ -162,6 +163,33 @@ def test_fractal_decode_matches_oracle(renderer, oracle, dims, T, max_ne, varian
     r.synchronize()
     assert np.array_equal(recon.cpu().numpy(), ref_recon)
     r.decode(V.SRC_FRACTAL)
+    got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_fractal_slabs_from_packed_device_arrays(renderer, oracle):
+    """vrdd_pack_fractal_errors + vrdd_set_fractal_device, one z-slab at a time (slab boundaries fall on chunk
+    boundaries because W*H is a multiple of 32), equals the whole-volume answer."""
+    import torch
+    import vrdd_b200 as V
+    dims, T = (64, 48, 12), 622
+    tmpl = oracle.synth_templates(9, T)
+    cb, err = oracle.synth_fractal(9, dims, T=T, max_ne=8)
+    ref, _ = oracle.decode_fractal(cb, err, tmpl)
+    sl = dims[0] * dims[1]
+    r = renderer
+    r.set_volume(*dims)
+    d_tm = torch.from_numpy(tmpl).cuda()
+    keep = []
+    for z0, nz in ((0, 5), (5, 4), (9, 3)):
+        ent, off = V.pack_fractal_errors(cb[z0 * sl:(z0 + nz) * sl], err[z0 * sl:(z0 + nz) * sl])
+        d_cb = torch.from_numpy(np.ascontiguousarray(cb[z0 * sl:(z0 + nz) * sl])).cuda()
+        d_er = torch.from_numpy(ent.view(np.uint8).reshape(-1).copy()).cuda()
+        d_off = torch.from_numpy(off.view(np.int64)).cuda()
+        keep += [d_cb, d_er, d_off]
+        r.set_fractal_device(d_cb, d_er, d_off, d_tm, T, z0, nz)
+        r.decode(V.SRC_FRACTAL, z0, nz)
+    n = sl * dims[2]
     got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
     np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
 
@@ -226,8 +254,10 @@ def test_device_synth_is_bit_identical_to_host_synth(renderer, oracle):
     assert np.array_equal(cb.cpu().numpy(), hcb)
     assert np.array_equal(tm.cpu().numpy(), oracle.synth_templates(seed, T))
     assert tot == int(hcb[:, 3].sum())
-    compact = np.concatenate([herr[v, :hcb[v, 3]] for v in range(n)])
-    assert np.array_equal(er.cpu().numpy()[:tot], compact)
+    from packing import round_major
+    want = round_major(hcb, herr)
+    got_e = er.cpu().numpy()[:tot]
+    assert np.array_equal(got_e[:, 0].view(np.int32), want["bin"]) and np.array_equal(got_e[:, 1], want["value"])
     offs = off.cpu().numpy()
     cum = np.concatenate([[0], np.cumsum(hcb[:, 3])])
     assert np.array_equal(offs[:-1], cum[0:n:V.ERR_CHUNK]) and offs[-1] == tot

@@ -85,6 +85,31 @@ for name in ("decode_hist", "raycast", "decode_fractal_moments"):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     open(os.path.join(P, f"ncu_raw_{name}_{tag}.csv"), "w").write(out)
 
+# ---- DRAM bytes of each of the 64 timed orbit launches of the ray caster ----------------------
+orbit = None
+oc = os.path.join(G, f"raycast_orbit_{tag}.csv")
+if os.path.exists(oc):
+    per = collections.defaultdict(dict)
+    for r in csv.DictReader(l for l in open(oc) if l.startswith('"')):
+        v = float(r["Metric Value"].replace(",", ""))
+        v *= {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12, "us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6,
+              "usecond": 1, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}.get(r["Metric Unit"], 1)
+        per[r["ID"]][r["Metric Name"]] = v
+    rd = [d["dram__bytes_read.sum"] for d in per.values()]
+    wr = [d["dram__bytes_write.sum"] for d in per.values()]
+    us = [d["gpu__time_duration.sum"] for d in per.values()]
+    n = len(rd)
+    orbit = {"launches": n, "dram_bytes_per_launch": (sum(rd) + sum(wr)) / n, "dram_read": sum(rd) / n, "dram_write": sum(wr) / n,
+             "dram_bytes_min": min(a + b for a, b in zip(rd, wr)), "dram_bytes_max": max(a + b for a, b in zip(rd, wr)),
+             "duration_us_under_ncu": sum(us) / n}
+    lines += ["## Ray caster, DRAM bytes of each timed launch of the 64-view orbit", "",
+              "`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:raycast_kernel -s 69 -c 64` on "
+              "`python bench.py --steps 64 --warmup 5 ...` (cold L2 before every launch)", "",
+              f"{n} launches: mean {orbit['dram_bytes_per_launch'] / 1e6:.1f} MB per launch (read {orbit['dram_read'] / 1e6:.1f}, "
+              f"write {orbit['dram_write'] / 1e6:.1f}), min {orbit['dram_bytes_min'] / 1e6:.1f}, max {orbit['dram_bytes_max'] / 1e6:.1f}; "
+              f"mean duration under ncu {orbit['duration_us_under_ncu']:.1f} us", ""]
+    subprocess.run(["cp", oc, os.path.join(P, f"raycast_orbit_{tag}.csv")])
+
 open(os.path.join(P, f"summary_{tag}.md"), "w").write("\n".join(lines) + "\n")
 
 # traffic.json: keyed by the kernel names bench.py reports, with the launch's algorithmic bytes
@@ -99,6 +124,9 @@ if os.path.exists(bench) and "decode_hist" in traffic:
                                    "dram_write": t["dram_write"], "source": f"profiles/ncu_raw_decode_hist_{tag}.csv"}
     if "raycast" in traffic:
         tj["raycast_kernel"] = dict(traffic["raycast"], source=f"profiles/ncu_raw_raycast_{tag}.csv")
+        if orbit:                      # the per-launch figure bench.py quotes is the orbit mean, like its launch time
+            tj["raycast_kernel"] = dict(orbit, source=f"profiles/raycast_orbit_{tag}.csv",
+                                        full_capture_side_view=dict(traffic["raycast"], source=f"profiles/ncu_raw_raycast_{tag}.csv"))
     if "decode_fractal_moments" in traffic:
         tj["decode_fractal_moments_kernel"] = dict(traffic["decode_fractal_moments"],
                                                    source=f"profiles/ncu_raw_decode_fractal_moments_{tag}.csv")

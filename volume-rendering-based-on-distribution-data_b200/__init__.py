@@ -27,7 +27,7 @@ ERR_CHUNK = 32
 EXPORTS = [
     "vrdd_create", "vrdd_destroy", "vrdd_set_stream", "vrdd_synchronize", "vrdd_last_error",
     "vrdd_kernel_launches", "vrdd_set_volume", "vrdd_set_histograms_host", "vrdd_set_histograms_device",
-    "vrdd_set_fractal_host", "vrdd_set_fractal_device", "vrdd_set_sampler", "vrdd_decode",
+    "vrdd_set_fractal_host", "vrdd_set_fractal_device", "vrdd_pack_fractal_errors", "vrdd_set_sampler", "vrdd_decode",
     "vrdd_get_decoded_host", "vrdd_get_decoded_planes_device", "vrdd_keep_linear_planes", "vrdd_commit_planes",
     "vrdd_reconstruct_fractal_device", "vrdd_set_transfer_function", "vrdd_set_view",
     "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_count_samples",
@@ -124,6 +124,7 @@ def lib():
             "vrdd_set_histograms_device": (i32, [vp, vp, i32, i32]),
             "vrdd_set_fractal_host": (i32, [vp, vp, vp, vp, i32]),
             "vrdd_set_fractal_device": (i32, [vp, vp, vp, vp, vp, i32, i32, i32]),
+            "vrdd_pack_fractal_errors": (i32, [vp, vp, C.c_int64, i32, vp, vp, C.POINTER(C.c_uint64)]),
             "vrdd_set_sampler": (i32, [vp, i32]),
             "vrdd_decode": (i32, [vp, i32, i32, i32]),
             "vrdd_get_decoded_host": (i32, [vp, i32, vp]),
@@ -238,6 +239,28 @@ class DeviceArray:
 def as_torch(ptr, shape, typestr="<f4", device="cuda"):
     import torch
     return torch.as_tensor(DeviceArray(ptr, shape, typestr), device=device)
+
+
+ERROR_ENTRY_DTYPE = [("bin", "<i4"), ("value", "<f4")]      # vrdd_error_entry
+
+
+def pack_fractal_errors(codebook, errors_dense, bins=32):
+    """vrdd_pack_fractal_errors: the reference's dense float2[V][bins] error table -> the compact form of
+    vrdd_set_fractal_device.  Returns (entries as a structured numpy array, chunk_offsets uint64)."""
+    import numpy as np
+    cb = np.ascontiguousarray(codebook, dtype=np.int32).reshape(-1, 4)
+    ed = np.ascontiguousarray(errors_dense, dtype=np.float32).reshape(cb.shape[0], bins, 2)
+    n = cb.shape[0]
+    off = np.zeros((n + ERR_CHUNK - 1) // ERR_CHUNK + 1, dtype=np.uint64)
+    tot = C.c_uint64()
+    rc = lib().vrdd_pack_fractal_errors(cb.ctypes.data, ed.ctypes.data, n, bins, None, off.ctypes.data, C.byref(tot))
+    if rc != 0:
+        raise VrddError(rc, "vrdd_pack_fractal_errors: codebook entry or error bin out of range")
+    ent = np.zeros(max(int(tot.value), 1), dtype=ERROR_ENTRY_DTYPE)
+    rc = lib().vrdd_pack_fractal_errors(cb.ctypes.data, ed.ctypes.data, n, bins, ent.ctypes.data, off.ctypes.data, C.byref(tot))
+    if rc != 0:
+        raise VrddError(rc, "vrdd_pack_fractal_errors failed")
+    return ent[:int(tot.value)], off
 
 
 class Renderer:

@@ -260,6 +260,55 @@ int vrdd_set_histograms_device(vrdd_handle h, const float* d_hist, int z0, int n
     return VRDD_OK;
 }
 
+// The compact error form (include/vrdd.h): per chunk of 32 consecutive voxels, round k holds the k-th error
+// of every voxel of the chunk with NE > k, in voxel order; rounds follow one another.  Returns 0, or 1 / 2
+// when a codebook entry / an error bin is out of range (the reference's guards, volumeRender_kernel.cu:781-816).
+static int pack_errors(const int32_t* codebook, const float* errors_dense, size_t V, int B, int num_templates,
+                       std::vector<vrdd_error_entry>* entries, std::vector<uint64_t>* offsets) {
+    const size_t nchunks = (V + VRDD_ERR_CHUNK - 1) / VRDD_ERR_CHUNK;
+    offsets->assign(nchunks + 1, 0);
+    uint64_t total = 0;
+    for (size_t v = 0; v < V; ++v) {
+        if (v % VRDD_ERR_CHUNK == 0) (*offsets)[v / VRDD_ERR_CHUNK] = total;
+        const int32_t* e = codebook + 4 * v;
+        if ((num_templates > 0 && (e[0] < 0 || e[0] >= num_templates)) || e[1] < 0 || e[1] > B || e[3] < 0 || e[3] > B)
+            return 1;
+        total += (uint64_t)e[3];
+    }
+    (*offsets)[nchunks] = total;
+    entries->resize(total);
+    uint64_t w = 0;
+    for (size_t c0 = 0; c0 < V; c0 += VRDD_ERR_CHUNK) {
+        const size_t c1 = (c0 + VRDD_ERR_CHUNK < V) ? c0 + VRDD_ERR_CHUNK : V;
+        for (int k = 0; k < B; ++k) {
+            bool any = false;
+            for (size_t v = c0; v < c1; ++v) {
+                if (codebook[4 * v + 3] <= k) continue;
+                any = true;
+                const float* row = errors_dense + 2 * (v * B + k);
+                const int bin = (int)row[0];
+                if (bin < 0 || bin >= B) return 2;
+                (*entries)[w].bin = bin; (*entries)[w].value = row[1];
+                ++w;
+            }
+            if (!any) break;
+        }
+    }
+    return 0;
+}
+
+int vrdd_pack_fractal_errors(const int32_t* codebook, const float* errors_dense, int64_t nvox, int bins,
+                             vrdd_error_entry* entries, uint64_t* chunk_offsets, uint64_t* total_ne) {
+    if (!codebook || !errors_dense || nvox <= 0 || bins <= 0 || !chunk_offsets) return VRDD_ERR_INVALID;
+    std::vector<vrdd_error_entry> e;
+    std::vector<uint64_t> off;
+    if (pack_errors(codebook, errors_dense, (size_t)nvox, bins, 0, &e, &off) != 0) return VRDD_ERR_RANGE;
+    std::memcpy(chunk_offsets, off.data(), sizeof(uint64_t) * off.size());
+    if (entries && !e.empty()) std::memcpy(entries, e.data(), sizeof(vrdd_error_entry) * e.size());
+    if (total_ne) *total_ne = e.size();
+    return VRDD_OK;
+}
+
 int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* errors_dense, const float* templates,
                           int num_templates) {
     CHECK_HANDLE(h);
@@ -267,30 +316,13 @@ int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* e
         return fail(c, VRDD_ERR_INVALID, "set_fractal_host: bad arguments");
     const int B = c->B;
     const size_t V = c->V;
-    // validate with the reference's guards (volumeRender_kernel.cu:781-816) and compact
     const size_t nchunks = (V + VRDD_ERR_CHUNK - 1) / VRDD_ERR_CHUNK;
-    std::vector<uint64_t> off(nchunks + 1);
-    uint64_t total = 0;
-    for (size_t v = 0; v < V; ++v) {
-        if (v % VRDD_ERR_CHUNK == 0) off[v / VRDD_ERR_CHUNK] = total;
-        const int32_t* e = codebook + 4 * v;
-        if (e[0] < 0 || e[0] >= num_templates || e[1] < 0 || e[1] > B || e[3] < 0 || e[3] > B)
-            return fail(c, VRDD_ERR_RANGE, "set_fractal_host: codebook entry out of range");
-        total += (uint64_t)e[3];
-    }
-    off[nchunks] = total;
-    std::vector<float> compact(2 * (total ? total : 1));
-    uint64_t w = 0;
-    for (size_t v = 0; v < V; ++v) {
-        const int ne = codebook[4 * v + 3];
-        const float* row = errors_dense + 2 * (v * B);
-        for (int k = 0; k < ne; ++k) {
-            const int bin = (int)row[2 * k];
-            if (bin < 0 || bin >= B) return fail(c, VRDD_ERR_RANGE, "set_fractal_host: error bin out of range");
-            compact[2 * w] = row[2 * k]; compact[2 * w + 1] = row[2 * k + 1];
-            ++w;
-        }
-    }
+    std::vector<vrdd_error_entry> compact;
+    std::vector<uint64_t> off;
+    const int bad = pack_errors(codebook, errors_dense, V, B, num_templates, &compact, &off);
+    if (bad == 1) return fail(c, VRDD_ERR_RANGE, "set_fractal_host: codebook entry out of range");
+    if (bad == 2) return fail(c, VRDD_ERR_RANGE, "set_fractal_host: error bin out of range");
+    if (compact.empty()) compact.resize(1);
     for (int i = 0; i < num_templates * B; ++i)
         if (!(templates[i] >= 0.0f && templates[i] <= 1.0f))
             return fail(c, VRDD_ERR_RANGE, "set_fractal_host: template frequency outside [0,1]");
@@ -300,11 +332,11 @@ int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* e
     if (c->tmpl_owned) cudaFree(c->tmpl_owned);
     c->cb_owned = nullptr; c->err_owned = nullptr; c->off_owned = nullptr; c->tmpl_owned = nullptr;
     VRDD_CUDA(c, cudaMalloc(&c->cb_owned, sizeof(int32_t) * 4 * V));
-    VRDD_CUDA(c, cudaMalloc(&c->err_owned, sizeof(float) * compact.size()));
+    VRDD_CUDA(c, cudaMalloc(&c->err_owned, sizeof(vrdd_error_entry) * compact.size()));
     VRDD_CUDA(c, cudaMalloc(&c->off_owned, sizeof(uint64_t) * (nchunks + 1)));
     VRDD_CUDA(c, cudaMalloc(&c->tmpl_owned, sizeof(float) * num_templates * B));
     VRDD_CUDA(c, cudaMemcpyAsync(c->cb_owned, codebook, sizeof(int32_t) * 4 * V, cudaMemcpyHostToDevice, c->stream));
-    VRDD_CUDA(c, cudaMemcpyAsync(c->err_owned, compact.data(), sizeof(float) * compact.size(),
+    VRDD_CUDA(c, cudaMemcpyAsync(c->err_owned, compact.data(), sizeof(vrdd_error_entry) * compact.size(),
                                  cudaMemcpyHostToDevice, c->stream));
     VRDD_CUDA(c, cudaMemcpyAsync(c->off_owned, off.data(), sizeof(uint64_t) * (nchunks + 1), cudaMemcpyHostToDevice,
                                  c->stream));
@@ -316,7 +348,7 @@ int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* e
     return build_template_moments(c, c->tmpl, num_templates);
 }
 
-int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const float* d_errors,
+int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const vrdd_error_entry* d_errors,
                             const uint64_t* d_chunk_offsets, const float* d_templates, int num_templates, int z0,
                             int nz) {
     CHECK_HANDLE(h);
@@ -584,8 +616,8 @@ int vrdd_synth_histograms_device(vrdd_handle h, uint32_t seed, int z0, int nz, f
 }
 
 int vrdd_synth_fractal_device(vrdd_handle h, uint32_t seed, int num_templates, int max_ne, int z0, int nz,
-                              int32_t* d_codebook, float* d_errors, uint64_t* d_chunk_offsets, float* d_templates,
-                              uint64_t* total_ne) {
+                              int32_t* d_codebook, vrdd_error_entry* d_errors, uint64_t* d_chunk_offsets,
+                              float* d_templates, uint64_t* total_ne) {
     CHECK_HANDLE(h);
     if (!c->V || !d_codebook || !d_errors || !d_chunk_offsets || !d_templates || num_templates <= 0 || max_ne < 0 ||
         max_ne > VRDD_BINS || z0 < 0 || nz <= 0 || z0 + nz > c->D)
@@ -692,7 +724,9 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
     } else if (w == "decode_fractal") {
         if (v == "dense") c->var_fractal = 0;
         else if (v == "moments") c->var_fractal = 1;
-        else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal is dense|moments");
+        else if (v == "moments_global") c->var_fractal = 2;
+        else if (v == "moments768") c->var_fractal = 3;
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal is dense|moments|moments_global");
     } else if (w == "decode_order") {
         if (v == "interleaved") c->var_decode_order = 0;
         else if (v == "chunked") c->var_decode_order = 1;

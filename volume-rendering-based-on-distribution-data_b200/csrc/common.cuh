@@ -200,16 +200,16 @@ struct vrdd_context {
 
     // fractal codes (attached slab)
     int32_t* cb_owned = nullptr;
-    float* err_owned = nullptr;
+    void* err_owned = nullptr;
     uint64_t* off_owned = nullptr;
     float* tmpl_owned = nullptr;
     const int32_t* cb = nullptr;
-    const float* errs = nullptr;
+    const void* errs = nullptr;          // vrdd_error_entry[], round-major per 32-voxel chunk
     const uint64_t* err_off = nullptr;
     const float* tmpl = nullptr;
     int num_templates = 0;
     int fr_z0 = 0, fr_nz = 0;
-    double* tmpl_mom = nullptr;      // per-template prefix moments (decode_fractal "moments" variant)
+    void* tmpl_mom = nullptr;        // per-(template, flip, shift) centred moments + {value, g(value)} rows (decode_fractal.cu)
 
     vrdd_decoded_volume vol[2];
     int sampler = VRDD_SAMPLER_TEXTURE;
@@ -238,7 +238,7 @@ struct vrdd_context {
     int var_decode_order = 1;        // tma tile order: 0 interleaved over CTAs, 1 one contiguous run per CTA (TLB-friendly, default)
     int var_tf = 1;                  // 0 texture unit, 1 shared-memory table (default: frees the TEX pipe)
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
-    int var_fractal = 1;             // 0 dense (O(B) per voxel), 1 moments (O(NE) per voxel, default)
+    int var_fractal = 1;             // 0 dense (O(B) per voxel), 1 moments (O(NE) per voxel, tables in smem, default), 2 moments with global tables
 };
 
 namespace vrdd {
@@ -256,14 +256,14 @@ int ensure_volume_storage(vrdd_context* c, int source);
 
 // kernels' host launchers (one per .cu)
 int launch_decode_hist(vrdd_context* c, const float* d_hist, long long nvox, const DecodeOut& out);
-int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const float* errs, const uint64_t* off,
+int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const void* errs, const uint64_t* off,
                           const float* tmpl, int T, long long nvox, const DecodeOut& out, float* d_recon);
 int build_template_moments(vrdd_context* c, const float* d_tmpl, int T);
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses);
 int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_hist);
 int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int z0, int nz, int32_t* d_cb,
-                         float* d_err, uint64_t* d_off, float* d_tmpl, uint64_t* total_ne);
+                         vrdd_error_entry* d_err, uint64_t* d_off, float* d_tmpl, uint64_t* total_ne);
 int launch_synth_hist_region(vrdd_context* c, uint32_t seed, int gw, int gh, int gd, int ox, int oy, int oz, int z0,
                              int nz, float* d_hist);
 int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float* d_out, int iw, int ih,

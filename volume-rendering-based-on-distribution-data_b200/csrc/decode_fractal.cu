@@ -14,38 +14,44 @@
 // before normalisation so tests can compare it bit for bit.  Statistics are fp32 with
 // MUFU.LG2 (see decode_hist.cu for why not fp64).
 //
-// Inputs are the compact form: 16 B codebook entry + 8*NE B of errors per voxel (the
-// reference's dense float2[V][32] error table is 256 B per voxel, mostly unused), with an
-// error-offset entry every 256 voxels; offsets inside a tile come from a block scan of NE.
-//
-// Kernel shape: persistent CTAs of 512 threads, one voxel per thread, 512 voxels per
-// iteration.  The template table (T x 32 floats, 79.6 KB at T = 622) is loaded into shared
-// memory once per CTA; a tile's errors are staged into shared memory with coalesced loads;
-// each thread's 32-bin working histogram lives in shared memory as cur[bin][thread], which
-// is bank-conflict-free for the data-dependent error updates.
+// Inputs are the compact form (include/vrdd.h, vrdd_set_fractal_device): 16 B codebook entry +
+// 8*NE B of errors per voxel (the reference's dense float2[V][32] error table is 256 B per
+// voxel, mostly unused).  Errors are grouped per chunk of 32 consecutive voxels — one warp —
+// and stored ROUND-MAJOR inside a chunk: first the first error of every voxel that has one (in
+// voxel order), then the second errors, ...  In round k the lanes with NE > k therefore read
+// consecutive entries: one coalesced load per round straight from global memory, no staging,
+// no prefix scan; a lane's slot in the round is its rank in the ballot of (k < NE).
 #include "common.cuh"
 
 namespace vrdd {
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kErrCap = 4096;          // staged error entries per tile (32 KB)
+struct ErrEntry { int bin; float val; };     // vrdd_error_entry
 
+__device__ __forceinline__ ErrEntry ldg_stream_err(const ErrEntry* p) {
+    ErrEntry r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.bin), "=f"(r.val) : "l"(p));
+    return r;
+}
+
+constexpr int kThreads = 512;
+
+// ---- "dense" variant: the reference's order of operations on a private 32-bin histogram -----
+// Persistent CTAs of 512 threads, one voxel per thread; the template table (T x 32 floats,
+// 79.6 KB at T = 622) sits in shared memory when it fits; each thread's working histogram lives
+// in shared memory as cur[bin][thread], bank-conflict-free for the data-dependent updates.
 __global__ void __launch_bounds__(kThreads, 1)
-decode_fractal_dense_kernel(const int4* __restrict__ codebook, const float2* __restrict__ errs,
+decode_fractal_dense_kernel(const int4* __restrict__ codebook, const ErrEntry* __restrict__ errs,
                             const unsigned long long* __restrict__ chunk_off,
                             const float* __restrict__ tmpl_g, int T, int tmpl_in_smem, long long nvox,
                             DecodeOut out, float* __restrict__ recon) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* cur = reinterpret_cast<float*>(smem_raw);                         // [32][kThreads]
-    float2* estage = reinterpret_cast<float2*>(cur + VRDD_BINS * kThreads);  // [kErrCap]
-    int* wsum = reinterpret_cast<int*>(estage + kErrCap);                    // [kThreads/32]
-    float* tmpl_s = reinterpret_cast<float*>(wsum + kThreads / 32);          // [T*32] if tmpl_in_smem
+    float* tmpl_s = cur + VRDD_BINS * kThreads;                              // [T*32] if tmpl_in_smem
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const unsigned lt = (1u << (tid & 31)) - 1u;
 
     if (tmpl_in_smem) {
         const float4* src = reinterpret_cast<const float4*>(tmpl_g);
@@ -70,29 +76,6 @@ decode_fractal_dense_kernel(const int4* __restrict__ codebook, const float2* __r
         const int flip = code.z;
         const int ne = live ? min(max(code.w, 0), VRDD_BINS) : 0;
 
-        // exclusive scan of NE over the tile -> this thread's first error
-        int incl = ne;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += n;
-        }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        int wbase = 0, tile_total = 0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) {
-            const int s = wsum[w];
-            if (w < warp) wbase += s;
-            tile_total += s;
-        }
-        const int my_off = wbase + incl - ne;
-        // chunk_off has one entry per VRDD_ERR_CHUNK (32) voxels; a tile spans 16 of them
-        const unsigned long long tile_base = chunk_off[tile * (kThreads / VRDD_ERR_CHUNK)];
-        const bool staged = tile_total <= kErrCap;
-        if (staged)
-            for (int i = tid; i < tile_total; i += kThreads) estage[i] = errs[tile_base + i];
-
         // template row, flipped and rotated, into this thread's column of cur[][]
         const float* row = tmpl + (size_t)id * VRDD_BINS;
 #pragma unroll
@@ -101,21 +84,20 @@ decode_fractal_dense_kernel(const int4* __restrict__ codebook, const float2* __r
             if (flip) si = VRDD_BINS - 1 - si;
             cur[m * kThreads + tid] = row[si];
         }
-        __syncthreads();                                   // estage complete (cur is thread-private)
 
-        // Uniform trip count + predicated body: with `k < ne` as the loop bound, lanes leave the loop
-        // at different iterations and ptxas does not reconverge them before the statistics below,
-        // which then run once per distinct NE with a sliver of the warp (ncu: 8.8x the instructions).
-        const int ne_warp = __reduce_max_sync(0xffffffffu, ne);
-        for (int k = 0; k < ne_warp; ++k) {
+        // rounds of the warp's chunk; warp-uniform trip count (the ballot) keeps the lanes converged
+        unsigned long long pos = (v - (tid & 31) < nvox) ? chunk_off[v >> 5] : 0ull;
+        for (int k = 0;; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, k < ne);
+            if (m == 0u) break;
             if (k < ne) {
-                const float2 e = staged ? estage[my_off + k] : errs[tile_base + my_off + k];
-                const int bin = (int)e.x;
-                if (bin >= 0 && bin < VRDD_BINS) {
-                    float x = cur[bin * kThreads + tid] + e.y;
-                    cur[bin * kThreads + tid] = (x < 0.f) ? 0.f : x;
+                const ErrEntry e = errs[pos + __popc(m & lt)];
+                if ((unsigned)e.bin < (unsigned)VRDD_BINS) {
+                    float x = cur[e.bin * kThreads + tid] + e.val;
+                    cur[e.bin * kThreads + tid] = (x < 0.f) ? 0.f : x;
                 }
             }
+            pos += __popc(m);
         }
         __syncwarp();
 
@@ -148,63 +130,177 @@ decode_fractal_dense_kernel(const int4* __restrict__ codebook, const float2* __r
             emit_decoded(out, v, mean_raw * (float)(1.0 / VRDD_MEAN_NORM), (va + vb) * (float)(1.0 / VRDD_VAR_NORM),
                          -(E0 + E1) * (1.0f / 5.0f));
         }
-        __syncthreads();                                   // estage / wsum reused by the next tile
     }
 }
 
 // ---- "moments" variant: O(NE) per voxel instead of O(B) ------------------------------------
 //
-// Everything d_basicDataProcessing computes from the reconstructed histogram is a function of
-// four sums over its bins m:  A0 = sum cur[m],  A1 = sum m cur[m],  A2 = sum m^2 cur[m],
-// AH = sum cur[m] log2 cur[m]:
-//     tot = A0;  mean1 = bw*A1/tot + bw/2;  variance1 = bw^2 (A2/tot - (A1/tot)^2);
+// Everything d_basicDataProcessing computes from the reconstructed histogram cur[] is a function of four
+// sums over its bins m, taken about any reference point c:
+//     A0 = sum cur[m],  B1 = sum (m-c) cur[m],  B2 = sum (m-c)^2 cur[m],  AH = sum cur[m] log2 cur[m]
+//     tot = A0;  mean1 = bw (c + B1/tot) + bw/2;  variance1 = bw^2 (B2/tot - (B1/tot)^2);
 //     entropy1 = -(AH/tot - log2 tot) / log2(32)
-// (volumeRender_kernel.cu:828-867 with p = cur/tot).  For cur = shift(flip(template)) those
-// sums follow from per-template prefix moments — a circular shift by s moves every bin by s
-// except the last s source bins, which wrap by -32; a flip maps j -> 31-j — and AH / A0 do not
-// depend on the permutation at all.  Each of the NE sparse errors then changes ONE bin from
-// `old` (a template entry) to `new = max(old + val, 0)`, which updates the four sums by
-// (new-old), m(new-old), m^2(new-old), g(new)-g(old).  The per-bin values are the same floats
-// the reference forms; only the order of the (double precision) summation differs, so results
-// agree with the oracle to rounding.  A voxel whose errors hit the same bin twice (the
-// reference applies them in order, with a clamp in between) takes the dense route in-thread.
+// (volumeRender_kernel.cu:828-867 with p = cur/tot).  For cur = shift(flip(template)) there are only
+// T x 2 x 32 different histograms, so their sums are tabulated once (fp64, build_moments_kernel) with c = the
+// permuted template's own mean, which makes B1 vanish and B2 its central second moment: one 16-byte entry
+// {c, B2, A0, AH} per (template, flip, shift).  Each of the NE sparse errors then changes ONE bin from `old`
+// (a template entry) to `new = max(old + val, 0)`, which updates the sums by (new-old), (m-c)(new-old),
+// (m-c)^2 (new-old), g(new)-g(old) with g(x) = x log2 x.  Because the sums are centred, the corrections and
+// the final combination need no more than fp32: B1/tot is the small shift of the mean the errors cause, so
+// B2/tot - (B1/tot)^2 does not cancel.  The per-bin values are the same floats the reference forms; only the
+// order of the summation differs, so results agree with the oracle to rounding.  A voxel whose errors hit
+// the same bin twice (the reference applies them in order, with a clamp in between) takes the dense route.
 //
-// Per voxel: 16 B codebook + 8*NE B errors + 12 B out from/to HBM; ~5 table words from L2/L1.
-constexpr int kMomStride = 72;          // doubles per template: pre0[33], pre1[33], P2, PH, pad
-constexpr int kMomThreads = 256;
+// Per voxel: 16 B codebook + 8*NE B errors + 12 B out from/to HBM, one 16-B table entry from L2.
+//
+// Table layout in vrdd_context::tmpl_mom: float4 [T][2][32] {c, B2, A0, AH} indexed (id, flip, shift), then
+// float2 [T][32] {t[j], g(t[j])}.
+constexpr int kMomBytesPerTemplate = 2 * VRDD_BINS * 16 + VRDD_BINS * 8;      // 1280
+constexpr int kMomThreads = 256;        // global-table kernel
 constexpr int kMomWarps = kMomThreads / 32;
-constexpr int kMomErrCap = 256;         // staged error entries per warp (2 KB)
 
-__global__ void build_moments_kernel(const float* __restrict__ tmpl, int T, double* __restrict__ mom) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
+__device__ __forceinline__ float xlog2x(float x) { return __fmul_rn(x, fast_log2(fmaxf(x, 1.0e-37f))); }
+
+__global__ void build_moments_kernel(const float* __restrict__ tmpl, int T, float4* __restrict__ perm,
+                                     float2* __restrict__ vg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // (t, flip, s)
+    if (i >= T * 2 * VRDD_BINS) return;
+    const int t = i / (2 * VRDD_BINS), s = i & (VRDD_BINS - 1);
+    const int fm = ((i / VRDD_BINS) & 1) ? VRDD_BINS - 1 : 0;
     const float* r = tmpl + (size_t)t * VRDD_BINS;
-    double* m = mom + (size_t)t * kMomStride;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, ah = 0.0;
-    for (int j = 0; j < VRDD_BINS; ++j) {
-        m[j] = a0; m[33 + j] = a1;
-        const double v = (double)r[j];
-        a0 += v; a1 += j * v; a2 += (double)(j * j) * v;
+    double a0 = 0.0, a1 = 0.0, ah = 0.0;
+    for (int m = 0; m < VRDD_BINS; ++m) {
+        const double v = (double)r[((m - s) & (VRDD_BINS - 1)) ^ fm];
+        a0 += v; a1 += m * v;
         if (v > 0.0) ah += v * log2(v);
     }
-    m[32] = a0; m[65] = a1; m[66] = a2; m[67] = ah;
-    m[68] = m[69] = m[70] = m[71] = 0.0;
+    const float c = (a0 > 0.0) ? (float)(a1 / a0) : 0.f;
+    double b2 = 0.0;
+    for (int m = 0; m < VRDD_BINS; ++m) {
+        const double dm = (double)m - (double)c;
+        b2 += dm * dm * (double)r[((m - s) & (VRDD_BINS - 1)) ^ fm];
+    }
+    // the residual first moment a1 - c*a0 (|.| < 2e-6 a0) is dropped: it moves the mean by < 1e-7 bins
+    perm[i] = make_float4(c, (float)b2, (float)a0, (float)ah);
+    if (i < T * VRDD_BINS) vg[i] = make_float2(tmpl[i], xlog2x(tmpl[i]));
 }
 
-__device__ __forceinline__ float xlog2x(float x) { return x * fast_log2(fmaxf(x, 1.0e-37f)); }
+// What one lane does for its voxel (shared by both moments kernels).  `row` is the voxel's
+// {value, g(value)} template row (shared or global memory), `ent` its table entry, `pos` the
+// warp's chunk offset.  Trip counts come from ballots, so they are warp-uniform and the lanes
+// stay converged for the tail.
+__device__ __forceinline__ void moments_voxel(const float2* __restrict__ row, const ErrEntry* __restrict__ errs,
+                                              unsigned long long pos, int ne, int s, int fm, const float4 ent,
+                                              unsigned lt, float& mean_n, float& var_n, float& ent_n) {
+    const float c = ent.x;
+    float d0 = 0.f, b1 = 0.f, b2 = 0.f, dh = 0.f;
+    unsigned touched = 0u, dup = 0u;
+    // branch-free: an absent or out-of-range entry is (bin 32, value 0): it reads a valid row slot, leaves
+    // new == old, so every increment below is exactly zero, and sets no bit (shl.b32 clamps the shift)
+    auto apply = [&](int bin, float val) {
+        const bool ok = (unsigned)bin < (unsigned)VRDD_BINS;
+        bin = ok ? bin : VRDD_BINS;
+        val = ok ? val : 0.f;
+        unsigned bit;
+        asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(bin));
+        dup |= touched & bit;
+        touched |= bit;
+        const float2 og = row[((bin - s) & (VRDD_BINS - 1)) ^ fm];
+        const float newv = fmaxf(og.x + val, 0.f);
+        const float d = newv - og.x;
+        const float fc = (__int_as_float(0x4b000000 | bin) - 8388608.f) - c;    // (float)bin - c without the conversion pipe
+        d0 += d; b1 = fmaf(fc, d, b1); b2 = fmaf(fc * fc, d, b2);
+        dh += __fadd_rn(xlog2x(newv), -og.y);                                   // exactly 0 when new == old
+    };
+    // The first kRounds rounds are loaded before any of them is used (their addresses depend only on the
+    // ballots), so a tile pays one memory latency for its errors, not one per round.
+    constexpr int kRounds = 8;
+    ErrEntry e[kRounds];
+    const ErrEntry* eb = errs + pos;
+    unsigned off = 0u;                                           // < 32 * 32 entries per chunk
+    int rounds = 0;                                              // warp-uniform: rounds with at least one error
+#pragma unroll
+    for (int k = 0; k < kRounds; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, k < ne);
+        e[k].bin = VRDD_BINS; e[k].val = 0.f;
+        if (k < ne) e[k] = ldg_stream_err(eb + (off + __popc(m & lt)));
+        off += __popc(m);
+        rounds += (m != 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < kRounds; ++k) {
+        if (k < rounds) apply(e[k].bin, e[k].val);
+    }
+    if (rounds == kRounds) {
+        for (int k = kRounds;; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, k < ne);
+            if (m == 0u) break;
+            ErrEntry x; x.bin = VRDD_BINS; x.val = 0.f;
+            if (k < ne) x = ldg_stream_err(eb + (off + __popc(m & lt)));
+            apply(x.bin, x.val);
+            off += __popc(m);
+        }
+    }
 
-// Warps are independent: a warp owns 32 consecutive voxels (one entry of the error-offset
-// table), scans their NE with shuffles, stages its own errors in its own slice of shared
-// memory and never meets a CTA-wide barrier.  The sparse corrections are accumulated in fp32
-// (they are small against the template sums); only the final combination is fp64.
+    const float bw = VRDD_MAX_HISTOGRAM / (float)VRDD_BINS;
+    mean_n = 0.f; var_n = 0.f; ent_n = 0.f;
+    const float A0 = ent.z + d0;
+    if (!dup && A0 > 0.f) {
+        const float inv = 1.0f / A0;
+        const float dm = b1 * inv;                               // shift of the mean caused by the errors
+        mean_n = fmaf(bw, c + dm, 0.5f * bw) * (float)(1.0 / VRDD_MEAN_NORM);
+        var_n = bw * bw * fmaxf(fmaf(ent.y + b2, inv, -dm * dm), 0.f) * (float)(1.0 / VRDD_VAR_NORM);
+        ent_n = -(fmaf(ent.w + dh, inv, -fast_log2(A0))) * 0.2f;
+    }                                             // A0 == 0: the all-zero histogram stays unnormalised (:833)
+    // A bin hit twice: do what the reference does, in order, on a private histogram.  The rounds are walked
+    // again by the whole warp (the ballots need every lane); only the lanes that saw a duplicate apply them.
+    if (__any_sync(0xffffffffu, dup != 0u)) {
+        float cur[VRDD_BINS];
+        if (dup)
+            for (int mm = 0; mm < VRDD_BINS; ++mm) cur[mm] = row[((mm - s) & (VRDD_BINS - 1)) ^ fm].x;
+        off = 0u;
+        for (int k = 0;; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, k < ne);
+            if (m == 0u) break;
+            if (dup && k < ne) {
+                const ErrEntry x = eb[off + __popc(m & lt)];
+                if ((unsigned)x.bin < (unsigned)VRDD_BINS) {
+                    const float y = cur[x.bin] + x.val;
+                    cur[x.bin] = (y < 0.f) ? 0.f : y;
+                }
+            }
+            off += __popc(m);
+        }
+        if (dup) {
+            float tot = 0.f;
+            for (int mm = 0; mm < VRDD_BINS; ++mm) tot += cur[mm];
+            const float inv = (tot > 0.f) ? 1.0f / tot : 1.0f;
+            float mean_raw = 0.f, E = 0.f, var = 0.f;
+            for (int mm = 0; mm < VRDD_BINS; ++mm) {
+                cur[mm] *= inv;
+                mean_raw = fmaf(cur[mm], fmaf(bw, (float)mm, 0.5f * bw), mean_raw);
+                E += plog2p(cur[mm]);
+            }
+            for (int mm = 0; mm < VRDD_BINS; ++mm) {
+                const float dd = fmaf(bw, (float)mm, 0.5f * bw) - mean_raw;
+                var = fmaf(cur[mm] * dd, dd, var);
+            }
+            mean_n = mean_raw * (float)(1.0 / VRDD_MEAN_NORM);
+            var_n = var * (float)(1.0 / VRDD_VAR_NORM);
+            ent_n = -E * 0.2f;
+        }
+        __syncwarp();
+    }
+}
+
+// Tables in global memory (any T).  A warp owns 32 consecutive voxels (one entry of the error-offset table).
 __global__ void __launch_bounds__(kMomThreads)
-decode_fractal_moments_kernel(const int4* __restrict__ codebook, const float2* __restrict__ errs,
-                              const unsigned long long* __restrict__ chunk_off, const float* __restrict__ tmpl,
-                              const double* __restrict__ mom, int T, long long nvox, DecodeOut out) {
-    __shared__ float2 estage_all[kMomWarps][kMomErrCap];
+decode_fractal_moments_kernel(const int4* __restrict__ codebook, const ErrEntry* __restrict__ errs,
+                              const unsigned long long* __restrict__ chunk_off,
+                              const float4* __restrict__ perm, const float2* __restrict__ vg_g, int T, long long nvox,
+                              DecodeOut out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2* estage = estage_all[warp];
-    const double bw = (double)(VRDD_MAX_HISTOGRAM / (float)VRDD_BINS);
+    const unsigned lt = (1u << lane) - 1u;
     const long long nwt = (nvox + 31) / 32;
     const long long wstride = (long long)gridDim.x * kMomWarps;
 
@@ -216,136 +312,131 @@ decode_fractal_moments_kernel(const int4* __restrict__ codebook, const float2* _
         const unsigned long long base = chunk_off[wt];          // same address in every lane: one broadcast load
         const int id = min(max(code.x, 0), T - 1);
         const int s = code.y & (VRDD_BINS - 1);
-        const bool flip = code.z != 0;
+        const int fl = code.z != 0;
         const int ne = live ? min(max(code.w, 0), VRDD_BINS) : 0;
-
-        // sums of the permuted template from its prefix moments
-        const double* m = mom + (size_t)id * kMomStride;
-        const double P0 = m[32], P1 = m[65], P2 = m[66], PH = m[67];
-        const double q0 = flip ? m[s] : m[32 - s], q1 = flip ? m[33 + s] : m[65 - s];
-
-        int incl = ne;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += n;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int my_off = incl - ne;
-        const bool staged = total <= kMomErrCap;
-        __syncwarp();                                           // previous tile's readers are done
-        if (staged)
-            for (int i = lane; i < total; i += 32) estage[i] = errs[base + i];
-        __syncwarp();
-
-        // sparse corrections: d0 = sum (new-old), d1 = sum bin (new-old), d2 = sum bin^2 (new-old),
-        // dh = sum g(new)-g(old); uniform trip count keeps the warp converged for the tail
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, dh = 0.f;
-        unsigned touched = 0u;
-        bool dup = false;
-        const float* row = tmpl + (size_t)id * VRDD_BINS;
-        const float2* my_err = staged ? (estage + my_off) : (errs + base + my_off);
-        const int ne_warp = __reduce_max_sync(0xffffffffu, ne);
-        for (int k = 0; k < ne_warp; ++k) {
-            if (k < ne) {
-                const float2 e = my_err[k];
-                const int bin = (int)e.x;
-                if (bin >= 0 && bin < VRDD_BINS) {
-                    dup = dup || ((touched >> bin) & 1u);
-                    touched |= 1u << bin;
-                    const int si = (bin - s) & (VRDD_BINS - 1);
-                    const float oldv = __ldg(row + (flip ? VRDD_BINS - 1 - si : si));
-                    const float newv = fmaxf(oldv + e.y, 0.f);
-                    const float d = newv - oldv, fb = (float)bin;
-                    d0 += d; d1 = fmaf(fb, d, d1); d2 = fmaf(fb * fb, d, d2);
-                    dh += xlog2x(newv) - xlog2x(oldv);
-                }
-            }
-        }
-        __syncwarp();
-
-        float mean_n = 0.f, var_n = 0.f, ent_n = 0.f;
-        if (!dup) {
-            double S1, S2, U0, U1;                   // moments of src[], and of its last s bins
-            if (!flip) { S1 = P1; S2 = P2; U0 = P0 - q0; U1 = P1 - q1; }
-            else { S1 = 31.0 * P0 - P1; S2 = 961.0 * P0 - 62.0 * P1 + P2; U0 = q0; U1 = 31.0 * q0 - q1; }
-            const double sd = (double)s;
-            const double A0 = P0 + (double)d0;
-            const double A1 = S1 + sd * P0 - 32.0 * U0 + (double)d1;
-            const double A2 = S2 + 2.0 * sd * S1 + sd * sd * P0 - 64.0 * (U1 + sd * U0) + 1024.0 * U0 + (double)d2;
-            const double AH = PH + (double)dh;
-            if (A0 > 0.0) {
-                double inv = (double)(1.0f / (float)A0);       // fp32 seed + one Newton step: ~1e-14
-                inv = inv * (2.0 - A0 * inv);
-                const double mi = A1 * inv;
-                mean_n = (float)((bw * mi + 0.5 * bw) * (1.0 / VRDD_MEAN_NORM));
-                var_n = (float)(bw * bw * fmax(A2 * inv - mi * mi, 0.0) * (1.0 / VRDD_VAR_NORM));
-                ent_n = (float)(-(AH * inv - (double)__log2f((float)A0)) * 0.2);
-            }                                         // else: all-zero histogram stays unnormalised (:833)
-        } else {
-            // a bin hit twice: do what the reference does, in order, on a private histogram
-            float cur[VRDD_BINS];
-            for (int mm = 0; mm < VRDD_BINS; ++mm) {
-                const int si = (mm - s) & (VRDD_BINS - 1);
-                cur[mm] = __ldg(row + (flip ? VRDD_BINS - 1 - si : si));
-            }
-            for (int k = 0; k < ne; ++k) {
-                const float2 e = my_err[k];
-                const int bin = (int)e.x;
-                if (bin < 0 || bin >= VRDD_BINS) continue;
-                const float x = cur[bin] + e.y;
-                cur[bin] = (x < 0.f) ? 0.f : x;
-            }
-            float tot = 0.f;
-            for (int mm = 0; mm < VRDD_BINS; ++mm) tot += cur[mm];
-            const float inv = (tot > 0.f) ? 1.0f / tot : 1.0f;
-            const float bwf = (float)bw;
-            float mean_raw = 0.f, E = 0.f, var = 0.f;
-            for (int mm = 0; mm < VRDD_BINS; ++mm) {
-                cur[mm] *= inv;
-                mean_raw = fmaf(cur[mm], fmaf(bwf, (float)mm, 0.5f * bwf), mean_raw);
-                E += plog2p(cur[mm]);
-            }
-            for (int mm = 0; mm < VRDD_BINS; ++mm) {
-                const float dd = fmaf(bwf, (float)mm, 0.5f * bwf) - mean_raw;
-                var = fmaf(cur[mm] * dd, dd, var);
-            }
-            mean_n = mean_raw * (float)(1.0 / VRDD_MEAN_NORM);
-            var_n = var * (float)(1.0 / VRDD_VAR_NORM);
-            ent_n = -E * 0.2f;
-        }
-        __syncwarp();
+        const float4 ent = __ldg(perm + ((id * 2 + fl) * VRDD_BINS + s));
+        float mean_n, var_n, ent_n;
+        moments_voxel(vg_g + (size_t)id * VRDD_BINS, errs, base, ne, s, fl ? VRDD_BINS - 1 : 0, ent, lt, mean_n, var_n, ent_n);
         if (live) emit_decoded(out, v, mean_n, var_n, ent_n);
     }
 }
 
+// The same algorithm with the {value, g(value)} rows in shared memory (T*256 B, 159 KB at T = 622): the
+// data-dependent row reads were 32-way divergent global loads and made the kernel L1-tag bound (ncu,
+// profiles/summary_r1d.md: l1tex 72 %, 230 tag requests per warp iteration); in shared memory they cost a few
+// bank-conflict wavefronts each.  Only the one table entry per voxel stays a global (L2-resident) load.
+// One persistent CTA of independent warps per SM; the next tile's codebook entry and error offset are loaded
+// before the current tile is processed; the voxel coordinate advances incrementally when tiles do not
+// straddle rows (W % 32 == 0) instead of being divided out per voxel.
+size_t moments_smem_bytes(int T) { return (size_t)T * VRDD_BINS * sizeof(float2); }
+
+template <int kSmThreads>
+__global__ void __launch_bounds__(kSmThreads, 1)
+decode_fractal_moments_smem_kernel(const int4* __restrict__ codebook, const ErrEntry* __restrict__ errs,
+                                   const unsigned long long* __restrict__ chunk_off,
+                                   const float4* __restrict__ perm, const float2* __restrict__ vg_g, int T,
+                                   long long nvox, DecodeOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* vg_s = reinterpret_cast<float2*>(smem_raw);                                   // [T][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    {
+        const float4* src = reinterpret_cast<const float4*>(vg_g);
+        float4* dst = reinterpret_cast<float4*>(vg_s);
+        for (int i = threadIdx.x; i < T * (VRDD_BINS / 2); i += kSmThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    constexpr int kSmWarps = kSmThreads / 32;
+    const long long nwt = (nvox + 31) / 32;
+    const long long wstride = (long long)gridDim.x * kSmWarps;
+    long long wt = (long long)blockIdx.x * kSmWarps + warp;
+    if (wt >= nwt) return;
+
+    // voxel coordinate of lane 0 of this warp's tile and of the stride between its tiles
+    const bool rows32 = ((out.W & 31) == 0) && ((out.v_base & 31) == 0) && (out.use_surf || out.brick[0]);
+    int x0 = 0, y0 = 0, z0 = 0, sx = 0, sy = 0, sz = 0;
+    if (rows32) {
+        split_voxel(out, out.v_base + wt * 32, x0, y0, z0);
+        split_voxel(out, wstride * 32, sx, sy, sz);
+    }
+
+    int4 code = make_int4(0, 0, 0, 0);
+    if (wt * 32 + lane < nvox) code = ldg_stream_i4(codebook + wt * 32 + lane);
+    unsigned long long base = chunk_off[wt];
+
+    while (true) {
+        const long long v = wt * 32 + lane;
+        const bool live = v < nvox;
+        const long long wt_n = wt + wstride;
+        int4 code_n = make_int4(0, 0, 0, 0);
+        unsigned long long base_n = 0ull;
+        if (wt_n < nwt) {                                        // next tile's inputs, in flight during this one
+            if (wt_n * 32 + lane < nvox) code_n = ldg_stream_i4(codebook + wt_n * 32 + lane);
+            base_n = chunk_off[wt_n];
+        }
+        const int id = min(max(code.x, 0), T - 1);
+        const int s = code.y & (VRDD_BINS - 1);
+        const int fl = code.z != 0;
+        const int ne = live ? min(max(code.w, 0), VRDD_BINS) : 0;
+        const float4 ent = __ldg(perm + ((id * 2 + fl) * VRDD_BINS + s));
+        float mean_n, var_n, ent_n;
+        moments_voxel(vg_s + id * VRDD_BINS, errs, base, ne, s, fl ? VRDD_BINS - 1 : 0, ent, lt, mean_n, var_n, ent_n);
+        if (live) {
+            if (rows32) emit_decoded_xyz(out, v, x0 + lane, y0, z0, mean_n, var_n, ent_n);
+            else emit_decoded(out, v, mean_n, var_n, ent_n);
+        }
+        if (wt_n >= nwt) break;
+        wt = wt_n; code = code_n; base = base_n;
+        if (rows32) {
+            x0 += sx; if (x0 >= out.W) { x0 -= out.W; ++y0; }
+            y0 += sy; if (y0 >= out.H) { y0 -= out.H; ++z0; }
+            z0 += sz;
+        }
+    }
+}
+
 size_t fractal_smem_bytes(int T, bool tmpl_in_smem) {
-    return (size_t)VRDD_BINS * kThreads * sizeof(float) + (size_t)kErrCap * sizeof(float2) +
-           (kThreads / 32) * sizeof(int) + (tmpl_in_smem ? (size_t)T * VRDD_BINS * sizeof(float) : 0);
+    return (size_t)VRDD_BINS * kThreads * sizeof(float) + (tmpl_in_smem ? (size_t)T * VRDD_BINS * sizeof(float) : 0);
 }
 
 }  // namespace
 
 int build_template_moments(vrdd_context* c, const float* d_tmpl, int T) {
     if (c->tmpl_mom) { cudaFree(c->tmpl_mom); c->tmpl_mom = nullptr; }
-    VRDD_CUDA(c, cudaMalloc(&c->tmpl_mom, sizeof(double) * (size_t)T * kMomStride));
-    build_moments_kernel<<<(T + 127) / 128, 128, 0, c->stream>>>(d_tmpl, T, c->tmpl_mom);
+    VRDD_CUDA(c, cudaMalloc(&c->tmpl_mom, (size_t)T * kMomBytesPerTemplate));
+    float4* perm = reinterpret_cast<float4*>(c->tmpl_mom);
+    float2* vg = reinterpret_cast<float2*>(perm + (size_t)T * 2 * VRDD_BINS);
+    build_moments_kernel<<<(T * 2 * VRDD_BINS + 127) / 128, 128, 0, c->stream>>>(d_tmpl, T, perm, vg);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;
 }
 
-int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const float* errs, const uint64_t* off,
+int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const void* errs, const uint64_t* off,
                           const float* tmpl, int T, long long nvox, const DecodeOut& out, float* d_recon) {
     if (nvox <= 0) return VRDD_OK;
     if (T <= 0) return fail(c, VRDD_ERR_INVALID, "decode_fractal: no templates");
-    if (c->var_fractal == 1 && d_recon == nullptr && c->tmpl_mom != nullptr) {
-        const long long nblk = (nvox + kMomThreads - 1) / kMomThreads;
-        const long long cap = (long long)c->num_sms * 8;
-        const int grid = (int)((nblk < cap) ? nblk : cap);
-        decode_fractal_moments_kernel<<<grid, kMomThreads, 0, c->stream>>>(
-            reinterpret_cast<const int4*>(cb), reinterpret_cast<const float2*>(errs),
-            reinterpret_cast<const unsigned long long*>(off), tmpl, c->tmpl_mom, T, nvox, out);
+    const int4* cb4 = reinterpret_cast<const int4*>(cb);
+    const ErrEntry* er = reinterpret_cast<const ErrEntry*>(errs);
+    const unsigned long long* of = reinterpret_cast<const unsigned long long*>(off);
+    if (c->var_fractal >= 1 && d_recon == nullptr && c->tmpl_mom != nullptr) {
+        const int threads = (c->var_fractal == 3) ? 768 : 1024;
+        const size_t smem = moments_smem_bytes(T);
+        const float4* perm = reinterpret_cast<const float4*>(c->tmpl_mom);
+        const float2* vg = reinterpret_cast<const float2*>(perm + (size_t)T * 2 * VRDD_BINS);
+        if (c->var_fractal != 2 && smem <= 227 * 1024) {        // the rows fit in shared memory (T <= 908)
+            auto kern = (threads == 768) ? decode_fractal_moments_smem_kernel<768> : decode_fractal_moments_smem_kernel<1024>;
+            VRDD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long nblk = (nvox + threads - 1) / threads;
+            const int grid = (int)((nblk < c->num_sms) ? nblk : c->num_sms);
+            kern<<<grid, threads, smem, c->stream>>>(cb4, er, of, perm, vg, T, nvox, out);
+        } else {
+            const long long nblk = (nvox + kMomThreads - 1) / kMomThreads;
+            const long long cap = (long long)c->num_sms * 8;
+            const int grid = (int)((nblk < cap) ? nblk : cap);
+            decode_fractal_moments_kernel<<<grid, kMomThreads, 0, c->stream>>>(cb4, er, of, perm, vg, T, nvox, out);
+        }
         c->launches += 1;
         VRDD_CUDA(c, cudaGetLastError());
         return VRDD_OK;
@@ -356,9 +447,8 @@ int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const float* errs,
                                       (int)smem));
     const long long ntiles = (nvox + kThreads - 1) / kThreads;
     const int grid = (int)((ntiles < c->num_sms) ? ntiles : c->num_sms);
-    decode_fractal_dense_kernel<<<grid, kThreads, smem, c->stream>>>(
-        reinterpret_cast<const int4*>(cb), reinterpret_cast<const float2*>(errs),
-        reinterpret_cast<const unsigned long long*>(off), tmpl, T, in_smem ? 1 : 0, nvox, out, d_recon);
+    decode_fractal_dense_kernel<<<grid, kThreads, smem, c->stream>>>(cb4, er, of, tmpl, T, in_smem ? 1 : 0, nvox, out,
+                                                                      d_recon);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;

@@ -76,10 +76,10 @@ synth_fractal_codes_kernel(uint32_t seed, int W, int H, int D, int T, int max_ne
     if ((threadIdx.x & 31) == 0 && chunk * VRDD_ERR_CHUNK < nvox) chunk_ne[chunk] = (unsigned int)s;
 }
 
-// pass 2: errors, compact, in voxel order
+// pass 2: errors in the compact form: per 32-voxel chunk, round k = the k-th error of every voxel with NE > k
 __global__ void __launch_bounds__(kSynthThreads)
 synth_fractal_errors_kernel(uint32_t seed, int W, int H, int D, int T, int max_ne, int z0, long long nvox,
-                            const unsigned long long* chunk_off, float2* errs) {
+                            const unsigned long long* chunk_off, vrdd_error_entry* errs) {
     const long long v = (long long)blockIdx.x * kSynthThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int code[4] = {0, 0, 0, 0}, eb[VRDD_BINS];
@@ -92,14 +92,19 @@ synth_fractal_errors_kernel(uint32_t seed, int W, int H, int D, int T, int max_n
         vrdd_synth_fractal_code(seed, x, y, z0 + z, W, H, D, VRDD_BINS, T, max_ne, code, eb, ev);
     }
     const int ne = code[3];
-    int incl = ne;
-    for (int d = 1; d < 32; d <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += n;
-    }
     if (v - lane >= nvox) return;
-    const unsigned long long base = chunk_off[v / VRDD_ERR_CHUNK] + (unsigned long long)(incl - ne);
-    for (int k = 0; k < ne; ++k) errs[base + k] = make_float2((float)eb[k], ev[k]);
+    unsigned long long pos = chunk_off[v / VRDD_ERR_CHUNK];
+    const unsigned lt = (1u << lane) - 1u;
+    for (int k = 0;; ++k) {
+        const unsigned m = __ballot_sync(0xffffffffu, k < ne);
+        if (m == 0u) break;
+        if (k < ne) {
+            vrdd_error_entry e;
+            e.bin = eb[k]; e.value = ev[k];
+            errs[pos + __popc(m & lt)] = e;
+        }
+        pos += __popc(m);
+    }
 }
 
 }  // namespace
@@ -127,7 +132,7 @@ int launch_synth_hist_region(vrdd_context* c, uint32_t seed, int gw, int gh, int
 }
 
 int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int z0, int nz, int32_t* d_cb,
-                         float* d_err, uint64_t* d_off, float* d_tmpl, uint64_t* total_ne) {
+                         vrdd_error_entry* d_err, uint64_t* d_off, float* d_tmpl, uint64_t* total_ne) {
     const long long nvox = (long long)c->W * c->H * nz;
     if (nvox <= 0) return VRDD_OK;
     const long long nchunks = (nvox + VRDD_ERR_CHUNK - 1) / VRDD_ERR_CHUNK;
@@ -154,7 +159,7 @@ int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int 
                                  c->stream));
     synth_fractal_errors_kernel<<<nblk, kSynthThreads, 0, c->stream>>>(
         seed, c->W, c->H, c->D, T, max_ne, z0, nvox, reinterpret_cast<const unsigned long long*>(d_off),
-        reinterpret_cast<float2*>(d_err));
+        d_err);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     VRDD_CUDA(c, cudaStreamSynchronize(c->stream));      // `off` must outlive the copy
