@@ -29,6 +29,11 @@ namespace {
 
 struct ErrEntry { int bin; float val; };     // vrdd_error_entry
 
+__device__ __forceinline__ unsigned long long ldg_stream_u64(const unsigned long long* p) {
+    unsigned long long r;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ ErrEntry ldg_stream_err(const ErrEntry* p) {
     ErrEntry r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.bin), "=f"(r.val) : "l"(p));
@@ -189,18 +194,19 @@ __global__ void build_moments_kernel(const float* __restrict__ tmpl, int T, floa
 // {value, g(value)} template row (shared or global memory), `ent` its table entry, `pos` the
 // warp's chunk offset.  Trip counts come from ballots, so they are warp-uniform and the lanes
 // stay converged for the tail.
+template <class AfterLoads>
 __device__ __forceinline__ void moments_voxel(const float2* __restrict__ row, const ErrEntry* __restrict__ errs,
                                               unsigned long long pos, int ne, int s, int fm, const float4 ent,
-                                              unsigned lt, float& mean_n, float& var_n, float& ent_n) {
+                                              unsigned lt, float& mean_n, float& var_n, float& ent_n,
+                                              AfterLoads&& after_loads) {
     const float c = ent.x;
     float d0 = 0.f, b1 = 0.f, b2 = 0.f, dh = 0.f;
     unsigned touched = 0u, dup = 0u;
-    // branch-free: an absent or out-of-range entry is (bin 32, value 0): it reads a valid row slot, leaves
-    // new == old, so every increment below is exactly zero, and sets no bit (shl.b32 clamps the shift)
+    // branch-free: an absent entry is (bin 32, value 0): it reads a valid row slot, leaves new == old, so
+    // every increment below is exactly zero, and sets no bit (shl.b32 clamps the shift).  Bins are trusted to
+    // be in [0, 32) (vrdd_set_fractal_host / vrdd_pack_fractal_errors reject others); whatever they hold, the
+    // row index is masked, so no access leaves the table.
     auto apply = [&](int bin, float val) {
-        const bool ok = (unsigned)bin < (unsigned)VRDD_BINS;
-        bin = ok ? bin : VRDD_BINS;
-        val = ok ? val : 0.f;
         unsigned bit;
         asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(bin));
         dup |= touched & bit;
@@ -216,17 +222,17 @@ __device__ __forceinline__ void moments_voxel(const float2* __restrict__ row, co
     // ballots), so a tile pays one memory latency for its errors, not one per round.
     constexpr int kRounds = 8;
     ErrEntry e[kRounds];
-    const ErrEntry* eb = errs + pos;
+    const char* eb = reinterpret_cast<const char*>(errs + pos);
     unsigned off = 0u;                                           // < 32 * 32 entries per chunk
-    int rounds = 0;                                              // warp-uniform: rounds with at least one error
+    const int rounds = min(__reduce_max_sync(0xffffffffu, ne), kRounds);          // warp-uniform
 #pragma unroll
     for (int k = 0; k < kRounds; ++k) {
         const unsigned m = __ballot_sync(0xffffffffu, k < ne);
         e[k].bin = VRDD_BINS; e[k].val = 0.f;
-        if (k < ne) e[k] = ldg_stream_err(eb + (off + __popc(m & lt)));
+        if (k < ne) e[k] = ldg_stream_err(reinterpret_cast<const ErrEntry*>(eb + ((off + __popc(m & lt)) << 3)));
         off += __popc(m);
-        rounds += (m != 0u);
     }
+    after_loads();
 #pragma unroll
     for (int k = 0; k < kRounds; ++k) {
         if (k < rounds) apply(e[k].bin, e[k].val);
@@ -236,7 +242,7 @@ __device__ __forceinline__ void moments_voxel(const float2* __restrict__ row, co
             const unsigned m = __ballot_sync(0xffffffffu, k < ne);
             if (m == 0u) break;
             ErrEntry x; x.bin = VRDD_BINS; x.val = 0.f;
-            if (k < ne) x = ldg_stream_err(eb + (off + __popc(m & lt)));
+            if (k < ne) x = ldg_stream_err(reinterpret_cast<const ErrEntry*>(eb + ((off + __popc(m & lt)) << 3)));
             apply(x.bin, x.val);
             off += __popc(m);
         }
@@ -246,7 +252,8 @@ __device__ __forceinline__ void moments_voxel(const float2* __restrict__ row, co
     mean_n = 0.f; var_n = 0.f; ent_n = 0.f;
     const float A0 = ent.z + d0;
     if (!dup && A0 > 0.f) {
-        const float inv = 1.0f / A0;
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(A0));   // one MUFU.RCP, 1 ulp; A0 is a sum of frequencies, ~1
         const float dm = b1 * inv;                               // shift of the mean caused by the errors
         mean_n = fmaf(bw, c + dm, 0.5f * bw) * (float)(1.0 / VRDD_MEAN_NORM);
         var_n = bw * bw * fmaxf(fmaf(ent.y + b2, inv, -dm * dm), 0.f) * (float)(1.0 / VRDD_VAR_NORM);
@@ -263,7 +270,7 @@ __device__ __forceinline__ void moments_voxel(const float2* __restrict__ row, co
             const unsigned m = __ballot_sync(0xffffffffu, k < ne);
             if (m == 0u) break;
             if (dup && k < ne) {
-                const ErrEntry x = eb[off + __popc(m & lt)];
+                const ErrEntry x = *reinterpret_cast<const ErrEntry*>(eb + ((off + __popc(m & lt)) << 3));
                 if ((unsigned)x.bin < (unsigned)VRDD_BINS) {
                     const float y = cur[x.bin] + x.val;
                     cur[x.bin] = (y < 0.f) ? 0.f : y;
@@ -316,7 +323,8 @@ decode_fractal_moments_kernel(const int4* __restrict__ codebook, const ErrEntry*
         const int ne = live ? min(max(code.w, 0), VRDD_BINS) : 0;
         const float4 ent = __ldg(perm + ((id * 2 + fl) * VRDD_BINS + s));
         float mean_n, var_n, ent_n;
-        moments_voxel(vg_g + (size_t)id * VRDD_BINS, errs, base, ne, s, fl ? VRDD_BINS - 1 : 0, ent, lt, mean_n, var_n, ent_n);
+        moments_voxel(vg_g + (size_t)id * VRDD_BINS, errs, base, ne, s, fl ? VRDD_BINS - 1 : 0, ent, lt, mean_n, var_n, ent_n,
+                      [] {});
         if (live) emit_decoded(out, v, mean_n, var_n, ent_n);
     }
 }
@@ -371,17 +379,19 @@ decode_fractal_moments_smem_kernel(const int4* __restrict__ codebook, const ErrE
         const long long wt_n = wt + wstride;
         int4 code_n = make_int4(0, 0, 0, 0);
         unsigned long long base_n = 0ull;
-        if (wt_n < nwt) {                                        // next tile's inputs, in flight during this one
-            if (wt_n * 32 + lane < nvox) code_n = ldg_stream_i4(codebook + wt_n * 32 + lane);
-            base_n = chunk_off[wt_n];
-        }
         const int id = min(max(code.x, 0), T - 1);
         const int s = code.y & (VRDD_BINS - 1);
         const int fl = code.z != 0;
         const int ne = live ? min(max(code.w, 0), VRDD_BINS) : 0;
         const float4 ent = __ldg(perm + ((id * 2 + fl) * VRDD_BINS + s));
         float mean_n, var_n, ent_n;
-        moments_voxel(vg_s + id * VRDD_BINS, errs, base, ne, s, fl ? VRDD_BINS - 1 : 0, ent, lt, mean_n, var_n, ent_n);
+        moments_voxel(vg_s + id * VRDD_BINS, errs, base, ne, s, fl ? VRDD_BINS - 1 : 0, ent, lt, mean_n, var_n, ent_n, [&] {
+            // next tile's inputs: issued behind this tile's loads, in flight while it is processed
+            if (wt_n < nwt) {
+                if (wt_n * 32 + lane < nvox) code_n = ldg_stream_i4(codebook + wt_n * 32 + lane);
+                base_n = ldg_stream_u64(chunk_off + wt_n);
+            }
+        });
         if (live) {
             if (rows32) emit_decoded_xyz(out, v, x0 + lane, y0, z0, mean_n, var_n, ent_n);
             else emit_decoded(out, v, mean_n, var_n, ent_n);
