@@ -307,7 +307,9 @@ def run_ours(args):
             torch.cuda.synchronize()
             fr_ms += e0.elapsed_time(e1) / reps
             fr_bytes += nz * slice_vox * (16 + 12) + tot * 8      # codebook + planes + 8 B per error
-        decode["fractal"] = {"kernel": "decode_fractal_" + args.fractal_variant + "_kernel", "ms": fr_ms,
+        fr_kernel = {"moments": "decode_fractal_moments_smem_kernel", "moments768": "decode_fractal_moments_smem_kernel",
+                     "moments_global": "decode_fractal_moments_kernel", "dense": "decode_fractal_dense_kernel"}
+        decode["fractal"] = {"kernel": fr_kernel.get(args.fractal_variant, args.fractal_variant), "ms": fr_ms,
                              "gbs": fr_bytes / (fr_ms * 1e-3) / 1e9,
                              "frac_of_hbm_peak": fr_bytes / (fr_ms * 1e-3) / 1e9 / hbm_peak,
                              "gvoxels_per_s": total_vox / (fr_ms * 1e-3) / 1e9, "bytes_per_voxel": fr_bytes / total_vox,
@@ -750,7 +752,7 @@ def main():
     ap.add_argument("--slab-z", type=int, default=256, help="z-slices decoded per launch (256 -> 34 GB of histograms)")
     ap.add_argument("--decode-reps", type=int, default=3)
     ap.add_argument("--decode-variant", default="tma", choices=["tma", "ldg"])
-    ap.add_argument("--fractal-variant", default="moments", choices=["moments", "dense"])
+    ap.add_argument("--fractal-variant", default="moments", choices=["moments", "moments768", "moments_global", "dense"])
     ap.add_argument("--sampler", default="texture", choices=["texture", "bricked"])
     ap.add_argument("--tf", default=None, choices=[None, "texture", "smem"])
     ap.add_argument("--unroll", type=int, default=0, choices=[0, 1, 2, 4, 8])

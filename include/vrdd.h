@@ -321,7 +321,7 @@ int vrdd_flex_prefix_spans(int x, int32_t* spans);
 /* ---- diagnostics ------------------------------------------------------------------------ */
 
 /* Selects a kernel variant by name for A/B measurement: "decode_hist" -> "tma" | "ldg";
- * "decode_order" -> "chunked" | "interleaved"; "decode_fractal" -> "moments" | "dense";
+ * "decode_order" -> "chunked" | "interleaved"; "decode_fractal" -> "moments" | "moments768" | "moments_global" | "dense";
  * "raycast_tf" -> "texture" | "smem";
  * "raycast_unroll" -> "1" | "2" | "4" | "8" (ray-march steps whose fetches are in flight
  * together).  Results do not depend on the variant.  Unknown names return VRDD_ERR_INVALID. */
