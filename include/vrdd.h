@@ -209,6 +209,15 @@ int vrdd_render(vrdd_handle h, uint32_t* d_output, int image_w, int image_h,
  * (render() + the read-back of runSingleTest, volumeRender.cpp:194-217, 1073-1074). */
 int vrdd_render_host(vrdd_handle h, uint32_t* h_output, int image_w, int image_h,
                      const vrdd_render_params* params);
+/* Pipelined form for a sequence of frames (an orbit, an animation): queues the frame and returns.
+ * Frames alternate between two device buffers; a second stream copies frame k to h_output while
+ * frame k+1 renders (the render of frame k+2 waits for that copy).  h_output should be page-locked
+ * (cudaHostAlloc / cudaHostRegister) for the copy to overlap, and holds the image once
+ * vrdd_render_host_wait has returned; use a different h_output for frames that are in flight
+ * together.  The view and parameters are taken at the call, so they may change between calls. */
+int vrdd_render_host_async(vrdd_handle h, uint32_t* h_output, int image_w, int image_h,
+                           const vrdd_render_params* params);
+int vrdd_render_host_wait(vrdd_handle h);
 /* Enables counting of transfer-function lookups (the S of Gsamples/s) in vrdd_render and
  * reads / resets the counter.  Reading synchronises. */
 int vrdd_count_samples(vrdd_handle h, int enable);

@@ -189,6 +189,29 @@ def test_render_host_end_to_end(renderer, golden):
     assert _lsb_diff(out, golden["images"][k]).max() <= 1
 
 
+def test_render_host_async_pipeline_equals_synchronous_frames(renderer, golden):
+    """vrdd_render_host_async / vrdd_render_host_wait: a sequence of views with two frames in flight (each into its
+    own pinned buffer) gives the frames of the one-at-a-time call, also across a change of image size and of the
+    render parameters between calls."""
+    import torch
+    import vrdd_b200 as V
+    r = renderer
+    _load_golden_volume(r, V, golden)
+    seq = [(vi, (96, 64) if i < 5 else (64, 48), 1 + (i % 6)) for i, vi in enumerate([0, 1, 2, 0, 2, 1, 0, 2])]
+    want = []
+    for vi, (w, h), qm in seq:
+        r.set_view(golden["views"][vi])
+        want.append(r.render_host(np.zeros((h, w), np.uint32), w, h, V.default_render_params(query_method=qm)).copy())
+    bufs = [torch.zeros(h, w, dtype=torch.int32).pin_memory() for _, (w, h), _ in seq]
+    for (vi, (w, h), qm), b in zip(seq, bufs):
+        r.set_view(golden["views"][vi])
+        r.render_host_async(b, w, h, V.default_render_params(query_method=qm))
+    r.render_host_wait()
+    for b, ref in zip(bufs, want):
+        assert np.array_equal(b.numpy().view(np.uint32), ref)
+    assert any(w_.any() for w_ in want)
+
+
 def test_custom_transfer_function(renderer, oracle, golden):
     import vrdd_b200 as V
     r = renderer

@@ -30,7 +30,8 @@ EXPORTS = [
     "vrdd_set_fractal_host", "vrdd_set_fractal_device", "vrdd_pack_fractal_errors", "vrdd_set_sampler", "vrdd_decode",
     "vrdd_get_decoded_host", "vrdd_get_decoded_planes_device", "vrdd_keep_linear_planes", "vrdd_commit_planes",
     "vrdd_reconstruct_fractal_device", "vrdd_set_transfer_function", "vrdd_set_view",
-    "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_count_samples",
+    "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_render_host_async",
+    "vrdd_render_host_wait", "vrdd_count_samples",
     "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
     "vrdd_set_variant", "vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function",
     "vrdd_debug_sample_texture_point", "vrdd_debug_sample_texture_unnorm", "vrdd_enable_interpolated_mean",
@@ -138,6 +139,8 @@ def lib():
             "vrdd_default_render_params": (None, [C.POINTER(RenderParams)]),
             "vrdd_render": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(TilePartition), i32]),
             "vrdd_render_host": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams)]),
+            "vrdd_render_host_async": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams)]),
+            "vrdd_render_host_wait": (i32, [vp]),
             "vrdd_count_samples": (i32, [vp, i32]),
             "vrdd_get_sample_count": (i32, [vp, C.POINTER(C.c_int64), i32]),
             "vrdd_view_matrix": (None, [f32, f32, f32, f32, f32, vp]),
@@ -363,6 +366,13 @@ class Renderer:
         self._ck(lib().vrdd_render_host(self._h, _ptr(h_output), w, h,
                                         C.byref(params) if params is not None else None))
         return h_output
+
+    def render_host_async(self, h_output, w, h, params=None):
+        self._ck(lib().vrdd_render_host_async(self._h, _ptr(h_output), w, h,
+                                              C.byref(params) if params is not None else None))
+
+    def render_host_wait(self):
+        self._ck(lib().vrdd_render_host_wait(self._h))
 
     def count_samples(self, enable=True):
         self._ck(lib().vrdd_count_samples(self._h, int(enable)))

@@ -203,6 +203,15 @@ int vrdd_destroy(vrdd_handle h) {
     free_tf(c);
     if (c->d_samples) cudaFree(c->d_samples);
     if (c->frame) cudaFree(c->frame);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < 2; ++i) {
+            if (c->pframe[i]) cudaFree(c->pframe[i]);
+            if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]);
+            if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+        }
+        cudaStreamDestroy(c->copy_stream);
+    }
     destroy_flex(c);
     delete c;
     return VRDD_OK;
@@ -573,6 +582,49 @@ int vrdd_render_host(vrdd_handle h, uint32_t* h_output, int image_w, int image_h
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (rc == VRDD_OK && e != cudaSuccess) rc = fail_cuda(c, e, "render_host: synchronize");
     return rc;
+}
+
+// Pipelined read-back: frame k is copied to the host by a second stream while frame k+1 renders.
+int vrdd_render_host_async(vrdd_handle h, uint32_t* h_output, int image_w, int image_h,
+                           const vrdd_render_params* params) {
+    CHECK_HANDLE(h);
+    if (!h_output || image_w <= 0 || image_h <= 0) return fail(c, VRDD_ERR_INVALID, "render_host_async: bad image");
+    const size_t bytes = sizeof(uint32_t) * (size_t)image_w * image_h;
+    if (!c->copy_stream) {
+        VRDD_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            VRDD_CUDA(c, cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming));
+            VRDD_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    if (c->pframe_bytes < bytes) {
+        VRDD_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+        for (int i = 0; i < 2; ++i) {
+            if (c->pframe[i]) cudaFree(c->pframe[i]);
+            c->pframe[i] = nullptr;
+        }
+        c->pframe_bytes = 0;
+        for (int i = 0; i < 2; ++i) VRDD_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&c->pframe[i]), bytes));
+        c->pframe_bytes = bytes;
+        c->pslot = 0;
+    }
+    const int slot = (int)(c->pslot & 1u);
+    if (c->pslot >= 2) VRDD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));   // frame k-2 has left this slot
+    const int rc = vrdd_render(h, c->pframe[slot], image_w, image_h, params, nullptr, 1);
+    if (rc != VRDD_OK) return rc;
+    VRDD_CUDA(c, cudaEventRecord(c->ev_rendered[slot], c->stream));
+    VRDD_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[slot], 0));
+    VRDD_CUDA(c, cudaMemcpyAsync(h_output, c->pframe[slot], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    VRDD_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+    c->pslot += 1;
+    return VRDD_OK;
+}
+
+int vrdd_render_host_wait(vrdd_handle h) {
+    CHECK_HANDLE(h);
+    if (c->copy_stream) VRDD_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VRDD_OK;
 }
 
 int vrdd_count_samples(vrdd_handle h, int enable) {

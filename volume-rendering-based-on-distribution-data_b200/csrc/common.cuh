@@ -232,6 +232,11 @@ struct vrdd_context {
 
     uint32_t* frame = nullptr;       // device frame of vrdd_render_host, kept between calls
     size_t frame_bytes = 0;
+    uint32_t* pframe[2] = {nullptr, nullptr};   // vrdd_render_host_async: two device frames, a copy stream and
+    size_t pframe_bytes = 0;                    // the events that order render k+2 after copy k
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_rendered[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    unsigned pslot = 0;
 
     // kernel variants (vrdd_set_variant)
     int var_decode_hist = 0;         // 0 tma, 1 ldg
