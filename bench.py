@@ -577,6 +577,9 @@ def run_ours(args):
                             "traffic = " + traffic_what + ", profiles/traffic.json; sector over-fetch, not re-reads, "
                             "separates the two"}
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
+        if ray_traffic:                                   # what the DRAM actually moved per launch, against the same peak
+            roofline["traffic_gbs"] = ray_traffic / (kernel_ms * 1e-3) / 1e9
+            roofline["traffic_frac"] = roofline["traffic_gbs"] / roofline["peak"]
         line = {"metric": "raycast_throughput", "value": gsamples, "unit": "Gsamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -8,6 +8,7 @@ out=gpurun_out
 mkdir -p $out
 timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -5 > $out/tests_$tag.log
 cat $out/tests_$tag.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 echo "== bench (ours)"; ( time timeout 900 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err ) 2>&1 | grep real
 tail -c 400 $out/bench_$tag.err
 echo "== bench (reference arm)"; ( time timeout 600 python bench.py --impl reference --steps 8 --warmup 2 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err ) 2>&1 | grep real
