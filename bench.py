@@ -512,6 +512,33 @@ def run_ours(args):
         r2.close()
         del h_hist
 
+    # ---- queryMethod 7 (interpolated block means, point-sampled cells) on the same volume and views -------
+    mode7 = None
+    if world == 1 and args.mode7:
+        try:
+            r.enable_interpolated_mean(True)                      # the block-mean plane is only kept on request
+            hb = torch.empty(slab * slice_vox * 32, dtype=torch.float32, device=dev)
+            for z0 in range(0, Dz, slab):
+                nz = min(slab, Dz - z0)
+                r.synth_histograms_device(args.seed, z0, nz, hb)
+                r.set_histograms_device(hb, z0, nz)
+                r.decode(V.SRC_ORIGINAL, z0, nz)
+            torch.cuda.synchronize()
+            del hb
+            torch.cuda.empty_cache()
+            p7 = V.default_render_params(query_method=7)
+            n7 = min(args.steps, 32)
+            c7 = count_samples(p7, min(ORBIT_VIEWS, args.warmup + n7))
+            ms7, _ = time_render(p7, n7, args.warmup)
+            s7 = steps_samples(c7, args.warmup, n7)
+            mode7 = {"gsamples_per_s": s7 / (ms7 * 1e-3) / 1e9, "ms_per_step": ms7 / n7, "fps": n7 / (ms7 * 1e-3),
+                     "steps": n7, "kernel": "raycast_mode7_kernel",
+                     "note": "8 point fetches of the un-normalised block means per sample, the reference's cell cache and "
+                             "degenerate-cell artefact kept (volumeRender_kernel.cu:395-480); the reference reports < 5 fps "
+                             "for this mode on its 50x50x10 volume (ver1.9.6.txt:168)"}
+        except Exception as exc:                                   # never let the side measurement void the headline
+            mode7 = {"error": repr(exc)}
+
     # ---- the flexible-block chain on the reference's own configuration (64^3 raw volume, block size 6) ----
     flex = None
     if world == 1 and args.flex:
@@ -600,6 +627,8 @@ def run_ours(args):
                 "clocks": clk}
         if matched:
             line["raycast_resolution_matched"] = matched
+        if mode7:
+            line["query_method_7"] = mode7
         if flex:
             line["flex_chain"] = flex
         if gather_ms is not None:
@@ -784,6 +813,7 @@ def main():
     ap.add_argument("--unroll", type=int, default=0, choices=[0, 1, 2, 4, 8])
     ap.add_argument("--fractal", type=int, default=1)
     ap.add_argument("--matched", type=int, default=1)
+    ap.add_argument("--mode7", type=int, default=1, help="also time queryMethod 7 on the same volume and views")
     ap.add_argument("--flex", type=int, default=1, help="also time the flexible-block chain (64^3, block 6)")
     ap.add_argument("--e2e-decode-z", type=int, default=8, help="z-slices of the host-memory decode leg (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")

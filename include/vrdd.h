@@ -331,7 +331,8 @@ int vrdd_flex_prefix_spans(int x, int32_t* spans);
 
 /* Selects a kernel variant by name for A/B measurement: "decode_hist" -> "tma" | "ldg";
  * "decode_order" -> "chunked" | "interleaved"; "decode_fractal" -> "moments" | "moments768" | "moments_global" | "dense";
- * "raycast_tf" -> "texture" | "smem";
+ * "raycast_tf" -> "texture" | "smem"; "raycast_mode7" -> "texture" | "linear" (where queryMethod 7
+ * reads the block means from);
  * "raycast_unroll" -> "1" | "2" | "4" | "8" (ray-march steps whose fetches are in flight
  * together).  Results do not depend on the variant.  Unknown names return VRDD_ERR_INVALID. */
 int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);

@@ -325,6 +325,11 @@ def test_interpolated_mean_mode7(renderer, oracle, dims, img, rot):
     d = _lsb_diff(got, ref)
     assert d.max() <= 1, (int(d.max()), int((d > 1).sum()))
     assert (ref != 0).mean() > 0.1
+    r.count_samples(False)
+    # the block means read from the linear plane instead of the point-sampled 3-D array: the same texels
+    r.set_variant("raycast_mode7", "linear")
+    assert np.array_equal(_render(r, V, img[0], img[1], query_method=7), got)
+    r.set_variant("raycast_mode7", "texture")
     # modes 1..6 are untouched by the extra plane
     vol = oracle.decode_hist(hist)
     ref1, _ = oracle.render(vol, dims, view, image=img, query_method=1)

@@ -33,6 +33,8 @@ void free_volume(vrdd_decoded_volume& v) {
         if (v.brick[i]) cudaFree(v.brick[i]);
     }
     if (v.mean_raw) cudaFree(v.mean_raw);
+    if (v.mean_tex) cudaDestroyTextureObject(v.mean_tex);
+    if (v.mean_arr) cudaFreeArray(v.mean_arr);
     v = vrdd_decoded_volume();
 }
 
@@ -105,8 +107,23 @@ int ensure_volume_storage(vrdd_context* c, int source) {
             VRDD_CUDA(c, cudaMemsetAsync(v.brick[i], 0, sizeof(float) * brick_elems(c), c->stream));
         }
     }
-    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw)
+    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw) {
         VRDD_CUDA(c, cudaMalloc(&v.mean_raw, sizeof(float) * c->V));
+        // point-sampled, un-normalised coordinates: texel (x, y, z) is fetched at (x + .5, y + .5, z + .5)
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+        VRDD_CUDA(c, cudaMalloc3DArray(&v.mean_arr, &desc, make_cudaExtent(c->W, c->H, c->D), 0));
+        cudaResourceDesc rd;
+        std::memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = v.mean_arr;
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        VRDD_CUDA(c, cudaCreateTextureObject(&v.mean_tex, &rd, &td, nullptr));
+    }
     return VRDD_OK;
 }
 
@@ -417,6 +434,17 @@ int vrdd_decode(vrdd_handle h, int source, int z0, int nz) {
             return fail(c, VRDD_ERR_INVALID, "decode: fractal sub-slab must start on a 32-voxel boundary");
         rc = launch_decode_fractal(c, c->cb + 4 * local0, c->errs, c->err_off + local0 / VRDD_ERR_CHUNK, c->tmpl,
                                    c->num_templates, nvox, out, nullptr);
+    }
+    if (rc == VRDD_OK && orig && c->vol[source].mean_raw && c->vol[source].mean_arr) {
+        // the slab of block means, linear -> 3-D array (only when queryMethod 7 was asked for)
+        cudaMemcpy3DParms cp;
+        std::memset(&cp, 0, sizeof(cp));
+        cp.srcPtr = make_cudaPitchedPtr(c->vol[source].mean_raw + (size_t)z0 * slice, sizeof(float) * c->W, c->W, c->H);
+        cp.dstArray = c->vol[source].mean_arr;
+        cp.dstPos = make_cudaPos(0, 0, z0);
+        cp.extent = make_cudaExtent(c->W, c->H, nz);
+        cp.kind = cudaMemcpyDeviceToDevice;
+        VRDD_CUDA(c, cudaMemcpy3DAsync(&cp, c->stream));
     }
     if (rc == VRDD_OK) c->vol[source].decoded = true;
     return rc;
@@ -779,6 +807,10 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         else if (v == "moments_global") c->var_fractal = 2;
         else if (v == "moments768") c->var_fractal = 3;
         else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal is dense|moments|moments_global");
+    } else if (w == "raycast_mode7") {
+        if (v == "texture") c->var_mode7 = 0;
+        else if (v == "linear") c->var_mode7 = 1;
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_mode7 is texture|linear");
     } else if (w == "decode_order") {
         if (v == "interleaved") c->var_decode_order = 0;
         else if (v == "chunked") c->var_decode_order = 1;

@@ -179,6 +179,8 @@ struct vrdd_decoded_volume {
     cudaSurfaceObject_t surf[3] = {0, 0, 0};
     float* brick[3] = {nullptr, nullptr, nullptr};
     float* mean_raw = nullptr;       // un-normalised bin-centre mean per block, linear (queryMethod 7)
+    cudaArray_t mean_arr = nullptr;  // the same plane as a 3-D array read with point fetches: the march of
+    cudaTextureObject_t mean_tex = 0;   // queryMethod 7 wants the texture path's 3-D locality (side views)
     bool decoded = false;
 };
 
@@ -243,6 +245,7 @@ struct vrdd_context {
     int var_decode_order = 1;        // tma tile order: 0 interleaved over CTAs, 1 one contiguous run per CTA (TLB-friendly, default)
     int var_tf = 1;                  // 0 texture unit, 1 shared-memory table (default: frees the TEX pipe)
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
+    int var_mode7 = 0;               // 0 point-sampled 3-D array (default), 1 linear plane
     int var_fractal = 1;             // 0 dense (O(B) per voxel), 1 moments (O(NE) per voxel, tables in smem, default), 2 moments with global tables
 };
 

@@ -253,8 +253,31 @@ __device__ __forceinline__ int point_index_hw(float u, int n) {
     return (int)min(i, (unsigned long long)(n - 1));
 }
 
+// The march of mode 7 was bound by the conversion/special-function pipe (ncu: XU 63 %, everything else
+// < 30 %): 6 FRND, 6 F2I, 9 MUFU.RCP and 24 fp64<->fp32 conversions per sample.  The helpers below give the
+// same values without that pipe.
+// floor() for |v| < 2^22: adding 1.5 * 2^23 rounds to an integer, one compare fixes round-up.
+__device__ __forceinline__ float floor_small(float v) {
+    const float f = __fadd_rn(__fadd_rn(v, 12582912.0f), -12582912.0f);
+    return (f > v) ? __fadd_rn(f, -1.0f) : f;
+}
+// point_index_hw without F2I (0 <= sat(u) * 2^21 <= 2^21)
+__device__ __forceinline__ int point_index_fast(float u, int n) {
+    const float f = floor_small(__saturatef(u) * 2097152.0f);
+    const unsigned U = (unsigned)(__float_as_int(__fadd_rn(f, 12582912.0f)) - 0x4B400000);
+    const unsigned long long i = ((unsigned long long)U * (unsigned)n) >> 21;
+    return (int)min(i, (unsigned long long)(n - 1));
+}
+// k / n correctly rounded, for an integer-valued k in [-1, n + 1] and n <= 8192, from the correctly rounded
+// reciprocal and two FMAs (checked exhaustively against the division for every such k and n).
+__device__ __forceinline__ float div_small(float k, float n, float inv_n) {
+    const float q = __fmul_rn(k, inv_n);
+    return fmaf(fmaf(-q, n, k), inv_n, q);
+}
+
 struct Mode7Args {
     const float* mean_raw;
+    cudaTextureObject_t mean_tex;    // the same plane as a point-sampled 3-D array
     int W, H, D;
     const float4* tf_tab;
     int tf_n;
@@ -263,13 +286,31 @@ struct Mode7Args {
     float m[12];
     float density, brightness, t_offset, t_scale, tstep, thresh;
     int max_steps, clear_misses;
+    int use_tab, idx32;
     unsigned long long* samples;
 };
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) raycast_mode7_kernel(const Mode7Args A) {
+template <bool COUNT, int U>
+__global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Args A) {
     __shared__ float4 tf_s[VRDD_MAX_TF];
+    // Per axis and per cell boundary k in [-1, n+1]: {fl(k/n), index the texture unit's point rule gives it}.
+    // Both depend only on (k, n), so every block tabulates them once (A.use_tab: they fit in shared memory)
+    // and the march replaces 6 divisions and 6 index computations per sample by 6 shared-memory reads.
+    extern __shared__ float2 cell_tab[];
+    const float2* tabx = cell_tab;
+    const float2* taby = cell_tab + (A.W + 3);
+    const float2* tabz = taby + (A.H + 3);
     for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
+    if (A.use_tab) {
+        const int nx = A.W + 3, ny = A.H + 3, nz = A.D + 3;
+        for (int e = threadIdx.x; e < nx + ny + nz; e += kBlock) {
+            const int n = (e < nx) ? A.W : (e < nx + ny) ? A.H : A.D;
+            const int k = ((e < nx) ? e : (e < nx + ny) ? e - nx : e - nx - ny) - 1;
+            const float fn = (float)n;
+            const float v = div_small((float)k, fn, __fdiv_rn(1.0f, fn));
+            cell_tab[e] = make_float2(v, (float)point_index_fast(v, n) + 0.5f);      // texel centre
+        }
+    }
     __syncthreads();
     const int blocks_x = (A.iw + 15) / 16;
     const int by = blockIdx.x / blocks_x, bx = blockIdx.x - by * blocks_x;
@@ -300,44 +341,119 @@ __global__ void __launch_bounds__(kBlock) raycast_mode7_kernel(const Mode7Args A
                   pz = __fadd_rn(oz, __fmul_rn(dz, tnear));
             const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
             const float fW = (float)A.W, fH = (float)A.H, fD = (float)A.D;
-            float botx, boty, botz, topx, topy, topz, mean[8];
-            auto refresh = [&](float cx, float cy, float cz) {                       // :322-367, :398-463
-                botx = __fdiv_rn(floorf(__fmul_rn(cx, fW)), fW); topx = __fdiv_rn(ceilf(__fmul_rn(cx, fW)), fW);
-                boty = __fdiv_rn(floorf(__fmul_rn(cy, fH)), fH); topy = __fdiv_rn(ceilf(__fmul_rn(cy, fH)), fH);
-                botz = __fdiv_rn(floorf(__fmul_rn(cz, fD)), fD); topz = __fdiv_rn(ceilf(__fmul_rn(cz, fD)), fD);
-                const int x0 = point_index_hw(botx, A.W), x1 = point_index_hw(topx, A.W);
-                const int y0 = point_index_hw(boty, A.H), y1 = point_index_hw(topy, A.H);
-                const int z0 = point_index_hw(botz, A.D), z1 = point_index_hw(topz, A.D);
+            // The reference keeps the eight corner means of the current cell and refreshes them when a sample
+            // leaves it (:396).  Here the march runs in batches of U steps like raycast_kernel: for each of
+            // the next U samples the cell a refresh WOULD produce at that sample is computed and its eight
+            // loads are issued up front (8U loads in flight); the in-order pass below then either keeps the
+            // cached cell or adopts the sample's own, which is exactly the refresh the reference would do.
+            float botx = 0.f, boty = 0.f, botz = 0.f, topx = 0.f, topy = 0.f, topz = 0.f, mean[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const size_t idx = (size_t)((j & 1) ? x1 : x0) + (size_t)A.W * (((j & 2) ? y1 : y0) + (size_t)A.H * ((j & 4) ? z1 : z0));
-                    mean[j] = __ldg(A.mean_raw + idx);
+            for (int j = 0; j < 8; ++j) mean[j] = 0.f;
+            bool have = false;
+            int i = 0;
+            bool alive = A.max_steps > 0;
+            while (alive) {
+                float cu[U], cv[U], cw[U];
+                bool valid[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    valid[k] = alive;
+                    cu[k] = fmaf(px, 0.5f, 0.5f); cv[k] = fmaf(py, 0.5f, 0.5f); cw[k] = fmaf(pz, 0.5f, 0.5f);
+                    const float tn = __fadd_rn(t, A.tstep);
+                    const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
+                    if (cont) {
+                        t = tn; ++i;
+                        px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+                    }
+                    alive = cont;
                 }
-            };
-            refresh(fmaf(px, 0.5f, 0.5f), fmaf(py, 0.5f, 0.5f), fmaf(pz, 0.5f, 0.5f));
-            for (int i = 0; i < A.max_steps; ++i) {
-                const float cx = fmaf(px, 0.5f, 0.5f), cy = fmaf(py, 0.5f, 0.5f), cz = fmaf(pz, 0.5f, 0.5f);
-                if (cx < botx || cy < boty || cz < botz || cx > topx || cy > topy || cz > topz) refresh(cx, cy, cz);   // :396
-                const double xd = (double)__fdiv_rn(__fsub_rn(cx, botx), __fsub_rn(topx, botx));     // :466-471
-                const double yd = (double)__fdiv_rn(__fsub_rn(cy, boty), __fsub_rn(topy, boty));
-                const double zd = (double)__fdiv_rn(__fsub_rn(cz, botz), __fsub_rn(topz, botz));
-                const float m00 = (float)((double)mean[0] * (1.0 - xd) + (double)mean[1] * xd);       // :472-478
-                const float m10 = (float)((double)mean[2] * (1.0 - xd) + (double)mean[3] * xd);
-                const float m01 = (float)((double)mean[4] * (1.0 - xd) + (double)mean[5] * xd);
-                const float m11 = (float)((double)mean[6] * (1.0 - xd) + (double)mean[7] * xd);
-                const float m0 = (float)((double)m00 * (1.0 - yd) + (double)m10 * yd);
-                const float m1 = (float)((double)m01 * (1.0 - yd) + (double)m11 * yd);
-                const float s = (float)((double)m0 * (1.0 - zd) + (double)m1 * zd) * 50.0f;          // :479
-                if (COUNT) ++nsamp;
-                float4 col = tf_lookup_smem(tf_s, A.tf_n, (s - A.t_offset) * A.t_scale);
-                col.w *= A.density;
-                col.x *= col.w; col.y *= col.w; col.z *= col.w;
-                const float kk = 1.0f - sa;
-                sr += col.x * kk; sg += col.y * kk; sb += col.z * kk; sa += col.w * kk;
-                if (sa > A.thresh) break;
-                t = __fadd_rn(t, A.tstep);
-                if (t > tfar) break;
-                px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+                float sbx[U], sby[U], sbz[U], stx_[U], sty_[U], stz_[U], sm[U][8];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {                                       // :322-367, :398-463
+                    int x0, x1, y0, y1, z0, z1;
+                    float xf0, xf1, yf0, yf1, zf0, zf1;              // texel centres
+                    if (A.use_tab) {
+                        const float vx = __fmul_rn(cu[k], fW), vy = __fmul_rn(cv[k], fH), vz = __fmul_rn(cw[k], fD);
+                        const float fx = floor_small(vx), fy = floor_small(vy), fz = floor_small(vz);
+                        // k + 1 for floor and ceil, as integers (|f| < 2^22), clamped to the table
+                        const int ex0 = min(max(__float_as_int(__fadd_rn(fx, 12582912.0f)) - 0x4B400000 + 1, 0), A.W + 1);
+                        const int ey0 = min(max(__float_as_int(__fadd_rn(fy, 12582912.0f)) - 0x4B400000 + 1, 0), A.H + 1);
+                        const int ez0 = min(max(__float_as_int(__fadd_rn(fz, 12582912.0f)) - 0x4B400000 + 1, 0), A.D + 1);
+                        const float2 ax = tabx[ex0], bx_ = tabx[ex0 + (fx < vx)];
+                        const float2 ay = taby[ey0], by_ = taby[ey0 + (fy < vy)];
+                        const float2 az = tabz[ez0], bz_ = tabz[ez0 + (fz < vz)];
+                        sbx[k] = ax.x; stx_[k] = bx_.x; xf0 = ax.y; xf1 = bx_.y;
+                        sby[k] = ay.x; sty_[k] = by_.x; yf0 = ay.y; yf1 = by_.y;
+                        sbz[k] = az.x; stz_[k] = bz_.x; zf0 = az.y; zf1 = bz_.y;
+                        x0 = (int)xf0; x1 = (int)xf1; y0 = (int)yf0; y1 = (int)yf1; z0 = (int)zf0; z1 = (int)zf1;   // dead on the texture path
+                    } else {
+                        sbx[k] = __fdiv_rn(floorf(__fmul_rn(cu[k], fW)), fW); stx_[k] = __fdiv_rn(ceilf(__fmul_rn(cu[k], fW)), fW);
+                        sby[k] = __fdiv_rn(floorf(__fmul_rn(cv[k], fH)), fH); sty_[k] = __fdiv_rn(ceilf(__fmul_rn(cv[k], fH)), fH);
+                        sbz[k] = __fdiv_rn(floorf(__fmul_rn(cw[k], fD)), fD); stz_[k] = __fdiv_rn(ceilf(__fmul_rn(cw[k], fD)), fD);
+                        x0 = point_index_hw(sbx[k], A.W); x1 = point_index_hw(stx_[k], A.W);
+                        y0 = point_index_hw(sby[k], A.H); y1 = point_index_hw(sty_[k], A.H);
+                        z0 = point_index_hw(sbz[k], A.D); z1 = point_index_hw(stz_[k], A.D);
+                        xf0 = (float)x0 + 0.5f; xf1 = (float)x1 + 0.5f; yf0 = (float)y0 + 0.5f; yf1 = (float)y1 + 0.5f;
+                        zf0 = (float)z0 + 0.5f; zf1 = (float)z1 + 0.5f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sm[k][j] = 0.f;
+                    if (valid[k] && A.mean_tex) {
+                        sm[k][0] = tex3D<float>(A.mean_tex, xf0, yf0, zf0); sm[k][1] = tex3D<float>(A.mean_tex, xf1, yf0, zf0);
+                        sm[k][2] = tex3D<float>(A.mean_tex, xf0, yf1, zf0); sm[k][3] = tex3D<float>(A.mean_tex, xf1, yf1, zf0);
+                        sm[k][4] = tex3D<float>(A.mean_tex, xf0, yf0, zf1); sm[k][5] = tex3D<float>(A.mean_tex, xf1, yf0, zf1);
+                        sm[k][6] = tex3D<float>(A.mean_tex, xf0, yf1, zf1); sm[k][7] = tex3D<float>(A.mean_tex, xf1, yf1, zf1);
+                    } else if (valid[k]) {
+                        if (A.idx32) {                           // W*H*D < 2^31: 32-bit index arithmetic
+                            const unsigned zb0 = (unsigned)A.H * z0, zb1 = (unsigned)A.H * z1;
+                            const unsigned r00 = (unsigned)A.W * (y0 + zb0), r10 = (unsigned)A.W * (y1 + zb0);
+                            const unsigned r01 = (unsigned)A.W * (y0 + zb1), r11 = (unsigned)A.W * (y1 + zb1);
+                            sm[k][0] = __ldg(A.mean_raw + (r00 + x0)); sm[k][1] = __ldg(A.mean_raw + (r00 + x1));
+                            sm[k][2] = __ldg(A.mean_raw + (r10 + x0)); sm[k][3] = __ldg(A.mean_raw + (r10 + x1));
+                            sm[k][4] = __ldg(A.mean_raw + (r01 + x0)); sm[k][5] = __ldg(A.mean_raw + (r01 + x1));
+                            sm[k][6] = __ldg(A.mean_raw + (r11 + x0)); sm[k][7] = __ldg(A.mean_raw + (r11 + x1));
+                        } else {
+                            const size_t r00 = (size_t)A.W * (y0 + (size_t)A.H * z0), r10 = (size_t)A.W * (y1 + (size_t)A.H * z0);
+                            const size_t r01 = (size_t)A.W * (y0 + (size_t)A.H * z1), r11 = (size_t)A.W * (y1 + (size_t)A.H * z1);
+                            sm[k][0] = __ldg(A.mean_raw + r00 + x0); sm[k][1] = __ldg(A.mean_raw + r00 + x1);
+                            sm[k][2] = __ldg(A.mean_raw + r10 + x0); sm[k][3] = __ldg(A.mean_raw + r10 + x1);
+                            sm[k][4] = __ldg(A.mean_raw + r01 + x0); sm[k][5] = __ldg(A.mean_raw + r01 + x1);
+                            sm[k][6] = __ldg(A.mean_raw + r11 + x0); sm[k][7] = __ldg(A.mean_raw + r11 + x1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    if (!valid[k]) { alive = false; break; }
+                    const float cx = cu[k], cy = cv[k], cz = cw[k];
+                    if (!have || cx < botx || cy < boty || cz < botz || cx > topx || cy > topy || cz > topz) {   // :396
+                        botx = sbx[k]; boty = sby[k]; botz = sbz[k]; topx = stx_[k]; topy = sty_[k]; topz = stz_[k];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) mean[j] = sm[k][j];
+                        have = true;
+                    }
+                    // :466-479.  The reference blends in double (its literals promote); fp32 with the same
+                    // expression shape keeps the special values (0/0 -> NaN, x/0 -> inf, inf - inf -> NaN: the
+                    // degenerate-cell artefact) and differs by an ulp at most, far inside the +-1 LSB bar.
+                    const float xd = __fdividef(__fsub_rn(cx, botx), __fsub_rn(topx, botx));   // a * rcp(b): 0/0 and x/0
+                    const float yd = __fdividef(__fsub_rn(cy, boty), __fsub_rn(topy, boty));   // stay NaN and inf
+                    const float zd = __fdividef(__fsub_rn(cz, botz), __fsub_rn(topz, botz));
+                    const float wx = 1.0f - xd, wy = 1.0f - yd, wz = 1.0f - zd;
+                    const float m00 = fmaf(mean[1], xd, mean[0] * wx);
+                    const float m10 = fmaf(mean[3], xd, mean[2] * wx);
+                    const float m01 = fmaf(mean[5], xd, mean[4] * wx);
+                    const float m11 = fmaf(mean[7], xd, mean[6] * wx);
+                    const float m0 = fmaf(m10, yd, m00 * wy);
+                    const float m1 = fmaf(m11, yd, m01 * wy);
+                    const float s = fmaf(m1, zd, m0 * wz) * 50.0f;
+                    if (COUNT) ++nsamp;
+                    float4 col = tf_lookup_smem(tf_s, A.tf_n, (s - A.t_offset) * A.t_scale);
+                    col.w *= A.density;
+                    col.x *= col.w; col.y *= col.w; col.z *= col.w;
+                    const float kk = 1.0f - sa;
+                    sr += col.x * kk; sg += col.y * kk; sb += col.z * kk; sa += col.w * kk;
+                    if (sa > A.thresh) { alive = false; break; }
+                }
             }
             A.out[(size_t)y * A.iw + x] = pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);
         } else if (A.clear_misses) {
@@ -395,7 +511,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         if (iw <= 0 || ih <= 0 || !d_out) return fail(c, VRDD_ERR_INVALID, "render: bad image");
         if (part.parts != 1) return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod 7 does not take a tile partition");
         Mode7Args A;
-        A.mean_raw = v0.mean_raw; A.W = c->W; A.H = c->H; A.D = c->D;
+        A.mean_raw = v0.mean_raw; A.mean_tex = (c->var_mode7 == 0) ? v0.mean_tex : 0; A.W = c->W; A.H = c->H; A.D = c->D;
         A.tf_tab = reinterpret_cast<const float4*>(c->tf_dev); A.tf_n = c->tf_n;
         A.out = d_out; A.iw = iw; A.ih = ih;
         for (int i = 0; i < 12; ++i) A.m[i] = c->view[i];
@@ -403,8 +519,13 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         A.tstep = p.tstep; A.thresh = p.opacity_threshold; A.max_steps = p.max_steps; A.clear_misses = clear_misses;
         A.samples = c->d_samples;
         const int grid7 = ((iw + 15) / 16) * ((ih + 15) / 16);
-        if (c->count_samples && c->d_samples) raycast_mode7_kernel<true><<<grid7, kBlock, 0, c->stream>>>(A);
-        else raycast_mode7_kernel<false><<<grid7, kBlock, 0, c->stream>>>(A);
+        const size_t tab_bytes = sizeof(float2) * ((size_t)c->W + c->H + c->D + 9);
+        A.use_tab = (c->W <= 8192 && c->H <= 8192 && c->D <= 8192 && tab_bytes <= 64 * 1024) ? 1 : 0;   // div_small's checked range
+        A.idx32 = ((unsigned long long)c->W * c->H * c->D < (1ull << 31)) ? 1 : 0;
+        const size_t smem7 = A.use_tab ? tab_bytes : 0;
+        auto k7 = (c->count_samples && c->d_samples) ? raycast_mode7_kernel<true, 4> : raycast_mode7_kernel<false, 4>;
+        VRDD_CUDA(c, cudaFuncSetAttribute(k7, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        k7<<<grid7, kBlock, smem7, c->stream>>>(A);
         c->launches += 1;
         VRDD_CUDA(c, cudaGetLastError());
         return VRDD_OK;
