@@ -671,7 +671,7 @@ def run_sortlast(args):
     origin, size, lo, hi = D.brick_geometry(gdims, grid, q)
     r = V.Renderer(local)
     r.set_stream(torch.cuda.current_stream().cuda_stream)
-    r.set_sampler(V.SAMPLER_LINEAR if args.sortlast_layout == "linear" else V.SAMPLER_BRICKED)
+    r.set_sampler({"texture": V.SAMPLER_TEXTURE, "linear": V.SAMPLER_LINEAR, "bricked": V.SAMPLER_BRICKED}[args.sortlast_layout])
     r.set_volume(*size)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -823,7 +823,7 @@ def main():
     ap.add_argument("--image-sortlast", type=int, default=2048)
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "reduce"],
                     help="N > 1 tiles: p2p = kernels store tiles into rank 0's frame over NVLink; reduce = NCCL reduce")
-    ap.add_argument("--sortlast-layout", default="bricked", choices=["bricked", "linear"])
+    ap.add_argument("--sortlast-layout", default="texture", choices=["texture", "bricked", "linear"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

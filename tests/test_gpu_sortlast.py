@@ -65,7 +65,8 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
 @gpu
 @pytest.mark.parametrize("grid", [(2, 2, 2), (2, 1, 1), (3, 2, 1)])
 @pytest.mark.parametrize("rot", [(0.0, 0.0), (25.0, 40.0), (-35.0, 200.0), (90.0, 0.0)])
-def test_sortlast_matches_single_volume_and_oracle(oracle, grid, rot):
+@pytest.mark.parametrize("store", ["texture", "planes"])
+def test_sortlast_matches_single_volume_and_oracle(oracle, grid, rot, store):
     import vrdd_b200 as V
     import vrdd_b200.dist as D
     gdims, img, seed = (24, 20, 16), (96, 80), 31
@@ -76,7 +77,9 @@ def test_sortlast_matches_single_volume_and_oracle(oracle, grid, rot):
         params = V.default_render_params(query_method=1, **over)
         ref, ref_s = oracle.render(vol, gdims, view, image=img, density=params.density, brightness=params.brightness,
                                    opacity_threshold=params.opacity_threshold)
-        layout = V.SAMPLER_BRICKED if over else V.SAMPLER_LINEAR            # both plane layouts
+        # bricks as 3-D arrays filtered by the texture unit (the default), or as planes in global memory
+        # (both plane layouts) filtered by the integer restatement of the unit
+        layout = V.SAMPLER_TEXTURE if store == "texture" else (V.SAMPLER_BRICKED if over else V.SAMPLER_LINEAR)
         got, s = _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist, layout)
         d = _lsb(got, ref)
         assert d.max() <= 1, (grid, rot, over, int(d.max()), int((d > 1).sum()))

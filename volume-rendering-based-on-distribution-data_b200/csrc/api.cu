@@ -27,6 +27,7 @@ const float kDefaultTf[9][4] = {{0, 0, 0, 0}, {1, 0, 0, 1}, {1, 0.5f, 0, 1}, {1,
 void free_volume(vrdd_decoded_volume& v) {
     for (int i = 0; i < 3; ++i) {
         if (v.tex[i]) cudaDestroyTextureObject(v.tex[i]);
+        if (v.tex_un[i]) cudaDestroyTextureObject(v.tex_un[i]);
         if (v.surf[i]) cudaDestroySurfaceObject(v.surf[i]);
         if (v.arr[i]) cudaFreeArray(v.arr[i]);
         if (v.lin[i]) cudaFree(v.lin[i]);

@@ -176,6 +176,7 @@ struct vrdd_decoded_volume {
     float* lin[3] = {nullptr, nullptr, nullptr};
     cudaArray_t arr[3] = {nullptr, nullptr, nullptr};
     cudaTextureObject_t tex[3] = {0, 0, 0};
+    cudaTextureObject_t tex_un[3] = {0, 0, 0};   // same arrays, un-normalised coordinates (sort-last bricks)
     cudaSurfaceObject_t surf[3] = {0, 0, 0};
     float* brick[3] = {nullptr, nullptr, nullptr};
     float* mean_raw = nullptr;       // un-normalised bin-centre mean per block, linear (queryMethod 7)

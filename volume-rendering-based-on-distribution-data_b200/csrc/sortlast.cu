@@ -25,6 +25,8 @@
 // fp32 rounding in A_in and in the final sum: within +-1 LSB (tests/test_gpu_sortlast.py).
 #include "common.cuh"
 
+#include <cstring>
+
 namespace vrdd {
 
 namespace {
@@ -32,7 +34,8 @@ namespace {
 constexpr int kBlock = 256;
 
 struct BrickArgs {
-    const float* plane;             // this brick's plane of the sampled component
+    cudaTextureObject_t tex;        // this brick's plane as a 3-D array, linear filter, UN-normalised coordinates; or 0
+    const float* plane;             // ... or as a plane in global memory
     int bricked, bW, bH;            // layout of `plane`: 4x4x4-bricked (common.cuh) or linear, x fastest
     int sx, sy, sz;                 // local (stored) size in voxels, ghost included
     int gw, gh, gd;                 // global volume size
@@ -103,6 +106,22 @@ __device__ __forceinline__ float sample_brick(const BrickArgs& A, float u, float
     return acc * (1.0f / 256.0f);
 }
 
+// The same filter from the texture unit.  The fixed-point coordinate q = 256 * texel + fraction is formed
+// from the GLOBAL coordinate exactly as the unit would for the whole volume (split_hw), moved into the
+// brick, and handed over as the un-normalised coordinate (q + 128) / 256 — exact in fp32 — from which the
+// unit recovers q_local = floor(x * 256 + 0.5) - 128 (measured, tools/probe_texture4.py) and applies its
+// own weight split: one fetch instead of eight loads and forty integer operations.
+__device__ __forceinline__ float sample_brick_tex(const BrickArgs& A, float u, float v, float w) {
+    int i, j, k, a, b, c;
+    split_hw(u, A.gw << 8, i, a);
+    split_hw(v, A.gh << 8, j, b);
+    split_hw(w, A.gd << 8, k, c);
+    const float xl = (float)(((i - A.ox) << 8) + a + 128) * (1.0f / 256.0f);
+    const float yl = (float)(((j - A.oy) << 8) + b + 128) * (1.0f / 256.0f);
+    const float zl = (float)(((k - A.oz) << 8) + c + 128) * (1.0f / 256.0f);
+    return tex3D<float>(A.tex, xl, yl, zl);
+}
+
 __device__ __forceinline__ float4 tf_lookup(const float4* tab, int n, float u) {
     int i, a;
     split_hw(u, n << 8, i, a);
@@ -140,8 +159,9 @@ __device__ __forceinline__ RaySetup make_ray(const float* m, int x, int y, int i
 }
 
 // PASS 1: alpha of this brick's segment.  PASS 2: colour increments from the incoming alpha.
-template <int PASS, bool COUNT>
+template <int PASS, bool COUNT, bool TEX>
 __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A) {
+    constexpr int U = 4;
     __shared__ float4 tf_s[VRDD_MAX_TF];
     for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
     __syncthreads();
@@ -196,26 +216,48 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
                 if (t > R.tfar) { alive = false; break; }
                 px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
             }
-            for (; alive && i <= i_last; ++i) {
-                const float cu = fmaf(px, 0.5f, 0.5f), cv = fmaf(py, 0.5f, 0.5f), cw = fmaf(pz, 0.5f, 0.5f);
-                const bool mine = cu >= A.lo[0] && cu < A.hi[0] && cv >= A.lo[1] && cv < A.hi[1] &&
-                                  cw >= A.lo[2] && cw < A.hi[2];
-                if (mine) {
-                    const float s = sample_brick(A, cu, cv, cw);
-                    float4 col = tf_lookup(tf_s, A.tf_n, (s - A.t_offset) * A.t_scale);
-                    if (COUNT) ++nsamp;
-                    col.w *= A.density;
-                    const float kk = 1.0f - sa;
-                    if (PASS == 2) {
-                        col.x *= col.w; col.y *= col.w; col.z *= col.w;
-                        sr += col.x * kk; sg += col.y * kk; sb += col.z * kk;
+            alive = alive && i <= i_last;
+            // the march, in batches of U steps like raycast_kernel: geometry, U fetches in flight, then
+            // in-order compositing with the early exit
+            while (alive) {
+                float cu[U], cv[U], cw[U];
+                bool valid[U], mine[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    valid[k] = alive;
+                    cu[k] = fmaf(px, 0.5f, 0.5f); cv[k] = fmaf(py, 0.5f, 0.5f); cw[k] = fmaf(pz, 0.5f, 0.5f);
+                    mine[k] = alive && cu[k] >= A.lo[0] && cu[k] < A.hi[0] && cv[k] >= A.lo[1] && cv[k] < A.hi[1] &&
+                              cw[k] >= A.lo[2] && cw[k] < A.hi[2];
+                    const float tn = __fadd_rn(t, A.tstep);
+                    const bool cont = alive && !(tn > R.tfar) && (i + 1 <= i_last);
+                    if (cont) {
+                        t = tn; ++i;
+                        px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
                     }
-                    sa += col.w * kk;
-                    if (sa > A.thresh) break;                              // :698, on the GLOBAL alpha in pass 2
+                    alive = cont;
                 }
-                t = __fadd_rn(t, A.tstep);
-                if (t > R.tfar) break;
-                px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+                float s[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    s[k] = 0.f;
+                    if (mine[k]) s[k] = TEX ? sample_brick_tex(A, cu[k], cv[k], cw[k]) : sample_brick(A, cu[k], cv[k], cw[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    if (!valid[k]) { alive = false; break; }
+                    if (mine[k]) {
+                        float4 col = tf_lookup(tf_s, A.tf_n, (s[k] - A.t_offset) * A.t_scale);
+                        if (COUNT) ++nsamp;
+                        col.w *= A.density;
+                        const float kk = 1.0f - sa;
+                        if (PASS == 2) {
+                            col.x *= col.w; col.y *= col.w; col.z *= col.w;
+                            sr += col.x * kk; sg += col.y * kk; sb += col.z * kk;
+                        }
+                        sa += col.w * kk;
+                        if (sa > A.thresh) { alive = false; break; }               // :698, on the GLOBAL alpha in pass 2
+                    }
+                }
             }
         }
         if (PASS == 1) A.alpha_seg[pix] = sa;
@@ -268,12 +310,30 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
     if (qm < 1 || qm > 6) return fail(c, VRDD_ERR_UNSUPPORTED, "render_brick: queryMethod must be 1..6");
     const int source = (qm >= 4) ? VRDD_SRC_FRACTAL : VRDD_SRC_ORIGINAL, comp = (qm - 1) % 3;
     vrdd_decoded_volume& vol = c->vol[source];
-    if (!vol.decoded || !(vol.lin[comp] || vol.brick[comp]))
-        return fail(c, VRDD_ERR_INVALID, "render_brick: decode with VRDD_SAMPLER_BRICKED or VRDD_SAMPLER_LINEAR first");
+    if (!vol.decoded || !(vol.lin[comp] || vol.brick[comp] || vol.arr[comp]))
+        return fail(c, VRDD_ERR_INVALID, "render_brick: decode the brick first");
     if (iw <= 0 || ih <= 0 || !d_out || (pass == 2 && !d_alpha_in)) return fail(c, VRDD_ERR_INVALID, "render_brick: bad arguments");
     BrickArgs A;
+    A.tex = 0;
+    if (vol.arr[comp] && c->sampler == VRDD_SAMPLER_TEXTURE) {
+        if (!vol.tex_un[comp]) {                               // same array, un-normalised coordinates
+            cudaResourceDesc rd;
+            std::memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = vol.arr[comp];
+            cudaTextureDesc td;
+            std::memset(&td, 0, sizeof(td));
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModeLinear;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            VRDD_CUDA(c, cudaCreateTextureObject(&vol.tex_un[comp], &rd, &td, nullptr));
+        }
+        A.tex = vol.tex_un[comp];
+    }
     A.bricked = vol.brick[comp] != nullptr;
     A.plane = A.bricked ? vol.brick[comp] : vol.lin[comp];
+    if (!A.tex && !A.plane) return fail(c, VRDD_ERR_INVALID, "render_brick: no plane for the current sampler");
     A.bW = c->bW; A.bH = c->bH;
     A.sx = c->W; A.sy = c->H; A.sz = c->D;
     A.gw = b.gw; A.gh = b.gh; A.gd = b.gd; A.ox = b.ox; A.oy = b.oy; A.oz = b.oz;
@@ -287,9 +347,15 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
     A.samples = c->d_samples;
     const int grid = ((iw + 15) / 16) * ((ih + 15) / 16);
     const bool count = c->count_samples && pass == 2;
-    if (pass == 1) raycast_brick_kernel<1, false><<<grid, kBlock, 0, c->stream>>>(A);
-    else if (count) raycast_brick_kernel<2, true><<<grid, kBlock, 0, c->stream>>>(A);
-    else raycast_brick_kernel<2, false><<<grid, kBlock, 0, c->stream>>>(A);
+    if (A.tex) {
+        if (pass == 1) raycast_brick_kernel<1, false, true><<<grid, kBlock, 0, c->stream>>>(A);
+        else if (count) raycast_brick_kernel<2, true, true><<<grid, kBlock, 0, c->stream>>>(A);
+        else raycast_brick_kernel<2, false, true><<<grid, kBlock, 0, c->stream>>>(A);
+    } else {
+        if (pass == 1) raycast_brick_kernel<1, false, false><<<grid, kBlock, 0, c->stream>>>(A);
+        else if (count) raycast_brick_kernel<2, true, false><<<grid, kBlock, 0, c->stream>>>(A);
+        else raycast_brick_kernel<2, false, false><<<grid, kBlock, 0, c->stream>>>(A);
+    }
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;
