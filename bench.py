@@ -469,19 +469,87 @@ def run_ours(args):
         call = ("vrdd_set_view + vrdd_render_host_async per frame, vrdd_render_host_wait at the end (two frames in "
                 "flight: read-back of frame k overlaps rendering of frame k+1)")
     else:
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.warmup, args.warmup + args.steps):
-            render_step(k, params)
+        # N ranks fill ONE frame in shared host memory: full-width 64-row bands, round-robin over ranks; every rank
+        # renders its bands and copies them to their place in the frame over its own PCIe link, the copy of frame k
+        # overlapping the rendering of frame k+1.  A barrier per frame (behind a device-side fence on the previous
+        # frame's copy) marks frame k-1 complete on all ranks.
+        from multiprocessing import shared_memory
+        import numpy as np
+        nbytes = fw * fh * 4
+        shm, shared_ok = None, 1
+        try:
             if rank == 0:
-                src = V.as_torch(frames[k & 1], (fh, fw), typestr="<i4", device=dev) if p2p else red
-                host_img.copy_(src, non_blocking=True)
+                shm = shared_memory.SharedMemory(create=True, size=2 * nbytes)
+            box_ = [shm.name if rank == 0 else None]
+            dist.broadcast_object_list(box_, src=0)
+            if rank != 0:
+                shm = shared_memory.SharedMemory(name=box_[0])
+                try:                                              # rank 0 owns the segment: keep this process's
+                    from multiprocessing import resource_tracker  # tracker from unlinking it again at exit
+                    resource_tracker.unregister(shm._name, "shared_memory")
+                except Exception:
+                    pass
+            host2 = np.ndarray((2, fh, fw), dtype=np.int32, buffer=shm.buf)
+            if rank == 0:
+                host2[:] = 0
+            V.host_register(host2.ctypes.data, 2 * nbytes)
+        except Exception:
+            shared_ok = 0
+        t_ok = torch.tensor([shared_ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 1:
+            bands = V.TilePartition(fw, 64, rank, world)
+            band_counts = None
+            barrier()
+            for k in range(3):
+                r.set_view(orbit_view(V, k)); r.render_host_async(host2[k & 1], fw, fh, params, part=bands)
+            r.render_host_wait()
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(args.warmup, args.warmup + args.steps):
+                r.set_view(orbit_view(V, k))
+                r.render_host_async(host2[k & 1], fw, fh, params, part=bands)
+                r.render_host_fence(1)                            # stream waits for the copy of frame k-1 ...
+                dist.barrier()                                    # ... then all ranks: frame k-1 is complete in host memory
+            r.render_host_wait()
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            # the frame in shared host memory is, bit for bit, the one the device-side assembly gives
+            last = args.warmup + args.steps - 1
+            render_step(last, params)
             torch.cuda.synchronize()
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        call = ("vrdd_set_view + vrdd_render (my tiles, stored into rank 0's frame over NVLink) + barrier + "
-                "device->pinned-host frame copy") if p2p else \
-               "vrdd_set_view + vrdd_render (my tiles) + NCCL reduce to rank 0 + device->pinned-host frame copy"
+            barrier()
+            if rank == 0:
+                src = V.as_torch(frames[last & 1], (fh, fw), typestr="<i4", device=dev) if p2p else red
+                if not np.array_equal(src.cpu().numpy(), host2[last & 1]):
+                    raise SystemExit("bench.py: the frame assembled in shared host memory differs from the device-assembled frame")
+            call = ("vrdd_set_view + vrdd_render_host_async(part = my 64-row bands) per frame on every rank into one frame in "
+                    "shared, page-locked host memory (N PCIe links), vrdd_render_host_fence + barrier per frame, "
+                    "vrdd_render_host_wait at the end")
+            V.host_unregister(host2.ctypes.data)
+            del host2
+            shm.close()
+            barrier()
+            if rank == 0:
+                shm.unlink()
+        else:
+            if shm is not None:
+                shm.close()
+                if rank == 0:
+                    shm.unlink()
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(args.warmup, args.warmup + args.steps):
+                render_step(k, params)
+                if rank == 0:
+                    src = V.as_torch(frames[k & 1], (fh, fw), typestr="<i4", device=dev) if p2p else red
+                    host_img.copy_(src, non_blocking=True)
+                torch.cuda.synchronize()
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            call = ("vrdd_set_view + vrdd_render (my tiles, stored into rank 0's frame over NVLink) + barrier + "
+                    "device->pinned-host frame copy") if p2p else \
+                   "vrdd_set_view + vrdd_render (my tiles) + NCCL reduce to rank 0 + device->pinned-host frame copy"
     e2e = {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48 + 32,
            "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt, "call": call}
     if e2e_sync:

@@ -212,12 +212,22 @@ int vrdd_render_host(vrdd_handle h, uint32_t* h_output, int image_w, int image_h
 /* Pipelined form for a sequence of frames (an orbit, an animation): queues the frame and returns.
  * Frames alternate between two device buffers; a second stream copies frame k to h_output while
  * frame k+1 renders (the render of frame k+2 waits for that copy).  h_output should be page-locked
- * (cudaHostAlloc / cudaHostRegister) for the copy to overlap, and holds the image once
- * vrdd_render_host_wait has returned; use a different h_output for frames that are in flight
- * together.  The view and parameters are taken at the call, so they may change between calls. */
+ * (cudaHostAlloc / cudaHostRegister / vrdd_host_register) for the copy to overlap, and holds the
+ * image once vrdd_render_host_wait has returned; use a different h_output for frames that are in
+ * flight together.  The view and parameters are taken at the call, so they may change between calls.
+ * part == NULL: the whole frame.  Otherwise the partition must consist of full-width row bands
+ * (tile_w >= image_w): only this rank's bands are rendered and copied, into their place in the
+ * full-frame buffer h_output — with h_output in shared host memory, N ranks fill one frame over
+ * N PCIe links (bench.py --gpus N, e2e). */
 int vrdd_render_host_async(vrdd_handle h, uint32_t* h_output, int image_w, int image_h,
-                           const vrdd_render_params* params);
+                           const vrdd_render_params* params, const vrdd_tile_partition* part);
+/* Device-side fence: the handle's stream waits until the read-back queued `lag` (0 or 1) calls ago is
+ * done; the host does not block.  Put it in front of a per-frame barrier between ranks. */
+int vrdd_render_host_fence(vrdd_handle h, int lag);
 int vrdd_render_host_wait(vrdd_handle h);
+/* cudaHostRegister / cudaHostUnregister for caller memory (e.g. a frame in POSIX shared memory). */
+int vrdd_host_register(void* p, size_t bytes);
+int vrdd_host_unregister(void* p);
 /* Enables counting of transfer-function lookups (the S of Gsamples/s) in vrdd_render and
  * reads / resets the counter.  Reading synchronises. */
 int vrdd_count_samples(vrdd_handle h, int enable);

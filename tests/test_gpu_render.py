@@ -212,6 +212,33 @@ def test_render_host_async_pipeline_equals_synchronous_frames(renderer, golden):
     assert any(w_.any() for w_ in want)
 
 
+def test_render_host_async_row_bands_fill_one_host_frame(renderer, golden):
+    """vrdd_render_host_async with a partition of full-width row bands: each "rank" renders and copies only its
+    bands into the shared full-frame host buffer (registered with vrdd_host_register); together they give the
+    whole frame, also when the last band is ragged.  Other tile shapes are refused."""
+    import vrdd_b200 as V
+    r = renderer
+    _load_golden_volume(r, V, golden)
+    w, h = 96, 70                                                   # 70 rows: bands of 16 -> 4 full + one of 6
+    p = V.default_render_params(query_method=2)
+    r.set_view(golden["views"][1])
+    want = r.render_host(np.zeros((h, w), np.uint32), w, h, p).copy()
+    for parts in (2, 3, 5):
+        frame = np.full((h, w), 0xDEADBEEF, np.uint32)
+        V.host_register(frame.ctypes.data, frame.nbytes)
+        try:
+            for part in range(parts):
+                r.render_host_async(frame, w, h, p, part=V.TilePartition(w, 16, part, parts))
+                r.render_host_fence(1)
+            r.render_host_wait()
+            assert np.array_equal(frame, want), parts
+        finally:
+            V.host_unregister(frame.ctypes.data)
+    with pytest.raises(V.VrddError) as e:
+        r.render_host_async(np.zeros((h, w), np.uint32), w, h, p, part=V.TilePartition(64, 64, 0, 2))
+    assert e.value.code == V.ERR_UNSUPPORTED
+
+
 def test_custom_transfer_function(renderer, oracle, golden):
     import vrdd_b200 as V
     r = renderer

@@ -31,7 +31,7 @@ EXPORTS = [
     "vrdd_get_decoded_host", "vrdd_get_decoded_planes_device", "vrdd_keep_linear_planes", "vrdd_commit_planes",
     "vrdd_reconstruct_fractal_device", "vrdd_set_transfer_function", "vrdd_set_view",
     "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_render_host_async",
-    "vrdd_render_host_wait", "vrdd_count_samples",
+    "vrdd_render_host_wait", "vrdd_render_host_fence", "vrdd_host_register", "vrdd_host_unregister", "vrdd_count_samples",
     "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
     "vrdd_set_variant", "vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function",
     "vrdd_debug_sample_texture_point", "vrdd_debug_sample_texture_unnorm", "vrdd_enable_interpolated_mean",
@@ -139,8 +139,11 @@ def lib():
             "vrdd_default_render_params": (None, [C.POINTER(RenderParams)]),
             "vrdd_render": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(TilePartition), i32]),
             "vrdd_render_host": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams)]),
-            "vrdd_render_host_async": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams)]),
+            "vrdd_render_host_async": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(TilePartition)]),
             "vrdd_render_host_wait": (i32, [vp]),
+            "vrdd_render_host_fence": (i32, [vp, i32]),
+            "vrdd_host_register": (i32, [vp, C.c_size_t]),
+            "vrdd_host_unregister": (i32, [vp]),
             "vrdd_count_samples": (i32, [vp, i32]),
             "vrdd_get_sample_count": (i32, [vp, C.POINTER(C.c_int64), i32]),
             "vrdd_view_matrix": (None, [f32, f32, f32, f32, f32, vp]),
@@ -266,6 +269,17 @@ def pack_fractal_errors(codebook, errors_dense, bins=32):
     return ent[:int(tot.value)], off
 
 
+def host_register(ptr, nbytes):
+    """vrdd_host_register: page-lock caller memory (address or array) for asynchronous copies."""
+    rc = lib().vrdd_host_register(_ptr(ptr), nbytes)
+    if rc != 0:
+        raise VrddError(rc, "vrdd_host_register failed")
+
+
+def host_unregister(ptr):
+    lib().vrdd_host_unregister(_ptr(ptr))
+
+
 class Renderer:
     """One vrdd handle.  Methods map 1:1 onto the vrdd_* C functions."""
 
@@ -367,9 +381,13 @@ class Renderer:
                                         C.byref(params) if params is not None else None))
         return h_output
 
-    def render_host_async(self, h_output, w, h, params=None):
+    def render_host_async(self, h_output, w, h, params=None, part=None):
         self._ck(lib().vrdd_render_host_async(self._h, _ptr(h_output), w, h,
-                                              C.byref(params) if params is not None else None))
+                                              C.byref(params) if params is not None else None,
+                                              C.byref(part) if part is not None else None))
+
+    def render_host_fence(self, lag=1):
+        self._ck(lib().vrdd_render_host_fence(self._h, lag))
 
     def render_host_wait(self):
         self._ck(lib().vrdd_render_host_wait(self._h))

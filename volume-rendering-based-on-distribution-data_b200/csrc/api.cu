@@ -614,10 +614,16 @@ int vrdd_render_host(vrdd_handle h, uint32_t* h_output, int image_w, int image_h
 }
 
 // Pipelined read-back: frame k is copied to the host by a second stream while frame k+1 renders.
+// With a partition of full-width row bands (tile_w >= image_w) only this rank's bands are rendered and only
+// they are copied, into their place in the caller's full-frame host buffer: N ranks fill one frame in shared
+// host memory over N PCIe links.
 int vrdd_render_host_async(vrdd_handle h, uint32_t* h_output, int image_w, int image_h,
-                           const vrdd_render_params* params) {
+                           const vrdd_render_params* params, const vrdd_tile_partition* part) {
     CHECK_HANDLE(h);
     if (!h_output || image_w <= 0 || image_h <= 0) return fail(c, VRDD_ERR_INVALID, "render_host_async: bad image");
+    const bool banded = part && part->parts > 1;
+    if (banded && (part->tile_w < image_w || part->tile_h < 1 || part->part < 0 || part->part >= part->parts))
+        return fail(c, VRDD_ERR_UNSUPPORTED, "render_host_async: a partition must consist of full-width row bands");
     const size_t bytes = sizeof(uint32_t) * (size_t)image_w * image_h;
     if (!c->copy_stream) {
         VRDD_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -639,13 +645,44 @@ int vrdd_render_host_async(vrdd_handle h, uint32_t* h_output, int image_w, int i
     }
     const int slot = (int)(c->pslot & 1u);
     if (c->pslot >= 2) VRDD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));   // frame k-2 has left this slot
-    const int rc = vrdd_render(h, c->pframe[slot], image_w, image_h, params, nullptr, 1);
+    const int rc = vrdd_render(h, c->pframe[slot], image_w, image_h, params, banded ? part : nullptr, 1);
     if (rc != VRDD_OK) return rc;
     VRDD_CUDA(c, cudaEventRecord(c->ev_rendered[slot], c->stream));
     VRDD_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[slot], 0));
-    VRDD_CUDA(c, cudaMemcpyAsync(h_output, c->pframe[slot], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (!banded) {
+        VRDD_CUDA(c, cudaMemcpyAsync(h_output, c->pframe[slot], bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    } else {
+        // bands part, part + parts, ...: the complete ones are one strided copy, a ragged last band a second
+        const size_t row = sizeof(uint32_t) * (size_t)image_w, band = row * part->tile_h;
+        const int nbands = (image_h + part->tile_h - 1) / part->tile_h;
+        const int nfull = image_h / part->tile_h;                      // bands [0, nfull) are complete
+        const int mine_full = (nfull > part->part) ? (nfull - part->part + part->parts - 1) / part->parts : 0;
+        const size_t first = band * part->part;
+        if (mine_full > 0)
+            VRDD_CUDA(c, cudaMemcpy2DAsync(reinterpret_cast<char*>(h_output) + first, band * part->parts,
+                                           reinterpret_cast<const char*>(c->pframe[slot]) + first, band * part->parts, band,
+                                           mine_full, cudaMemcpyDeviceToHost, c->copy_stream));
+        if (nbands > nfull && (nfull % part->parts) == part->part) {
+            const size_t off = band * nfull;
+            VRDD_CUDA(c, cudaMemcpyAsync(reinterpret_cast<char*>(h_output) + off,
+                                         reinterpret_cast<const char*>(c->pframe[slot]) + off, bytes - off,
+                                         cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+    }
     VRDD_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
     c->pslot += 1;
+    return VRDD_OK;
+}
+
+// The handle's stream waits (on the device, the host does not block) until the read-back of the frame queued
+// `lag` calls ago has finished: lag 0 = the last frame, 1 = the one before (what a per-frame barrier between
+// ranks should wait for, so that the last frame's copy still overlaps the next render).
+int vrdd_render_host_fence(vrdd_handle h, int lag) {
+    CHECK_HANDLE(h);
+    if (lag < 0 || lag > 1) return fail(c, VRDD_ERR_INVALID, "render_host_fence: lag is 0 or 1");
+    if (!c->copy_stream || c->pslot <= (unsigned)lag) return VRDD_OK;
+    const int slot = (int)((c->pslot - 1u - (unsigned)lag) & 1u);
+    VRDD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
     return VRDD_OK;
 }
 
@@ -654,6 +691,18 @@ int vrdd_render_host_wait(vrdd_handle h) {
     if (c->copy_stream) VRDD_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
     return VRDD_OK;
+}
+
+// Page-locks caller memory (for instance a frame in POSIX shared memory that several ranks fill) so that
+// copies into it are asynchronous and run at full PCIe rate.
+int vrdd_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return VRDD_ERR_INVALID;
+    return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? VRDD_OK : VRDD_ERR_CUDA;
+}
+
+int vrdd_host_unregister(void* p) {
+    if (!p) return VRDD_ERR_INVALID;
+    return cudaHostUnregister(p) == cudaSuccess ? VRDD_OK : VRDD_ERR_CUDA;
 }
 
 int vrdd_count_samples(vrdd_handle h, int enable) {
