@@ -490,8 +490,9 @@ def run_ours(args):
                 except Exception:
                     pass
             host2 = np.ndarray((2, fh, fw), dtype=np.int32, buffer=shm.buf)
-            if rank == 0:
-                host2[:] = 0
+            for y0 in range(64 * rank, fh, 64 * world):          # first touch by the rank that fills the band: its pages
+                host2[:, y0:y0 + 64] = 0                          # land on that rank's NUMA node
+            barrier()
             V.host_register(host2.ctypes.data, 2 * nbytes)
         except Exception:
             shared_ok = 0
@@ -509,8 +510,9 @@ def run_ours(args):
             for k in range(args.warmup, args.warmup + args.steps):
                 r.set_view(orbit_view(V, k))
                 r.render_host_async(host2[k & 1], fw, fh, params, part=bands)
-                r.render_host_fence(1)                            # stream waits for the copy of frame k-1 ...
-                dist.barrier()                                    # ... then all ranks: frame k-1 is complete in host memory
+                if args.e2e_sync_every and (k % args.e2e_sync_every) == 0:
+                    r.render_host_fence(1)                        # stream waits for the copy of frame k-1 ...
+                    dist.barrier()                                # ... then all ranks: frame k-1 is complete in host memory
             r.render_host_wait()
             barrier()
             dt = max_over_ranks(time.perf_counter() - t0)
@@ -881,6 +883,8 @@ def main():
     ap.add_argument("--unroll", type=int, default=0, choices=[0, 1, 2, 4, 8])
     ap.add_argument("--fractal", type=int, default=1)
     ap.add_argument("--matched", type=int, default=1)
+    ap.add_argument("--e2e-sync-every", type=int, default=1,
+                    help="N > 1 end-to-end path: fence + barrier between ranks every K frames (0: only at the end)")
     ap.add_argument("--mode7", type=int, default=1, help="also time queryMethod 7 on the same volume and views")
     ap.add_argument("--flex", type=int, default=1, help="also time the flexible-block chain (64^3, block 6)")
     ap.add_argument("--e2e-decode-z", type=int, default=8, help="z-slices of the host-memory decode leg (0 = skip)")
