@@ -476,12 +476,17 @@ def run_ours(args):
         from multiprocessing import shared_memory
         import numpy as np
         nbytes = fw * fh * 4
-        shm, shared_ok = None, 1
-        try:
-            if rank == 0:
+        shm, host2, shared_ok = None, None, 1
+        if rank == 0:
+            try:
                 shm = shared_memory.SharedMemory(create=True, size=2 * nbytes)
-            box_ = [shm.name if rank == 0 else None]
-            dist.broadcast_object_list(box_, src=0)
+            except Exception:
+                shm = None
+        box_ = [shm.name if shm is not None else None]
+        dist.broadcast_object_list(box_, src=0)                   # every rank takes part, whatever happened above
+        try:
+            if box_[0] is None:
+                raise RuntimeError("no shared memory segment")
             if rank != 0:
                 shm = shared_memory.SharedMemory(name=box_[0])
                 try:                                              # rank 0 owns the segment: keep this process's
@@ -492,7 +497,6 @@ def run_ours(args):
             host2 = np.ndarray((2, fh, fw), dtype=np.int32, buffer=shm.buf)
             for y0 in range(64 * rank, fh, 64 * world):          # first touch by the rank that fills the band: its pages
                 host2[:, y0:y0 + 64] = 0                          # land on that rank's NUMA node
-            barrier()
             V.host_register(host2.ctypes.data, 2 * nbytes)
         except Exception:
             shared_ok = 0
@@ -535,6 +539,7 @@ def run_ours(args):
             if rank == 0:
                 shm.unlink()
         else:
+            host2 = None
             if shm is not None:
                 shm.close()
                 if rank == 0:
