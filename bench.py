@@ -587,6 +587,48 @@ def run_ours(args):
         r2.close()
         del h_hist
 
+    # ---- BASELINE.json configs[1]: 512^3 volume, 1024x1024 frames, the 64-view orbit, one GPU ----------------------
+    cfg1 = None
+    if world == 1 and args.config1 and args.volume != 512:
+        try:
+            r5 = V.Renderer(local)
+            r5.set_stream(torch.cuda.current_stream().cuda_stream)
+            r5.set_volume(512, 512, 512)
+            hb = torch.empty(512 ** 3 * 32, dtype=torch.float32, device=dev)
+            r5.synth_histograms_device(args.seed, 0, 512, hb)
+            r5.set_histograms_device(hb, 0, 512)
+            r5.decode(V.SRC_ORIGINAL)
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record(); r5.decode(V.SRC_ORIGINAL); e1.record()
+            torch.cuda.synchronize()
+            d_ms = e0.elapsed_time(e1)
+            del hb
+            torch.cuda.empty_cache()
+            img5 = torch.zeros(1024, 1024, dtype=torch.int32, device=dev)
+            p5 = V.default_render_params(query_method=1)
+            r5.count_samples(True)
+            c5 = []
+            for k in range(ORBIT_VIEWS):
+                r5.set_view(orbit_view(V, k)); r5.render(img5, 1024, 1024, p5, clear_misses=True); c5.append(r5.get_sample_count())
+            r5.count_samples(False)
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for k in range(ORBIT_VIEWS):
+                r5.set_view(orbit_view(V, k)); r5.render(img5, 1024, 1024, p5, clear_misses=True)
+            e1.record()
+            torch.cuda.synchronize()
+            o_ms = e0.elapsed_time(e1)
+            cfg1 = {"workload": "512^3 volume decoded once, 1024x1024 frames, 64-view orbit, reference constants",
+                    "decode_ms": d_ms, "decode_frac_of_hbm_peak": 512 ** 3 * HIST_BYTES_PER_VOXEL / (d_ms * 1e-3) / 1e9 / hbm_peak,
+                    "gsamples_per_s": sum(c5) / (o_ms * 1e-3) / 1e9, "fps": ORBIT_VIEWS / (o_ms * 1e-3),
+                    "ms_per_view": o_ms / ORBIT_VIEWS, "samples_per_frame": sum(c5) / ORBIT_VIEWS}
+            r5.close()
+            del img5
+        except Exception as exc:
+            cfg1 = {"error": repr(exc)}
+
     # ---- queryMethod 7 (interpolated block means, point-sampled cells) on the same volume and views -------
     mode7 = None
     if world == 1 and args.mode7:
@@ -702,6 +744,8 @@ def run_ours(args):
                 "clocks": clk}
         if matched:
             line["raycast_resolution_matched"] = matched
+        if cfg1:
+            line["config_512"] = cfg1
         if mode7:
             line["query_method_7"] = mode7
         if flex:
@@ -890,6 +934,7 @@ def main():
     ap.add_argument("--matched", type=int, default=1)
     ap.add_argument("--e2e-sync-every", type=int, default=1,
                     help="N > 1 end-to-end path: fence + barrier between ranks every K frames (0: only at the end)")
+    ap.add_argument("--config1", type=int, default=1, help="also time BASELINE.json configs[1] (512^3 volume, 64-view orbit)")
     ap.add_argument("--mode7", type=int, default=1, help="also time queryMethod 7 on the same volume and views")
     ap.add_argument("--flex", type=int, default=1, help="also time the flexible-block chain (64^3, block 6)")
     ap.add_argument("--e2e-decode-z", type=int, default=8, help="z-slices of the host-memory decode leg (0 = skip)")

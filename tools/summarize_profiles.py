@@ -48,7 +48,7 @@ if os.path.exists(ll):
         a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += float(r["Metric Value"]) / 1e6
     tot = sum(a[1] for a in agg.values())
     lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold-cache and serialised: compare shares)",
-              "", "Command: `python bench.py --steps 16 --warmup 3 --decode-reps 1 --no-cpu --e2e-decode-z 0`", "",
+              "", "Command: `python bench.py --steps 16 --warmup 3 --decode-reps 1 --no-cpu --e2e-decode-z 0 --config1 0 --mode7 0`", "",
               "| kernel | launches | total ms | avg ms | share |", "|---|---:|---:|---:|---:|"]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"| `{k[:70]}` | {n} | {t:.3f} | {t / n:.4f} | {t / tot * 100:.1f}% |")
