@@ -124,10 +124,20 @@ def orbit_view(V, k):
 # CPU legs (oracle).  bench.py may execute oracle/ only here: as the timed CPU baseline.
 # ---------------------------------------------------------------------------------------------
 
+def host_threads():
+    """Threads the CPU legs use: every core this process may run on.  Set explicitly because torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would silently make the reference arm single-threaded."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_decode_baseline(seed):
     """Raw-histogram decode on the host cores: a 256x256x64 slab of the same synthetic volume."""
     from oracle.vrdd_oracle import Oracle
     o = Oracle(fast=True)
+    o.set_num_threads(host_threads())
     hist = o.synth_histograms(seed, (256, 256, 256), z0=96, nz=64)
     best = 1e30
     for _ in range(3):
@@ -147,6 +157,7 @@ class CpuRaycaster:
         import numpy as np
         from oracle.vrdd_oracle import Oracle
         self.o = Oracle(fast=True)
+        self.o.set_num_threads(host_threads())
         self.dims = (256, 256, 256)
         self.img = img
         vol = np.empty((256 ** 3, 4), np.float32)
