@@ -319,6 +319,7 @@ def run_ours(args):
             fr_ms += e0.elapsed_time(e1) / reps
             fr_bytes += nz * slice_vox * (16 + 12) + tot * 8      # codebook + planes + 8 B per error
         fr_kernel = {"moments": "decode_fractal_moments_smem_kernel", "moments768": "decode_fractal_moments_smem_kernel",
+                     "moments2": "decode_fractal_moments2_kernel", "moments2r": "decode_fractal_moments2_kernel",
                      "moments_global": "decode_fractal_moments_kernel", "dense": "decode_fractal_dense_kernel"}
         decode["fractal"] = {"kernel": fr_kernel.get(args.fractal_variant, args.fractal_variant), "ms": fr_ms,
                              "gbs": fr_bytes / (fr_ms * 1e-3) / 1e9,
@@ -937,7 +938,8 @@ def main():
     ap.add_argument("--slab-z", type=int, default=256, help="z-slices decoded per launch (256 -> 34 GB of histograms)")
     ap.add_argument("--decode-reps", type=int, default=3)
     ap.add_argument("--decode-variant", default="tma", choices=["tma", "ldg"])
-    ap.add_argument("--fractal-variant", default="moments", choices=["moments", "moments768", "moments_global", "dense"])
+    ap.add_argument("--fractal-variant", default="moments2",
+                    choices=["moments2", "moments2r", "moments", "moments768", "moments_global", "dense"])
     ap.add_argument("--sampler", default="texture", choices=["texture", "bricked"])
     ap.add_argument("--tf", default=None, choices=[None, "texture", "smem"])
     ap.add_argument("--unroll", type=int, default=0, choices=[0, 1, 2, 4, 8])

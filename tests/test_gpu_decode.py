@@ -113,7 +113,7 @@ def _from_device_ptr(ptr, n):
     return V.as_torch(ptr, (n,)).cpu().numpy()
 
 
-@pytest.mark.parametrize("variant", ["moments", "moments_global", "dense"])
+@pytest.mark.parametrize("variant", ["moments", "moments2", "moments2r", "moments2b", "moments2br", "moments_global", "dense"])
 def test_fractal_decode_matches_golden_and_is_bit_exact_in_its_integer_part(renderer, golden, variant):
     """The golden codes include shift == 32, flip + shift, NE == 0, a clamp to zero and a bin hit
     three times (the moments variant must fall back to the ordered dense route there)."""
@@ -134,7 +134,7 @@ def test_fractal_decode_matches_golden_and_is_bit_exact_in_its_integer_part(rend
     np.testing.assert_allclose(got, golden["decoded_fractal"], rtol=RTOL, atol=ATOL)
 
 
-@pytest.mark.parametrize("variant", ["moments", "moments768", "moments_global", "dense"])
+@pytest.mark.parametrize("variant", ["moments", "moments2", "moments2r", "moments2b", "moments2br", "moments768", "moments_global", "dense"])
 @pytest.mark.parametrize("dims,T,max_ne", [((1, 1, 1), 3, 8), ((30, 9, 2), 622, 8), ((50, 50, 10), 622, 8),
                                             ((64, 32, 5), 100, 32), ((16, 16, 4), 1500, 0), ((96, 64, 40), 622, 8)])
 def test_fractal_decode_matches_oracle(renderer, oracle, dims, T, max_ne, variant):

@@ -65,7 +65,7 @@ def sweep_fractal(edge, reps=3):
         nbytes += nvs * 28 + tot * 8
     r.close()
     n = edge ** 3
-    return {"source": "fractal codes", "kernel": "decode_fractal_moments_smem_kernel", "edge": edge, "layout": "texture",
+    return {"source": "fractal codes", "kernel": "decode_fractal_moments2_kernel", "edge": edge, "layout": "texture",
             "ms": ms, "gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / PEAK, "gvoxels_per_s": n / ms / 1e6,
             "bytes_per_voxel": nbytes / n}
 

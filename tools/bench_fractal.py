@@ -25,7 +25,10 @@ for sink in ("tex", "linear"):
         if sink == "linear":
             r.set_sampler(V.SAMPLER_LINEAR)
         r.set_volume(edge, edge, nz)
-        r.set_variant("decode_fractal", variant)
+        name, _, pf = variant.partition("+pf")
+        r.set_variant("decode_fractal", name)
+        if pf:
+            r.set_variant("decode_fractal_prefetch", pf)
         tot = r.synth_fractal_device(1234, T, max_ne, 0, nz, cb, er, off, tm)
         r.set_fractal_device(cb, er, off, tm, T, 0, nz)
         r.decode(V.SRC_FRACTAL); torch.cuda.synchronize()

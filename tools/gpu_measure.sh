@@ -21,7 +21,7 @@ echo "== ncu DRAM traffic of every view of the orbit (the 64 timed ray-cast laun
 ORB="python bench.py --steps 64 --warmup 5 --decode-reps 1 --no-cpu --e2e-decode-z 0 --config1 0 --mode7 0"
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:raycast_kernel -s 69 -c 64 --csv --log-file $out/raycast_orbit_$tag.csv $ORB > $out/ncu_orbit_$tag.log 2>&1
 echo "rc=$?"
-for spec in "decode_hist_tma_kernel 1 1 decode_hist" "raycast_kernel 30 2 raycast" "decode_fractal_moments_smem_kernel 1 1 decode_fractal_moments"; do
+for spec in "decode_hist_tma_kernel 1 1 decode_hist" "raycast_kernel 30 2 raycast" "decode_fractal_moments2_kernel 1 1 decode_fractal_moments"; do
   set -- $spec
   echo "== ncu full: $1"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$1 -s $2 -c $3 -f -o $out/prof_$4_$tag $CMD > $out/ncu_$4_$tag.log 2>&1; echo "rc=$?"

@@ -128,7 +128,7 @@ if os.path.exists(bench) and "decode_hist" in traffic:
             tj["raycast_kernel"] = dict(orbit, source=f"profiles/raycast_orbit_{tag}.csv",
                                         full_capture_side_view=dict(traffic["raycast"], source=f"profiles/ncu_raw_raycast_{tag}.csv"))
     if "decode_fractal_moments" in traffic:
-        tj["decode_fractal_moments_smem_kernel"] = dict(traffic["decode_fractal_moments"],
+        tj["decode_fractal_moments2_kernel"] = dict(traffic["decode_fractal_moments"],
                                                    source=f"profiles/ncu_raw_decode_fractal_moments_{tag}.csv")
     json.dump(tj, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     subprocess.run(["cp", bench, os.path.join(P, f"bench_{tag}.json")])

@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -431,8 +432,10 @@ int vrdd_decode(vrdd_handle h, int source, int z0, int nz) {
     if (orig) {
         rc = launch_decode_hist(c, c->hist + local0 * c->B, nvox, out);
     } else {
-        if (local0 % VRDD_ERR_CHUNK != 0)
-            return fail(c, VRDD_ERR_INVALID, "decode: fractal sub-slab must start on a 32-voxel boundary");
+        // the error table is grouped per chunk of 32 voxels (round-major inside a chunk), so a sub-slab has to be
+        // made of whole chunks; only the very end of the attached input may fall inside one
+        if (local0 % VRDD_ERR_CHUNK != 0 || ((local0 + nvox) % VRDD_ERR_CHUNK != 0 && z0 + nz != az0 + anz))
+            return fail(c, VRDD_ERR_INVALID, "decode: fractal sub-slab must start and end on a 32-voxel boundary");
         rc = launch_decode_fractal(c, c->cb + 4 * local0, c->errs, c->err_off + local0 / VRDD_ERR_CHUNK, c->tmpl,
                                    c->num_templates, nvox, out, nullptr);
     }
@@ -856,7 +859,15 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         else if (v == "moments") c->var_fractal = 1;
         else if (v == "moments_global") c->var_fractal = 2;
         else if (v == "moments768") c->var_fractal = 3;
+        else if (v == "moments2") c->var_fractal = 4;          // scan + predicated rows
+        else if (v == "moments2r") c->var_fractal = 5;         // ... + float rows, g(old) recomputed
+        else if (v == "moments2b") c->var_fractal = 6;         // ballots + predicated rows
+        else if (v == "moments2br") c->var_fractal = 7;
         else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal is dense|moments|moments_global");
+    } else if (w == "decode_fractal_prefetch") {
+        const int n = std::atoi(variant);
+        if (n < 0 || n > 32) return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal_prefetch is 0..32 lines");
+        c->var_fractal_pf = n;
     } else if (w == "raycast_mode7") {
         if (v == "texture") c->var_mode7 = 0;
         else if (v == "linear") c->var_mode7 = 1;

@@ -247,7 +247,9 @@ struct vrdd_context {
     int var_tf = 1;                  // 0 texture unit, 1 shared-memory table (default: frees the TEX pipe)
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
     int var_mode7 = 0;               // 0 point-sampled 3-D array (default), 1 linear plane
-    int var_fractal = 1;             // 0 dense (O(B) per voxel), 1 moments (O(NE) per voxel, tables in smem, default), 2 moments with global tables
+    int var_fractal_pf = 12;         // moments2: 128-byte lines of the next tile's errors prefetched into L2 (0..32)
+    int var_fractal = 4;             // 0 dense (O(B) per voxel); moments (O(NE) per voxel): 1 r1f kernel, 2 tables in global memory,
+                                     // 3 768 threads, 4 moments2 (default), 5 moments2r, 6 moments2b, 7 moments2br (decode_fractal.cu)
 };
 
 namespace vrdd {

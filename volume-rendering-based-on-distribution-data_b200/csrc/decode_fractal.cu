@@ -406,6 +406,261 @@ decode_fractal_moments_smem_kernel(const int4* __restrict__ codebook, const ErrE
     }
 }
 
+// ---- second generation of the shared-memory moments kernel ----------------------------------
+// Same algorithm and the same numbers per voxel as moments_voxel; what changes is how the work is issued.
+// The r1f capture (profiles/summary_r1f.md) shows the kernel at 75 % issue-slot and 89 % LSU-data-pipe
+// utilisation, 170 of its 449 instructions per 32 voxels in the address phase of the eight rounds and 44 of
+// its 60 shared-memory wavefronts in bank conflicts.  Hence:
+//  * SCAN: a lane's slot in round k is (entries of rounds < k) + (lanes below it with NE > k).  The eight
+//    indicator bits (NE > k) are packed one per byte into two words and ONE warp scan (5 steps, 10 SHFL)
+//    yields the eight ranks together; the round offsets are the byte-wise prefix sums of the totals, a
+//    multiply by 0x01010100.  Replaces 8 ballots + 16 POPC (quarter-rate pipe) + 64-bit address chains.
+//  * row reads are predicated on k < NE: an absent entry used to read a (valid, random) slot, taking part
+//    in the bank conflicts of the round; now it contributes {0, 0}, which still leaves every increment
+//    exactly zero (new = max(0 + 0, 0) = old, g(0) - 0 = 0).
+//  * RECOMP: rows hold only the template values (float, the reference's own table, 80 KB at T = 622);
+//    g(old) = old*log2(old) is recomputed with the function the table was built with (identical bits), one
+//    MUFU more per round against a 32-bit instead of a 64-bit shared load (half the wavefronts).
+//  * a bin hit twice is detected once per voxel, popc(touched) != NE, not per round.
+//  * rounds are skipped in pairs (warp-uniform), absent entries being no-ops anyway.
+__device__ __forceinline__ unsigned shl_clamp(unsigned x, unsigned n) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n));            // PTX shl clamps n > 31 (result 0)
+    return r;
+}
+// inclusive warp scan step: x += (lane >= d) ? x of lane - d : 0, using the shuffle's own in-range predicate
+__device__ __forceinline__ unsigned scan_step(unsigned x, int d) {
+    unsigned r;
+    asm("{\n\t.reg .u32 t;\n\t.reg .pred p;\n\t"
+        "shfl.sync.up.b32 t|p, %1, %2, 0, 0xffffffff;\n\t"      // out of range: t = own value, p = false
+        "@p add.u32 t, t, %1;\n\t"
+        "mov.u32 %0, t;\n\t}"
+        : "=r"(r) : "r"(x), "r"(d));
+    return r;
+}
+
+template <bool SCAN, bool RECOMP>
+struct RowT { using type = float2; };
+template <bool SCAN>
+struct RowT<SCAN, true> { using type = float; };
+
+template <bool SCAN, bool RECOMP, class AfterLoads>
+__device__ __forceinline__ void moments_voxel2(const typename RowT<SCAN, RECOMP>::type* __restrict__ row,
+                                               const ErrEntry* __restrict__ errs, unsigned long long pos, int ne, int s,
+                                               int fm, const float4 ent, unsigned lt, float& mean_n, float& var_n,
+                                               float& ent_n, AfterLoads&& after_loads) {
+    const float c = ent.x;
+    float d0 = 0.f, b1 = 0.f, b2 = 0.f, dh = 0.f;
+    unsigned touched = 0u;
+    auto row_at = [&](int bin) -> float2 {
+        const int j = ((bin - s) & (VRDD_BINS - 1)) ^ fm;
+        if constexpr (RECOMP) { const float t = row[j]; return make_float2(t, xlog2x(t)); }
+        else return row[j];
+    };
+    auto apply = [&](int bin, float val) {
+        touched |= shl_clamp(1u, (unsigned)bin);
+        float2 og = make_float2(0.f, 0.f);
+        if ((unsigned)bin < (unsigned)VRDD_BINS) og = row_at(bin);     // absent entry: bin == 32 (a short-lived predicate;
+                                                                        // keeping (k < NE) alive per round made ptxas sink the loads)
+        const float newv = fmaxf(og.x + val, 0.f);
+        const float d = newv - og.x;
+        const float fc = (__int_as_float(0x4b000000 | bin) - 8388608.f) - c;    // (float)bin - c without the conversion pipe
+        d0 += d; b1 = fmaf(fc, d, b1); b2 = fmaf(fc * fc, d, b2);
+        dh += __fadd_rn(xlog2x(newv), -og.y);                                   // exactly 0 when new == old
+    };
+    constexpr int kRounds = 8;
+    ErrEntry e[kRounds];
+    const char* eb = reinterpret_cast<const char*>(errs + pos);
+    unsigned off = 0u;
+    const int rounds = min(__reduce_max_sync(0xffffffffu, ne), kRounds);          // warp-uniform
+    if constexpr (SCAN) {
+        const unsigned ones = 0x01010101u;
+        const unsigned lo = ones & ~shl_clamp(0xffffffffu, 8u * (unsigned)ne);                  // byte k: NE > k
+        const unsigned hi = ones & ~shl_clamp(0xffffffffu, 8u * (unsigned)max(ne - 4, 0));      // byte k: NE > 4 + k
+        unsigned il = lo, ih = hi;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { il = scan_step(il, d); ih = scan_step(ih, d); }
+        const unsigned tl = __shfl_sync(0xffffffffu, il, 31), th = __shfl_sync(0xffffffffu, ih, 31);
+        const unsigned sum_lo = (tl * ones) >> 24;                               // entries of rounds 0..3 (<= 128)
+        // byte k = entries of the rounds before round k (+ lanes below with an entry in round k): < 256
+        const unsigned slot_lo = tl * 0x01010100u + (il - lo);
+        const unsigned slot_hi = th * 0x01010100u + sum_lo * ones + (ih - hi);
+        off = sum_lo + ((th * ones) >> 24);
+#pragma unroll
+        for (int k = 0; k < kRounds; ++k) {
+            const unsigned idx = __byte_perm(k < 4 ? slot_lo : slot_hi, 0u, 0x4440u + (k & 3));
+            e[k].bin = VRDD_BINS; e[k].val = 0.f;
+            if (k < ne) e[k] = ldg_stream_err(reinterpret_cast<const ErrEntry*>(eb + ((size_t)idx << 3)));
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kRounds; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, k < ne);
+            e[k].bin = VRDD_BINS; e[k].val = 0.f;
+            if (k < ne) e[k] = ldg_stream_err(reinterpret_cast<const ErrEntry*>(eb + ((off + __popc(m & lt)) << 3)));
+            off += __popc(m);
+        }
+    }
+    after_loads();
+    // Pin the order "all loads, then all uses": the empty volatile statements stay behind the (volatile) loads
+    // and every use below depends on them; without this ptxas sinks the later rounds' loads next to their
+    // use and the tile pays a memory latency per pair of rounds (5.4 instead of 4.3 ms per 2^28 voxels).
+#pragma unroll
+    for (int k = 0; k < kRounds; ++k) asm volatile("" : "+r"(e[k].bin), "+f"(e[k].val));
+#pragma unroll
+    for (int k = 0; k < kRounds; k += 2) {
+        if (k < rounds) { apply(e[k].bin, e[k].val); apply(e[k + 1].bin, e[k + 1].val); }
+    }
+    if (rounds == kRounds) {
+        for (int k = kRounds;; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, k < ne);
+            if (m == 0u) break;
+            ErrEntry x; x.bin = VRDD_BINS; x.val = 0.f;
+            if (k < ne) x = ldg_stream_err(reinterpret_cast<const ErrEntry*>(eb + ((off + __popc(m & lt)) << 3)));
+            apply(x.bin, x.val);
+            off += __popc(m);
+        }
+    }
+    const bool dup = __popc(touched) != ne;      // NE distinct bins set NE bits (bins are in [0, 32), see moments_voxel)
+
+    const float bw = VRDD_MAX_HISTOGRAM / (float)VRDD_BINS;
+    mean_n = 0.f; var_n = 0.f; ent_n = 0.f;
+    const float A0 = ent.z + d0;
+    if (!dup && A0 > 0.f) {
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(A0));
+        const float dm = b1 * inv;
+        mean_n = fmaf(bw, c + dm, 0.5f * bw) * (float)(1.0 / VRDD_MEAN_NORM);
+        var_n = bw * bw * fmaxf(fmaf(ent.y + b2, inv, -dm * dm), 0.f) * (float)(1.0 / VRDD_VAR_NORM);
+        ent_n = -(fmaf(ent.w + dh, inv, -fast_log2(A0))) * 0.2f;
+    }
+    // A bin hit twice: the reference's ordered route on a private histogram, as in moments_voxel.
+    if (__any_sync(0xffffffffu, dup)) {
+        float cur[VRDD_BINS];
+        if (dup)
+            for (int mm = 0; mm < VRDD_BINS; ++mm) {
+                const int j = ((mm - s) & (VRDD_BINS - 1)) ^ fm;
+                if constexpr (RECOMP) cur[mm] = row[j]; else cur[mm] = row[j].x;
+            }
+        off = 0u;
+        for (int k = 0;; ++k) {
+            const unsigned m = __ballot_sync(0xffffffffu, k < ne);
+            if (m == 0u) break;
+            if (dup && k < ne) {
+                const ErrEntry x = *reinterpret_cast<const ErrEntry*>(eb + ((off + __popc(m & lt)) << 3));
+                if ((unsigned)x.bin < (unsigned)VRDD_BINS) {
+                    const float y = cur[x.bin] + x.val;
+                    cur[x.bin] = (y < 0.f) ? 0.f : y;
+                }
+            }
+            off += __popc(m);
+        }
+        if (dup) {
+            float tot = 0.f;
+            for (int mm = 0; mm < VRDD_BINS; ++mm) tot += cur[mm];
+            const float inv = (tot > 0.f) ? 1.0f / tot : 1.0f;
+            float mean_raw = 0.f, E = 0.f, var = 0.f;
+            for (int mm = 0; mm < VRDD_BINS; ++mm) {
+                cur[mm] *= inv;
+                mean_raw = fmaf(cur[mm], fmaf(bw, (float)mm, 0.5f * bw), mean_raw);
+                E += plog2p(cur[mm]);
+            }
+            for (int mm = 0; mm < VRDD_BINS; ++mm) {
+                const float dd = fmaf(bw, (float)mm, 0.5f * bw) - mean_raw;
+                var = fmaf(cur[mm] * dd, dd, var);
+            }
+            mean_n = mean_raw * (float)(1.0 / VRDD_MEAN_NORM);
+            var_n = var * (float)(1.0 / VRDD_VAR_NORM);
+            ent_n = -E * 0.2f;
+        }
+        __syncwarp();
+    }
+}
+
+template <bool SCAN, bool RECOMP>
+__global__ void __launch_bounds__(1024, 1)
+decode_fractal_moments2_kernel(const int4* __restrict__ codebook, const ErrEntry* __restrict__ errs,
+                               const unsigned long long* __restrict__ chunk_off, const float4* __restrict__ perm,
+                               const void* __restrict__ rows_g, int T, long long nvox, DecodeOut out, int pf_lines) {
+    using Row = typename RowT<SCAN, RECOMP>::type;
+    constexpr int kSmThreads = 1024;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Row* rows_s = reinterpret_cast<Row*>(smem_raw);                                       // [T][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    {
+        const float4* src = reinterpret_cast<const float4*>(rows_g);
+        float4* dst = reinterpret_cast<float4*>(smem_raw);
+        const int n16 = T * VRDD_BINS * (int)sizeof(Row) / 16;
+        for (int i = threadIdx.x; i < n16; i += kSmThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    constexpr int kSmWarps = kSmThreads / 32;
+    const long long nwt = (nvox + 31) / 32;
+    const long long wstride = (long long)gridDim.x * kSmWarps;
+    long long wt = (long long)blockIdx.x * kSmWarps + warp;
+    if (wt >= nwt) return;
+
+    const bool rows32 = ((out.W & 31) == 0) && ((out.v_base & 31) == 0) && (out.use_surf || out.brick[0]);
+    int x0 = 0, y0 = 0, z0 = 0, sx = 0, sy = 0, sz = 0;
+    if (rows32) {
+        split_voxel(out, out.v_base + wt * 32, x0, y0, z0);
+        split_voxel(out, wstride * 32, sx, sy, sz);
+    }
+
+    int4 code = make_int4(0, 0, 0, 0);
+    if (wt * 32 + lane < nvox) code = ldg_stream_i4(codebook + wt * 32 + lane);
+    unsigned long long base = chunk_off[wt];
+    // The error offsets run two tiles ahead, so the NEXT tile's errors (the bulk of a voxel's bytes, and the
+    // one input whose address is data-dependent) can be pulled into L2 while this tile is processed: the
+    // first pf_lines lanes touch one 128-byte line each behind errs[base_n].  ncu had the kernel at 4.5
+    // warps per issue stalled on the long scoreboard with issue slots and LSU pipe no longer the limit.
+    unsigned long long base_n = (wt + wstride < nwt) ? chunk_off[wt + wstride] : 0ull;
+    const unsigned long long err_total = chunk_off[nwt];
+
+    while (true) {
+        const long long v = wt * 32 + lane;
+        const bool live = v < nvox;
+        const long long wt_n = wt + wstride, wt_nn = wt_n + wstride;
+        int4 code_n;
+        unsigned long long base_nn;
+        if (lane < pf_lines && wt_n < nwt) {
+            const unsigned long long first = base_n + 16ull * (unsigned)lane;           // 16 entries per line
+            if (first < err_total) asm volatile("prefetch.global.L2 [%0];" ::"l"(errs + first));
+        }
+        const int id = min(max(code.x, 0), T - 1);
+        const int s = code.y & (VRDD_BINS - 1);
+        // flip as ARITHMETIC, not as a predicate: ptxas hoists `setp.ne code.z, 0` of the next tile across the
+        // back edge to right behind the prefetch that defines code.z (a predicate frees a register), and
+        // every tile then waits a full DRAM latency on the prefetch it has just issued — 32 % of all stall
+        // samples sat on that one ISETP (ncu source page, r1f kernel and this one alike).
+        int fl;
+        asm("min.u32 %0, %1, 1;" : "=r"(fl) : "r"(code.z));        // (code.z != 0) as 0 / 1, opaque to the optimiser
+        const int ne = live ? min(max(code.w, 0), VRDD_BINS) : 0;
+        const float4 ent = __ldg(perm + ((id * 2 + fl) * VRDD_BINS + s));
+        float mean_n, var_n, ent_n;
+        moments_voxel2<SCAN, RECOMP>(rows_s + id * VRDD_BINS, errs, base, ne, s, fl * (VRDD_BINS - 1), ent, lt, mean_n,
+                                     var_n, ent_n, [&] {
+            // unconditional, from clamped (always valid) addresses: a predicated load merged with a default
+            // value made ptxas copy one of the four registers right behind the load — the same stall again
+            code_n = ldg_stream_i4(codebook + min(wt_n * 32 + lane, nvox - 1));
+            base_nn = ldg_stream_u64(chunk_off + min(wt_nn, nwt));
+        });
+        if (live) {
+            if (rows32) emit_decoded_xyz(out, v, x0 + lane, y0, z0, mean_n, var_n, ent_n);
+            else emit_decoded(out, v, mean_n, var_n, ent_n);
+        }
+        if (wt_n >= nwt) break;
+        wt = wt_n; code = code_n; base = base_n; base_n = base_nn;
+        if (rows32) {
+            x0 += sx; if (x0 >= out.W) { x0 -= out.W; ++y0; }
+            y0 += sy; if (y0 >= out.H) { y0 -= out.H; ++z0; }
+            z0 += sz;
+        }
+    }
+}
+
 size_t fractal_smem_bytes(int T, bool tmpl_in_smem) {
     return (size_t)VRDD_BINS * kThreads * sizeof(float) + (tmpl_in_smem ? (size_t)T * VRDD_BINS * sizeof(float) : 0);
 }
@@ -435,7 +690,19 @@ int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const void* errs, 
         const size_t smem = moments_smem_bytes(T);
         const float4* perm = reinterpret_cast<const float4*>(c->tmpl_mom);
         const float2* vg = reinterpret_cast<const float2*>(perm + (size_t)T * 2 * VRDD_BINS);
-        if (c->var_fractal != 2 && smem <= 227 * 1024) {        // the rows fit in shared memory (T <= 908)
+        const bool gen2 = c->var_fractal >= 4 && c->var_fractal <= 7;
+        const bool recomp = gen2 && (c->var_fractal & 1) != 0;
+        const size_t smem2 = recomp ? (size_t)T * VRDD_BINS * sizeof(float) : smem;
+        if (gen2 && smem2 <= 227 * 1024) {                      // second-generation kernel (moments_voxel2)
+            const bool scan = c->var_fractal <= 5;
+            auto kern = scan ? (recomp ? decode_fractal_moments2_kernel<true, true> : decode_fractal_moments2_kernel<true, false>)
+                             : (recomp ? decode_fractal_moments2_kernel<false, true> : decode_fractal_moments2_kernel<false, false>);
+            VRDD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            const long long nblk = (nvox + 1023) / 1024;
+            const int grid = (int)((nblk < c->num_sms) ? nblk : c->num_sms);
+            kern<<<grid, 1024, smem2, c->stream>>>(cb4, er, of, perm, recomp ? (const void*)tmpl : (const void*)vg, T, nvox, out,
+                                                   c->var_fractal_pf);
+        } else if (c->var_fractal != 2 && smem <= 227 * 1024) {        // the rows fit in shared memory (T <= 908)
             auto kern = (threads == 768) ? decode_fractal_moments_smem_kernel<768> : decode_fractal_moments_smem_kernel<1024>;
             VRDD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const long long nblk = (nvox + threads - 1) / threads;
