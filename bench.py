@@ -661,10 +661,11 @@ def run_ours(args):
             ms7, _ = time_render(p7, n7, args.warmup)
             s7 = steps_samples(c7, args.warmup, n7)
             mode7 = {"gsamples_per_s": s7 / (ms7 * 1e-3) / 1e9, "ms_per_step": ms7 / n7, "fps": n7 / (ms7 * 1e-3),
-                     "steps": n7, "kernel": "raycast_mode7_kernel",
-                     "note": "8 point fetches of the un-normalised block means per sample, the reference's cell cache and "
-                             "degenerate-cell artefact kept (volumeRender_kernel.cu:395-480); the reference reports < 5 fps "
-                             "for this mode on its 50x50x10 volume (ver1.9.6.txt:168)"}
+                     "steps": n7, "kernel": "raycast_mode7_kernel<gather>",
+                     "note": "the 8 cell corners of the un-normalised block means come from two tld4 gathers per sample "
+                             "(layered 2-D array; 8 point fetches where the extents do not allow it), the reference's cell "
+                             "cache and degenerate-cell artefact kept (volumeRender_kernel.cu:395-480); the reference "
+                             "reports < 5 fps for this mode on its 50x50x10 volume (ver1.9.6.txt:168)"}
         except Exception as exc:                                   # never let the side measurement void the headline
             mode7 = {"error": repr(exc)}
 

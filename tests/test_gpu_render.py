@@ -331,6 +331,41 @@ def test_transfer_function_texture_matches_the_filter_model(renderer, oracle):
         assert np.abs(hw - model).max() <= 2e-7, (n, float(np.abs(hw - model).max()))
 
 
+@pytest.mark.parametrize("dims,img,rot", [((32, 16, 8), (256, 192), (20.0, 35.0)), ((64, 64, 4), (200, 200), (0.0, 0.0)),
+                                          ((16, 32, 5), (160, 120), (-40.0, 100.0)), ((33, 16, 8), (160, 120), (10.0, 80.0))])
+def test_mode7_gather_fetches_the_same_texels(renderer, oracle, dims, img, rot):
+    """The tld4 path of queryMethod 7 (two gathers per sample from a layered 2-D array instead of eight point
+    fetches) must produce the frames of the point-fetch path bit for bit, edge cells and degenerate cells
+    included, and fall back to it when an x / y extent breaks the regular point rule (33 here)."""
+    import vrdd_b200 as V
+    hist = oracle.synth_histograms(23, dims)
+    r = renderer
+    r.enable_interpolated_mean(True)                             # tld4 is the default fetch path where the extents allow
+    r.set_volume(*dims)
+    r.set_histograms_host(hist)
+    r.decode(V.SRC_ORIGINAL)
+    view = oracle.view_matrix(*rot)
+    r.set_view(view)
+    got = _render(r, V, img[0], img[1], query_method=7)
+    ref, _ = oracle.render_mode7(hist, dims, view, image=img)
+    d = _lsb_diff(got, ref)
+    assert d.max() <= 1, (int(d.max()), int((d > 1).sum()))
+    assert (ref != 0).mean() > 0.1
+    r.set_variant("raycast_mode7", "linear")                     # plain loads of the same texels from the linear plane
+    assert np.array_equal(_render(r, V, img[0], img[1], query_method=7), got)
+    r2 = V.Renderer(0)                                           # and the point-sampled 3-D array, chosen before the decode
+    try:
+        r2.enable_interpolated_mean(True)
+        r2.set_variant("raycast_mode7", "texture")
+        r2.set_volume(*dims)
+        r2.set_histograms_host(hist)
+        r2.decode(V.SRC_ORIGINAL)
+        r2.set_view(view)
+        assert np.array_equal(_render(r2, V, img[0], img[1], query_method=7), got)
+    finally:
+        r2.close()
+
+
 @pytest.mark.parametrize("dims,img,rot", [((50, 50, 10), (512, 512), (0.0, 0.0)), ((12, 10, 8), (160, 120), (25.0, 40.0)),
                                           ((33, 17, 9), (200, 150), (-35.0, 200.0))])
 def test_interpolated_mean_mode7(renderer, oracle, dims, img, rot):

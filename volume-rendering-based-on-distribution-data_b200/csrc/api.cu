@@ -37,6 +37,8 @@ void free_volume(vrdd_decoded_volume& v) {
     if (v.mean_raw) cudaFree(v.mean_raw);
     if (v.mean_tex) cudaDestroyTextureObject(v.mean_tex);
     if (v.mean_arr) cudaFreeArray(v.mean_arr);
+    if (v.mean_gather) cudaDestroyTextureObject(v.mean_gather);
+    if (v.mean_lay) cudaFreeArray(v.mean_lay);
     v = vrdd_decoded_volume();
 }
 
@@ -109,8 +111,32 @@ int ensure_volume_storage(vrdd_context* c, int source) {
             VRDD_CUDA(c, cudaMemsetAsync(v.brick[i], 0, sizeof(float) * brick_elems(c), c->stream));
         }
     }
-    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw) {
-        VRDD_CUDA(c, cudaMalloc(&v.mean_raw, sizeof(float) * c->V));
+    // queryMethod 7 reads the block means through ONE of two arrays: a layered 2-D array fetched with tld4 when
+    // the extents allow it (layer limit 2048, regular point rule in x and y: raycast_mode7_kernel<GATHER>),
+    // else a point-sampled 3-D array; the linear plane is kept in both cases (decode target, fallback).
+    const bool want_gather = c->var_mode7 == 2 && c->D <= 2048 && c->W <= 32768 && c->H <= 32768 &&
+                             point_rule_is_regular(c->W) && point_rule_is_regular(c->H);
+    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw && want_gather) {
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+        // (cudaArrayTextureGather is rejected together with cudaArrayLayered; tld4.a2d itself does not need it)
+        if (cudaMalloc3DArray(&v.mean_lay, &desc, make_cudaExtent(c->W, c->H, c->D), cudaArrayLayered) == cudaSuccess) {
+            cudaResourceDesc rd;
+            std::memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = v.mean_lay;
+            cudaTextureDesc td;
+            std::memset(&td, 0, sizeof(td));
+            td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+            td.filterMode = cudaFilterModePoint;
+            td.readMode = cudaReadModeElementType;
+            td.normalizedCoords = 0;
+            VRDD_CUDA(c, cudaCreateTextureObject(&v.mean_gather, &rd, &td, nullptr));
+        } else {
+            cudaGetLastError();                              // no layered array: the 3-D array below takes over
+            v.mean_lay = nullptr;
+        }
+    }
+    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw && !v.mean_lay) {
         // point-sampled, un-normalised coordinates: texel (x, y, z) is fetched at (x + .5, y + .5, z + .5)
         cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
         VRDD_CUDA(c, cudaMalloc3DArray(&v.mean_arr, &desc, make_cudaExtent(c->W, c->H, c->D), 0));
@@ -126,6 +152,8 @@ int ensure_volume_storage(vrdd_context* c, int source) {
         td.normalizedCoords = 0;
         VRDD_CUDA(c, cudaCreateTextureObject(&v.mean_tex, &rd, &td, nullptr));
     }
+    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw)      // last: its presence marks the set-up as done
+        VRDD_CUDA(c, cudaMalloc(&v.mean_raw, sizeof(float) * c->V));
     return VRDD_OK;
 }
 
@@ -439,12 +467,13 @@ int vrdd_decode(vrdd_handle h, int source, int z0, int nz) {
         rc = launch_decode_fractal(c, c->cb + 4 * local0, c->errs, c->err_off + local0 / VRDD_ERR_CHUNK, c->tmpl,
                                    c->num_templates, nvox, out, nullptr);
     }
-    if (rc == VRDD_OK && orig && c->vol[source].mean_raw && c->vol[source].mean_arr) {
-        // the slab of block means, linear -> 3-D array (only when queryMethod 7 was asked for)
+    if (rc == VRDD_OK && orig && c->vol[source].mean_raw && (c->vol[source].mean_arr || c->vol[source].mean_lay)) {
+        // the slab of block means, linear -> the array queryMethod 7 fetches from: slices [z0, z0 + nz) of the
+        // 3-D array, or the same layers of the layered one (only when queryMethod 7 was asked for)
         cudaMemcpy3DParms cp;
         std::memset(&cp, 0, sizeof(cp));
         cp.srcPtr = make_cudaPitchedPtr(c->vol[source].mean_raw + (size_t)z0 * slice, sizeof(float) * c->W, c->W, c->H);
-        cp.dstArray = c->vol[source].mean_arr;
+        cp.dstArray = c->vol[source].mean_lay ? c->vol[source].mean_lay : c->vol[source].mean_arr;
         cp.dstPos = make_cudaPos(0, 0, z0);
         cp.extent = make_cudaExtent(c->W, c->H, nz);
         cp.kind = cudaMemcpyDeviceToDevice;
@@ -871,7 +900,8 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
     } else if (w == "raycast_mode7") {
         if (v == "texture") c->var_mode7 = 0;
         else if (v == "linear") c->var_mode7 = 1;
-        else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_mode7 is texture|linear");
+        else if (v == "gather") c->var_mode7 = 2;             // set before the decode (the layered copy is made there)
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_mode7 is texture|linear|gather");
     } else if (w == "decode_order") {
         if (v == "interleaved") c->var_decode_order = 0;
         else if (v == "chunked") c->var_decode_order = 1;

@@ -182,6 +182,8 @@ struct vrdd_decoded_volume {
     float* mean_raw = nullptr;       // un-normalised bin-centre mean per block, linear (queryMethod 7)
     cudaArray_t mean_arr = nullptr;  // the same plane as a 3-D array read with point fetches: the march of
     cudaTextureObject_t mean_tex = 0;   // queryMethod 7 wants the texture path's 3-D locality (side views)
+    cudaArray_t mean_lay = nullptr;  // and as a layered 2-D array (layer = z) read with tld4: the 2x2 (x, y) corners
+    cudaTextureObject_t mean_gather = 0;   // of a cell in one fetch (variant raycast_mode7 = gather)
     bool decoded = false;
 };
 
@@ -246,7 +248,7 @@ struct vrdd_context {
     int var_decode_order = 1;        // tma tile order: 0 interleaved over CTAs, 1 one contiguous run per CTA (TLB-friendly, default)
     int var_tf = 1;                  // 0 texture unit, 1 shared-memory table (default: frees the TEX pipe)
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
-    int var_mode7 = 0;               // 0 point-sampled 3-D array (default), 1 linear plane
+    int var_mode7 = 2;               // 2 layered array + tld4 where the volume allows it (default), 0 point-sampled 3-D array, 1 linear plane
     int var_fractal_pf = 12;         // moments2: 128-byte lines of the next tile's errors prefetched into L2 (0..32)
     int var_fractal = 4;             // 0 dense (O(B) per voxel); moments (O(NE) per voxel): 1 r1f kernel, 2 tables in global memory,
                                      // 3 768 threads, 4 moments2 (default), 5 moments2r, 6 moments2b, 7 moments2br (decode_fractal.cu)
@@ -270,6 +272,7 @@ int launch_decode_hist(vrdd_context* c, const float* d_hist, long long nvox, con
 int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const void* errs, const uint64_t* off,
                           const float* tmpl, int T, long long nvox, const DecodeOut& out, float* d_recon);
 int build_template_moments(vrdd_context* c, const float* d_tmpl, int T);
+bool point_rule_is_regular(int n);       // raycast.cu: does the point rule map boundary k to texel min(k, n - 1)?
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses);
 int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_hist);

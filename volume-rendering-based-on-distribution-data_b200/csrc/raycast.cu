@@ -278,6 +278,7 @@ __device__ __forceinline__ float div_small(float k, float n, float inv_n) {
 struct Mode7Args {
     const float* mean_raw;
     cudaTextureObject_t mean_tex;    // the same plane as a point-sampled 3-D array
+    cudaTextureObject_t mean_gather; // the same plane as a layered 2-D array for tld4 (GATHER kernels)
     int W, H, D;
     const float4* tf_tab;
     int tf_n;
@@ -290,7 +291,23 @@ struct Mode7Args {
     unsigned long long* samples;
 };
 
-template <bool COUNT, int U>
+// tld4 on a layered 2-D texture: the four texels a bilinear fetch at (x, y) of layer `layer` would blend,
+// unfiltered: .x = (i, j+1), .y = (i+1, j+1), .z = (i+1, j), .w = (i, j) with i = floor(x - .5), j = floor(y - .5).
+__device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, float x, float y, int layer) {
+    float4 r;
+    asm volatile("tld4.r.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(tex), "r"(layer), "f"(x), "f"(y));
+    return r;
+}
+
+// GATHER: the 2x2 (x, y) corners of a cell come from ONE tld4 per z layer (two fetches per sample instead of
+// eight).  Valid when the texel the texture unit's point rule gives boundary k is k itself on the x and y axes
+// (checked on the host for the volume's extents; true for powers of two, where k/n is exact): the corners are
+// then texels (k, k+1), which is the footprint of a fetch at the texel corner k+1.  The two cases where the
+// reference fetches the SAME texel twice are covered too: at the last cell the clamp returns texel n-1 for
+// n, and in a degenerate cell (floor == ceil) the blend is 0/0 = NaN whatever the means are.
+template <bool COUNT, int U, bool GATHER>
 __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Args A) {
     __shared__ float4 tf_s[VRDD_MAX_TF];
     // Per axis and per cell boundary k in [-1, n+1]: {fl(k/n), index the texture unit's point rule gives it}.
@@ -372,9 +389,11 @@ __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Arg
                 for (int k = 0; k < U; ++k) {                                       // :322-367, :398-463
                     int x0, x1, y0, y1, z0, z1;
                     float xf0, xf1, yf0, yf1, zf0, zf1;              // texel centres
+                    float gfx = 0.f, gfy = 0.f;                      // floor(pos01 * dim) in x and y (GATHER)
                     if (A.use_tab) {
                         const float vx = __fmul_rn(cu[k], fW), vy = __fmul_rn(cv[k], fH), vz = __fmul_rn(cw[k], fD);
                         const float fx = floor_small(vx), fy = floor_small(vy), fz = floor_small(vz);
+                        gfx = fx; gfy = fy;
                         // k + 1 for floor and ceil, as integers (|f| < 2^22), clamped to the table
                         const int ex0 = min(max(__float_as_int(__fadd_rn(fx, 12582912.0f)) - 0x4B400000 + 1, 0), A.W + 1);
                         const int ey0 = min(max(__float_as_int(__fadd_rn(fy, 12582912.0f)) - 0x4B400000 + 1, 0), A.H + 1);
@@ -398,7 +417,22 @@ __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Arg
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) sm[k][j] = 0.f;
-                    if (valid[k] && A.mean_tex) {
+                    if (GATHER) {
+                        if (valid[k]) {
+                            // the texel corner at the cell's upper boundary, floor + 1 clamped to [0, n]: texels
+                            // (k, k+1) inside, (n-1, n-1) at and beyond the last boundary, (0, 0) for the cell
+                            // below zero that rounding of the box entry can produce (floor == -1)
+                            const float gx = fminf(fmaxf(__fadd_rn(gfx, 1.0f), 0.0f), fW);
+                            const float gy = fminf(fmaxf(__fadd_rn(gfy, 1.0f), 0.0f), fH);
+                            // layer = texel centre - 0.5 as an integer, without the conversion pipe
+                            const int l0 = __float_as_int(__fadd_rn(__fadd_rn(zf0, -0.5f), 12582912.0f)) - 0x4B400000;
+                            const int l1 = __float_as_int(__fadd_rn(__fadd_rn(zf1, -0.5f), 12582912.0f)) - 0x4B400000;
+                            const float4 a = gather_layer(A.mean_gather, gx, gy, l0);
+                            const float4 b = gather_layer(A.mean_gather, gx, gy, l1);
+                            sm[k][0] = a.w; sm[k][1] = a.z; sm[k][2] = a.x; sm[k][3] = a.y;
+                            sm[k][4] = b.w; sm[k][5] = b.z; sm[k][6] = b.x; sm[k][7] = b.y;
+                        }
+                    } else if (valid[k] && A.mean_tex) {
                         sm[k][0] = tex3D<float>(A.mean_tex, xf0, yf0, zf0); sm[k][1] = tex3D<float>(A.mean_tex, xf1, yf0, zf0);
                         sm[k][2] = tex3D<float>(A.mean_tex, xf0, yf1, zf0); sm[k][3] = tex3D<float>(A.mean_tex, xf1, yf1, zf0);
                         sm[k][4] = tex3D<float>(A.mean_tex, xf0, yf0, zf1); sm[k][5] = tex3D<float>(A.mean_tex, xf1, yf0, zf1);
@@ -497,6 +531,20 @@ void launch_variant(bool count, int grid, cudaStream_t st, const RayArgs& A, int
 
 }  // namespace
 
+// Host restatement of point_index_hw for the boundary coordinates fl(k / n): true when boundary k fetches
+// texel min(k, n - 1) for every k in [0, n] (the precondition of the tld4 path of queryMethod 7).
+bool point_rule_is_regular(int n) {
+    for (int k = 0; k <= n; ++k) {
+        float u = (float)k / (float)n;
+        u = u < 0.f ? 0.f : (u > 1.f ? 1.f : u);
+        const unsigned U = (unsigned)(u * 2097152.0f);
+        unsigned long long i = ((unsigned long long)U * (unsigned)n) >> 21;
+        if (i > (unsigned long long)(n - 1)) i = (unsigned long long)(n - 1);
+        if ((int)i != (k < n ? k : n - 1)) return false;
+    }
+    return true;
+}
+
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses) {
     const int qm = p.query_method;
@@ -511,7 +559,10 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         if (iw <= 0 || ih <= 0 || !d_out) return fail(c, VRDD_ERR_INVALID, "render: bad image");
         if (part.parts != 1) return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod 7 does not take a tile partition");
         Mode7Args A;
-        A.mean_raw = v0.mean_raw; A.mean_tex = (c->var_mode7 == 0) ? v0.mean_tex : 0; A.W = c->W; A.H = c->H; A.D = c->D;
+        // fetch path: tld4 on the layered copy (default when it exists), else point fetches on the 3-D array,
+        // else (or when asked for) plain loads from the linear plane — the same texels every time
+        A.mean_raw = v0.mean_raw; A.mean_tex = (c->var_mode7 != 1) ? v0.mean_tex : 0; A.W = c->W; A.H = c->H; A.D = c->D;
+        A.mean_gather = v0.mean_gather;
         A.tf_tab = reinterpret_cast<const float4*>(c->tf_dev); A.tf_n = c->tf_n;
         A.out = d_out; A.iw = iw; A.ih = ih;
         for (int i = 0; i < 12; ++i) A.m[i] = c->view[i];
@@ -523,7 +574,11 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         A.use_tab = (c->W <= 8192 && c->H <= 8192 && c->D <= 8192 && tab_bytes <= 64 * 1024) ? 1 : 0;   // div_small's checked range
         A.idx32 = ((unsigned long long)c->W * c->H * c->D < (1ull << 31)) ? 1 : 0;
         const size_t smem7 = A.use_tab ? tab_bytes : 0;
-        auto k7 = (c->count_samples && c->d_samples) ? raycast_mode7_kernel<true, 4> : raycast_mode7_kernel<false, 4>;
+        // tld4 path: asked for, its layered copy exists, and the point rule maps every x / y boundary to itself
+        const bool gather = c->var_mode7 == 2 && v0.mean_gather && A.use_tab;   // regular x / y rule: checked when it was made
+        const bool cnt = c->count_samples && c->d_samples;
+        auto k7 = gather ? (cnt ? raycast_mode7_kernel<true, 4, true> : raycast_mode7_kernel<false, 4, true>)
+                         : (cnt ? raycast_mode7_kernel<true, 4, false> : raycast_mode7_kernel<false, 4, false>);
         VRDD_CUDA(c, cudaFuncSetAttribute(k7, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         k7<<<grid7, kBlock, smem7, c->stream>>>(A);
         c->launches += 1;
