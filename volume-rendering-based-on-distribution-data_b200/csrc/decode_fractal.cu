@@ -596,33 +596,38 @@ decode_fractal_moments2_kernel(const int4* __restrict__ codebook, const ErrEntry
     }
     __syncthreads();
 
+    // tile indices are 32-bit (the launcher checks nvox < 2^36): the per-tile bookkeeping is a handful of
+    // integer instructions instead of 64-bit compare / min chains in a kernel that is issue-bound
     constexpr int kSmWarps = kSmThreads / 32;
-    const long long nwt = (nvox + 31) / 32;
-    const long long wstride = (long long)gridDim.x * kSmWarps;
-    long long wt = (long long)blockIdx.x * kSmWarps + warp;
+    const int nwt = (int)((nvox + 31) / 32);
+    const int wstride = (int)gridDim.x * kSmWarps;
+    int wt = (int)blockIdx.x * kSmWarps + warp;
     if (wt >= nwt) return;
+    const int tail = (int)(nvox - (long long)(nwt - 1) * 32);        // live lanes of the very last tile (1..32)
+    const int last_vox_lane = tail - 1;
 
     const bool rows32 = ((out.W & 31) == 0) && ((out.v_base & 31) == 0) && (out.use_surf || out.brick[0]);
     int x0 = 0, y0 = 0, z0 = 0, sx = 0, sy = 0, sz = 0;
     if (rows32) {
-        split_voxel(out, out.v_base + wt * 32, x0, y0, z0);
-        split_voxel(out, wstride * 32, sx, sy, sz);
+        split_voxel(out, out.v_base + (long long)wt * 32, x0, y0, z0);
+        split_voxel(out, (long long)wstride * 32, sx, sy, sz);
     }
 
-    int4 code = make_int4(0, 0, 0, 0);
-    if (wt * 32 + lane < nvox) code = ldg_stream_i4(codebook + wt * 32 + lane);
+    // lane's voxel of tile t, clamped into the volume (only the last tile can be partial)
+    auto vox_clamped = [&](int t) { return (long long)t * 32 + ((t == nwt - 1) ? min(lane, last_vox_lane) : lane); };
+    int4 code = ldg_stream_i4(codebook + vox_clamped(wt));
     unsigned long long base = chunk_off[wt];
     // The error offsets run two tiles ahead, so the NEXT tile's errors (the bulk of a voxel's bytes, and the
     // one input whose address is data-dependent) can be pulled into L2 while this tile is processed: the
     // first pf_lines lanes touch one 128-byte line each behind errs[base_n].  ncu had the kernel at 4.5
     // warps per issue stalled on the long scoreboard with issue slots and LSU pipe no longer the limit.
-    unsigned long long base_n = (wt + wstride < nwt) ? chunk_off[wt + wstride] : 0ull;
+    unsigned long long base_n = chunk_off[min(wt + wstride, nwt)];
     const unsigned long long err_total = chunk_off[nwt];
 
     while (true) {
-        const long long v = wt * 32 + lane;
-        const bool live = v < nvox;
-        const long long wt_n = wt + wstride, wt_nn = wt_n + wstride;
+        const long long v = (long long)wt * 32 + lane;
+        const bool live = (wt != nwt - 1) || (lane < tail);
+        const int wt_n = wt + wstride;
         int4 code_n;
         unsigned long long base_nn;
         if (lane < pf_lines && wt_n < nwt) {
@@ -644,8 +649,8 @@ decode_fractal_moments2_kernel(const int4* __restrict__ codebook, const ErrEntry
                                      var_n, ent_n, [&] {
             // unconditional, from clamped (always valid) addresses: a predicated load merged with a default
             // value made ptxas copy one of the four registers right behind the load — the same stall again
-            code_n = ldg_stream_i4(codebook + min(wt_n * 32 + lane, nvox - 1));
-            base_nn = ldg_stream_u64(chunk_off + min(wt_nn, nwt));
+            code_n = ldg_stream_i4(codebook + vox_clamped(min(wt_n, nwt - 1)));
+            base_nn = ldg_stream_u64(chunk_off + min(wt_n + wstride, nwt));
         });
         if (live) {
             if (rows32) emit_decoded_xyz(out, v, x0 + lane, y0, z0, mean_n, var_n, ent_n);
@@ -693,7 +698,7 @@ int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const void* errs, 
         const bool gen2 = c->var_fractal >= 4 && c->var_fractal <= 7;
         const bool recomp = gen2 && (c->var_fractal & 1) != 0;
         const size_t smem2 = recomp ? (size_t)T * VRDD_BINS * sizeof(float) : smem;
-        if (gen2 && smem2 <= 227 * 1024) {                      // second-generation kernel (moments_voxel2)
+        if (gen2 && smem2 <= 227 * 1024 && nvox < (1ll << 36)) {        // second-generation kernel (moments_voxel2; 32-bit tile indices)
             const bool scan = c->var_fractal <= 5;
             auto kern = scan ? (recomp ? decode_fractal_moments2_kernel<true, true> : decode_fractal_moments2_kernel<true, false>)
                              : (recomp ? decode_fractal_moments2_kernel<false, true> : decode_fractal_moments2_kernel<false, false>);
