@@ -856,17 +856,38 @@ def run_sortlast(args):
     part = torch.zeros(fh, fw, 4, dtype=torch.float32, device=dev)
     frame = torch.zeros(fh, fw, dtype=torch.int32, device=dev)
 
+    windows = bool(args.sortlast_windows)
+    coll_bytes = [0, 0]                                   # all-gather (received per rank), reduce (sent per rank), per frame
+
     def step(k):
-        r.set_view(orbit_view(V, k))
+        view = orbit_view(V, k)
+        r.set_view(view)
         r.render_brick_alpha(seg, fw, fh, params, br)
-        if world > 1:
-            dist.all_gather_into_tensor(seg_all, seg)
+        if windows:
+            # Only the image rows a brick's screen footprint can touch travel: every rank derives the same
+            # table of row windows from the view matrix (dist.brick_row_windows), contributes the rows of its
+            # own window (a contiguous slab of `seg`), and the composition reads brick b at row y - row0[b].
+            row0, rows, (u0, u1) = D.brick_row_windows(view, grid, fh)
+            seg_rows = seg_all.view(-1)[:world * rows * fw].view(world, rows, fw)
+            mine = seg[row0[rank]:row0[rank] + rows]
+            if world > 1:
+                dist.all_gather_into_tensor(seg_rows, mine)
+            else:
+                seg_rows[0].copy_(mine)
+            r.compose_alpha_in_rows(seg_rows, grid, q, row0, rows, a_in, fw, fh)
+            coll_bytes[0] = world * rows * fw * 4
         else:
-            seg_all[0].copy_(seg)
-        r.compose_alpha_in(seg_all, grid, q, a_in, fw, fh)
+            if world > 1:
+                dist.all_gather_into_tensor(seg_all, seg)
+            else:
+                seg_all[0].copy_(seg)
+            r.compose_alpha_in(seg_all, grid, q, a_in, fw, fh)
+            u0, u1 = 0, fh
+            coll_bytes[0] = world * fh * fw * 4
         r.render_brick_color(a_in, part, fw, fh, params, br)
         if world > 1:
-            dist.reduce(part, dst=0, op=dist.ReduceOp.SUM)
+            dist.reduce(part[u0:u1], dst=0, op=dist.ReduceOp.SUM)      # no brick has samples outside the union rows
+        coll_bytes[1] = (u1 - u0) * fw * 16
         if rank == 0:
             r.pack_frame(part, frame, fw, fh, params.brightness)
 
@@ -914,7 +935,10 @@ def run_sortlast(args):
                 "config": {"workload": f"sort-last: {gdims[0]}x{gdims[1]}x{gdims[2]} distribution volume in {grid[0]}x{grid[1]}x{grid[2]} "
                                        f"bricks of {E}^3 (+1 ghost) over {world} GPUs, {fw}x{fh} frames of the 64-view orbit, reference "
                                        "constants; alpha pre-pass, NCCL all-gather of segment alphas, colour pass, NCCL SUM "
-                                       "reduction of float4 increments, pack on rank 0",
+                                       "reduction of float4 increments, pack on rank 0"
+                                       + ("; collectives restricted to the image rows of each brick's screen footprint" if windows else ""),
+                           "collective_bytes_per_frame": {"all_gather": coll_bytes[0], "reduce": coll_bytes[1],
+                                                          "full_frame": [world * fh * fw * 4, fh * fw * 16]},
                            "volume": list(gdims), "image": [fw, fh], "histogram_bytes_total": decoded_vox * 128,
                            "l2": "inputs larger than L2; no flush"},
                 "decode": {"kernel": "decode_hist_tma_kernel", "voxels": decoded_vox, "ms": dec_ms, "gbs": dec_gbs,
@@ -953,6 +977,8 @@ def main():
     ap.add_argument("--mode7", type=int, default=1, help="also time queryMethod 7 on the same volume and views")
     ap.add_argument("--flex", type=int, default=1, help="also time the flexible-block chain (64^3, block 6)")
     ap.add_argument("--e2e-decode-z", type=int, default=8, help="z-slices of the host-memory decode leg (0 = skip)")
+    ap.add_argument("--sortlast-windows", type=int, default=1,
+                    help="sort-last: restrict the collectives to each brick's screen rows (0: whole frames)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--workload", default="tiles", choices=["tiles", "sortlast"],

@@ -171,7 +171,8 @@ int vrdd_get_decoded_host(vrdd_handle h, int source, float* out4);
 int vrdd_get_decoded_planes_device(vrdd_handle h, int source, float** mean, float** variance,
                                    float** entropy);
 /* queryMethod 7 (the reference's "interpolated mean", volumeRender_kernel.cu:320-367, 395-480) blends
- * the UN-normalised block means.  Enable before decoding the raw histograms to keep them (4 B/voxel). */
+ * the UN-normalised block means.  Enable before decoding the raw histograms to keep them (4 B/voxel for the
+ * linear plane + 4 B/voxel for the array the ray caster fetches from). */
 int vrdd_enable_interpolated_mean(vrdd_handle h, int enable);
 /* Keep linear planes next to the texture arrays (needed for the call above and for
  * vrdd_commit_planes).  Off by default: the decode then writes the arrays directly. */
@@ -266,6 +267,12 @@ int vrdd_render_brick_alpha(vrdd_handle h, float* d_alpha_seg, int image_w, int 
  * d_alpha_seg_all = float[gz][gy][gx][image_h][image_w] (brick index x fastest). */
 int vrdd_compose_alpha_in(vrdd_handle h, const float* d_alpha_seg_all, int gx, int gy, int gz, int qx, int qy,
                           int qz, float* d_alpha_in, int image_w, int image_h);
+/* The same from row windows: brick b contributed only rows [row0[b], row0[b] + rows) of its pass-1 image
+ * (the rows its screen footprint can touch, padded to one common count so that an all-gather applies):
+ * d_alpha_seg_rows = float[gz][gy][gx][rows][image_w]; row0 = host int[gx*gy*gz]; rows outside a brick's
+ * window count as 0.  At most 64 bricks.  vrdd_compose_alpha_in is the case row0 = 0, rows = image_h. */
+int vrdd_compose_alpha_in_rows(vrdd_handle h, const float* d_alpha_seg_rows, int gx, int gy, int gz, int qx, int qy,
+                               int qz, const int* row0, int rows, float* d_alpha_in, int image_w, int image_h);
 /* Pass 2: colour increments (dR, dG, dB, dA) of this brick, float4[image_h][image_w], starting
  * from d_alpha_in with the reference's early exit on the global alpha. */
 int vrdd_render_brick_color(vrdd_handle h, const float* d_alpha_in, float* d_partial4, int image_w, int image_h,
@@ -340,9 +347,12 @@ int vrdd_flex_prefix_spans(int x, int32_t* spans);
 /* ---- diagnostics ------------------------------------------------------------------------ */
 
 /* Selects a kernel variant by name for A/B measurement: "decode_hist" -> "tma" | "ldg";
- * "decode_order" -> "chunked" | "interleaved"; "decode_fractal" -> "moments" | "moments768" | "moments_global" | "dense";
- * "raycast_tf" -> "texture" | "smem"; "raycast_mode7" -> "texture" | "linear" (where queryMethod 7
- * reads the block means from);
+ * "decode_order" -> "chunked" | "interleaved"; "decode_fractal" -> "moments2" (default) | "moments2r" | "moments2b" |
+ * "moments2br" | "moments" | "moments768" | "moments_global" | "dense"; "decode_fractal_prefetch" -> "0".."32"
+ * (128-byte lines of the next tile's errors the moments2 kernels pull into L2, default 12);
+ * "raycast_tf" -> "texture" | "smem"; "raycast_mode7" -> "gather" (default) | "texture" | "linear": where queryMethod 7
+ * reads the block means from — a layered 2-D array with tld4 (where the extents allow it), a point-sampled 3-D
+ * array, or the linear plane; "gather" / "texture" decide which array the DECODE fills, so set them before it;
  * "raycast_unroll" -> "1" | "2" | "4" | "8" (ray-march steps whose fetches are in flight
  * together).  Results do not depend on the variant.  Unknown names return VRDD_ERR_INVALID. */
 int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);

@@ -42,6 +42,17 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
     seg_all = torch.zeros(nb, h, w, dtype=torch.float32, device="cuda")
     for b, (r, q) in enumerate(handles):
         r.render_brick_alpha(seg_all[b], w, h, params, bricks[b])            # pass 1 (+ "all-gather")
+    # the row windows the multi-GPU path gathers instead of whole images: conservative (no brick has alpha outside
+    # its window), and the composition from the windows is the composition from the whole images, bit for bit
+    row0, rows, (u0, u1) = D.brick_row_windows(view, grid, h)
+    handles[0][0].synchronize()
+    seg_rows = torch.zeros(nb, rows, w, dtype=torch.float32, device="cuda")
+    for b in range(nb):
+        outside = seg_all[b].clone()
+        outside[row0[b]:row0[b] + rows] = 0
+        assert float(outside.abs().max()) == 0.0, (grid, b, row0[b], rows)
+        assert u0 <= row0[b] or float(seg_all[b][:u0].abs().max()) == 0.0
+        seg_rows[b].copy_(seg_all[b][row0[b]:row0[b] + rows])
     total = torch.zeros(h, w, 4, dtype=torch.float32, device="cuda")
     samples = 0
     for b, (r, q) in enumerate(handles):
@@ -49,11 +60,16 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
         part = torch.empty(h, w, 4, dtype=torch.float32, device="cuda")
         r.synchronize()
         r.compose_alpha_in(seg_all, grid, q, a_in, w, h)
+        a_win = torch.empty(h, w, dtype=torch.float32, device="cuda")
+        r.compose_alpha_in_rows(seg_rows, grid, q, row0, rows, a_win, w, h)
+        r.synchronize()
+        assert torch.equal(a_win, a_in)
         r.count_samples(True)
         r.render_brick_color(a_in, part, w, h, params, bricks[b])            # pass 2
         r.synchronize()
         samples += r.get_sample_count()
-        total += part                                                        # "reduce (SUM)"
+        assert float(part[:u0].abs().max() if u0 > 0 else 0.0) == 0.0 and float(part[u1:].abs().max() if u1 < h else 0.0) == 0.0
+        total += part                                                        # "reduce (SUM)" (of the union rows)
     out = torch.zeros(h, w, dtype=torch.int32, device="cuda")
     handles[0][0].pack_frame(total, out, w, h, params.brightness)
     handles[0][0].synchronize()
@@ -92,6 +108,31 @@ def test_sortlast_matches_single_volume_and_oracle(oracle, grid, rot, store):
         r.render(one, img[0], img[1], params, clear_misses=True); r.synchronize()
         assert _lsb(got, one.cpu().numpy().view(np.uint32)).max() <= 1
         r.close()
+
+
+def test_brick_row_windows_are_consistent():
+    """Host logic of the row windows (no GPU): one common row count, windows inside the frame and inside the union,
+    the whole frame for a matrix that is not a rotation, and symmetric windows for the frontal view."""
+    import vrdd_b200.dist as D
+    import math
+    def view(rx, ry, tz=4.0):                                 # Rx(-rx) Ry(-ry) T(0,0,tz), rows as in volumeRender.cpp:229-246
+        ax, ay = math.radians(-rx), math.radians(-ry)
+        cx, sx, cy, sy = math.cos(ax), math.sin(ax), math.cos(ay), math.sin(ay)
+        R = [[cy, 0.0, sy], [sx * sy, cx, -sx * cy], [-cx * sy, sx, cx * cy]]
+        return [R[0][0], R[0][1], R[0][2], R[0][2] * tz, R[1][0], R[1][1], R[1][2], R[1][2] * tz,
+                R[2][0], R[2][1], R[2][2], R[2][2] * tz]
+    H = 512
+    for grid in ((2, 2, 2), (2, 1, 1), (3, 2, 1), (1, 1, 1)):
+        for rot in ((0.0, 0.0), (25.0, 40.0), (-35.0, 200.0), (90.0, 0.0), (0.0, 45.0)):
+            row0, rows, (u0, u1) = D.brick_row_windows(view(*rot), grid, H)
+            assert len(row0) == grid[0] * grid[1] * grid[2] and 1 <= rows <= H and 0 <= u0 < u1 <= H
+            assert all(0 <= y and y + rows <= H for y in row0)
+            assert u1 - u0 < H                                   # the box never fills the frame from this distance
+    row0, rows, (u0, u1) = D.brick_row_windows(view(0.0, 0.0), (2, 2, 2), H)
+    assert abs((u0 + u1) - H) <= 2 and rows < 0.45 * H           # frontal view: centred, a brick spans about a third of the rows
+    sheared = view(0.0, 0.0); sheared[1] = 0.3
+    assert D.brick_row_windows(sheared, (2, 2, 2), H)[1:] == (H, (0, H))
+    assert D.brick_row_windows(view(0.0, 0.0, tz=0.5), (2, 2, 2), H)[1] == H      # eye inside the box: whole frame
 
 
 def test_brick_geometry_partitions_the_volume():

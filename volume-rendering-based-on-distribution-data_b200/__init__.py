@@ -38,7 +38,7 @@ EXPORTS = [
     "vrdd_flex_divide_blocks", "vrdd_flex_prefix_spans", "vrdd_flex_set_tables_host", "vrdd_flex_process",
     "vrdd_flex_get_blocks_host",
     "vrdd_frame_alloc", "vrdd_frame_free", "vrdd_frame_export", "vrdd_frame_open", "vrdd_frame_close",
-    "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_render_brick_color", "vrdd_pack_frame",
+    "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_compose_alpha_in_rows", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
 IO_EXPORTS = ["vrdd_io_read_histograms", "vrdd_io_codebook_blocks", "vrdd_io_read_codebook", "vrdd_io_template_count",
@@ -156,6 +156,7 @@ def lib():
             "vrdd_debug_sample_texture_unnorm": (i32, [vp, i32, i32, vp, i32, vp]),
             "vrdd_render_brick_alpha": (i32, [vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_compose_alpha_in": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, i32]),
+            "vrdd_compose_alpha_in_rows": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, i32]),
             "vrdd_render_brick_color": (i32, [vp, vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_pack_frame": (i32, [vp, vp, vp, i32, i32, f32]),
             "vrdd_synth_histograms_region_device": (i32, [vp, u32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
@@ -475,6 +476,13 @@ class Renderer:
     def compose_alpha_in(self, d_alpha_seg_all, grid, q, d_alpha_in, w, h):
         self._ck(lib().vrdd_compose_alpha_in(self._h, _ptr(d_alpha_seg_all), grid[0], grid[1], grid[2], q[0], q[1], q[2],
                                              _ptr(d_alpha_in), w, h))
+
+    def compose_alpha_in_rows(self, d_alpha_seg_rows, grid, q, row0, rows, d_alpha_in, w, h):
+        """Row-window form: brick b contributed rows [row0[b], row0[b] + rows) of its pass-1 image."""
+        n = grid[0] * grid[1] * grid[2]
+        tab = (C.c_int * n)(*[int(v) for v in row0])
+        self._ck(lib().vrdd_compose_alpha_in_rows(self._h, _ptr(d_alpha_seg_rows), grid[0], grid[1], grid[2], q[0], q[1],
+                                                  q[2], tab, int(rows), _ptr(d_alpha_in), w, h))
 
     def render_brick_color(self, d_alpha_in, d_partial4, w, h, params, brick):
         self._ck(lib().vrdd_render_brick_color(self._h, _ptr(d_alpha_in), _ptr(d_partial4), w, h, C.byref(params),

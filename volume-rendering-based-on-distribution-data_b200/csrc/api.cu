@@ -866,7 +866,14 @@ int vrdd_render_brick_color(vrdd_handle h, const float* d_alpha_in, float* d_par
 int vrdd_compose_alpha_in(vrdd_handle h, const float* d_alpha_seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
                           float* d_alpha_in, int image_w, int image_h) {
     CHECK_HANDLE(h);
-    return launch_compose_alpha_in(c, d_alpha_seg_all, gx, gy, gz, qx, qy, qz, d_alpha_in, image_w, image_h);
+    return launch_compose_alpha_in(c, d_alpha_seg_all, gx, gy, gz, qx, qy, qz, nullptr, image_h, d_alpha_in, image_w, image_h);
+}
+
+int vrdd_compose_alpha_in_rows(vrdd_handle h, const float* d_alpha_seg_rows, int gx, int gy, int gz, int qx, int qy, int qz,
+                               const int* row0, int rows, float* d_alpha_in, int image_w, int image_h) {
+    CHECK_HANDLE(h);
+    if (!row0) return fail(c, VRDD_ERR_INVALID, "compose_alpha_in_rows: no row table");
+    return launch_compose_alpha_in(c, d_alpha_seg_rows, gx, gy, gz, qx, qy, qz, row0, rows, d_alpha_in, image_w, image_h);
 }
 
 int vrdd_pack_frame(vrdd_handle h, const float* d_sum4, uint32_t* d_output, int image_w, int image_h, float brightness) {

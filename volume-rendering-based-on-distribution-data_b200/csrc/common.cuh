@@ -282,8 +282,8 @@ int launch_synth_hist_region(vrdd_context* c, uint32_t seed, int gw, int gh, int
                              int nz, float* d_hist);
 int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float* d_out, int iw, int ih,
                       const vrdd_render_params& p, const vrdd_brick& b);
-int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
-                            float* d_alpha_in, int iw, int ih);
+int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_rows, int gx, int gy, int gz, int qx, int qy, int qz,
+                            const int* row0, int rows, float* d_alpha_in, int iw, int ih);
 int launch_pack_frame(vrdd_context* c, const float* d_sum4, uint32_t* d_out, int iw, int ih, float brightness);
 void destroy_flex(vrdd_context* c);
 int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p, int clear_misses);

@@ -273,13 +273,18 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
 // alpha entering brick (qx,qy,qz): composite, front to back, of the segment alphas of every brick
 // that precedes it along the ray in all three axes.  Bricks the ray does not cross hold 0 and
 // leave the accumulator untouched, so any linear extension of the axis-wise order is exact.
+// Every brick contributes a window of `rows` image rows starting at row0[brick] (the rows its screen footprint
+// can touch; the whole image when rows == ih and row0 == 0): seg_rows = float[brick][rows][iw].
 struct ViewMatrix { float m[12]; };
-__global__ void compose_alpha_in_kernel(const float* __restrict__ seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
-                                        float* __restrict__ alpha_in, int iw, int ih, const ViewMatrix M) {
+constexpr int kMaxBricks = 64;
+struct RowWindows { int row0[kMaxBricks]; int rows; };
+__global__ void compose_alpha_in_kernel(const float* __restrict__ seg_rows, int gx, int gy, int gz, int qx, int qy, int qz,
+                                        float* __restrict__ alpha_in, int iw, int ih, const ViewMatrix M,
+                                        const RowWindows Wn) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= iw || y >= ih) return;
     const RaySetup R = make_ray(M.m, x, y, iw, ih);
-    const size_t pix = (size_t)y * iw + x, npix = (size_t)iw * ih;
+    const size_t pix = (size_t)y * iw + x;
     const bool fx = R.dx >= 0.f, fy = R.dy >= 0.f, fz = R.dz >= 0.f;
     const int rqx = fx ? qx : gx - 1 - qx, rqy = fy ? qy : gy - 1 - qy, rqz = fz ? qz : gz - 1 - qz;
     float a = 0.f;
@@ -288,7 +293,9 @@ __global__ void compose_alpha_in_kernel(const float* __restrict__ seg_all, int g
             for (int rx = 0; rx <= rqx; ++rx) {
                 if (rx == rqx && ry == rqy && rz == rqz) continue;
                 const int bx = fx ? rx : gx - 1 - rx, by = fy ? ry : gy - 1 - ry, bz = fz ? rz : gz - 1 - rz;
-                const float s = seg_all[((size_t)(bz * gy + by) * gx + bx) * npix + pix];
+                const int b = (bz * gy + by) * gx + bx;
+                const int yy = y - Wn.row0[b];
+                const float s = ((unsigned)yy < (unsigned)Wn.rows) ? seg_rows[((size_t)b * Wn.rows + yy) * iw + x] : 0.0f;
                 a += s * (1.0f - a);
             }
     alpha_in[pix] = a;
@@ -361,15 +368,21 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
     return VRDD_OK;
 }
 
-int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
-                            float* d_alpha_in, int iw, int ih) {
-    if (!d_seg_all || !d_alpha_in || iw <= 0 || ih <= 0 || gx < 1 || gy < 1 || gz < 1 || qx < 0 || qx >= gx || qy < 0 ||
+int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_rows, int gx, int gy, int gz, int qx, int qy, int qz,
+                            const int* row0, int rows, float* d_alpha_in, int iw, int ih) {
+    if (!d_seg_rows || !d_alpha_in || iw <= 0 || ih <= 0 || gx < 1 || gy < 1 || gz < 1 || qx < 0 || qx >= gx || qy < 0 ||
         qy >= gy || qz < 0 || qz >= gz)
         return fail(c, VRDD_ERR_INVALID, "compose_alpha_in: bad arguments");
+    const long long nb = (long long)gx * gy * gz;
+    if (nb > kMaxBricks) return fail(c, VRDD_ERR_UNSUPPORTED, "compose_alpha_in: more than 64 bricks");
+    RowWindows Wn;
+    Wn.rows = row0 ? rows : ih;
+    if (Wn.rows <= 0 || Wn.rows > ih) return fail(c, VRDD_ERR_INVALID, "compose_alpha_in: bad row window");
+    for (int b = 0; b < kMaxBricks; ++b) Wn.row0[b] = (row0 && b < nb) ? row0[b] : 0;
     ViewMatrix M;
     for (int i = 0; i < 12; ++i) M.m[i] = c->view[i];
     dim3 grid((iw + 127) / 128, ih);
-    compose_alpha_in_kernel<<<grid, 128, 0, c->stream>>>(d_seg_all, gx, gy, gz, qx, qy, qz, d_alpha_in, iw, ih, M);
+    compose_alpha_in_kernel<<<grid, 128, 0, c->stream>>>(d_seg_rows, gx, gy, gz, qx, qy, qz, d_alpha_in, iw, ih, M, Wn);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;

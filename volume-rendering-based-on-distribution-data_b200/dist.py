@@ -95,3 +95,56 @@ def brick_geometry(gdims, grid, q):
         lo.append(float("-inf") if k == 0 else b0 / n)
         hi.append(float("inf") if k == g - 1 else b1 / n)
     return tuple(origin), tuple(size), tuple(lo), tuple(hi)
+
+
+def _screen_rows_of_box(view, lo, hi, height, pad):
+    """Rows [y0, y1) of a `height`-row frame that rays through the world-space box [lo, hi] can belong to.
+    The camera is d_render's (volumeRender_kernel.cu:282-296): pixel row y has v = 2y/H - 1 and the ray through it is
+    o + t * M3x3 * normalize(u, v, -2), so a world point p lies on the ray of the (continuous) row
+    y = (1 - 2 e_y / e_z) * H / 2 with e = M3x3^T (p - o).  Under a perspective map the extremes over a box in front
+    of the eye are taken at its corners.  Whole frame when the matrix is not a rotation or a corner is not in front."""
+    m = [float(v) for v in view]
+    rows3 = (m[0:3], m[4:7], m[8:11])
+    o = (m[3], m[7], m[11])
+    for i in range(3):                                       # orthonormal 3x3?  (M^T is then its inverse)
+        for j in range(3):
+            dot = sum(rows3[i][k] * rows3[j][k] for k in range(3))
+            if abs(dot - (1.0 if i == j else 0.0)) > 1e-4:
+                return 0, height
+    ys = []
+    for cx in (lo[0], hi[0]):
+        for cy in (lo[1], hi[1]):
+            for cz in (lo[2], hi[2]):
+                d = (cx - o[0], cy - o[1], cz - o[2])
+                ey = rows3[0][1] * d[0] + rows3[1][1] * d[1] + rows3[2][1] * d[2]        # column 1 of M . d
+                ez = rows3[0][2] * d[0] + rows3[1][2] * d[1] + rows3[2][2] * d[2]        # column 2 of M . d
+                if ez > -1e-3:
+                    return 0, height
+                ys.append((1.0 - 2.0 * ey / ez) * 0.5 * height)
+    import math
+    y0 = max(0, int(math.floor(min(ys))) - pad)
+    y1 = min(height, int(math.ceil(max(ys))) + 1 + pad)
+    return (y0, y1) if y1 > y0 else (0, 0)
+
+
+def brick_row_windows(view, grid, height, pad=2, eps=1e-3, align=8):
+    """Screen-row windows of the bricks of a `grid` decomposition of the box [-1, 1]^3 for one view.
+
+    Returns (row0, rows, union): brick b (x fastest, like brick_of_rank) can only have samples on rows
+    [row0[b], row0[b] + rows) — `rows` is one common count (the largest footprint, rounded up to `align`, start moved
+    up where the window would leave the frame) so that the windows can be all-gathered; `union` = (y0, y1) covers
+    every brick.  A brick owns the samples whose texture coordinate lies in [k/g, (k+1)/g) per axis (brick_geometry);
+    in world coordinates that is [2k/g - 1, 2(k+1)/g - 1], widened by eps for positions that rounding moves across a
+    face.  Pure host arithmetic on the view matrix: every rank computes the same table."""
+    gx, gy, gz = grid
+    spans = []
+    for b in range(gx * gy * gz):
+        q = (b % gx, (b // gx) % gy, b // (gx * gy))
+        lo = [2.0 * k / g - 1.0 - eps for k, g in zip(q, grid)]
+        hi = [2.0 * (k + 1) / g - 1.0 + eps for k, g in zip(q, grid)]
+        spans.append(_screen_rows_of_box(view, lo, hi, height, pad))
+    rows = max(1, max(y1 - y0 for y0, y1 in spans))
+    rows = min(height, (rows + align - 1) // align * align)
+    row0 = [min(y0, height - rows) for y0, _ in spans]
+    union = (min(y0 for y0, _ in spans), max(max(y1 for _, y1 in spans), 1))
+    return row0, rows, union
