@@ -868,12 +868,7 @@ def run_sortlast(args):
             # table of row windows from the view matrix (dist.brick_row_windows), contributes the rows of its
             # own window (a contiguous slab of `seg`), and the composition reads brick b at row y - row0[b].
             row0, rows, (u0, u1) = D.brick_row_windows(view, grid, fh)
-            seg_rows = seg_all.view(-1)[:world * rows * fw].view(world, rows, fw)
-            mine = seg[row0[rank]:row0[rank] + rows]
-            if world > 1:
-                dist.all_gather_into_tensor(seg_rows, mine)
-            else:
-                seg_rows[0].copy_(mine)
+            seg_rows = D.gather_row_windows(seg, seg_all, row0, rows, rank, world)
             r.compose_alpha_in_rows(seg_rows, grid, q, row0, rows, a_in, fw, fh)
             coll_bytes[0] = world * rows * fw * 4
         else:
@@ -885,8 +880,7 @@ def run_sortlast(args):
             u0, u1 = 0, fh
             coll_bytes[0] = world * fh * fw * 4
         r.render_brick_color(a_in, part, fw, fh, params, br)
-        if world > 1:
-            dist.reduce(part[u0:u1], dst=0, op=dist.ReduceOp.SUM)      # no brick has samples outside the union rows
+        D.reduce_union_rows(part, (u0, u1), dst=0)             # no brick has samples outside the union rows
         coll_bytes[1] = (u1 - u0) * fw * 16
         if rank == 0:
             r.pack_frame(part, frame, fw, fh, params.brightness)

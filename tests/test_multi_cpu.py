@@ -76,6 +76,60 @@ def test_two_ranks_decode_allgather_and_tile_reduce(dims):
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
+def _sortlast_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import vrdd_b200.dist as D
+        from oracle.vrdd_oracle import Oracle
+        o = Oracle()
+        grid = D.brick_grid(world)
+        W, H = 40, 64
+        for rot in ((0.0, 0.0), (30.0, 50.0), (-35.0, 200.0)):
+            view = o.view_matrix(*rot)
+            row0, rows, union = D.brick_row_windows(view, grid, H)
+            # a pass-1 image that is non-zero exactly on the rows the window promises to cover
+            g = torch.Generator().manual_seed(100 + rank)
+            seg = torch.zeros(H, W)
+            seg[row0[rank]:row0[rank] + rows] = torch.rand(rows, W, generator=g)
+            buf = torch.empty(world * H * W)
+            seg_rows = D.gather_row_windows(seg, buf, row0, rows, rank, world)
+            full = torch.empty(world * H, W)
+            dist.all_gather_into_tensor(full, seg)
+            full = full.view(world, H, W)
+            for b in range(world):                              # windows == the same rows of the whole images
+                assert torch.equal(seg_rows[b], full[b, row0[b]:row0[b] + rows]), (rot, b)
+            # increments: zero outside the union on every rank; reducing the union rows is reducing the frame
+            part = torch.zeros(H, W, 4)
+            part[union[0]:union[1]] = torch.rand(union[1] - union[0], W, 4, generator=g)
+            ref = part.clone()
+            dist.reduce(ref, dst=0, op=dist.ReduceOp.SUM)
+            D.reduce_union_rows(part, union, dst=0)
+            if rank == 0:
+                assert torch.equal(part, ref), rot
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_sortlast_row_window_exchange():
+    """The sort-last exchange restricted to row windows (dist.gather_row_windows / reduce_union_rows) moves the
+    same data as whole-frame collectives, world size 2 (bricks 2x1x1) over gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sortlast_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_sharding_rules():
     import vrdd_b200.dist as D
     for depth in (1, 7, 64, 1024):

@@ -148,3 +148,27 @@ def brick_row_windows(view, grid, height, pad=2, eps=1e-3, align=8):
     row0 = [min(y0, height - rows) for y0, _ in spans]
     union = (min(y0 for y0, _ in spans), max(max(y1 for _, y1 in spans), 1))
     return row0, rows, union
+
+
+def gather_row_windows(seg, seg_all_buf, row0, rows, rank, world, group=None):
+    """Pass-1 exchange of the sort-last path restricted to row windows: `seg` is this rank's float[H][W] segment
+    alpha (zero outside rows [row0[rank], row0[rank] + rows)), `seg_all_buf` any float buffer of at least
+    world*rows*W elements.  Returns the view float[world][rows][W] holding every brick's window, the layout
+    vrdd_compose_alpha_in_rows reads."""
+    width = seg.shape[-1]
+    flat = seg_all_buf.view(-1)[:world * rows * width].view(world * rows, width)   # concatenated form: every backend takes it
+    mine = seg[row0[rank]:row0[rank] + rows]                  # a contiguous slab: no packing copy
+    if world > 1:
+        dist.all_gather_into_tensor(flat, mine, group=group)
+    else:
+        flat.copy_(mine)
+    return flat.view(world, rows, width)
+
+
+def reduce_union_rows(part, union, dst=0, group=None):
+    """SUM reduction of the colour increments float[H][W][4] to `dst`, over the rows any brick can touch
+    (no brick has samples outside `union`, so the rows outside it are zero on every rank)."""
+    u0, u1 = union
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(part[u0:u1], dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return part
