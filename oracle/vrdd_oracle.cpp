@@ -13,12 +13,22 @@
  * may load this library, and only as the checker or the timed CPU baseline.  The product
  * (libvrdd.so) never links, loads or calls it.
  *
- * PARITY UNPINNED.  The reference cannot be compiled with CUDA 12.9 (texture references
- * were removed; helper_math.h / helper_cuda.h / GL headers are not vendored) and ships no
- * input data, no reference image and no unit tests.  Nothing from the
- * reference pins this restatement; it is checked against hand-computed known answers and
- * its own invariants in tests/test_oracle.py, and the texture-filter model (WQ_HW below) was
- * fitted to, and is checked against, the B200 texture unit itself
+ * PARITY PINNED BY THE REFERENCE'S OWN DEVICE CODE, RUN ON A B200.  The reference ships no input data, no
+ * reference image and no unit tests, and as it stands it does not compile with CUDA 12.9
+ * (texture references were removed; helper_math.h / helper_cuda.h are not vendored).  oracle/ref_shim gives CUDA 12
+ * those spellings back on top of texture objects, oracle/ref_driver.cu includes volumeRender_kernel.cu where it
+ * lies and replays the reference's call sequence (initCuda, basicDataProcessing, copyInvViewMatrix,
+ * render_kernel) on seeded inputs (oracle/Makefile `ref`, tools/ref_pin.py); what it computed on the GPU is
+ * tests/golden/ref_gpu_v1.npz.  tests/test_reference_pin.py holds this restatement to it:
+ *   - raw-histogram decode: the mean bit for bit, variance and entropy to 3e-7;
+ *   - d_render, queryMethod 1..3: every byte of two 256x256 frames within 1 LSB, at most 12 bytes differing;
+ *   - fractal decode: to 1e-6 wherever the reference's build still does what its source says — its
+ *     fractalDecoding() returns a pointer to a local array (:196-221), and what nvcc 12.9 makes of that wrecks
+ *     the flipped voxels and 3.6 % of the others;
+ *   - queryMethod 7 is discontinuous at cell boundaries, so the last bit of a sample position decides single
+ *     samples: see g_fma_contract below.
+ * Besides that it is checked against hand-computed known answers and its own invariants (tests/test_oracle.py), and
+ * the texture-filter model (WQ_HW below) was fitted to, and is checked against, the B200 texture unit itself
  * (tools/probe_texture*.py, tests/test_gpu_render.py::test_texture_unit_matches_the_filter_model).
  *
  * Arithmetic that lives outside /root/reference and is restated from its public definition:
@@ -280,6 +290,52 @@ inline int intersect_box(f3 o, f3 d, f3 bmin, f3 bmax, float* tnear, float* tfar
 
 inline float saturate(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }  /* NaN -> 0 like __saturatef */
 
+/* How the ray set-up and the compositing are ROUNDED.  The source (:282-312, :695) does not say: it leaves the
+ * contraction of a*b + c into one fused multiply-add to the compiler.  0 (default): no contraction, 1/sqrtf — the
+ * order the CUDA kernels of this repository reproduce bit for bit.  1: what nvcc 12.9 makes of the reference's
+ * d_render with its default -fmad=true, read off the PTX of the reference compiled where it lies
+ * (oracle/Makefile `ref`): u*u + v*v fused, + 4 added, rsqrt; each component of M*dir as
+ * fma(dir.z, m.z, fma(dir.x, m.x, dir.y*m.y)); pos = fma(d, tnear, o); sum = fma(col, 1 - sum.w, sum).  rsqrt is
+ * the correctly rounded 1/sqrt here (the GPU's rsqrt.approx is within an ulp of it).  The two settings give
+ * the same frames to +-1 LSB in queryMethod 1..6; queryMethod 7 amplifies the last bit of a position wherever a
+ * sample sits on a cell boundary (its "vertical and horizontal line" artefact, ver1.9.6.txt:166), and only
+ * setting 1 reproduces the frames of the reference's own binary there (tests/test_reference_pin.py). */
+static int g_fma_contract = 0;
+
+struct RaySetup { f3 o, d; };
+inline RaySetup make_ray(const float* m12, int x, int y, int imageW, int imageH) {
+    RaySetup R;
+    float u = ((float)x / (float)imageW) * 2.0f - 1.0f;                    /* :288 (the same value fused or not) */
+    float v = ((float)y / (float)imageH) * 2.0f - 1.0f;                    /* :289 */
+    R.o = {m12[3], m12[7], m12[11]};               /* mul(M, (0,0,0,1)) == the translation column exactly (:293-294) */
+    f3 r0 = {m12[0], m12[1], m12[2]}, r1 = {m12[4], m12[5], m12[6]}, r2 = {m12[8], m12[9], m12[10]};
+    if (!g_fma_contract) {
+        f3 dv = {u, v, -2.0f};                                             /* :295 */
+        float inv_len = 1.0f / sqrtf(dot3(dv, dv));
+        dv.x = dv.x * inv_len; dv.y = dv.y * inv_len; dv.z = dv.z * inv_len;
+        R.d = {dot3(dv, r0), dot3(dv, r1), dot3(dv, r2)};                  /* :296, 168-174 */
+    } else {
+        float dd = fmaf(u, u, v * v) + 4.0f;
+        float inv_len = (float)(1.0 / std::sqrt((double)dd));
+        f3 dv = {u * inv_len, v * inv_len, inv_len * -2.0f};
+        R.d = {fmaf(dv.z, r0.z, fmaf(dv.x, r0.x, dv.y * r0.y)), fmaf(dv.z, r1.z, fmaf(dv.x, r1.x, dv.y * r1.y)),
+               fmaf(dv.z, r2.z, fmaf(dv.x, r2.x, dv.y * r2.y))};
+    }
+    return R;
+}
+inline f3 first_pos(f3 o, f3 d, float tnear) {                             /* :311 */
+    if (g_fma_contract) return {fmaf(d.x, tnear, o.x), fmaf(d.y, tnear, o.y), fmaf(d.z, tnear, o.z)};
+    return {o.x + d.x * tnear, o.y + d.y * tnear, o.z + d.z * tnear};
+}
+inline void composite(f4& sum, f4 col) {                                   /* :695 */
+    float k = 1.0f - sum.w;
+    if (g_fma_contract) {
+        sum.x = fmaf(col.x, k, sum.x); sum.y = fmaf(col.y, k, sum.y); sum.z = fmaf(col.z, k, sum.z); sum.w = fmaf(col.w, k, sum.w);
+    } else {
+        sum.x = sum.x + col.x * k; sum.y = sum.y + col.y * k; sum.z = sum.z + col.z * k; sum.w = sum.w + col.w * k;
+    }
+}
+
 /* volumeRender_kernel.cu:186-193: saturate, x255, truncate, pack A<<24|B<<16|G<<8|R */
 inline uint32_t pack_rgba(f4 c) {
     float r = saturate(c.x), g = saturate(c.y), b = saturate(c.z), a = saturate(c.w);
@@ -301,6 +357,9 @@ struct vrdd_oracle_render_params {
     int weight_quant;        /* 3 = the measured B200 texture-unit filter (default); 0/1/2 = textbook variants */
     int y0, y1;              /* rows [y0, y1) to render (whole image: 0, image_h) */
 };
+
+/* 0 / 1: see g_fma_contract.  Process-wide; returns the previous setting. */
+int vrdd_oracle_set_fma_contract(int on) { const int prev = g_fma_contract; g_fma_contract = on ? 1 : 0; return prev; }
 
 int vrdd_oracle_num_threads(void) {
 #ifdef _OPENMP
@@ -414,21 +473,14 @@ int64_t vrdd_oracle_render(const float* vol_original4, const float* vol_fractal4
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : samples)
     for (int y = P->y0; y < P->y1; ++y) {
         for (int x = 0; x < imageW; ++x) {
-            float u = ((float)x / (float)imageW) * 2.0f - 1.0f;                    /* :288 */
-            float v = ((float)y / (float)imageH) * 2.0f - 1.0f;                    /* :289 */
-            /* mul(M, (0,0,0,1)) == the translation column exactly (:293-294) */
-            f3 o = {m12[3], m12[7], m12[11]};
-            f3 dv = {u, v, -2.0f};                                                 /* :295 */
-            float inv_len = 1.0f / sqrtf(dot3(dv, dv));
-            dv.x = dv.x * inv_len; dv.y = dv.y * inv_len; dv.z = dv.z * inv_len;
-            f3 r0 = {m12[0], m12[1], m12[2]}, r1 = {m12[4], m12[5], m12[6]}, r2 = {m12[8], m12[9], m12[10]};
-            f3 d = {dot3(dv, r0), dot3(dv, r1), dot3(dv, r2)};                     /* :296, 168-174 */
+            const RaySetup ray = make_ray(m12, x, y, imageW, imageH);                /* :288-296 */
+            const f3 o = ray.o, d = ray.d;
             float tnear, tfar;
             if (!intersect_box(o, d, boxMin, boxMax, &tnear, &tfar)) continue;    /* :300-303 */
             if (tnear < 0.0f) tnear = 0.0f;                                        /* :305-306 */
             f4 sum = {0, 0, 0, 0};
             float t = tnear;
-            f3 pos = {o.x + d.x * tnear, o.y + d.y * tnear, o.z + d.z * tnear};    /* :311 */
+            f3 pos = first_pos(o, d, tnear);                                       /* :311 */
             f3 step = {d.x * P->tstep, d.y * P->tstep, d.z * P->tstep};            /* :312 */
             for (int i = 0; i < P->max_steps; ++i) {                              /* :381 */
                 float sample = tex3d_linear_comp(vol, comp, pos.x * 0.5f + 0.5f, pos.y * 0.5f + 0.5f,
@@ -438,9 +490,7 @@ int64_t vrdd_oracle_render(const float* vol_original4, const float* vol_fractal4
                                        P->weight_quant);                           /* :683-684 */
                 col.w = col.w * P->density;                                        /* :685 */
                 col.x = col.x * col.w; col.y = col.y * col.w; col.z = col.z * col.w; /* :691-693 */
-                float k = 1.0f - sum.w;                                            /* :695 */
-                sum.x = sum.x + col.x * k; sum.y = sum.y + col.y * k;
-                sum.z = sum.z + col.z * k; sum.w = sum.w + col.w * k;
+                composite(sum, col);                                               /* :695 */
                 if (sum.w > P->opacity_threshold) break;                           /* :698 */
                 t = t + P->tstep;                                                  /* :701 */
                 if (t > tfar) break;                                               /* :703 */
@@ -495,20 +545,14 @@ int64_t vrdd_oracle_render_mode7(const float* hist, int W, int H, int D, int B, 
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : samples)
     for (int y = P->y0; y < P->y1; ++y) {
         for (int x = 0; x < imageW; ++x) {
-            float u = ((float)x / (float)imageW) * 2.0f - 1.0f;
-            float v = ((float)y / (float)imageH) * 2.0f - 1.0f;
-            f3 o = {m12[3], m12[7], m12[11]};
-            f3 dv = {u, v, -2.0f};
-            float inv_len = 1.0f / sqrtf(dot3(dv, dv));
-            dv.x = dv.x * inv_len; dv.y = dv.y * inv_len; dv.z = dv.z * inv_len;
-            f3 r0 = {m12[0], m12[1], m12[2]}, r1 = {m12[4], m12[5], m12[6]}, r2 = {m12[8], m12[9], m12[10]};
-            f3 d = {dot3(dv, r0), dot3(dv, r1), dot3(dv, r2)};
+            const RaySetup ray = make_ray(m12, x, y, imageW, imageH);                /* :288-296 */
+            const f3 o = ray.o, d = ray.d;
             float tnear, tfar;
             if (!intersect_box(o, d, boxMin, boxMax, &tnear, &tfar)) continue;
             if (tnear < 0.0f) tnear = 0.0f;
             f4 sum = {0, 0, 0, 0};
             float t = tnear;
-            f3 pos = {o.x + d.x * tnear, o.y + d.y * tnear, o.z + d.z * tnear};
+            f3 pos = first_pos(o, d, tnear);                                       /* :311 */
             f3 step = {d.x * P->tstep, d.y * P->tstep, d.z * P->tstep};
             f3 bot, top;                 /* interPos[0] and interPos[7]; the other six corners mix their components */
             float mean[8];
@@ -530,21 +574,22 @@ int64_t vrdd_oracle_render_mode7(const float* hist, int W, int H, int D, int B, 
                 float xd = (px - bot.x) / (top.x - bot.x);                          /* :466-471 */
                 float yd = (py - bot.y) / (top.y - bot.y);
                 float zd = (pz - bot.z) / (top.z - bot.z);
-                float mean00 = (float)((double)mean[0] * (1.0 - (double)xd) + (double)mean[1] * (double)xd);   /* :472-478 */
-                float mean10 = (float)((double)mean[2] * (1.0 - (double)xd) + (double)mean[3] * (double)xd);
-                float mean01 = (float)((double)mean[4] * (1.0 - (double)xd) + (double)mean[5] * (double)xd);
-                float mean11 = (float)((double)mean[6] * (1.0 - (double)xd) + (double)mean[7] * (double)xd);
-                float mean0 = (float)((double)mean00 * (1.0 - (double)yd) + (double)mean10 * (double)yd);
-                float mean1 = (float)((double)mean01 * (1.0 - (double)yd) + (double)mean11 * (double)yd);
-                float interMean = (float)((double)mean0 * (1.0 - (double)zd) + (double)mean1 * (double)zd);
+                /* :472-478.  `a * (1.0 - w) + b * w` with float a, b, w: the first product is promoted by the double
+                 * literal, the second is a FLOAT product, the sum is double (fused by nvcc: contraction setting 1) */
+                auto lerp7 = [](float a, float b, float w) {
+                    const double wa = 1.0 - (double)w, pb = (double)(b * w);
+                    return (float)(g_fma_contract ? std::fma(wa, (double)a, pb) : (double)a * wa + pb);
+                };
+                float mean00 = lerp7(mean[0], mean[1], xd), mean10 = lerp7(mean[2], mean[3], xd);
+                float mean01 = lerp7(mean[4], mean[5], xd), mean11 = lerp7(mean[6], mean[7], xd);
+                float mean0 = lerp7(mean00, mean10, yd), mean1 = lerp7(mean01, mean11, yd);
+                float interMean = lerp7(mean0, mean1, zd);
                 float sample = interMean * 50;                                      /* :479 */
                 samples += 1;
                 f4 col = tex1d_linear4(tf4, tf_n, (sample - P->transfer_offset) * P->transfer_scale, WQ_HW);
                 col.w = col.w * P->density;
                 col.x = col.x * col.w; col.y = col.y * col.w; col.z = col.z * col.w;
-                float k = 1.0f - sum.w;
-                sum.x = sum.x + col.x * k; sum.y = sum.y + col.y * k;
-                sum.z = sum.z + col.z * k; sum.w = sum.w + col.w * k;
+                composite(sum, col);                                               /* :695 */
                 if (sum.w > P->opacity_threshold) break;
                 t = t + P->tstep;
                 if (t > tfar) break;
@@ -721,20 +766,14 @@ int64_t vrdd_oracle_render_flex(const float* blocks4, int nx, int ny, int nz, co
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : samples)
     for (int y = P->y0; y < P->y1; ++y) {
         for (int x = 0; x < imageW; ++x) {
-            float u = ((float)x / (float)imageW) * 2.0f - 1.0f;
-            float v = ((float)y / (float)imageH) * 2.0f - 1.0f;
-            f3 o = {m12[3], m12[7], m12[11]};
-            f3 dv = {u, v, -2.0f};
-            float inv_len = 1.0f / sqrtf(dot3(dv, dv));
-            dv.x = dv.x * inv_len; dv.y = dv.y * inv_len; dv.z = dv.z * inv_len;
-            f3 r0 = {m12[0], m12[1], m12[2]}, r1 = {m12[4], m12[5], m12[6]}, r2 = {m12[8], m12[9], m12[10]};
-            f3 d = {dot3(dv, r0), dot3(dv, r1), dot3(dv, r2)};
+            const RaySetup ray = make_ray(m12, x, y, imageW, imageH);                /* :288-296 */
+            const f3 o = ray.o, d = ray.d;
             float tnear, tfar;
             if (!intersect_box(o, d, boxMin, boxMax, &tnear, &tfar)) continue;
             if (tnear < 0.0f) tnear = 0.0f;
             f4 sum = {0, 0, 0, 0};
             float t = tnear;
-            f3 pos = {o.x + d.x * tnear, o.y + d.y * tnear, o.z + d.z * tnear};
+            f3 pos = first_pos(o, d, tnear);                                       /* :311 */
             f3 step = {d.x * P->tstep, d.y * P->tstep, d.z * P->tstep};
             for (int i = 0; i < P->max_steps; ++i) {
                 float sample = tex3d_flex(blocks4, nx, ny, nz, comp, (pos.x * 0.5f + 0.5f) * (float)nx,
@@ -743,9 +782,7 @@ int64_t vrdd_oracle_render_flex(const float* blocks4, int nx, int ny, int nz, co
                 f4 col = tex1d_linear4(tf4, tf_n, (sample - P->transfer_offset) * P->transfer_scale, WQ_HW);
                 col.w = col.w * P->density;
                 col.x = col.x * col.w; col.y = col.y * col.w; col.z = col.z * col.w;
-                float k = 1.0f - sum.w;
-                sum.x = sum.x + col.x * k; sum.y = sum.y + col.y * k;
-                sum.z = sum.z + col.z * k; sum.w = sum.w + col.w * k;
+                composite(sum, col);                                               /* :695 */
                 if (sum.w > P->opacity_threshold) break;
                 t = t + P->tstep;
                 if (t > tfar) break;

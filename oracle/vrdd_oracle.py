@@ -1,8 +1,9 @@
 """ctypes binding of the CPU oracle (oracle/vrdd_oracle.cpp).
 
 TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs
-may import this module; the product package never does.  PARITY UNPINNED: the reference
-ships no fixtures and does not compile with CUDA 12.9 (see the header of vrdd_oracle.cpp).
+may import this module; the product package never does.  The reference ships no fixtures; the
+oracle is pinned by outputs of the reference's own device code run on a B200 (oracle/_ref,
+tests/golden/ref_gpu_v1.npz, tests/test_reference_pin.py; see the header of vrdd_oracle.cpp).
 """
 import ctypes as C
 import os
@@ -73,6 +74,8 @@ class Oracle:
         L = self.lib
         L.vrdd_oracle_num_threads.restype = C.c_int
         L.vrdd_oracle_set_num_threads.argtypes = [C.c_int]
+        L.vrdd_oracle_set_fma_contract.argtypes = [C.c_int]
+        L.vrdd_oracle_set_fma_contract.restype = C.c_int
         L.vrdd_oracle_decode_hist.argtypes = [_f32p, C.c_int64, C.c_int, _f32p]
         L.vrdd_oracle_decode_fractal.argtypes = [_i32p, _f32p, _f32p, C.c_int, C.c_int64, C.c_int, _f32p,
                                                  C.c_void_p]
@@ -106,6 +109,12 @@ class Oracle:
 
     def set_num_threads(self, n):
         self.lib.vrdd_oracle_set_num_threads(int(n))
+
+    def set_fma_contract(self, on):
+        """Rounding of the ray set-up and compositing: False (default) = no contraction, the order the CUDA kernels
+        reproduce bit for bit; True = nvcc's default contraction of the reference's d_render (vrdd_oracle.cpp,
+        g_fma_contract).  Returns the previous setting."""
+        return bool(self.lib.vrdd_oracle_set_fma_contract(1 if on else 0))
 
     # -- synthetic inputs -----------------------------------------------------------
     def synth_histograms(self, seed, dims, bins=32, z0=0, nz=None):

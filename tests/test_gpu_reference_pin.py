@@ -1,0 +1,71 @@
+"""The CUDA path against the REFERENCE'S OWN device code: the same fixture as tests/test_reference_pin.py
+(what /root/reference/volumeRender_kernel.cu computed on a B200, tests/golden/ref_gpu_v1.npz), compared with the
+kernels of libvrdd.so through the C ABI — no oracle in between except to mark where the reference's build is
+defined (its fractalDecoding returns a dangling pointer, see test_reference_pin.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.fixture(scope="module")
+def pin(oracle):
+    import ref_pin as R
+    fx = dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_gpu_v1.npz")))
+    hist, cb, tmpl, err, views = R.inputs(oracle)
+    assert R.digest(hist, cb, tmpl, err, views) == str(fx["inputs_sha256"])
+    return dict(fx=fx, hist=hist, cb=cb, tmpl=tmpl, err=err, views=views, dims=R.DIMS, image=R.IMAGE)
+
+
+def _byte_diff(a, b):
+    return np.abs(np.ascontiguousarray(a).view(np.uint8).astype(np.int16) - np.ascontiguousarray(b).view(np.uint8).astype(np.int16))
+
+
+def _frame(r, V, w, h, qm):
+    import torch
+    out = torch.zeros(h, w, dtype=torch.int32, device="cuda")
+    r.render(out, w, h, V.default_render_params(query_method=qm), clear_misses=False)     # pre-cleared, like volumeRender.cpp:208
+    r.synchronize()
+    return out.cpu().numpy().view(np.uint32)
+
+
+def test_cuda_decode_and_frames_match_the_reference_binary(renderer, oracle, pin):
+    import vrdd_b200 as V
+    r = renderer
+    n = pin["dims"][0] * pin["dims"][1] * pin["dims"][2]
+    r.enable_interpolated_mean(True)
+    r.set_volume(*pin["dims"])
+    r.set_histograms_host(pin["hist"])
+    r.set_fractal_host(pin["cb"], pin["err"], pin["tmpl"])
+    r.decode(V.SRC_ORIGINAL)
+    r.decode(V.SRC_FRACTAL)
+    # P1, raw histograms: every voxel (fp32 + MUFU.LG2 on our side, float/double mix on the reference's)
+    got = r.get_decoded_host(V.SRC_ORIGINAL, np.empty((n, 4), np.float32))
+    np.testing.assert_allclose(got[:, :3], pin["fx"]["original"][:, :3], rtol=2e-5, atol=2e-6)
+    # P1, fractal codes: where the reference's build is defined (the oracle marks the voxels its UB left alone)
+    mine, _ = oracle.decode_fractal(pin["cb"], pin["err"], pin["tmpl"])
+    ref = pin["fx"]["fractal"]
+    defined = (np.abs(mine[:, :3] - ref[:, :3]) / np.maximum(np.abs(ref[:, :3]), 1e-3)).max(axis=1) <= 1e-5
+    assert defined.sum() > 0.45 * n
+    gotf = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
+    np.testing.assert_allclose(gotf[defined, :3], ref[defined, :3], rtol=2e-5, atol=2e-6)
+    # P2, queryMethod 1..3: +-1 LSB on every byte of both frames
+    w, h = pin["image"]
+    worst, differing = 0, 0
+    for k in range(pin["views"].shape[0]):
+        r.set_view(pin["views"][k])
+        for qm in (1, 2, 3):
+            d = _byte_diff(_frame(r, V, w, h, qm), pin["fx"]["images"][k, qm - 1])
+            worst = max(worst, int(d.max())); differing = max(differing, int((d != 0).sum()))
+    assert worst <= 1, worst
+    assert differing <= 64, differing                              # of 262 144 bytes per frame
+    # queryMethod 7: single boundary samples (see test_reference_pin.py); no byte is off by more than one sample
+    for k in range(pin["views"].shape[0]):
+        r.set_view(pin["views"][k])
+        d = _byte_diff(_frame(r, V, w, h, 7), pin["fx"]["images"][k, 6])
+        assert d.max() <= 13 and (d > 1).sum() < 0.04 * d.size, (k, int(d.max()), int((d > 1).sum()))
