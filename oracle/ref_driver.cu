@@ -50,7 +50,7 @@ void write_file(const std::string& path, const void* p, size_t bytes) {
 
 int main(int argc, char** argv) {
     if (argc < 5) {
-        std::fprintf(stderr, "usage: ref_driver <dir> <width> <height> <nviews>\n");
+        std::fprintf(stderr, "usage: ref_driver <dir> <width> <height> <nviews> [time]\n");
         return 2;
     }
     const std::string dir = argv[1];
@@ -106,6 +106,41 @@ int main(int argc, char** argv) {
             write_file(dir + "/out/img_v" + std::to_string(k) + "_q" + std::to_string(qm) + ".u32", img.data(),
                        img.size() * sizeof(uint));
         }
+    }
+    // Optional: how long the reference's own kernels take on this GPU at the reference's configuration
+    // (its runSingleTest pattern, volumeRender.cpp:1048-1067: a warm-up launch, then timed launches).
+    if (argc > 5 && std::string(argv[5]) == "time") {
+        const unsigned TW = 512, TH = 512;                       // the reference's window (volumeRender.cpp:121)
+        uint* d_big = nullptr;
+        checkCudaErrors(cudaMalloc((void**)&d_big, (size_t)TW * TH * sizeof(uint)));
+        checkCudaErrors(cudaMemset(d_big, 0, (size_t)TW * TH * sizeof(uint)));
+        const dim3 g2((TW + 15) / 16, (TH + 15) / 16);
+        cudaEvent_t e0, e1;
+        checkCudaErrors(cudaEventCreate(&e0)); checkCudaErrors(cudaEventCreate(&e1));
+        copyInvViewMatrix(views.data(), sizeof(float4) * 3);
+        for (int qm : {1, 4, 7}) {
+            const int iters = (qm == 7) ? 20 : 200;
+            render_kernel(g2, blockSize, d_big, TW, TH, 0.05f, 1.0f, 0.0f, 1.0f, qm, volumeSize);
+            checkCudaErrors(cudaDeviceSynchronize());
+            checkCudaErrors(cudaEventRecord(e0));
+            for (int i = 0; i < iters; ++i)
+                render_kernel(g2, blockSize, d_big, TW, TH, 0.05f, 1.0f, 0.0f, 1.0f, qm, volumeSize);
+            checkCudaErrors(cudaEventRecord(e1));
+            checkCudaErrors(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            checkCudaErrors(cudaEventElapsedTime(&ms, e0, e1));
+            std::printf("ref_time d_render queryMethod %d %ux%u: %.4f ms per frame\n", qm, TW, TH, ms / iters);
+        }
+        d_basicDataProcessing<<<dim3(5, 5, 5), dim3(10, 10, 2)>>>();
+        checkCudaErrors(cudaDeviceSynchronize());
+        checkCudaErrors(cudaEventRecord(e0));
+        for (int i = 0; i < 20; ++i) d_basicDataProcessing<<<dim3(5, 5, 5), dim3(10, 10, 2)>>>();
+        checkCudaErrors(cudaEventRecord(e1));
+        checkCudaErrors(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        checkCudaErrors(cudaEventElapsedTime(&ms, e0, e1));
+        std::printf("ref_time d_basicDataProcessing (25000 blocks, both halves): %.4f ms per launch\n", ms / 20);
+        checkCudaErrors(cudaFree(d_big));
     }
     checkCudaErrors(cudaFree(d_output));
     std::printf("ref_driver: %d blocks decoded, %d views x 7 query methods rendered at %ux%u\n", nBlocks, nviews, W, H);
