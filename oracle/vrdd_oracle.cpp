@@ -22,9 +22,10 @@
  * tests/golden/ref_gpu_v1.npz.  tests/test_reference_pin.py holds this restatement to it:
  *   - raw-histogram decode: the mean bit for bit, variance and entropy to 3e-7;
  *   - d_render, queryMethod 1..3: every byte of two 256x256 frames within 1 LSB, at most 12 bytes differing;
- *   - fractal decode: to 1e-6 wherever the reference's build still does what its source says — its
- *     fractalDecoding() returns a pointer to a local array (:196-221), and what nvcc 12.9 makes of that wrecks
- *     the flipped voxels and 3.6 % of the others;
+ *   - fractal decode: every voxel to 1e-6, and the frames of queryMethod 4..6, once the stores the reference's
+ *     build drops are modelled — its fractalDecoding() returns a pointer to a local array (:196-221), and nvcc 12.9
+ *     keeps only the stores of template bins 0..22 (unflipped) resp. 8..31 (flipped) into it
+ *     (tools/ref_pin.as_the_reference_build_decodes); this restatement keeps the source's intent, all 32 bins;
  *   - queryMethod 7 is discontinuous at cell boundaries, so the last bit of a sample position decides single
  *     samples: see g_fma_contract below.
  * Besides that it is checked against hand-computed known answers and its own invariants (tests/test_oracle.py), and

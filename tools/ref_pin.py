@@ -38,6 +38,22 @@ def inputs(o):
     return hist, cb, tmpl, err, views
 
 
+def as_the_reference_build_decodes(cb, tmpl):
+    """Codes and templates under which the SOURCE'S algorithm gives what the reference's nvcc 12.9 build gives.
+
+    fractalDecoding() returns a pointer to its local array `decoded` (volumeRender_kernel.cu:196-221), so the compiler
+    may drop stores into it: in the PTX of d_basicDataProcessing the unflipped branch keeps the stores of
+    original[0..22] only, the flipped branch those of the first 24 reversed elements (original[8..31]); the rest of
+    `decoded` stays zero.  That is the same as decoding with template bins 23..31 (unflipped) resp. 0..7 (flipped)
+    zeroed: a doubled template table, flipped voxels pointing into its second half."""
+    T = tmpl.shape[0]
+    a = tmpl.copy(); a[:, 23:] = 0.0
+    b = tmpl.copy(); b[:, :8] = 0.0
+    cb2 = cb.copy()
+    cb2[cb[:, 2] != 0, 0] += T
+    return cb2, np.concatenate([a, b]).astype(np.float32)
+
+
 def digest(*arrays):
     h = hashlib.sha256()
     for a in arrays:
