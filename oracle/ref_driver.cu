@@ -16,7 +16,9 @@
 //     <dir>/out/img_v<k>_q<m>.u32                   uint[H][W] of d_render for queryMethod m = 1..7
 // The volume is the reference's hard-wired 50x50x10 blocks of 32 bins (volumeRender.cpp:86-90,
 // volumeRender_kernel.cu:727-729).  The flexible-block arguments of initCuda get zero-filled tables of the sizes
-// it hard-codes (:96-101); dataProcessing() is not called (its span tables do not ship).
+// it hard-codes (:96-101) and dataProcessing() is skipped (its span tables do not ship) — unless the fifth argument
+// is "flex": then <dir>/in/flex_*.{i32,f32} hold span tables of those sizes, dataProcessing() runs as main() runs it,
+// and out/flex_dims.i32, out/flex_blocks.f32 and the frames of queryMethod 8, 9, 0 are written as well.
 // Test infrastructure: only tests/ and tools/ run this binary, never the product.
 #include REF_KERNEL_CU
 
@@ -50,7 +52,7 @@ void write_file(const std::string& path, const void* p, size_t bytes) {
 
 int main(int argc, char** argv) {
     if (argc < 5) {
-        std::fprintf(stderr, "usage: ref_driver <dir> <width> <height> <nviews> [time]\n");
+        std::fprintf(stderr, "usage: ref_driver <dir> <width> <height> <nviews> [time|flex]\n");
         return 2;
     }
     const std::string dir = argv[1];
@@ -70,16 +72,47 @@ int main(int argc, char** argv) {
     std::vector<float2> errors = read_file<float2>(dir + "/in/errors.f32", (size_t)nBlocks * nBins);
     std::vector<float> views = read_file<float>(dir + "/in/views.f32", (size_t)nviews * 12);
 
-    // zero tables of the hard-coded flexible-block sizes (volumeRender_kernel.cu:96-101)
-    const size_t nspan = 64 * 64 * 32;
-    std::vector<int4> z4(nspan, make_int4(0, 0, 0, 0));
-    std::vector<float2> zf2((size_t)64 * 2048 * 64, make_float2(0.f, 0.f));
-    std::vector<int> zi(nspan, 0);
-    std::vector<float> zt(64 * 469, 0.f);
+    // The flexible-block tables, at the sizes initCuda hard-codes (volumeRender_kernel.cu:96-101: 131 072 spans each,
+    // 64 entries per span, 469 templates of 64 bins): zero-filled, or — mode "flex" — read from <dir>/in/flex_*.
+    const bool flex = argc > 5 && std::string(argv[5]) == "flex";
+    const size_t nspan = 64 * 64 * 32, nent = (size_t)64 * 2048 * 64;
+    std::vector<int4> spanLow(nspan, make_int4(0, 0, 0, 0)), spanHigh(spanLow), flexCode(spanLow), simpleLow(spanLow),
+        simpleHigh(spanLow);
+    std::vector<float2> flexErr(nent, make_float2(0.f, 0.f)), simpleHist(flexErr);
+    std::vector<int> simpleCount(nspan, 0);
+    std::vector<float> flexTmpl(64 * 469, 0.f);
+    if (flex) {
+        spanLow = read_file<int4>(dir + "/in/flex_span_low.i32", nspan);
+        spanHigh = read_file<int4>(dir + "/in/flex_span_high.i32", nspan);
+        flexCode = read_file<int4>(dir + "/in/flex_codebook.i32", nspan);
+        flexErr = read_file<float2>(dir + "/in/flex_errors.f32", nent);
+        simpleLow = read_file<int4>(dir + "/in/flex_simple_low.i32", nspan);
+        simpleHigh = read_file<int4>(dir + "/in/flex_simple_high.i32", nspan);
+        simpleCount = read_file<int>(dir + "/in/flex_simple_count.i32", nspan);
+        simpleHist = read_file<float2>(dir + "/in/flex_simple_hist.f32", nent);
+        flexTmpl = read_file<float>(dir + "/in/flex_templates.f32", 64 * 469);
+    }
 
     initCuda(hist.data(), volumeSize, histogramSize, codebook.data(), codebookSize, templates.data(), templatesSize,
-             errors.data(), errorsbookSize, z4.data(), z4.data(), z4.data(), zf2.data(), z4.data(), z4.data(), zi.data(),
-             zf2.data(), zt.data());
+             errors.data(), errorsbookSize, spanLow.data(), spanHigh.data(), flexCode.data(), flexErr.data(),
+             simpleLow.data(), simpleHigh.data(), simpleCount.data(), simpleHist.data(), flexTmpl.data());
+    if (flex) {
+        // main()'s order (volumeRender.cpp:1220-1221): dataProcessing() — block size 6 on the 64^3 raw volume, hard-coded
+        // at volumeRender_kernel.cu:1737 and :101 — then basicDataProcessing()
+        dataProcessing();
+        checkCudaErrors(cudaDeviceSynchronize());
+        int nb[4] = {0, 0, 0, 0};
+        checkCudaErrors(cudaMemcpyFromSymbol(&nb[0], nFlexBlock, sizeof(int)));
+        checkCudaErrors(cudaMemcpyFromSymbol(&nb[1], nFlexBlockX, sizeof(int)));
+        checkCudaErrors(cudaMemcpyFromSymbol(&nb[2], nFlexBlockY, sizeof(int)));
+        checkCudaErrors(cudaMemcpyFromSymbol(&nb[3], nFlexBlockZ, sizeof(int)));
+        write_file(dir + "/out/flex_dims.i32", nb, sizeof(nb));
+        if (nb[0] > 0 && nb[0] <= 1000000) {
+            std::vector<float4> fb(nb[0]);
+            checkCudaErrors(cudaMemcpyFromSymbol(fb.data(), flexBlockData, sizeof(float4) * nb[0]));
+            write_file(dir + "/out/flex_blocks.f32", fb.data(), sizeof(float4) * nb[0]);
+        }
+    }
     basicDataProcessing();
     checkCudaErrors(cudaDeviceSynchronize());
 
@@ -97,7 +130,7 @@ int main(int argc, char** argv) {
     const dim3 gridSize((W + 15) / 16, (H + 15) / 16);
     for (int k = 0; k < nviews; ++k) {
         copyInvViewMatrix(views.data() + 12 * k, sizeof(float4) * 3);
-        for (int qm = 1; qm <= 7; ++qm) {
+        for (int qm = flex ? 0 : 1; qm <= (flex ? 9 : 7); ++qm) {       // 8, 9, 0 sample the flexible-block volume
             checkCudaErrors(cudaMemset(d_output, 0, (size_t)W * H * sizeof(uint)));
             render_kernel(gridSize, blockSize, d_output, W, H, 0.05f, 1.0f, 0.0f, 1.0f, qm, volumeSize);
             getLastCudaError("render_kernel failed");
