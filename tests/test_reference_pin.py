@@ -18,7 +18,6 @@ What it pins, and what it cannot:
     ver1.9.6.txt:166), so the last bit of a sample position decides single samples.  With the compiler's FMA
     contraction of the ray set-up modelled (Oracle.set_fma_contract) about half of the differing bytes disappear;
     the rest hang on the GPU's approximate rsqrt, which a CPU cannot reproduce bit for bit."""
-import hashlib
 import os
 import sys
 

@@ -1,6 +1,10 @@
 """queryMethod 7: the three fetch paths against the oracle and against one another at small sizes."""
-import sys, os, numpy as np
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vrdd_b200 as V
 import torch
 from oracle.vrdd_oracle import Oracle

@@ -1,12 +1,9 @@
 """The reference's own kernels and ours on the same GPU at the REFERENCE'S configuration (50x50x10 blocks x 32 bins,
 512x512 frames, its self-test view): oracle/_ref/ref_driver ... time, then libvrdd.so through the C ABI.  No torch."""
-import ctypes as C
 import os
 import subprocess
 import sys
 import time
-
-import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
