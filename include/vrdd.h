@@ -354,7 +354,11 @@ int vrdd_flex_prefix_spans(int x, int32_t* spans);
  * reads the block means from — a layered 2-D array with tld4 (where the extents allow it), a point-sampled 3-D
  * array, or the linear plane; "gather" / "texture" decide which array the DECODE fills, so set them before it;
  * "raycast_unroll" -> "1" | "2" | "4" | "8" (ray-march steps whose fetches are in flight
- * together).  Results do not depend on the variant.  Unknown names return VRDD_ERR_INVALID. */
+ * together).  Results do not depend on these variants.
+ * "ray_setup" -> "source" (default) | "nvcc" is different: it selects how the eye ray of vrdd_render is ROUNDED —
+ * the uncontracted order of the reference's source, or what nvcc's default FMA contraction and rsqrt make of it in
+ * the reference's own build (csrc/raycast.cu, ray_dir_nvcc).  Frames agree to +-1 LSB except in queryMethod 7,
+ * whose cell logic is discontinuous.  Unknown names return VRDD_ERR_INVALID. */
 int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);
 /* Samples the texture unit: out[i] = tex3D(plane `comp` of `source`, u[i], v[i], w[i]) with
  * the ray caster's texture object.  For the filter-model conformance test.  Device ptrs. */

@@ -5,6 +5,7 @@ where it lies behind oracle/ref_shim, run on the GPU with the real texture unit)
     python tools/ref_pin.py run <dir>       oracle/_ref/ref_driver on them (GPU box)              -> <dir>/out
     python tools/ref_pin.py compare <dir>   oracle vs the reference's outputs; writes <dir>/ref_gpu_v1.npz
     python tools/ref_pin.py all <dir>       the three in a row
+    python tools/ref_pin.py cuda [fixture]  the CUDA path against the fixture, ray set-up "source" and "nvcc" (GPU)
 
 The fixture (tests/golden/ref_gpu_v1.npz, checked by tests/test_reference_pin.py without a GPU) holds the seeds, a
 digest of the inputs and what the reference computed: both decoded volumes and the frames of queryMethod 1..7 for
@@ -146,7 +147,35 @@ def compare(d):
     print("fixture:", out, os.path.getsize(out), "bytes; worst decode rel", worst[0], "worst LSB", worst[1])
 
 
+def cuda(fixture):
+    """The CUDA path (libvrdd.so, needs a GPU) against the fixture, for both roundings of the ray set-up."""
+    import torch
+    import vrdd_b200 as V
+    from oracle.vrdd_oracle import Oracle
+    o = Oracle()
+    fx = dict(np.load(fixture))
+    hist, cb, tmpl, err, views = inputs(o)
+    assert digest(hist, cb, tmpl, err, views) == str(fx["inputs_sha256"])
+    for setup in ("source", "nvcc"):
+        r = V.Renderer(0)
+        r.enable_interpolated_mean(True)
+        r.set_variant("ray_setup", setup)
+        r.set_volume(*DIMS); r.set_histograms_host(hist); r.decode(V.SRC_ORIGINAL)
+        out = torch.zeros(IMAGE[1], IMAGE[0], dtype=torch.int32, device="cuda")
+        for k in range(len(VIEWS)):
+            r.set_view(views[k])
+            for qm in (1, 2, 3, 7):
+                out.zero_()
+                r.render(out, IMAGE[0], IMAGE[1], V.default_render_params(query_method=qm)); r.synchronize()
+                d = np.abs(out.cpu().numpy().view(np.uint8).astype(np.int16) - fx["images"][k, qm - 1].view(np.uint8).astype(np.int16))
+                print(f"ray_setup {setup:6s} view {k} queryMethod {qm}: max LSB diff {int(d.max())}  bytes off by >1: {int((d > 1).sum())}  by 1: {int((d == 1).sum())}")
+        r.close()
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "cuda":
+        cuda(sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "tests", "golden", "ref_gpu_v1.npz"))
+        raise SystemExit(0)
     what, d = sys.argv[1], os.path.abspath(sys.argv[2])
     if what in ("gen", "all"):
         gen(d)

@@ -47,6 +47,7 @@ struct RayArgs {
     int tile_w, tile_h, tiles_x, part, parts, n_my_tiles;
     int blocks_x, blocks_per_tile;   // 16x16-pixel blocks inside a tile
     int clear_misses;
+    int ref_rounding;                // ray set-up rounded like the reference's nvcc build (see ray_dir_nvcc)
     unsigned long long* samples;
 };
 
@@ -108,6 +109,24 @@ __device__ __forceinline__ float sample_bricked(const RayArgs& A, float u, float
     return acc * (1.0f / 256.0f);
 }
 
+// Ray set-up and first sample position with the ROUNDING OF THE REFERENCE'S OWN BUILD (opt-in, variant
+// "ray_setup" = "nvcc"): what nvcc 12.9 generates for d_render with its default -fmad=true, read off the PTX of the
+// reference compiled where it lies (oracle/Makefile `ref`; DESIGN.md §2, finding 2) — u*u + v*v fused, + 4,
+// rsqrt.approx; each component of M*dir as fma(dir.z, m.z, fma(dir.x, m.x, dir.y*m.y)); IEEE reciprocals in the slab
+// test; pos = fma(d, tnear, o).  The default ("source") is the uncontracted order of the oracle, written out with
+// explicitly rounded operations in the kernels.  Only queryMethod 7 can tell the two apart beyond +-1 LSB.
+struct RaySetupRef { float dx, dy, dz; };
+__device__ __forceinline__ RaySetupRef ray_dir_nvcc(const float* m, float u, float v) {
+    const float dd = __fadd_rn(fmaf(u, u, __fmul_rn(v, v)), 4.0f);
+    const float inv = rsqrtf(dd);                                       // rsqrt.approx.f32, as in the reference's build
+    const float a = __fmul_rn(u, inv), b = __fmul_rn(v, inv), c = __fmul_rn(inv, -2.0f);
+    RaySetupRef R;
+    R.dx = fmaf(c, m[2], fmaf(a, m[0], __fmul_rn(b, m[1])));
+    R.dy = fmaf(c, m[6], fmaf(a, m[4], __fmul_rn(b, m[5])));
+    R.dz = fmaf(c, m[10], fmaf(a, m[8], __fmul_rn(b, m[9])));
+    return R;
+}
+
 __device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a) {
     // saturate, scale, truncate, pack (volumeRender_kernel.cu:186-193)
     return ((uint32_t)(__saturatef(a) * 255.0f) << 24) | ((uint32_t)(__saturatef(b) * 255.0f) << 16) |
@@ -151,9 +170,10 @@ __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
         const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
         const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
         dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
-        const float dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[0]), __fmul_rn(dy0, A.m[1])), __fmul_rn(dz0, A.m[2]));
-        const float dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[4]), __fmul_rn(dy0, A.m[5])), __fmul_rn(dz0, A.m[6]));
-        const float dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[8]), __fmul_rn(dy0, A.m[9])), __fmul_rn(dz0, A.m[10]));
+        float dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[0]), __fmul_rn(dy0, A.m[1])), __fmul_rn(dz0, A.m[2]));
+        float dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[4]), __fmul_rn(dy0, A.m[5])), __fmul_rn(dz0, A.m[6]));
+        float dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[8]), __fmul_rn(dy0, A.m[9])), __fmul_rn(dz0, A.m[10]));
+        if (A.ref_rounding) { const RaySetupRef R = ray_dir_nvcc(A.m, u, v); dx = R.dx; dy = R.dy; dz = R.dz; }
         // ---- slab test against [-1,1]^3 (:136-156) --------------------------------------
         const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
         const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, ox));
@@ -171,6 +191,7 @@ __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
             float px = __fadd_rn(ox, __fmul_rn(dx, tnear));                          // :311
             float py = __fadd_rn(oy, __fmul_rn(dy, tnear));
             float pz = __fadd_rn(oz, __fmul_rn(dz, tnear));
+            if (A.ref_rounding) { px = fmaf(dx, tnear, ox); py = fmaf(dy, tnear, oy); pz = fmaf(dz, tnear, oz); }
             const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
             int i = 0;
             bool alive = A.max_steps > 0;                 // the geometric state (i, t, p) is a live step
@@ -288,6 +309,7 @@ struct Mode7Args {
     float density, brightness, t_offset, t_scale, tstep, thresh;
     int max_steps, clear_misses;
     int use_tab, idx32;
+    int ref_rounding;                // ray set-up rounded like the reference's nvcc build (see ray_dir_nvcc)
     unsigned long long* samples;
 };
 
@@ -342,9 +364,10 @@ __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Arg
         const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
         const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
         dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
-        const float dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[0]), __fmul_rn(dy0, A.m[1])), __fmul_rn(dz0, A.m[2]));
-        const float dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[4]), __fmul_rn(dy0, A.m[5])), __fmul_rn(dz0, A.m[6]));
-        const float dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[8]), __fmul_rn(dy0, A.m[9])), __fmul_rn(dz0, A.m[10]));
+        float dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[0]), __fmul_rn(dy0, A.m[1])), __fmul_rn(dz0, A.m[2]));
+        float dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[4]), __fmul_rn(dy0, A.m[5])), __fmul_rn(dz0, A.m[6]));
+        float dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[8]), __fmul_rn(dy0, A.m[9])), __fmul_rn(dz0, A.m[10]));
+        if (A.ref_rounding) { const RaySetupRef R = ray_dir_nvcc(A.m, u, v); dx = R.dx; dy = R.dy; dz = R.dz; }
         const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
         const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, ox));
         const float by0 = __fmul_rn(iy, __fsub_rn(-1.0f, oy)), by1 = __fmul_rn(iy, __fsub_rn(1.0f, oy));
@@ -356,6 +379,7 @@ __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Arg
             float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, t = tnear;
             float px = __fadd_rn(ox, __fmul_rn(dx, tnear)), py = __fadd_rn(oy, __fmul_rn(dy, tnear)),
                   pz = __fadd_rn(oz, __fmul_rn(dz, tnear));
+            if (A.ref_rounding) { px = fmaf(dx, tnear, ox); py = fmaf(dy, tnear, oy); pz = fmaf(dz, tnear, oz); }
             const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
             const float fW = (float)A.W, fH = (float)A.H, fD = (float)A.D;
             // The reference keeps the eight corner means of the current cell and refreshes them when a sample
@@ -569,6 +593,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         A.density = p.density; A.brightness = p.brightness; A.t_offset = p.transfer_offset; A.t_scale = p.transfer_scale;
         A.tstep = p.tstep; A.thresh = p.opacity_threshold; A.max_steps = p.max_steps; A.clear_misses = clear_misses;
         A.samples = c->d_samples;
+        A.ref_rounding = c->var_ray_setup;
         const int grid7 = ((iw + 15) / 16) * ((ih + 15) / 16);
         const size_t tab_bytes = sizeof(float2) * ((size_t)c->W + c->H + c->D + 9);
         A.use_tab = (c->W <= 8192 && c->H <= 8192 && c->D <= 8192 && tab_bytes <= 64 * 1024) ? 1 : 0;   // div_small's checked range
@@ -613,6 +638,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
     A.blocks_x = (part.tile_w + 15) / 16;
     A.blocks_per_tile = A.blocks_x * ((part.tile_h + 15) / 16);
     A.clear_misses = clear_misses;
+    A.ref_rounding = c->var_ray_setup;
     A.samples = c->d_samples;
     if (A.n_my_tiles <= 0) return VRDD_OK;
     const long long grid = (long long)A.n_my_tiles * A.blocks_per_tile;
