@@ -439,13 +439,13 @@ __device__ __forceinline__ unsigned scan_step(unsigned x, int d) {
     return r;
 }
 
-template <bool SCAN, bool RECOMP>
-struct RowT { using type = float2; };
-template <bool SCAN>
-struct RowT<SCAN, true> { using type = float; };
+template <bool RECOMP>
+struct RowT { using type = float2; };          // {t, t*log2 t}
+template <>
+struct RowT<true> { using type = float; };     // t only: g(t) is recomputed
 
 template <bool SCAN, bool RECOMP, class AfterLoads>
-__device__ __forceinline__ void moments_voxel2(const typename RowT<SCAN, RECOMP>::type* __restrict__ row,
+__device__ __forceinline__ void moments_voxel2(const typename RowT<RECOMP>::type* __restrict__ row,
                                                const ErrEntry* __restrict__ errs, unsigned long long pos, int ne, int s,
                                                int fm, const float4 ent, unsigned lt, float& mean_n, float& var_n,
                                                float& ent_n, AfterLoads&& after_loads) {
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(1024, 1)
 decode_fractal_moments2_kernel(const int4* __restrict__ codebook, const ErrEntry* __restrict__ errs,
                                const unsigned long long* __restrict__ chunk_off, const float4* __restrict__ perm,
                                const void* __restrict__ rows_g, int T, long long nvox, DecodeOut out, int pf_lines) {
-    using Row = typename RowT<SCAN, RECOMP>::type;
+    using Row = typename RowT<RECOMP>::type;
     constexpr int kSmThreads = 1024;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Row* rows_s = reinterpret_cast<Row*>(smem_raw);                                       // [T][32]
