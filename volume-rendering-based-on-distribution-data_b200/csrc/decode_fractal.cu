@@ -596,7 +596,7 @@ decode_fractal_moments2_kernel(const int4* __restrict__ codebook, const ErrEntry
     }
     __syncthreads();
 
-    // tile indices are 32-bit (the launcher checks nvox < 2^36): the per-tile bookkeeping is a handful of
+    // tile indices are 32-bit (the launcher checks nvox < 2^35): the per-tile bookkeeping is a handful of
     // integer instructions instead of 64-bit compare / min chains in a kernel that is issue-bound
     constexpr int kSmWarps = kSmThreads / 32;
     const int nwt = (int)((nvox + 31) / 32);
@@ -698,7 +698,8 @@ int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const void* errs, 
         const bool gen2 = c->var_fractal >= 4 && c->var_fractal <= 7;
         const bool recomp = gen2 && (c->var_fractal & 1) != 0;
         const size_t smem2 = recomp ? (size_t)T * VRDD_BINS * sizeof(float) : smem;
-        if (gen2 && smem2 <= 227 * 1024 && nvox < (1ll << 36)) {        // second-generation kernel (moments_voxel2; 32-bit tile indices)
+        if (gen2 && smem2 <= 227 * 1024 && nvox < (1ll << 35)) {        // second-generation kernel (moments_voxel2); its tile indices are
+                                                                         // 32-bit: nvox / 32 plus two grid strides must stay below 2^31
             const bool scan = c->var_fractal <= 5;
             auto kern = scan ? (recomp ? decode_fractal_moments2_kernel<true, true> : decode_fractal_moments2_kernel<true, false>)
                              : (recomp ? decode_fractal_moments2_kernel<false, true> : decode_fractal_moments2_kernel<false, false>);
