@@ -19,6 +19,13 @@
 // it hard-codes (:96-101) and dataProcessing() is skipped (its span tables do not ship) — unless the fifth argument
 // is "flex": then <dir>/in/flex_*.{i32,f32} hold span tables of those sizes, dataProcessing() runs as main() runs it,
 // and out/flex_dims.i32, out/flex_blocks.f32 and the frames of queryMethod 8, 9, 0 are written as well.
+// Mode "flexscrub" launches the kernels of dataProcessing() itself, in its order and with its launch shapes
+// (volumeRender_kernel.cu:1751-1794), with one kernel of this file in between: right before d_querySpanNew every
+// thread slot's local memory is zeroed.  flexibleFractalDecoding() returns a pointer to its local array (:224-251) and
+// nvcc keeps only part of the stores into it, so d_querySpanNew reads local memory nobody initialised: after the
+// kernels that ran before it that is their stack garbage ("flex" mode shows it: values like -3.7e19 in the
+// histograms), on scrubbed memory it is zero — the deterministic form of the reference's build, the one its fixed
+// path meets on a fresh context and the one tools/ref_pin_flex.py models.
 // Test infrastructure: only tests/ and tools/ run this binary, never the product.
 #include REF_KERNEL_CU
 
@@ -39,6 +46,13 @@ std::vector<T> read_file(const std::string& path, size_t count) {
     return v;
 }
 
+// zero the local-memory window of every thread slot of the device (a superset of what any reference kernel maps)
+__global__ void scrub_local_memory(int* sink) {
+    volatile float a[1024];
+    for (int i = 0; i < 1024; ++i) a[i] = 0.0f;
+    if (sink && a[threadIdx.x & 1023] != 0.0f) *sink = 1;
+}
+
 void write_file(const std::string& path, const void* p, size_t bytes) {
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f || std::fwrite(p, 1, bytes, f) != bytes) {
@@ -52,7 +66,7 @@ void write_file(const std::string& path, const void* p, size_t bytes) {
 
 int main(int argc, char** argv) {
     if (argc < 5) {
-        std::fprintf(stderr, "usage: ref_driver <dir> <width> <height> <nviews> [time|flex]\n");
+        std::fprintf(stderr, "usage: ref_driver <dir> <width> <height> <nviews> [time|flex|flexscrub [blockSize]]\n");
         return 2;
     }
     const std::string dir = argv[1];
@@ -74,7 +88,8 @@ int main(int argc, char** argv) {
 
     // The flexible-block tables, at the sizes initCuda hard-codes (volumeRender_kernel.cu:96-101: 131 072 spans each,
     // 64 entries per span, 469 templates of 64 bins): zero-filled, or — mode "flex" — read from <dir>/in/flex_*.
-    const bool flex = argc > 5 && std::string(argv[5]) == "flex";
+    const bool scrub = argc > 5 && std::string(argv[5]) == "flexscrub";
+    const bool flex = scrub || (argc > 5 && std::string(argv[5]) == "flex");
     const size_t nspan = 64 * 64 * 32, nent = (size_t)64 * 2048 * 64;
     std::vector<int4> spanLow(nspan, make_int4(0, 0, 0, 0)), spanHigh(spanLow), flexCode(spanLow), simpleLow(spanLow),
         simpleHigh(spanLow);
@@ -99,7 +114,33 @@ int main(int argc, char** argv) {
     if (flex) {
         // main()'s order (volumeRender.cpp:1220-1221): dataProcessing() — block size 6 on the 64^3 raw volume, hard-coded
         // at volumeRender_kernel.cu:1737 and :101 — then basicDataProcessing()
-        dataProcessing();
+        if (!scrub) {
+            dataProcessing();
+        } else {
+            // dataProcessing()'s launches (volumeRender_kernel.cu:1737, 1751-1794), local memory scrubbed before d_querySpanNew
+            // block size: 6 as hard-coded in dataProcessing(), or the 6th argument (the kernels take it as a parameter).
+            // d_querySpanNew runs one 1000-thread CTA per corner; from its second wave on, a CTA inherits the local
+            // memory of the CTA that ran before it on the same SM — the `decoded` arrays of other spans — so only
+            // the first wave (at least 148 CTAs = the corners of 18 blocks) is deterministic.  A block size of 32
+            // (2x2x2 blocks, 64 CTAs) keeps the whole chain inside it.
+            const int blockSize = argc > 6 ? std::atoi(argv[6]) : 6;
+            d_divideBlock<<<1, 1>>>(blockSize, rawVolumeDim);
+            int h_nFlexBlock = 0;
+            checkCudaErrors(cudaMemcpyFromSymbol(&h_nFlexBlock, nFlexBlock, sizeof(int)));
+            d_allocateSpace<<<1, 1>>>(h_nFlexBlock);
+            d_queryBlockNew<<<h_nFlexBlock, 8>>>(rawVolumeDim, blockSize);
+            checkCudaErrors(cudaDeviceSynchronize());
+            int dev = 0, sms = 0;
+            checkCudaErrors(cudaGetDevice(&dev));
+            checkCudaErrors(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            scrub_local_memory<<<sms * 16, 1024>>>(nullptr);
+            checkCudaErrors(cudaDeviceSynchronize());
+            d_querySpanNew<<<h_nFlexBlock * 8, 1000>>>();
+            d_computeBlock<<<h_nFlexBlock, 1>>>();
+            checkCudaErrors(cudaDeviceSynchronize());
+            bindToTex();
+            cleanPointers<<<1, 1>>>(h_nFlexBlock);
+        }
         checkCudaErrors(cudaDeviceSynchronize());
         int nb[4] = {0, 0, 0, 0};
         checkCudaErrors(cudaMemcpyFromSymbol(&nb[0], nFlexBlock, sizeof(int)));
@@ -112,6 +153,10 @@ int main(int argc, char** argv) {
             checkCudaErrors(cudaMemcpyFromSymbol(fb.data(), flexBlockData, sizeof(float4) * nb[0]));
             write_file(dir + "/out/flex_blocks.f32", fb.data(), sizeof(float4) * nb[0]);
         }
+    }
+    if (scrub) {                      // d_basicDataProcessing has the same dangling array (:196-221): give it clean local memory too
+        scrub_local_memory<<<148 * 16, 1024>>>(nullptr);
+        checkCudaErrors(cudaDeviceSynchronize());
     }
     basicDataProcessing();
     checkCudaErrors(cudaDeviceSynchronize());

@@ -297,11 +297,29 @@ inline float saturate(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }  /* NaN -
  * d_render with its default -fmad=true, read off the PTX of the reference compiled where it lies
  * (oracle/Makefile `ref`): u*u + v*v fused, + 4 added, rsqrt; each component of M*dir as
  * fma(dir.z, m.z, fma(dir.x, m.x, dir.y*m.y)); pos = fma(d, tnear, o); sum = fma(col, 1 - sum.w, sum).  rsqrt is
- * the correctly rounded 1/sqrt here (the GPU's rsqrt.approx is within an ulp of it).  The two settings give
+ * the GPU's rsqrt.approx.f32 looked up in a table dumped on a B200 (g_rsqrt_delta below; the correctly rounded
+ * 1/sqrt, within two ulps of it, when no table is installed).  The two settings give
  * the same frames to +-1 LSB in queryMethod 1..6; queryMethod 7 amplifies the last bit of a position wherever a
  * sample sits on a cell boundary (its "vertical and horizontal line" artefact, ver1.9.6.txt:166), and only
  * setting 1 reproduces the frames of the reference's own binary there (tests/test_reference_pin.py). */
 static int g_fma_contract = 0;
+/* rsqrt.approx.f32 as the B200 computes it, for every float of [lo, hi] (the argument u*u + v*v + 4 of the eye ray's
+ * normalize() lies in [4, 6]): distance in ulps from (float)(1.0 / sqrt((double)x)), dumped on the GPU by
+ * tools/rsqrt_dump.cu (tests/golden/rsqrt_approx_b200_v1.npz).  With it setting 1 reproduces the ray set-up of the
+ * reference's own binary BIT FOR BIT; without it (or outside the interval) the correctly rounded value stands in. */
+static std::vector<int8_t> g_rsqrt_delta;
+static uint32_t g_rsqrt_lo = 0;
+inline float rsqrt_as_the_gpu(float x) {
+    float r = (float)(1.0 / std::sqrt((double)x));
+    uint32_t xb, rb;
+    std::memcpy(&xb, &x, 4);
+    if (!g_rsqrt_delta.empty() && xb >= g_rsqrt_lo && (size_t)(xb - g_rsqrt_lo) < g_rsqrt_delta.size()) {
+        std::memcpy(&rb, &r, 4);
+        rb = (uint32_t)((int64_t)rb + g_rsqrt_delta[xb - g_rsqrt_lo]);
+        std::memcpy(&r, &rb, 4);
+    }
+    return r;
+}
 
 struct RaySetup { f3 o, d; };
 inline RaySetup make_ray(const float* m12, int x, int y, int imageW, int imageH) {
@@ -317,7 +335,7 @@ inline RaySetup make_ray(const float* m12, int x, int y, int imageW, int imageH)
         R.d = {dot3(dv, r0), dot3(dv, r1), dot3(dv, r2)};                  /* :296, 168-174 */
     } else {
         float dd = fmaf(u, u, v * v) + 4.0f;
-        float inv_len = (float)(1.0 / std::sqrt((double)dd));
+        float inv_len = rsqrt_as_the_gpu(dd);
         f3 dv = {u * inv_len, v * inv_len, inv_len * -2.0f};
         R.d = {fmaf(dv.z, r0.z, fmaf(dv.x, r0.x, dv.y * r0.y)), fmaf(dv.z, r1.z, fmaf(dv.x, r1.x, dv.y * r1.y)),
                fmaf(dv.z, r2.z, fmaf(dv.x, r2.x, dv.y * r2.y))};
@@ -361,6 +379,13 @@ struct vrdd_oracle_render_params {
 
 /* 0 / 1: see g_fma_contract.  Process-wide; returns the previous setting. */
 int vrdd_oracle_set_fma_contract(int on) { const int prev = g_fma_contract; g_fma_contract = on ? 1 : 0; return prev; }
+
+/* Installs (n > 0) or removes (n == 0) the rsqrt.approx table: delta[i] belongs to the float with bit pattern lo_bits + i. */
+void vrdd_oracle_set_rsqrt_table(uint32_t lo_bits, int64_t n, const int8_t* delta) {
+    g_rsqrt_lo = lo_bits;
+    if (n > 0 && delta) g_rsqrt_delta.assign(delta, delta + n);
+    else g_rsqrt_delta.clear();
+}
 
 int vrdd_oracle_num_threads(void) {
 #ifdef _OPENMP

@@ -12,6 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
 
 
 class RenderParams(C.Structure):
@@ -76,6 +77,8 @@ class Oracle:
         L.vrdd_oracle_set_num_threads.argtypes = [C.c_int]
         L.vrdd_oracle_set_fma_contract.argtypes = [C.c_int]
         L.vrdd_oracle_set_fma_contract.restype = C.c_int
+        L.vrdd_oracle_set_rsqrt_table.argtypes = [C.c_uint32, C.c_int64, C.c_void_p]
+        L.vrdd_oracle_set_rsqrt_table.restype = None
         L.vrdd_oracle_decode_hist.argtypes = [_f32p, C.c_int64, C.c_int, _f32p]
         L.vrdd_oracle_decode_fractal.argtypes = [_i32p, _f32p, _f32p, C.c_int, C.c_int64, C.c_int, _f32p,
                                                  C.c_void_p]
@@ -115,6 +118,19 @@ class Oracle:
         reproduce bit for bit; True = nvcc's default contraction of the reference's d_render (vrdd_oracle.cpp,
         g_fma_contract).  Returns the previous setting."""
         return bool(self.lib.vrdd_oracle_set_fma_contract(1 if on else 0))
+
+    def set_reference_build(self, on=True):
+        """Rounding of the reference's own nvcc build for the ray set-up and compositing (the default of libvrdd.so,
+        variant ray_setup = "nvcc"): FMA contraction as in its PTX plus the B200's rsqrt.approx.f32 from
+        tests/golden/rsqrt_approx_b200_v1.npz (tools/rsqrt_dump.cu).  With the table the ray geometry is the
+        binary's bit for bit.  Returns the previous contraction setting."""
+        if on:
+            fx = np.load(os.path.join(_ROOT, "tests", "golden", "rsqrt_approx_b200_v1.npz"))
+            delta = np.ascontiguousarray(fx["delta"], np.int8)
+            self.lib.vrdd_oracle_set_rsqrt_table(int(fx["lo_bits"]), delta.size, delta.ctypes.data)
+        else:
+            self.lib.vrdd_oracle_set_rsqrt_table(0, 0, None)
+        return self.set_fma_contract(on)
 
     # -- synthetic inputs -----------------------------------------------------------
     def synth_histograms(self, seed, dims, bins=32, z0=0, nz=None):

@@ -267,3 +267,75 @@ def test_device_synth_is_bit_identical_to_host_synth(renderer, oracle):
     got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
     ref, _ = oracle.decode_fractal(hcb, herr, oracle.synth_templates(seed, T))
     np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("variant", ["moments", "moments2", "moments2r", "moments_global"])
+def test_fractal_errors_that_cancel_the_template(renderer, oracle, variant):
+    """Errors that remove all, or all but a thousandth, of a template's mass: the corrected sum of the moment table is
+    then rounding noise (about 1e-7 where the reference's tot is exactly 0 and it writes 0, 0, 0), so such voxels must
+    take the in-order dense route.  Templates with 3, 8 and 32 occupied bins; every voxel of the volume is one case."""
+    import vrdd_b200 as V
+    rng = np.random.default_rng(5)
+    T, dims = 6, (32, 4, 2)
+    n = dims[0] * dims[1] * dims[2]
+    tmpl = np.zeros((T, 32), np.float32)
+    for t, k in enumerate((3, 3, 8, 8, 32, 32)):
+        bins = rng.choice(32, k, replace=False)
+        w = rng.random(k).astype(np.float32) + 0.1
+        tmpl[t, bins] = (w / w.sum()).astype(np.float32)
+    cb = np.zeros((n, 4), np.int32)
+    err = np.zeros((n, 32, 2), np.float32)
+    for v in range(n):
+        t, shift, flip = v % T, int(rng.integers(0, 33)), int(rng.integers(0, 2))
+        src = tmpl[t][::-1] if flip else tmpl[t]
+        cur = np.roll(src, shift % 32)
+        nzb = np.nonzero(cur)[0]
+        kind = v % 3
+        keep = nzb[0]
+        k = 0
+        for b in nzb:
+            if kind == 0:
+                val = -cur[b]                                        # exactly cancelled: tot == 0 in the reference
+            elif kind == 1:
+                val = -np.float32(1.5) * cur[b]                      # over-cancelled, clamped to 0: tot == 0
+            else:
+                val = -cur[b] if b != keep else -np.float32(0.999) * cur[b]      # 99.9 % of the bin, the rest gone
+            err[v, k] = (b, val); k += 1
+        cb[v] = (t, shift, flip, k)
+    ref, bad = oracle.decode_fractal(cb, err, tmpl)
+    assert bad == 0
+    assert (ref[0::3, :3] == 0).all() and (ref[1::3, :3] == 0).all()           # the reference's all-zero histogram
+    r = renderer
+    r.set_variant("decode_fractal", variant)
+    r.set_volume(*dims)
+    r.set_fractal_host(cb, err, tmpl)
+    r.decode(V.SRC_FRACTAL)
+    got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
+    assert (got[0::3, :3] == 0).all() and (got[1::3, :3] == 0).all()
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_templates_rewritten_in_place_are_picked_up(renderer, oracle):
+    """vrdd_set_fractal_device with the SAME template pointer after the table was rewritten in place: the moment table
+    derived from it is rebuilt on every call (it used to be keyed on the address)."""
+    import torch
+    import vrdd_b200 as V
+    dims, T = (32, 8, 4), 50
+    n = dims[0] * dims[1] * dims[2]
+    cb, err = oracle.synth_fractal(21, dims, T=T, max_ne=8)
+    ent, off = V.pack_fractal_errors(cb, err)
+    d_cb = torch.from_numpy(cb).cuda()
+    d_er = torch.from_numpy(ent.view(np.uint8).reshape(-1).copy()).cuda()
+    d_off = torch.from_numpy(off.view(np.int64)).cuda()
+    d_tm = torch.empty(T, 32, dtype=torch.float32, device="cuda")
+    r = renderer
+    r.set_volume(*dims)
+    for seed in (3, 4):
+        tmpl = oracle.synth_templates(seed, T)
+        d_tm.copy_(torch.from_numpy(tmpl))                            # same address, new contents
+        torch.cuda.synchronize()
+        r.set_fractal_device(d_cb, d_er, d_off, d_tm, T, 0, dims[2])
+        r.decode(V.SRC_FRACTAL)
+        got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
+        ref, _ = oracle.decode_fractal(cb, err, tmpl)
+        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)

@@ -77,23 +77,22 @@ def test_cuda_decode_and_frames_match_the_reference_binary(renderer, oracle, pin
         r.set_view(pin["views"][k])
         for qm in (4, 5, 6):
             d = _byte_diff(_frame(r, V, w, h, qm), pin["fx"]["images"][k, qm - 1])
-            assert d.max() <= 2 and (d > 1).sum() <= 64 and (d != 0).sum() <= 2000, (k, qm, int(d.max()), int((d > 1).sum()), int((d != 0).sum()))
-    # queryMethod 7: single boundary samples (see test_reference_pin.py); no byte is off by more than one sample
+            assert d.max() <= 1 and (d != 0).sum() <= 2000, (k, qm, int(d.max()), int((d != 0).sum()))
+    # queryMethod 7 amplifies the last bit of a sample position at every cell boundary (see test_reference_pin.py): with
+    # the ray set-up rounded as in the reference's build (the default) no byte is off by more than 1 LSB
     for k in range(pin["views"].shape[0]):
         r.set_view(pin["views"][k])
         d = _byte_diff(_frame(r, V, w, h, 7), pin["fx"]["images"][k, 6])
-        assert d.max() <= 13 and (d > 1).sum() < 0.04 * d.size, (k, int(d.max()), int((d > 1).sum()))
+        assert d.max() <= 1 and (d != 0).sum() <= 16, (k, int(d.max()), int((d != 0).sum()))
 
 
-@pytest.mark.skipif(os.environ.get("VRDD_TEST_RAY_SETUP_NVCC") != "1",
-                    reason="variant ray_setup=nvcc was written after round 1's last GPU run; enable once measured (tools/ref_pin.py cuda)")
-def test_query_method_7_with_the_reference_builds_rounding(renderer, pin):
-    """With the eye ray rounded as in the reference's own build (rsqrt.approx, nvcc's FMA pattern: the same
-    instructions, so the same bits) queryMethod 7 should lose the boundary-sample differences."""
+def test_query_method_7_in_the_sources_uncontracted_order(renderer, pin):
+    """Variant ray_setup = "source" (uncontracted, IEEE 1/sqrt): single boundary samples land on the other side of a
+    cell boundary; no byte is off by more than one sample (13 LSB), fewer than 4 % of the bytes by more than 1."""
     import vrdd_b200 as V
     r = renderer
     r.enable_interpolated_mean(True)
-    r.set_variant("ray_setup", "nvcc")
+    r.set_variant("ray_setup", "source")
     r.set_volume(*pin["dims"])
     r.set_histograms_host(pin["hist"])
     r.decode(V.SRC_ORIGINAL)
@@ -101,4 +100,4 @@ def test_query_method_7_with_the_reference_builds_rounding(renderer, pin):
     for k in range(pin["views"].shape[0]):
         r.set_view(pin["views"][k])
         d = _byte_diff(_frame(r, V, w, h, 7), pin["fx"]["images"][k, 6])
-        assert (d > 1).sum() < 0.002 * d.size, (k, int(d.max()), int((d > 1).sum()))
+        assert d.max() <= 13 and (d > 1).sum() < 0.04 * d.size, (k, int(d.max()), int((d > 1).sum()))

@@ -86,10 +86,11 @@ int ensure_volume_storage(vrdd_context* c, int source) {
     const bool want_brick = c->sampler == VRDD_SAMPLER_BRICKED;
     const bool want_lin = c->keep_linear || c->sampler == VRDD_SAMPLER_LINEAR;
     for (int i = 0; i < 3; ++i) {
-        if (want_tex && !v.arr[i]) {
+        if (want_tex && (!v.arr[i] || !v.tex[i] || !v.surf[i])) {
             cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
-            VRDD_CUDA(c, cudaMalloc3DArray(&v.arr[i], &desc, make_cudaExtent(c->W, c->H, c->D),
-                                           cudaArraySurfaceLoadStore));
+            if (!v.arr[i])
+                VRDD_CUDA(c, cudaMalloc3DArray(&v.arr[i], &desc, make_cudaExtent(c->W, c->H, c->D),
+                                               cudaArraySurfaceLoadStore));
             cudaResourceDesc rd;
             std::memset(&rd, 0, sizeof(rd));
             rd.resType = cudaResourceTypeArray;
@@ -102,8 +103,8 @@ int ensure_volume_storage(vrdd_context* c, int source) {
             td.filterMode = cudaFilterModeLinear;
             td.readMode = cudaReadModeElementType;
             td.normalizedCoords = 1;
-            VRDD_CUDA(c, cudaCreateTextureObject(&v.tex[i], &rd, &td, nullptr));
-            VRDD_CUDA(c, cudaCreateSurfaceObject(&v.surf[i], &rd));
+            if (!v.tex[i]) VRDD_CUDA(c, cudaCreateTextureObject(&v.tex[i], &rd, &td, nullptr));
+            if (!v.surf[i]) VRDD_CUDA(c, cudaCreateSurfaceObject(&v.surf[i], &rd));
         }
         if (want_lin && !v.lin[i]) VRDD_CUDA(c, cudaMalloc(&v.lin[i], sizeof(float) * c->V));
         if (want_brick && !v.brick[i]) {
@@ -116,10 +117,11 @@ int ensure_volume_storage(vrdd_context* c, int source) {
     // else a point-sampled 3-D array; the linear plane is kept in both cases (decode target, fallback).
     const bool want_gather = c->var_mode7 == 2 && c->D <= 2048 && c->W <= 32768 && c->H <= 32768 &&
                              point_rule_is_regular(c->W) && point_rule_is_regular(c->H);
-    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw && want_gather) {
+    // every resource below is created only if it does not exist yet, so a call that failed half-way can be repeated
+    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw && want_gather && !v.mean_gather) {
         cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
         // (cudaArrayTextureGather is rejected together with cudaArrayLayered; tld4.a2d itself does not need it)
-        if (cudaMalloc3DArray(&v.mean_lay, &desc, make_cudaExtent(c->W, c->H, c->D), cudaArrayLayered) == cudaSuccess) {
+        if (v.mean_lay || cudaMalloc3DArray(&v.mean_lay, &desc, make_cudaExtent(c->W, c->H, c->D), cudaArrayLayered) == cudaSuccess) {
             cudaResourceDesc rd;
             std::memset(&rd, 0, sizeof(rd));
             rd.resType = cudaResourceTypeArray;
@@ -136,10 +138,10 @@ int ensure_volume_storage(vrdd_context* c, int source) {
             v.mean_lay = nullptr;
         }
     }
-    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw && !v.mean_lay) {
+    if (c->keep_mean_raw && source == VRDD_SRC_ORIGINAL && !v.mean_raw && !v.mean_lay && !v.mean_tex) {
         // point-sampled, un-normalised coordinates: texel (x, y, z) is fetched at (x + .5, y + .5, z + .5)
         cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
-        VRDD_CUDA(c, cudaMalloc3DArray(&v.mean_arr, &desc, make_cudaExtent(c->W, c->H, c->D), 0));
+        if (!v.mean_arr) VRDD_CUDA(c, cudaMalloc3DArray(&v.mean_arr, &desc, make_cudaExtent(c->W, c->H, c->D), 0));
         cudaResourceDesc rd;
         std::memset(&rd, 0, sizeof(rd));
         rd.resType = cudaResourceTypeArray;
@@ -224,7 +226,7 @@ int vrdd_create(int device, vrdd_handle* out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return VRDD_ERR_NO_DEVICE; }
     c->num_sms = prop.multiProcessorCount;
-    if (prop.major < 10) {
+    if (prop.major != 10 || prop.minor != 0) {       // arch-specific ("a") code runs on exactly this compute capability
         std::fprintf(stderr, "libvrdd: device %d is sm_%d%d; this library is built for sm_100a only\n", device,
                      prop.major, prop.minor);
         delete c;
@@ -387,6 +389,8 @@ int vrdd_set_fractal_host(vrdd_handle h, const int32_t* codebook, const float* e
     if (c->off_owned) cudaFree(c->off_owned);
     if (c->tmpl_owned) cudaFree(c->tmpl_owned);
     c->cb_owned = nullptr; c->err_owned = nullptr; c->off_owned = nullptr; c->tmpl_owned = nullptr;
+    // nothing may keep pointing at the freed buffers if one of the calls below fails
+    c->cb = nullptr; c->errs = nullptr; c->err_off = nullptr; c->tmpl = nullptr; c->fr_nz = 0; c->num_templates = 0;
     VRDD_CUDA(c, cudaMalloc(&c->cb_owned, sizeof(int32_t) * 4 * V));
     VRDD_CUDA(c, cudaMalloc(&c->err_owned, sizeof(vrdd_error_entry) * compact.size()));
     VRDD_CUDA(c, cudaMalloc(&c->off_owned, sizeof(uint64_t) * (nchunks + 1)));
@@ -414,12 +418,12 @@ int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const vrdd
     if (((reinterpret_cast<uintptr_t>(d_codebook) | reinterpret_cast<uintptr_t>(d_templates)) & 15u) != 0 ||
         (reinterpret_cast<uintptr_t>(d_errors) & 7u) != 0)
         return fail(c, VRDD_ERR_INVALID, "set_fractal_device: misaligned pointer");
-    const bool same_table = c->tmpl == d_templates && c->num_templates == num_templates && c->tmpl_mom;
     c->cb = d_codebook; c->errs = d_errors; c->err_off = d_chunk_offsets; c->tmpl = d_templates;
     c->num_templates = num_templates; c->fr_z0 = z0; c->fr_nz = nz;
-    // slabs of one volume share the template table: its prefix moments are built once per pointer;
-    // call vrdd_set_fractal_device again with a different pointer (or after vrdd_set_volume) to rebuild
-    return same_table ? VRDD_OK : build_template_moments(c, d_templates, num_templates);
+    // The per-(template, flip, shift) moment table is rebuilt on EVERY call: it is keyed on the table's contents, and a
+    // pointer tells nothing about those (a caller may rewrite the templates in place, or an allocator may hand the
+    // same address out again).  T x 64 threads: microseconds next to a slab decode.
+    return build_template_moments(c, d_templates, num_templates);
 }
 
 int vrdd_set_sampler(vrdd_handle h, int sampler) {

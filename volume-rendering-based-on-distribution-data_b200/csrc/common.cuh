@@ -167,6 +167,62 @@ __device__ __forceinline__ float fast_log2(float x) {
 }
 __device__ __forceinline__ float plog2p(float p) { return p * fast_log2(fmaxf(p, 1.0e-37f)); }
 
+// ---- eye ray of a pixel (volumeRender_kernel.cu:282-312, intersectBox :136-156, mul :168-184) -----------------
+// Shared by every ray kernel (raycast.cu, sortlast.cu, flex.cu), so all of them — and every rank — agree bit for bit
+// on direction, tnear, tfar and the first sample position.  Two roundings, chosen at run time:
+//   ref_rounding = 1 (default, variant ray_setup = "nvcc"): what nvcc 12.9 generates for the reference's d_render
+//     with its default -fmad=true, read off the PTX of the reference compiled where it lies (oracle/Makefile `ref`):
+//     u*u + v*v fused, + 4, rsqrt.approx (helper_math.h normalize()); each component of M*dir as
+//     fma(dir.z, m.z, fma(dir.x, m.x, dir.y*m.y)); pos = fma(d, tnear, o).  These are the instructions of the
+//     reference's own binary, hence its bits: measured on a B200 against tests/golden/ref_gpu_v1.npz, queryMethod 7
+//     (which amplifies the last bit of a position at every cell boundary) has no byte off by more than 1 LSB with
+//     this rounding and 3-4 % of its bytes off with the other one.
+//   ref_rounding = 0 ("source"): the source's expressions without contraction and with an IEEE 1/sqrt — the
+//     oracle's default order.
+// The slab test is the same in both: IEEE reciprocals and products, as in the reference's PTX.
+struct EyeRay { float ox, oy, oz, dx, dy, dz, tnear, tfar; };      // tnear not yet clamped to 0 (:305-306)
+__device__ __forceinline__ EyeRay eye_ray(const float* m, int x, int y, int iw, int ih, int ref_rounding) {
+    EyeRay R;
+    const float u = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)iw), 2.0f), 1.0f);     // :288 (the same value fused or not)
+    const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)ih), 2.0f), 1.0f);
+    R.ox = m[3]; R.oy = m[7]; R.oz = m[11];
+    if (ref_rounding) {
+        const float dd = __fadd_rn(fmaf(u, u, __fmul_rn(v, v)), 4.0f);
+        float inv;
+        asm("rsqrt.approx.f32 %0, %1;" : "=f"(inv) : "f"(dd));                            // as in the reference's build
+        const float a = __fmul_rn(u, inv), b = __fmul_rn(v, inv), c = __fmul_rn(inv, -2.0f);
+        R.dx = fmaf(c, m[2], fmaf(a, m[0], __fmul_rn(b, m[1])));
+        R.dy = fmaf(c, m[6], fmaf(a, m[4], __fmul_rn(b, m[5])));
+        R.dz = fmaf(c, m[10], fmaf(a, m[8], __fmul_rn(b, m[9])));
+    } else {
+        float dx0 = u, dy0 = v, dz0 = -2.0f;
+        const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
+        const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
+        dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
+        R.dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, m[0]), __fmul_rn(dy0, m[1])), __fmul_rn(dz0, m[2]));
+        R.dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, m[4]), __fmul_rn(dy0, m[5])), __fmul_rn(dz0, m[6]));
+        R.dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, m[8]), __fmul_rn(dy0, m[9])), __fmul_rn(dz0, m[10]));
+    }
+    // slab test against [-1,1]^3 (:136-156)
+    const float ix = __fdiv_rn(1.0f, R.dx), iy = __fdiv_rn(1.0f, R.dy), iz = __fdiv_rn(1.0f, R.dz);
+    const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, R.ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, R.ox));
+    const float by0 = __fmul_rn(iy, __fsub_rn(-1.0f, R.oy)), by1 = __fmul_rn(iy, __fsub_rn(1.0f, R.oy));
+    const float bz0 = __fmul_rn(iz, __fsub_rn(-1.0f, R.oz)), bz1 = __fmul_rn(iz, __fsub_rn(1.0f, R.oz));
+    const float tminx = fminf(bx1, bx0), tminy = fminf(by1, by0), tminz = fminf(bz1, bz0);
+    const float tmaxx = fmaxf(bx1, bx0), tmaxy = fmaxf(by1, by0), tmaxz = fmaxf(bz1, bz0);
+    R.tnear = fmaxf(fmaxf(tminx, tminy), fmaxf(tminx, tminz));
+    R.tfar = fminf(fminf(tmaxx, tmaxy), fminf(tmaxx, tmaxz));
+    return R;
+}
+// first sample position o + d * tnear (:311)
+__device__ __forceinline__ void eye_ray_start(const EyeRay& R, float tnear, int ref_rounding, float& px, float& py, float& pz) {
+    if (ref_rounding) {
+        px = fmaf(R.dx, tnear, R.ox); py = fmaf(R.dy, tnear, R.oy); pz = fmaf(R.dz, tnear, R.oz);
+    } else {
+        px = __fadd_rn(R.ox, __fmul_rn(R.dx, tnear)); py = __fadd_rn(R.oy, __fmul_rn(R.dy, tnear)); pz = __fadd_rn(R.oz, __fmul_rn(R.dz, tnear));
+    }
+}
+
 }  // namespace vrdd
 
 struct vrdd_flex_state;                  // flexible-block chain (flex.cu)
@@ -248,7 +304,7 @@ struct vrdd_context {
     int var_decode_order = 1;        // tma tile order: 0 interleaved over CTAs, 1 one contiguous run per CTA (TLB-friendly, default)
     int var_tf = 1;                  // 0 texture unit, 1 shared-memory table (default: frees the TEX pipe)
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
-    int var_ray_setup = 0;           // 0 "source": the oracle's uncontracted order (default); 1 "nvcc": the rounding of the reference's own build (raycast.cu, ray_dir_nvcc)
+    int var_ray_setup = 1;           // 1 "nvcc" (default): the rounding of the reference's own build; 0 "source": the source's uncontracted order (eye_ray above)
     int var_mode7 = 2;               // 2 layered array + tld4 where the volume allows it (default), 0 point-sampled 3-D array, 1 linear plane
     int var_fractal_pf = 12;         // moments2: 128-byte lines of the next tile's errors prefetched into L2 (0..32)
     int var_fractal = 4;             // 0 dense (O(B) per voxel); moments (O(NE) per voxel): 1 r1f kernel, 2 tables in global memory,

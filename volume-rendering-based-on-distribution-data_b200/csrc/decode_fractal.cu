@@ -251,6 +251,12 @@ __device__ __forceinline__ void moments_voxel(const float2* __restrict__ row, co
     const float bw = VRDD_MAX_HISTOGRAM / (float)VRDD_BINS;
     mean_n = 0.f; var_n = 0.f; ent_n = 0.f;
     const float A0 = ent.z + d0;
+    // Heavy cancellation: when the errors remove (nearly) all of the template's mass, A0 = table sum (fp64, rounded) +
+    // sequential fp32 corrections is rounding noise — about 1e-7 where the reference's tot is 0 (it then writes
+    // 0, 0, 0; 1/1e-7 here would give garbage), or a small value with too few correct digits: the noise is ~1e-7 of
+    // the mass, so below 1/64 of the mass the 2e-5 tolerance of the statistics is at risk.  Such voxels take the
+    // reference's in-order dense route below, like the voxels with a bin hit twice.
+    if (A0 <= 0.015625f * (ent.z + fabsf(d0)) && (ent.z + fabsf(d0)) > 0.f) dup |= 0x80000000u;
     if (!dup && A0 > 0.f) {
         float inv;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(A0));   // one MUFU.RCP, 1 ulp; A0 is a sum of frequencies, ~1
@@ -521,11 +527,13 @@ __device__ __forceinline__ void moments_voxel2(const typename RowT<RECOMP>::type
             off += __popc(m);
         }
     }
-    const bool dup = __popc(touched) != ne;      // NE distinct bins set NE bits (bins are in [0, 32), see moments_voxel)
-
     const float bw = VRDD_MAX_HISTOGRAM / (float)VRDD_BINS;
     mean_n = 0.f; var_n = 0.f; ent_n = 0.f;
     const float A0 = ent.z + d0;
+    // NE distinct bins set NE bits (bins are in [0, 32), see moments_voxel); a bin hit twice, or errors that cancel
+    // (nearly) all of the template's mass (A0 is then rounding noise, see moments_voxel), take the dense route
+    const float mass = ent.z + fabsf(d0);
+    const bool dup = (__popc(touched) != ne) || (A0 <= 0.015625f * mass && mass > 0.f);
     if (!dup && A0 > 0.f) {
         float inv;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(A0));

@@ -189,6 +189,7 @@ struct FlexRayArgs {
     float m[12];
     float density, brightness, t_offset, t_scale, tstep, thresh;
     int max_steps, clear_misses;
+    int ref_rounding;               // ray set-up rounded like the reference's nvcc build (common.cuh, eye_ray)
     unsigned long long* samples;
 };
 
@@ -223,27 +224,14 @@ __global__ void __launch_bounds__(256) raycast_flex_kernel(const FlexRayArgs A) 
     const int x = bx * 16 + (warp & 1) * 8 + (lane & 7), y = by * 16 + (warp >> 1) * 4 + (lane >> 3);
     unsigned long long nsamp = 0;
     if (x < A.iw && y < A.ih) {
-        const float u = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)A.iw), 2.0f), 1.0f);
-        const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)A.ih), 2.0f), 1.0f);
-        const float ox = A.m[3], oy = A.m[7], oz = A.m[11];
-        float dx0 = u, dy0 = v, dz0 = -2.0f;
-        const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
-        const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
-        dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
-        const float dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[0]), __fmul_rn(dy0, A.m[1])), __fmul_rn(dz0, A.m[2]));
-        const float dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[4]), __fmul_rn(dy0, A.m[5])), __fmul_rn(dz0, A.m[6]));
-        const float dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[8]), __fmul_rn(dy0, A.m[9])), __fmul_rn(dz0, A.m[10]));
-        const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
-        const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, ox));
-        const float by0 = __fmul_rn(iy, __fsub_rn(-1.0f, oy)), by1 = __fmul_rn(iy, __fsub_rn(1.0f, oy));
-        const float bz0 = __fmul_rn(iz, __fsub_rn(-1.0f, oz)), bz1 = __fmul_rn(iz, __fsub_rn(1.0f, oz));
-        float tnear = fmaxf(fmaxf(fminf(bx1, bx0), fminf(by1, by0)), fmaxf(fminf(bx1, bx0), fminf(bz1, bz0)));
-        const float tfar = fminf(fminf(fmaxf(bx1, bx0), fmaxf(by1, by0)), fminf(fmaxf(bx1, bx0), fmaxf(bz1, bz0)));
+        const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
+        const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
+        float tnear = R.tnear;
         if (tfar > tnear) {
             if (tnear < 0.0f) tnear = 0.0f;
             float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, t = tnear;
-            float px = __fadd_rn(ox, __fmul_rn(dx, tnear)), py = __fadd_rn(oy, __fmul_rn(dy, tnear)),
-                  pz = __fadd_rn(oz, __fmul_rn(dz, tnear));
+            float px, py, pz;
+            eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);
             const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
             for (int i = 0; i < A.max_steps; ++i) {
                 int ii, jj, kk, a, b, c;                                    // (pos01 * nFlexBlock), un-normalised (:655-657)
@@ -347,6 +335,7 @@ int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const 
     for (int i = 0; i < 12; ++i) A.m[i] = c->view[i];
     A.density = p.density; A.brightness = p.brightness; A.t_offset = p.transfer_offset; A.t_scale = p.transfer_scale;
     A.tstep = p.tstep; A.thresh = p.opacity_threshold; A.max_steps = p.max_steps; A.clear_misses = clear_misses;
+    A.ref_rounding = c->var_ray_setup;
     A.samples = c->d_samples;
     const int grid = ((iw + 15) / 16) * ((ih + 15) / 16);
     if (c->count_samples && c->d_samples) raycast_flex_kernel<true><<<grid, 256, 0, c->stream>>>(A);

@@ -13,11 +13,12 @@
 //   * image-space partitions (tiles, round-robin over ranks) and an optional fused clear
 //     of missed pixels are part of the launch.
 //
-// Ray set-up (eye ray, slab test, first position, step) and the t / pos recurrences use
-// explicitly rounded operations (__fmul_rn / __fadd_rn / __fdiv_rn / __fsqrt_rn) in the
-// oracle's order, so tnear, tfar and every sample position are bit-identical to the
-// oracle's and both sides take the same number of steps.  Compositing is plain fp32 and
-// may contract to FMA; images agree with the oracle within +-1 LSB per channel.
+// Ray set-up (eye ray, slab test, first position: common.cuh, eye_ray) and the t / pos recurrences use
+// explicitly rounded operations, by default with the rounding of the reference's own nvcc build
+// (FMA pattern of its PTX, rsqrt.approx), so tnear, tfar and every sample position are bit-identical
+// to the reference binary's and to the oracle's (Oracle.set_reference_build) and all sides take the
+// same number of steps.  Compositing is plain fp32 and may contract to FMA, as in the reference's
+// build; images agree with the oracle within +-1 LSB per channel.
 //
 // Samplers:
 //   texture — tex3D<float> on a 3-D cudaArray, linear / normalised / clamp: the texture
@@ -47,7 +48,7 @@ struct RayArgs {
     int tile_w, tile_h, tiles_x, part, parts, n_my_tiles;
     int blocks_x, blocks_per_tile;   // 16x16-pixel blocks inside a tile
     int clear_misses;
-    int ref_rounding;                // ray set-up rounded like the reference's nvcc build (see ray_dir_nvcc)
+    int ref_rounding;                // ray set-up rounded like the reference's nvcc build (common.cuh, eye_ray)
     unsigned long long* samples;
 };
 
@@ -109,24 +110,6 @@ __device__ __forceinline__ float sample_bricked(const RayArgs& A, float u, float
     return acc * (1.0f / 256.0f);
 }
 
-// Ray set-up and first sample position with the ROUNDING OF THE REFERENCE'S OWN BUILD (opt-in, variant
-// "ray_setup" = "nvcc"): what nvcc 12.9 generates for d_render with its default -fmad=true, read off the PTX of the
-// reference compiled where it lies (oracle/Makefile `ref`; DESIGN.md §2, finding 2) — u*u + v*v fused, + 4,
-// rsqrt.approx; each component of M*dir as fma(dir.z, m.z, fma(dir.x, m.x, dir.y*m.y)); IEEE reciprocals in the slab
-// test; pos = fma(d, tnear, o).  The default ("source") is the uncontracted order of the oracle, written out with
-// explicitly rounded operations in the kernels.  Only queryMethod 7 can tell the two apart beyond +-1 LSB.
-struct RaySetupRef { float dx, dy, dz; };
-__device__ __forceinline__ RaySetupRef ray_dir_nvcc(const float* m, float u, float v) {
-    const float dd = __fadd_rn(fmaf(u, u, __fmul_rn(v, v)), 4.0f);
-    const float inv = rsqrtf(dd);                                       // rsqrt.approx.f32, as in the reference's build
-    const float a = __fmul_rn(u, inv), b = __fmul_rn(v, inv), c = __fmul_rn(inv, -2.0f);
-    RaySetupRef R;
-    R.dx = fmaf(c, m[2], fmaf(a, m[0], __fmul_rn(b, m[1])));
-    R.dy = fmaf(c, m[6], fmaf(a, m[4], __fmul_rn(b, m[5])));
-    R.dz = fmaf(c, m[10], fmaf(a, m[8], __fmul_rn(b, m[9])));
-    return R;
-}
-
 __device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a) {
     // saturate, scale, truncate, pack (volumeRender_kernel.cu:186-193)
     return ((uint32_t)(__saturatef(a) * 255.0f) << 24) | ((uint32_t)(__saturatef(b) * 255.0f) << 16) |
@@ -162,36 +145,17 @@ __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
     unsigned long long nsamp = 0;
 
     if (lx < A.tile_w && ly < A.tile_h && x < A.iw && y < A.ih) {
-        // ---- eye ray (volumeRender_kernel.cu:288-296), explicitly rounded --------------
-        const float u = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)A.iw), 2.0f), 1.0f);
-        const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)A.ih), 2.0f), 1.0f);
-        const float ox = A.m[3], oy = A.m[7], oz = A.m[11];
-        float dx0 = u, dy0 = v, dz0 = -2.0f;
-        const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
-        const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
-        dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
-        float dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[0]), __fmul_rn(dy0, A.m[1])), __fmul_rn(dz0, A.m[2]));
-        float dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[4]), __fmul_rn(dy0, A.m[5])), __fmul_rn(dz0, A.m[6]));
-        float dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[8]), __fmul_rn(dy0, A.m[9])), __fmul_rn(dz0, A.m[10]));
-        if (A.ref_rounding) { const RaySetupRef R = ray_dir_nvcc(A.m, u, v); dx = R.dx; dy = R.dy; dz = R.dz; }
-        // ---- slab test against [-1,1]^3 (:136-156) --------------------------------------
-        const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
-        const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, ox));
-        const float by0 = __fmul_rn(iy, __fsub_rn(-1.0f, oy)), by1 = __fmul_rn(iy, __fsub_rn(1.0f, oy));
-        const float bz0 = __fmul_rn(iz, __fsub_rn(-1.0f, oz)), bz1 = __fmul_rn(iz, __fsub_rn(1.0f, oz));
-        const float tminx = fminf(bx1, bx0), tminy = fminf(by1, by0), tminz = fminf(bz1, bz0);
-        const float tmaxx = fmaxf(bx1, bx0), tmaxy = fmaxf(by1, by0), tmaxz = fmaxf(bz1, bz0);
-        float tnear = fmaxf(fmaxf(tminx, tminy), fmaxf(tminx, tminz));
-        const float tfar = fminf(fminf(tmaxx, tmaxy), fminf(tmaxx, tmaxz));
+        // ---- eye ray, slab test (volumeRender_kernel.cu:288-303): common.cuh, eye_ray ---------
+        const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
+        const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
+        float tnear = R.tnear;
 
         if (tfar > tnear) {
             if (tnear < 0.0f) tnear = 0.0f;                                          // :305-306
             float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
             float t = tnear;
-            float px = __fadd_rn(ox, __fmul_rn(dx, tnear));                          // :311
-            float py = __fadd_rn(oy, __fmul_rn(dy, tnear));
-            float pz = __fadd_rn(oz, __fmul_rn(dz, tnear));
-            if (A.ref_rounding) { px = fmaf(dx, tnear, ox); py = fmaf(dy, tnear, oy); pz = fmaf(dz, tnear, oz); }
+            float px, py, pz;
+            eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);                     // :311
             const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
             int i = 0;
             bool alive = A.max_steps > 0;                 // the geometric state (i, t, p) is a live step
@@ -309,7 +273,7 @@ struct Mode7Args {
     float density, brightness, t_offset, t_scale, tstep, thresh;
     int max_steps, clear_misses;
     int use_tab, idx32;
-    int ref_rounding;                // ray set-up rounded like the reference's nvcc build (see ray_dir_nvcc)
+    int ref_rounding;                // ray set-up rounded like the reference's nvcc build (common.cuh, eye_ray)
     unsigned long long* samples;
 };
 
@@ -357,29 +321,14 @@ __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Arg
     const int x = bx * 16 + (warp & 1) * 8 + (lane & 7), y = by * 16 + (warp >> 1) * 4 + (lane >> 3);
     unsigned long long nsamp = 0;
     if (x < A.iw && y < A.ih) {
-        const float u = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)A.iw), 2.0f), 1.0f);
-        const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)A.ih), 2.0f), 1.0f);
-        const float ox = A.m[3], oy = A.m[7], oz = A.m[11];
-        float dx0 = u, dy0 = v, dz0 = -2.0f;
-        const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
-        const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
-        dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
-        float dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[0]), __fmul_rn(dy0, A.m[1])), __fmul_rn(dz0, A.m[2]));
-        float dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[4]), __fmul_rn(dy0, A.m[5])), __fmul_rn(dz0, A.m[6]));
-        float dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, A.m[8]), __fmul_rn(dy0, A.m[9])), __fmul_rn(dz0, A.m[10]));
-        if (A.ref_rounding) { const RaySetupRef R = ray_dir_nvcc(A.m, u, v); dx = R.dx; dy = R.dy; dz = R.dz; }
-        const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
-        const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, ox));
-        const float by0 = __fmul_rn(iy, __fsub_rn(-1.0f, oy)), by1 = __fmul_rn(iy, __fsub_rn(1.0f, oy));
-        const float bz0 = __fmul_rn(iz, __fsub_rn(-1.0f, oz)), bz1 = __fmul_rn(iz, __fsub_rn(1.0f, oz));
-        float tnear = fmaxf(fmaxf(fminf(bx1, bx0), fminf(by1, by0)), fmaxf(fminf(bx1, bx0), fminf(bz1, bz0)));
-        const float tfar = fminf(fminf(fmaxf(bx1, bx0), fmaxf(by1, by0)), fminf(fmaxf(bx1, bx0), fmaxf(bz1, bz0)));
+        const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
+        const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
+        float tnear = R.tnear;
         if (tfar > tnear) {
             if (tnear < 0.0f) tnear = 0.0f;
             float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, t = tnear;
-            float px = __fadd_rn(ox, __fmul_rn(dx, tnear)), py = __fadd_rn(oy, __fmul_rn(dy, tnear)),
-                  pz = __fadd_rn(oz, __fmul_rn(dz, tnear));
-            if (A.ref_rounding) { px = fmaf(dx, tnear, ox); py = fmaf(dy, tnear, oy); pz = fmaf(dz, tnear, oz); }
+            float px, py, pz;
+            eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);
             const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
             const float fW = (float)A.W, fH = (float)A.H, fD = (float)A.D;
             // The reference keeps the eight corner means of the current cell and refreshes them when a sample

@@ -47,6 +47,7 @@ struct BrickArgs {
     float m[12];
     float density, t_offset, t_scale, tstep, thresh;
     int max_steps;
+    int ref_rounding;               // ray set-up rounded like the reference's nvcc build (common.cuh, eye_ray)
     const float* alpha_in;          // pass 2
     float* alpha_seg;               // pass 1 out
     float4* partial;                // pass 2 out
@@ -130,29 +131,13 @@ __device__ __forceinline__ float4 tf_lookup(const float4* tab, int n, float u) {
     return make_float4(w0 * c0.x + w1 * c1.x, w0 * c0.y + w1 * c1.y, w0 * c0.z + w1 * c1.z, w0 * c0.w + w1 * c1.w);
 }
 
-// Eye ray of pixel (x, y): the same explicitly rounded operations as raycast.cu, so every rank
-// and the single-GPU kernel agree bit for bit on direction, tnear and tfar.
+// Eye ray of pixel (x, y): common.cuh, eye_ray — the same function as raycast.cu, so every rank and the
+// single-GPU kernel agree bit for bit on direction, tnear and tfar.
 struct RaySetup { float ox, oy, oz, dx, dy, dz, tnear, tfar; bool hit; };
-__device__ __forceinline__ RaySetup make_ray(const float* m, int x, int y, int iw, int ih) {
+__device__ __forceinline__ RaySetup make_ray(const float* m, int x, int y, int iw, int ih, int ref_rounding) {
+    const EyeRay E = eye_ray(m, x, y, iw, ih, ref_rounding);
     RaySetup R;
-    const float u = __fsub_rn(__fmul_rn(__fdiv_rn((float)x, (float)iw), 2.0f), 1.0f);
-    const float v = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)ih), 2.0f), 1.0f);
-    R.ox = m[3]; R.oy = m[7]; R.oz = m[11];
-    float dx0 = u, dy0 = v, dz0 = -2.0f;
-    const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(dx0, dx0), __fmul_rn(dy0, dy0)), __fmul_rn(dz0, dz0));
-    const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(len2));
-    dx0 = __fmul_rn(dx0, inv_len); dy0 = __fmul_rn(dy0, inv_len); dz0 = __fmul_rn(dz0, inv_len);
-    R.dx = __fadd_rn(__fadd_rn(__fmul_rn(dx0, m[0]), __fmul_rn(dy0, m[1])), __fmul_rn(dz0, m[2]));
-    R.dy = __fadd_rn(__fadd_rn(__fmul_rn(dx0, m[4]), __fmul_rn(dy0, m[5])), __fmul_rn(dz0, m[6]));
-    R.dz = __fadd_rn(__fadd_rn(__fmul_rn(dx0, m[8]), __fmul_rn(dy0, m[9])), __fmul_rn(dz0, m[10]));
-    const float ix = __fdiv_rn(1.0f, R.dx), iy = __fdiv_rn(1.0f, R.dy), iz = __fdiv_rn(1.0f, R.dz);
-    const float bx0 = __fmul_rn(ix, __fsub_rn(-1.0f, R.ox)), bx1 = __fmul_rn(ix, __fsub_rn(1.0f, R.ox));
-    const float by0 = __fmul_rn(iy, __fsub_rn(-1.0f, R.oy)), by1 = __fmul_rn(iy, __fsub_rn(1.0f, R.oy));
-    const float bz0 = __fmul_rn(iz, __fsub_rn(-1.0f, R.oz)), bz1 = __fmul_rn(iz, __fsub_rn(1.0f, R.oz));
-    const float tminx = fminf(bx1, bx0), tminy = fminf(by1, by0), tminz = fminf(bz1, bz0);
-    const float tmaxx = fmaxf(bx1, bx0), tmaxy = fmaxf(by1, by0), tmaxz = fmaxf(bz1, bz0);
-    R.tnear = fmaxf(fmaxf(tminx, tminy), fmaxf(tminx, tminz));
-    R.tfar = fminf(fminf(tmaxx, tmaxy), fminf(tmaxx, tmaxz));
+    R.ox = E.ox; R.oy = E.oy; R.oz = E.oz; R.dx = E.dx; R.dy = E.dy; R.dz = E.dz; R.tnear = E.tnear; R.tfar = E.tfar;
     R.hit = R.tfar > R.tnear;
     if (R.tnear < 0.0f) R.tnear = 0.0f;
     return R;
@@ -173,15 +158,17 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
     unsigned long long nsamp = 0;
     if (x < A.iw && y < A.ih) {
         const size_t pix = (size_t)y * A.iw + x;
-        const RaySetup R = make_ray(A.m, x, y, A.iw, A.ih);
+        const RaySetup R = make_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
         float sr = 0.f, sg = 0.f, sb = 0.f;
         const float a_in = (PASS == 2) ? A.alpha_in[pix] : 0.f;
         float sa = a_in;
         if (R.hit && !(sa > A.thresh)) {
             float t = R.tnear;
-            float px = __fadd_rn(R.ox, __fmul_rn(R.dx, R.tnear));
-            float py = __fadd_rn(R.oy, __fmul_rn(R.dy, R.tnear));
-            float pz = __fadd_rn(R.oz, __fmul_rn(R.dz, R.tnear));
+            float px, py, pz;
+            {
+                EyeRay E; E.ox = R.ox; E.oy = R.oy; E.oz = R.oz; E.dx = R.dx; E.dy = R.dy; E.dz = R.dz; E.tnear = R.tnear; E.tfar = R.tfar;
+                eye_ray_start(E, R.tnear, A.ref_rounding, px, py, pz);
+            }
             const float stx = __fmul_rn(R.dx, A.tstep), sty = __fmul_rn(R.dy, A.tstep), stz = __fmul_rn(R.dz, A.tstep);
             // Steps that can fall into this brick: slab test of the ray against the brick's box in
             // world coordinates (texcoord c <-> world 2c-1), widened by two steps.  Outside that range
@@ -280,10 +267,10 @@ constexpr int kMaxBricks = 64;
 struct RowWindows { int row0[kMaxBricks]; int rows; };
 __global__ void compose_alpha_in_kernel(const float* __restrict__ seg_rows, int gx, int gy, int gz, int qx, int qy, int qz,
                                         float* __restrict__ alpha_in, int iw, int ih, const ViewMatrix M,
-                                        const RowWindows Wn) {
+                                        const RowWindows Wn, int ref_rounding) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= iw || y >= ih) return;
-    const RaySetup R = make_ray(M.m, x, y, iw, ih);
+    const RaySetup R = make_ray(M.m, x, y, iw, ih, ref_rounding);
     const size_t pix = (size_t)y * iw + x;
     const bool fx = R.dx >= 0.f, fy = R.dy >= 0.f, fz = R.dz >= 0.f;
     const int rqx = fx ? qx : gx - 1 - qx, rqy = fy ? qy : gy - 1 - qy, rqz = fz ? qz : gz - 1 - qz;
@@ -349,7 +336,7 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
     A.iw = iw; A.ih = ih;
     for (int i = 0; i < 12; ++i) A.m[i] = c->view[i];
     A.density = p.density; A.t_offset = p.transfer_offset; A.t_scale = p.transfer_scale; A.tstep = p.tstep;
-    A.thresh = p.opacity_threshold; A.max_steps = p.max_steps;
+    A.thresh = p.opacity_threshold; A.max_steps = p.max_steps; A.ref_rounding = c->var_ray_setup;
     A.alpha_in = d_alpha_in; A.alpha_seg = d_out; A.partial = reinterpret_cast<float4*>(d_out);
     A.samples = c->d_samples;
     const int grid = ((iw + 15) / 16) * ((ih + 15) / 16);
@@ -382,7 +369,7 @@ int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_rows, int gx, in
     ViewMatrix M;
     for (int i = 0; i < 12; ++i) M.m[i] = c->view[i];
     dim3 grid((iw + 127) / 128, ih);
-    compose_alpha_in_kernel<<<grid, 128, 0, c->stream>>>(d_seg_rows, gx, gy, gz, qx, qy, qz, d_alpha_in, iw, ih, M, Wn);
+    compose_alpha_in_kernel<<<grid, 128, 0, c->stream>>>(d_seg_rows, gx, gy, gz, qx, qy, qz, d_alpha_in, iw, ih, M, Wn, c->var_ray_setup);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;
