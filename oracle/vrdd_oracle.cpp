@@ -135,6 +135,8 @@ inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v
 struct Volume4 {
     const float* data;   /* float4[V], x fastest (volumeRender_kernel.cu:740, 771-773) */
     int W, H, D;
+    int stride = 4;      /* floats per texel: 4 = the reference's float4 volume; 1 = ONE component as a plane (the headline
+                            sizes: a 1024^3 float4 volume is 17 GB, its sampled component 4.3 GB) */
 };
 
 inline float tex3d_linear_comp(const Volume4& v, int comp, float u, float vv, float w, int wq) {
@@ -148,7 +150,7 @@ inline float tex3d_linear_comp(const Volume4& v, int comp, float u, float vv, fl
         for (int n = 0; n < 8; ++n) {
             if (wt[n] == 0) continue;                       /* also keeps i+1 == N out of reach */
             int x = i + (n & 1), y = j + ((n >> 1) & 1), z = k + (n >> 2);
-            float t = v.data[4 * ((size_t)x + (size_t)v.W * ((size_t)y + (size_t)v.H * (size_t)z)) + comp];
+            float t = v.data[(size_t)v.stride * ((size_t)x + (size_t)v.W * ((size_t)y + (size_t)v.H * (size_t)z)) + comp];
             acc = acc + ((float)wt[n] * (1.0f / 256.0f)) * t;
         }
         return acc;
@@ -161,7 +163,7 @@ inline float tex3d_linear_comp(const Volume4& v, int comp, float u, float vv, fl
     int j0 = clampi(j, 0, v.H - 1), j1 = clampi(j + 1, 0, v.H - 1);
     int k0 = clampi(k, 0, v.D - 1), k1 = clampi(k + 1, 0, v.D - 1);
     auto T = [&](int x, int y, int z) -> float {
-        return v.data[4 * ((size_t)x + (size_t)v.W * ((size_t)y + (size_t)v.H * (size_t)z)) + comp];
+        return v.data[(size_t)v.stride * ((size_t)x + (size_t)v.W * ((size_t)y + (size_t)v.H * (size_t)z)) + comp];
     };
     /* (1-a)(1-b)(1-c) T000 + ... evaluated as nested lerps, x then y then z */
     float oa = 1.0f - a, ob = 1.0f - b, oc = 1.0f - c;
@@ -492,8 +494,10 @@ int64_t vrdd_oracle_render(const float* vol_original4, const float* vol_fractal4
                            const vrdd_oracle_render_params* P) {
     const f3 boxMin = {-1.0f, -1.0f, -1.0f}, boxMax = {1.0f, 1.0f, 1.0f};
     const int qm = P->query_method;
-    const int comp = (qm - 1) % 3;
-    Volume4 vol = {(qm >= 4) ? vol_fractal4 : vol_original4, W, H, D};
+    /* query_method + 100: the volume argument of that query method is ONE plane float[V] holding its component */
+    const bool planar = qm >= 100;
+    const int comp = planar ? 0 : (qm - 1) % 3;
+    Volume4 vol = {((qm % 100) >= 4) ? vol_fractal4 : vol_original4, W, H, D, planar ? 1 : 4};
     const int imageW = P->image_w, imageH = P->image_h;
     int64_t samples = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : samples)

@@ -187,13 +187,19 @@ class Oracle:
 
     def render(self, vol4, dims, view, image=(512, 512), query_method=1, tf=None, density=0.05,
                brightness=1.0, transfer_offset=0.0, transfer_scale=1.0, tstep=0.01, max_steps=500,
-               opacity_threshold=0.95, weight_quant=3, vol_fractal4=None, rows=None):
-        """Returns (uint32 image[h][w] pre-cleared to 0, sample count)."""
+               opacity_threshold=0.95, weight_quant=3, vol_fractal4=None, rows=None, plane=None):
+        """Returns (uint32 image[h][w] pre-cleared to 0, sample count).  plane: float[V] holding the ONE component
+        query_method samples (instead of the float4 volumes), for volumes whose float4 form is too large."""
         W, H, D = dims
         iw, ih = image
         tf = self.default_transfer_function() if tf is None else np.ascontiguousarray(tf, np.float32)
         vo = None if vol4 is None else np.ascontiguousarray(vol4, np.float32)
         vf = None if vol_fractal4 is None else np.ascontiguousarray(vol_fractal4, np.float32)
+        if plane is not None:
+            plane = np.ascontiguousarray(plane, np.float32)
+            assert plane.size == W * H * D
+            vo, vf = (plane, None) if query_method < 4 else (None, plane)
+            query_method += 100
         out = np.zeros((ih, iw), np.uint32)
         y0, y1 = (0, ih) if rows is None else rows
         P = RenderParams(iw, ih, density, brightness, transfer_offset, transfer_scale, query_method, tstep,

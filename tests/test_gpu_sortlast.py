@@ -28,13 +28,15 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
         d_hist = torch.empty(size[0] * size[1] * size[2], 32, dtype=torch.float32, device="cuda")
         r.synth_histograms_region_device(seed, gdims, origin, 0, size[2], d_hist)
         r.synchronize()
-        sub = hist_full.reshape(gdims[2], gdims[1], gdims[0], 32)[origin[2]:origin[2] + size[2],
-                                                                 origin[1]:origin[1] + size[1],
-                                                                 origin[0]:origin[0] + size[0]].reshape(-1, 32)
-        assert np.array_equal(d_hist.cpu().numpy(), sub)          # brick == sub-box of the whole, bit for bit
+        if hist_full is not None:
+            sub = hist_full.reshape(gdims[2], gdims[1], gdims[0], 32)[origin[2]:origin[2] + size[2],
+                                                                     origin[1]:origin[1] + size[1],
+                                                                     origin[0]:origin[0] + size[0]].reshape(-1, 32)
+            assert np.array_equal(d_hist.cpu().numpy(), sub)          # brick == sub-box of the whole, bit for bit
         r.set_histograms_device(d_hist, 0, size[2])
         r.decode(V.SRC_ORIGINAL)
         r.synchronize()
+        del d_hist
         r.set_view(view)
         br = V.Brick(gdims[0], gdims[1], gdims[2], origin[0], origin[1], origin[2], (V.C.c_float * 3)(*lo),
                      (V.C.c_float * 3)(*hi))
