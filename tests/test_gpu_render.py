@@ -413,3 +413,77 @@ def test_peer_visible_frame_roundtrip(renderer, golden):
     got = V.as_torch(p, (h, w), typestr="<i4").cpu().numpy().view(np.uint32)
     assert _lsb_diff(got, golden["images"][0]).max() <= 1
     r.frame_free(p)
+
+
+@pytest.mark.parametrize("layout", ["layers_x", "layers_y"])
+@pytest.mark.parametrize("dims,img,rot", [((50, 50, 10), (256, 256), (0.0, 0.0)),
+                                          ((33, 47, 29), (250, 130), (40.0, 115.0)),     # ragged volume and image
+                                          ((64, 64, 64), (256, 256), (-20.0, 300.0)),
+                                          ((40, 24, 72), (192, 160), (0.0, 90.0))])      # rays along x: the case the copies are for
+def test_sector_aligned_layouts_give_the_same_frames(renderer, oracle, layout, dims, img, rot):
+    """variant raycast_layout = layers_x | layers_y: the plane as a layered copy stacked along x / y, raw texels by tld4
+    and the texture unit's integer weights in the kernel (raycast_gather_kernel).  Same samples as the 3-D array path: within
+    +-1 LSB of the oracle, the same sample counts, and nearly every byte equal to the texture unit's frame (the two
+    differ in the fp32 summation order of the eight weighted texels only)."""
+    import vrdd_b200 as V
+    hist = oracle.synth_histograms(78, dims)
+    r = renderer
+    r.set_volume(*dims)
+    r.set_histograms_host(hist)
+    cb, err = oracle.synth_fractal(78, dims, T=50)
+    tmpl = oracle.synth_templates(78, 50)
+    r.set_fractal_host(cb, err, tmpl)
+    r.decode(V.SRC_ORIGINAL)
+    r.decode(V.SRC_FRACTAL)
+    n = hist.shape[0]
+    vol = r.get_decoded_host(V.SRC_ORIGINAL, np.empty((n, 4), np.float32))
+    volf = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
+    view = oracle.view_matrix(*rot)
+    r.set_view(view)
+    r.count_samples(True)
+    for qm, over in ((1, {}), (3, {}), (5, {}), (2, {"density": 0.3, "opacity_threshold": 0.7, "tstep": 0.004, "max_steps": 1000})):
+        ref, s = oracle.render(vol, dims, view, image=img, query_method=qm, vol_fractal4=volf, **over)
+        r.set_variant("raycast_layout", "array")
+        hw = _render(r, V, img[0], img[1], query_method=qm, **over)
+        s_hw = r.get_sample_count()
+        r.set_variant("raycast_layout", layout)
+        got = _render(r, V, img[0], img[1], query_method=qm, **over)
+        s_got = r.get_sample_count()
+        assert _close_counts(s_got, s) and _close_counts(s_got, s_hw)
+        d = _lsb_diff(got, ref)
+        assert d.max() <= 1, (layout, qm, int(d.max()), int((d > 1).sum()))
+        dh = _lsb_diff(got, hw)
+        assert dh.max() <= 1 and (dh != 0).mean() < 0.01, (layout, qm, int(dh.max()), float((dh != 0).mean()))
+        assert (ref != 0).sum() > 0.05 * ref.size
+
+
+def test_sector_layout_is_chosen_per_view_and_follows_a_new_decode(renderer, oracle):
+    """raycast_layout = auto: views along x or y with a coarse step take the layered copy stacked along that axis,
+    frontal and oblique views the 3-D array; the copy is rebuilt after the volume is decoded again; tile partitions
+    compose to the whole frame."""
+    import vrdd_b200 as V
+    dims, img = (96, 64, 80), (200, 160)
+    r = renderer
+    r.set_volume(*dims)
+    r.set_variant("raycast_layout_min_step", "0.3")          # small volume: 0.01 * 48 voxels per step
+    for seed in (5, 6):
+        hist = oracle.synth_histograms(seed, dims)
+        r.set_histograms_host(hist)
+        r.decode(V.SRC_ORIGINAL)
+        vol = r.get_decoded_host(V.SRC_ORIGINAL, np.empty((hist.shape[0], 4), np.float32))
+        for rot in ((0.0, 0.0), (0.0, 90.0), (90.0, 0.0), (35.0, 60.0)):
+            view = oracle.view_matrix(*rot)
+            r.set_view(view)
+            ref, _ = oracle.render(vol, dims, view, image=img)
+            l0 = r.kernel_launches()
+            got = _render(r, V, img[0], img[1], clear=True)
+            assert _lsb_diff(got, ref).max() <= 1, (seed, rot)
+            if rot in ((0.0, 90.0), (90.0, 0.0)):
+                assert r.kernel_launches() - l0 == 2              # the copy is (re)built, then the frame
+            if rot == (0.0, 90.0):
+                acc = np.zeros_like(got)
+                for part in range(3):
+                    acc |= _render(r, V, img[0], img[1], clear=True, part=V.TilePartition(32, 32, part, 3))
+                assert np.array_equal(acc, got)
+            if rot in ((0.0, 0.0), (35.0, 60.0)):
+                assert r.kernel_launches() - l0 == 1

@@ -34,6 +34,12 @@ void free_volume(vrdd_decoded_volume& v) {
         if (v.lin[i]) cudaFree(v.lin[i]);
         if (v.brick[i]) cudaFree(v.brick[i]);
     }
+    for (int i = 0; i < 3; ++i)
+        for (int a = 0; a < 3; ++a) {
+            if (v.gtex[i][a]) cudaDestroyTextureObject(v.gtex[i][a]);
+            if (v.gsurf[i][a]) cudaDestroySurfaceObject(v.gsurf[i][a]);
+            if (v.garr[i][a]) cudaFreeArray(v.garr[i][a]);
+        }
     if (v.mean_raw) cudaFree(v.mean_raw);
     if (v.mean_tex) cudaDestroyTextureObject(v.mean_tex);
     if (v.mean_arr) cudaFreeArray(v.mean_arr);
@@ -484,6 +490,7 @@ int vrdd_decode(vrdd_handle h, int source, int z0, int nz) {
         VRDD_CUDA(c, cudaMemcpy3DAsync(&cp, c->stream));
     }
     if (rc == VRDD_OK) c->vol[source].decoded = true;
+    invalidate_gather_copies(c->vol[source]);
     return rc;
 }
 
@@ -497,6 +504,7 @@ int vrdd_reconstruct_fractal_device(vrdd_handle h, float* d_out) {
     rc = launch_decode_fractal(c, c->cb, c->errs, c->err_off, c->tmpl, c->num_templates, (long long)c->fr_nz * slice,
                                out, d_out);
     if (rc == VRDD_OK) c->vol[VRDD_SRC_FRACTAL].decoded = true;
+    invalidate_gather_copies(c->vol[VRDD_SRC_FRACTAL]);
     return rc;
 }
 
@@ -542,6 +550,7 @@ int vrdd_commit_planes(vrdd_handle h, int source, int z0, int nz) {
         }
     }
     v.decoded = true;
+    invalidate_gather_copies(v);
     return VRDD_OK;
 }
 
@@ -924,6 +933,20 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
     } else if (w == "raycast_unroll") {
         if (v == "1" || v == "2" || v == "4" || v == "8") c->var_unroll = v[0] - '0';
         else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_unroll is 1|2|4|8");
+    } else if (w == "raycast_layout") {
+        if (v == "auto") c->var_layout = 0;
+        else if (v == "array") c->var_layout = 1;
+        else if (v == "layers_x") c->var_layout = 2;
+        else if (v == "layers_y") c->var_layout = 3;
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_layout is auto|array|layers_x|layers_y");
+    } else if (w == "raycast_layout_min_step") {
+        const float f = (float)std::atof(variant);
+        if (!(f >= 0.f)) return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_layout_min_step is a number of voxels >= 0");
+        c->var_layout_min_step = f;
+    } else if (w == "raycast_layout_cos") {
+        const float f = (float)std::atof(variant);
+        if (!(f >= 0.f && f <= 1.f)) return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_layout_cos is in [0, 1]");
+        c->var_layout_cos = f;
     } else if (w == "raycast_tf") {
         if (v == "texture") c->var_tf = 0;
         else if (v == "smem") c->var_tf = 1;

@@ -240,6 +240,15 @@ struct vrdd_decoded_volume {
     cudaTextureObject_t mean_tex = 0;   // queryMethod 7 wants the texture path's 3-D locality (side views)
     cudaArray_t mean_lay = nullptr;  // and as a layered 2-D array (layer = z) read with tld4: the 2x2 (x, y) corners
     cudaTextureObject_t mean_gather = 0;   // of a cell in one fetch (variant raycast_mode7 = gather)
+    // Copies of a plane for the gather path of the ray caster (raycast.cu, raycast_gather_kernel): DRAM delivers whole
+    // 128-byte lines = 8 x 4 x 1 texels of the 3-D array above, thin in z only, so only views along z skip the slices
+    // between two samples.  A copy is a layered 2-D array stacked along x (index 1) or y (index 2), read with tld4,
+    // for views along that axis; it is built lazily from the 3-D array the first time a view selects it and refilled
+    // after the source is decoded again.
+    cudaArray_t garr[3][3] = {};                 // [plane][stacking axis]; [.][0] unused (z = the 3-D array itself)
+    cudaTextureObject_t gtex[3][3] = {};
+    cudaSurfaceObject_t gsurf[3][3] = {};
+    bool gvalid[3][3] = {};
     bool decoded = false;
 };
 
@@ -304,6 +313,10 @@ struct vrdd_context {
     int var_decode_order = 1;        // tma tile order: 0 interleaved over CTAs, 1 one contiguous run per CTA (TLB-friendly, default)
     int var_tf = 1;                  // 0 texture unit, 1 shared-memory table (default: frees the TEX pipe)
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
+    int var_layout = 0;              // array the ray caster samples: 0 auto (per view, launch_raycast), 1 the 3-D array (texture unit
+                                     // filters), 2 / 3 the layered copy stacked along x / y (tld4 + the unit's integer weights in the kernel)
+    float var_layout_min_step = 2.5f;   // auto: a copy only if a ray advances more than this many voxels per step along its stacking axis
+    float var_layout_cos = 0.68f;       // ... and the view direction is within acos(this) of that axis (47 degrees)
     int var_ray_setup = 1;           // 1 "nvcc" (default): the rounding of the reference's own build; 0 "source": the source's uncontracted order (eye_ray above)
     int var_mode7 = 2;               // 2 layered array + tld4 where the volume allows it (default), 0 point-sampled 3-D array, 1 linear plane
     int var_fractal_pf = 12;         // moments2: 128-byte lines of the next tile's errors prefetched into L2 (0..32)
@@ -332,6 +345,7 @@ int build_template_moments(vrdd_context* c, const float* d_tmpl, int T);
 bool point_rule_is_regular(int n);       // raycast.cu: does the point rule map boundary k to texel min(k, n - 1)?
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses);
+void invalidate_gather_copies(vrdd_decoded_volume& v);   // after a decode / commit: the copies no longer match the 3-D arrays
 int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_hist);
 int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int z0, int nz, int32_t* d_cb,
                          vrdd_error_entry* d_err, uint64_t* d_off, float* d_tmpl, uint64_t* total_ne);

@@ -29,6 +29,9 @@
 // with the same filter, chosen with vrdd_set_variant("raycast_tf", ...).
 #include "common.cuh"
 
+#include <cmath>
+#include <cstring>
+
 namespace vrdd {
 
 namespace {
@@ -486,6 +489,184 @@ __global__ void debug_sample_tf_kernel(cudaTextureObject_t tex, const float* __r
     if (i < n) out[i] = tex1D<float4>(tex, u[i]);
 }
 
+
+// ---- gather path: the plane as a layered 2-D array whose LAYERS are stacked along x or y -----------------------
+// What DRAM delivers is the full 128-byte line: 8 (x) x 4 (y) x 1 (z) texels of a CUDA array, 3-D or layered, whatever
+// the load asks for (tools/probe_atom.cu, probe_atom_linear.cu: a random 4-byte read moves 127 B; the L2 fetch-
+// granularity limit changes nothing).  With the reference's fixed step a 1024^3 volume is sampled every 5 voxels
+// along the ray and every ~2 across, so almost every line of the region the rays cross holds a texel of some sample:
+// 64 B per sample, compulsory — EXCEPT when the rays run along the axis the lines are thin in, because then all rays
+// sample the same planes and three slices out of five are never touched (frontal views of the 3-D array, thin in z:
+// 24 B per sample; ncu, profiles/raycast_orbit_r1h.csv).  A copy whose layers are stacked along x (or y) gives the
+// views that look along x (or y) the same advantage.  Only the identity mapping of the axes keeps the texture unit's
+// weight split (z, then x, then y), so on a copy the filter moves into the kernel: the eight raw texels come from
+// two tld4 fetches (one per layer) and are blended with the unit's integer weights, bit for bit the scheme of
+// split_hw / sample_bricked above.
+// AXIS = 1: layers along x — array (x' = y, y' = z, layer = x);  AXIS = 2: layers along y — array (x' = z, y' = x, layer = y).
+__device__ __forceinline__ int split_q(float u, unsigned n256) {
+    // q = 256 * texel + weight of split_hw, without the conversion pipe: 2^23 + trunc(sat(u) * 2^21) in one FFMA.RZ
+    const float r = __fmaf_rz(__saturatef(u), 2097152.0f, 8388608.0f);
+    const unsigned U = __float_as_uint(r) & 0x7fffffu;
+    const long long p = (long long)((unsigned long long)U * n256) + ((1ll << 20) - (128ll << 21));
+    const int q = (int)(p >> 21);
+    return min(max(q, 0), (int)n256 - 256);
+}
+__device__ __forceinline__ float small_int_as_float(int i) {        // 0 <= i < 2^23, without I2F
+    return __uint_as_float(0x4b000000u | (unsigned)i) - 8388608.0f;
+}
+
+struct GatherFetch { float4 l0, l1; int abc; };                      // raw texels of both layers, weights packed a | b<<8 | c<<16
+
+template <int AXIS>
+__device__ __forceinline__ GatherFetch gather_issue(cudaTextureObject_t tex, float cu, float cv, float cw, int W, int H, int D) {
+    const int qx = split_q(cu, (unsigned)W << 8), qy = split_q(cv, (unsigned)H << 8), qz = split_q(cw, (unsigned)D << 8);
+    const int i = qx >> 8, j = qy >> 8, k = qz >> 8;
+    GatherFetch G;
+    G.abc = (qx & 255) | ((qy & 255) << 8) | ((qz & 255) << 16);
+    // texel corner (row index + 1, column index + 1): the 2x2 footprint {idx, idx + 1}^2, clamped at the far edge
+    // (where the weight of the clamped texel is 0: q <= 256 * (N - 1))
+    if (AXIS == 1) {
+        const float gx = small_int_as_float(j + 1), gy = small_int_as_float(k + 1);
+        G.l0 = gather_layer(tex, gx, gy, i);
+        G.l1 = gather_layer(tex, gx, gy, min(i + 1, W - 1));
+    } else {
+        const float gx = small_int_as_float(k + 1), gy = small_int_as_float(i + 1);
+        G.l0 = gather_layer(tex, gx, gy, j);
+        G.l1 = gather_layer(tex, gx, gy, min(j + 1, H - 1));
+    }
+    return G;
+}
+
+// tld4 returns .w = (x', y'), .z = (x'+1, y'), .x = (x', y'+1), .y = (x'+1, y'+1)
+template <int AXIS>
+__device__ __forceinline__ float gather_blend(const GatherFetch& G) {
+    const int a = G.abc & 255, b = (G.abc >> 8) & 255, c = G.abc >> 16;
+    float t000, t100, t010, t110, t001, t101, t011, t111;            // t[x][y][z]
+    if (AXIS == 1) {       // x' = y, y' = z, layer = x
+        t000 = G.l0.w; t010 = G.l0.z; t001 = G.l0.x; t011 = G.l0.y;
+        t100 = G.l1.w; t110 = G.l1.z; t101 = G.l1.x; t111 = G.l1.y;
+    } else {               // x' = z, y' = x, layer = y
+        t000 = G.l0.w; t001 = G.l0.z; t100 = G.l0.x; t101 = G.l0.y;
+        t010 = G.l1.w; t011 = G.l1.z; t110 = G.l1.x; t111 = G.l1.y;
+    }
+    const int z1 = c, z0 = 256 - c;
+    const int x10 = (z0 * a + 128) >> 8, x00 = z0 - x10;
+    const int x11 = (z1 * a + 128) >> 8, x01 = z1 - x11;
+    const int w000 = (x00 * (256 - b) + 128) >> 8, w010 = x00 - w000;
+    const int w110 = (x10 * b + 128) >> 8, w100 = x10 - w110;
+    const int w001 = (x01 * (256 - b) + 128) >> 8, w011 = x01 - w001;
+    const int w111 = (x11 * b + 128) >> 8, w101 = x11 - w111;
+    float acc = (float)w000 * t000;
+    acc = fmaf((float)w010, t010, acc);
+    acc = fmaf((float)w100, t100, acc);
+    acc = fmaf((float)w110, t110, acc);
+    acc = fmaf((float)w001, t001, acc);
+    acc = fmaf((float)w011, t011, acc);
+    acc = fmaf((float)w101, t101, acc);
+    acc = fmaf((float)w111, t111, acc);
+    return acc * (1.0f / 256.0f);
+}
+
+// Same march as raycast_kernel (batches of U steps, in-order compositing with the reference's early exit); only the
+// sampler differs.  RayArgs::vol_tex is the layered copy.
+template <int AXIS, bool COUNT, int U>
+__global__ void __launch_bounds__(kBlock) raycast_gather_kernel(const RayArgs A) {
+    __shared__ float4 tf_s[VRDD_MAX_TF];
+    for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
+    __syncthreads();
+    const int lt = blockIdx.x / A.blocks_per_tile;
+    const int bt = blockIdx.x - lt * A.blocks_per_tile;
+    const int gt = A.part + lt * A.parts;
+    const int ty = gt / A.tiles_x, tx = gt - ty * A.tiles_x;
+    const int by = bt / A.blocks_x, bx = bt - by * A.blocks_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lx = bx * 16 + (warp & 1) * 8 + (lane & 7);
+    const int ly = by * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const int x = tx * A.tile_w + lx, y = ty * A.tile_h + ly;
+    unsigned long long nsamp = 0;
+    if (lx < A.tile_w && ly < A.tile_h && x < A.iw && y < A.ih) {
+        const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
+        const float tfar = R.tfar;
+        float tnear = R.tnear;
+        if (tfar > tnear) {
+            if (tnear < 0.0f) tnear = 0.0f;
+            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
+            float t = tnear;
+            float px, py, pz;
+            eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);
+            const float stx = __fmul_rn(R.dx, A.tstep), sty = __fmul_rn(R.dy, A.tstep), stz = __fmul_rn(R.dz, A.tstep);
+            int i = 0;
+            bool alive = A.max_steps > 0;
+            while (alive) {
+                GatherFetch G[U];
+                bool valid[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    valid[k] = alive;
+                    if (alive) G[k] = gather_issue<AXIS>(A.vol_tex, fmaf(px, 0.5f, 0.5f), fmaf(py, 0.5f, 0.5f), fmaf(pz, 0.5f, 0.5f), A.W, A.H, A.D);
+                    const float tn = __fadd_rn(t, A.tstep);
+                    const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
+                    if (cont) {
+                        t = tn; ++i;
+                        px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+                    }
+                    alive = cont;
+                }
+                float4 col[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    col[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid[k]) col[k] = tf_lookup_smem(tf_s, A.tf_n, (gather_blend<AXIS>(G[k]) - A.t_offset) * A.t_scale);
+                }
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    if (!valid[k]) { alive = false; break; }
+                    if (COUNT) ++nsamp;
+                    float4 c = col[k];
+                    c.w *= A.density;
+                    c.x *= c.w; c.y *= c.w; c.z *= c.w;
+                    const float kk = 1.0f - sa;
+                    sr += c.x * kk; sg += c.y * kk; sb += c.z * kk; sa += c.w * kk;
+                    if (sa > A.thresh) { alive = false; break; }
+                }
+            }
+            A.out[(size_t)y * A.iw + x] = pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);
+        } else if (A.clear_misses) {
+            A.out[(size_t)y * A.iw + x] = 0u;
+        }
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, d);
+        if (lane == 0 && nsamp) atomicAdd(A.samples, nsamp);
+    }
+}
+
+// 3-D array (x fastest) -> layered copy: 32x32 tiles through shared memory, coalesced on both sides.
+// AXIS 1: tiles over (x, y) at fixed z -> copy(x' = y, y' = z, layer = x);  grid = (ceil(W/32), ceil(H/32), D)
+// AXIS 2: tiles over (x, z) at fixed y -> copy(x' = z, y' = x, layer = y);  grid = (ceil(W/32), ceil(D/32), H)
+template <int AXIS>
+__global__ void build_gather_copy_kernel(cudaSurfaceObject_t src, cudaSurfaceObject_t dst, int W, int H, int D) {
+    __shared__ float tile[32][33];
+    const int x0 = blockIdx.x * 32, r0 = blockIdx.y * 32, fixed = blockIdx.z;
+    const int nrow = (AXIS == 1) ? H : D;
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int x = x0 + threadIdx.x, row = r0 + r;
+        if (x < W && row < nrow)
+            tile[r][threadIdx.x] = (AXIS == 1) ? surf3Dread<float>(src, x * 4, row, fixed) : surf3Dread<float>(src, x * 4, fixed, row);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int row = r0 + threadIdx.x, x = x0 + r;                // now the row index is the fast one
+        if (x < W && row < nrow) {
+            if (AXIS == 1) surf2DLayeredwrite(tile[threadIdx.x][r], dst, row * 4, fixed, x);
+            else surf2DLayeredwrite(tile[threadIdx.x][r], dst, row * 4, x, fixed);
+        }
+    }
+}
+
 template <int SAMPLER, int TFMODE, int U>
 void launch_u(bool count, int grid, cudaStream_t st, const RayArgs& A) {
     if (count) raycast_kernel<SAMPLER, TFMODE, true, U><<<grid, kBlock, 0, st>>>(A);
@@ -517,6 +698,89 @@ bool point_rule_is_regular(int n) {
     }
     return true;
 }
+
+
+void invalidate_gather_copies(vrdd_decoded_volume& v) {
+    for (int i = 0; i < 3; ++i)
+        for (int a = 0; a < 3; ++a) v.gvalid[i][a] = false;
+}
+
+namespace {
+
+// The layered copy of plane `comp` with its layers stacked along `axis` (1 = x, 2 = y): created on first use, refilled
+// from the 3-D array after every decode.  Returns VRDD_ERR_UNSUPPORTED when the extents do not fit a layered array.
+int ensure_gather_copy(vrdd_context* c, vrdd_decoded_volume& v, int comp, int axis) {
+    const int nrow = (axis == 1) ? c->H : c->D, ncol = (axis == 1) ? c->D : c->W, nlayer = (axis == 1) ? c->W : c->H;
+    if (nlayer > 2048 || nrow > 32768 || ncol > 32768) return VRDD_ERR_UNSUPPORTED;
+    if (!v.arr[comp] || !v.surf[comp]) return VRDD_ERR_UNSUPPORTED;
+    if (!v.garr[comp][axis]) {
+        cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+        if (cudaMalloc3DArray(&v.garr[comp][axis], &desc, make_cudaExtent(nrow, ncol, nlayer),
+                              cudaArrayLayered | cudaArraySurfaceLoadStore) != cudaSuccess) {
+            cudaGetLastError();
+            v.garr[comp][axis] = nullptr;
+            return VRDD_ERR_UNSUPPORTED;                       // e.g. out of memory: the 3-D array path still works
+        }
+    }
+    cudaResourceDesc rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = v.garr[comp][axis];
+    if (!v.gtex[comp][axis]) {
+        cudaTextureDesc td;
+        std::memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        VRDD_CUDA(c, cudaCreateTextureObject(&v.gtex[comp][axis], &rd, &td, nullptr));
+    }
+    if (!v.gsurf[comp][axis]) VRDD_CUDA(c, cudaCreateSurfaceObject(&v.gsurf[comp][axis], &rd));
+    if (!v.gvalid[comp][axis]) {
+        const dim3 grid((c->W + 31) / 32, (nrow + 31) / 32, (axis == 1) ? c->D : c->H), block(32, 8);
+        if (axis == 1) build_gather_copy_kernel<1><<<grid, block, 0, c->stream>>>(v.surf[comp], v.gsurf[comp][axis], c->W, c->H, c->D);
+        else build_gather_copy_kernel<2><<<grid, block, 0, c->stream>>>(v.surf[comp], v.gsurf[comp][axis], c->W, c->H, c->D);
+        c->launches += 1;
+        VRDD_CUDA(c, cudaGetLastError());
+        v.gvalid[comp][axis] = true;
+    }
+    return VRDD_OK;
+}
+
+// Which array serves this view: 0 = the 3-D array (lines thin in z, filtered by the texture unit: fewest instructions),
+// 1 / 2 = the layered copy stacked along x / y (lines thin in x / y, filtered in the kernel).  Measured over the orbit
+// (tools/bench_layouts.py, 1024^3, tstep 0.01): the copy stacked along x is the faster one from 45 degrees off the z
+// axis on (0.234 against 0.243 ms at 45 degrees, 0.190 against 0.240 ms looking straight along x; 0.245 against 0.213 ms
+// at 39 degrees) — it halves the lines touched when the view is within ~20 degrees of its axis and is no worse in
+// between, where every line of the region the rays cross is touched whatever its shape.  So: the stacking axis the
+// centre ray is most parallel to, if it is within acos(var_layout_cos) = 47 degrees of it and a step advances by more
+// than var_layout_min_step voxels along it (otherwise no slice is ever skipped and the cheaper texture-unit path wins).
+int choose_sector_axis(const vrdd_context* c, const vrdd_render_params& p) {
+    if (c->var_layout == 1) return 0;
+    if (c->var_layout == 2) return 1;
+    if (c->var_layout == 3) return 2;
+    const float dir[2] = {std::fabs(c->view[2]), std::fabs(c->view[6])};       // |x|, |y| of the centre ray (third column of M)
+    const float adv[2] = {dir[0] * p.tstep * 0.5f * (float)c->W, dir[1] * p.tstep * 0.5f * (float)c->H};
+    const int a = dir[0] >= dir[1] ? 0 : 1;
+    if (dir[a] >= c->var_layout_cos && adv[a] > c->var_layout_min_step) return a + 1;
+    return 0;
+}
+
+template <int AXIS>
+void launch_gather(bool count, int grid, cudaStream_t st, const RayArgs& A, int unroll) {
+    if (unroll >= 8) {
+        if (count) raycast_gather_kernel<AXIS, true, 8><<<grid, kBlock, 0, st>>>(A);
+        else raycast_gather_kernel<AXIS, false, 8><<<grid, kBlock, 0, st>>>(A);
+    } else if (unroll <= 2) {
+        if (count) raycast_gather_kernel<AXIS, true, 2><<<grid, kBlock, 0, st>>>(A);
+        else raycast_gather_kernel<AXIS, false, 2><<<grid, kBlock, 0, st>>>(A);
+    } else {
+        if (count) raycast_gather_kernel<AXIS, true, 4><<<grid, kBlock, 0, st>>>(A);
+        else raycast_gather_kernel<AXIS, false, 4><<<grid, kBlock, 0, st>>>(A);
+    }
+}
+
+}  // namespace
 
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses) {
@@ -600,7 +864,17 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
     if (sampler == VRDD_SAMPLER_TEXTURE && !A.vol_tex) return fail(c, VRDD_ERR_INVALID, "render: no texture volume");
     if (sampler == VRDD_SAMPLER_BRICKED && !A.vol_brick) return fail(c, VRDD_ERR_INVALID, "render: no bricked volume");
     if (sampler == VRDD_SAMPLER_TEXTURE) {
-        if (tfm == 0) launch_variant<0, 0>(count, (int)grid, c->stream, A, c->var_unroll);
+        int axis = (tfm == 1) ? choose_sector_axis(c, p) : 0;
+        if (axis != 0) {
+            const int rc = ensure_gather_copy(c, vol, comp, axis);
+            if (rc == VRDD_ERR_UNSUPPORTED && c->var_layout == 0) axis = 0;       // auto: the 3-D array always works
+            else if (rc != VRDD_OK) return rc == VRDD_ERR_UNSUPPORTED ? fail(c, rc, "render: no layered copy for this volume") : rc;
+        }
+        if (axis != 0) {
+            A.vol_tex = vol.gtex[comp][axis];
+            if (axis == 1) launch_gather<1>(count, (int)grid, c->stream, A, c->var_unroll);
+            else launch_gather<2>(count, (int)grid, c->stream, A, c->var_unroll);
+        } else if (tfm == 0) launch_variant<0, 0>(count, (int)grid, c->stream, A, c->var_unroll);
         else launch_variant<0, 1>(count, (int)grid, c->stream, A, c->var_unroll);
     } else {
         launch_variant<1, 1>(count, (int)grid, c->stream, A, c->var_unroll);
