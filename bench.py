@@ -4,24 +4,26 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload), all inputs synthetic and generated on the device
-(include/vrdd_synth.h):
-  * decode: a VOL^3 distribution volume (default 1024^3 x 32 bins = 137 GB of raw
-    histograms) is decoded z-slab by z-slab (default 256 slices = 34 GB per launch); every
-    slab is resident in HBM before its timed region starts.  Reported in `decode` and in
-    `roofline` (GB/s against the measured HBM peak), with the fractal-code decode of the same
-    volume next to it.
-  * ray cast (the `metric`): a "step" renders one IMG x IMG view (default 1024^2) of the
-    decoded volume with the reference's constants (tstep 0.01, 500 steps, threshold 0.95,
-    density 0.05, rainbow transfer function, queryMethod 1), cycling through the 64-view orbit
-    of BASELINE.json configs[1].  Gsamples/s = transfer-function lookups / time; the lookups
-    are counted exactly by the kernel in an untimed pass over the same views.
-  * N > 1: image-space tiles (64x64, round-robin over ranks) of a frame that grows with N so
-    every GPU keeps IMG^2 pixels (weak scaling); every rank decodes VOL/N z-slices and the
-    decoded planes are all-gathered (NCCL); partial frames are reduced to rank 0 (NCCL).
-Timing: CUDA events on the launching stream, >= 3 warm-up steps, barrier + synchronize on
-both sides, max over ranks.  The sampled plane (4.3 GB) and every decode slab (>= 8 GB) are
-far larger than the 126 MB L2, so no L2 flush is needed between iterations.
+Workload (config.workload), all inputs synthetic and generated on the device (include/vrdd_synth.h):
+  * decode: a VOL^3 distribution volume (default 1024^3 x 32 bins = 137 GB of raw histograms) is decoded z-slab by
+    z-slab (default 256 slices = 34 GB per launch); every slab is resident in HBM before its timed region starts.
+    Reported in `decode` and `roofline_decode` (GB/s against the measured HBM peak), with the fractal-code decode of
+    the same volume next to it.
+  * ray cast (the `metric`): a "step" renders one IMG x IMG view (default 1024^2) of the decoded volume with the
+    reference's constants (tstep 0.01, 500 steps, threshold 0.95, density 0.05, rainbow transfer function,
+    queryMethod 1).  The K timed views are ALWAYS spread over the whole 64-view orbit of BASELINE.json configs[1]
+    (view k * 64 / K), whatever K is, and the sample counts, the device-timed loop, the kernel-only loop and the
+    end-to-end loop all use exactly those views.  Gsamples/s = transfer-function lookups / time; the lookups are
+    counted exactly by the kernel in an untimed pass over the same views.
+  * N > 1 (one process per GPU, torchrun): every rank decodes VOL/N z-slices and the decode kernel itself stores its
+    slab into every other rank's planes over NVLink (vrdd_set_peer_planes); image-space tiles (64x64, round-robin over
+    ranks); the kernels store their tiles straight into rank 0's frame over NVLink and the last block of each launch
+    bumps a counter next to the frame that rank 0's stream waits on — no host barrier per frame.  Two records:
+    weak scaling (the frame grows with N so every GPU keeps IMG^2 pixels: the top-level line) and `strong` (BASELINE
+    configs[2]: a fixed 2048 x 2048 frame of the same volume at every N).  `sortlast` (configs[4]): one VOL^3 brick per
+    rank of a volume too large for one GPU.
+Timing: CUDA events on the launching stream, >= 3 warm-up steps, barrier + synchronize on both sides, max over ranks.
+The sampled plane (4.3 GB) and every decode slab (>= 8 GB) are far larger than the 126 MB L2, so no L2 flush is needed.
 """
 import argparse
 import json
@@ -39,6 +41,7 @@ HIST_BYTES_PER_VOXEL = 128 + 12          # 32 fp32 bins read, thr
 SAMPLE_BYTES = 32                        # 8 fp32 texels per trilinear sample
 ORBIT_VIEWS = 64
 HBM_FALLBACK_GBS = 6650.0                # /opt/skills/guides/B200_PROFILING.md
+STRONG_IMAGE = 2048                      # BASELINE.json configs[2]
 
 
 def measured_peaks():
@@ -49,17 +52,31 @@ def measured_peaks():
         return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel, bytes_per_launch):
-    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json),
-    if that capture was taken on the same launch shape; else None."""
+def traffic_record(key):
+    """DRAM bytes per launch of a kernel / launch shape from the committed ncu captures (profiles/traffic.json)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(kernel)
-        if t and abs(t["algorithmic_bytes_per_launch"] - bytes_per_launch) < 1e-6 * bytes_per_launch:
-            return t["dram_bytes_per_launch"]
+            return json.load(f).get(key)
     except Exception:
-        pass
+        return None
+
+
+def ncu_traffic(kernel, bytes_per_launch):
+    t = traffic_record(kernel)
+    if t and abs(t["algorithmic_bytes_per_launch"] - bytes_per_launch) < 1e-6 * bytes_per_launch:
+        return t["dram_bytes_per_launch"]
     return None
+
+
+def l1tex_peak():
+    """The texture pipe's own peak for the ray caster's operation, measured live (tools/l1tex_peak.cu: one trilinear
+    fp32 tex3D fetch per sample, nothing else in the loop): SURVEY.md §8d's L1TEX roofline."""
+    exe = os.path.join(ROOT, "tools", "l1tex_peak")
+    try:
+        out = subprocess.run([exe, "json"], capture_output=True, text=True, timeout=120).stdout.strip().splitlines()
+        return json.loads(out[0])
+    except Exception as exc:
+        return {"error": repr(exc)}
 
 
 class ClockSampler:
@@ -114,6 +131,13 @@ class ClockSampler:
         return out
 
 
+def timed_views(steps):
+    """The K views a run times: spread over the whole 64-view orbit whatever K is (K >= 64: the orbit, repeated)."""
+    if steps >= ORBIT_VIEWS:
+        return [k % ORBIT_VIEWS for k in range(steps)]
+    return [(k * ORBIT_VIEWS) // steps for k in range(steps)]
+
+
 def orbit_view(V, k):
     """View k of the 64-view orbit: viewRotation.y = k * 5.625 deg, translation (0,0,-4)
     (volumeRender.cpp:126, 229-246)."""
@@ -149,52 +173,68 @@ def cpu_decode_baseline(seed):
 
 
 class CpuRaycaster:
-    """The oracle ray caster on a bounded volume: 256^3 decoded on the host, IMG^2 views of the
-    same orbit with the reference's constants (the sample count per view hardly depends on
-    the volume resolution because tstep is fixed)."""
+    """The oracle ray caster (OpenMP port of the reference's d_render, the reference build's rounding) on the SAME
+    workload as the GPU arm: the EDGE^3 synthetic volume (default 1024^3, 1.07 G voxels, 137 GB of histograms generated
+    and decoded on the host 4 M voxels at a time — about half a minute on 16 cores, untimed like the GPU arm's decode);
+    only the plane queryMethod 1 samples is kept (4.3 GB).  Frames are the arm's own (IMG_W x IMG_H views of the same
+    orbit, the reference's constants)."""
 
-    def __init__(self, seed, img):
+    def __init__(self, seed, img, edge=512):
         import numpy as np
         from oracle.vrdd_oracle import Oracle
         self.o = Oracle(fast=True)
+        self.o.set_reference_build(True)
         self.o.set_num_threads(host_threads())
-        self.dims = (256, 256, 256)
+        self.edge = edge
+        self.dims = (edge, edge, edge)
         self.img = img
-        vol = np.empty((256 ** 3, 4), np.float32)
-        sl = 256 * 256
-        for z0 in range(0, 256, 32):
-            vol[z0 * sl:(z0 + 32) * sl] = self.o.decode_hist(self.o.synth_histograms(seed, self.dims, z0=z0, nz=32))
-        self.vol = vol
+        plane = np.empty(edge ** 3, np.float32)
+        sl = edge * edge
+        step = max(1, min(edge, (1 << 22) // sl))                 # ~4 M voxels (0.5 GB of histograms) at a time
+        t0 = time.perf_counter()
+        for z0 in range(0, edge, step):
+            nz = min(step, edge - z0)
+            plane[z0 * sl:(z0 + nz) * sl] = self.o.decode_hist(self.o.synth_histograms(seed, self.dims, z0=z0, nz=nz))[:, 0]
+        self.setup_s = time.perf_counter() - t0
+        self.plane = plane
 
     def step(self, k):
         view = self.o.view_matrix(0.0, (k % ORBIT_VIEWS) * (360.0 / ORBIT_VIEWS))
-        _, s = self.o.render(self.vol, self.dims, view, image=self.img)
+        _, s = self.o.render(None, self.dims, view, image=self.img, plane=self.plane)
         return s
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  The reference itself cannot be compiled
-    (CUDA 12.9 removed texture references), so this is the OpenMP oracle port
-    with all host threads, on the same metric/config as our arm.  One step = one view."""
+    """--impl reference: the reference's CPU path.  The reference has no CPU implementation and its CUDA file does not
+    compile as it stands (CUDA 12.9 removed texture references), so this is the OpenMP oracle port of
+    its d_render with all host threads, on the same metric, the same volume (--ref-volume, 1024^3, decoded on the
+    host), the same views and the arm's own frame size.  One step = one view."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    img = (args.image, args.image)
-    rc = CpuRaycaster(args.seed, img)
-    warm = min(args.warmup, ORBIT_VIEWS)                # a step takes ~60 ms on 16 cores: K and W are honoured as given
-    for k in range(warm):
-        rc.step(k)
+    import vrdd_b200.dist as D
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    img = D.frame_size(args.image, world)
+    rc = CpuRaycaster(args.seed, img, args.ref_volume)
     steps = max(1, min(args.steps, 1024))
+    views = timed_views(steps)
+    warm = min(args.warmup, len(views))
+    for k in views[:warm]:
+        rc.step(k)
     t0 = time.perf_counter()
-    samples = sum(rc.step(warm + k) for k in range(steps))
+    samples = sum(rc.step(k) for k in views)
     dt = time.perf_counter() - t0
     val = samples / dt / 1e9
-    sample = f"{steps} {img[0]}x{img[1]} views of the 64-view orbit on a 256^3 volume decoded on the host"
+    sample = (f"{steps} {img[0]}x{img[1]} views spread over the 64-view orbit on a {args.ref_volume}^3 volume decoded on the host "
+              f"({rc.setup_s:.0f} s, untimed)")
     line = {"impl": "reference", "metric": "raycast_throughput", "value": val, "unit": "Gsamples/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "fps": steps / dt,
-            "config": {"workload": f"ray cast {img[0]}x{img[1]} orbit views, reference constants (tstep 0.01, 500 steps, "
-                                   "threshold 0.95), OpenMP port of the reference's d_render on a bounded 256^3 volume"},
+            "fps": steps / dt, "samples_per_frame": samples / steps,
+            "config": {"workload": f"{args.ref_volume}^3 distribution volume (32 bins) decoded on the host, ray cast {img[0]}x{img[1]} "
+                                   "per step over the 64-view orbit, reference constants (tstep 0.01, 500 steps, threshold 0.95, "
+                                   "density 0.05, queryMethod 1); OpenMP port of the reference's d_render",
+                       "volume": [args.ref_volume] * 3, "image": list(img),
+                       "views": f"{steps} timed views spread over the 64-view orbit (view k*64/K)"},
             "cpu_baseline": {"value": val, "unit": "Gsamples/s", "cores": rc.o.num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": val, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -205,6 +245,119 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+
+class Dist:
+    """Rank bookkeeping + the two collectives the harness itself needs."""
+
+    def __init__(self, torch, dist, dev):
+        self.torch, self.dist, self.dev = torch, dist, dev
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_list(self, xs):
+        if self.world == 1:
+            return list(xs)
+        t = self.torch.tensor(list(xs), dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t)
+        return [int(v) for v in t.tolist()]
+
+    def all_ok(self, ok):
+        if self.world == 1:
+            return bool(ok)
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return int(t.item()) == 1
+
+
+class PeerFrames:
+    """N > 1: two frames (double buffer) + three counters in rank 0's HBM, mapped by every rank over CUDA IPC.  The
+    ray-cast kernels of all ranks store their tiles straight into the current frame; the last block of each launch bumps
+    done[slot]; rank 0's STREAM waits for world * generation and then bumps `consumed`, which the other ranks' streams
+    wait for before they render into that slot again.  No host barrier per frame."""
+
+    def __init__(self, V, r, ctx, nbytes):
+        self.V, self.r, self.ctx = V, r, ctx
+        self.nbytes = nbytes
+        dist = ctx.dist
+        mine = [r.frame_alloc(nbytes), r.frame_alloc(nbytes), r.frame_alloc(256)] if ctx.rank == 0 else None
+        box = [[r.frame_export(p) for p in mine]] if ctx.rank == 0 else [None]
+        dist.broadcast_object_list(box, src=0)
+        ok, opened = True, None
+        try:
+            opened = mine if ctx.rank == 0 else [r.frame_open(hb) for hb in box[0]]
+        except V.VrddError:
+            ok = False
+        self.ok = ctx.all_ok(ok)
+        self.owned, self.ptrs = mine, opened
+        if not self.ok:
+            self.close()
+            return
+        self.frames = opened[:2]
+        self.done = [opened[2], opened[2] + 64]
+        self.consumed = opened[2] + 128
+        self.frame_no = 0                                         # frames rendered so far (same on every rank)
+
+    def render(self, fw, fh, params, part):
+        """One frame: every rank renders its tiles into rank 0's current frame; returns the slot."""
+        r, k = self.r, self.frame_no
+        s = k & 1
+        if self.ctx.rank != 0 and k >= 2:
+            r.stream_wait_flag(self.consumed, k - 1)              # frame k - 2 (the slot's previous content) has been consumed
+        r.set_frame_signal(self.done[s])
+        r.render(self.frames[s], fw, fh, params, part=part, clear_misses=True)
+        r.set_frame_signal(None)
+        if self.ctx.rank == 0:
+            r.stream_wait_flag(self.done[s], self.ctx.world * (k // 2 + 1))      # all ranks' tiles of frame k are in
+            r.stream_post_flag(self.consumed)
+        self.frame_no = k + 1
+        return s
+
+    def close(self):
+        if self.ptrs:
+            for p in self.ptrs:
+                (self.r.frame_free if self.ctx.rank == 0 else self.r.frame_close)(p)
+        self.ptrs = None
+
+
+def decode_volume(V, D, r, ctx, torch, args, peers=None):
+    """P1a: raw-histogram decode of my z-range, slab by slab; returns (my_ms, n_slabs, slab, z_lo, z_hi)."""
+    W = H = Dz = args.volume
+    slice_vox = W * H
+    z_lo, z_hi = D.slab_range(Dz, ctx.rank, ctx.world)
+    # N > 1: a rank's whole z-range is one slab (N = 2: 69 GB of histograms), so the replication pass below decodes from a
+    # resident buffer
+    slab = (z_hi - z_lo) if ctx.world > 1 else max(1, min(args.slab_z, z_hi - z_lo))
+    reps = max(1, args.decode_reps)
+    hist_buf = torch.empty(slab * slice_vox * 32, dtype=torch.float32, device=ctx.dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    dec_ms = 0.0
+    for z0 in range(z_lo, z_hi, slab):
+        nz = min(slab, z_hi - z0)
+        r.synth_histograms_device(args.seed, z0, nz, hist_buf)     # untimed: the slab is resident before timing
+        r.set_histograms_device(hist_buf, z0, nz)
+        r.decode(V.SRC_ORIGINAL, z0, nz)                           # warm-up (also creates the arrays)
+        ctx.barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(reps):
+            r.decode(V.SRC_ORIGINAL, z0, nz)
+        e1.record()
+        torch.cuda.synchronize()
+        dec_ms += e0.elapsed_time(e1) / reps
+    return dec_ms, (z_hi - z_lo + slab - 1) // slab, slab, z_lo, z_hi, hist_buf
+
 
 def run_ours(args):
     import numpy as np
@@ -222,6 +375,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    ctx = Dist(torch, dist, dev)
+    barrier, max_over_ranks = ctx.barrier, ctx.max
     peaks, peak_src = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
 
@@ -235,6 +390,7 @@ def run_ours(args):
         r.set_variant("raycast_tf", args.tf)
     if args.unroll:
         r.set_variant("raycast_unroll", str(args.unroll))
+    r.set_variant("raycast_layout", args.layout)
     r.set_variant("decode_hist", args.decode_variant)
     r.set_variant("decode_fractal", args.fractal_variant)
     if world > 1:
@@ -242,47 +398,13 @@ def run_ours(args):
     r.set_volume(W, H, Dz)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = r.kernel_launches()
 
-    # ---- P1a: raw-histogram decode of my z-range, slab by slab -------------------------------
-    z_lo, z_hi = D.slab_range(Dz, rank, world)
-    slab = max(1, min(args.slab_z, z_hi - z_lo))
-    n_slabs = (z_hi - z_lo + slab - 1) // slab
-    reps = max(1, args.decode_reps)
-    hist_buf = torch.empty(slab * slice_vox * 32, dtype=torch.float32, device=dev)
-    dec_ms = 0.0
-    for z0 in range(z_lo, z_hi, slab):
-        nz = min(slab, z_hi - z0)
-        r.synth_histograms_device(args.seed, z0, nz, hist_buf)     # untimed: the slab is resident before timing
-        r.set_histograms_device(hist_buf, z0, nz)
-        r.decode(V.SRC_ORIGINAL, z0, nz)                           # warm-up (also creates the arrays)
-        barrier()
-        e0, e1 = ev(), ev()
-        e0.record()
-        for _ in range(reps):
-            r.decode(V.SRC_ORIGINAL, z0, nz)
-        e1.record()
-        torch.cuda.synchronize()
-        dec_ms += e0.elapsed_time(e1) / reps
-    del hist_buf
-    torch.cuda.empty_cache()
-    my_dec_ms = dec_ms
-    dec_ms = max_over_ranks(dec_ms)
+    # ---- P1a: raw-histogram decode of my z-range, slab by slab (no replication yet) ------------------------
+    my_dec_ms, n_slabs, slab, z_lo, z_hi, hist_buf = decode_volume(V, D, r, ctx, torch, args)
+    dec_ms = max_over_ranks(my_dec_ms)
     dec_gbs = total_vox * HIST_BYTES_PER_VOXEL / (dec_ms * 1e-3) / 1e9
     decode = {"kernel": "decode_hist_" + args.decode_variant + "_kernel", "voxels": total_vox, "ms": dec_ms,
               "gbs": dec_gbs, "gvoxels_per_s": total_vox / (dec_ms * 1e-3) / 1e9,
@@ -295,7 +417,88 @@ def run_ours(args):
                        "bytes_per_launch": launch_bytes, "traffic": ncu_traffic(decode["kernel"], launch_bytes)}
     roofline_decode["frac"] = roofline_decode["achieved"] / roofline_decode["peak"]
 
+    # ---- N > 1: replication fused into the decode ---------------------------------------------------------------
+    # Every rank maps the other ranks' linear planes (CUDA IPC) and decodes its slab once more with them attached: the
+    # decode kernel stores every value into all N copies over NVLink.  The plane the frames sample (mean) first, then
+    # the other two; each rank commits what it received into its 3-D arrays.  An in-place NCCL all-gather of one plane
+    # is timed next to it for comparison.
+    replicate = None
+    if world > 1:
+        my_planes = r.get_decoded_planes_device(V.SRC_ORIGINAL)
+        handles = [None] * world
+        dist.all_gather_object(handles, [r.frame_export(p) for p in my_planes])
+        opened, ok = {}, True
+        try:
+            for q in range(world):
+                if q != rank:
+                    opened[q] = [r.frame_open(hb) for hb in handles[q]]
+        except V.VrddError:
+            ok = False
+        fused = ctx.all_ok(ok)
+        others = [q for q in range(world) if q != rank]
+        nz_mine = z_hi - z_lo
+        # the slab buffer still holds my LAST slab; regenerate per slab when there are several
+        def decode_with_peers(mask):
+            peers = [[opened[q][i] if (mask >> i) & 1 else None for i in range(3)] for q in others]
+            r.set_peer_planes(V.SRC_ORIGINAL, peers)
+            for z0 in range(z_lo, z_hi, slab):
+                nz = min(slab, z_hi - z0)
+                if n_slabs > 1:
+                    r.synth_histograms_device(args.seed, z0, nz, hist_buf)
+                    r.set_histograms_device(hist_buf, z0, nz)
+                r.decode(V.SRC_ORIGINAL, z0, nz)
+            r.set_peer_planes(V.SRC_ORIGINAL, [])
+
+        def commit_received(mask):
+            for q in others:
+                a, b = D.slab_range(Dz, q, world)
+                r.commit_planes(V.SRC_ORIGINAL, a, b - a, plane_mask=mask)
+
+        replicate = {"fused": fused}
+        if fused:
+            times = {}
+            for name, mask in (("mean", 1), ("variance_entropy", 6)):
+                barrier()
+                e0, e1, e2 = ev(), ev(), ev()
+                e0.record()
+                decode_with_peers(mask)
+                e1.record()
+                barrier()                                          # every rank's stores have landed
+                e1b = ev(); e1b.record()
+                commit_received(mask)
+                e2.record()
+                torch.cuda.synchronize()
+                times[name] = {"decode_and_peer_stores_ms": max_over_ranks(e0.elapsed_time(e1)),
+                               "commit_ms": max_over_ranks(e1b.elapsed_time(e2))}
+                times[name]["total_ms"] = times[name]["decode_and_peer_stores_ms"] + times[name]["commit_ms"]
+            replicate.update(times)
+            replicate["note"] = ("decode of my z-slab with the other ranks' planes attached (vrdd_set_peer_planes): the decode "
+                                 "kernel stores into all N copies over NVLink; then the received slabs are committed to the 3-D "
+                                 "arrays.  mean = what the frames sample (decode + replicate + commit); variance_entropy = the "
+                                 "other two planes, afterwards")
+            replicate["bytes_sent_per_rank"] = {"mean": nz_mine * slice_vox * 4 * (world - 1),
+                                                "variance_entropy": nz_mine * slice_vox * 8 * (world - 1)}
+        # comparison / fallback: in-place NCCL all-gather of the mean plane (and of all planes when IPC is not available)
+        planes_t = [V.as_torch(p, (Dz * slice_vox,), device=dev) for p in my_planes]
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for p in (planes_t if not fused else planes_t[:1]):
+            D.allgather_plane(p, Dz, slice_vox, rank, world)
+        if not fused:
+            r.commit_planes(V.SRC_ORIGINAL, 0, Dz)
+        e1.record()
+        torch.cuda.synchronize()
+        replicate["nccl_allgather_ms"] = max_over_ranks(e0.elapsed_time(e1))
+        replicate["nccl_allgather_what"] = "mean plane, in place, no commit (comparison)" if fused else "three planes + commit"
+        for q in opened:
+            for p in opened[q]:
+                r.frame_close(p)
+    del hist_buf
+    torch.cuda.empty_cache()
+
     # ---- P1b: fractal-code decode of the same volume (compact codes) --------------------------
+    reps = max(1, args.decode_reps)
     if args.fractal and world == 1:
         T, max_ne = 622, 8
         nvs = slab * slice_vox
@@ -321,142 +524,151 @@ def run_ours(args):
         fr_kernel = {"moments": "decode_fractal_moments_smem_kernel", "moments768": "decode_fractal_moments_smem_kernel",
                      "moments2": "decode_fractal_moments2_kernel", "moments2r": "decode_fractal_moments2_kernel",
                      "moments_global": "decode_fractal_moments_kernel", "dense": "decode_fractal_dense_kernel"}
+        fr_traffic = traffic_record("decode_fractal_moments2_kernel")
         decode["fractal"] = {"kernel": fr_kernel.get(args.fractal_variant, args.fractal_variant), "ms": fr_ms,
                              "gbs": fr_bytes / (fr_ms * 1e-3) / 1e9,
                              "frac_of_hbm_peak": fr_bytes / (fr_ms * 1e-3) / 1e9 / hbm_peak,
                              "gvoxels_per_s": total_vox / (fr_ms * 1e-3) / 1e9, "bytes_per_voxel": fr_bytes / total_vox,
                              "templates": T, "mean_ne": (fr_bytes / total_vox - 28) / 8}
+        if fr_traffic and args.fractal_variant == "moments2":
+            decode["fractal"]["dram_bytes_over_algorithmic"] = fr_traffic["dram_bytes_per_launch"] / (fr_bytes / (Dz / slab))
         del cb, er, off, tm
         torch.cuda.empty_cache()
 
-    # ---- N > 1: replicate the decoded planes, one in-place all-gather per plane (NCCL) --------
-    gather_ms = None
-    if world > 1:
-        planes = r.get_decoded_planes_device(V.SRC_ORIGINAL)
-        barrier()
-        e0, e1 = ev(), ev()
-        e0.record()
-        for p in planes:
-            D.allgather_plane(V.as_torch(p, (Dz * slice_vox,), device=dev), Dz, slice_vox, rank, world)
-        r.commit_planes(V.SRC_ORIGINAL, 0, Dz)
-        e1.record()
-        torch.cuda.synchronize()
-        gather_ms = max_over_ranks(e0.elapsed_time(e1))
-
     # ---- P2: ray casting -----------------------------------------------------------------------
-    fw, fh = D.frame_size(args.image, world)
-    part = V.TilePartition(D.TILE, D.TILE, rank, world) if world > 1 else None
-    img = torch.zeros(fh, fw, dtype=torch.int32, device=dev)
-    red = torch.zeros_like(img) if world > 1 else None
-    # N > 1, --assemble p2p: rank 0 owns two frames (double buffer); every other rank maps them (CUDA IPC) and
-    # its ray-cast kernel stores its tiles straight into rank 0's HBM over NVLink; one barrier orders a frame.
+    views = timed_views(args.steps)
+    warm_views = [views[k % len(views)] for k in range(args.warmup)]
+    distinct = sorted(set(views))
     p2p = world > 1 and args.assemble == "p2p"
-    frames = None
-    if p2p:
-        nbytes = fw * fh * 4
-        mine = [r.frame_alloc(nbytes), r.frame_alloc(nbytes)] if rank == 0 else None
-        box = [[r.frame_export(p) for p in mine]] if rank == 0 else [None]
-        dist.broadcast_object_list(box, src=0)
-        ok = 1
-        try:
-            frames = mine if rank == 0 else [r.frame_open(hb) for hb in box[0]]
-        except V.VrddError:
-            ok = 0
-        t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        if int(t_ok.item()) == 0:                      # some rank cannot map the frame: NCCL reduce instead
-            if rank == 0:
-                for p_ in mine:
-                    r.frame_free(p_)
-            elif ok:
-                for p_ in frames:
-                    r.frame_close(p_)
-            p2p, frames = False, None
 
-    def render_step(k, params):
-        r.set_view(orbit_view(V, k))
-        if p2p:
-            r.render(frames[k & 1], fw, fh, params, part=part, clear_misses=True)
-            dist.barrier()                                    # frame k is complete on rank 0
-        else:
-            r.render(img, fw, fh, params, part=part, clear_misses=True)
-            if world > 1:
-                D.reduce_frame(img, red, dst=0)
+    class Frames:
+        """One frame geometry (weak: grows with N; strong: fixed 2048^2): buffers, partition, how a step is rendered."""
 
-    def count_samples(params, nviews):
-        r.count_samples(True)
-        counts = []
-        for k in range(nviews):
+        def __init__(self, fw, fh):
+            self.fw, self.fh = fw, fh
+            self.part = V.TilePartition(D.TILE, D.TILE, rank, world) if world > 1 else None
+            self.img = torch.zeros(fh, fw, dtype=torch.int32, device=dev)
+            self.red = torch.zeros_like(self.img) if world > 1 else None
+            self.peer = None
+            if p2p:
+                pf = PeerFrames(V, r, ctx, fw * fh * 4)
+                self.peer = pf if pf.ok else None
+
+        def render_step(self, k, params):
             r.set_view(orbit_view(V, k))
-            r.render(img, fw, fh, params, part=part, clear_misses=True)
-            counts.append(r.get_sample_count())
-        r.count_samples(False)
-        if world > 1:
-            t = torch.tensor(counts, dtype=torch.int64, device=dev)
-            dist.all_reduce(t)
-            counts = [int(x) for x in t.tolist()]
-        return counts
+            if self.peer:
+                return self.peer.render(self.fw, self.fh, params, self.part)
+            r.render(self.img, self.fw, self.fh, params, part=self.part, clear_misses=True)
+            if world > 1:
+                D.reduce_frame(self.img, self.red, dst=0)
+            return 0
 
-    def time_render(params, steps, warmup, with_reduce=True):
-        for k in range(warmup):
-            render_step(k, params) if with_reduce else (r.set_view(orbit_view(V, k)),
-                                                        r.render(img, fw, fh, params, part=part, clear_misses=True))
-        barrier()
-        l0 = r.kernel_launches()
-        e0, e1 = ev(), ev()
-        e0.record()
-        for k in range(warmup, warmup + steps):
-            if with_reduce:
-                render_step(k, params)
-            else:
-                r.set_view(orbit_view(V, k))
-                r.render(img, fw, fh, params, part=part, clear_misses=True)
-        e1.record()
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1)), r.kernel_launches() - l0
+        def render_local(self, k, params):                       # the ray-cast kernel alone, into a local buffer
+            r.set_view(orbit_view(V, k))
+            r.render(self.img, self.fw, self.fh, params, part=self.part, clear_misses=True)
+
+        def count_samples(self, params, view_ids):
+            r.count_samples(True)
+            counts = []
+            for k in view_ids:
+                self.render_local(k, params)
+                counts.append(r.get_sample_count())
+            r.count_samples(False)
+            return dict(zip(view_ids, ctx.sum_list(counts)))
+
+        def time(self, params, view_ids, warm_ids, local=False):
+            step = self.render_local if local else self.render_step
+            for k in warm_ids:
+                step(k, params)
+            barrier()
+            l0 = r.kernel_launches()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for k in view_ids:
+                step(k, params)
+            e1.record()
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)), r.kernel_launches() - l0
+
+        def check_assembly(self, params):
+            """The frame the kernels assemble in rank 0's HBM must be, bit for bit, the NCCL-reduced one."""
+            if not self.peer:
+                return
+            self.render_local(7, params)
+            D.reduce_frame(self.img, self.red, dst=0)
+            s = self.render_step(7, params)
+            barrier()
+            if rank == 0 and not torch.equal(V.as_torch(self.peer.frames[s], (self.fh, self.fw), typestr="<i4", device=dev), self.red):
+                raise SystemExit("bench.py: peer-assembled frame differs from the NCCL-reduced frame")
+
+        def device_frame(self, slot):
+            if self.peer:
+                return V.as_torch(self.peer.frames[slot], (self.fh, self.fw), typestr="<i4", device=dev)
+            return self.red if world > 1 else self.img
+
+        def close(self):
+            if self.peer:
+                barrier()
+                self.peer.close()
 
     params = V.default_render_params(query_method=1)
-    if p2p:
-        # the frame the kernels assemble in rank 0's HBM must be, bit for bit, the NCCL-reduced one
-        r.set_view(orbit_view(V, 7))
-        r.render(img, fw, fh, params, part=part, clear_misses=True)
-        D.reduce_frame(img, red, dst=0)
-        r.render(frames[0], fw, fh, params, part=part, clear_misses=True)
-        barrier()
-        if rank == 0 and not torch.equal(V.as_torch(frames[0], (fh, fw), typestr="<i4", device=dev), red):
-            raise SystemExit("bench.py: peer-assembled frame differs from the NCCL-reduced frame")
-    nviews = min(ORBIT_VIEWS, args.warmup + args.steps)
-    counts = count_samples(params, nviews)
-    steps_samples = lambda c, w, s: sum(c[k % len(c)] for k in range(w, w + s))
-    ray_ms, ray_launches = time_render(params, args.steps, args.warmup)
-    samples = steps_samples(counts, args.warmup, args.steps)
+    fw, fh = D.frame_size(args.image, world)
+    F = Frames(fw, fh)
+    F.check_assembly(params)
+    counts = F.count_samples(params, distinct)                   # also builds the layered copies the views select
+    samples = sum(counts[k] for k in views)
+    ray_ms, ray_launches = F.time(params, views, warm_views)
     gsamples = samples / (ray_ms * 1e-3) / 1e9
     ms_per_step = ray_ms / args.steps
-    kernel_ms, _ = time_render(params, args.steps, 0, with_reduce=False)      # ray-cast kernel alone
+    kernel_ms, _ = F.time(params, views, warm_views, local=True)  # the ray-cast kernel alone, on the SAME views
     kernel_ms /= args.steps
+
+    # ---- strong scaling (BASELINE.json configs[2]): a fixed 2048 x 2048 frame of the same volume at every N --------
+    strong = None
+    if args.strong:
+        S = Frames(STRONG_IMAGE, STRONG_IMAGE) if (fw, fh) != (STRONG_IMAGE, STRONG_IMAGE) else F
+        s_counts = S.count_samples(params, distinct) if S is not F else counts
+        s_samples = sum(s_counts[k] for k in views)
+        s_ms, s_launches = (S.time(params, views, warm_views) if S is not F else (ray_ms, ray_launches))
+        sk_ms, _ = (S.time(params, views, warm_views, local=True) if S is not F else (kernel_ms * args.steps, 0))
+        tk = "raycast_strong_n%d" % world
+        tr = traffic_record(tk)
+        strong = {"workload": f"{args.volume}^3 volume, fixed {STRONG_IMAGE}x{STRONG_IMAGE} frame, image-space tiles over {world} GPU(s) "
+                              "(BASELINE.json configs[2])", "scaling": "strong", "n_gpus": world,
+                  "value": s_samples / (s_ms * 1e-3) / 1e9, "unit": "Gsamples/s", "ms_per_step": s_ms / args.steps,
+                  "fps": args.steps / (s_ms * 1e-3), "samples_per_frame": s_samples / args.steps,
+                  "kernel_ms_per_step": sk_ms / args.steps, "gpu_launches": int(s_launches),
+                  "roofline": {"bound": "hbm", "achieved": s_samples / world / args.steps * SAMPLE_BYTES / (sk_ms / args.steps * 1e-3) / 1e9,
+                               "peak": hbm_peak, "unit": "GB/s", "traffic": tr["dram_bytes_per_launch"] if tr else None}}
+        strong["roofline"]["frac"] = strong["roofline"]["achieved"] / hbm_peak
+        if tr:
+            strong["roofline"]["traffic_frac"] = tr["dram_bytes_per_launch"] / (sk_ms / args.steps * 1e-3) / 1e9 / hbm_peak
+        if S is not F:
+            S.close()
+            del S
 
     # resolution-matched step (SURVEY.md §8d): tstep = 2/N so the volume is sampled once per voxel
     matched = None
     if args.matched and world == 1:
         mp_ = V.default_render_params(query_method=1, tstep=2.0 / args.volume,
                                       max_steps=int(math.ceil(math.sqrt(3.0) * args.volume)) + 1)
-        msteps = min(args.steps, 16)
-        mcounts = count_samples(mp_, min(ORBIT_VIEWS, args.warmup + msteps))
-        m_ms, _ = time_render(mp_, msteps, args.warmup)
-        ms_ = steps_samples(mcounts, args.warmup, msteps)
+        mviews = timed_views(min(args.steps, 16))
+        mcounts = F.count_samples(mp_, sorted(set(mviews)))
+        m_ms, _ = F.time(mp_, mviews, mviews[:3])
+        ms_ = sum(mcounts[k] for k in mviews)
         matched = {"tstep": 2.0 / args.volume, "max_steps": mp_.max_steps, "gsamples_per_s": ms_ / (m_ms * 1e-3) / 1e9,
-                   "ms_per_step": m_ms / msteps, "fps": msteps / (m_ms * 1e-3), "samples_per_frame": ms_ / msteps}
+                   "ms_per_step": m_ms / len(mviews), "fps": len(mviews) / (m_ms * 1e-3), "samples_per_frame": ms_ / len(mviews)}
 
     # ---- end to end through the C ABI with host buffers --------------------------------------
     host_img = torch.empty(fh, fw, dtype=torch.int32).pin_memory()
     e2e_sync = None
     if world == 1:
         # (i) one frame at a time: render, read back, synchronise
-        for k in range(3):
+        for k in warm_views[:3]:
             r.set_view(orbit_view(V, k)); r.render_host(host_img, fw, fh, params)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for k in range(args.warmup, args.warmup + args.steps):
+        for k in views:
             r.set_view(orbit_view(V, k))                         # copyInvViewMatrix: 48 B host -> kernel parameters
             r.render_host(host_img, fw, fh, params)              # render + D2H of the frame + synchronize
         dt_sync = time.perf_counter() - t0
@@ -465,19 +677,18 @@ def run_ours(args):
         # (ii) the orbit as a sequence: every frame still goes to host memory inside the timed region, but frame
         # k's read-back (second stream) overlaps frame k+1's rendering
         host_imgs = [host_img, torch.empty(fh, fw, dtype=torch.int32).pin_memory()]
-        for k in range(3):
-            r.set_view(orbit_view(V, k)); r.render_host_async(host_imgs[k & 1], fw, fh, params)
+        for i, k in enumerate(warm_views[:3]):
+            r.set_view(orbit_view(V, k)); r.render_host_async(host_imgs[i & 1], fw, fh, params)
         r.render_host_wait()
         t0 = time.perf_counter()
-        for k in range(args.warmup, args.warmup + args.steps):
+        for i, k in enumerate(views):
             r.set_view(orbit_view(V, k))
-            r.render_host_async(host_imgs[k & 1], fw, fh, params)
+            r.render_host_async(host_imgs[i & 1], fw, fh, params)
         r.render_host_wait()                                     # all frames are in host memory
         dt = time.perf_counter() - t0
-        last = args.warmup + args.steps - 1                      # the pipelined frame is the synchronous frame
-        check = torch.empty(fh, fw, dtype=torch.int32).pin_memory()
-        r.set_view(orbit_view(V, last)); r.render_host(check, fw, fh, params)
-        assert torch.equal(check, host_imgs[last & 1]), "pipelined read-back differs from the synchronous frame"
+        check = torch.empty(fh, fw, dtype=torch.int32).pin_memory()   # the pipelined frame is the synchronous frame
+        r.set_view(orbit_view(V, views[-1])); r.render_host(check, fw, fh, params)
+        assert torch.equal(check, host_imgs[(len(views) - 1) & 1]), "pipelined read-back differs from the synchronous frame"
         call = ("vrdd_set_view + vrdd_render_host_async per frame, vrdd_render_host_wait at the end (two frames in "
                 "flight: read-back of frame k overlaps rendering of frame k+1)")
     else:
@@ -486,7 +697,6 @@ def run_ours(args):
         # overlapping the rendering of frame k+1.  A barrier per frame (behind a device-side fence on the previous
         # frame's copy) marks frame k-1 complete on all ranks.
         from multiprocessing import shared_memory
-        import numpy as np
         nbytes = fw * fh * 4
         shm, host2, shared_ok = None, None, 1
         if rank == 0:
@@ -512,34 +722,29 @@ def run_ours(args):
             V.host_register(host2.ctypes.data, 2 * nbytes)
         except Exception:
             shared_ok = 0
-        t_ok = torch.tensor([shared_ok], dtype=torch.int32, device=dev)
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        if int(t_ok.item()) == 1:
+        if ctx.all_ok(shared_ok):
             bands = V.TilePartition(fw, 64, rank, world)
-            band_counts = None
             barrier()
-            for k in range(3):
-                r.set_view(orbit_view(V, k)); r.render_host_async(host2[k & 1], fw, fh, params, part=bands)
+            for i, k in enumerate(warm_views[:3]):
+                r.set_view(orbit_view(V, k)); r.render_host_async(host2[i & 1], fw, fh, params, part=bands)
             r.render_host_wait()
             barrier()
             t0 = time.perf_counter()
-            for k in range(args.warmup, args.warmup + args.steps):
+            for i, k in enumerate(views):
                 r.set_view(orbit_view(V, k))
-                r.render_host_async(host2[k & 1], fw, fh, params, part=bands)
-                if args.e2e_sync_every and (k % args.e2e_sync_every) == 0:
+                r.render_host_async(host2[i & 1], fw, fh, params, part=bands)
+                if args.e2e_sync_every and (i % args.e2e_sync_every) == 0:
                     r.render_host_fence(1)                        # stream waits for the copy of frame k-1 ...
                     dist.barrier()                                # ... then all ranks: frame k-1 is complete in host memory
             r.render_host_wait()
             barrier()
             dt = max_over_ranks(time.perf_counter() - t0)
             # the frame in shared host memory is, bit for bit, the one the device-side assembly gives
-            last = args.warmup + args.steps - 1
-            render_step(last, params)
+            slot = F.render_step(views[-1], params)
             torch.cuda.synchronize()
             barrier()
             if rank == 0:
-                src = V.as_torch(frames[last & 1], (fh, fw), typestr="<i4", device=dev) if p2p else red
-                if not np.array_equal(src.cpu().numpy(), host2[last & 1]):
+                if not np.array_equal(F.device_frame(slot).cpu().numpy(), host2[(len(views) - 1) & 1]):
                     raise SystemExit("bench.py: the frame assembled in shared host memory differs from the device-assembled frame")
             call = ("vrdd_set_view + vrdd_render_host_async(part = my 64-row bands) per frame on every rank into one frame in "
                     "shared, page-locked host memory (N PCIe links), vrdd_render_host_fence + barrier per frame, "
@@ -558,16 +763,15 @@ def run_ours(args):
                     shm.unlink()
             barrier()
             t0 = time.perf_counter()
-            for k in range(args.warmup, args.warmup + args.steps):
-                render_step(k, params)
+            for k in views:
+                slot = F.render_step(k, params)
                 if rank == 0:
-                    src = V.as_torch(frames[k & 1], (fh, fw), typestr="<i4", device=dev) if p2p else red
-                    host_img.copy_(src, non_blocking=True)
+                    host_img.copy_(F.device_frame(slot), non_blocking=True)
                 torch.cuda.synchronize()
             barrier()
             dt = max_over_ranks(time.perf_counter() - t0)
-            call = ("vrdd_set_view + vrdd_render (my tiles, stored into rank 0's frame over NVLink) + barrier + "
-                    "device->pinned-host frame copy") if p2p else \
+            call = ("vrdd_set_view + vrdd_render (my tiles, stored into rank 0's frame over NVLink, frame-complete counter) + "
+                    "device->pinned-host frame copy") if F.peer else \
                    "vrdd_set_view + vrdd_render (my tiles) + NCCL reduce to rank 0 + device->pinned-host frame copy"
     e2e = {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 48 + 32,
            "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt, "call": call}
@@ -656,12 +860,12 @@ def run_ours(args):
             del hb
             torch.cuda.empty_cache()
             p7 = V.default_render_params(query_method=7)
-            n7 = min(args.steps, 32)
-            c7 = count_samples(p7, min(ORBIT_VIEWS, args.warmup + n7))
-            ms7, _ = time_render(p7, n7, args.warmup)
-            s7 = steps_samples(c7, args.warmup, n7)
-            mode7 = {"gsamples_per_s": s7 / (ms7 * 1e-3) / 1e9, "ms_per_step": ms7 / n7, "fps": n7 / (ms7 * 1e-3),
-                     "steps": n7, "kernel": "raycast_mode7_kernel<gather>",
+            v7 = timed_views(min(args.steps, 32))
+            c7 = F.count_samples(p7, sorted(set(v7)))
+            ms7, _ = F.time(p7, v7, v7[:3])
+            s7 = sum(c7[k] for k in v7)
+            mode7 = {"gsamples_per_s": s7 / (ms7 * 1e-3) / 1e9, "ms_per_step": ms7 / len(v7), "fps": len(v7) / (ms7 * 1e-3),
+                     "steps": len(v7), "kernel": "raycast_mode7_kernel<gather>",
                      "note": "the 8 cell corners of the un-normalised block means come from two tld4 gathers per sample "
                              "(layered 2-D array; 8 point fetches where the extents do not allow it), the reference's cell "
                              "cache and degenerate-cell artefact kept (volumeRender_kernel.cu:395-480); the reference "
@@ -673,9 +877,8 @@ def run_ours(args):
     flex = None
     if world == 1 and args.flex:
         try:
-            sys.path.insert(0, os.path.join(ROOT, "tests"))
-            import flex_synth                                   # synthetic span store (test data, numpy)
-            tables = flex_synth.make_tables(5, 64, n_templates=469, block=6)
+            from vrdd_b200 import synth_flex                    # synthetic span store (numpy; the span tables do not ship)
+            tables = synth_flex.make_tables(5, 64, n_templates=469, block=6)
             r.flex_set_tables_host(tables)
             r.flex_process(6)
             torch.cuda.synchronize()
@@ -698,46 +901,63 @@ def run_ours(args):
 
     clk = clocks.stop()
     total_launches = r.kernel_launches() - launches0
+    tex_peak = l1tex_peak() if (rank == 0 and world == 1 and args.l1tex) else None
 
     # ---- CPU baselines (rank 0, N = 1) ---------------------------------------------------------
     cpu_ray = None
     if rank == 0 and world == 1 and not args.no_cpu:
         decode["cpu_baseline"] = cpu_decode_baseline(args.seed)
-        rc = CpuRaycaster(args.seed, (args.image, args.image))
-        rc.step(0)
-        n_cpu = ORBIT_VIEWS                                     # the whole orbit the GPU arm renders, once (~4 s on 16 cores)
+        rc = CpuRaycaster(args.seed, (args.image, args.image), args.ref_volume)
+        cviews = timed_views(min(args.steps, 32))
+        rc.step(cviews[0])
         t0 = time.perf_counter()
-        s_cpu = sum(rc.step(k) for k in range(n_cpu))
-        dt = time.perf_counter() - t0
-        cpu_ray = {"value": s_cpu / dt / 1e9, "unit": "Gsamples/s", "cores": rc.o.num_threads(), "kind": "port",
-                   "sample": f"the {n_cpu} {args.image}x{args.image} views of the orbit on a 256^3 volume decoded on the host "
-                             "(same constants), OpenMP oracle -O3 -march=x86-64-v3", "fps": n_cpu / dt}
+        s_cpu = sum(rc.step(k) for k in cviews)
+        dt_c = time.perf_counter() - t0
+        cpu_ray = {"value": s_cpu / dt_c / 1e9, "unit": "Gsamples/s", "cores": rc.o.num_threads(), "kind": "port",
+                   "sample": f"{len(cviews)} {args.image}x{args.image} views spread over the orbit on a {args.ref_volume}^3 volume decoded "
+                             f"on the host ({rc.setup_s:.0f} s, untimed; same constants), OpenMP oracle -O3 -march=x86-64-v3",
+                   "fps": len(cviews) / dt_c}
+        del rc
+
+    # ---- N > 1: sort-last bricks (configs[4]) as a sub-record of the same line --------------------------------------
+    F.close()
+    r.close()
+    sortlast = None
+    if world > 1 and args.sortlast:
+        torch.cuda.empty_cache()
+        try:
+            sortlast = sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps=min(args.steps, 16))
+        except Exception as exc:
+            sortlast = {"error": repr(exc)}
 
     if rank == 0:
         my_samples = samples / world / args.steps
-        # the dominant kernel of the timed step is the ray caster; at 1024^3 with the reference's fixed step ncu
-        # shows it DRAM-bound (profiles/README.md), so its roofline is HBM with 32 algorithmic bytes per sample
+        # the dominant kernel of the timed step is the ray caster; at 1024^3 with the reference's fixed step ncu shows it
+        # DRAM-bound (profiles/README.md).  achieved = 32 algorithmic bytes per sample / launch time; what
+        # DRAM really moves is whole 128-byte lines (traffic, traffic_frac): tools/probe_atom*.cu.
+        tkey = "raycast_kernel" if world == 1 else "raycast_tiles_n%d" % world
+        tj = traffic_record(tkey)
         ray_traffic, traffic_what = None, "no ncu capture for this configuration"
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                tj = json.load(f)["raycast_kernel"]
-            if args.volume == 1024 and world == 1 and args.image == 1024:
-                ray_traffic = tj["dram_bytes_per_launch"]
-                traffic_what = ("mean DRAM bytes of the %d orbit launches under ncu (cold L2 before each)" % tj["launches"]
-                                if "launches" in tj else "DRAM bytes of one ncu-captured launch (an orbit side view)")
-        except Exception:
-            pass
-        roofline = {"kernel": "raycast_kernel", "bound": "hbm",
+        if tj and args.volume == 1024 and args.image == 1024:
+            ray_traffic = tj["dram_bytes_per_launch"]
+            traffic_what = "mean DRAM bytes of the %d orbit launches under ncu (%s)" % (tj.get("launches", 1), tj.get("source", "profiles/"))
+        roofline = {"kernel": "raycast_kernel / raycast_gather_kernel (per view)", "bound": "hbm",
                     "achieved": my_samples * SAMPLE_BYTES / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "peak_source": peak_src, "launch_ms": kernel_ms, "bytes_per_launch": my_samples * SAMPLE_BYTES,
                     "gsamples_per_s_kernel_only": my_samples / (kernel_ms * 1e-3) / 1e9, "traffic": ray_traffic,
                     "note": "algorithmic bytes = 32 B per trilinear sample (8 fp32 texels) x samples of the average launch; "
-                            "traffic = " + traffic_what + ", profiles/traffic.json; sector over-fetch, not re-reads, "
-                            "separates the two"}
+                            "traffic = " + traffic_what + "; DRAM delivers whole 128-byte lines (8x4x1 texels), so on oblique views "
+                            "every line of the region the rays cross is read once: 64 B per sample is compulsory there, 24 B on "
+                            "views along an axis"}
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
         if ray_traffic:                                   # what the DRAM actually moved per launch, against the same peak
             roofline["traffic_gbs"] = ray_traffic / (kernel_ms * 1e-3) / 1e9
             roofline["traffic_frac"] = roofline["traffic_gbs"] / roofline["peak"]
+        if tex_peak and "tex3d_linear_l1_gsamples_per_s" in tex_peak:
+            l1 = tex_peak["tex3d_linear_l1_gsamples_per_s"]
+            roofline["l1tex"] = {"achieved": my_samples / (kernel_ms * 1e-3) / 1e9, "peak": l1, "unit": "Gsamples/s (one trilinear fp32 fetch each)",
+                                 "frac": my_samples / (kernel_ms * 1e-3) / 1e9 / l1, "peak_source": "tools/l1tex_peak.cu, run in this process",
+                                 "all": tex_peak}
         line = {"metric": "raycast_throughput", "value": gsamples, "unit": "Gsamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -745,17 +965,27 @@ def run_ours(args):
                 "config": {"workload": f"{args.volume}^3 distribution volume (32 bins) decoded on device, ray cast "
                                        f"{fw}x{fh} per step over the 64-view orbit, reference constants "
                                        "(tstep 0.01, 500 steps, threshold 0.95, density 0.05, queryMethod 1)",
-                           "volume": [W, H, Dz], "image": [fw, fh], "sampler": args.sampler,
+                           "volume": [W, H, Dz], "image": [fw, fh], "sampler": args.sampler, "layout": args.layout,
+                           "views": f"{args.steps} timed views spread over the 64-view orbit (view k*64/K)",
                            "partition": "single GPU" if world == 1 else
-                           f"64x64 image tiles round-robin over {world} ranks; z-slab decode + NCCL all-gather of the "
-                           "decoded planes; " + ("tiles stored by the ray-cast kernels into rank 0's frame over NVLink "
-                                                 "(CUDA IPC), one barrier per frame" if p2p else
-                                                 "NCCL reduce of frames to rank 0"),
+                           f"64x64 image tiles round-robin over {world} ranks; z-slab decode with the slabs stored into every rank's "
+                           "planes by the decode kernel (NVLink); " + ("tiles stored by the ray-cast kernels into rank 0's frame over NVLink "
+                                                                      "(CUDA IPC), frame-complete counter instead of a barrier" if F.peer else
+                                                                      "NCCL reduce of frames to rank 0"),
                            "l2": f"inputs larger than L2 ({total_vox * 4 / 1e9:.1f} GB sampled plane, "
                                  f"{launch_bytes / 1e9:.1f} GB per decode launch); no flush"},
+                "parity": {"bar": "+-1 LSB per RGBA8 channel (queryMethod 1-7), fp32 decode rtol 2e-5",
+                           "pinned_by": "the reference's own device code run on a B200 (tests/golden/ref_gpu_v1.npz, ref_gpu_flex_v1.npz)",
+                           "fractal_decode": "matches the reference BINARY once the stores its build drops are modelled "
+                                             "(fractalDecoding returns a pointer to a local array, volumeRender_kernel.cu:196-221); the "
+                                             "kernels keep the source's intent, all 32 bins"},
                 "decode": decode, "roofline": roofline, "roofline_decode": roofline_decode,
                 "e2e": e2e, "gpu_launches": int(ray_launches), "gpu_launches_total": int(total_launches),
-                "clocks": clk}
+                "kernel_ms_per_step": kernel_ms, "clocks": clk}
+        if "fractal" in decode:
+            line["decode_fractal_frac_of_hbm_peak"] = decode["fractal"]["frac_of_hbm_peak"]
+        if strong:
+            line["strong"] = strong
         if matched:
             line["raycast_resolution_matched"] = matched
         if cfg1:
@@ -764,39 +994,26 @@ def run_ours(args):
             line["query_method_7"] = mode7
         if flex:
             line["flex_chain"] = flex
-        if gather_ms is not None:
-            line["allgather_planes_ms"] = gather_ms
+        if replicate is not None:
+            line["replicate"] = replicate
+        if sortlast:
+            line["sortlast"] = sortlast
         if cpu_ray:
             line["cpu_baseline"] = cpu_ray
+        ref_gpu = traffic_record("reference_gpu_kernel")
+        if ref_gpu:
+            line["reference_gpu_kernel"] = ref_gpu
         print(json.dumps(line), flush=True)
-    if p2p:
-        barrier()
-        for p in frames:
-            (r.frame_free if rank == 0 else r.frame_close)(p)
-    r.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_sortlast(args):
-    """--workload sortlast (BASELINE.json configs[4]): every rank owns one VOL^3 brick (plus a one-voxel
-    ghost layer) of a volume too large for one GPU — 8 ranks: 2x2x2 bricks of a (2*VOL)^3 volume, 1.1 TB of
-    histograms at VOL = 1024.  Per step: alpha pre-pass -> NCCL all-gather of the segment alphas ->
-    incoming alpha -> colour pass -> NCCL SUM reduction of the float4 increments -> pack on rank 0."""
-    import torch
-    import torch.distributed as dist
-    import vrdd_b200 as V
-    import vrdd_b200.dist as D
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    peaks, peak_src = measured_peaks()
-    hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, warmup=3):
+    """configs[4]: every rank owns one VOL^3 brick (plus a one-voxel ghost layer) of a volume too large for one GPU —
+    8 ranks: 2x2x2 bricks of a (2*VOL)^3 volume, 1.1 TB of histograms at VOL = 1024.  Per step: alpha pre-pass -> NCCL
+    all-gather of the segment alphas -> incoming alpha -> colour pass -> NCCL SUM reduction of the float4 increments ->
+    pack on rank 0.  Returns the record (rank 0) or None."""
+    world, rank = ctx.world, ctx.rank
     grid = D.brick_grid(world)
     q = D.brick_of_rank(rank, grid)
     E = args.volume
@@ -807,21 +1024,7 @@ def run_sortlast(args):
     r.set_sampler({"texture": V.SAMPLER_TEXTURE, "linear": V.SAMPLER_LINEAR, "bricked": V.SAMPLER_BRICKED}[args.sortlast_layout])
     r.set_volume(*size)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    clocks = ClockSampler(local)
-    clocks.start()
+    barrier, max_over_ranks = ctx.barrier, ctx.max
     # ---- decode my brick slab by slab -----------------------------------------------------------
     slice_vox = size[0] * size[1]
     slab = max(1, min(args.slab_z, size[2]))
@@ -855,11 +1058,10 @@ def run_sortlast(args):
     a_in = torch.zeros(fh, fw, dtype=torch.float32, device=dev)
     part = torch.zeros(fh, fw, 4, dtype=torch.float32, device=dev)
     frame = torch.zeros(fh, fw, dtype=torch.int32, device=dev)
-
     windows = bool(args.sortlast_windows)
     coll_bytes = [0, 0]                                   # all-gather (received per rank), reduce (sent per rank), per frame
 
-    def step(k):
+    def step(k, frame=frame):
         view = orbit_view(V, k)
         r.set_view(view)
         r.render_brick_alpha(seg, fw, fh, params, br)
@@ -885,64 +1087,99 @@ def run_sortlast(args):
         if rank == 0:
             r.pack_frame(part, frame, fw, fh, params.brightness)
 
-    nviews = min(ORBIT_VIEWS, args.warmup + args.steps)
+    views = timed_views(steps)
+    distinct = sorted(set(views))
     r.count_samples(True)
-    counts = []
-    for k in range(nviews):
+    cnt = []
+    for k in distinct:
         step(k)
-        counts.append(r.get_sample_count())
+        cnt.append(r.get_sample_count())
     r.count_samples(False)
-    if world > 1:
-        t = torch.tensor(counts, dtype=torch.int64, device=dev)
-        dist.all_reduce(t)
-        counts = [int(x) for x in t.tolist()]
-    for k in range(args.warmup):
+    counts = dict(zip(distinct, ctx.sum_list(cnt)))
+    for k in views[:warmup]:
         step(k)
     barrier()
     l0 = r.kernel_launches()
     e0, e1 = ev(), ev()
     e0.record()
-    for k in range(args.warmup, args.warmup + args.steps):
+    for k in views:
         step(k)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = r.kernel_launches() - l0
-    samples = sum(counts[k % len(counts)] for k in range(args.warmup, args.warmup + args.steps))
-    host = torch.empty(fh, fw, dtype=torch.int32).pin_memory()
+    samples = sum(counts[k] for k in views)
+    # end to end: the packed frame of step k is copied to pinned host memory by a second stream while step k+1 runs
+    # (two device frames, two host frames; step k+2 waits for the copy of frame k before it packs into that buffer)
+    host = [torch.empty(fh, fw, dtype=torch.int32).pin_memory() for _ in range(2)]
+    frames2 = [frame, torch.zeros_like(frame)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [None, None]
+    main = torch.cuda.current_stream()
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.warmup, args.warmup + args.steps):
-        step(k)
+    for i, k in enumerate(views):
+        if copied[i & 1] is not None:
+            main.wait_event(copied[i & 1])
+        step(k, frames2[i & 1])
         if rank == 0:
-            host.copy_(frame, non_blocking=True)
-        torch.cuda.synchronize()
+            packed = torch.cuda.Event(); packed.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(packed)
+                host[i & 1].copy_(frames2[i & 1], non_blocking=True)
+                copied[i & 1] = torch.cuda.Event(); copied[i & 1].record(copy_stream)
+    torch.cuda.synchronize()
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
-    clk = clocks.stop()
-    if rank == 0:
-        dec_gbs = decoded_vox * HIST_BYTES_PER_VOXEL / (dec_ms * 1e-3) / 1e9
-        line = {"metric": "raycast_throughput", "value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "fps": args.steps / (ms * 1e-3),
-                "samples_per_frame": samples / args.steps,
-                "config": {"workload": f"sort-last: {gdims[0]}x{gdims[1]}x{gdims[2]} distribution volume in {grid[0]}x{grid[1]}x{grid[2]} "
-                                       f"bricks of {E}^3 (+1 ghost) over {world} GPUs, {fw}x{fh} frames of the 64-view orbit, reference "
-                                       "constants; alpha pre-pass, NCCL all-gather of segment alphas, colour pass, NCCL SUM "
-                                       "reduction of float4 increments, pack on rank 0"
-                                       + ("; collectives restricted to the image rows of each brick's screen footprint" if windows else ""),
-                           "collective_bytes_per_frame": {"all_gather": coll_bytes[0], "reduce": coll_bytes[1],
-                                                          "full_frame": [world * fh * fw * 4, fh * fw * 16]},
-                           "volume": list(gdims), "image": [fw, fh], "histogram_bytes_total": decoded_vox * 128,
-                           "l2": "inputs larger than L2; no flush"},
-                "decode": {"kernel": "decode_hist_tma_kernel", "voxels": decoded_vox, "ms": dec_ms, "gbs": dec_gbs,
-                           "frac_of_hbm_peak": dec_gbs / (hbm_peak * world), "peak_gbs": hbm_peak * world},
-                "e2e": {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 80,
-                        "d2h_bytes_per_step": fw * fh * 4, "fps": args.steps / dt,
-                        "call": "vrdd_render_brick_alpha/compose/color + NCCL + vrdd_pack_frame + device->pinned-host frame copy"},
-                "gpu_launches": int(launches), "clocks": clk}
-        print(json.dumps(line), flush=True)
     r.close()
+    if rank != 0:
+        return None
+    dec_gbs = decoded_vox * HIST_BYTES_PER_VOXEL / (dec_ms * 1e-3) / 1e9
+    return {"workload": f"sort-last: {gdims[0]}x{gdims[1]}x{gdims[2]} distribution volume in {grid[0]}x{grid[1]}x{grid[2]} "
+                        f"bricks of {E}^3 (+1 ghost) over {world} GPUs, {fw}x{fh} frames of the orbit, reference constants; alpha pre-pass, "
+                        "NCCL all-gather of segment alphas, colour pass, NCCL SUM reduction of float4 increments, pack on rank 0"
+                        + ("; collectives restricted to the image rows of each brick's screen footprint" if windows else ""),
+            "n_gpus": world, "value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s", "steps": len(views), "ms_per_step": ms / len(views),
+            "fps": len(views) / (ms * 1e-3), "samples_per_frame": samples / len(views),
+            "collective_bytes_per_frame": {"all_gather": coll_bytes[0], "reduce": coll_bytes[1], "full_frame": [world * fh * fw * 4, fh * fw * 16]},
+            "volume": list(gdims), "image": [fw, fh], "histogram_bytes_total": decoded_vox * 128,
+            "decode": {"kernel": "decode_hist_tma_kernel", "voxels": decoded_vox, "ms": dec_ms, "gbs": dec_gbs,
+                       "frac_of_hbm_peak": dec_gbs / (hbm_peak * world), "peak_gbs": hbm_peak * world},
+            "e2e": {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 80, "d2h_bytes_per_step": fw * fh * 4,
+                    "fps": len(views) / dt,
+                    "call": "vrdd_render_brick_alpha/compose/color + NCCL + vrdd_pack_frame; the frame of step k is copied to pinned host memory "
+                            "by a second stream while step k+1 renders"},
+            "gpu_launches": int(launches)}
+
+
+def run_sortlast(args):
+    """--workload sortlast: the sort-last record as the top-level line."""
+    import torch
+    import torch.distributed as dist
+    import vrdd_b200 as V
+    import vrdd_b200.dist as D
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Dist(torch, dist, dev)
+    peaks, _ = measured_peaks()
+    clocks = ClockSampler(local)
+    clocks.start()
+    rec = sortlast_record(args, ctx, V, D, torch, dist, local, dev, float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS)), steps=args.steps,
+                          warmup=args.warmup)
+    clk = clocks.stop()
+    if ctx.rank == 0:
+        line = {"metric": "raycast_throughput", "value": rec["value"], "unit": "Gsamples/s", "n_gpus": world, "steps": rec["steps"],
+                "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "fps": rec["fps"], "samples_per_frame": rec["samples_per_frame"],
+                "config": {"workload": rec["workload"], "collective_bytes_per_frame": rec["collective_bytes_per_frame"],
+                           "volume": rec["volume"], "image": rec["image"], "histogram_bytes_total": rec["histogram_bytes_total"],
+                           "l2": "inputs larger than L2; no flush"},
+                "decode": rec["decode"], "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"], "clocks": clk}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -955,16 +1192,22 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--volume", type=int, default=1024, help="distribution volume edge (voxels)")
     ap.add_argument("--image", type=int, default=1024, help="frame edge per GPU (pixels)")
+    ap.add_argument("--ref-volume", type=int, default=1024,
+                    help="volume edge of the CPU legs, decoded on the host (1024^3: ~35 s of untimed set-up on 16 cores)")
     ap.add_argument("--slab-z", type=int, default=256, help="z-slices decoded per launch (256 -> 34 GB of histograms)")
     ap.add_argument("--decode-reps", type=int, default=3)
     ap.add_argument("--decode-variant", default="tma", choices=["tma", "ldg"])
     ap.add_argument("--fractal-variant", default="moments2",
                     choices=["moments2", "moments2r", "moments", "moments768", "moments_global", "dense"])
     ap.add_argument("--sampler", default="texture", choices=["texture", "bricked"])
+    ap.add_argument("--layout", default="auto", choices=["auto", "array", "layers_x", "layers_y"])
     ap.add_argument("--tf", default=None, choices=[None, "texture", "smem"])
     ap.add_argument("--unroll", type=int, default=0, choices=[0, 1, 2, 4, 8])
     ap.add_argument("--fractal", type=int, default=1)
     ap.add_argument("--matched", type=int, default=1)
+    ap.add_argument("--strong", type=int, default=1, help="also time the fixed 2048x2048 frame (BASELINE.json configs[2])")
+    ap.add_argument("--sortlast", type=int, default=1, help="N > 1: also emit the sort-last record (BASELINE.json configs[4])")
+    ap.add_argument("--l1tex", type=int, default=1, help="N = 1: run tools/l1tex_peak for the L1TEX roofline")
     ap.add_argument("--e2e-sync-every", type=int, default=1,
                     help="N > 1 end-to-end path: fence + barrier between ranks every K frames (0: only at the end)")
     ap.add_argument("--config1", type=int, default=1, help="also time BASELINE.json configs[1] (512^3 volume, 64-view orbit)")

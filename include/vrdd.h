@@ -180,6 +180,9 @@ int vrdd_keep_linear_planes(vrdd_handle h, int keep);
 /* After writing z-slices [z0, z0+nz) of the linear planes from outside (e.g. an NCCL
  * all-gather), republish them to the sampler's layout. */
 int vrdd_commit_planes(vrdd_handle h, int source, int z0, int nz);
+/* Same for the planes in plane_mask only (bit 0 mean, bit 1 variance, bit 2 entropy): with vrdd_set_peer_planes a
+ * rank can replicate the plane the next frames sample first and the others later. */
+int vrdd_commit_planes_mask(vrdd_handle h, int source, int z0, int nz, int plane_mask);
 
 /* Bit-comparable view of the integer part of the fractal decode: the reconstructed
  * histogram float[nvox][bins] after template lookup, flip, shift, error merge and clamp,
@@ -246,6 +249,26 @@ int vrdd_frame_free(vrdd_handle h, void* d_frame);
 int vrdd_frame_export(vrdd_handle h, const void* d_frame, unsigned char* ipc_handle /* [64] */);
 int vrdd_frame_open(vrdd_handle h, const unsigned char* ipc_handle /* [64] */, void** d_peer_frame);
 int vrdd_frame_close(vrdd_handle h, void* d_peer_frame);
+
+/* Frame-complete signal, so that no host barrier is needed per frame: after vrdd_set_frame_signal(h, d_flag) the last
+ * block of every vrdd_render launch of this handle adds 1 to *d_flag with system-scope release semantics, once all
+ * tiles of the launch are stored — d_flag may point into the frame owner's memory (vrdd_frame_alloc / _open), next to
+ * the frame.  The owner orders its stream behind the N ranks with vrdd_stream_wait_flag(h, d_flag, generation * N):
+ * the stream (not the host) waits until *d_flag >= at_least.  vrdd_stream_post_flag adds 1 from the stream (e.g. "frame
+ * consumed, its buffer may be overwritten", which the other ranks wait for before they render into it again).
+ * NULL switches the signal off.  Counters only grow; the caller keeps track of the generation. */
+int vrdd_set_frame_signal(vrdd_handle h, uint32_t* d_flag);
+int vrdd_stream_wait_flag(vrdd_handle h, const uint32_t* d_flag, uint32_t at_least);
+int vrdd_stream_post_flag(vrdd_handle h, uint32_t* d_flag);
+
+/* Replication of the decoded planes fused into the decode (N ranks, each decoding its z-slab of a volume that every
+ * rank samples): d_planes[3 * q + i] is plane i (mean, variance, entropy) of peer q's LINEAR planes
+ * (vrdd_keep_linear_planes + vrdd_get_decoded_planes_device there, exported with vrdd_frame_export and opened here
+ * with vrdd_frame_open), or NULL for a plane that is not to be replicated now.  Every later vrdd_decode of `source`
+ * also stores each value at its global voxel index in those planes, over NVLink, from the decode kernel itself — no
+ * all-gather pass.  When all ranks have synchronised, each commits the slabs it received with vrdd_commit_planes.
+ * n_peers = 0 switches it off.  At most 7 peers. */
+int vrdd_set_peer_planes(vrdd_handle h, int source, int n_peers, float* const* d_planes);
 
 /* ---- sort-last rendering of a brick-decomposed volume (volumes larger than one GPU's HBM;
  *      new work, the reference is single-GPU; scheme in csrc/sortlast.cu) ------------------------- */
@@ -355,10 +378,15 @@ int vrdd_flex_prefix_spans(int x, int32_t* spans);
  * array, or the linear plane; "gather" / "texture" decide which array the DECODE fills, so set them before it;
  * "raycast_unroll" -> "1" | "2" | "4" | "8" (ray-march steps whose fetches are in flight
  * together).  Results do not depend on these variants.
- * "ray_setup" -> "source" (default) | "nvcc" is different: it selects how the eye ray of vrdd_render is ROUNDED —
- * the uncontracted order of the reference's source, or what nvcc's default FMA contraction and rsqrt make of it in
- * the reference's own build (csrc/raycast.cu, ray_dir_nvcc).  Frames agree to +-1 LSB except in queryMethod 7,
- * whose cell logic is discontinuous.  Unknown names return VRDD_ERR_INVALID. */
+ * "ray_setup" -> "nvcc" (default) | "source" is different: it selects how the eye ray of every ray kernel is ROUNDED —
+ * what nvcc's default FMA contraction and rsqrt.approx make of it in the reference's own build (the same instructions,
+ * hence the same bits: queryMethod 7 then matches the reference binary to +-1 LSB), or the uncontracted order of the
+ * reference's source (csrc/common.cuh, eye_ray).  Frames agree to +-1 LSB except in queryMethod 7, whose cell logic
+ * is discontinuous.
+ * "raycast_layout" -> "auto" (default) | "array" | "layers_x" | "layers_y": which copy of the sampled plane
+ * queryMethod 1..6 read — the 3-D array filtered by the texture unit, or a layered copy stacked along x / y read with
+ * tld4 and filtered in the kernel with the unit's integer weights (same samples; csrc/raycast.cu,
+ * raycast_gather_kernel); auto chooses per view.  Unknown names return VRDD_ERR_INVALID. */
 int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);
 /* Samples the texture unit: out[i] = tex3D(plane `comp` of `source`, u[i], v[i], w[i]) with
  * the ray caster's texture object.  For the filter-model conformance test.  Device ptrs. */

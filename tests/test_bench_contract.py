@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--image", "96"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--image", "96", "--ref-volume", "64"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -33,7 +33,21 @@ def test_reference_arm_uses_all_host_threads_under_torchrun():
     """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must still use every core it may run on."""
     env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
-                        "--warmup", "0", "--image", "96"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+                        "--warmup", "0", "--image", "96", "--ref-volume", "64"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
+def test_timed_views_span_the_orbit_whatever_the_step_count():
+    """The headline must not depend on --steps: K timed views are always spread over the whole 64-view orbit."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for k in (1, 3, 20, 64, 100):
+        v = bench.timed_views(k)
+        assert len(v) == k and all(0 <= x < 64 for x in v)
+    assert bench.timed_views(64) == list(range(64))
+    v20 = bench.timed_views(20)
+    assert v20[0] == 0 and v20[-1] >= 57 and len(set(v20)) == 20
+    assert max(b - a for a, b in zip(v20, v20[1:])) <= 4
+    assert bench.timed_views(130)[64:70] == [0, 1, 2, 3, 4, 5]

@@ -339,3 +339,69 @@ def test_templates_rewritten_in_place_are_picked_up(renderer, oracle):
         got = r.get_decoded_host(V.SRC_FRACTAL, np.empty((n, 4), np.float32))
         ref, _ = oracle.decode_fractal(cb, err, tmpl)
         np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("source", ["original", "fractal"])
+def test_decode_stores_into_the_peers_planes(oracle, source):
+    """vrdd_set_peer_planes: two handles play two ranks, each decodes its z-slab and the decode kernel itself stores
+    every value into the other's linear planes as well (over NVLink on a node; the same pointers here); after
+    committing the received slab both hold the whole volume — the all-gather costs no pass of its own."""
+    import torch
+    import vrdd_b200 as V
+    dims, T = (64, 32, 12), 60
+    sl = dims[0] * dims[1]
+    n = sl * dims[2]
+    hist = oracle.synth_histograms(13, dims)
+    cb, err = oracle.synth_fractal(13, dims, T=T)
+    tmpl = oracle.synth_templates(13, T)
+    ref = oracle.decode_hist(hist) if source == "original" else oracle.decode_fractal(cb, err, tmpl)[0]
+    src = V.SRC_ORIGINAL if source == "original" else V.SRC_FRACTAL
+    slabs = ((0, 7), (7, 5))
+    ranks, keep = [], []
+    for k in range(2):
+        r = V.Renderer(0)
+        r.keep_linear_planes(True)
+        r.set_volume(*dims)
+        ranks.append(r)
+    planes = [r.get_decoded_planes_device(src) for r in ranks]
+    for k, r in enumerate(ranks):
+        z0, nz = slabs[k]
+        other = planes[1 - k]
+        r.set_peer_planes(src, [(other[0], None, other[2])] if k == 0 else [other])       # rank 0 skips the variance for now
+        if source == "original":
+            d = torch.from_numpy(hist[z0 * sl:(z0 + nz) * sl]).cuda(); keep.append(d)
+            r.set_histograms_device(d, z0, nz)
+        else:
+            ent, off = V.pack_fractal_errors(cb[z0 * sl:(z0 + nz) * sl], err[z0 * sl:(z0 + nz) * sl])
+            d_cb = torch.from_numpy(np.ascontiguousarray(cb[z0 * sl:(z0 + nz) * sl])).cuda()
+            d_er = torch.from_numpy(ent.view(np.uint8).reshape(-1).copy()).cuda()
+            d_off = torch.from_numpy(off.view(np.int64)).cuda()
+            d_tm = torch.from_numpy(tmpl).cuda()
+            keep += [d_cb, d_er, d_off, d_tm]
+            r.set_fractal_device(d_cb, d_er, d_off, d_tm, T, z0, nz)
+        r.decode(src, z0, nz)
+    for r in ranks:
+        r.synchronize()
+    # rank 1 received mean and entropy of slab 0 (variance later); rank 0 received all of slab 1
+    ranks[1].commit_planes(src, slabs[0][0], slabs[0][1], plane_mask=5)
+    ranks[0].commit_planes(src, slabs[1][0], slabs[1][1])
+    got0 = ranks[0].get_decoded_host(src, np.empty((n, 4), np.float32))
+    np.testing.assert_allclose(got0, ref, rtol=RTOL, atol=ATOL)
+    # the arrays the ray caster samples hold the same: a frame from either rank is the single-volume frame
+    view = oracle.view_matrix(15.0, 35.0)
+    frames = []
+    for r in ranks:
+        r.set_view(view)
+        out = torch.zeros(96, 128, dtype=torch.int32, device="cuda")
+        r.render(out, 128, 96, V.default_render_params(query_method=3 if source == "original" else 4), clear_misses=True)
+        r.synchronize()
+        frames.append(out.cpu().numpy())
+    assert np.array_equal(frames[0], frames[1])
+    # the variance of slab 0 follows: decode again with all three planes mapped
+    ranks[0].set_peer_planes(src, [planes[1]])
+    ranks[0].decode(src, slabs[0][0], slabs[0][1]); ranks[0].synchronize()
+    ranks[1].commit_planes(src, slabs[0][0], slabs[0][1], plane_mask=2)
+    got1 = ranks[1].get_decoded_host(src, np.empty((n, 4), np.float32))
+    np.testing.assert_allclose(got1, ref, rtol=RTOL, atol=ATOL)
+    for r in ranks:
+        r.close()

@@ -28,7 +28,7 @@ EXPORTS = [
     "vrdd_create", "vrdd_destroy", "vrdd_set_stream", "vrdd_synchronize", "vrdd_last_error",
     "vrdd_kernel_launches", "vrdd_set_volume", "vrdd_set_histograms_host", "vrdd_set_histograms_device",
     "vrdd_set_fractal_host", "vrdd_set_fractal_device", "vrdd_pack_fractal_errors", "vrdd_set_sampler", "vrdd_decode",
-    "vrdd_get_decoded_host", "vrdd_get_decoded_planes_device", "vrdd_keep_linear_planes", "vrdd_commit_planes",
+    "vrdd_get_decoded_host", "vrdd_get_decoded_planes_device", "vrdd_keep_linear_planes", "vrdd_commit_planes", "vrdd_commit_planes_mask",
     "vrdd_reconstruct_fractal_device", "vrdd_set_transfer_function", "vrdd_set_view",
     "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_render_host_async",
     "vrdd_render_host_wait", "vrdd_render_host_fence", "vrdd_host_register", "vrdd_host_unregister", "vrdd_count_samples",
@@ -38,6 +38,7 @@ EXPORTS = [
     "vrdd_flex_divide_blocks", "vrdd_flex_prefix_spans", "vrdd_flex_set_tables_host", "vrdd_flex_process",
     "vrdd_flex_get_blocks_host",
     "vrdd_frame_alloc", "vrdd_frame_free", "vrdd_frame_export", "vrdd_frame_open", "vrdd_frame_close",
+    "vrdd_set_frame_signal", "vrdd_stream_wait_flag", "vrdd_stream_post_flag", "vrdd_set_peer_planes",
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_compose_alpha_in_rows", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
@@ -133,6 +134,7 @@ def lib():
             "vrdd_keep_linear_planes": (i32, [vp, i32]),
             "vrdd_enable_interpolated_mean": (i32, [vp, i32]),
             "vrdd_commit_planes": (i32, [vp, i32, i32, i32]),
+            "vrdd_commit_planes_mask": (i32, [vp, i32, i32, i32, i32]),
             "vrdd_reconstruct_fractal_device": (i32, [vp, vp]),
             "vrdd_set_transfer_function": (i32, [vp, vp, i32]),
             "vrdd_set_view": (i32, [vp, vp]),
@@ -170,6 +172,10 @@ def lib():
             "vrdd_frame_export": (i32, [vp, vp, vp]),
             "vrdd_frame_open": (i32, [vp, vp, C.POINTER(vp)]),
             "vrdd_frame_close": (i32, [vp, vp]),
+            "vrdd_set_frame_signal": (i32, [vp, vp]),
+            "vrdd_stream_wait_flag": (i32, [vp, vp, u32]),
+            "vrdd_stream_post_flag": (i32, [vp, vp]),
+            "vrdd_set_peer_planes": (i32, [vp, i32, i32, vp]),
             # on-disk formats (include/vrdd_io.h)
             "vrdd_io_read_histograms": (i32, [C.c_char_p, C.c_size_t, i32, vp]),
             "vrdd_io_codebook_blocks": (C.c_int64, [C.c_char_p]),
@@ -356,8 +362,8 @@ class Renderer:
         self._ck(lib().vrdd_get_decoded_planes_device(self._h, source, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
-    def commit_planes(self, source, z0, nz):
-        self._ck(lib().vrdd_commit_planes(self._h, source, z0, nz))
+    def commit_planes(self, source, z0, nz, plane_mask=7):
+        self._ck(lib().vrdd_commit_planes_mask(self._h, source, z0, nz, plane_mask))
 
     def reconstruct_fractal_device(self, d_out):
         self._ck(lib().vrdd_reconstruct_fractal_device(self._h, _ptr(d_out)))
@@ -464,6 +470,25 @@ class Renderer:
 
     def frame_close(self, ptr):
         self._ck(lib().vrdd_frame_close(self._h, ptr))
+
+    # frame-complete signals (no host barrier per frame) and decode-fused replication
+    def set_frame_signal(self, d_flag):
+        self._ck(lib().vrdd_set_frame_signal(self._h, _ptr(d_flag)))
+
+    def stream_wait_flag(self, d_flag, at_least):
+        self._ck(lib().vrdd_stream_wait_flag(self._h, _ptr(d_flag), int(at_least) & 0xffffffff))
+
+    def stream_post_flag(self, d_flag):
+        self._ck(lib().vrdd_stream_post_flag(self._h, _ptr(d_flag)))
+
+    def set_peer_planes(self, source, peers):
+        """peers: list (one entry per other rank) of 3 device pointers (mean, variance, entropy planes; None = skip)."""
+        n = len(peers)
+        arr = (C.c_void_p * max(1, 3 * n))()
+        for q, planes in enumerate(peers):
+            for i in range(3):
+                arr[3 * q + i] = planes[i]
+        self._ck(lib().vrdd_set_peer_planes(self._h, source, n, arr))
 
     # sort-last bricks
     def synth_histograms_region_device(self, seed, gdims, origin, z0, nz, d_hist):

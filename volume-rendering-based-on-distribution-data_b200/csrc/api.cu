@@ -179,10 +179,19 @@ DecodeOut make_decode_out(vrdd_context* c, int source, long long v_base) {
     o.v_base = v_base;
     o.bW = c->bW; o.bH = c->bH;
     o.inv_wh = 1.0f / ((float)c->W * (float)c->H);
+    o.n_peers = c->n_peers[source];
+    for (int q = 0; q < VRDD_MAX_PEERS; ++q)
+        for (int i = 0; i < 3; ++i) o.peer[q][i] = (q < o.n_peers) ? c->peer_planes[source][q][i] : nullptr;
     return o;
 }
 
 }  // namespace vrdd
+
+// linear plane slab -> 3-D array
+__global__ void commit_array_kernel(const float* __restrict__ lin, cudaSurfaceObject_t surf, int W, int H, int z0) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = z0 + blockIdx.z;
+    if (x < W) surf3Dwrite(lin[((size_t)z * H + y) * W + x], surf, x * 4, y, z);
+}
 
 // linear plane slab -> sampler layout
 __global__ void commit_brick_kernel(const float* __restrict__ lin, float* __restrict__ brick, int W, int H, int bW,
@@ -239,7 +248,9 @@ int vrdd_create(int device, vrdd_handle* out) {
         return VRDD_ERR_NO_DEVICE;
     }
     if (cudaMalloc(&c->d_samples, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(c->d_samples, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMemset(c->d_samples, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&c->d_tickets, sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(c->d_tickets, 0, sizeof(unsigned)) != cudaSuccess) {
         delete c;
         return VRDD_ERR_CUDA;
     }
@@ -257,6 +268,7 @@ int vrdd_destroy(vrdd_handle h) {
     free_inputs(c);
     free_tf(c);
     if (c->d_samples) cudaFree(c->d_samples);
+    if (c->d_tickets) cudaFree(c->d_tickets);
     if (c->frame) cudaFree(c->frame);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
@@ -521,9 +533,11 @@ int vrdd_get_decoded_planes_device(vrdd_handle h, int source, float** mean, floa
     return VRDD_OK;
 }
 
-int vrdd_commit_planes(vrdd_handle h, int source, int z0, int nz) {
+int vrdd_commit_planes(vrdd_handle h, int source, int z0, int nz) { return vrdd_commit_planes_mask(h, source, z0, nz, 7); }
+
+int vrdd_commit_planes_mask(vrdd_handle h, int source, int z0, int nz, int plane_mask) {
     CHECK_HANDLE(h);
-    if (source < 0 || source > 1 || z0 < 0 || nz <= 0 || z0 + nz > c->D)
+    if (source < 0 || source > 1 || z0 < 0 || nz <= 0 || z0 + nz > c->D || (plane_mask & ~7) || !plane_mask)
         return fail(c, VRDD_ERR_INVALID, "commit_planes: bad arguments");
     vrdd_decoded_volume& v = c->vol[source];
     if (!v.lin[0]) return fail(c, VRDD_ERR_INVALID, "commit_planes: linear planes are not kept");
@@ -531,15 +545,13 @@ int vrdd_commit_planes(vrdd_handle h, int source, int z0, int nz) {
     if (rc != VRDD_OK) return rc;
     const long long slice = (long long)c->W * c->H;
     for (int i = 0; i < 3; ++i) {
-        if (v.arr[i]) {
-            cudaMemcpy3DParms p;
-            std::memset(&p, 0, sizeof(p));
-            p.srcPtr = make_cudaPitchedPtr(v.lin[i] + (size_t)z0 * slice, c->W * sizeof(float), c->W, c->H);
-            p.dstArray = v.arr[i];
-            p.dstPos = make_cudaPos(0, 0, z0);
-            p.extent = make_cudaExtent(c->W, c->H, nz);
-            p.kind = cudaMemcpyDeviceToDevice;
-            VRDD_CUDA(c, cudaMemcpy3DAsync(&p, c->stream));
+        if (!(plane_mask & (1 << i))) continue;
+        if (v.arr[i] && v.surf[i]) {
+            // linear slab -> 3-D array through the surface: one thread per voxel, coalesced reads, x-fastest writes
+            const dim3 grid((c->W + 255) / 256, c->H, nz);
+            commit_array_kernel<<<grid, 256, 0, c->stream>>>(v.lin[i], v.surf[i], c->W, c->H, z0);
+            c->launches += 1;
+            VRDD_CUDA(c, cudaGetLastError());
         }
         if (v.brick[i]) {
             const long long nvox = (long long)nz * slice;
@@ -837,6 +849,35 @@ int vrdd_frame_open(vrdd_handle h, const unsigned char* ipc_handle, void** d_pee
 int vrdd_frame_close(vrdd_handle h, void* d_peer_frame) {
     CHECK_HANDLE(h);
     VRDD_CUDA(c, cudaIpcCloseMemHandle(d_peer_frame));
+    return VRDD_OK;
+}
+
+int vrdd_set_frame_signal(vrdd_handle h, uint32_t* d_flag) {
+    CHECK_HANDLE(h);
+    if (d_flag && (reinterpret_cast<uintptr_t>(d_flag) & 3u)) return fail(c, VRDD_ERR_INVALID, "set_frame_signal: misaligned flag");
+    c->frame_signal = d_flag;
+    return VRDD_OK;
+}
+
+int vrdd_stream_wait_flag(vrdd_handle h, const uint32_t* d_flag, uint32_t at_least) {
+    CHECK_HANDLE(h);
+    if (!d_flag) return fail(c, VRDD_ERR_INVALID, "stream_wait_flag: null flag");
+    return launch_stream_wait_flag(c, d_flag, at_least);
+}
+
+int vrdd_stream_post_flag(vrdd_handle h, uint32_t* d_flag) {
+    CHECK_HANDLE(h);
+    if (!d_flag) return fail(c, VRDD_ERR_INVALID, "stream_post_flag: null flag");
+    return launch_stream_post_flag(c, d_flag);
+}
+
+int vrdd_set_peer_planes(vrdd_handle h, int source, int n_peers, float* const* d_planes) {
+    CHECK_HANDLE(h);
+    if (source < 0 || source > 1 || n_peers < 0 || n_peers > VRDD_MAX_PEERS || (n_peers > 0 && !d_planes))
+        return fail(c, VRDD_ERR_INVALID, "set_peer_planes: bad arguments");
+    c->n_peers[source] = n_peers;
+    for (int q = 0; q < VRDD_MAX_PEERS; ++q)
+        for (int i = 0; i < 3; ++i) c->peer_planes[source][q][i] = (q < n_peers) ? d_planes[3 * q + i] : nullptr;
     return VRDD_OK;
 }
 

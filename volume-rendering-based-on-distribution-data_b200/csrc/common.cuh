@@ -11,6 +11,7 @@
 #define VRDD_BINS 32                 // volumeRender_kernel.cu:91 (nBins); the only supported value
 #define VRDD_ERR_CHUNK 32            // voxels per entry of the fractal error-offset table (one warp)
 #define VRDD_MAX_TF 1024             // transfer-function entries kept in shared memory
+#define VRDD_MAX_PEERS 7             // other ranks of an 8-GPU node
 
 // Dataset scale constants of the reference (volumeRender_kernel.cu:736, 758-759)
 #define VRDD_MAX_HISTOGRAM 0.0217f
@@ -32,6 +33,11 @@ struct DecodeOut {
     long long v_base;                // global index of local voxel 0
     int bW, bH;                      // bricks per row / per slice (bricked layout)
     float inv_wh;                    // 1 / (W*H), for the index split in emit_decoded
+    // Replication fused into the decode (N > 1, vrdd_set_peer_planes): the linear planes of the OTHER ranks of the node,
+    // mapped over CUDA IPC; every decoded value is also stored at its global index in each of them, over NVLink, so the
+    // all-gather of the slabs costs no extra pass.  Planes a rank does not want replicated are nullptr.
+    int n_peers;
+    float* peer[VRDD_MAX_PEERS][3];
 };
 
 // Bricked layout for the manual sampler: 4x4x4-texel bricks, 256 B each (two 128-B lines),
@@ -59,6 +65,19 @@ __device__ __forceinline__ void split_voxel(const DecodeOut& o, long long gv, in
     x = r - y * o.W;
 }
 
+// Stores into the other ranks' linear planes (NVLink; consecutive lanes hold consecutive voxels, so a warp writes
+// whole 128-byte lines).  n_peers == 0 on a single GPU: one uniform branch.
+__device__ __forceinline__ void emit_to_peers(const DecodeOut& o, long long gv, float mean, float var, float ent) {
+#pragma unroll
+    for (int p = 0; p < VRDD_MAX_PEERS; ++p) {
+        if (p < o.n_peers) {
+            if (o.peer[p][0]) o.peer[p][0][gv] = mean;
+            if (o.peer[p][1]) o.peer[p][1][gv] = var;
+            if (o.peer[p][2]) o.peer[p][2][gv] = ent;
+        }
+    }
+}
+
 // Same sink with the voxel coordinate supplied by the caller (kernels that walk consecutive
 // tiles advance (x, y, z) incrementally instead of dividing per voxel).
 __device__ __forceinline__ void emit_decoded_xyz(const DecodeOut& o, long long v_local, int x, int y, int z, float mean,
@@ -76,6 +95,7 @@ __device__ __forceinline__ void emit_decoded_xyz(const DecodeOut& o, long long v
         const size_t bi = brick_index(x, y, z, o.bW, o.bH);
         o.brick[0][bi] = mean; o.brick[1][bi] = var; o.brick[2][bi] = ent;
     }
+    emit_to_peers(o, gv, mean, var, ent);
 }
 
 __device__ __forceinline__ void emit_decoded(const DecodeOut& o, long long v_local, float mean, float var,
@@ -97,6 +117,7 @@ __device__ __forceinline__ void emit_decoded(const DecodeOut& o, long long v_loc
             o.brick[0][bi] = mean; o.brick[1][bi] = var; o.brick[2][bi] = ent;
         }
     }
+    emit_to_peers(o, gv, mean, var, ent);
 }
 
 // ---- mbarrier / bulk-copy (TMA 1-D) PTX wrappers ------------------------------------------
@@ -166,6 +187,50 @@ __device__ __forceinline__ float fast_log2(float x) {
     return r;
 }
 __device__ __forceinline__ float plog2p(float p) { return p * fast_log2(fmaxf(p, 1.0e-37f)); }
+
+// ---- which pixel a thread renders: image-space tiles, 16x16-pixel blocks, 8x4 pixels per warp ----------------------
+// The image is cut into tile_w x tile_h tiles numbered row-major; a launch renders the tiles with index % parts == part
+// (vrdd_tile_partition).  Every tile is covered by blocks of 256 threads = 16x16 pixels, each warp an 8x4 sub-tile, so
+// the eight texels around the 32 samples of one step share cache lines.  Shared by every ray kernel of vrdd_render.
+struct TileMap {
+    int iw, ih;
+    int tile_w, tile_h, tiles_x, part, parts;
+    int blocks_x, blocks_per_tile;                                   // 16x16-pixel blocks inside a tile
+    __device__ __forceinline__ bool pixel(int& x, int& y) const {
+        const int lt = blockIdx.x / blocks_per_tile;                 // my tile number
+        const int bt = blockIdx.x - lt * blocks_per_tile;            // block inside the tile
+        const int gt = part + lt * parts;                            // global tile index
+        const int ty = gt / tiles_x, tx = gt - ty * tiles_x;
+        const int by = bt / blocks_x, bx = bt - by * blocks_x;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int lx = bx * 16 + (warp & 1) * 8 + (lane & 7);
+        const int ly = by * 16 + (warp >> 1) * 4 + (lane >> 3);
+        x = tx * tile_w + lx; y = ty * tile_h + ly;
+        return lx < tile_w && ly < tile_h && x < iw && y < ih;
+    }
+};
+
+// ---- frame-complete signal (vrdd_set_frame_signal) -----------------------------------------------------------------
+// N ranks store their tiles into one frame in rank 0's memory; instead of a host barrier per frame, the LAST block of
+// each rank's launch bumps a counter next to that frame with system-scope release semantics, and the owner's stream
+// waits for the count (vrdd_stream_wait_flag).  Every block: stores -> __syncthreads -> system fence -> local ticket;
+// the block that draws the last ticket has (cumulatively) all stores of the launch before it and publishes.
+struct FrameSignal {
+    unsigned* flag;            // device pointer, possibly into a peer's memory; nullptr = no signal
+    unsigned* tickets;         // this context's block counter (zero between launches)
+    __device__ __forceinline__ void block_done() const {
+        if (!flag) return;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(tickets, 1u) == gridDim.x - 1) {
+                *tickets = 0u;                                         // the next launch on this stream starts from zero
+                __threadfence_system();
+                asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+            }
+        }
+    }
+};
 
 // ---- eye ray of a pixel (volumeRender_kernel.cu:282-312, intersectBox :136-156, mul :168-184) -----------------
 // Shared by every ray kernel (raycast.cu, sortlast.cu, flex.cu), so all of them — and every rank — agree bit for bit
@@ -298,6 +363,12 @@ struct vrdd_context {
     unsigned long long* d_samples = nullptr;
     bool count_samples = false;
 
+    unsigned* d_tickets = nullptr;   // block counter of the frame-complete signal (FrameSignal)
+    unsigned* frame_signal = nullptr;   // vrdd_set_frame_signal: bumped by the last block of every vrdd_render launch
+
+    int n_peers[2] = {0, 0};         // vrdd_set_peer_planes: the other ranks' linear planes, per source
+    float* peer_planes[2][VRDD_MAX_PEERS][3] = {};
+
     vrdd_flex_state* flex = nullptr; // span store + block volume of the flexible-block chain
 
     uint32_t* frame = nullptr;       // device frame of vrdd_render_host, kept between calls
@@ -345,6 +416,10 @@ int build_template_moments(vrdd_context* c, const float* d_tmpl, int T);
 bool point_rule_is_regular(int n);       // raycast.cu: does the point rule map boundary k to texel min(k, n - 1)?
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses);
+// host side of TileMap: fills `tm`, returns the grid size (0: this part owns no tile, -1: bad partition / too large)
+long long make_tile_map(int iw, int ih, const vrdd_tile_partition& part, TileMap* tm);
+int launch_stream_wait_flag(vrdd_context* c, const unsigned* d_flag, unsigned at_least);
+int launch_stream_post_flag(vrdd_context* c, unsigned* d_flag);
 void invalidate_gather_copies(vrdd_decoded_volume& v);   // after a decode / commit: the copies no longer match the 3-D arrays
 int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_hist);
 int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int z0, int nz, int32_t* d_cb,
@@ -357,7 +432,8 @@ int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_rows, int gx, in
                             const int* row0, int rows, float* d_alpha_in, int iw, int ih);
 int launch_pack_frame(vrdd_context* c, const float* d_sum4, uint32_t* d_out, int iw, int ih, float brightness);
 void destroy_flex(vrdd_context* c);
-int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p, int clear_misses);
+int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
+                        const vrdd_tile_partition& part, int clear_misses);
 int launch_debug_sample(vrdd_context* c, cudaTextureObject_t tex, const float* d_uvw, int n, float* d_out);
 int launch_debug_sample_tf(vrdd_context* c, const float* d_u, int n, float* d_out4);
 

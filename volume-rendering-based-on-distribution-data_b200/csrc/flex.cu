@@ -190,6 +190,8 @@ struct FlexRayArgs {
     float density, brightness, t_offset, t_scale, tstep, thresh;
     int max_steps, clear_misses;
     int ref_rounding;               // ray set-up rounded like the reference's nvcc build (common.cuh, eye_ray)
+    TileMap tiles;                  // which pixels this launch renders (common.cuh)
+    FrameSignal done;
     unsigned long long* samples;
 };
 
@@ -218,12 +220,11 @@ __global__ void __launch_bounds__(256) raycast_flex_kernel(const FlexRayArgs A) 
     __shared__ float4 tf_s[VRDD_MAX_TF];
     for (int i = threadIdx.x; i < A.tf_n; i += 256) tf_s[i] = A.tf_tab[i];
     __syncthreads();
-    const int blocks_x = (A.iw + 15) / 16;
-    const int by = blockIdx.x / blocks_x, bx = blockIdx.x - by * blocks_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = bx * 16 + (warp & 1) * 8 + (lane & 7), y = by * 16 + (warp >> 1) * 4 + (lane >> 3);
+    int x, y;
+    const bool mine = A.tiles.pixel(x, y);
+    const int lane = threadIdx.x & 31;
     unsigned long long nsamp = 0;
-    if (x < A.iw && y < A.ih) {
+    if (mine) {
         const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
         const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
         float tnear = R.tnear;
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(256) raycast_flex_kernel(const FlexRayArgs A) 
         for (int d = 16; d > 0; d >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, d);
         if (lane == 0 && nsamp) atomicAdd(A.samples, nsamp);
     }
+    A.done.block_done();
 }
 
 void free_flex(vrdd_flex_state* f) {
@@ -323,7 +325,8 @@ void destroy_flex(vrdd_context* c) {
     c->flex = nullptr;
 }
 
-int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p, int clear_misses) {
+int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
+                        const vrdd_tile_partition& part, int clear_misses) {
     vrdd_flex_state* f = c->flex;
     if (!f || !f->blocks) return fail(c, VRDD_ERR_INVALID, "render: queryMethod 8/9/0 needs vrdd_flex_process first");
     if (iw <= 0 || ih <= 0 || !d_out) return fail(c, VRDD_ERR_INVALID, "render: bad image");
@@ -337,9 +340,12 @@ int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const 
     A.tstep = p.tstep; A.thresh = p.opacity_threshold; A.max_steps = p.max_steps; A.clear_misses = clear_misses;
     A.ref_rounding = c->var_ray_setup;
     A.samples = c->d_samples;
-    const int grid = ((iw + 15) / 16) * ((ih + 15) / 16);
-    if (c->count_samples && c->d_samples) raycast_flex_kernel<true><<<grid, 256, 0, c->stream>>>(A);
-    else raycast_flex_kernel<false><<<grid, 256, 0, c->stream>>>(A);
+    const long long grid = make_tile_map(iw, ih, part, &A.tiles);
+    if (grid < 0) return fail(c, VRDD_ERR_INVALID, "render: bad tile partition or image too large");
+    if (grid == 0) return c->frame_signal ? launch_stream_post_flag(c, c->frame_signal) : VRDD_OK;
+    A.done.flag = c->frame_signal; A.done.tickets = c->d_tickets;
+    if (c->count_samples && c->d_samples) raycast_flex_kernel<true><<<(unsigned)grid, 256, 0, c->stream>>>(A);
+    else raycast_flex_kernel<false><<<(unsigned)grid, 256, 0, c->stream>>>(A);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;

@@ -48,8 +48,8 @@ struct RayArgs {
     float m[12];
     float density, brightness, t_offset, t_scale, tstep, thresh;
     int max_steps;
-    int tile_w, tile_h, tiles_x, part, parts, n_my_tiles;
-    int blocks_x, blocks_per_tile;   // 16x16-pixel blocks inside a tile
+    TileMap tiles;                   // which pixels this launch renders (common.cuh)
+    FrameSignal done;                // frame-complete signal (common.cuh)
     int clear_misses;
     int ref_rounding;                // ray set-up rounded like the reference's nvcc build (common.cuh, eye_ray)
     unsigned long long* samples;
@@ -135,19 +135,12 @@ __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
         __syncthreads();
     }
 
-    // ---- which pixel ----------------------------------------------------------------
-    const int lt = blockIdx.x / A.blocks_per_tile;                 // my tile number
-    const int bt = blockIdx.x - lt * A.blocks_per_tile;            // block inside the tile
-    const int gt = A.part + lt * A.parts;                          // global tile index
-    const int ty = gt / A.tiles_x, tx = gt - ty * A.tiles_x;
-    const int by = bt / A.blocks_x, bx = bt - by * A.blocks_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lx = bx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int ly = by * 16 + (warp >> 1) * 4 + (lane >> 3);
-    const int x = tx * A.tile_w + lx, y = ty * A.tile_h + ly;
+    int x, y;
+    const bool mine = A.tiles.pixel(x, y);                          // which pixel (common.cuh, TileMap)
+    const int lane = threadIdx.x & 31;
     unsigned long long nsamp = 0;
 
-    if (lx < A.tile_w && ly < A.tile_h && x < A.iw && y < A.ih) {
+    if (mine) {
         // ---- eye ray, slab test (volumeRender_kernel.cu:288-303): common.cuh, eye_ray ---------
         const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
         const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
@@ -224,6 +217,7 @@ __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
         for (int d = 16; d > 0; d >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, d);
         if (lane == 0 && nsamp) atomicAdd(A.samples, nsamp);
     }
+    A.done.block_done();
 }
 
 // ---- queryMethod 7: interpolated mean (volumeRender_kernel.cu:253-270, 320-367, 395-480) ---------------
@@ -275,6 +269,8 @@ struct Mode7Args {
     float m[12];
     float density, brightness, t_offset, t_scale, tstep, thresh;
     int max_steps, clear_misses;
+    TileMap tiles;
+    FrameSignal done;
     int use_tab, idx32;
     int ref_rounding;                // ray set-up rounded like the reference's nvcc build (common.cuh, eye_ray)
     unsigned long long* samples;
@@ -318,12 +314,11 @@ __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Arg
         }
     }
     __syncthreads();
-    const int blocks_x = (A.iw + 15) / 16;
-    const int by = blockIdx.x / blocks_x, bx = blockIdx.x - by * blocks_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = bx * 16 + (warp & 1) * 8 + (lane & 7), y = by * 16 + (warp >> 1) * 4 + (lane >> 3);
+    int x, y;
+    const bool mine = A.tiles.pixel(x, y);
+    const int lane = threadIdx.x & 31;
     unsigned long long nsamp = 0;
-    if (x < A.iw && y < A.ih) {
+    if (mine) {
         const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
         const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
         float tnear = R.tnear;
@@ -475,6 +470,7 @@ __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Arg
         for (int d = 16; d > 0; d >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, d);
         if (lane == 0 && nsamp) atomicAdd(A.samples, nsamp);
     }
+    A.done.block_done();
 }
 
 __global__ void debug_sample_kernel(cudaTextureObject_t tex, const float* __restrict__ uvw, int n,
@@ -574,17 +570,11 @@ __global__ void __launch_bounds__(kBlock) raycast_gather_kernel(const RayArgs A)
     __shared__ float4 tf_s[VRDD_MAX_TF];
     for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
     __syncthreads();
-    const int lt = blockIdx.x / A.blocks_per_tile;
-    const int bt = blockIdx.x - lt * A.blocks_per_tile;
-    const int gt = A.part + lt * A.parts;
-    const int ty = gt / A.tiles_x, tx = gt - ty * A.tiles_x;
-    const int by = bt / A.blocks_x, bx = bt - by * A.blocks_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lx = bx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int ly = by * 16 + (warp >> 1) * 4 + (lane >> 3);
-    const int x = tx * A.tile_w + lx, y = ty * A.tile_h + ly;
+    int x, y;
+    const bool mine = A.tiles.pixel(x, y);
+    const int lane = threadIdx.x & 31;
     unsigned long long nsamp = 0;
-    if (lx < A.tile_w && ly < A.tile_h && x < A.iw && y < A.ih) {
+    if (mine) {
         const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
         const float tfar = R.tfar;
         float tnear = R.tnear;
@@ -640,6 +630,7 @@ __global__ void __launch_bounds__(kBlock) raycast_gather_kernel(const RayArgs A)
         for (int d = 16; d > 0; d >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, d);
         if (lane == 0 && nsamp) atomicAdd(A.samples, nsamp);
     }
+    A.done.block_done();
 }
 
 // 3-D array (x fastest) -> layered copy: 32x32 tiles through shared memory, coalesced on both sides.
@@ -699,6 +690,54 @@ bool point_rule_is_regular(int n) {
     return true;
 }
 
+
+long long make_tile_map(int iw, int ih, const vrdd_tile_partition& part, TileMap* tm) {
+    if (iw <= 0 || ih <= 0 || part.parts < 1 || part.part < 0 || part.part >= part.parts || part.tile_w < 1 || part.tile_h < 1)
+        return -1;
+    tm->iw = iw; tm->ih = ih;
+    tm->tile_w = part.tile_w; tm->tile_h = part.tile_h;
+    tm->tiles_x = (iw + part.tile_w - 1) / part.tile_w;
+    const int tiles_y = (ih + part.tile_h - 1) / part.tile_h;
+    const long long ntiles = (long long)tm->tiles_x * tiles_y;
+    tm->part = part.part; tm->parts = part.parts;
+    const long long mine = (ntiles - part.part + part.parts - 1) / part.parts;
+    tm->blocks_x = (part.tile_w + 15) / 16;
+    tm->blocks_per_tile = tm->blocks_x * ((part.tile_h + 15) / 16);
+    if (mine <= 0) return 0;
+    const long long grid = mine * tm->blocks_per_tile;
+    return grid > 0x7fffffffLL ? -1 : grid;
+}
+
+namespace {
+// The wait gives up after 10 s (a rank that died must not hang the device); a frame is then simply not ordered.
+__global__ void stream_wait_flag_kernel(const unsigned* flag, unsigned at_least) {
+    unsigned v;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while ((int)(v - at_least) < 0 && t1 - t0 < 10000000000ull);     // wrap-safe "v >= at_least"
+}
+__global__ void stream_post_flag_kernel(unsigned* flag) {
+    __threadfence_system();
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+}
+}  // namespace
+
+int launch_stream_wait_flag(vrdd_context* c, const unsigned* d_flag, unsigned at_least) {
+    stream_wait_flag_kernel<<<1, 1, 0, c->stream>>>(d_flag, at_least);
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+int launch_stream_post_flag(vrdd_context* c, unsigned* d_flag) {
+    stream_post_flag_kernel<<<1, 1, 0, c->stream>>>(d_flag);
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
 
 void invalidate_gather_copies(vrdd_decoded_volume& v) {
     for (int i = 0; i < 3; ++i)
@@ -785,17 +824,18 @@ void launch_gather(bool count, int grid, cudaStream_t st, const RayArgs& A, int 
 int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_render_params& p,
                    const vrdd_tile_partition& part, int clear_misses) {
     const int qm = p.query_method;
-    if (qm == 8 || qm == 9 || qm == 0) {                           // flexible blocks (:654-680)
-        if (part.parts != 1) return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod 8/9/0 does not take a tile partition");
-        return launch_raycast_flex(c, d_out, iw, ih, p, clear_misses);
-    }
+    if (qm == 8 || qm == 9 || qm == 0)                             // flexible blocks (:654-680)
+        return launch_raycast_flex(c, d_out, iw, ih, p, part, clear_misses);
     if (qm == 7) {
         vrdd_decoded_volume& v0 = c->vol[VRDD_SRC_ORIGINAL];
         if (!v0.decoded || !v0.mean_raw)
             return fail(c, VRDD_ERR_INVALID, "render: queryMethod 7 needs vrdd_enable_interpolated_mean before the decode");
         if (iw <= 0 || ih <= 0 || !d_out) return fail(c, VRDD_ERR_INVALID, "render: bad image");
-        if (part.parts != 1) return fail(c, VRDD_ERR_UNSUPPORTED, "render: queryMethod 7 does not take a tile partition");
         Mode7Args A;
+        const long long grid7 = make_tile_map(iw, ih, part, &A.tiles);
+        if (grid7 < 0) return fail(c, VRDD_ERR_INVALID, "render: bad tile partition or image too large");
+        if (grid7 == 0) return c->frame_signal ? launch_stream_post_flag(c, c->frame_signal) : VRDD_OK;
+        A.done.flag = c->frame_signal; A.done.tickets = c->d_tickets;
         // fetch path: tld4 on the layered copy (default when it exists), else point fetches on the 3-D array,
         // else (or when asked for) plain loads from the linear plane — the same texels every time
         A.mean_raw = v0.mean_raw; A.mean_tex = (c->var_mode7 != 1) ? v0.mean_tex : 0; A.W = c->W; A.H = c->H; A.D = c->D;
@@ -807,7 +847,6 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         A.tstep = p.tstep; A.thresh = p.opacity_threshold; A.max_steps = p.max_steps; A.clear_misses = clear_misses;
         A.samples = c->d_samples;
         A.ref_rounding = c->var_ray_setup;
-        const int grid7 = ((iw + 15) / 16) * ((ih + 15) / 16);
         const size_t tab_bytes = sizeof(float2) * ((size_t)c->W + c->H + c->D + 9);
         A.use_tab = (c->W <= 8192 && c->H <= 8192 && c->D <= 8192 && tab_bytes <= 64 * 1024) ? 1 : 0;   // div_small's checked range
         A.idx32 = ((unsigned long long)c->W * c->H * c->D < (1ull << 31)) ? 1 : 0;
@@ -818,7 +857,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         auto k7 = gather ? (cnt ? raycast_mode7_kernel<true, 4, true> : raycast_mode7_kernel<false, 4, true>)
                          : (cnt ? raycast_mode7_kernel<true, 4, false> : raycast_mode7_kernel<false, 4, false>);
         VRDD_CUDA(c, cudaFuncSetAttribute(k7, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        k7<<<grid7, kBlock, smem7, c->stream>>>(A);
+        k7<<<(unsigned)grid7, kBlock, smem7, c->stream>>>(A);
         c->launches += 1;
         VRDD_CUDA(c, cudaGetLastError());
         return VRDD_OK;
@@ -830,8 +869,6 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
     vrdd_decoded_volume& vol = c->vol[source];
     if (!vol.decoded) return fail(c, VRDD_ERR_INVALID, "render: the requested volume has not been decoded");
     if (iw <= 0 || ih <= 0 || !d_out) return fail(c, VRDD_ERR_INVALID, "render: bad image");
-    if (part.parts < 1 || part.part < 0 || part.part >= part.parts || part.tile_w < 1 || part.tile_h < 1)
-        return fail(c, VRDD_ERR_INVALID, "render: bad tile partition");
 
     RayArgs A;
     A.vol_tex = vol.tex[comp];
@@ -842,20 +879,13 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
     for (int i = 0; i < 12; ++i) A.m[i] = c->view[i];
     A.density = p.density; A.brightness = p.brightness; A.t_offset = p.transfer_offset;
     A.t_scale = p.transfer_scale; A.tstep = p.tstep; A.thresh = p.opacity_threshold; A.max_steps = p.max_steps;
-    A.tile_w = part.tile_w; A.tile_h = part.tile_h;
-    A.tiles_x = (iw + part.tile_w - 1) / part.tile_w;
-    const int tiles_y = (ih + part.tile_h - 1) / part.tile_h;
-    const int ntiles = A.tiles_x * tiles_y;
-    A.part = part.part; A.parts = part.parts;
-    A.n_my_tiles = (ntiles - part.part + part.parts - 1) / part.parts;
-    A.blocks_x = (part.tile_w + 15) / 16;
-    A.blocks_per_tile = A.blocks_x * ((part.tile_h + 15) / 16);
+    const long long grid = make_tile_map(iw, ih, part, &A.tiles);
+    if (grid < 0) return fail(c, VRDD_ERR_INVALID, "render: bad tile partition or image too large");
+    A.done.flag = c->frame_signal; A.done.tickets = c->d_tickets;
     A.clear_misses = clear_misses;
     A.ref_rounding = c->var_ray_setup;
     A.samples = c->d_samples;
-    if (A.n_my_tiles <= 0) return VRDD_OK;
-    const long long grid = (long long)A.n_my_tiles * A.blocks_per_tile;
-    if (grid > 0x7fffffffLL) return fail(c, VRDD_ERR_INVALID, "render: image too large");
+    if (grid == 0) return c->frame_signal ? launch_stream_post_flag(c, c->frame_signal) : VRDD_OK;   // no tile of mine: still counted
 
     if (c->sampler == VRDD_SAMPLER_LINEAR)
         return fail(c, VRDD_ERR_INVALID, "render: VRDD_SAMPLER_LINEAR volumes are rendered with vrdd_render_brick_*");
