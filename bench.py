@@ -319,8 +319,8 @@ class PeerFrames:
         r.render(self.frames[s], fw, fh, params, part=part, clear_misses=True)
         r.set_frame_signal(None)
         if self.ctx.rank == 0:
-            r.stream_wait_flag(self.done[s], self.ctx.world * (k // 2 + 1))      # all ranks' tiles of frame k are in
-            r.stream_post_flag(self.consumed)
+            # all ranks' tiles of frame k are in -> consumed (one stream operation)
+            r.stream_wait_post_flag(self.done[s], self.ctx.world * (k // 2 + 1), self.consumed)
         self.frame_no = k + 1
         return s
 
@@ -457,7 +457,7 @@ def run_ours(args):
         replicate = {"fused": fused}
         if fused:
             times = {}
-            for name, mask in (("mean", 1), ("variance_entropy", 6)):
+            for name, mask in (("all_planes", 7), ("mean", 1), ("variance_entropy", 6)):
                 barrier()
                 e0, e1, e2 = ev(), ev(), ev()
                 e0.record()
@@ -474,9 +474,9 @@ def run_ours(args):
             replicate.update(times)
             replicate["note"] = ("decode of my z-slab with the other ranks' planes attached (vrdd_set_peer_planes): the decode "
                                  "kernel stores into all N copies over NVLink; then the received slabs are committed to the 3-D "
-                                 "arrays.  mean = what the frames sample (decode + replicate + commit); variance_entropy = the "
-                                 "other two planes, afterwards")
-            replicate["bytes_sent_per_rank"] = {"mean": nz_mine * slice_vox * 4 * (world - 1),
+                                 "arrays.  all_planes = one pass for the three planes; mean = only what the frames sample (decode + "
+                                 "replicate + commit), variance_entropy = the other two planes afterwards")
+            replicate["bytes_sent_per_rank"] = {"all_planes": nz_mine * slice_vox * 12 * (world - 1), "mean": nz_mine * slice_vox * 4 * (world - 1),
                                                 "variance_entropy": nz_mine * slice_vox * 8 * (world - 1)}
         # comparison / fallback: in-place NCCL all-gather of the mean plane (and of all planes when IPC is not available)
         planes_t = [V.as_torch(p, (Dz * slice_vox,), device=dev) for p in my_planes]

@@ -256,10 +256,13 @@ int vrdd_frame_close(vrdd_handle h, void* d_peer_frame);
  * the frame.  The owner orders its stream behind the N ranks with vrdd_stream_wait_flag(h, d_flag, generation * N):
  * the stream (not the host) waits until *d_flag >= at_least.  vrdd_stream_post_flag adds 1 from the stream (e.g. "frame
  * consumed, its buffer may be overwritten", which the other ranks wait for before they render into it again).
- * NULL switches the signal off.  Counters only grow; the caller keeps track of the generation. */
+ * NULL switches the signal off.  Counters only grow; the caller keeps track of the generation.  A wait gives up after
+ * 10 s, so that a rank that died cannot hang the device. */
 int vrdd_set_frame_signal(vrdd_handle h, uint32_t* d_flag);
 int vrdd_stream_wait_flag(vrdd_handle h, const uint32_t* d_flag, uint32_t at_least);
 int vrdd_stream_post_flag(vrdd_handle h, uint32_t* d_flag);
+/* vrdd_stream_wait_flag(d_wait, at_least) followed by vrdd_stream_post_flag(d_post), as one stream operation. */
+int vrdd_stream_wait_post_flag(vrdd_handle h, const uint32_t* d_wait, uint32_t at_least, uint32_t* d_post);
 
 /* Replication of the decoded planes fused into the decode (N ranks, each decoding its z-slab of a volume that every
  * rank samples): d_planes[3 * q + i] is plane i (mean, variance, entropy) of peer q's LINEAR planes

@@ -26,6 +26,14 @@
 // kernels that ran before it that is their stack garbage ("flex" mode shows it: values like -3.7e19 in the
 // histograms), on scrubbed memory it is zero — the deterministic form of the reference's build, the one its fixed
 // path meets on a fresh context and the one tools/ref_pin_flex.py models.
+// Mode "headline <plane.f32> <N> <reps>": the reference's OWN d_render at the size of the headline benchmark.  The file
+// holds one fp32 plane of an N^3 volume (the mean plane libvrdd decoded, written by tools/ref_speed_headline.py); it
+// becomes the .x lane of an N^3 float4 array — the reference's layout, 16 B per texel (volumeRender_kernel.cu:86,
+// 1865-1876) — which is bound to originalQueryTex in place of the 50x50x10 array basicDataProcessing() made; then
+// render_kernel (:2387-2401) is launched as render() launches it (16x16 blocks, default parameters, queryMethod 1) for
+// every view of <dir>/in/views.f32 at <width> x <height>: frames go to <dir>/out/headline_v<k>.u32, the time per
+// frame (CUDA events, 1 warm-up + <reps> launches) is printed.  The reference's unconditional 8x33-fetch prologue
+// and its dead 32-fetch per-step loop (:354-367, :605-612) run as written: that is its kernel.
 // Test infrastructure: only tests/ and tools/ run this binary, never the product.
 #include REF_KERNEL_CU
 
@@ -66,7 +74,7 @@ void write_file(const std::string& path, const void* p, size_t bytes) {
 
 int main(int argc, char** argv) {
     if (argc < 5) {
-        std::fprintf(stderr, "usage: ref_driver <dir> <width> <height> <nviews> [time|flex|flexscrub [blockSize]]\n");
+        std::fprintf(stderr, "usage: ref_driver <dir> <width> <height> <nviews> [time | flex | flexscrub [blockSize] | headline <plane.f32> <N> [reps]]\n");
         return 2;
     }
     const std::string dir = argv[1];
@@ -173,7 +181,8 @@ int main(int argc, char** argv) {
     std::vector<uint> img((size_t)W * H);
     const dim3 blockSize(16, 16);
     const dim3 gridSize((W + 15) / 16, (H + 15) / 16);
-    for (int k = 0; k < nviews; ++k) {
+    const bool headline = argc > 7 && std::string(argv[5]) == "headline";
+    for (int k = 0; k < (headline ? 0 : nviews); ++k) {            // (headline mode renders its own frames below)
         copyInvViewMatrix(views.data() + 12 * k, sizeof(float4) * 3);
         for (int qm = flex ? 0 : 1; qm <= (flex ? 9 : 7); ++qm) {       // 8, 9, 0 sample the flexible-block volume
             checkCudaErrors(cudaMemset(d_output, 0, (size_t)W * H * sizeof(uint)));
@@ -184,6 +193,50 @@ int main(int argc, char** argv) {
             write_file(dir + "/out/img_v" + std::to_string(k) + "_q" + std::to_string(qm) + ".u32", img.data(),
                        img.size() * sizeof(uint));
         }
+    }
+    if (headline) {
+        const int N = std::atoi(argv[7]);
+        const int reps = argc > 8 ? std::atoi(argv[8]) : 5;
+        const size_t nv = (size_t)N * N * N;
+        std::vector<float> plane = read_file<float>(argv[6], nv);
+        std::vector<float4> vol4(nv);
+        for (size_t i = 0; i < nv; ++i) vol4[i] = make_float4(plane[i], 0.f, 0.f, 0.f);
+        plane.clear(); plane.shrink_to_fit();
+        cudaArray* big = nullptr;
+        cudaChannelFormatDesc desc4 = cudaCreateChannelDesc<float4>();
+        checkCudaErrors(cudaMalloc3DArray(&big, &desc4, make_cudaExtent(N, N, N)));
+        cudaMemcpy3DParms cp = {0};
+        cp.srcPtr = make_cudaPitchedPtr(vol4.data(), (size_t)N * sizeof(float4), N, N);
+        cp.dstArray = big;
+        cp.extent = make_cudaExtent(N, N, N);
+        cp.kind = cudaMemcpyHostToDevice;
+        checkCudaErrors(cudaMemcpy3D(&cp));
+        vol4.clear(); vol4.shrink_to_fit();
+        // the texture modes basicDataProcessing() set stay (normalised, linear, clamp: :1865-1870); only the array changes
+        checkCudaErrors(cudaBindTextureToArray(originalQueryTex, big, desc4));
+        const cudaExtent bigSize = make_cudaExtent(N, N, N);
+        cudaEvent_t e0, e1;
+        checkCudaErrors(cudaEventCreate(&e0)); checkCudaErrors(cudaEventCreate(&e1));
+        double total_ms = 0.0;
+        for (int k = 0; k < nviews; ++k) {
+            copyInvViewMatrix(views.data() + 12 * k, sizeof(float4) * 3);
+            checkCudaErrors(cudaMemset(d_output, 0, (size_t)W * H * sizeof(uint)));
+            render_kernel(gridSize, blockSize, d_output, W, H, 0.05f, 1.0f, 0.0f, 1.0f, 1, bigSize);
+            getLastCudaError("render_kernel failed");
+            checkCudaErrors(cudaDeviceSynchronize());
+            checkCudaErrors(cudaMemcpy(img.data(), d_output, img.size() * sizeof(uint), cudaMemcpyDeviceToHost));
+            write_file(dir + "/out/headline_v" + std::to_string(k) + ".u32", img.data(), img.size() * sizeof(uint));
+            checkCudaErrors(cudaEventRecord(e0));
+            for (int i = 0; i < reps; ++i) render_kernel(gridSize, blockSize, d_output, W, H, 0.05f, 1.0f, 0.0f, 1.0f, 1, bigSize);
+            checkCudaErrors(cudaEventRecord(e1));
+            checkCudaErrors(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            checkCudaErrors(cudaEventElapsedTime(&ms, e0, e1));
+            std::printf("ref_headline view %d: %.4f ms per frame (%ux%u, %d^3 float4 volume)\n", k, ms / reps, W, H, N);
+            total_ms += ms / reps;
+        }
+        std::printf("ref_headline mean: %.4f ms per frame over %d views\n", total_ms / nviews, nviews);
+        checkCudaErrors(cudaFreeArray(big));
     }
     // Optional: how long the reference's own kernels take on this GPU at the reference's configuration
     // (its runSingleTest pattern, volumeRender.cpp:1048-1067: a warm-up launch, then timed launches).

@@ -38,7 +38,7 @@ EXPORTS = [
     "vrdd_flex_divide_blocks", "vrdd_flex_prefix_spans", "vrdd_flex_set_tables_host", "vrdd_flex_process",
     "vrdd_flex_get_blocks_host",
     "vrdd_frame_alloc", "vrdd_frame_free", "vrdd_frame_export", "vrdd_frame_open", "vrdd_frame_close",
-    "vrdd_set_frame_signal", "vrdd_stream_wait_flag", "vrdd_stream_post_flag", "vrdd_set_peer_planes",
+    "vrdd_set_frame_signal", "vrdd_stream_wait_flag", "vrdd_stream_post_flag", "vrdd_stream_wait_post_flag", "vrdd_set_peer_planes",
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_compose_alpha_in_rows", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
@@ -175,6 +175,7 @@ def lib():
             "vrdd_set_frame_signal": (i32, [vp, vp]),
             "vrdd_stream_wait_flag": (i32, [vp, vp, u32]),
             "vrdd_stream_post_flag": (i32, [vp, vp]),
+            "vrdd_stream_wait_post_flag": (i32, [vp, vp, u32, vp]),
             "vrdd_set_peer_planes": (i32, [vp, i32, i32, vp]),
             # on-disk formats (include/vrdd_io.h)
             "vrdd_io_read_histograms": (i32, [C.c_char_p, C.c_size_t, i32, vp]),
@@ -480,6 +481,9 @@ class Renderer:
 
     def stream_post_flag(self, d_flag):
         self._ck(lib().vrdd_stream_post_flag(self._h, _ptr(d_flag)))
+
+    def stream_wait_post_flag(self, d_wait, at_least, d_post):
+        self._ck(lib().vrdd_stream_wait_post_flag(self._h, _ptr(d_wait), int(at_least) & 0xffffffff, _ptr(d_post)))
 
     def set_peer_planes(self, source, peers):
         """peers: list (one entry per other rank) of 3 device pointers (mean, variance, entropy planes; None = skip)."""

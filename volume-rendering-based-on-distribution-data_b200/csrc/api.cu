@@ -249,8 +249,8 @@ int vrdd_create(int device, vrdd_handle* out) {
     }
     if (cudaMalloc(&c->d_samples, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(c->d_samples, 0, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc(&c->d_tickets, sizeof(unsigned)) != cudaSuccess ||
-        cudaMemset(c->d_tickets, 0, sizeof(unsigned)) != cudaSuccess) {
+        cudaMalloc(&c->d_tickets, 2 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(c->d_tickets, 0, 2 * sizeof(unsigned)) != cudaSuccess) {
         delete c;
         return VRDD_ERR_CUDA;
     }
@@ -862,7 +862,13 @@ int vrdd_set_frame_signal(vrdd_handle h, uint32_t* d_flag) {
 int vrdd_stream_wait_flag(vrdd_handle h, const uint32_t* d_flag, uint32_t at_least) {
     CHECK_HANDLE(h);
     if (!d_flag) return fail(c, VRDD_ERR_INVALID, "stream_wait_flag: null flag");
-    return launch_stream_wait_flag(c, d_flag, at_least);
+    return launch_stream_wait_flag(c, d_flag, at_least, nullptr);
+}
+
+int vrdd_stream_wait_post_flag(vrdd_handle h, const uint32_t* d_wait, uint32_t at_least, uint32_t* d_post) {
+    CHECK_HANDLE(h);
+    if (!d_wait || !d_post) return fail(c, VRDD_ERR_INVALID, "stream_wait_post_flag: null flag");
+    return launch_stream_wait_flag(c, d_wait, at_least, d_post);
 }
 
 int vrdd_stream_post_flag(vrdd_handle h, uint32_t* d_flag) {

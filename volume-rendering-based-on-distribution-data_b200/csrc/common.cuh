@@ -196,9 +196,10 @@ struct TileMap {
     int iw, ih;
     int tile_w, tile_h, tiles_x, part, parts;
     int blocks_x, blocks_per_tile;                                   // 16x16-pixel blocks inside a tile
-    __device__ __forceinline__ bool pixel(int& x, int& y) const {
-        const int lt = blockIdx.x / blocks_per_tile;                 // my tile number
-        const int bt = blockIdx.x - lt * blocks_per_tile;            // block inside the tile
+    int n_items;                                                     // 16x16-pixel blocks this launch renders
+    __device__ __forceinline__ bool pixel(int item, int& x, int& y) const {
+        const int lt = item / blocks_per_tile;                       // my tile number
+        const int bt = item - lt * blocks_per_tile;                  // block inside the tile
         const int gt = part + lt * parts;                            // global tile index
         const int ty = gt / tiles_x, tx = gt - ty * tiles_x;
         const int by = bt / blocks_x, bx = bt - by * blocks_x;
@@ -210,23 +211,47 @@ struct TileMap {
     }
 };
 
-// ---- frame-complete signal (vrdd_set_frame_signal) -----------------------------------------------------------------
-// N ranks store their tiles into one frame in rank 0's memory; instead of a host barrier per frame, the LAST block of
-// each rank's launch bumps a counter next to that frame with system-scope release semantics, and the owner's stream
-// waits for the count (vrdd_stream_wait_flag).  Every block: stores -> __syncthreads -> system fence -> local ticket;
-// the block that draws the last ticket has (cumulatively) all stores of the launch before it and publishes.
+// ---- persistent blocks, work queue and frame-complete signal ------------------------------------------------------
+// A ray kernel is launched with as many 256-thread blocks as the device holds at once; each block takes 16x16-pixel
+// items from a queue (tickets[1]) until none is left, then draws a ticket (tickets[0]); the block that draws the last
+// one resets both counters for the next launch of this context's stream.
+// Frame-complete signal (vrdd_set_frame_signal): N ranks store their tiles into one frame in rank 0's memory; instead of
+// a host barrier per frame, the last block of each rank's launch bumps a counter next to that frame with system-scope
+// release semantics, and the owner's stream waits for the count (vrdd_stream_wait_flag).  Every block: stores ->
+// __syncthreads -> system fence -> ticket; the block that draws the last ticket has (cumulatively) all stores of the
+// launch before it and publishes.  Persistent blocks keep that to one fence per resident block instead of one per item.
 struct FrameSignal {
     unsigned* flag;            // device pointer, possibly into a peer's memory; nullptr = no signal
-    unsigned* tickets;         // this context's block counter (zero between launches)
+    unsigned* tickets;         // this context's counters: [0] finished blocks, [1] next item (both zero between launches)
+    // The queue: thread 0 draws the NEXT item while the block works on the current one, so the atomic's latency is hidden
+    // and an item costs one __syncthreads.  for (item = queue_begin(); item < n; item = queue_next(it++)) { queue_prefetch(it); ... }
+    __device__ __forceinline__ int* queue_slots() const {
+        __shared__ int s_item[2];
+        return s_item;
+    }
+    __device__ __forceinline__ int queue_begin() const {             // the same value for every thread of the block
+        int* s = queue_slots();
+        if (threadIdx.x == 0) s[0] = (int)atomicAdd(tickets + 1, 1u);
+        __syncthreads();
+        return s[0];
+    }
+    __device__ __forceinline__ void queue_prefetch(int it) const {
+        if (threadIdx.x == 0) queue_slots()[(it + 1) & 1] = (int)atomicAdd(tickets + 1, 1u);
+    }
+    __device__ __forceinline__ int queue_next(int it) const {
+        __syncthreads();                                               // the slot is written; everybody is done with the other one
+        return queue_slots()[(it + 1) & 1];
+    }
     __device__ __forceinline__ void block_done() const {
-        if (!flag) return;
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence_system();
+            if (flag) __threadfence_system(); else __threadfence();
             if (atomicAdd(tickets, 1u) == gridDim.x - 1) {
-                *tickets = 0u;                                         // the next launch on this stream starts from zero
-                __threadfence_system();
-                asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+                tickets[0] = 0u; tickets[1] = 0u;                      // every block has left its loop: the next launch starts from zero
+                if (flag) {
+                    __threadfence_system();
+                    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+                }
             }
         }
     }
@@ -363,7 +388,7 @@ struct vrdd_context {
     unsigned long long* d_samples = nullptr;
     bool count_samples = false;
 
-    unsigned* d_tickets = nullptr;   // block counter of the frame-complete signal (FrameSignal)
+    unsigned* d_tickets = nullptr;   // {finished blocks, next item} of the persistent ray kernels (FrameSignal)
     unsigned* frame_signal = nullptr;   // vrdd_set_frame_signal: bumped by the last block of every vrdd_render launch
 
     int n_peers[2] = {0, 0};         // vrdd_set_peer_planes: the other ranks' linear planes, per source
@@ -418,7 +443,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
                    const vrdd_tile_partition& part, int clear_misses);
 // host side of TileMap: fills `tm`, returns the grid size (0: this part owns no tile, -1: bad partition / too large)
 long long make_tile_map(int iw, int ih, const vrdd_tile_partition& part, TileMap* tm);
-int launch_stream_wait_flag(vrdd_context* c, const unsigned* d_flag, unsigned at_least);
+int launch_stream_wait_flag(vrdd_context* c, const unsigned* d_flag, unsigned at_least, unsigned* d_post);
 int launch_stream_post_flag(vrdd_context* c, unsigned* d_flag);
 void invalidate_gather_copies(vrdd_decoded_volume& v);   // after a decode / commit: the copies no longer match the 3-D arrays
 int launch_synth_hist(vrdd_context* c, uint32_t seed, int z0, int nz, float* d_hist);

@@ -220,59 +220,62 @@ __global__ void __launch_bounds__(256) raycast_flex_kernel(const FlexRayArgs A) 
     __shared__ float4 tf_s[VRDD_MAX_TF];
     for (int i = threadIdx.x; i < A.tf_n; i += 256) tf_s[i] = A.tf_tab[i];
     __syncthreads();
-    int x, y;
-    const bool mine = A.tiles.pixel(x, y);
     const int lane = threadIdx.x & 31;
     unsigned long long nsamp = 0;
-    if (mine) {
-        const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
-        const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
-        float tnear = R.tnear;
-        if (tfar > tnear) {
-            if (tnear < 0.0f) tnear = 0.0f;
-            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, t = tnear;
-            float px, py, pz;
-            eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);
-            const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
-            for (int i = 0; i < A.max_steps; ++i) {
-                int ii, jj, kk, a, b, c;                                    // (pos01 * nFlexBlock), un-normalised (:655-657)
-                split_unnorm(__fmul_rn(fmaf(px, 0.5f, 0.5f), (float)A.nx), ii, a);
-                split_unnorm(__fmul_rn(fmaf(py, 0.5f, 0.5f), (float)A.ny), jj, b);
-                split_unnorm(__fmul_rn(fmaf(pz, 0.5f, 0.5f), (float)A.nz), kk, c);
-                const int z1 = c, z0 = 256 - c;
-                const int x10 = (z0 * a + 128) >> 8, x00 = z0 - x10, x11 = (z1 * a + 128) >> 8, x01 = z1 - x11;
-                const int w000 = (x00 * (256 - b) + 128) >> 8, w010 = x00 - w000, w110 = (x10 * b + 128) >> 8, w100 = x10 - w110;
-                const int w001 = (x01 * (256 - b) + 128) >> 8, w011 = x01 - w001, w111 = (x11 * b + 128) >> 8, w101 = x11 - w111;
-                float s = (float)w000 * flex_texel(A, ii, jj, kk);
-                s = fmaf((float)w010, flex_texel(A, ii, jj + 1, kk), s);
-                s = fmaf((float)w100, flex_texel(A, ii + 1, jj, kk), s);
-                s = fmaf((float)w110, flex_texel(A, ii + 1, jj + 1, kk), s);
-                s = fmaf((float)w001, flex_texel(A, ii, jj, kk + 1), s);
-                s = fmaf((float)w011, flex_texel(A, ii, jj + 1, kk + 1), s);
-                s = fmaf((float)w101, flex_texel(A, ii + 1, jj, kk + 1), s);
-                s = fmaf((float)w111, flex_texel(A, ii + 1, jj + 1, kk + 1), s);
-                s *= (1.0f / 256.0f);
-                if (COUNT) ++nsamp;
-                int ti, ta;
-                split_norm((s - A.t_offset) * A.t_scale, A.tf_n << 8, ti, ta);
-                const float4 c0 = tf_s[ti], c1 = tf_s[min(ti + 1, A.tf_n - 1)];
-                const float w0 = (float)(256 - ta) * (1.0f / 256.0f), w1 = (float)ta * (1.0f / 256.0f);
-                float4 col = make_float4(w0 * c0.x + w1 * c1.x, w0 * c0.y + w1 * c1.y, w0 * c0.z + w1 * c1.z, w0 * c0.w + w1 * c1.w);
-                col.w *= A.density;
-                col.x *= col.w; col.y *= col.w; col.z *= col.w;
-                const float k = 1.0f - sa;
-                sr += col.x * k; sg += col.y * k; sb += col.z * k; sa += col.w * k;
-                if (sa > A.thresh) break;
-                t = __fadd_rn(t, A.tstep);
-                if (t > tfar) break;
-                px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+    int it = 0;
+    for (int item = A.done.queue_begin(); item < A.tiles.n_items; item = A.done.queue_next(it++)) {
+        A.done.queue_prefetch(it);
+        int x, y;
+        if (A.tiles.pixel(item, x, y)) {
+            const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
+            const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
+            float tnear = R.tnear;
+            if (tfar > tnear) {
+                if (tnear < 0.0f) tnear = 0.0f;
+                float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, t = tnear;
+                float px, py, pz;
+                eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);
+                const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
+                for (int i = 0; i < A.max_steps; ++i) {
+                    int ii, jj, kk, a, b, c;                                    // (pos01 * nFlexBlock), un-normalised (:655-657)
+                    split_unnorm(__fmul_rn(fmaf(px, 0.5f, 0.5f), (float)A.nx), ii, a);
+                    split_unnorm(__fmul_rn(fmaf(py, 0.5f, 0.5f), (float)A.ny), jj, b);
+                    split_unnorm(__fmul_rn(fmaf(pz, 0.5f, 0.5f), (float)A.nz), kk, c);
+                    const int z1 = c, z0 = 256 - c;
+                    const int x10 = (z0 * a + 128) >> 8, x00 = z0 - x10, x11 = (z1 * a + 128) >> 8, x01 = z1 - x11;
+                    const int w000 = (x00 * (256 - b) + 128) >> 8, w010 = x00 - w000, w110 = (x10 * b + 128) >> 8, w100 = x10 - w110;
+                    const int w001 = (x01 * (256 - b) + 128) >> 8, w011 = x01 - w001, w111 = (x11 * b + 128) >> 8, w101 = x11 - w111;
+                    float s = (float)w000 * flex_texel(A, ii, jj, kk);
+                    s = fmaf((float)w010, flex_texel(A, ii, jj + 1, kk), s);
+                    s = fmaf((float)w100, flex_texel(A, ii + 1, jj, kk), s);
+                    s = fmaf((float)w110, flex_texel(A, ii + 1, jj + 1, kk), s);
+                    s = fmaf((float)w001, flex_texel(A, ii, jj, kk + 1), s);
+                    s = fmaf((float)w011, flex_texel(A, ii, jj + 1, kk + 1), s);
+                    s = fmaf((float)w101, flex_texel(A, ii + 1, jj, kk + 1), s);
+                    s = fmaf((float)w111, flex_texel(A, ii + 1, jj + 1, kk + 1), s);
+                    s *= (1.0f / 256.0f);
+                    if (COUNT) ++nsamp;
+                    int ti, ta;
+                    split_norm((s - A.t_offset) * A.t_scale, A.tf_n << 8, ti, ta);
+                    const float4 c0 = tf_s[ti], c1 = tf_s[min(ti + 1, A.tf_n - 1)];
+                    const float w0 = (float)(256 - ta) * (1.0f / 256.0f), w1 = (float)ta * (1.0f / 256.0f);
+                    float4 col = make_float4(w0 * c0.x + w1 * c1.x, w0 * c0.y + w1 * c1.y, w0 * c0.z + w1 * c1.z, w0 * c0.w + w1 * c1.w);
+                    col.w *= A.density;
+                    col.x *= col.w; col.y *= col.w; col.z *= col.w;
+                    const float k = 1.0f - sa;
+                    sr += col.x * k; sg += col.y * k; sb += col.z * k; sa += col.w * k;
+                    if (sa > A.thresh) break;
+                    t = __fadd_rn(t, A.tstep);
+                    if (t > tfar) break;
+                    px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+                }
+                A.out[(size_t)y * A.iw + x] = ((uint32_t)(__saturatef(sa * A.brightness) * 255.0f) << 24) |
+                                              ((uint32_t)(__saturatef(sb * A.brightness) * 255.0f) << 16) |
+                                              ((uint32_t)(__saturatef(sg * A.brightness) * 255.0f) << 8) |
+                                              (uint32_t)(__saturatef(sr * A.brightness) * 255.0f);
+            } else if (A.clear_misses) {
+                A.out[(size_t)y * A.iw + x] = 0u;
             }
-            A.out[(size_t)y * A.iw + x] = ((uint32_t)(__saturatef(sa * A.brightness) * 255.0f) << 24) |
-                                          ((uint32_t)(__saturatef(sb * A.brightness) * 255.0f) << 16) |
-                                          ((uint32_t)(__saturatef(sg * A.brightness) * 255.0f) << 8) |
-                                          (uint32_t)(__saturatef(sr * A.brightness) * 255.0f);
-        } else if (A.clear_misses) {
-            A.out[(size_t)y * A.iw + x] = 0u;
         }
     }
     if (COUNT) {
@@ -344,8 +347,11 @@ int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const 
     if (grid < 0) return fail(c, VRDD_ERR_INVALID, "render: bad tile partition or image too large");
     if (grid == 0) return c->frame_signal ? launch_stream_post_flag(c, c->frame_signal) : VRDD_OK;
     A.done.flag = c->frame_signal; A.done.tickets = c->d_tickets;
-    if (c->count_samples && c->d_samples) raycast_flex_kernel<true><<<(unsigned)grid, 256, 0, c->stream>>>(A);
-    else raycast_flex_kernel<false><<<(unsigned)grid, 256, 0, c->stream>>>(A);
+    // persistent blocks sharing the items through FrameSignal's queue (common.cuh): at most 8 blocks of 256 threads per SM
+    const long long cap = 8ll * c->num_sms;
+    const unsigned nblk = (unsigned)(grid < cap ? grid : cap);
+    if (c->count_samples && c->d_samples) raycast_flex_kernel<true><<<nblk, 256, 0, c->stream>>>(A);
+    else raycast_flex_kernel<false><<<nblk, 256, 0, c->stream>>>(A);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;

@@ -31,6 +31,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <map>
 
 namespace vrdd {
 
@@ -135,81 +136,83 @@ __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
         __syncthreads();
     }
 
-    int x, y;
-    const bool mine = A.tiles.pixel(x, y);                          // which pixel (common.cuh, TileMap)
     const int lane = threadIdx.x & 31;
     unsigned long long nsamp = 0;
+    int it = 0;
+    for (int item = A.done.queue_begin(); item < A.tiles.n_items; item = A.done.queue_next(it++)) {
+        A.done.queue_prefetch(it);
+        int x, y;
+        if (A.tiles.pixel(item, x, y)) {
+            // ---- eye ray, slab test (volumeRender_kernel.cu:288-303): common.cuh, eye_ray ---------
+            const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
+            const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
+            float tnear = R.tnear;
 
-    if (mine) {
-        // ---- eye ray, slab test (volumeRender_kernel.cu:288-303): common.cuh, eye_ray ---------
-        const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
-        const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
-        float tnear = R.tnear;
-
-        if (tfar > tnear) {
-            if (tnear < 0.0f) tnear = 0.0f;                                          // :305-306
-            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
-            float t = tnear;
-            float px, py, pz;
-            eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);                     // :311
-            const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
-            int i = 0;
-            bool alive = A.max_steps > 0;                 // the geometric state (i, t, p) is a live step
-            while (alive) {
-                // -- geometry of the next U steps (:381, :701-706), exactly as the one-step loop
-                float cu[U], cv[U], cw[U];
-                bool valid[U];
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    valid[k] = alive;
-                    // pos*0.5 is exact, so fma == mul-then-add here
-                    cu[k] = fmaf(px, 0.5f, 0.5f); cv[k] = fmaf(py, 0.5f, 0.5f); cw[k] = fmaf(pz, 0.5f, 0.5f);
-                    const float tn = __fadd_rn(t, A.tstep);
-                    const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
-                    if (cont) {
-                        t = tn; ++i;
-                        px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+            if (tfar > tnear) {
+                if (tnear < 0.0f) tnear = 0.0f;                                          // :305-306
+                float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
+                float t = tnear;
+                float px, py, pz;
+                eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);                     // :311
+                const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
+                int i = 0;
+                bool alive = A.max_steps > 0;                 // the geometric state (i, t, p) is a live step
+                while (alive) {
+                    // -- geometry of the next U steps (:381, :701-706), exactly as the one-step loop
+                    float cu[U], cv[U], cw[U];
+                    bool valid[U];
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        valid[k] = alive;
+                        // pos*0.5 is exact, so fma == mul-then-add here
+                        cu[k] = fmaf(px, 0.5f, 0.5f); cv[k] = fmaf(py, 0.5f, 0.5f); cw[k] = fmaf(pz, 0.5f, 0.5f);
+                        const float tn = __fadd_rn(t, A.tstep);
+                        const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
+                        if (cont) {
+                            t = tn; ++i;
+                            px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+                        }
+                        alive = cont;
                     }
-                    alive = cont;
-                }
-                // -- U volume fetches in flight (:601-651)
-                float s[U];
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    s[k] = 0.f;
-                    if (valid[k]) {
-                        if (SAMPLER == 0) s[k] = tex3D<float>(A.vol_tex, cu[k], cv[k], cw[k]);
-                        else s[k] = sample_bricked(A, cu[k], cv[k], cw[k]);
+                    // -- U volume fetches in flight (:601-651)
+                    float s[U];
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        s[k] = 0.f;
+                        if (valid[k]) {
+                            if (SAMPLER == 0) s[k] = tex3D<float>(A.vol_tex, cu[k], cv[k], cw[k]);
+                            else s[k] = sample_bricked(A, cu[k], cv[k], cw[k]);
+                        }
+                    }
+                    // -- U transfer-function lookups (:683-684)
+                    float4 col[U];
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        col[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid[k]) {
+                            const float tu = (s[k] - A.t_offset) * A.t_scale;
+                            if (TFMODE == 0) col[k] = tex1D<float4>(A.tf_tex, tu);
+                            else col[k] = tf_lookup_smem(tf_s, A.tf_n, tu);
+                        }
+                    }
+                    // -- front-to-back compositing, in order, with the early exit (:685-699)
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        if (!valid[k]) { alive = false; break; }
+                        if (COUNT) ++nsamp;
+                        float4 c = col[k];
+                        c.w *= A.density;
+                        c.x *= c.w; c.y *= c.w; c.z *= c.w;
+                        const float kk = 1.0f - sa;
+                        sr += c.x * kk; sg += c.y * kk; sb += c.z * kk; sa += c.w * kk;
+                        if (sa > A.thresh) { alive = false; break; }
                     }
                 }
-                // -- U transfer-function lookups (:683-684)
-                float4 col[U];
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    col[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid[k]) {
-                        const float tu = (s[k] - A.t_offset) * A.t_scale;
-                        if (TFMODE == 0) col[k] = tex1D<float4>(A.tf_tex, tu);
-                        else col[k] = tf_lookup_smem(tf_s, A.tf_n, tu);
-                    }
-                }
-                // -- front-to-back compositing, in order, with the early exit (:685-699)
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    if (!valid[k]) { alive = false; break; }
-                    if (COUNT) ++nsamp;
-                    float4 c = col[k];
-                    c.w *= A.density;
-                    c.x *= c.w; c.y *= c.w; c.z *= c.w;
-                    const float kk = 1.0f - sa;
-                    sr += c.x * kk; sg += c.y * kk; sb += c.z * kk; sa += c.w * kk;
-                    if (sa > A.thresh) { alive = false; break; }
-                }
+                A.out[(size_t)y * A.iw + x] =
+                    pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);  // :713-716
+            } else if (A.clear_misses) {
+                A.out[(size_t)y * A.iw + x] = 0u;                                        // volumeRender.cpp:208
             }
-            A.out[(size_t)y * A.iw + x] =
-                pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);  // :713-716
-        } else if (A.clear_misses) {
-            A.out[(size_t)y * A.iw + x] = 0u;                                        // volumeRender.cpp:208
         }
     }
     if (COUNT) {
@@ -314,155 +317,158 @@ __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Arg
         }
     }
     __syncthreads();
-    int x, y;
-    const bool mine = A.tiles.pixel(x, y);
     const int lane = threadIdx.x & 31;
     unsigned long long nsamp = 0;
-    if (mine) {
-        const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
-        const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
-        float tnear = R.tnear;
-        if (tfar > tnear) {
-            if (tnear < 0.0f) tnear = 0.0f;
-            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, t = tnear;
-            float px, py, pz;
-            eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);
-            const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
-            const float fW = (float)A.W, fH = (float)A.H, fD = (float)A.D;
-            // The reference keeps the eight corner means of the current cell and refreshes them when a sample
-            // leaves it (:396).  Here the march runs in batches of U steps like raycast_kernel: for each of
-            // the next U samples the cell a refresh WOULD produce at that sample is computed and its eight
-            // loads are issued up front (8U loads in flight); the in-order pass below then either keeps the
-            // cached cell or adopts the sample's own, which is exactly the refresh the reference would do.
-            float botx = 0.f, boty = 0.f, botz = 0.f, topx = 0.f, topy = 0.f, topz = 0.f, mean[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) mean[j] = 0.f;
-            bool have = false;
-            int i = 0;
-            bool alive = A.max_steps > 0;
-            while (alive) {
-                float cu[U], cv[U], cw[U];
-                bool valid[U];
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    valid[k] = alive;
-                    cu[k] = fmaf(px, 0.5f, 0.5f); cv[k] = fmaf(py, 0.5f, 0.5f); cw[k] = fmaf(pz, 0.5f, 0.5f);
-                    const float tn = __fadd_rn(t, A.tstep);
-                    const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
-                    if (cont) {
-                        t = tn; ++i;
-                        px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
-                    }
-                    alive = cont;
-                }
-                float sbx[U], sby[U], sbz[U], stx_[U], sty_[U], stz_[U], sm[U][8];
-#pragma unroll
-                for (int k = 0; k < U; ++k) {                                       // :322-367, :398-463
-                    int x0, x1, y0, y1, z0, z1;
-                    float xf0, xf1, yf0, yf1, zf0, zf1;              // texel centres
-                    float gfx = 0.f, gfy = 0.f;                      // floor(pos01 * dim) in x and y (GATHER)
-                    if (A.use_tab) {
-                        const float vx = __fmul_rn(cu[k], fW), vy = __fmul_rn(cv[k], fH), vz = __fmul_rn(cw[k], fD);
-                        const float fx = floor_small(vx), fy = floor_small(vy), fz = floor_small(vz);
-                        gfx = fx; gfy = fy;
-                        // k + 1 for floor and ceil, as integers (|f| < 2^22), clamped to the table
-                        const int ex0 = min(max(__float_as_int(__fadd_rn(fx, 12582912.0f)) - 0x4B400000 + 1, 0), A.W + 1);
-                        const int ey0 = min(max(__float_as_int(__fadd_rn(fy, 12582912.0f)) - 0x4B400000 + 1, 0), A.H + 1);
-                        const int ez0 = min(max(__float_as_int(__fadd_rn(fz, 12582912.0f)) - 0x4B400000 + 1, 0), A.D + 1);
-                        const float2 ax = tabx[ex0], bx_ = tabx[ex0 + (fx < vx)];
-                        const float2 ay = taby[ey0], by_ = taby[ey0 + (fy < vy)];
-                        const float2 az = tabz[ez0], bz_ = tabz[ez0 + (fz < vz)];
-                        sbx[k] = ax.x; stx_[k] = bx_.x; xf0 = ax.y; xf1 = bx_.y;
-                        sby[k] = ay.x; sty_[k] = by_.x; yf0 = ay.y; yf1 = by_.y;
-                        sbz[k] = az.x; stz_[k] = bz_.x; zf0 = az.y; zf1 = bz_.y;
-                        x0 = (int)xf0; x1 = (int)xf1; y0 = (int)yf0; y1 = (int)yf1; z0 = (int)zf0; z1 = (int)zf1;   // dead on the texture path
-                    } else {
-                        sbx[k] = __fdiv_rn(floorf(__fmul_rn(cu[k], fW)), fW); stx_[k] = __fdiv_rn(ceilf(__fmul_rn(cu[k], fW)), fW);
-                        sby[k] = __fdiv_rn(floorf(__fmul_rn(cv[k], fH)), fH); sty_[k] = __fdiv_rn(ceilf(__fmul_rn(cv[k], fH)), fH);
-                        sbz[k] = __fdiv_rn(floorf(__fmul_rn(cw[k], fD)), fD); stz_[k] = __fdiv_rn(ceilf(__fmul_rn(cw[k], fD)), fD);
-                        x0 = point_index_hw(sbx[k], A.W); x1 = point_index_hw(stx_[k], A.W);
-                        y0 = point_index_hw(sby[k], A.H); y1 = point_index_hw(sty_[k], A.H);
-                        z0 = point_index_hw(sbz[k], A.D); z1 = point_index_hw(stz_[k], A.D);
-                        xf0 = (float)x0 + 0.5f; xf1 = (float)x1 + 0.5f; yf0 = (float)y0 + 0.5f; yf1 = (float)y1 + 0.5f;
-                        zf0 = (float)z0 + 0.5f; zf1 = (float)z1 + 0.5f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) sm[k][j] = 0.f;
-                    if (GATHER) {
-                        if (valid[k]) {
-                            // the texel corner at the cell's upper boundary, floor + 1 clamped to [0, n]: texels
-                            // (k, k+1) inside, (n-1, n-1) at and beyond the last boundary, (0, 0) for the cell
-                            // below zero that rounding of the box entry can produce (floor == -1)
-                            const float gx = fminf(fmaxf(__fadd_rn(gfx, 1.0f), 0.0f), fW);
-                            const float gy = fminf(fmaxf(__fadd_rn(gfy, 1.0f), 0.0f), fH);
-                            // layer = texel centre - 0.5 as an integer, without the conversion pipe
-                            const int l0 = __float_as_int(__fadd_rn(__fadd_rn(zf0, -0.5f), 12582912.0f)) - 0x4B400000;
-                            const int l1 = __float_as_int(__fadd_rn(__fadd_rn(zf1, -0.5f), 12582912.0f)) - 0x4B400000;
-                            const float4 a = gather_layer(A.mean_gather, gx, gy, l0);
-                            const float4 b = gather_layer(A.mean_gather, gx, gy, l1);
-                            sm[k][0] = a.w; sm[k][1] = a.z; sm[k][2] = a.x; sm[k][3] = a.y;
-                            sm[k][4] = b.w; sm[k][5] = b.z; sm[k][6] = b.x; sm[k][7] = b.y;
+    int it = 0;
+    for (int item = A.done.queue_begin(); item < A.tiles.n_items; item = A.done.queue_next(it++)) {
+        A.done.queue_prefetch(it);
+        int x, y;
+        if (A.tiles.pixel(item, x, y)) {
+            const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
+            const float dx = R.dx, dy = R.dy, dz = R.dz, tfar = R.tfar;
+            float tnear = R.tnear;
+            if (tfar > tnear) {
+                if (tnear < 0.0f) tnear = 0.0f;
+                float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f, t = tnear;
+                float px, py, pz;
+                eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);
+                const float stx = __fmul_rn(dx, A.tstep), sty = __fmul_rn(dy, A.tstep), stz = __fmul_rn(dz, A.tstep);
+                const float fW = (float)A.W, fH = (float)A.H, fD = (float)A.D;
+                // The reference keeps the eight corner means of the current cell and refreshes them when a sample
+                // leaves it (:396).  Here the march runs in batches of U steps like raycast_kernel: for each of
+                // the next U samples the cell a refresh WOULD produce at that sample is computed and its eight
+                // loads are issued up front (8U loads in flight); the in-order pass below then either keeps the
+                // cached cell or adopts the sample's own, which is exactly the refresh the reference would do.
+                float botx = 0.f, boty = 0.f, botz = 0.f, topx = 0.f, topy = 0.f, topz = 0.f, mean[8];
+    #pragma unroll
+                for (int j = 0; j < 8; ++j) mean[j] = 0.f;
+                bool have = false;
+                int i = 0;
+                bool alive = A.max_steps > 0;
+                while (alive) {
+                    float cu[U], cv[U], cw[U];
+                    bool valid[U];
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        valid[k] = alive;
+                        cu[k] = fmaf(px, 0.5f, 0.5f); cv[k] = fmaf(py, 0.5f, 0.5f); cw[k] = fmaf(pz, 0.5f, 0.5f);
+                        const float tn = __fadd_rn(t, A.tstep);
+                        const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
+                        if (cont) {
+                            t = tn; ++i;
+                            px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
                         }
-                    } else if (valid[k] && A.mean_tex) {
-                        sm[k][0] = tex3D<float>(A.mean_tex, xf0, yf0, zf0); sm[k][1] = tex3D<float>(A.mean_tex, xf1, yf0, zf0);
-                        sm[k][2] = tex3D<float>(A.mean_tex, xf0, yf1, zf0); sm[k][3] = tex3D<float>(A.mean_tex, xf1, yf1, zf0);
-                        sm[k][4] = tex3D<float>(A.mean_tex, xf0, yf0, zf1); sm[k][5] = tex3D<float>(A.mean_tex, xf1, yf0, zf1);
-                        sm[k][6] = tex3D<float>(A.mean_tex, xf0, yf1, zf1); sm[k][7] = tex3D<float>(A.mean_tex, xf1, yf1, zf1);
-                    } else if (valid[k]) {
-                        if (A.idx32) {                           // W*H*D < 2^31: 32-bit index arithmetic
-                            const unsigned zb0 = (unsigned)A.H * z0, zb1 = (unsigned)A.H * z1;
-                            const unsigned r00 = (unsigned)A.W * (y0 + zb0), r10 = (unsigned)A.W * (y1 + zb0);
-                            const unsigned r01 = (unsigned)A.W * (y0 + zb1), r11 = (unsigned)A.W * (y1 + zb1);
-                            sm[k][0] = __ldg(A.mean_raw + (r00 + x0)); sm[k][1] = __ldg(A.mean_raw + (r00 + x1));
-                            sm[k][2] = __ldg(A.mean_raw + (r10 + x0)); sm[k][3] = __ldg(A.mean_raw + (r10 + x1));
-                            sm[k][4] = __ldg(A.mean_raw + (r01 + x0)); sm[k][5] = __ldg(A.mean_raw + (r01 + x1));
-                            sm[k][6] = __ldg(A.mean_raw + (r11 + x0)); sm[k][7] = __ldg(A.mean_raw + (r11 + x1));
+                        alive = cont;
+                    }
+                    float sbx[U], sby[U], sbz[U], stx_[U], sty_[U], stz_[U], sm[U][8];
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {                                       // :322-367, :398-463
+                        int x0, x1, y0, y1, z0, z1;
+                        float xf0, xf1, yf0, yf1, zf0, zf1;              // texel centres
+                        float gfx = 0.f, gfy = 0.f;                      // floor(pos01 * dim) in x and y (GATHER)
+                        if (A.use_tab) {
+                            const float vx = __fmul_rn(cu[k], fW), vy = __fmul_rn(cv[k], fH), vz = __fmul_rn(cw[k], fD);
+                            const float fx = floor_small(vx), fy = floor_small(vy), fz = floor_small(vz);
+                            gfx = fx; gfy = fy;
+                            // k + 1 for floor and ceil, as integers (|f| < 2^22), clamped to the table
+                            const int ex0 = min(max(__float_as_int(__fadd_rn(fx, 12582912.0f)) - 0x4B400000 + 1, 0), A.W + 1);
+                            const int ey0 = min(max(__float_as_int(__fadd_rn(fy, 12582912.0f)) - 0x4B400000 + 1, 0), A.H + 1);
+                            const int ez0 = min(max(__float_as_int(__fadd_rn(fz, 12582912.0f)) - 0x4B400000 + 1, 0), A.D + 1);
+                            const float2 ax = tabx[ex0], bx_ = tabx[ex0 + (fx < vx)];
+                            const float2 ay = taby[ey0], by_ = taby[ey0 + (fy < vy)];
+                            const float2 az = tabz[ez0], bz_ = tabz[ez0 + (fz < vz)];
+                            sbx[k] = ax.x; stx_[k] = bx_.x; xf0 = ax.y; xf1 = bx_.y;
+                            sby[k] = ay.x; sty_[k] = by_.x; yf0 = ay.y; yf1 = by_.y;
+                            sbz[k] = az.x; stz_[k] = bz_.x; zf0 = az.y; zf1 = bz_.y;
+                            x0 = (int)xf0; x1 = (int)xf1; y0 = (int)yf0; y1 = (int)yf1; z0 = (int)zf0; z1 = (int)zf1;   // dead on the texture path
                         } else {
-                            const size_t r00 = (size_t)A.W * (y0 + (size_t)A.H * z0), r10 = (size_t)A.W * (y1 + (size_t)A.H * z0);
-                            const size_t r01 = (size_t)A.W * (y0 + (size_t)A.H * z1), r11 = (size_t)A.W * (y1 + (size_t)A.H * z1);
-                            sm[k][0] = __ldg(A.mean_raw + r00 + x0); sm[k][1] = __ldg(A.mean_raw + r00 + x1);
-                            sm[k][2] = __ldg(A.mean_raw + r10 + x0); sm[k][3] = __ldg(A.mean_raw + r10 + x1);
-                            sm[k][4] = __ldg(A.mean_raw + r01 + x0); sm[k][5] = __ldg(A.mean_raw + r01 + x1);
-                            sm[k][6] = __ldg(A.mean_raw + r11 + x0); sm[k][7] = __ldg(A.mean_raw + r11 + x1);
+                            sbx[k] = __fdiv_rn(floorf(__fmul_rn(cu[k], fW)), fW); stx_[k] = __fdiv_rn(ceilf(__fmul_rn(cu[k], fW)), fW);
+                            sby[k] = __fdiv_rn(floorf(__fmul_rn(cv[k], fH)), fH); sty_[k] = __fdiv_rn(ceilf(__fmul_rn(cv[k], fH)), fH);
+                            sbz[k] = __fdiv_rn(floorf(__fmul_rn(cw[k], fD)), fD); stz_[k] = __fdiv_rn(ceilf(__fmul_rn(cw[k], fD)), fD);
+                            x0 = point_index_hw(sbx[k], A.W); x1 = point_index_hw(stx_[k], A.W);
+                            y0 = point_index_hw(sby[k], A.H); y1 = point_index_hw(sty_[k], A.H);
+                            z0 = point_index_hw(sbz[k], A.D); z1 = point_index_hw(stz_[k], A.D);
+                            xf0 = (float)x0 + 0.5f; xf1 = (float)x1 + 0.5f; yf0 = (float)y0 + 0.5f; yf1 = (float)y1 + 0.5f;
+                            zf0 = (float)z0 + 0.5f; zf1 = (float)z1 + 0.5f;
+                        }
+    #pragma unroll
+                        for (int j = 0; j < 8; ++j) sm[k][j] = 0.f;
+                        if (GATHER) {
+                            if (valid[k]) {
+                                // the texel corner at the cell's upper boundary, floor + 1 clamped to [0, n]: texels
+                                // (k, k+1) inside, (n-1, n-1) at and beyond the last boundary, (0, 0) for the cell
+                                // below zero that rounding of the box entry can produce (floor == -1)
+                                const float gx = fminf(fmaxf(__fadd_rn(gfx, 1.0f), 0.0f), fW);
+                                const float gy = fminf(fmaxf(__fadd_rn(gfy, 1.0f), 0.0f), fH);
+                                // layer = texel centre - 0.5 as an integer, without the conversion pipe
+                                const int l0 = __float_as_int(__fadd_rn(__fadd_rn(zf0, -0.5f), 12582912.0f)) - 0x4B400000;
+                                const int l1 = __float_as_int(__fadd_rn(__fadd_rn(zf1, -0.5f), 12582912.0f)) - 0x4B400000;
+                                const float4 a = gather_layer(A.mean_gather, gx, gy, l0);
+                                const float4 b = gather_layer(A.mean_gather, gx, gy, l1);
+                                sm[k][0] = a.w; sm[k][1] = a.z; sm[k][2] = a.x; sm[k][3] = a.y;
+                                sm[k][4] = b.w; sm[k][5] = b.z; sm[k][6] = b.x; sm[k][7] = b.y;
+                            }
+                        } else if (valid[k] && A.mean_tex) {
+                            sm[k][0] = tex3D<float>(A.mean_tex, xf0, yf0, zf0); sm[k][1] = tex3D<float>(A.mean_tex, xf1, yf0, zf0);
+                            sm[k][2] = tex3D<float>(A.mean_tex, xf0, yf1, zf0); sm[k][3] = tex3D<float>(A.mean_tex, xf1, yf1, zf0);
+                            sm[k][4] = tex3D<float>(A.mean_tex, xf0, yf0, zf1); sm[k][5] = tex3D<float>(A.mean_tex, xf1, yf0, zf1);
+                            sm[k][6] = tex3D<float>(A.mean_tex, xf0, yf1, zf1); sm[k][7] = tex3D<float>(A.mean_tex, xf1, yf1, zf1);
+                        } else if (valid[k]) {
+                            if (A.idx32) {                           // W*H*D < 2^31: 32-bit index arithmetic
+                                const unsigned zb0 = (unsigned)A.H * z0, zb1 = (unsigned)A.H * z1;
+                                const unsigned r00 = (unsigned)A.W * (y0 + zb0), r10 = (unsigned)A.W * (y1 + zb0);
+                                const unsigned r01 = (unsigned)A.W * (y0 + zb1), r11 = (unsigned)A.W * (y1 + zb1);
+                                sm[k][0] = __ldg(A.mean_raw + (r00 + x0)); sm[k][1] = __ldg(A.mean_raw + (r00 + x1));
+                                sm[k][2] = __ldg(A.mean_raw + (r10 + x0)); sm[k][3] = __ldg(A.mean_raw + (r10 + x1));
+                                sm[k][4] = __ldg(A.mean_raw + (r01 + x0)); sm[k][5] = __ldg(A.mean_raw + (r01 + x1));
+                                sm[k][6] = __ldg(A.mean_raw + (r11 + x0)); sm[k][7] = __ldg(A.mean_raw + (r11 + x1));
+                            } else {
+                                const size_t r00 = (size_t)A.W * (y0 + (size_t)A.H * z0), r10 = (size_t)A.W * (y1 + (size_t)A.H * z0);
+                                const size_t r01 = (size_t)A.W * (y0 + (size_t)A.H * z1), r11 = (size_t)A.W * (y1 + (size_t)A.H * z1);
+                                sm[k][0] = __ldg(A.mean_raw + r00 + x0); sm[k][1] = __ldg(A.mean_raw + r00 + x1);
+                                sm[k][2] = __ldg(A.mean_raw + r10 + x0); sm[k][3] = __ldg(A.mean_raw + r10 + x1);
+                                sm[k][4] = __ldg(A.mean_raw + r01 + x0); sm[k][5] = __ldg(A.mean_raw + r01 + x1);
+                                sm[k][6] = __ldg(A.mean_raw + r11 + x0); sm[k][7] = __ldg(A.mean_raw + r11 + x1);
+                            }
                         }
                     }
-                }
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    if (!valid[k]) { alive = false; break; }
-                    const float cx = cu[k], cy = cv[k], cz = cw[k];
-                    if (!have || cx < botx || cy < boty || cz < botz || cx > topx || cy > topy || cz > topz) {   // :396
-                        botx = sbx[k]; boty = sby[k]; botz = sbz[k]; topx = stx_[k]; topy = sty_[k]; topz = stz_[k];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) mean[j] = sm[k][j];
-                        have = true;
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        if (!valid[k]) { alive = false; break; }
+                        const float cx = cu[k], cy = cv[k], cz = cw[k];
+                        if (!have || cx < botx || cy < boty || cz < botz || cx > topx || cy > topy || cz > topz) {   // :396
+                            botx = sbx[k]; boty = sby[k]; botz = sbz[k]; topx = stx_[k]; topy = sty_[k]; topz = stz_[k];
+    #pragma unroll
+                            for (int j = 0; j < 8; ++j) mean[j] = sm[k][j];
+                            have = true;
+                        }
+                        // :466-479.  The reference blends in double (its literals promote); fp32 with the same
+                        // expression shape keeps the special values (0/0 -> NaN, x/0 -> inf, inf - inf -> NaN: the
+                        // degenerate-cell artefact) and differs by an ulp at most, far inside the +-1 LSB bar.
+                        const float xd = __fdividef(__fsub_rn(cx, botx), __fsub_rn(topx, botx));   // a * rcp(b): 0/0 and x/0
+                        const float yd = __fdividef(__fsub_rn(cy, boty), __fsub_rn(topy, boty));   // stay NaN and inf
+                        const float zd = __fdividef(__fsub_rn(cz, botz), __fsub_rn(topz, botz));
+                        const float wx = 1.0f - xd, wy = 1.0f - yd, wz = 1.0f - zd;
+                        const float m00 = fmaf(mean[1], xd, mean[0] * wx);
+                        const float m10 = fmaf(mean[3], xd, mean[2] * wx);
+                        const float m01 = fmaf(mean[5], xd, mean[4] * wx);
+                        const float m11 = fmaf(mean[7], xd, mean[6] * wx);
+                        const float m0 = fmaf(m10, yd, m00 * wy);
+                        const float m1 = fmaf(m11, yd, m01 * wy);
+                        const float s = fmaf(m1, zd, m0 * wz) * 50.0f;
+                        if (COUNT) ++nsamp;
+                        float4 col = tf_lookup_smem(tf_s, A.tf_n, (s - A.t_offset) * A.t_scale);
+                        col.w *= A.density;
+                        col.x *= col.w; col.y *= col.w; col.z *= col.w;
+                        const float kk = 1.0f - sa;
+                        sr += col.x * kk; sg += col.y * kk; sb += col.z * kk; sa += col.w * kk;
+                        if (sa > A.thresh) { alive = false; break; }
                     }
-                    // :466-479.  The reference blends in double (its literals promote); fp32 with the same
-                    // expression shape keeps the special values (0/0 -> NaN, x/0 -> inf, inf - inf -> NaN: the
-                    // degenerate-cell artefact) and differs by an ulp at most, far inside the +-1 LSB bar.
-                    const float xd = __fdividef(__fsub_rn(cx, botx), __fsub_rn(topx, botx));   // a * rcp(b): 0/0 and x/0
-                    const float yd = __fdividef(__fsub_rn(cy, boty), __fsub_rn(topy, boty));   // stay NaN and inf
-                    const float zd = __fdividef(__fsub_rn(cz, botz), __fsub_rn(topz, botz));
-                    const float wx = 1.0f - xd, wy = 1.0f - yd, wz = 1.0f - zd;
-                    const float m00 = fmaf(mean[1], xd, mean[0] * wx);
-                    const float m10 = fmaf(mean[3], xd, mean[2] * wx);
-                    const float m01 = fmaf(mean[5], xd, mean[4] * wx);
-                    const float m11 = fmaf(mean[7], xd, mean[6] * wx);
-                    const float m0 = fmaf(m10, yd, m00 * wy);
-                    const float m1 = fmaf(m11, yd, m01 * wy);
-                    const float s = fmaf(m1, zd, m0 * wz) * 50.0f;
-                    if (COUNT) ++nsamp;
-                    float4 col = tf_lookup_smem(tf_s, A.tf_n, (s - A.t_offset) * A.t_scale);
-                    col.w *= A.density;
-                    col.x *= col.w; col.y *= col.w; col.z *= col.w;
-                    const float kk = 1.0f - sa;
-                    sr += col.x * kk; sg += col.y * kk; sb += col.z * kk; sa += col.w * kk;
-                    if (sa > A.thresh) { alive = false; break; }
                 }
+                A.out[(size_t)y * A.iw + x] = pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);
+            } else if (A.clear_misses) {
+                A.out[(size_t)y * A.iw + x] = 0u;
             }
-            A.out[(size_t)y * A.iw + x] = pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);
-        } else if (A.clear_misses) {
-            A.out[(size_t)y * A.iw + x] = 0u;
         }
     }
     if (COUNT) {
@@ -570,59 +576,62 @@ __global__ void __launch_bounds__(kBlock) raycast_gather_kernel(const RayArgs A)
     __shared__ float4 tf_s[VRDD_MAX_TF];
     for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
     __syncthreads();
-    int x, y;
-    const bool mine = A.tiles.pixel(x, y);
     const int lane = threadIdx.x & 31;
     unsigned long long nsamp = 0;
-    if (mine) {
-        const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
-        const float tfar = R.tfar;
-        float tnear = R.tnear;
-        if (tfar > tnear) {
-            if (tnear < 0.0f) tnear = 0.0f;
-            float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
-            float t = tnear;
-            float px, py, pz;
-            eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);
-            const float stx = __fmul_rn(R.dx, A.tstep), sty = __fmul_rn(R.dy, A.tstep), stz = __fmul_rn(R.dz, A.tstep);
-            int i = 0;
-            bool alive = A.max_steps > 0;
-            while (alive) {
-                GatherFetch G[U];
-                bool valid[U];
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    valid[k] = alive;
-                    if (alive) G[k] = gather_issue<AXIS>(A.vol_tex, fmaf(px, 0.5f, 0.5f), fmaf(py, 0.5f, 0.5f), fmaf(pz, 0.5f, 0.5f), A.W, A.H, A.D);
-                    const float tn = __fadd_rn(t, A.tstep);
-                    const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
-                    if (cont) {
-                        t = tn; ++i;
-                        px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+    int it = 0;
+    for (int item = A.done.queue_begin(); item < A.tiles.n_items; item = A.done.queue_next(it++)) {
+        A.done.queue_prefetch(it);
+        int x, y;
+        if (A.tiles.pixel(item, x, y)) {
+            const EyeRay R = eye_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
+            const float tfar = R.tfar;
+            float tnear = R.tnear;
+            if (tfar > tnear) {
+                if (tnear < 0.0f) tnear = 0.0f;
+                float sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
+                float t = tnear;
+                float px, py, pz;
+                eye_ray_start(R, tnear, A.ref_rounding, px, py, pz);
+                const float stx = __fmul_rn(R.dx, A.tstep), sty = __fmul_rn(R.dy, A.tstep), stz = __fmul_rn(R.dz, A.tstep);
+                int i = 0;
+                bool alive = A.max_steps > 0;
+                while (alive) {
+                    GatherFetch G[U];
+                    bool valid[U];
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        valid[k] = alive;
+                        if (alive) G[k] = gather_issue<AXIS>(A.vol_tex, fmaf(px, 0.5f, 0.5f), fmaf(py, 0.5f, 0.5f), fmaf(pz, 0.5f, 0.5f), A.W, A.H, A.D);
+                        const float tn = __fadd_rn(t, A.tstep);
+                        const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
+                        if (cont) {
+                            t = tn; ++i;
+                            px = __fadd_rn(px, stx); py = __fadd_rn(py, sty); pz = __fadd_rn(pz, stz);
+                        }
+                        alive = cont;
                     }
-                    alive = cont;
+                    float4 col[U];
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        col[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid[k]) col[k] = tf_lookup_smem(tf_s, A.tf_n, (gather_blend<AXIS>(G[k]) - A.t_offset) * A.t_scale);
+                    }
+    #pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        if (!valid[k]) { alive = false; break; }
+                        if (COUNT) ++nsamp;
+                        float4 c = col[k];
+                        c.w *= A.density;
+                        c.x *= c.w; c.y *= c.w; c.z *= c.w;
+                        const float kk = 1.0f - sa;
+                        sr += c.x * kk; sg += c.y * kk; sb += c.z * kk; sa += c.w * kk;
+                        if (sa > A.thresh) { alive = false; break; }
+                    }
                 }
-                float4 col[U];
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    col[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid[k]) col[k] = tf_lookup_smem(tf_s, A.tf_n, (gather_blend<AXIS>(G[k]) - A.t_offset) * A.t_scale);
-                }
-#pragma unroll
-                for (int k = 0; k < U; ++k) {
-                    if (!valid[k]) { alive = false; break; }
-                    if (COUNT) ++nsamp;
-                    float4 c = col[k];
-                    c.w *= A.density;
-                    c.x *= c.w; c.y *= c.w; c.z *= c.w;
-                    const float kk = 1.0f - sa;
-                    sr += c.x * kk; sg += c.y * kk; sb += c.z * kk; sa += c.w * kk;
-                    if (sa > A.thresh) { alive = false; break; }
-                }
+                A.out[(size_t)y * A.iw + x] = pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);
+            } else if (A.clear_misses) {
+                A.out[(size_t)y * A.iw + x] = 0u;
             }
-            A.out[(size_t)y * A.iw + x] = pack_rgba(sr * A.brightness, sg * A.brightness, sb * A.brightness, sa * A.brightness);
-        } else if (A.clear_misses) {
-            A.out[(size_t)y * A.iw + x] = 0u;
         }
     }
     if (COUNT) {
@@ -658,19 +667,35 @@ __global__ void build_gather_copy_kernel(cudaSurfaceObject_t src, cudaSurfaceObj
     }
 }
 
+// Persistent launch: as many blocks as the device holds at once (never more than there are items); the blocks share
+// the items through the queue of FrameSignal.
+template <class Kernel, class Args>
+void launch_persistent(vrdd_context* c, Kernel kernel, const Args& A, long long items, size_t smem) {
+    static std::map<const void*, int> per_sm_cache;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    auto it = per_sm_cache.find(key);
+    if (it == per_sm_cache.end()) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        it = per_sm_cache.emplace(key, per_sm).first;
+    }
+    const long long cap = (long long)it->second * c->num_sms;
+    kernel<<<(unsigned)(items < cap ? items : cap), kBlock, smem, c->stream>>>(A);
+}
+
 template <int SAMPLER, int TFMODE, int U>
-void launch_u(bool count, int grid, cudaStream_t st, const RayArgs& A) {
-    if (count) raycast_kernel<SAMPLER, TFMODE, true, U><<<grid, kBlock, 0, st>>>(A);
-    else raycast_kernel<SAMPLER, TFMODE, false, U><<<grid, kBlock, 0, st>>>(A);
+void launch_u(vrdd_context* c, bool count, long long items, const RayArgs& A) {
+    if (count) launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, true, U>, A, items, 0);
+    else launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, false, U>, A, items, 0);
 }
 
 template <int SAMPLER, int TFMODE>
-void launch_variant(bool count, int grid, cudaStream_t st, const RayArgs& A, int unroll) {
+void launch_variant(vrdd_context* c, bool count, long long items, const RayArgs& A, int unroll) {
     switch (unroll) {
-        case 1: launch_u<SAMPLER, TFMODE, 1>(count, grid, st, A); break;
-        case 2: launch_u<SAMPLER, TFMODE, 2>(count, grid, st, A); break;
-        case 8: launch_u<SAMPLER, TFMODE, 8>(count, grid, st, A); break;
-        default: launch_u<SAMPLER, TFMODE, 4>(count, grid, st, A); break;
+        case 1: launch_u<SAMPLER, TFMODE, 1>(c, count, items, A); break;
+        case 2: launch_u<SAMPLER, TFMODE, 2>(c, count, items, A); break;
+        case 8: launch_u<SAMPLER, TFMODE, 8>(c, count, items, A); break;
+        default: launch_u<SAMPLER, TFMODE, 4>(c, count, items, A); break;
     }
 }
 
@@ -703,14 +728,17 @@ long long make_tile_map(int iw, int ih, const vrdd_tile_partition& part, TileMap
     const long long mine = (ntiles - part.part + part.parts - 1) / part.parts;
     tm->blocks_x = (part.tile_w + 15) / 16;
     tm->blocks_per_tile = tm->blocks_x * ((part.tile_h + 15) / 16);
+    tm->n_items = 0;
     if (mine <= 0) return 0;
-    const long long grid = mine * tm->blocks_per_tile;
-    return grid > 0x7fffffffLL ? -1 : grid;
+    const long long items = mine * tm->blocks_per_tile;
+    if (items > 0x7fffffffLL) return -1;
+    tm->n_items = (int)items;
+    return items;
 }
 
 namespace {
 // The wait gives up after 10 s (a rank that died must not hang the device); a frame is then simply not ordered.
-__global__ void stream_wait_flag_kernel(const unsigned* flag, unsigned at_least) {
+__global__ void stream_wait_flag_kernel(const unsigned* flag, unsigned at_least, unsigned* post) {
     unsigned v;
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -718,6 +746,10 @@ __global__ void stream_wait_flag_kernel(const unsigned* flag, unsigned at_least)
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     } while ((int)(v - at_least) < 0 && t1 - t0 < 10000000000ull);     // wrap-safe "v >= at_least"
+    if (post) {                                                          // ... then publish (e.g. "frame consumed")
+        __threadfence_system();
+        asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(post) : "memory");
+    }
 }
 __global__ void stream_post_flag_kernel(unsigned* flag) {
     __threadfence_system();
@@ -725,8 +757,8 @@ __global__ void stream_post_flag_kernel(unsigned* flag) {
 }
 }  // namespace
 
-int launch_stream_wait_flag(vrdd_context* c, const unsigned* d_flag, unsigned at_least) {
-    stream_wait_flag_kernel<<<1, 1, 0, c->stream>>>(d_flag, at_least);
+int launch_stream_wait_flag(vrdd_context* c, const unsigned* d_flag, unsigned at_least, unsigned* d_post) {
+    stream_wait_flag_kernel<<<1, 1, 0, c->stream>>>(d_flag, at_least, d_post);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;
@@ -806,16 +838,16 @@ int choose_sector_axis(const vrdd_context* c, const vrdd_render_params& p) {
 }
 
 template <int AXIS>
-void launch_gather(bool count, int grid, cudaStream_t st, const RayArgs& A, int unroll) {
+void launch_gather(vrdd_context* c, bool count, long long items, const RayArgs& A, int unroll) {
     if (unroll >= 8) {
-        if (count) raycast_gather_kernel<AXIS, true, 8><<<grid, kBlock, 0, st>>>(A);
-        else raycast_gather_kernel<AXIS, false, 8><<<grid, kBlock, 0, st>>>(A);
+        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, true, 8>, A, items, 0);
+        else launch_persistent(c, raycast_gather_kernel<AXIS, false, 8>, A, items, 0);
     } else if (unroll <= 2) {
-        if (count) raycast_gather_kernel<AXIS, true, 2><<<grid, kBlock, 0, st>>>(A);
-        else raycast_gather_kernel<AXIS, false, 2><<<grid, kBlock, 0, st>>>(A);
+        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, true, 2>, A, items, 0);
+        else launch_persistent(c, raycast_gather_kernel<AXIS, false, 2>, A, items, 0);
     } else {
-        if (count) raycast_gather_kernel<AXIS, true, 4><<<grid, kBlock, 0, st>>>(A);
-        else raycast_gather_kernel<AXIS, false, 4><<<grid, kBlock, 0, st>>>(A);
+        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, true, 4>, A, items, 0);
+        else launch_persistent(c, raycast_gather_kernel<AXIS, false, 4>, A, items, 0);
     }
 }
 
@@ -857,7 +889,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         auto k7 = gather ? (cnt ? raycast_mode7_kernel<true, 4, true> : raycast_mode7_kernel<false, 4, true>)
                          : (cnt ? raycast_mode7_kernel<true, 4, false> : raycast_mode7_kernel<false, 4, false>);
         VRDD_CUDA(c, cudaFuncSetAttribute(k7, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        k7<<<(unsigned)grid7, kBlock, smem7, c->stream>>>(A);
+        launch_persistent(c, k7, A, grid7, smem7);
         c->launches += 1;
         VRDD_CUDA(c, cudaGetLastError());
         return VRDD_OK;
@@ -902,12 +934,12 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         }
         if (axis != 0) {
             A.vol_tex = vol.gtex[comp][axis];
-            if (axis == 1) launch_gather<1>(count, (int)grid, c->stream, A, c->var_unroll);
-            else launch_gather<2>(count, (int)grid, c->stream, A, c->var_unroll);
-        } else if (tfm == 0) launch_variant<0, 0>(count, (int)grid, c->stream, A, c->var_unroll);
-        else launch_variant<0, 1>(count, (int)grid, c->stream, A, c->var_unroll);
+            if (axis == 1) launch_gather<1>(c, count, grid, A, c->var_unroll);
+            else launch_gather<2>(c, count, grid, A, c->var_unroll);
+        } else if (tfm == 0) launch_variant<0, 0>(c, count, grid, A, c->var_unroll);
+        else launch_variant<0, 1>(c, count, grid, A, c->var_unroll);
     } else {
-        launch_variant<1, 1>(count, (int)grid, c->stream, A, c->var_unroll);
+        launch_variant<1, 1>(c, count, grid, A, c->var_unroll);
     }
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
