@@ -300,7 +300,7 @@ class PeerFrames:
         except V.VrddError:
             ok = False
         self.ok = ctx.all_ok(ok)
-        self.owned, self.ptrs = mine, opened
+        self.owned, self.ptrs = mine, (opened if ok else None)
         if not self.ok:
             self.close()
             return
@@ -325,9 +325,14 @@ class PeerFrames:
         return s
 
     def close(self):
-        if self.ptrs:
+        """Importers unmap first, then the owner frees (freeing exported memory that is still mapped elsewhere is undefined)."""
+        if self.ptrs and self.ctx.rank != 0:
             for p in self.ptrs:
-                (self.r.frame_free if self.ctx.rank == 0 else self.r.frame_close)(p)
+                self.r.frame_close(p)
+        self.ctx.barrier()
+        if self.ptrs and self.ctx.rank == 0:
+            for p in self.ptrs:
+                self.r.frame_free(p)
         self.ptrs = None
 
 
@@ -744,8 +749,13 @@ def run_ours(args):
             torch.cuda.synchronize()
             barrier()
             if rank == 0:
-                if not np.array_equal(F.device_frame(slot).cpu().numpy(), host2[(len(views) - 1) & 1]):
-                    raise SystemExit("bench.py: the frame assembled in shared host memory differs from the device-assembled frame")
+                dev_frame = F.device_frame(slot).cpu().numpy()
+                if not np.array_equal(dev_frame, host2[(len(views) - 1) & 1]):
+                    bad = np.argwhere(dev_frame != host2[(len(views) - 1) & 1])
+                    raise SystemExit("bench.py: the frame assembled in shared host memory differs from the device-assembled frame: "
+                                     f"{len(bad)} pixels, rows {bad[:, 0].min()}..{bad[:, 0].max()}, columns {bad[:, 1].min()}..{bad[:, 1].max()}, "
+                                     f"first {bad[:4].tolist()}, device {[hex(int(dev_frame[y, x])) for y, x in bad[:4]]} "
+                                     f"host {[hex(int(host2[(len(views) - 1) & 1][y, x])) for y, x in bad[:4]]}")
             call = ("vrdd_set_view + vrdd_render_host_async(part = my 64-row bands) per frame on every rank into one frame in "
                     "shared, page-locked host memory (N PCIe links), vrdd_render_host_fence + barrier per frame, "
                     "vrdd_render_host_wait at the end")

@@ -405,3 +405,31 @@ def test_decode_stores_into_the_peers_planes(oracle, source):
     np.testing.assert_allclose(got1, ref, rtol=RTOL, atol=ATOL)
     for r in ranks:
         r.close()
+
+
+def test_tma_decode_is_reproducible():
+    """The bulk-copy ring of decode_hist_tma_kernel: a slot may only be refilled once every warp has its rows in
+    registers.  Decoding the same 1024x1024x128 slab forty times must give the same bits forty times (a release of the
+    slot that did not wait for the shared-memory loads gave torn rows in a handful of voxels per 6 G decoded)."""
+    import torch
+    import vrdd_b200 as V
+    W, H, nz = 1024, 1024, 128
+    r = V.Renderer(0)
+    r.keep_linear_planes(True)
+    r.set_volume(W, H, nz)
+    buf = torch.empty(nz * W * H * 32, dtype=torch.float32, device="cuda")
+    r.synth_histograms_device(77, 0, nz, buf)
+    r.set_histograms_device(buf, 0, nz)
+    planes = [V.as_torch(p, (W * H * nz,)) for p in r.get_decoded_planes_device(V.SRC_ORIGINAL)]
+    r.decode(V.SRC_ORIGINAL); r.synchronize()
+    ref = [p.clone() for p in planes]
+    r.set_variant("decode_hist", "ldg")                       # an independent kernel agrees to rounding
+    r.decode(V.SRC_ORIGINAL); r.synchronize()
+    for c in range(3):
+        assert float((planes[c] - ref[c]).abs().max()) < 1e-6
+    r.set_variant("decode_hist", "tma")
+    for it in range(40):
+        r.decode(V.SRC_ORIGINAL); r.synchronize()
+        for c in range(3):
+            assert torch.equal(planes[c].view(torch.int32), ref[c].view(torch.int32)), (it, c)
+    r.close()

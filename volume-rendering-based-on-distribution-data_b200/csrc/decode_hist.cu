@@ -127,9 +127,6 @@ decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut
         float4 q[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) q[j] = row[(j + tid) & 7];   // rotated: conflict-free LDS.128
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);                   // slot may be refilled now
-        if (++s == kStages) { s = 0; phase ^= 1u; }
         const int cx = vx, cy = vy, cz = vz;                     // this tile's coordinate; then step to the next tile
         if (need_xyz) {
             if (t_step == 1) {
@@ -140,8 +137,8 @@ decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut
                 split_voxel(out, out.v_base + (t + t_step) * kTileVox + tid, vx, vy, vz);
             }
         }
-        if (v >= nvox) continue;
 
+        // first pass over the row (rows past the end of the volume hold stale data: computed, never emitted)
         float S0 = 0.f, S1 = 0.f, E = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -152,6 +149,21 @@ decode_hist_tma_kernel(const float* __restrict__ hist, long long nvox, DecodeOut
             S1 += fmaf(fc, sum4, t1);
             E += (plog2p(q[j].x) + plog2p(q[j].y)) + (plog2p(q[j].z) + plog2p(q[j].w));
         }
+        // The slot may be refilled once every lane's row is IN REGISTERS — not merely requested.  Issued right after the
+        // eight LDS.128, as it was, SYNCS.ARRIVE does not wait for their scoreboard: when this warp is the last of the
+        // sixteen to arrive, the producer's next bulk copy can land in the slot while these loads are still queued
+        // behind the other warps' — a torn row (measured on a B200, round 2: 7 wrong voxels in 6.4 G decoded;
+        // tests/test_gpu_decode.py::test_tma_decode_is_reproducible).  The arrive now carries a DATA dependency on the
+        // first pass, whose sums have consumed all 32 loaded values: `dep` is 0 for every value an addition can produce
+        // (a NaN comes out as 0x7fffffff), but ptxas cannot know that, so the barrier address waits for the sums.
+        const unsigned dep = (__float_as_uint((S0 + S1) + E) == 0x7fc12345u) ? 8u : 0u;
+        __syncwarp();
+        if (lane == 0)
+            asm volatile("{\n\t.reg .b32 a;\n\tadd.u32 a, %0, %1;\n\tmbarrier.arrive.shared::cta.b64 _, [a];\n\t}" ::"r"(smem_u32(&empty[s])), "r"(dep)
+                         : "memory");                            // slot may be refilled now
+        if (++s == kStages) { s = 0; phase ^= 1u; }
+        if (v >= nvox) continue;
+
         const float mean_raw = fmaf(bw, S1, hb * S0);
         float var_a = 0.f, var_b = 0.f;                          // two chains: halves the FFMA latency
 #pragma unroll
