@@ -19,6 +19,10 @@ ap.add_argument("--layouts", default="array,layers_x,auto")
 ap.add_argument("--rot-x", type=float, default=0.0)
 ap.add_argument("--vol", type=int, default=1024)
 ap.add_argument("--img", type=int, default=1024)
+ap.add_argument("--world", type=int, default=1, help="render rank 0's tiles of the WORLD-rank weak frame")
+ap.add_argument("--persist", default="100")
+ap.add_argument("--gather-tf", default="follow")
+ap.add_argument("--gather-unroll", default="")
 a = ap.parse_args()
 vol, img = a.vol, a.img
 r = V.Renderer(0); r.set_stream(torch.cuda.current_stream().cuda_stream); r.set_volume(vol, vol, vol)
@@ -27,11 +31,18 @@ buf = torch.empty(slab * vol * vol * 32, dtype=torch.float32, device="cuda")
 for z0 in range(0, vol, slab):
     r.synth_histograms_device(1234, z0, slab, buf); r.set_histograms_device(buf, z0, slab); r.decode(V.SRC_ORIGINAL, z0, slab)
 r.synchronize(); del buf; torch.cuda.empty_cache()
-out = torch.zeros(img, img, dtype=torch.int32, device="cuda")
+import vrdd_b200.dist as D
+fw, fh = D.frame_size(img, a.world)
+part = V.TilePartition(D.TILE, D.TILE, 0, a.world) if a.world > 1 else None
+out = torch.zeros(fh, fw, dtype=torch.int32, device="cuda")
+r.set_variant("raycast_persist_pct", a.persist)
+r.set_variant("raycast_gather_tf", a.gather_tf)
 import math
 ms_ = int(math.ceil(2 * math.sqrt(3.0) / a.tstep)) + 1
 p = V.default_render_params(query_method=1, tstep=a.tstep, max_steps=max(500, ms_))
-r.set_variant("raycast_unroll", a.unroll)
+r.set_variant("raycast_unroll", a.unroll if a.unroll in ("1", "2", "4", "8") else "4")
+if a.gather_unroll:
+    r.set_variant("raycast_gather_unroll", a.gather_unroll)
 res = {}
 ref_frames = {}
 for lay in a.layouts.split(","):
@@ -39,8 +50,8 @@ for lay in a.layouts.split(","):
     rows = []
     for k in range(0, 64, a.every):
         r.set_view(V.view_matrix(a.rot_x, k * 360.0 / 64))
-        r.count_samples(True); r.render(out, img, img, p, clear_misses=True); S = r.get_sample_count(); r.count_samples(False)
-        for _ in range(3): r.render(out, img, img, p, clear_misses=True)
+        r.count_samples(True); r.render(out, fw, fh, p, part=part, clear_misses=True); S = r.get_sample_count(); r.count_samples(False)
+        for _ in range(3): r.render(out, fw, fh, p, part=part, clear_misses=True)
         torch.cuda.synchronize()
         if lay == "array":
             ref_frames[k] = out.clone()
@@ -49,7 +60,7 @@ for lay in a.layouts.split(","):
             assert int(d.max()) <= 1, (lay, k, int(d.max()))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10): r.render(out, img, img, p, clear_misses=True)
+        for _ in range(10): r.render(out, fw, fh, p, part=part, clear_misses=True)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         rows.append((k, ms, S))

@@ -990,6 +990,18 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         const float f = (float)std::atof(variant);
         if (!(f >= 0.f)) return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_layout_min_step is a number of voxels >= 0");
         c->var_layout_min_step = f;
+    } else if (w == "raycast_gather_unroll") {
+        if (v == "2" || v == "4") c->var_gather_unroll = v[0] - '0';
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_gather_unroll is 2|4");
+    } else if (w == "raycast_gather_tf") {
+        if (v == "texture") c->var_gather_tf = 0;
+        else if (v == "smem") c->var_gather_tf = 1;
+        else if (v == "follow") c->var_gather_tf = -1;
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_gather_tf is texture|smem|follow");
+    } else if (w == "raycast_persist_pct") {
+        const int n = std::atoi(variant);
+        if (n < 0 || n > 400) return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_persist_pct is 0..400");
+        c->var_persist_pct = n;
     } else if (w == "raycast_layout_cos") {
         const float f = (float)std::atof(variant);
         if (!(f >= 0.f && f <= 1.f)) return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_layout_cos is in [0, 1]");

@@ -409,6 +409,9 @@ struct vrdd_context {
     int var_decode_order = 1;        // tma tile order: 0 interleaved over CTAs, 1 one contiguous run per CTA (TLB-friendly, default)
     int var_tf = 1;                  // 0 texture unit, 1 shared-memory table (default: frees the TEX pipe)
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
+    int var_gather_unroll = 2;       // march batch of raycast_gather_kernel (2: 48 registers, five blocks per SM — measured faster than 4)
+    int var_gather_tf = -1;          // transfer function of raycast_gather_kernel: -1 follow var_tf, 0 texture unit, 1 shared-memory table
+    int var_persist_pct = 100;       // ray kernels: blocks launched in percent of the resident capacity (0: one block per item)
     int var_layout = 0;              // array the ray caster samples: 0 auto (per view, launch_raycast), 1 the 3-D array (texture unit
                                      // filters), 2 / 3 the layered copy stacked along x / y (tld4 + the unit's integer weights in the kernel)
     float var_layout_min_step = 2.5f;   // auto: a copy only if a ray advances more than this many voxels per step along its stacking axis

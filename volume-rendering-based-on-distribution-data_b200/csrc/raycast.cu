@@ -51,6 +51,7 @@ struct RayArgs {
     int max_steps;
     TileMap tiles;                   // which pixels this launch renders (common.cuh)
     FrameSignal done;                // frame-complete signal (common.cuh)
+    int pow2_shift[3];               // gather path, all extents powers of two <= 4096: 13 - log2(extent) per axis
     int clear_misses;
     int ref_rounding;                // ray set-up rounded like the reference's nvcc build (common.cuh, eye_ray)
     unsigned long long* samples;
@@ -505,12 +506,19 @@ __global__ void debug_sample_tf_kernel(cudaTextureObject_t tex, const float* __r
 // two tld4 fetches (one per layer) and are blended with the unit's integer weights, bit for bit the scheme of
 // split_hw / sample_bricked above.
 // AXIS = 1: layers along x — array (x' = y, y' = z, layer = x);  AXIS = 2: layers along y — array (x' = z, y' = x, layer = y).
-__device__ __forceinline__ int split_q(float u, unsigned n256) {
+template <bool POW2>
+__device__ __forceinline__ int split_q(float u, unsigned n256, int sh) {
     // q = 256 * texel + weight of split_hw, without the conversion pipe: 2^23 + trunc(sat(u) * 2^21) in one FFMA.RZ
     const float r = __fmaf_rz(__saturatef(u), 2097152.0f, 8388608.0f);
     const unsigned U = __float_as_uint(r) & 0x7fffffu;
-    const long long p = (long long)((unsigned long long)U * n256) + ((1ll << 20) - (128ll << 21));
-    const int q = (int)(p >> 21);
+    int q;
+    if (POW2) {
+        // N = 2^m (m <= 12): (U * 2^(m+8) + 2^20) >> 21 = (U + 2^(12-m)) >> (13-m), sh = 13 - m
+        q = (int)((U + ((1u << sh) >> 1)) >> sh) - 128;
+    } else {
+        const long long p = (long long)((unsigned long long)U * n256) + ((1ll << 20) - (128ll << 21));
+        q = (int)(p >> 21);
+    }
     return min(max(q, 0), (int)n256 - 256);
 }
 __device__ __forceinline__ float small_int_as_float(int i) {        // 0 <= i < 2^23, without I2F
@@ -519,12 +527,15 @@ __device__ __forceinline__ float small_int_as_float(int i) {        // 0 <= i < 
 
 struct GatherFetch { float4 l0, l1; int abc; };                      // raw texels of both layers, weights packed a | b<<8 | c<<16
 
-template <int AXIS>
-__device__ __forceinline__ GatherFetch gather_issue(cudaTextureObject_t tex, float cu, float cv, float cw, int W, int H, int D) {
-    const int qx = split_q(cu, (unsigned)W << 8), qy = split_q(cv, (unsigned)H << 8), qz = split_q(cw, (unsigned)D << 8);
+template <int AXIS, bool POW2>
+__device__ __forceinline__ GatherFetch gather_issue(cudaTextureObject_t tex, float cu, float cv, float cw, int W, int H, int D, int shx,
+                                                    int shy, int shz) {
+    const int qx = split_q<POW2>(cu, (unsigned)W << 8, shx), qy = split_q<POW2>(cv, (unsigned)H << 8, shy),
+              qz = split_q<POW2>(cw, (unsigned)D << 8, shz);
     const int i = qx >> 8, j = qy >> 8, k = qz >> 8;
     GatherFetch G;
-    G.abc = (qx & 255) | ((qy & 255) << 8) | ((qz & 255) << 16);
+    // a | b << 8 | c << 16 in two PRMT (q < 2^24, so byte 3 of qx is the zero byte the selectors borrow)
+    G.abc = (int)__byte_perm(__byte_perm((unsigned)qx, (unsigned)qy, 0x3340), (unsigned)qz, 0x3410);
     // texel corner (row index + 1, column index + 1): the 2x2 footprint {idx, idx + 1}^2, clamped at the far edge
     // (where the weight of the clamped texel is 0: q <= 256 * (N - 1))
     if (AXIS == 1) {
@@ -542,7 +553,7 @@ __device__ __forceinline__ GatherFetch gather_issue(cudaTextureObject_t tex, flo
 // tld4 returns .w = (x', y'), .z = (x'+1, y'), .x = (x', y'+1), .y = (x'+1, y'+1)
 template <int AXIS>
 __device__ __forceinline__ float gather_blend(const GatherFetch& G) {
-    const int a = G.abc & 255, b = (G.abc >> 8) & 255, c = G.abc >> 16;
+    const int a = G.abc & 255, b = (int)__byte_perm((unsigned)G.abc, 0u, 0x4441), c = G.abc >> 16;
     float t000, t100, t010, t110, t001, t101, t011, t111;            // t[x][y][z]
     if (AXIS == 1) {       // x' = y, y' = z, layer = x
         t000 = G.l0.w; t010 = G.l0.z; t001 = G.l0.x; t011 = G.l0.y;
@@ -551,6 +562,10 @@ __device__ __forceinline__ float gather_blend(const GatherFetch& G) {
         t000 = G.l0.w; t001 = G.l0.z; t100 = G.l0.x; t101 = G.l0.y;
         t010 = G.l1.w; t011 = G.l1.z; t110 = G.l1.x; t111 = G.l1.y;
     }
+    // the unit's eight integer weights: split z, then x, then y (sample_bricked).  Measured and rejected: the same
+    // weights in fp32 (each rounded product as fma(fma(p, m, .5), 2^-8, 1.5 * 2^23) - 1.5 * 2^23, exact; three
+    // conversions instead of eight, the work moved from the integer to the FMA pipe): 54 instead of 48 registers, four
+    // instead of five blocks per SM, 0.205 instead of 0.197 ms on a side view.
     const int z1 = c, z0 = 256 - c;
     const int x10 = (z0 * a + 128) >> 8, x00 = z0 - x10;
     const int x11 = (z1 * a + 128) >> 8, x01 = z1 - x11;
@@ -571,11 +586,14 @@ __device__ __forceinline__ float gather_blend(const GatherFetch& G) {
 
 // Same march as raycast_kernel (batches of U steps, in-order compositing with the reference's early exit); only the
 // sampler differs.  RayArgs::vol_tex is the layered copy.
-template <int AXIS, bool COUNT, int U>
+template <int AXIS, int TFMODE, bool POW2, bool COUNT, int U>
 __global__ void __launch_bounds__(kBlock) raycast_gather_kernel(const RayArgs A) {
-    __shared__ float4 tf_s[VRDD_MAX_TF];
-    for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
-    __syncthreads();
+    __shared__ float4 tf_s[TFMODE == 1 ? VRDD_MAX_TF : 1];
+    if (TFMODE == 1) {
+        for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
+        __syncthreads();
+    }
+    const int shx = A.pow2_shift[0], shy = A.pow2_shift[1], shz = A.pow2_shift[2];
     const int lane = threadIdx.x & 31;
     unsigned long long nsamp = 0;
     int it = 0;
@@ -601,7 +619,7 @@ __global__ void __launch_bounds__(kBlock) raycast_gather_kernel(const RayArgs A)
     #pragma unroll
                     for (int k = 0; k < U; ++k) {
                         valid[k] = alive;
-                        if (alive) G[k] = gather_issue<AXIS>(A.vol_tex, fmaf(px, 0.5f, 0.5f), fmaf(py, 0.5f, 0.5f), fmaf(pz, 0.5f, 0.5f), A.W, A.H, A.D);
+                        if (alive) G[k] = gather_issue<AXIS, POW2>(A.vol_tex, fmaf(px, 0.5f, 0.5f), fmaf(py, 0.5f, 0.5f), fmaf(pz, 0.5f, 0.5f), A.W, A.H, A.D, shx, shy, shz);
                         const float tn = __fadd_rn(t, A.tstep);
                         const bool cont = alive && !(tn > tfar) && (i + 1 < A.max_steps);
                         if (cont) {
@@ -614,7 +632,11 @@ __global__ void __launch_bounds__(kBlock) raycast_gather_kernel(const RayArgs A)
     #pragma unroll
                     for (int k = 0; k < U; ++k) {
                         col[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid[k]) col[k] = tf_lookup_smem(tf_s, A.tf_n, (gather_blend<AXIS>(G[k]) - A.t_offset) * A.t_scale);
+                        if (valid[k]) {
+                            const float tu = (gather_blend<AXIS>(G[k]) - A.t_offset) * A.t_scale;
+                            if (TFMODE == 0) col[k] = tex1D<float4>(A.tf_tex, tu);
+                            else col[k] = tf_lookup_smem(tf_s, A.tf_n, tu);
+                        }
                     }
     #pragma unroll
                     for (int k = 0; k < U; ++k) {
@@ -679,7 +701,10 @@ void launch_persistent(vrdd_context* c, Kernel kernel, const Args& A, long long 
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         it = per_sm_cache.emplace(key, per_sm).first;
     }
-    const long long cap = (long long)it->second * c->num_sms;
+    // var_persist_pct: resident blocks launched, in percent of what the device holds (100 = one wave of persistent blocks;
+    // 0 = one block per item, i.e. the hardware's block scheduler instead of the queue)
+    long long cap = (long long)it->second * c->num_sms * c->var_persist_pct / 100;
+    if (c->var_persist_pct <= 0 || cap < 1) cap = items;
     kernel<<<(unsigned)(items < cap ? items : cap), kBlock, smem, c->stream>>>(A);
 }
 
@@ -837,18 +862,32 @@ int choose_sector_axis(const vrdd_context* c, const vrdd_render_params& p) {
     return 0;
 }
 
-template <int AXIS>
-void launch_gather(vrdd_context* c, bool count, long long items, const RayArgs& A, int unroll) {
-    if (unroll >= 8) {
-        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, true, 8>, A, items, 0);
-        else launch_persistent(c, raycast_gather_kernel<AXIS, false, 8>, A, items, 0);
-    } else if (unroll <= 2) {
-        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, true, 2>, A, items, 0);
-        else launch_persistent(c, raycast_gather_kernel<AXIS, false, 2>, A, items, 0);
+template <int AXIS, int TFMODE, bool POW2>
+void launch_gather_u(vrdd_context* c, bool count, long long items, const RayArgs& A, int unroll) {
+    if (unroll <= 2) {
+        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, true, 2>, A, items, 0);
+        else launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, false, 2>, A, items, 0);
     } else {
-        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, true, 4>, A, items, 0);
-        else launch_persistent(c, raycast_gather_kernel<AXIS, false, 4>, A, items, 0);
+        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, true, 4>, A, items, 0);
+        else launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, false, 4>, A, items, 0);
     }
+}
+
+template <int AXIS>
+void launch_gather(vrdd_context* c, bool count, long long items, RayArgs& A, int unroll, int tfm) {
+    bool pow2 = true;
+    const int ext[3] = {A.W, A.H, A.D};
+    for (int i = 0; i < 3; ++i) {
+        int m = 0;
+        while ((1 << m) < ext[i]) ++m;
+        if ((1 << m) != ext[i] || m > 12) pow2 = false;
+        A.pow2_shift[i] = 13 - m;
+    }
+    // The transfer function always comes from the shared-memory table here: through the texture unit (a third fetch
+    // per sample next to the two tld4) the same views take 0.29 instead of 0.20 ms.
+    (void)tfm;
+    if (pow2) launch_gather_u<AXIS, 1, true>(c, count, items, A, unroll);
+    else launch_gather_u<AXIS, 1, false>(c, count, items, A, unroll);
 }
 
 }  // namespace
@@ -926,7 +965,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
     if (sampler == VRDD_SAMPLER_TEXTURE && !A.vol_tex) return fail(c, VRDD_ERR_INVALID, "render: no texture volume");
     if (sampler == VRDD_SAMPLER_BRICKED && !A.vol_brick) return fail(c, VRDD_ERR_INVALID, "render: no bricked volume");
     if (sampler == VRDD_SAMPLER_TEXTURE) {
-        int axis = (tfm == 1) ? choose_sector_axis(c, p) : 0;
+        int axis = choose_sector_axis(c, p);
         if (axis != 0) {
             const int rc = ensure_gather_copy(c, vol, comp, axis);
             if (rc == VRDD_ERR_UNSUPPORTED && c->var_layout == 0) axis = 0;       // auto: the 3-D array always works
@@ -934,8 +973,9 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         }
         if (axis != 0) {
             A.vol_tex = vol.gtex[comp][axis];
-            if (axis == 1) launch_gather<1>(c, count, grid, A, c->var_unroll);
-            else launch_gather<2>(c, count, grid, A, c->var_unroll);
+            const int gtf = (c->var_gather_tf >= 0) ? c->var_gather_tf : tfm;
+            if (axis == 1) launch_gather<1>(c, count, grid, A, c->var_gather_unroll, gtf);
+            else launch_gather<2>(c, count, grid, A, c->var_gather_unroll, gtf);
         } else if (tfm == 0) launch_variant<0, 0>(c, count, grid, A, c->var_unroll);
         else launch_variant<0, 1>(c, count, grid, A, c->var_unroll);
     } else {
