@@ -391,6 +391,7 @@ int vrdd_flex_prefix_spans(int x, int32_t* spans);
  * tld4 and filtered in the kernel with the unit's integer weights (same samples; csrc/raycast.cu,
  * raycast_gather_kernel); auto chooses per view.  Unknown names return VRDD_ERR_INVALID. */
 int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant);
+/* ---- texture-unit probes: exported only when the library is built with -DVRDD_PROBE_EXPORTS (csrc/Makefile PROBES=1) ---- */
 /* Samples the texture unit: out[i] = tex3D(plane `comp` of `source`, u[i], v[i], w[i]) with
  * the ray caster's texture object.  For the filter-model conformance test.  Device ptrs. */
 int vrdd_debug_sample_texture(vrdd_handle h, int source, int comp, const float* d_uvw, int n,

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported():
             "copyInvViewMatrix", "setTextureFilterMode", "freeCudaBuffers", "dataProcessing"} <= names
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
-    assert names == set(V.EXPORTS) | set(V.LEGACY_EXPORTS) | set(V.IO_EXPORTS)
+    assert names == set(V.EXPORTS) | set(V.LEGACY_EXPORTS) | set(V.IO_EXPORTS) | set(V.PROBE_EXPORTS)
 
 
 def test_legacy_signatures_match_reference_declarations():

@@ -33,8 +33,7 @@ EXPORTS = [
     "vrdd_default_render_params", "vrdd_render", "vrdd_render_host", "vrdd_render_host_async",
     "vrdd_render_host_wait", "vrdd_render_host_fence", "vrdd_host_register", "vrdd_host_unregister", "vrdd_count_samples",
     "vrdd_get_sample_count", "vrdd_view_matrix", "vrdd_synth_histograms_device", "vrdd_synth_fractal_device",
-    "vrdd_set_variant", "vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function",
-    "vrdd_debug_sample_texture_point", "vrdd_debug_sample_texture_unnorm", "vrdd_enable_interpolated_mean",
+    "vrdd_set_variant", "vrdd_enable_interpolated_mean",
     "vrdd_flex_divide_blocks", "vrdd_flex_prefix_spans", "vrdd_flex_set_tables_host", "vrdd_flex_process",
     "vrdd_flex_get_blocks_host",
     "vrdd_frame_alloc", "vrdd_frame_free", "vrdd_frame_export", "vrdd_frame_open", "vrdd_frame_close",
@@ -42,6 +41,9 @@ EXPORTS = [
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_compose_alpha_in_rows", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
+# texture-unit probes: present when libvrdd.so was built with PROBES=1 (csrc/Makefile; the default of this repository)
+PROBE_EXPORTS = ["vrdd_debug_sample_texture", "vrdd_debug_sample_transfer_function", "vrdd_debug_sample_texture_point",
+                 "vrdd_debug_sample_texture_unnorm"]
 IO_EXPORTS = ["vrdd_io_read_histograms", "vrdd_io_codebook_blocks", "vrdd_io_read_codebook", "vrdd_io_template_count",
               "vrdd_io_read_templates", "vrdd_io_write_histograms", "vrdd_io_write_codebook", "vrdd_io_write_templates",
               "vrdd_io_write_ppm", "vrdd_io_read_ppm", "vrdd_io_span_count", "vrdd_io_read_span_list",
@@ -207,6 +209,8 @@ def lib():
             "vrdd_legacy_handle": (vp, []),
         }
         for name, (res, args) in sig.items():
+            if name in PROBE_EXPORTS and not hasattr(L, name):
+                continue                                    # a library built without the probes
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L

@@ -1016,6 +1016,10 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
     return VRDD_OK;
 }
 
+// ---- texture-unit probes: for the filter-model conformance tests and tools/probe_texture*.py only.  Built when the
+// library is compiled with -DVRDD_PROBE_EXPORTS (csrc/Makefile: PROBES=1, the default of this repository's test build;
+// `make PROBES=0` gives the library without them).
+#ifdef VRDD_PROBE_EXPORTS
 int vrdd_debug_sample_texture(vrdd_handle h, int source, int comp, const float* d_uvw, int n, float* d_out) {
     CHECK_HANDLE(h);
     if (source < 0 || source > 1 || comp < 0 || comp > 2 || !c->vol[source].tex[comp])
@@ -1072,5 +1076,6 @@ int vrdd_debug_sample_transfer_function(vrdd_handle h, const float* d_u, int n, 
     if (!c->tf_tex || !d_u || !d_out4) return fail(c, VRDD_ERR_INVALID, "debug_sample_transfer_function: bad arguments");
     return launch_debug_sample_tf(c, d_u, n, d_out4);
 }
+#endif  // VRDD_PROBE_EXPORTS
 
 }  // extern "C"

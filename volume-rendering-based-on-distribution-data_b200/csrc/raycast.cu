@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Arg
     A.done.block_done();
 }
 
+#ifdef VRDD_PROBE_EXPORTS
 __global__ void debug_sample_kernel(cudaTextureObject_t tex, const float* __restrict__ uvw, int n,
                                     float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,6 +492,7 @@ __global__ void debug_sample_tf_kernel(cudaTextureObject_t tex, const float* __r
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = tex1D<float4>(tex, u[i]);
 }
+#endif  // VRDD_PROBE_EXPORTS
 
 
 // ---- gather path: the plane as a layered 2-D array whose LAYERS are stacked along x or y -----------------------
@@ -714,14 +716,20 @@ void launch_u(vrdd_context* c, bool count, long long items, const RayArgs& A) {
     else launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, false, U>, A, items, 0);
 }
 
+// The march batch U is a measured knob (vrdd_set_variant("raycast_unroll")) of the default path only: texture
+// sampler, shared-memory transfer function; the two alternatives (transfer function through the texture unit, bricked
+// manual sampler) exist for the comparison in DESIGN.md §4 and are built at U = 4.
 template <int SAMPLER, int TFMODE>
 void launch_variant(vrdd_context* c, bool count, long long items, const RayArgs& A, int unroll) {
-    switch (unroll) {
-        case 1: launch_u<SAMPLER, TFMODE, 1>(c, count, items, A); break;
-        case 2: launch_u<SAMPLER, TFMODE, 2>(c, count, items, A); break;
-        case 8: launch_u<SAMPLER, TFMODE, 8>(c, count, items, A); break;
-        default: launch_u<SAMPLER, TFMODE, 4>(c, count, items, A); break;
+    if (SAMPLER == 0 && TFMODE == 1) {
+        switch (unroll) {
+            case 1: launch_u<0, 1, 1>(c, count, items, A); return;
+            case 2: launch_u<0, 1, 2>(c, count, items, A); return;
+            case 8: launch_u<0, 1, 8>(c, count, items, A); return;
+            default: launch_u<0, 1, 4>(c, count, items, A); return;
+        }
     }
+    launch_u<SAMPLER, TFMODE, 4>(c, count, items, A);
 }
 
 }  // namespace
@@ -986,6 +994,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
     return VRDD_OK;
 }
 
+#ifdef VRDD_PROBE_EXPORTS
 int launch_debug_sample(vrdd_context* c, cudaTextureObject_t tex, const float* d_uvw, int n, float* d_out) {
     if (n <= 0) return VRDD_OK;
     debug_sample_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(tex, d_uvw, n, d_out);
@@ -1001,5 +1010,7 @@ int launch_debug_sample_tf(vrdd_context* c, const float* d_u, int n, float* d_ou
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;
 }
+
+#endif  // VRDD_PROBE_EXPORTS
 
 }  // namespace vrdd
