@@ -496,6 +496,29 @@ def run_ours(args):
         torch.cuda.synchronize()
         replicate["nccl_allgather_ms"] = max_over_ranks(e0.elapsed_time(e1))
         replicate["nccl_allgather_what"] = "mean plane, in place, no commit (comparison)" if fused else "three planes + commit"
+        # queryMethod 7 interpolates the UN-normalised block means: the same fused replication for that plane
+        if fused and args.mode7:
+            r.enable_interpolated_mean(True)
+            raw_handles = [None] * world
+            dist.all_gather_object(raw_handles, r.frame_export(r.get_mean_raw_device()))
+            raw_opened = {q: r.frame_open(raw_handles[q]) for q in others}
+            r.set_peer_planes(V.SRC_ORIGINAL, [[None, None, None] for _ in others])
+            r.set_peer_mean_raw([raw_opened[q] for q in others])
+            barrier()
+            e0, e1 = ev(), ev()
+            e0.record()
+            r.decode(V.SRC_ORIGINAL, z_lo, z_hi - z_lo)          # n_slabs == 1 at N > 1: the slab is still attached
+            r.set_peer_planes(V.SRC_ORIGINAL, [])
+            barrier()
+            for q in others:
+                a, b = D.slab_range(Dz, q, world)
+                r.commit_mean_raw(a, b - a)
+            e1.record()
+            torch.cuda.synchronize()
+            replicate["mean_raw_ms"] = max_over_ranks(e0.elapsed_time(e1))
+            barrier()
+            for q in raw_opened:
+                r.frame_close(raw_opened[q])
         for q in opened:
             for p in opened[q]:
                 r.frame_close(p)
@@ -857,18 +880,19 @@ def run_ours(args):
 
     # ---- queryMethod 7 (interpolated block means, point-sampled cells) on the same volume and views -------
     mode7 = None
-    if world == 1 and args.mode7:
+    if args.mode7 and (world == 1 or (replicate and "mean_raw_ms" in replicate)):
         try:
-            r.enable_interpolated_mean(True)                      # the block-mean plane is only kept on request
-            hb = torch.empty(slab * slice_vox * 32, dtype=torch.float32, device=dev)
-            for z0 in range(0, Dz, slab):
-                nz = min(slab, Dz - z0)
-                r.synth_histograms_device(args.seed, z0, nz, hb)
-                r.set_histograms_device(hb, z0, nz)
-                r.decode(V.SRC_ORIGINAL, z0, nz)
-            torch.cuda.synchronize()
-            del hb
-            torch.cuda.empty_cache()
+            if world == 1:
+                r.enable_interpolated_mean(True)                  # the block-mean plane is only kept on request
+                hb = torch.empty(slab * slice_vox * 32, dtype=torch.float32, device=dev)
+                for z0 in range(0, Dz, slab):
+                    nz = min(slab, Dz - z0)
+                    r.synth_histograms_device(args.seed, z0, nz, hb)
+                    r.set_histograms_device(hb, z0, nz)
+                    r.decode(V.SRC_ORIGINAL, z0, nz)
+                torch.cuda.synchronize()
+                del hb
+                torch.cuda.empty_cache()
             p7 = V.default_render_params(query_method=7)
             v7 = timed_views(min(args.steps, 32))
             c7 = F.count_samples(p7, sorted(set(v7)))

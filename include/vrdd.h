@@ -272,6 +272,13 @@ int vrdd_stream_wait_post_flag(vrdd_handle h, const uint32_t* d_wait, uint32_t a
  * all-gather pass.  When all ranks have synchronised, each commits the slabs it received with vrdd_commit_planes.
  * n_peers = 0 switches it off.  At most 7 peers. */
 int vrdd_set_peer_planes(vrdd_handle h, int source, int n_peers, float* const* d_planes);
+/* The same for the un-normalised block-mean plane queryMethod 7 interpolates (vrdd_enable_interpolated_mean on every
+ * rank): vrdd_get_mean_raw_device gives this rank's plane (to export), vrdd_set_peer_mean_raw attaches the peers'
+ * (d_mean_raw[q], same peers and order as vrdd_set_peer_planes; NULL entries are skipped), and after the ranks have
+ * synchronised vrdd_commit_mean_raw republishes the received z-slices to the array the ray caster fetches from. */
+int vrdd_get_mean_raw_device(vrdd_handle h, float** d_mean_raw);
+int vrdd_set_peer_mean_raw(vrdd_handle h, int n_peers, float* const* d_mean_raw);
+int vrdd_commit_mean_raw(vrdd_handle h, int z0, int nz);
 
 /* ---- sort-last rendering of a brick-decomposed volume (volumes larger than one GPU's HBM;
  *      new work, the reference is single-GPU; scheme in csrc/sortlast.cu) ------------------------- */

@@ -433,3 +433,50 @@ def test_tma_decode_is_reproducible():
         for c in range(3):
             assert torch.equal(planes[c].view(torch.int32), ref[c].view(torch.int32)), (it, c)
     r.close()
+
+
+def test_mean_raw_plane_is_replicated_for_query_method_7(oracle):
+    """vrdd_set_peer_mean_raw: the un-normalised block means of queryMethod 7 travel like the three planes; both
+    'ranks' then render the same queryMethod-7 frame as one handle that decoded everything, tiles included."""
+    import torch
+    import vrdd_b200 as V
+    dims, (w, h) = (32, 32, 16), (160, 128)
+    sl = dims[0] * dims[1]
+    hist = oracle.synth_histograms(21, dims)
+    slabs = ((0, 9), (9, 7))
+    one = V.Renderer(0)
+    one.enable_interpolated_mean(True)
+    one.set_volume(*dims); one.set_histograms_host(hist); one.decode(V.SRC_ORIGINAL)
+    view = oracle.view_matrix(20.0, 40.0)
+    p7 = V.default_render_params(query_method=7)
+
+    def frame(r, part=None):
+        out = torch.zeros(h, w, dtype=torch.int32, device="cuda")
+        r.set_view(view); r.render(out, w, h, p7, part=part, clear_misses=True); r.synchronize()
+        return out.cpu().numpy()
+    want = frame(one)
+    ranks, keep = [], []
+    for k in range(2):
+        r = V.Renderer(0)
+        r.keep_linear_planes(True); r.enable_interpolated_mean(True)
+        r.set_volume(*dims)
+        ranks.append(r)
+    raws = [r.get_mean_raw_device() for r in ranks]
+    for k, r in enumerate(ranks):
+        z0, nz = slabs[k]
+        d = torch.from_numpy(hist[z0 * sl:(z0 + nz) * sl]).cuda(); keep.append(d)
+        r.set_histograms_device(d, z0, nz)
+        r.set_peer_planes(V.SRC_ORIGINAL, [[None, None, None]])
+        r.set_peer_mean_raw([raws[1 - k]])
+        r.decode(V.SRC_ORIGINAL, z0, nz)
+    for r in ranks:
+        r.synchronize()
+    for k, r in enumerate(ranks):
+        r.commit_mean_raw(*slabs[1 - k])
+    acc = np.zeros_like(want)
+    for k, r in enumerate(ranks):
+        assert np.array_equal(frame(r), want), k
+        acc |= frame(r, part=V.TilePartition(32, 32, k, 2))
+    assert np.array_equal(acc, want)
+    for r in ranks + [one]:
+        r.close()

@@ -38,6 +38,7 @@ EXPORTS = [
     "vrdd_flex_get_blocks_host",
     "vrdd_frame_alloc", "vrdd_frame_free", "vrdd_frame_export", "vrdd_frame_open", "vrdd_frame_close",
     "vrdd_set_frame_signal", "vrdd_stream_wait_flag", "vrdd_stream_post_flag", "vrdd_stream_wait_post_flag", "vrdd_set_peer_planes",
+    "vrdd_get_mean_raw_device", "vrdd_set_peer_mean_raw", "vrdd_commit_mean_raw",
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_compose_alpha_in_rows", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
@@ -179,6 +180,9 @@ def lib():
             "vrdd_stream_post_flag": (i32, [vp, vp]),
             "vrdd_stream_wait_post_flag": (i32, [vp, vp, u32, vp]),
             "vrdd_set_peer_planes": (i32, [vp, i32, i32, vp]),
+            "vrdd_get_mean_raw_device": (i32, [vp, C.POINTER(vp)]),
+            "vrdd_set_peer_mean_raw": (i32, [vp, i32, vp]),
+            "vrdd_commit_mean_raw": (i32, [vp, i32, i32]),
             # on-disk formats (include/vrdd_io.h)
             "vrdd_io_read_histograms": (i32, [C.c_char_p, C.c_size_t, i32, vp]),
             "vrdd_io_codebook_blocks": (C.c_int64, [C.c_char_p]),
@@ -497,6 +501,18 @@ class Renderer:
             for i in range(3):
                 arr[3 * q + i] = planes[i]
         self._ck(lib().vrdd_set_peer_planes(self._h, source, n, arr))
+
+    def get_mean_raw_device(self):
+        p = C.c_void_p()
+        self._ck(lib().vrdd_get_mean_raw_device(self._h, C.byref(p)))
+        return p.value
+
+    def set_peer_mean_raw(self, peers):
+        arr = (C.c_void_p * max(1, len(peers)))(*peers)
+        self._ck(lib().vrdd_set_peer_mean_raw(self._h, len(peers), arr))
+
+    def commit_mean_raw(self, z0, nz):
+        self._ck(lib().vrdd_commit_mean_raw(self._h, z0, nz))
 
     # sort-last bricks
     def synth_histograms_region_device(self, seed, gdims, origin, z0, nz, d_hist):

@@ -180,8 +180,10 @@ DecodeOut make_decode_out(vrdd_context* c, int source, long long v_base) {
     o.bW = c->bW; o.bH = c->bH;
     o.inv_wh = 1.0f / ((float)c->W * (float)c->H);
     o.n_peers = c->n_peers[source];
-    for (int q = 0; q < VRDD_MAX_PEERS; ++q)
+    for (int q = 0; q < VRDD_MAX_PEERS; ++q) {
         for (int i = 0; i < 3; ++i) o.peer[q][i] = (q < o.n_peers) ? c->peer_planes[source][q][i] : nullptr;
+        o.peer_mean_raw[q] = (q < o.n_peers && source == VRDD_SRC_ORIGINAL) ? c->peer_mean_raw[q] : nullptr;
+    }
     return o;
 }
 
@@ -464,6 +466,49 @@ int vrdd_keep_linear_planes(vrdd_handle h, int keep) {
     return VRDD_OK;
 }
 
+// the slab [z0, z0 + nz) of un-normalised block means, linear -> the array queryMethod 7 fetches from: slices of the 3-D
+// array, or the same layers of the layered one (only when queryMethod 7 was asked for)
+static int commit_mean_raw(vrdd_context* c, int z0, int nz) {
+    vrdd_decoded_volume& v = c->vol[VRDD_SRC_ORIGINAL];
+    if (!v.mean_raw || !(v.mean_arr || v.mean_lay)) return VRDD_OK;
+    const size_t slice = (size_t)c->W * c->H;
+    cudaMemcpy3DParms cp;
+    std::memset(&cp, 0, sizeof(cp));
+    cp.srcPtr = make_cudaPitchedPtr(v.mean_raw + (size_t)z0 * slice, sizeof(float) * c->W, c->W, c->H);
+    cp.dstArray = v.mean_lay ? v.mean_lay : v.mean_arr;
+    cp.dstPos = make_cudaPos(0, 0, z0);
+    cp.extent = make_cudaExtent(c->W, c->H, nz);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    VRDD_CUDA(c, cudaMemcpy3DAsync(&cp, c->stream));
+    return VRDD_OK;
+}
+
+int vrdd_get_mean_raw_device(vrdd_handle h, float** d_mean_raw) {
+    CHECK_HANDLE(h);
+    if (!d_mean_raw) return fail(c, VRDD_ERR_INVALID, "get_mean_raw_device: null");
+    if (c->keep_mean_raw && c->V) {
+        int rc = ensure_volume_storage(c, VRDD_SRC_ORIGINAL);
+        if (rc != VRDD_OK) return rc;
+    }
+    *d_mean_raw = c->vol[VRDD_SRC_ORIGINAL].mean_raw;
+    return VRDD_OK;
+}
+
+int vrdd_set_peer_mean_raw(vrdd_handle h, int n_peers, float* const* d_mean_raw) {
+    CHECK_HANDLE(h);
+    if (n_peers < 0 || n_peers > VRDD_MAX_PEERS || (n_peers > 0 && !d_mean_raw))
+        return fail(c, VRDD_ERR_INVALID, "set_peer_mean_raw: bad arguments");
+    for (int q = 0; q < VRDD_MAX_PEERS; ++q) c->peer_mean_raw[q] = (q < n_peers) ? d_mean_raw[q] : nullptr;
+    if (n_peers > c->n_peers[VRDD_SRC_ORIGINAL]) c->n_peers[VRDD_SRC_ORIGINAL] = n_peers;
+    return VRDD_OK;
+}
+
+int vrdd_commit_mean_raw(vrdd_handle h, int z0, int nz) {
+    CHECK_HANDLE(h);
+    if (z0 < 0 || nz <= 0 || z0 + nz > c->D) return fail(c, VRDD_ERR_INVALID, "commit_mean_raw: bad arguments");
+    return commit_mean_raw(c, z0, nz);
+}
+
 int vrdd_decode(vrdd_handle h, int source, int z0, int nz) {
     CHECK_HANDLE(h);
     if (source != VRDD_SRC_ORIGINAL && source != VRDD_SRC_FRACTAL) return fail(c, VRDD_ERR_INVALID, "decode: bad source");
@@ -489,18 +534,7 @@ int vrdd_decode(vrdd_handle h, int source, int z0, int nz) {
         rc = launch_decode_fractal(c, c->cb + 4 * local0, c->errs, c->err_off + local0 / VRDD_ERR_CHUNK, c->tmpl,
                                    c->num_templates, nvox, out, nullptr);
     }
-    if (rc == VRDD_OK && orig && c->vol[source].mean_raw && (c->vol[source].mean_arr || c->vol[source].mean_lay)) {
-        // the slab of block means, linear -> the array queryMethod 7 fetches from: slices [z0, z0 + nz) of the
-        // 3-D array, or the same layers of the layered one (only when queryMethod 7 was asked for)
-        cudaMemcpy3DParms cp;
-        std::memset(&cp, 0, sizeof(cp));
-        cp.srcPtr = make_cudaPitchedPtr(c->vol[source].mean_raw + (size_t)z0 * slice, sizeof(float) * c->W, c->W, c->H);
-        cp.dstArray = c->vol[source].mean_lay ? c->vol[source].mean_lay : c->vol[source].mean_arr;
-        cp.dstPos = make_cudaPos(0, 0, z0);
-        cp.extent = make_cudaExtent(c->W, c->H, nz);
-        cp.kind = cudaMemcpyDeviceToDevice;
-        VRDD_CUDA(c, cudaMemcpy3DAsync(&cp, c->stream));
-    }
+    if (rc == VRDD_OK && orig) rc = commit_mean_raw(c, z0, nz);
     if (rc == VRDD_OK) c->vol[source].decoded = true;
     invalidate_gather_copies(c->vol[source]);
     return rc;

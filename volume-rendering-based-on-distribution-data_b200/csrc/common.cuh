@@ -38,6 +38,7 @@ struct DecodeOut {
     // all-gather of the slabs costs no extra pass.  Planes a rank does not want replicated are nullptr.
     int n_peers;
     float* peer[VRDD_MAX_PEERS][3];
+    float* peer_mean_raw[VRDD_MAX_PEERS];   // the peers' un-normalised mean planes (queryMethod 7), or nullptr
 };
 
 // Bricked layout for the manual sampler: 4x4x4-texel bricks, 256 B each (two 128-B lines),
@@ -68,13 +69,12 @@ __device__ __forceinline__ void split_voxel(const DecodeOut& o, long long gv, in
 // Stores into the other ranks' linear planes (NVLink; consecutive lanes hold consecutive voxels, so a warp writes
 // whole 128-byte lines).  n_peers == 0 on a single GPU: one uniform branch.
 __device__ __forceinline__ void emit_to_peers(const DecodeOut& o, long long gv, float mean, float var, float ent) {
-#pragma unroll
-    for (int p = 0; p < VRDD_MAX_PEERS; ++p) {
-        if (p < o.n_peers) {
-            if (o.peer[p][0]) o.peer[p][0][gv] = mean;
-            if (o.peer[p][1]) o.peer[p][1][gv] = var;
-            if (o.peer[p][2]) o.peer[p][2][gv] = ent;
-        }
+    if (o.n_peers == 0) return;                                       // single GPU: one uniform branch per voxel
+#pragma unroll 1
+    for (int p = 0; p < o.n_peers; ++p) {
+        if (o.peer[p][0]) o.peer[p][0][gv] = mean;
+        if (o.peer[p][1]) o.peer[p][1][gv] = var;
+        if (o.peer[p][2]) o.peer[p][2][gv] = ent;
     }
 }
 
@@ -393,6 +393,7 @@ struct vrdd_context {
 
     int n_peers[2] = {0, 0};         // vrdd_set_peer_planes: the other ranks' linear planes, per source
     float* peer_planes[2][VRDD_MAX_PEERS][3] = {};
+    float* peer_mean_raw[VRDD_MAX_PEERS] = {};   // vrdd_set_peer_mean_raw (same peers as source 0)
 
     vrdd_flex_state* flex = nullptr; // span store + block volume of the flexible-block chain
 

@@ -40,17 +40,25 @@ constexpr int kRowBytes = VRDD_BINS * 4;            // 128
 constexpr int kTileBytes = kTileVox * kRowBytes;    // 65536
 constexpr size_t kTmaSmem = (size_t)kStages * kTileBytes + 2 * kStages * sizeof(uint64_t);
 
+// the un-normalised block mean queryMethod 7 interpolates: my plane and, on N GPUs, every peer's (like emit_to_peers)
+__device__ __forceinline__ void emit_mean_raw(const DecodeOut& out, long long v, float mean_raw) {
+    out.mean_raw[out.v_base + v] = mean_raw;
+#pragma unroll 1
+    for (int p = 0; p < out.n_peers; ++p)
+        if (out.peer_mean_raw[p]) out.peer_mean_raw[p][out.v_base + v] = mean_raw;
+}
+
 __device__ __forceinline__ void finish_and_emit(const DecodeOut& out, long long v, float mean_raw, float var_raw,
                                                 float plogp) {
     const float inv_mean_norm = (float)(1.0 / VRDD_MEAN_NORM);
     const float inv_var_norm = (float)(1.0 / VRDD_VAR_NORM);
     const float inv_log2_bins = 1.0f / 5.0f;        // 1 / log2(32)
-    if (out.mean_raw) out.mean_raw[out.v_base + v] = mean_raw;
+    if (out.mean_raw) emit_mean_raw(out, v, mean_raw);
     emit_decoded(out, v, mean_raw * inv_mean_norm, var_raw * inv_var_norm, -plogp * inv_log2_bins);
 }
 __device__ __forceinline__ void finish_and_emit_xyz(const DecodeOut& out, long long v, int x, int y, int z, float mean_raw,
                                                     float var_raw, float plogp) {
-    if (out.mean_raw) out.mean_raw[out.v_base + v] = mean_raw;
+    if (out.mean_raw) emit_mean_raw(out, v, mean_raw);
     emit_decoded_xyz(out, v, x, y, z, mean_raw * (float)(1.0 / VRDD_MEAN_NORM), var_raw * (float)(1.0 / VRDD_VAR_NORM),
                      -plogp * (1.0f / 5.0f));
 }
