@@ -23,6 +23,7 @@ ap.add_argument("--world", type=int, default=1, help="render rank 0's tiles of t
 ap.add_argument("--persist", default="100")
 ap.add_argument("--gather-tf", default="follow")
 ap.add_argument("--gather-unroll", default="")
+ap.add_argument("--tf", default="")
 a = ap.parse_args()
 vol, img = a.vol, a.img
 r = V.Renderer(0); r.set_stream(torch.cuda.current_stream().cuda_stream); r.set_volume(vol, vol, vol)
@@ -37,6 +38,8 @@ part = V.TilePartition(D.TILE, D.TILE, 0, a.world) if a.world > 1 else None
 out = torch.zeros(fh, fw, dtype=torch.int32, device="cuda")
 r.set_variant("raycast_persist_pct", a.persist)
 r.set_variant("raycast_gather_tf", a.gather_tf)
+if a.tf:
+    r.set_variant("raycast_tf", a.tf)
 import math
 ms_ = int(math.ceil(2 * math.sqrt(3.0) / a.tstep)) + 1
 p = V.default_render_params(query_method=1, tstep=a.tstep, max_steps=max(500, ms_))
