@@ -217,7 +217,7 @@ __device__ __forceinline__ float flex_texel(const FlexRayArgs& A, int x, int y, 
 
 template <bool COUNT>
 __global__ void __launch_bounds__(256) raycast_flex_kernel(const FlexRayArgs A) {
-    __shared__ float4 tf_s[VRDD_MAX_TF];
+    extern __shared__ float4 tf_s[];                 // tf_n entries (dynamic: sized to the function, not to VRDD_MAX_TF)
     for (int i = threadIdx.x; i < A.tf_n; i += 256) tf_s[i] = A.tf_tab[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -350,8 +350,8 @@ int launch_raycast_flex(vrdd_context* c, uint32_t* d_out, int iw, int ih, const 
     // persistent blocks sharing the items through FrameSignal's queue (common.cuh): at most 8 blocks of 256 threads per SM
     const long long cap = 8ll * c->num_sms;
     const unsigned nblk = (unsigned)(grid < cap ? grid : cap);
-    if (c->count_samples && c->d_samples) raycast_flex_kernel<true><<<nblk, 256, 0, c->stream>>>(A);
-    else raycast_flex_kernel<false><<<nblk, 256, 0, c->stream>>>(A);
+    if (c->count_samples && c->d_samples) raycast_flex_kernel<true><<<nblk, 256, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
+    else raycast_flex_kernel<false><<<nblk, 256, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;

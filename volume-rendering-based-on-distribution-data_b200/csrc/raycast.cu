@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <utility>
 
 namespace vrdd {
 
@@ -135,7 +136,9 @@ __device__ __forceinline__ uint32_t pack_rgba(float r, float g, float b, float a
 // idles on long-scoreboard stalls with the L1TEX pipe at 41 %).
 template <int SAMPLER, int TFMODE, bool COUNT, int U>
 __global__ void __launch_bounds__(kBlock) raycast_kernel(const RayArgs A) {
-    __shared__ float4 tf_s[TFMODE == 1 ? VRDD_MAX_TF : 1];
+    // the transfer-function table, sized to the function (dynamic shared memory: tf_n * 16 B; a static 1024-entry array
+    // would take 16 KB per block, 80 KB per SM, out of the L1 the volume fetches live in)
+    extern __shared__ float4 tf_s[];
     if (TFMODE == 1) {
         for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
         __syncthreads();
@@ -302,11 +305,12 @@ __device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, float x,
 // n, and in a degenerate cell (floor == ceil) the blend is 0/0 = NaN whatever the means are.
 template <bool COUNT, int U, bool GATHER>
 __global__ void __launch_bounds__(kBlock, 2) raycast_mode7_kernel(const Mode7Args A) {
-    __shared__ float4 tf_s[VRDD_MAX_TF];
+    // dynamic shared memory: the transfer-function table (tf_n float4), then the cell table.
     // Per axis and per cell boundary k in [-1, n+1]: {fl(k/n), index the texture unit's point rule gives it}.
     // Both depend only on (k, n), so every block tabulates them once (A.use_tab: they fit in shared memory)
     // and the march replaces 6 divisions and 6 index computations per sample by 6 shared-memory reads.
-    extern __shared__ float2 cell_tab[];
+    extern __shared__ float4 tf_s[];
+    float2* cell_tab = reinterpret_cast<float2*>(tf_s + A.tf_n);
     const float2* tabx = cell_tab;
     const float2* taby = cell_tab + (A.W + 3);
     const float2* tabz = taby + (A.H + 3);
@@ -594,7 +598,9 @@ __device__ __forceinline__ float gather_blend(const GatherFetch& G) {
 // sampler differs.  RayArgs::vol_tex is the layered copy.
 template <int AXIS, int TFMODE, bool POW2, bool COUNT, int U>
 __global__ void __launch_bounds__(kBlock) raycast_gather_kernel(const RayArgs A) {
-    __shared__ float4 tf_s[TFMODE == 1 ? VRDD_MAX_TF : 1];
+    // the transfer-function table, sized to the function (dynamic shared memory: tf_n * 16 B; a static 1024-entry array
+    // would take 16 KB per block, 80 KB per SM, out of the L1 the volume fetches live in)
+    extern __shared__ float4 tf_s[];
     if (TFMODE == 1) {
         for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
         __syncthreads();
@@ -699,8 +705,8 @@ __global__ void build_gather_copy_kernel(cudaSurfaceObject_t src, cudaSurfaceObj
 // the items through the queue of FrameSignal.
 template <class Kernel, class Args>
 void launch_persistent(vrdd_context* c, Kernel kernel, const Args& A, long long items, size_t smem) {
-    static std::map<const void*, int> per_sm_cache;
-    const void* key = reinterpret_cast<const void*>(kernel);
+    static std::map<std::pair<const void*, size_t>, int> per_sm_cache;
+    const std::pair<const void*, size_t> key(reinterpret_cast<const void*>(kernel), smem);
     auto it = per_sm_cache.find(key);
     if (it == per_sm_cache.end()) {
         int per_sm = 0;
@@ -716,8 +722,9 @@ void launch_persistent(vrdd_context* c, Kernel kernel, const Args& A, long long 
 
 template <int SAMPLER, int TFMODE, int U>
 void launch_u(vrdd_context* c, bool count, long long items, const RayArgs& A) {
-    if (count) launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, true, U>, A, items, 0);
-    else launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, false, U>, A, items, 0);
+    const size_t smem = (TFMODE == 1) ? sizeof(float4) * (size_t)A.tf_n : 0;
+    if (count) launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, true, U>, A, items, smem);
+    else launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, false, U>, A, items, smem);
 }
 
 // The march batch U is a measured knob (vrdd_set_variant("raycast_unroll")) of the default path only: texture
@@ -876,12 +883,13 @@ int choose_sector_axis(const vrdd_context* c, const vrdd_render_params& p) {
 
 template <int AXIS, int TFMODE, bool POW2>
 void launch_gather_u(vrdd_context* c, bool count, long long items, const RayArgs& A, int unroll) {
+    const size_t smem = (TFMODE == 1) ? sizeof(float4) * (size_t)A.tf_n : 0;
     if (unroll <= 2) {
-        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, true, 2>, A, items, 0);
-        else launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, false, 2>, A, items, 0);
+        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, true, 2>, A, items, smem);
+        else launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, false, 2>, A, items, smem);
     } else {
-        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, true, 4>, A, items, 0);
-        else launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, false, 4>, A, items, 0);
+        if (count) launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, true, 4>, A, items, smem);
+        else launch_persistent(c, raycast_gather_kernel<AXIS, TFMODE, POW2, false, 4>, A, items, smem);
     }
 }
 
@@ -931,15 +939,15 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
         A.samples = c->d_samples;
         A.ref_rounding = c->var_ray_setup;
         const size_t tab_bytes = sizeof(float2) * ((size_t)c->W + c->H + c->D + 9);
-        A.use_tab = (c->W <= 8192 && c->H <= 8192 && c->D <= 8192 && tab_bytes <= 64 * 1024) ? 1 : 0;   // div_small's checked range
+        A.use_tab = (c->W <= 8192 && c->H <= 8192 && c->D <= 8192 && tab_bytes <= 48 * 1024) ? 1 : 0;   // div_small's checked range
         A.idx32 = ((unsigned long long)c->W * c->H * c->D < (1ull << 31)) ? 1 : 0;
-        const size_t smem7 = A.use_tab ? tab_bytes : 0;
+        const size_t smem7 = sizeof(float4) * (size_t)A.tf_n + (A.use_tab ? tab_bytes : 0);
         // tld4 path: asked for, its layered copy exists, and the point rule maps every x / y boundary to itself
         const bool gather = c->var_mode7 == 2 && v0.mean_gather && A.use_tab;   // regular x / y rule: checked when it was made
         const bool cnt = c->count_samples && c->d_samples;
         auto k7 = gather ? (cnt ? raycast_mode7_kernel<true, 4, true> : raycast_mode7_kernel<false, 4, true>)
                          : (cnt ? raycast_mode7_kernel<true, 4, false> : raycast_mode7_kernel<false, 4, false>);
-        VRDD_CUDA(c, cudaFuncSetAttribute(k7, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        VRDD_CUDA(c, cudaFuncSetAttribute(k7, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));   // <= 16 KB table + 48 KB cells
         launch_persistent(c, k7, A, grid7, smem7);
         c->launches += 1;
         VRDD_CUDA(c, cudaGetLastError());

@@ -147,7 +147,7 @@ __device__ __forceinline__ RaySetup make_ray(const float* m, int x, int y, int i
 template <int PASS, bool COUNT, bool TEX>
 __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A) {
     constexpr int U = 4;
-    __shared__ float4 tf_s[VRDD_MAX_TF];
+    extern __shared__ float4 tf_s[];                 // tf_n entries (dynamic: sized to the function, not to VRDD_MAX_TF)
     for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
     __syncthreads();
     const int blocks_x = (A.iw + 15) / 16;
@@ -342,13 +342,13 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
     const int grid = ((iw + 15) / 16) * ((ih + 15) / 16);
     const bool count = c->count_samples && pass == 2;
     if (A.tex) {
-        if (pass == 1) raycast_brick_kernel<1, false, true><<<grid, kBlock, 0, c->stream>>>(A);
-        else if (count) raycast_brick_kernel<2, true, true><<<grid, kBlock, 0, c->stream>>>(A);
-        else raycast_brick_kernel<2, false, true><<<grid, kBlock, 0, c->stream>>>(A);
+        if (pass == 1) raycast_brick_kernel<1, false, true><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
+        else if (count) raycast_brick_kernel<2, true, true><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
+        else raycast_brick_kernel<2, false, true><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
     } else {
-        if (pass == 1) raycast_brick_kernel<1, false, false><<<grid, kBlock, 0, c->stream>>>(A);
-        else if (count) raycast_brick_kernel<2, true, false><<<grid, kBlock, 0, c->stream>>>(A);
-        else raycast_brick_kernel<2, false, false><<<grid, kBlock, 0, c->stream>>>(A);
+        if (pass == 1) raycast_brick_kernel<1, false, false><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
+        else if (count) raycast_brick_kernel<2, true, false><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
+        else raycast_brick_kernel<2, false, false><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
     }
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
