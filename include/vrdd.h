@@ -313,6 +313,27 @@ int vrdd_render_brick_color(vrdd_handle h, const float* d_alpha_in, float* d_par
 /* Sum of all bricks' increments -> RGBA8 frame (brightness, saturate, truncate, pack: :713-716). */
 int vrdd_pack_frame(vrdd_handle h, const float* d_sum4, uint32_t* d_output, int image_w, int image_h, float brightness);
 
+/* Direct-send form of the same scheme: the two exchanges travel in the kernels' own stores over NVLink instead of in
+ * collectives.  Every rank holds a table of segment alphas float[nbricks][rows][W] and a counter; the root also holds a
+ * table of increments float4[nbricks][rows][W] and a counter (vrdd_frame_alloc + _export / _open; double-buffer them by
+ * frame parity).  `rows` is the common window height and row0 this brick's first row (vrdd_b200.dist.brick_row_windows).
+ *   pass 1   vrdd_render_brick_alpha_send   marches rows [row0, row0 + rows) only and stores them into slot [brick_index] of
+ *                                           each of the n_tables tables (d_seg_tables[i], mine included); the last block of
+ *                                           the launch adds 1 to every d_flags[i] (release.sys)
+ *            vrdd_stream_wait_flag(my counter, nranks * generation), then vrdd_compose_alpha_in_rows on my table
+ *   pass 2   vrdd_render_brick_color_send   stores the increments into slot [brick_index] of the root's table and adds 1 to
+ *                                           the root's counter
+ *   root     vrdd_stream_wait_flag(counter, nranks * generation), vrdd_pack_frame_slots: the frame is the sum of the
+ *                                           slots in brick order, packed to RGBA8. */
+int vrdd_render_brick_alpha_send(vrdd_handle h, float* const* d_seg_tables, uint32_t* const* d_flags, int n_tables, int brick_index,
+                                 int row0, int rows, int image_w, int image_h, const vrdd_render_params* params,
+                                 const vrdd_brick* brick);
+int vrdd_render_brick_color_send(vrdd_handle h, const float* d_alpha_in, float* d_root_slots4, uint32_t* d_root_flag, int brick_index,
+                                 int row0, int rows, int image_w, int image_h, const vrdd_render_params* params,
+                                 const vrdd_brick* brick);
+int vrdd_pack_frame_slots(vrdd_handle h, const float* d_slots4, int nbricks, const int* row0, int rows, uint32_t* d_output,
+                          int image_w, int image_h, float brightness);
+
 /* Host helper: the inverse view matrix the reference builds with OpenGL
  * (volumeRender.cpp:224-246): M = Rx(-rot_x) * Ry(-rot_y) * T(-trans), top three rows,
  * row-major.  Angles in degrees.  (0, 0, (0,0,-4)) is the self-test view (:1024-1043). */

@@ -75,6 +75,30 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
     out = torch.zeros(h, w, dtype=torch.int32, device="cuda")
     handles[0][0].pack_frame(total, out, w, h, params.brightness)
     handles[0][0].synchronize()
+    # The direct-send form of the same frame (vrdd_render_brick_alpha_send / _color_send / vrdd_pack_frame_slots): every
+    # "rank" stores its window rows into all ranks' tables and bumps their counters, waits on its own counter from its
+    # stream, composes, stores its increments into the root's table; the root sums the slots in brick order.  Twice, to
+    # exercise the counter generations.  Must be the frame of the collective form, bit for bit.
+    root = handles[0][0]
+    seg_tabs = [torch.zeros(nb * rows * w, dtype=torch.float32, device="cuda") for _ in range(nb)]
+    flags = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(nb)]
+    slots = torch.zeros(nb * rows * w * 4, dtype=torch.float32, device="cuda")
+    root_flag = torch.zeros(16, dtype=torch.int32, device="cuda")
+    for gen in (1, 2):
+        for b, (r, q) in enumerate(handles):
+            r.render_brick_alpha_send(seg_tabs, flags, b, row0[b], rows, w, h, params, bricks[b])
+        for b, (r, q) in enumerate(handles):
+            a_in = torch.empty(h, w, dtype=torch.float32, device="cuda")
+            r.stream_wait_flag(flags[b], nb * gen)
+            r.compose_alpha_in_rows(seg_tabs[b], grid, q, row0, rows, a_in, w, h)
+            r.render_brick_color_send(a_in, slots, root_flag, b, row0[b], rows, w, h, params, bricks[b])
+            r.synchronize()
+        out2 = torch.zeros(h, w, dtype=torch.int32, device="cuda")
+        root.stream_wait_flag(root_flag, nb * gen)
+        root.pack_frame_slots(slots, nb, row0, rows, out2, w, h, params.brightness)
+        root.synchronize()
+        assert torch.equal(out2, out), (grid, gen, int((out2 != out).sum()))
+        assert int(root_flag[0]) == nb * gen and all(int(f[0]) == nb * gen for f in flags)
     for r, _ in handles:
         r.close()
     return out.cpu().numpy().view(np.uint32), samples

@@ -39,6 +39,7 @@ EXPORTS = [
     "vrdd_frame_alloc", "vrdd_frame_free", "vrdd_frame_export", "vrdd_frame_open", "vrdd_frame_close",
     "vrdd_set_frame_signal", "vrdd_stream_wait_flag", "vrdd_stream_post_flag", "vrdd_stream_wait_post_flag", "vrdd_set_peer_planes",
     "vrdd_get_mean_raw_device", "vrdd_set_peer_mean_raw", "vrdd_commit_mean_raw",
+    "vrdd_render_brick_alpha_send", "vrdd_render_brick_color_send", "vrdd_pack_frame_slots",
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_compose_alpha_in_rows", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
@@ -164,6 +165,9 @@ def lib():
             "vrdd_compose_alpha_in_rows": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, i32]),
             "vrdd_render_brick_color": (i32, [vp, vp, vp, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_pack_frame": (i32, [vp, vp, vp, i32, i32, f32]),
+            "vrdd_render_brick_alpha_send": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
+            "vrdd_render_brick_color_send": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
+            "vrdd_pack_frame_slots": (i32, [vp, vp, i32, vp, i32, vp, i32, i32, f32]),
             "vrdd_synth_histograms_region_device": (i32, [vp, u32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
             "vrdd_flex_set_tables_host": (i32, [vp, C.POINTER(FlexTables)]),
             "vrdd_flex_process": (i32, [vp, i32, C.POINTER(C.c_int64)]),
@@ -521,6 +525,20 @@ class Renderer:
 
     def render_brick_alpha(self, d_alpha_seg, w, h, params, brick):
         self._ck(lib().vrdd_render_brick_alpha(self._h, _ptr(d_alpha_seg), w, h, C.byref(params), C.byref(brick)))
+
+    def render_brick_alpha_send(self, seg_tables, flags, brick_index, row0, rows, w, h, params, brick):
+        n = len(seg_tables)
+        t = (C.c_void_p * n)(*[_ptr(x) for x in seg_tables])
+        f = (C.c_void_p * n)(*[_ptr(x) for x in flags])
+        self._ck(lib().vrdd_render_brick_alpha_send(self._h, t, f, n, brick_index, row0, rows, w, h, C.byref(params), C.byref(brick)))
+
+    def render_brick_color_send(self, d_alpha_in, root_slots, root_flag, brick_index, row0, rows, w, h, params, brick):
+        self._ck(lib().vrdd_render_brick_color_send(self._h, _ptr(d_alpha_in), _ptr(root_slots), _ptr(root_flag), brick_index, row0,
+                                                    rows, w, h, C.byref(params), C.byref(brick)))
+
+    def pack_frame_slots(self, d_slots, nbricks, row0, rows, d_out, w, h, brightness):
+        r0 = (C.c_int * nbricks)(*row0)
+        self._ck(lib().vrdd_pack_frame_slots(self._h, _ptr(d_slots), nbricks, r0, rows, _ptr(d_out), w, h, brightness))
 
     def compose_alpha_in(self, d_alpha_seg_all, grid, q, d_alpha_in, w, h):
         self._ck(lib().vrdd_compose_alpha_in(self._h, _ptr(d_alpha_seg_all), grid[0], grid[1], grid[2], q[0], q[1], q[2],

@@ -957,6 +957,48 @@ int vrdd_render_brick_color(vrdd_handle h, const float* d_alpha_in, float* d_par
     return launch_brick_pass(c, 2, d_alpha_in, d_partial4, image_w, image_h, p, *brick);
 }
 
+int vrdd_render_brick_alpha_send(vrdd_handle h, float* const* d_seg_tables, uint32_t* const* d_flags, int n_tables, int brick_index,
+                                 int row0, int rows, int image_w, int image_h, const vrdd_render_params* params,
+                                 const vrdd_brick* brick) {
+    CHECK_HANDLE(h);
+    int rc = check_brick(c, brick);
+    if (rc != VRDD_OK) return rc;
+    if (!d_seg_tables || !d_flags || n_tables < 1 || n_tables > VRDD_MAX_PEERS + 1 || brick_index < 0 || rows < 1)
+        return fail(c, VRDD_ERR_INVALID, "render_brick_alpha_send: bad arguments");
+    vrdd_render_params p;
+    if (params) p = *params; else vrdd_default_render_params(&p);
+    BrickSend s;
+    s.n_dst = n_tables; s.row0 = row0; s.rows = rows;
+    for (int d = 0; d < n_tables; ++d) {
+        if (!d_seg_tables[d]) return fail(c, VRDD_ERR_INVALID, "render_brick_alpha_send: null table");
+        s.dst[d] = d_seg_tables[d] + (size_t)brick_index * rows * image_w;           // slot [brick]: float[rows][W]
+        s.flags[d] = d_flags[d];
+    }
+    return launch_brick_pass(c, 1, nullptr, nullptr, image_w, image_h, p, *brick, &s);
+}
+
+int vrdd_render_brick_color_send(vrdd_handle h, const float* d_alpha_in, float* d_root_slots4, uint32_t* d_root_flag, int brick_index,
+                                 int row0, int rows, int image_w, int image_h, const vrdd_render_params* params,
+                                 const vrdd_brick* brick) {
+    CHECK_HANDLE(h);
+    int rc = check_brick(c, brick);
+    if (rc != VRDD_OK) return rc;
+    if (!d_root_slots4 || brick_index < 0 || rows < 1) return fail(c, VRDD_ERR_INVALID, "render_brick_color_send: bad arguments");
+    vrdd_render_params p;
+    if (params) p = *params; else vrdd_default_render_params(&p);
+    BrickSend s;
+    s.n_dst = 1; s.row0 = row0; s.rows = rows;
+    s.dst[0] = d_root_slots4 + (size_t)brick_index * rows * image_w * 4;              // slot [brick]: float4[rows][W]
+    s.flags[0] = d_root_flag;
+    return launch_brick_pass(c, 2, d_alpha_in, nullptr, image_w, image_h, p, *brick, &s);
+}
+
+int vrdd_pack_frame_slots(vrdd_handle h, const float* d_slots4, int nbricks, const int* row0, int rows, uint32_t* d_output,
+                          int image_w, int image_h, float brightness) {
+    CHECK_HANDLE(h);
+    return launch_pack_frame_slots(c, d_slots4, nbricks, row0, rows, d_output, image_w, image_h, brightness);
+}
+
 int vrdd_compose_alpha_in(vrdd_handle h, const float* d_alpha_seg_all, int gx, int gy, int gz, int qx, int qy, int qz,
                           float* d_alpha_in, int image_w, int image_h) {
     CHECK_HANDLE(h);

@@ -455,8 +455,17 @@ int launch_synth_fractal(vrdd_context* c, uint32_t seed, int T, int max_ne, int 
                          vrdd_error_entry* d_err, uint64_t* d_off, float* d_tmpl, uint64_t* total_ne);
 int launch_synth_hist_region(vrdd_context* c, uint32_t seed, int gw, int gh, int gd, int ox, int oy, int oz, int z0,
                              int nz, float* d_hist);
+// direct-send form of the sort-last passes (sortlast.cu): where this launch's window rows go, and whom it tells
+struct BrickSend {
+    int n_dst;
+    float* dst[VRDD_MAX_PEERS + 1];
+    unsigned* flags[VRDD_MAX_PEERS + 1];
+    int row0, rows;
+};
 int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float* d_out, int iw, int ih,
-                      const vrdd_render_params& p, const vrdd_brick& b);
+                      const vrdd_render_params& p, const vrdd_brick& b, const BrickSend* send = nullptr);
+int launch_pack_frame_slots(vrdd_context* c, const float* d_slots4, int nbricks, const int* row0, int rows, uint32_t* d_out, int iw,
+                            int ih, float brightness);
 int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_rows, int gx, int gy, int gz, int qx, int qy, int qz,
                             const int* row0, int rows, float* d_alpha_in, int iw, int ih);
 int launch_pack_frame(vrdd_context* c, const float* d_sum4, uint32_t* d_out, int iw, int ih, float brightness);

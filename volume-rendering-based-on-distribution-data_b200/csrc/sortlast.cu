@@ -17,6 +17,15 @@
 //                                     exit, and emits the increments (dR, dG, dB, dA)
 //           SUM reduction of the increments over ranks (NCCL), then vrdd_pack_frame.
 //
+// Direct-send form (round 2; vrdd_render_brick_alpha_send / _color_send / vrdd_pack_frame_slots): the two exchanges travel
+// in the kernels' own stores over NVLink instead of in NCCL calls.  Pass 1 writes the rows of its screen window straight
+// into slot [brick] of EVERY rank's table of segment alphas (CUDA IPC mappings), pass 2 writes its increments into slot
+// [brick] of the ROOT's table, the last block of each launch bumps a counter next to the table(s) with release.sys, and
+// the reader's stream waits for the count (vrdd_stream_wait_flag).  The root sums the slots in brick order and packs.
+// Only the window rows are launched at all.  Tables are double-buffered by frame parity: a rank that sees every other
+// rank's pass-1 counter of frame k + 1 knows they have finished reading the tables of frame k (stream order there), so
+// frame k + 2 may overwrite them.
+//
 // A sample belongs to the brick whose half-open texture-coordinate box contains it; every
 // rank walks the SAME ray recurrence from the global box entry (pos += step is not
 // restarted mid-ray, cf. SURVEY.md §7 "incremental stepping"), and filters with the texture
@@ -52,6 +61,12 @@ struct BrickArgs {
     float* alpha_seg;               // pass 1 out
     float4* partial;                // pass 2 out
     unsigned long long* samples;
+    // direct-send form: n_dst > 0
+    int n_dst;                      // tables to write (pass 1: every rank's; pass 2: the root's only)
+    float* dst[VRDD_MAX_PEERS + 1]; // base of slot [brick] in each table: float[rows][iw] (pass 1) or float4[rows][iw] (pass 2)
+    unsigned* flags[VRDD_MAX_PEERS + 1];   // counter next to each table, bumped when the launch is complete
+    unsigned* tickets;              // this context's block counter
+    int row0, rows;                 // my screen window: only these rows are launched and written
 };
 
 __device__ __forceinline__ void split_hw(float u, int n256, int& i, int& a) {
@@ -154,9 +169,9 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
     const int by = blockIdx.x / blocks_x, bx = blockIdx.x - by * blocks_x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = bx * 16 + (warp & 1) * 8 + (lane & 7);
-    const int y = by * 16 + (warp >> 1) * 4 + (lane >> 3);
+    const int y = A.row0 + by * 16 + (warp >> 1) * 4 + (lane >> 3);          // row0 = 0, rows = ih without a window
     unsigned long long nsamp = 0;
-    if (x < A.iw && y < A.ih) {
+    if (x < A.iw && y < A.row0 + A.rows) {
         const size_t pix = (size_t)y * A.iw + x;
         const RaySetup R = make_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
         float sr = 0.f, sg = 0.f, sb = 0.f;
@@ -247,13 +262,33 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
                 }
             }
         }
-        if (PASS == 1) A.alpha_seg[pix] = sa;
+        if (A.n_dst > 0) {                                   // direct send: my window's rows into slot [brick] of the table(s)
+            const size_t wpix = (size_t)(y - A.row0) * A.iw + x;
+#pragma unroll 1
+            for (int d = 0; d < A.n_dst; ++d) {
+                if (PASS == 1) A.dst[d][wpix] = sa;
+                else reinterpret_cast<float4*>(A.dst[d])[wpix] = make_float4(sr, sg, sb, sa - a_in);
+            }
+        } else if (PASS == 1) A.alpha_seg[pix] = sa;
         else A.partial[pix] = make_float4(sr, sg, sb, sa - a_in);
     }
     if (COUNT) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) nsamp += __shfl_xor_sync(0xffffffffu, nsamp, d);
         if (lane == 0 && nsamp) atomicAdd(A.samples, nsamp);
+    }
+    if (A.n_dst > 0) {                                       // launch complete -> bump every reader's counter (cf. FrameSignal)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(A.tickets, 1u) == gridDim.x - 1) {
+                *A.tickets = 0u;
+                __threadfence_system();
+#pragma unroll 1
+                for (int d = 0; d < A.n_dst; ++d)
+                    if (A.flags[d]) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(A.flags[d]) : "memory");
+            }
+        }
     }
 }
 
@@ -296,17 +331,36 @@ __global__ void pack_frame_kernel(const float4* __restrict__ sum, uint32_t* __re
              ((uint32_t)(__saturatef(c.y * brightness) * 255.0f) << 8) | (uint32_t)(__saturatef(c.x * brightness) * 255.0f);
 }
 
+// root, direct-send form: the frame is the sum, in brick order, of the slots whose window holds the row
+__global__ void pack_frame_slots_kernel(const float4* __restrict__ slots, int nb, const RowWindows Wn, uint32_t* __restrict__ out,
+                                        int iw, int ih, float brightness) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= iw || y >= ih) return;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < nb; ++b) {
+        const int yy = y - Wn.row0[b];
+        if ((unsigned)yy < (unsigned)Wn.rows) {
+            const float4 v = slots[((size_t)b * Wn.rows + yy) * iw + x];
+            c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+        }
+    }
+    out[(size_t)y * iw + x] = ((uint32_t)(__saturatef(c.w * brightness) * 255.0f) << 24) | ((uint32_t)(__saturatef(c.z * brightness) * 255.0f) << 16) |
+                              ((uint32_t)(__saturatef(c.y * brightness) * 255.0f) << 8) | (uint32_t)(__saturatef(c.x * brightness) * 255.0f);
+}
+
 }  // namespace
 
 int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float* d_out, int iw, int ih,
-                      const vrdd_render_params& p, const vrdd_brick& b) {
+                      const vrdd_render_params& p, const vrdd_brick& b, const BrickSend* send) {
     const int qm = p.query_method;
     if (qm < 1 || qm > 6) return fail(c, VRDD_ERR_UNSUPPORTED, "render_brick: queryMethod must be 1..6");
     const int source = (qm >= 4) ? VRDD_SRC_FRACTAL : VRDD_SRC_ORIGINAL, comp = (qm - 1) % 3;
     vrdd_decoded_volume& vol = c->vol[source];
     if (!vol.decoded || !(vol.lin[comp] || vol.brick[comp] || vol.arr[comp]))
         return fail(c, VRDD_ERR_INVALID, "render_brick: decode the brick first");
-    if (iw <= 0 || ih <= 0 || !d_out || (pass == 2 && !d_alpha_in)) return fail(c, VRDD_ERR_INVALID, "render_brick: bad arguments");
+    if (iw <= 0 || ih <= 0 || (!d_out && !send) || (pass == 2 && !d_alpha_in)) return fail(c, VRDD_ERR_INVALID, "render_brick: bad arguments");
+    if (send && (send->n_dst < 1 || send->n_dst > VRDD_MAX_PEERS + 1 || send->row0 < 0 || send->rows < 1 || send->row0 + send->rows > ih))
+        return fail(c, VRDD_ERR_INVALID, "render_brick: bad send window");
     BrickArgs A;
     A.tex = 0;
     if (vol.arr[comp] && c->sampler == VRDD_SAMPLER_TEXTURE) {
@@ -339,7 +393,13 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
     A.thresh = p.opacity_threshold; A.max_steps = p.max_steps; A.ref_rounding = c->var_ray_setup;
     A.alpha_in = d_alpha_in; A.alpha_seg = d_out; A.partial = reinterpret_cast<float4*>(d_out);
     A.samples = c->d_samples;
-    const int grid = ((iw + 15) / 16) * ((ih + 15) / 16);
+    A.n_dst = 0; A.row0 = 0; A.rows = ih; A.tickets = c->d_tickets;
+    for (int d = 0; d <= VRDD_MAX_PEERS; ++d) { A.dst[d] = nullptr; A.flags[d] = nullptr; }
+    if (send) {
+        A.n_dst = send->n_dst; A.row0 = send->row0; A.rows = send->rows;
+        for (int d = 0; d < send->n_dst; ++d) { A.dst[d] = send->dst[d]; A.flags[d] = send->flags[d]; }
+    }
+    const int grid = ((iw + 15) / 16) * ((A.rows + 15) / 16);      // only the rows of the window are launched
     const bool count = c->count_samples && pass == 2;
     if (A.tex) {
         if (pass == 1) raycast_brick_kernel<1, false, true><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
@@ -370,6 +430,20 @@ int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_rows, int gx, in
     for (int i = 0; i < 12; ++i) M.m[i] = c->view[i];
     dim3 grid((iw + 127) / 128, ih);
     compose_alpha_in_kernel<<<grid, 128, 0, c->stream>>>(d_seg_rows, gx, gy, gz, qx, qy, qz, d_alpha_in, iw, ih, M, Wn, c->var_ray_setup);
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+int launch_pack_frame_slots(vrdd_context* c, const float* d_slots4, int nbricks, const int* row0, int rows, uint32_t* d_out, int iw,
+                            int ih, float brightness) {
+    if (!d_slots4 || !d_out || !row0 || iw <= 0 || ih <= 0 || nbricks < 1 || nbricks > kMaxBricks || rows < 1 || rows > ih)
+        return fail(c, VRDD_ERR_INVALID, "pack_frame_slots: bad arguments");
+    RowWindows Wn;
+    Wn.rows = rows;
+    for (int b = 0; b < kMaxBricks; ++b) Wn.row0[b] = (b < nbricks) ? row0[b] : 0;
+    dim3 grid((iw + 127) / 128, ih);
+    pack_frame_slots_kernel<<<grid, 128, 0, c->stream>>>(reinterpret_cast<const float4*>(d_slots4), nbricks, Wn, d_out, iw, ih, brightness);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;
