@@ -1095,7 +1095,60 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     windows = bool(args.sortlast_windows)
     coll_bytes = [0, 0]                                   # all-gather (received per rank), reduce (sent per rank), per frame
 
-    def step(k, frame=frame):
+    # ---- direct-send exchange: tables in every rank's HBM mapped over CUDA IPC, counters instead of collectives ----
+    # Per frame parity: every rank owns a table of segment alphas float[world][rows][W] + a counter; rank 0 also a table of
+    # increments float4[world][rows][W] + a counter.  Pass 1 stores its window rows into slot [rank] of EVERY table, pass 2
+    # into slot [rank] of rank 0's; the last block of a launch bumps the counters (red.release.sys); readers wait in-stream.
+    # Reuse of a parity's tables at frame k + 2 is safe without a further signal: a rank has waited for every rank's pass 1
+    # of frame k + 1, which those ranks' streams issue after they finished reading the tables of frame k.
+    direct = None
+    if world > 1 and windows and args.sortlast_exchange == "direct":
+        seg_bytes, slot_bytes = world * fh * fw * 4, world * fh * fw * 16
+        mine = [r.frame_alloc(seg_bytes), r.frame_alloc(seg_bytes), r.frame_alloc(256)]
+        if rank == 0:
+            mine += [r.frame_alloc(slot_bytes), r.frame_alloc(slot_bytes)]
+        exported = [None] * world
+        dist.all_gather_object(exported, [r.frame_export(p) for p in mine])
+        ok, opened = True, {}
+        try:
+            for qq in range(world):
+                if qq != rank:
+                    opened[qq] = [r.frame_open(hb) for hb in exported[qq]]
+        except V.VrddError:
+            ok = False
+        if ctx.all_ok(ok):
+            ptrs = {qq: (mine if qq == rank else opened[qq]) for qq in range(world)}
+            direct = {"mine": mine, "opened": opened, "frame_no": 0,
+                      "seg": [[ptrs[qq][s] for qq in range(world)] for s in (0, 1)],
+                      "seg_flag": [[ptrs[qq][2] + 64 * s for qq in range(world)] for s in (0, 1)],
+                      "slots": [ptrs[0][3 + s] for s in (0, 1)], "slot_flag": [ptrs[0][2] + 128 + 64 * s for s in (0, 1)]}
+        else:
+            for qq in opened:
+                for pp in opened[qq]:
+                    r.frame_close(pp)
+            barrier()
+            for pp in mine:
+                r.frame_free(pp)
+
+    def step_direct(k, frame):
+        view = orbit_view(V, k)
+        r.set_view(view)
+        n = direct["frame_no"]; s = n & 1; gen = n // 2 + 1
+        row0, rows, (u0, u1) = D.brick_row_windows(view, grid, fh)
+        r.render_brick_alpha_send(direct["seg"][s], direct["seg_flag"][s], rank, row0[rank], rows, fw, fh, params, br)
+        r.stream_wait_flag(direct["seg_flag"][s][rank], world * gen)
+        r.compose_alpha_in_rows(direct["seg"][s][rank], grid, q, row0, rows, a_in, fw, fh)
+        r.render_brick_color_send(a_in, direct["slots"][s], direct["slot_flag"][s], rank, row0[rank], rows, fw, fh, params, br)
+        if rank == 0:
+            r.stream_wait_flag(direct["slot_flag"][s], world * gen)
+            r.pack_frame_slots(direct["slots"][s], world, row0, rows, frame, fw, fh, params.brightness)
+        direct["frame_no"] = n + 1
+        coll_bytes[0] = (world - 1) * rows * fw * 4            # peer stores sent per rank, pass 1
+        coll_bytes[1] = rows * fw * 16                         # peer stores sent per rank, pass 2
+
+    def step(k, frame=frame, collectives=False):
+        if direct and not collectives:
+            return step_direct(k, frame)
         view = orbit_view(V, k)
         r.set_view(view)
         r.render_brick_alpha(seg, fw, fh, params, br)
@@ -1123,6 +1176,25 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
 
     views = timed_views(steps)
     distinct = sorted(set(views))
+    exchange_check = None
+    if direct:
+        # the frame of the direct-send exchange against the frame of the NCCL exchange: the same increments, summed in brick
+        # order instead of NCCL's order (fp32 addition is not associative: a last-bit difference may flip a byte by 1)
+        other = torch.zeros_like(frame)
+        worst, differ = 0, 0
+        for k in (7, 23):
+            step(k, frame)
+            step(k, other, collectives=True)
+            torch.cuda.synchronize()
+            if rank == 0:
+                a = frame.view(torch.uint8).to(torch.int16); b = other.view(torch.uint8).to(torch.int16)
+                worst = max(worst, int((a - b).abs().max())); differ += int((a != b).sum())
+        barrier()
+        if rank == 0:
+            if worst > 1:
+                raise SystemExit(f"bench.py: direct-send sort-last frame differs from the NCCL form by {worst} LSB")
+            exchange_check = {"views": [7, 23], "max_lsb": worst, "bytes_differing": differ, "bytes": 2 * fw * fh * 4}
+        del other
     r.count_samples(True)
     cnt = []
     for k in distinct:
@@ -1165,23 +1237,37 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     torch.cuda.synchronize()
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
+    if direct:
+        for qq in direct["opened"]:
+            for pp in direct["opened"][qq]:
+                r.frame_close(pp)
+        barrier()
+        for pp in direct["mine"]:
+            r.frame_free(pp)
     r.close()
     if rank != 0:
         return None
+    how = ("alpha pre-pass storing each brick's window rows into every rank's table over NVLink, in-stream counter wait, colour pass "
+           "storing the float4 increments into rank 0's table, sum in brick order + pack on rank 0 (no collective, no host "
+           "synchronisation in the loop)") if direct else (
+           "alpha pre-pass, NCCL all-gather of segment alphas, colour pass, NCCL SUM reduction of float4 increments, pack on rank 0"
+           + ("; collectives restricted to the image rows of each brick's screen footprint" if windows else ""))
     dec_gbs = decoded_vox * HIST_BYTES_PER_VOXEL / (dec_ms * 1e-3) / 1e9
     return {"workload": f"sort-last: {gdims[0]}x{gdims[1]}x{gdims[2]} distribution volume in {grid[0]}x{grid[1]}x{grid[2]} "
-                        f"bricks of {E}^3 (+1 ghost) over {world} GPUs, {fw}x{fh} frames of the orbit, reference constants; alpha pre-pass, "
-                        "NCCL all-gather of segment alphas, colour pass, NCCL SUM reduction of float4 increments, pack on rank 0"
-                        + ("; collectives restricted to the image rows of each brick's screen footprint" if windows else ""),
+                        f"bricks of {E}^3 (+1 ghost) over {world} GPUs, {fw}x{fh} frames of the orbit, reference constants; " + how,
+            "exchange": "direct" if direct else "nccl", "exchange_check": exchange_check,
             "n_gpus": world, "value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s", "steps": len(views), "ms_per_step": ms / len(views),
             "fps": len(views) / (ms * 1e-3), "samples_per_frame": samples / len(views),
-            "collective_bytes_per_frame": {"all_gather": coll_bytes[0], "reduce": coll_bytes[1], "full_frame": [world * fh * fw * 4, fh * fw * 16]},
+            "collective_bytes_per_frame": {("alpha_sent_per_rank" if direct else "all_gather"): coll_bytes[0],
+                                           ("increments_sent_per_rank" if direct else "reduce"): coll_bytes[1],
+                                           "full_frame": [world * fh * fw * 4, fh * fw * 16]},
             "volume": list(gdims), "image": [fw, fh], "histogram_bytes_total": decoded_vox * 128,
             "decode": {"kernel": "decode_hist_tma_kernel", "voxels": decoded_vox, "ms": dec_ms, "gbs": dec_gbs,
                        "frac_of_hbm_peak": dec_gbs / (hbm_peak * world), "peak_gbs": hbm_peak * world},
             "e2e": {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 80, "d2h_bytes_per_step": fw * fh * 4,
                     "fps": len(views) / dt,
-                    "call": "vrdd_render_brick_alpha/compose/color + NCCL + vrdd_pack_frame; the frame of step k is copied to pinned host memory "
+                    "call": ("vrdd_render_brick_alpha_send/compose/color_send + vrdd_pack_frame_slots" if direct else
+                             "vrdd_render_brick_alpha/compose/color + NCCL + vrdd_pack_frame") + "; the frame of step k is copied to pinned host memory "
                             "by a second stream while step k+1 renders"},
             "gpu_launches": int(launches)}
 
@@ -1258,6 +1344,8 @@ def main():
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "reduce"],
                     help="N > 1 tiles: p2p = kernels store tiles into rank 0's frame over NVLink; reduce = NCCL reduce")
     ap.add_argument("--sortlast-layout", default="texture", choices=["texture", "bricked", "linear"])
+    ap.add_argument("--sortlast-exchange", default="direct", choices=["direct", "nccl"],
+                    help="direct: the kernels store into peer tables over NVLink (CUDA IPC) and signal with counters; nccl: collectives")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -25,10 +25,13 @@ for sink in ("tex", "linear"):
         if sink == "linear":
             r.set_sampler(V.SAMPLER_LINEAR)
         r.set_volume(edge, edge, nz)
-        name, _, pf = variant.partition("+pf")
+        name, *opts = variant.split("+")                      # e.g. moments2+pf12+generic
         r.set_variant("decode_fractal", name)
-        if pf:
-            r.set_variant("decode_fractal_prefetch", pf)
+        for o in opts:
+            if o.startswith("pf"):
+                r.set_variant("decode_fractal_prefetch", o[2:])
+            elif o in ("generic", "auto"):
+                r.set_variant("decode_fractal_sink", o)
         tot = r.synth_fractal_device(1234, T, max_ne, 0, nz, cb, er, off, tm)
         r.set_fractal_device(cb, er, off, tm, T, 0, nz)
         r.decode(V.SRC_FRACTAL); torch.cuda.synchronize()

@@ -1040,6 +1040,10 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         const int n = std::atoi(variant);
         if (n < 0 || n > 32) return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal_prefetch is 0..32 lines");
         c->var_fractal_pf = n;
+    } else if (w == "decode_fractal_sink") {
+        if (v == "generic") c->var_fractal_sink = 0;
+        else if (v == "auto") c->var_fractal_sink = 1;          // the surfaces-only instance where the sink allows it
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal_sink is auto|generic");
     } else if (w == "ray_setup") {
         if (v == "source") c->var_ray_setup = 0;
         else if (v == "nvcc") c->var_ray_setup = 1;            // queryMethod 1..7 of vrdd_render; see raycast.cu, ray_dir_nvcc

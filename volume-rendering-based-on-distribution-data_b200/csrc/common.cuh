@@ -419,6 +419,7 @@ struct vrdd_context {
     float var_layout_cos = 0.68f;       // ... and the view direction is within acos(this) of that axis (47 degrees)
     int var_ray_setup = 1;           // 1 "nvcc" (default): the rounding of the reference's own build; 0 "source": the source's uncontracted order (eye_ray above)
     int var_mode7 = 2;               // 2 layered array + tld4 where the volume allows it (default), 0 point-sampled 3-D array, 1 linear plane
+    int var_fractal_sink = 1;        // moments2: 1 = the surfaces-only instance where the sink is just the three 3-D arrays; 0 = generic
     int var_fractal_pf = 12;         // moments2: 128-byte lines of the next tile's errors prefetched into L2 (0..32)
     int var_fractal = 4;             // 0 dense (O(B) per voxel); moments (O(NE) per voxel): 1 r1f kernel, 2 tables in global memory,
                                      // 3 768 threads, 4 moments2 (default), 5 moments2r, 6 moments2b, 7 moments2br (decode_fractal.cu)

@@ -585,7 +585,12 @@ __device__ __forceinline__ void moments_voxel2(const typename RowT<RECOMP>::type
     }
 }
 
-template <bool SCAN, bool RECOMP>
+// SURF_ONLY: the sink is known at compile time to be the three 3-D arrays and nothing else (one GPU, texture sampler:
+// no linear / bricked planes, no peers) with whole 32-voxel rows: the generic sink's uniform tests — lin?, brick?, seven
+// peers x three planes — are ~35 of the ~430 instructions a tile costs in a kernel that is bound by instruction issue.
+// (Measured and rejected, round 2: two / four texels per surface store gathered with shuffles, +0.5 % / -4 %; the moment
+// gather through the texture pipe, -3.5 %: profiles/tuning_r2.md.)
+template <bool SCAN, bool RECOMP, bool SURF_ONLY = false>
 __global__ void __launch_bounds__(1024, 1)
 decode_fractal_moments2_kernel(const int4* __restrict__ codebook, const ErrEntry* __restrict__ errs,
                                const unsigned long long* __restrict__ chunk_off, const float4* __restrict__ perm,
@@ -614,7 +619,7 @@ decode_fractal_moments2_kernel(const int4* __restrict__ codebook, const ErrEntry
     const int tail = (int)(nvox - (long long)(nwt - 1) * 32);        // live lanes of the very last tile (1..32)
     const int last_vox_lane = tail - 1;
 
-    const bool rows32 = ((out.W & 31) == 0) && ((out.v_base & 31) == 0) && (out.use_surf || out.brick[0]);
+    const bool rows32 = SURF_ONLY || (((out.W & 31) == 0) && ((out.v_base & 31) == 0) && (out.use_surf || out.brick[0]));
     int x0 = 0, y0 = 0, z0 = 0, sx = 0, sy = 0, sz = 0;
     if (rows32) {
         split_voxel(out, out.v_base + (long long)wt * 32, x0, y0, z0);
@@ -661,7 +666,12 @@ decode_fractal_moments2_kernel(const int4* __restrict__ codebook, const ErrEntry
             base_nn = ldg_stream_u64(chunk_off + min(wt_n + wstride, nwt));
         });
         if (live) {
-            if (rows32) emit_decoded_xyz(out, v, x0 + lane, y0, z0, mean_n, var_n, ent_n);
+            if constexpr (SURF_ONLY) {
+                const int xb = (x0 + lane) * 4;
+                surf3Dwrite(mean_n, out.surf[0], xb, y0, z0);
+                surf3Dwrite(var_n, out.surf[1], xb, y0, z0);
+                surf3Dwrite(ent_n, out.surf[2], xb, y0, z0);
+            } else if (rows32) emit_decoded_xyz(out, v, x0 + lane, y0, z0, mean_n, var_n, ent_n);
             else emit_decoded(out, v, mean_n, var_n, ent_n);
         }
         if (wt_n >= nwt) break;
@@ -709,8 +719,11 @@ int launch_decode_fractal(vrdd_context* c, const int32_t* cb, const void* errs, 
         if (gen2 && smem2 <= 227 * 1024 && nvox < (1ll << 35)) {        // second-generation kernel (moments_voxel2); its tile indices are
                                                                          // 32-bit: nvox / 32 plus two grid strides must stay below 2^31
             const bool scan = c->var_fractal <= 5;
-            auto kern = scan ? (recomp ? decode_fractal_moments2_kernel<true, true> : decode_fractal_moments2_kernel<true, false>)
-                             : (recomp ? decode_fractal_moments2_kernel<false, true> : decode_fractal_moments2_kernel<false, false>);
+            const bool surf_only = scan && !recomp && c->var_fractal_sink != 0 && out.use_surf && !out.lin[0] && !out.brick[0] &&
+                                   out.n_peers == 0 && (out.W & 31) == 0 && (out.v_base & 31) == 0 && (nvox & 31) == 0;
+            auto kern = surf_only ? decode_fractal_moments2_kernel<true, false, true>
+                        : scan ? (recomp ? decode_fractal_moments2_kernel<true, true> : decode_fractal_moments2_kernel<true, false>)
+                               : (recomp ? decode_fractal_moments2_kernel<false, true> : decode_fractal_moments2_kernel<false, false>);
             VRDD_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             const long long nblk = (nvox + 1023) / 1024;
             const int grid = (int)((nblk < c->num_sms) ? nblk : c->num_sms);
