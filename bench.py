@@ -1057,6 +1057,7 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     r.set_stream(torch.cuda.current_stream().cuda_stream)
     r.set_sampler({"texture": V.SAMPLER_TEXTURE, "linear": V.SAMPLER_LINEAR, "bricked": V.SAMPLER_BRICKED}[args.sortlast_layout])
     r.set_volume(*size)
+    r.set_variant("sortlast_fuse", args.sortlast_fuse)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     barrier, max_over_ranks = ctx.barrier, ctx.max
     # ---- decode my brick slab by slab -----------------------------------------------------------
@@ -1130,18 +1131,34 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
             for pp in mine:
                 r.frame_free(pp)
 
+    main_s = torch.cuda.current_stream()
+    side_s = torch.cuda.Stream(device=dev) if direct else None
+    if direct:
+        direct["packed"] = [None, None]
+        direct["last_packed"] = None
+
     def step_direct(k, frame):
         view = orbit_view(V, k)
         r.set_view(view)
         n = direct["frame_no"]; s = n & 1; gen = n // 2 + 1
         row0, rows, (u0, u1) = D.brick_row_windows(view, grid, fh)
+        if rank == 0 and direct["packed"][s] is not None:
+            main_s.wait_event(direct["packed"][s])             # frame n - 2 has been summed: its slots may be overwritten (see above)
         r.render_brick_alpha_send(direct["seg"][s], direct["seg_flag"][s], rank, row0[rank], rows, fw, fh, params, br)
         r.stream_wait_flag(direct["seg_flag"][s][rank], world * gen)
         r.compose_alpha_in_rows(direct["seg"][s][rank], grid, q, row0, rows, a_in, fw, fh)
         r.render_brick_color_send(a_in, direct["slots"][s], direct["slot_flag"][s], rank, row0[rank], rows, fw, fh, params, br)
         if rank == 0:
+            # the wait for everybody's increments and the sum + pack run on a second stream: rank 0's pass 1 of the next frame
+            # (which every other rank waits for) is not held up by the slowest pass 2 of this one
+            after_p2 = torch.cuda.Event(); after_p2.record(main_s)
+            side_s.wait_event(after_p2)
+            r.set_stream(side_s.cuda_stream)
             r.stream_wait_flag(direct["slot_flag"][s], world * gen)
             r.pack_frame_slots(direct["slots"][s], world, row0, rows, frame, fw, fh, params.brightness)
+            r.set_stream(main_s.cuda_stream)
+            done = torch.cuda.Event(); done.record(side_s)
+            direct["packed"][s] = direct["last_packed"] = done
         direct["frame_no"] = n + 1
         coll_bytes[0] = (world - 1) * rows * fw * 4            # peer stores sent per rank, pass 1
         coll_bytes[1] = rows * fw * 16                         # peer stores sent per rank, pass 2
@@ -1210,6 +1227,8 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     e0.record()
     for k in views:
         step(k)
+    if direct and rank == 0:
+        main_s.wait_event(direct["last_packed"])               # the last frame is packed inside the timed region
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -1226,10 +1245,13 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     t0 = time.perf_counter()
     for i, k in enumerate(views):
         if copied[i & 1] is not None:
-            main.wait_event(copied[i & 1])
+            (side_s if direct else main).wait_event(copied[i & 1])   # direct: only the pack (second stream) writes the frame
         step(k, frames2[i & 1])
         if rank == 0:
-            packed = torch.cuda.Event(); packed.record(main)
+            if direct:
+                packed = direct["last_packed"]
+            else:
+                packed = torch.cuda.Event(); packed.record(main)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(packed)
                 host[i & 1].copy_(frames2[i & 1], non_blocking=True)
@@ -1256,6 +1278,7 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     return {"workload": f"sort-last: {gdims[0]}x{gdims[1]}x{gdims[2]} distribution volume in {grid[0]}x{grid[1]}x{grid[2]} "
                         f"bricks of {E}^3 (+1 ghost) over {world} GPUs, {fw}x{fh} frames of the orbit, reference constants; " + how,
             "exchange": "direct" if direct else "nccl", "exchange_check": exchange_check,
+            "fused_first_segment": bool(direct) and args.sortlast_fuse == "on",
             "n_gpus": world, "value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s", "steps": len(views), "ms_per_step": ms / len(views),
             "fps": len(views) / (ms * 1e-3), "samples_per_frame": samples / len(views),
             "collective_bytes_per_frame": {("alpha_sent_per_rank" if direct else "all_gather"): coll_bytes[0],
@@ -1344,6 +1367,8 @@ def main():
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "reduce"],
                     help="N > 1 tiles: p2p = kernels store tiles into rank 0's frame over NVLink; reduce = NCCL reduce")
     ap.add_argument("--sortlast-layout", default="texture", choices=["texture", "bricked", "linear"])
+    ap.add_argument("--sortlast-fuse", default="on", choices=["on", "off"],
+                    help="direct exchange: pass 1 keeps the colour of the march from alpha 0, pass 2 marches only pixels with incoming alpha")
     ap.add_argument("--sortlast-exchange", default="direct", choices=["direct", "nccl"],
                     help="direct: the kernels store into peer tables over NVLink (CUDA IPC) and signal with counters; nccl: collectives")
     args = ap.parse_args()

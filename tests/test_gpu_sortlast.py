@@ -84,8 +84,13 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
     flags = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(nb)]
     slots = torch.zeros(nb * rows * w * 4, dtype=torch.float32, device="cuda")
     root_flag = torch.zeros(16, dtype=torch.int32, device="cuda")
-    for gen in (1, 2):
+    # Generation 1 runs while samples are counted (pass 2 marches every pixel), 2 with the fused first segment (pass 1 keeps
+    # the colour of the march from alpha 0 and pass 2 forwards it where the incoming alpha is 0), 3 with the fusion off.
+    for gen in (1, 2, 3):
         for b, (r, q) in enumerate(handles):
+            r.count_samples(gen == 1)
+            r.set_variant("sortlast_fuse", "off" if gen == 3 else "on")
+            r.set_view(view)
             r.render_brick_alpha_send(seg_tabs, flags, b, row0[b], rows, w, h, params, bricks[b])
         for b, (r, q) in enumerate(handles):
             a_in = torch.empty(h, w, dtype=torch.float32, device="cuda")

@@ -271,6 +271,7 @@ int vrdd_destroy(vrdd_handle h) {
     free_tf(c);
     if (c->d_samples) cudaFree(c->d_samples);
     if (c->d_tickets) cudaFree(c->d_tickets);
+    if (c->d_first4) cudaFree(c->d_first4);
     if (c->frame) cudaFree(c->frame);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
@@ -303,6 +304,7 @@ int64_t vrdd_kernel_launches(vrdd_handle h) { return h ? h->launches : 0; }
 
 int vrdd_set_volume(vrdd_handle h, int width, int height, int depth, int bins) {
     CHECK_HANDLE(h);
+    c->first4_tag = 0;                                  // sort-last: the fused record of pass 1 is stale
     if (width <= 0 || height <= 0 || depth <= 0) return fail(c, VRDD_ERR_INVALID, "set_volume: bad size");
     if (bins != VRDD_BINS) return fail(c, VRDD_ERR_UNSUPPORTED, "set_volume: this build supports bins == 32 only");
     VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -448,6 +450,7 @@ int vrdd_set_fractal_device(vrdd_handle h, const int32_t* d_codebook, const vrdd
 
 int vrdd_set_sampler(vrdd_handle h, int sampler) {
     CHECK_HANDLE(h);
+    c->first4_tag = 0;                                  // sort-last: the fused record of pass 1 is stale
     if (sampler != VRDD_SAMPLER_TEXTURE && sampler != VRDD_SAMPLER_BRICKED && sampler != VRDD_SAMPLER_LINEAR)
         return fail(c, VRDD_ERR_INVALID, "set_sampler: unknown sampler");
     c->sampler = sampler;
@@ -511,6 +514,7 @@ int vrdd_commit_mean_raw(vrdd_handle h, int z0, int nz) {
 
 int vrdd_decode(vrdd_handle h, int source, int z0, int nz) {
     CHECK_HANDLE(h);
+    c->first4_tag = 0;                                  // sort-last: the fused record of pass 1 is stale
     if (source != VRDD_SRC_ORIGINAL && source != VRDD_SRC_FRACTAL) return fail(c, VRDD_ERR_INVALID, "decode: bad source");
     if (!c->V) return fail(c, VRDD_ERR_INVALID, "decode: set_volume first");
     const bool orig = source == VRDD_SRC_ORIGINAL;
@@ -571,6 +575,7 @@ int vrdd_commit_planes(vrdd_handle h, int source, int z0, int nz) { return vrdd_
 
 int vrdd_commit_planes_mask(vrdd_handle h, int source, int z0, int nz, int plane_mask) {
     CHECK_HANDLE(h);
+    c->first4_tag = 0;                                  // sort-last: the fused record of pass 1 is stale
     if (source < 0 || source > 1 || z0 < 0 || nz <= 0 || z0 + nz > c->D || (plane_mask & ~7) || !plane_mask)
         return fail(c, VRDD_ERR_INVALID, "commit_planes: bad arguments");
     vrdd_decoded_volume& v = c->vol[source];
@@ -637,6 +642,7 @@ int vrdd_get_decoded_host(vrdd_handle h, int source, float* out4) {
 
 int vrdd_set_transfer_function(vrdd_handle h, const float* tf, int n) {
     CHECK_HANDLE(h);
+    c->first4_tag = 0;                                  // sort-last: the fused record of pass 1 is stale
     if (!tf) { tf = &kDefaultTf[0][0]; n = 9; }
     if (n < 1 || n > VRDD_MAX_TF) return fail(c, VRDD_ERR_INVALID, "set_transfer_function: 1..1024 entries");
     VRDD_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1022,6 +1028,7 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
     if (!h || !what || !variant) return VRDD_ERR_INVALID;
     vrdd_context* c = h;
     const std::string w(what), v(variant);
+    c->first4_tag = 0;                                  // sort-last: the fused record of pass 1 is stale
     if (w == "decode_hist") {
         if (v == "tma") c->var_decode_hist = 0;
         else if (v == "ldg") c->var_decode_hist = 1;
@@ -1044,6 +1051,10 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         if (v == "generic") c->var_fractal_sink = 0;
         else if (v == "auto") c->var_fractal_sink = 1;          // the surfaces-only instance where the sink allows it
         else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal_sink is auto|generic");
+    } else if (w == "sortlast_fuse") {
+        if (v == "on") c->var_sortlast_fuse = 1;
+        else if (v == "off") c->var_sortlast_fuse = 0;
+        else return fail(c, VRDD_ERR_INVALID, "set_variant: sortlast_fuse is on|off");
     } else if (w == "ray_setup") {
         if (v == "source") c->var_ray_setup = 0;
         else if (v == "nvcc") c->var_ray_setup = 1;            // queryMethod 1..7 of vrdd_render; see raycast.cu, ray_dir_nvcc

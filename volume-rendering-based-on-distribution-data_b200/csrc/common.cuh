@@ -388,6 +388,9 @@ struct vrdd_context {
     unsigned long long* d_samples = nullptr;
     bool count_samples = false;
 
+    void* d_first4 = nullptr;        // sort-last, fused first segment: float4[rows][iw] record of pass 1 (sortlast.cu)
+    size_t first4_cap = 0;           // ... its capacity in pixels
+    unsigned long long first4_tag = 0;   // ... what it was computed for (0 = invalid)
     unsigned* d_tickets = nullptr;   // {finished blocks, next item} of the persistent ray kernels (FrameSignal)
     unsigned* frame_signal = nullptr;   // vrdd_set_frame_signal: bumped by the last block of every vrdd_render launch
 
@@ -412,6 +415,7 @@ struct vrdd_context {
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
     int var_gather_unroll = 2;       // march batch of raycast_gather_kernel (2: 48 registers, five blocks per SM — measured faster than 4)
     int var_gather_tf = -1;          // transfer function of raycast_gather_kernel: -1 follow var_tf, 0 texture unit, 1 shared-memory table
+    int var_sortlast_fuse = 1;       // direct-send sort-last: pass 1 keeps the colour of the march from alpha 0, pass 2 skips those pixels
     int var_persist_pct = 100;       // ray kernels: blocks launched in percent of the resident capacity (0: one block per item)
     int var_layout = 0;              // array the ray caster samples: 0 auto (per view, launch_raycast), 1 the 3-D array (texture unit
                                      // filters), 2 / 3 the layered copy stacked along x / y (tld4 + the unit's integer weights in the kernel)

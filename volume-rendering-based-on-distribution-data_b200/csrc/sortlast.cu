@@ -26,6 +26,13 @@
 // rank's pass-1 counter of frame k + 1 knows they have finished reading the tables of frame k (stream order there), so
 // frame k + 2 may overwrite them.
 //
+// Fused first segment (direct-send form): where nothing precedes a brick on a ray the incoming alpha is exactly 0, and
+// pass 2 would repeat pass 1's march step for step.  So pass 1 of the direct-send form accumulates colour as well (from
+// alpha 0, with the reference's early exit on its own alpha) and keeps (dR, dG, dB, dA) per pixel in a scratch buffer of
+// the context; pass 2 forwards that record for every pixel whose incoming alpha came out as 0.0f and marches only the
+// others.  With the reference's constants rays die within the first brick they cross, so pass 2 all but disappears.  The
+// record is bit for bit what pass 2 would compute (same code, same order).
+//
 // A sample belongs to the brick whose half-open texture-coordinate box contains it; every
 // rank walks the SAME ray recurrence from the global box entry (pos += step is not
 // restarted mid-ray, cf. SURVEY.md §7 "incremental stepping"), and filters with the texture
@@ -67,6 +74,7 @@ struct BrickArgs {
     unsigned* flags[VRDD_MAX_PEERS + 1];   // counter next to each table, bumped when the launch is complete
     unsigned* tickets;              // this context's block counter
     int row0, rows;                 // my screen window: only these rows are launched and written
+    float4* first4;                 // FUSE: (dR, dG, dB, dA) of the march from alpha 0, float4[rows][iw] (pass 1 writes, pass 2 reads)
 };
 
 __device__ __forceinline__ void split_hw(float u, int n256, int& i, int& a) {
@@ -159,8 +167,9 @@ __device__ __forceinline__ RaySetup make_ray(const float* m, int x, int y, int i
 }
 
 // PASS 1: alpha of this brick's segment.  PASS 2: colour increments from the incoming alpha.
-template <int PASS, bool COUNT, bool TEX>
+template <int PASS, bool COUNT, bool TEX, bool FUSE = false>
 __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A) {
+    constexpr bool COLOR = (PASS == 2) || FUSE;
     constexpr int U = 4;
     extern __shared__ float4 tf_s[];                 // tf_n entries (dynamic: sized to the function, not to VRDD_MAX_TF)
     for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
@@ -177,7 +186,13 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
         float sr = 0.f, sg = 0.f, sb = 0.f;
         const float a_in = (PASS == 2) ? A.alpha_in[pix] : 0.f;
         float sa = a_in;
-        if (R.hit && !(sa > A.thresh)) {
+        bool march = R.hit && !(sa > A.thresh);
+        if (PASS == 2 && FUSE && a_in == 0.0f) {             // nothing in front of this brick: pass 1 has marched this pixel
+            const float4 v = A.first4[(size_t)(y - A.row0) * A.iw + x];
+            sr = v.x; sg = v.y; sb = v.z; sa = v.w;
+            march = false;
+        }
+        if (march) {
             float t = R.tnear;
             float px, py, pz;
             {
@@ -252,7 +267,7 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
                         if (COUNT) ++nsamp;
                         col.w *= A.density;
                         const float kk = 1.0f - sa;
-                        if (PASS == 2) {
+                        if (COLOR) {
                             col.x *= col.w; col.y *= col.w; col.z *= col.w;
                             sr += col.x * kk; sg += col.y * kk; sb += col.z * kk;
                         }
@@ -262,6 +277,7 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
                 }
             }
         }
+        if (PASS == 1 && FUSE) A.first4[(size_t)(y - A.row0) * A.iw + x] = make_float4(sr, sg, sb, sa);
         if (A.n_dst > 0) {                                   // direct send: my window's rows into slot [brick] of the table(s)
             const size_t wpix = (size_t)(y - A.row0) * A.iw + x;
 #pragma unroll 1
@@ -401,7 +417,44 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
     }
     const int grid = ((iw + 15) / 16) * ((A.rows + 15) / 16);      // only the rows of the window are launched
     const bool count = c->count_samples && pass == 2;
-    if (A.tex) {
+    // Fused first segment: only in the direct-send form (pass 2 is known to follow pass 1 of the same frame), not while
+    // samples are counted (the count is taken in pass 2).  The record is tagged with everything the march depends on; a
+    // pass 2 whose tag differs marches every pixel.
+    A.first4 = nullptr;
+    bool fuse = false;
+    if (send && c->var_sortlast_fuse && !c->count_samples) {
+        uint64_t tag = 1469598103934665603ull;
+        auto mix = [&tag](const void* q, size_t n) {
+            const unsigned char* u = static_cast<const unsigned char*>(q);
+            for (size_t i = 0; i < n; ++i) { tag ^= u[i]; tag *= 1099511628211ull; }
+        };
+        mix(c->view, sizeof(c->view)); mix(&p, sizeof(p)); mix(&b, sizeof(b)); mix(&iw, sizeof(iw)); mix(&ih, sizeof(ih));
+        mix(&A.row0, sizeof(int)); mix(&A.rows, sizeof(int)); mix(&source, sizeof(source)); mix(&A.tex, sizeof(A.tex));
+        tag |= 1ull;                                              // 0 = invalid (api.cu clears the tag when volume / function change)
+        const size_t need = (size_t)A.rows * iw;
+        if (pass == 1) {
+            if (c->first4_cap < need) {
+                if (c->d_first4) { cudaFree(c->d_first4); c->d_first4 = nullptr; c->first4_cap = 0; }
+                VRDD_CUDA(c, cudaMalloc(&c->d_first4, need * sizeof(float4)));
+                c->first4_cap = need;
+            }
+            c->first4_tag = tag;
+            fuse = true;
+        } else {
+            fuse = c->d_first4 && c->first4_cap >= need && c->first4_tag == tag;
+        }
+        A.first4 = reinterpret_cast<float4*>(c->d_first4);
+    }
+    if (fuse) {
+        const size_t sm = sizeof(float4) * (size_t)A.tf_n;
+        if (A.tex) {
+            if (pass == 1) raycast_brick_kernel<1, false, true, true><<<grid, kBlock, sm, c->stream>>>(A);
+            else raycast_brick_kernel<2, false, true, true><<<grid, kBlock, sm, c->stream>>>(A);
+        } else {
+            if (pass == 1) raycast_brick_kernel<1, false, false, true><<<grid, kBlock, sm, c->stream>>>(A);
+            else raycast_brick_kernel<2, false, false, true><<<grid, kBlock, sm, c->stream>>>(A);
+        }
+    } else if (A.tex) {
         if (pass == 1) raycast_brick_kernel<1, false, true><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
         else if (count) raycast_brick_kernel<2, true, true><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
         else raycast_brick_kernel<2, false, true><<<grid, kBlock, sizeof(float4) * (size_t)A.tf_n, c->stream>>>(A);
