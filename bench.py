@@ -1103,11 +1103,19 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     # Reuse of a parity's tables at frame k + 2 is safe without a further signal: a rank has waited for every rank's pass 1
     # of frame k + 1, which those ranks' streams issue after they finished reading the tables of frame k.
     direct = None
+    banded = args.sortlast_compose == "bands" or (args.sortlast_compose == "auto" and world >= 4)
+    band_rows = (fh + world - 1) // world
     if world > 1 and windows and args.sortlast_exchange == "direct":
-        seg_bytes, slot_bytes = world * fh * fw * 4, world * fh * fw * 16
-        mine = [r.frame_alloc(seg_bytes), r.frame_alloc(seg_bytes), r.frame_alloc(256)]
-        if rank == 0:
-            mine += [r.frame_alloc(slot_bytes), r.frame_alloc(slot_bytes)]
+        seg_bytes = world * fh * fw * 4
+        # [0, 1] segment-alpha tables, [2] counters (64 B apart: segment 0/1, root slots 0/1, band 0/1, frame 0/1), then either
+        # the band tables [3, 4] of every rank (+ the root's two frames [5, 6]) or the root's slot tables [3, 4]
+        mine = [r.frame_alloc(seg_bytes), r.frame_alloc(seg_bytes), r.frame_alloc(512)]
+        if banded:
+            mine += [r.frame_alloc(world * band_rows * fw * 16), r.frame_alloc(world * band_rows * fw * 16)]
+            if rank == 0:
+                mine += [r.frame_alloc(fh * fw * 4), r.frame_alloc(fh * fw * 4)]
+        elif rank == 0:
+            mine += [r.frame_alloc(world * fh * fw * 16), r.frame_alloc(world * fh * fw * 16)]
         exported = [None] * world
         dist.all_gather_object(exported, [r.frame_export(p) for p in mine])
         ok, opened = True, {}
@@ -1121,8 +1129,15 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
             ptrs = {qq: (mine if qq == rank else opened[qq]) for qq in range(world)}
             direct = {"mine": mine, "opened": opened, "frame_no": 0,
                       "seg": [[ptrs[qq][s] for qq in range(world)] for s in (0, 1)],
-                      "seg_flag": [[ptrs[qq][2] + 64 * s for qq in range(world)] for s in (0, 1)],
-                      "slots": [ptrs[0][3 + s] for s in (0, 1)], "slot_flag": [ptrs[0][2] + 128 + 64 * s for s in (0, 1)]}
+                      "seg_flag": [[ptrs[qq][2] + 64 * s for qq in range(world)] for s in (0, 1)]}
+            if banded:
+                direct["band"] = [[ptrs[qq][3 + s] for qq in range(world)] for s in (0, 1)]
+                direct["band_flag"] = [[ptrs[qq][2] + 256 + 64 * s for qq in range(world)] for s in (0, 1)]
+                direct["frame"] = [ptrs[0][5 + s] for s in (0, 1)]
+                direct["frame_flag"] = [ptrs[0][2] + 384 + 64 * s for s in (0, 1)]
+            else:
+                direct["slots"] = [ptrs[0][3 + s] for s in (0, 1)]
+                direct["slot_flag"] = [ptrs[0][2] + 128 + 64 * s for s in (0, 1)]
         else:
             for qq in opened:
                 for pp in opened[qq]:
@@ -1136,26 +1151,39 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     if direct:
         direct["packed"] = [None, None]
         direct["last_packed"] = None
+        direct["last_frame"] = frame
 
     def step_direct(k, frame):
         view = orbit_view(V, k)
         r.set_view(view)
         n = direct["frame_no"]; s = n & 1; gen = n // 2 + 1
         row0, rows, (u0, u1) = D.brick_row_windows(view, grid, fh)
-        if rank == 0 and direct["packed"][s] is not None:
-            main_s.wait_event(direct["packed"][s])             # frame n - 2 has been summed: its slots may be overwritten (see above)
+        if direct["packed"][s] is not None:
+            main_s.wait_event(direct["packed"][s])             # my sum of frame n - 2 is done: its slots may be overwritten (see above)
         r.render_brick_alpha_send(direct["seg"][s], direct["seg_flag"][s], rank, row0[rank], rows, fw, fh, params, br)
         r.stream_wait_flag(direct["seg_flag"][s][rank], world * gen)
         r.compose_alpha_in_rows(direct["seg"][s][rank], grid, q, row0, rows, a_in, fw, fh)
-        r.render_brick_color_send(a_in, direct["slots"][s], direct["slot_flag"][s], rank, row0[rank], rows, fw, fh, params, br)
-        if rank == 0:
-            # the wait for everybody's increments and the sum + pack run on a second stream: rank 0's pass 1 of the next frame
-            # (which every other rank waits for) is not held up by the slowest pass 2 of this one
+        if banded:
+            r.render_brick_color_send_bands(a_in, direct["band"][s], direct["band_flag"][s], band_rows, rank, row0[rank], rows, fw, fh, params, br)
+        else:
+            r.render_brick_color_send(a_in, direct["slots"][s], direct["slot_flag"][s], rank, row0[rank], rows, fw, fh, params, br)
+        if banded or rank == 0:
+            # the wait for everybody's increments and the sum + pack run on a second stream: this rank's pass 1 of the next
+            # frame (which every other rank waits for) is not held up by the slowest pass 2 of this one
             after_p2 = torch.cuda.Event(); after_p2.record(main_s)
             side_s.wait_event(after_p2)
             r.set_stream(side_s.cuda_stream)
-            r.stream_wait_flag(direct["slot_flag"][s], world * gen)
-            r.pack_frame_slots(direct["slots"][s], world, row0, rows, frame, fw, fh, params.brightness)
+            if banded:
+                r.stream_wait_flag(direct["band_flag"][s][rank], world * gen)
+                r.pack_band_slots(direct["band"][s][rank], world, row0, rows, rank, band_rows, direct["frame"][s], direct["frame_flag"][s],
+                                  fw, fh, params.brightness)
+                if rank == 0:
+                    r.stream_wait_flag(direct["frame_flag"][s], world * gen)     # every band is in: the frame is complete
+                    direct["last_frame"] = V.as_torch(direct["frame"][s], (fh, fw), typestr="<i4", device=dev)
+            else:
+                r.stream_wait_flag(direct["slot_flag"][s], world * gen)
+                r.pack_frame_slots(direct["slots"][s], world, row0, rows, frame, fw, fh, params.brightness)
+                direct["last_frame"] = frame
             r.set_stream(main_s.cuda_stream)
             done = torch.cuda.Event(); done.record(side_s)
             direct["packed"][s] = direct["last_packed"] = done
@@ -1204,7 +1232,7 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
             step(k, other, collectives=True)
             torch.cuda.synchronize()
             if rank == 0:
-                a = frame.view(torch.uint8).to(torch.int16); b = other.view(torch.uint8).to(torch.int16)
+                a = direct["last_frame"].view(torch.uint8).to(torch.int16); b = other.view(torch.uint8).to(torch.int16)
                 worst = max(worst, int((a - b).abs().max())); differ += int((a != b).sum())
         barrier()
         if rank == 0:
@@ -1227,7 +1255,7 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     e0.record()
     for k in views:
         step(k)
-    if direct and rank == 0:
+    if direct and direct["last_packed"] is not None:
         main_s.wait_event(direct["last_packed"])               # the last frame is packed inside the timed region
     e1.record()
     barrier()
@@ -1245,7 +1273,9 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     t0 = time.perf_counter()
     for i, k in enumerate(views):
         if copied[i & 1] is not None:
-            (side_s if direct else main).wait_event(copied[i & 1])   # direct: only the pack (second stream) writes the frame
+            # root slots: only the pack (second stream) writes the frame; band owners: the other ranks' packs write it, and
+            # they follow this rank's pass 2 of the same frame
+            (side_s if (direct and not banded) else main).wait_event(copied[i & 1])
         step(k, frames2[i & 1])
         if rank == 0:
             if direct:
@@ -1254,7 +1284,7 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
                 packed = torch.cuda.Event(); packed.record(main)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(packed)
-                host[i & 1].copy_(frames2[i & 1], non_blocking=True)
+                host[i & 1].copy_(direct["last_frame"] if direct else frames2[i & 1], non_blocking=True)
                 copied[i & 1] = torch.cuda.Event(); copied[i & 1].record(copy_stream)
     torch.cuda.synchronize()
     barrier()
@@ -1270,15 +1300,17 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     if rank != 0:
         return None
     how = ("alpha pre-pass storing each brick's window rows into every rank's table over NVLink, in-stream counter wait, colour pass "
-           "storing the float4 increments into rank 0's table, sum in brick order + pack on rank 0 (no collective, no host "
-           "synchronisation in the loop)") if direct else (
+           + ("storing the float4 increments into the table of the owner of each band of image rows, every owner sums its band in brick "
+              "order, packs and stores the RGBA8 rows into rank 0's frame" if banded else
+              "storing the float4 increments into rank 0's table, sum in brick order + pack on rank 0")
+           + " (no collective, no host synchronisation in the loop)") if direct else (
            "alpha pre-pass, NCCL all-gather of segment alphas, colour pass, NCCL SUM reduction of float4 increments, pack on rank 0"
            + ("; collectives restricted to the image rows of each brick's screen footprint" if windows else ""))
     dec_gbs = decoded_vox * HIST_BYTES_PER_VOXEL / (dec_ms * 1e-3) / 1e9
     return {"workload": f"sort-last: {gdims[0]}x{gdims[1]}x{gdims[2]} distribution volume in {grid[0]}x{grid[1]}x{grid[2]} "
                         f"bricks of {E}^3 (+1 ghost) over {world} GPUs, {fw}x{fh} frames of the orbit, reference constants; " + how,
             "exchange": "direct" if direct else "nccl", "exchange_check": exchange_check,
-            "fused_first_segment": bool(direct) and args.sortlast_fuse == "on",
+            "fused_first_segment": bool(direct) and args.sortlast_fuse == "on", "compose": ("bands" if banded else "root") if direct else "nccl",
             "n_gpus": world, "value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s", "steps": len(views), "ms_per_step": ms / len(views),
             "fps": len(views) / (ms * 1e-3), "samples_per_frame": samples / len(views),
             "collective_bytes_per_frame": {("alpha_sent_per_rank" if direct else "all_gather"): coll_bytes[0],
@@ -1367,6 +1399,9 @@ def main():
     ap.add_argument("--assemble", default="p2p", choices=["p2p", "reduce"],
                     help="N > 1 tiles: p2p = kernels store tiles into rank 0's frame over NVLink; reduce = NCCL reduce")
     ap.add_argument("--sortlast-layout", default="texture", choices=["texture", "bricked", "linear"])
+    ap.add_argument("--sortlast-compose", default="auto", choices=["auto", "bands", "root"],
+                    help="direct exchange: increments summed + packed by band owners (every rank 1/N of the rows) or all by rank 0; "
+                         "auto = bands from 4 ranks on (N = 2: root 1581 fps, bands 1505; N = 8: root 1508, bands 1792)")
     ap.add_argument("--sortlast-fuse", default="on", choices=["on", "off"],
                     help="direct exchange: pass 1 keeps the colour of the march from alpha 0, pass 2 marches only pixels with incoming alpha")
     ap.add_argument("--sortlast-exchange", default="direct", choices=["direct", "nccl"],

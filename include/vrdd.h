@@ -334,6 +334,21 @@ int vrdd_render_brick_color_send(vrdd_handle h, const float* d_alpha_in, float* 
 int vrdd_pack_frame_slots(vrdd_handle h, const float* d_slots4, int nbricks, const int* row0, int rows, uint32_t* d_output,
                           int image_w, int image_h, float brightness);
 
+/* Band owners: the same pass 2 with the increments dealt out over ALL ranks instead of converging on the root.  Image rows
+ * [o * band_rows, (o + 1) * band_rows) belong to owner o (n_owners * band_rows >= image_h); every owner holds a table
+ * float4[nbricks][band_rows][W] and a counter.
+ *   pass 2   vrdd_render_brick_color_send_bands   stores each pixel's increment into slot [brick_index] of the table of the
+ *                                                 owner of its row, then adds 1 to every owner's counter
+ *   owner o  vrdd_stream_wait_flag(my counter, nranks * generation), then vrdd_pack_band_slots: sums the slots of band o in
+ *            brick order, packs to RGBA8 and stores the rows into d_frame (the root's frame, peer-mapped: 4 bytes per
+ *            pixel cross NVLink); the last block adds 1 to *d_frame_flag (may be NULL)
+ *   root     vrdd_stream_wait_flag(frame counter, n_owners * generation): the frame is complete. */
+int vrdd_render_brick_color_send_bands(vrdd_handle h, const float* d_alpha_in, float* const* d_owner_slots4, uint32_t* const* d_owner_flags,
+                                       int n_owners, int band_rows, int brick_index, int row0, int rows, int image_w, int image_h,
+                                       const vrdd_render_params* params, const vrdd_brick* brick);
+int vrdd_pack_band_slots(vrdd_handle h, const float* d_slots4, int nbricks, const int* row0, int rows, int band_index, int band_rows,
+                         uint32_t* d_frame, uint32_t* d_frame_flag, int image_w, int image_h, float brightness);
+
 /* Host helper: the inverse view matrix the reference builds with OpenGL
  * (volumeRender.cpp:224-246): M = Rx(-rot_x) * Ry(-rot_y) * T(-trans), top three rows,
  * row-major.  Angles in degrees.  (0, 0, (0,0,-4)) is the self-test view (:1024-1043). */

@@ -84,6 +84,11 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
     flags = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(nb)]
     slots = torch.zeros(nb * rows * w * 4, dtype=torch.float32, device="cuda")
     root_flag = torch.zeros(16, dtype=torch.int32, device="cuda")
+    # band owners (vrdd_render_brick_color_send_bands / vrdd_pack_band_slots): "rank" o owns rows [o * band, (o + 1) * band)
+    band = (h + nb - 1) // nb
+    owner_tabs = [torch.zeros(nb * band * w * 4, dtype=torch.float32, device="cuda") for _ in range(nb)]
+    owner_flags = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(nb)]
+    frame_flag = torch.zeros(16, dtype=torch.int32, device="cuda")
     # Generation 1 runs while samples are counted (pass 2 marches every pixel), 2 with the fused first segment (pass 1 keeps
     # the colour of the march from alpha 0 and pass 2 forwards it where the incoming alpha is 0), 3 with the fusion off.
     for gen in (1, 2, 3):
@@ -97,6 +102,7 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
             r.stream_wait_flag(flags[b], nb * gen)
             r.compose_alpha_in_rows(seg_tabs[b], grid, q, row0, rows, a_in, w, h)
             r.render_brick_color_send(a_in, slots, root_flag, b, row0[b], rows, w, h, params, bricks[b])
+            r.render_brick_color_send_bands(a_in, owner_tabs, owner_flags, band, b, row0[b], rows, w, h, params, bricks[b])
             r.synchronize()
         out2 = torch.zeros(h, w, dtype=torch.int32, device="cuda")
         root.stream_wait_flag(root_flag, nb * gen)
@@ -104,6 +110,14 @@ def _render_bricks(V, D, oracle, gdims, grid, view, img, params, seed, hist_full
         root.synchronize()
         assert torch.equal(out2, out), (grid, gen, int((out2 != out).sum()))
         assert int(root_flag[0]) == nb * gen and all(int(f[0]) == nb * gen for f in flags)
+        out3 = torch.full((h, w), -1, dtype=torch.int32, device="cuda")
+        for o, (r, q) in enumerate(handles):                   # every owner sums + packs its band into the "root's" frame
+            r.stream_wait_flag(owner_flags[o], nb * gen)
+            r.pack_band_slots(owner_tabs[o], nb, row0, rows, o, band, out3, frame_flag, w, h, params.brightness)
+            r.synchronize()
+        root.stream_wait_flag(frame_flag, nb * gen)
+        root.synchronize()
+        assert torch.equal(out3, out), (grid, gen, int((out3 != out).sum()))
     for r, _ in handles:
         r.close()
     return out.cpu().numpy().view(np.uint32), samples

@@ -40,6 +40,7 @@ EXPORTS = [
     "vrdd_set_frame_signal", "vrdd_stream_wait_flag", "vrdd_stream_post_flag", "vrdd_stream_wait_post_flag", "vrdd_set_peer_planes",
     "vrdd_get_mean_raw_device", "vrdd_set_peer_mean_raw", "vrdd_commit_mean_raw",
     "vrdd_render_brick_alpha_send", "vrdd_render_brick_color_send", "vrdd_pack_frame_slots",
+    "vrdd_render_brick_color_send_bands", "vrdd_pack_band_slots",
     "vrdd_render_brick_alpha", "vrdd_compose_alpha_in", "vrdd_compose_alpha_in_rows", "vrdd_render_brick_color", "vrdd_pack_frame",
     "vrdd_synth_histograms_region_device",
 ]
@@ -168,6 +169,8 @@ def lib():
             "vrdd_render_brick_alpha_send": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_render_brick_color_send": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
             "vrdd_pack_frame_slots": (i32, [vp, vp, i32, vp, i32, vp, i32, i32, f32]),
+            "vrdd_render_brick_color_send_bands": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(RenderParams), C.POINTER(Brick)]),
+            "vrdd_pack_band_slots": (i32, [vp, vp, i32, vp, i32, i32, i32, vp, vp, i32, i32, f32]),
             "vrdd_synth_histograms_region_device": (i32, [vp, u32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
             "vrdd_flex_set_tables_host": (i32, [vp, C.POINTER(FlexTables)]),
             "vrdd_flex_process": (i32, [vp, i32, C.POINTER(C.c_int64)]),
@@ -535,6 +538,18 @@ class Renderer:
     def render_brick_color_send(self, d_alpha_in, root_slots, root_flag, brick_index, row0, rows, w, h, params, brick):
         self._ck(lib().vrdd_render_brick_color_send(self._h, _ptr(d_alpha_in), _ptr(root_slots), _ptr(root_flag), brick_index, row0,
                                                     rows, w, h, C.byref(params), C.byref(brick)))
+
+    def render_brick_color_send_bands(self, d_alpha_in, owner_slots, owner_flags, band_rows, brick_index, row0, rows, w, h, params, brick):
+        n = len(owner_slots)
+        t = (C.c_void_p * n)(*[_ptr(x) for x in owner_slots])
+        f = (C.c_void_p * n)(*[_ptr(x) for x in owner_flags])
+        self._ck(lib().vrdd_render_brick_color_send_bands(self._h, _ptr(d_alpha_in), t, f, n, band_rows, brick_index, row0, rows, w, h,
+                                                          C.byref(params), C.byref(brick)))
+
+    def pack_band_slots(self, d_slots, nbricks, row0, rows, band_index, band_rows, d_frame, d_frame_flag, w, h, brightness):
+        r0 = (C.c_int * nbricks)(*row0)
+        self._ck(lib().vrdd_pack_band_slots(self._h, _ptr(d_slots), nbricks, r0, rows, band_index, band_rows, _ptr(d_frame),
+                                            _ptr(d_frame_flag), w, h, brightness))
 
     def pack_frame_slots(self, d_slots, nbricks, row0, rows, d_out, w, h, brightness):
         r0 = (C.c_int * nbricks)(*row0)

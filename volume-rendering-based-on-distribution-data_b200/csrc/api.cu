@@ -251,8 +251,8 @@ int vrdd_create(int device, vrdd_handle* out) {
     }
     if (cudaMalloc(&c->d_samples, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(c->d_samples, 0, sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMalloc(&c->d_tickets, 2 * sizeof(unsigned)) != cudaSuccess ||
-        cudaMemset(c->d_tickets, 0, 2 * sizeof(unsigned)) != cudaSuccess) {
+        cudaMalloc(&c->d_tickets, 4 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(c->d_tickets, 0, 4 * sizeof(unsigned)) != cudaSuccess) {
         delete c;
         return VRDD_ERR_CUDA;
     }
@@ -997,6 +997,32 @@ int vrdd_render_brick_color_send(vrdd_handle h, const float* d_alpha_in, float* 
     s.dst[0] = d_root_slots4 + (size_t)brick_index * rows * image_w * 4;              // slot [brick]: float4[rows][W]
     s.flags[0] = d_root_flag;
     return launch_brick_pass(c, 2, d_alpha_in, nullptr, image_w, image_h, p, *brick, &s);
+}
+
+int vrdd_render_brick_color_send_bands(vrdd_handle h, const float* d_alpha_in, float* const* d_owner_slots4, uint32_t* const* d_owner_flags,
+                                       int n_owners, int band_rows, int brick_index, int row0, int rows, int image_w, int image_h,
+                                       const vrdd_render_params* params, const vrdd_brick* brick) {
+    CHECK_HANDLE(h);
+    int rc = check_brick(c, brick);
+    if (rc != VRDD_OK) return rc;
+    if (!d_owner_slots4 || !d_owner_flags || n_owners < 1 || n_owners > VRDD_MAX_PEERS + 1 || band_rows < 1 || brick_index < 0 || rows < 1)
+        return fail(c, VRDD_ERR_INVALID, "render_brick_color_send_bands: bad arguments");
+    vrdd_render_params p;
+    if (params) p = *params; else vrdd_default_render_params(&p);
+    BrickSend s;
+    s.n_dst = n_owners; s.row0 = row0; s.rows = rows; s.band_rows = band_rows;
+    for (int o = 0; o < n_owners; ++o) {
+        if (!d_owner_slots4[o]) return fail(c, VRDD_ERR_INVALID, "render_brick_color_send_bands: null table");
+        s.dst[o] = d_owner_slots4[o] + (size_t)brick_index * band_rows * image_w * 4;   // slot [brick]: float4[band_rows][W]
+        s.flags[o] = d_owner_flags[o];
+    }
+    return launch_brick_pass(c, 2, d_alpha_in, nullptr, image_w, image_h, p, *brick, &s);
+}
+
+int vrdd_pack_band_slots(vrdd_handle h, const float* d_slots4, int nbricks, const int* row0, int rows, int band_index, int band_rows,
+                         uint32_t* d_frame, uint32_t* d_frame_flag, int image_w, int image_h, float brightness) {
+    CHECK_HANDLE(h);
+    return launch_pack_band_slots(c, d_slots4, nbricks, row0, rows, band_index, band_rows, d_frame, d_frame_flag, image_w, image_h, brightness);
 }
 
 int vrdd_pack_frame_slots(vrdd_handle h, const float* d_slots4, int nbricks, const int* row0, int rows, uint32_t* d_output,

@@ -391,7 +391,8 @@ struct vrdd_context {
     void* d_first4 = nullptr;        // sort-last, fused first segment: float4[rows][iw] record of pass 1 (sortlast.cu)
     size_t first4_cap = 0;           // ... its capacity in pixels
     unsigned long long first4_tag = 0;   // ... what it was computed for (0 = invalid)
-    unsigned* d_tickets = nullptr;   // {finished blocks, next item} of the persistent ray kernels (FrameSignal)
+    unsigned* d_tickets = nullptr;   // {finished blocks, next item} of the persistent ray kernels (FrameSignal); [2] = finished blocks
+                                     // of pack_band_slots_kernel, which may run on another stream beside a ray kernel
     unsigned* frame_signal = nullptr;   // vrdd_set_frame_signal: bumped by the last block of every vrdd_render launch
 
     int n_peers[2] = {0, 0};         // vrdd_set_peer_planes: the other ranks' linear planes, per source
@@ -466,9 +467,12 @@ struct BrickSend {
     float* dst[VRDD_MAX_PEERS + 1];
     unsigned* flags[VRDD_MAX_PEERS + 1];
     int row0, rows;
+    int band_rows = 0;               // pass 2, band owners: dst[o] = slot [brick] of the owner of image rows [o * band_rows, (o + 1) * band_rows)
 };
 int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float* d_out, int iw, int ih,
                       const vrdd_render_params& p, const vrdd_brick& b, const BrickSend* send = nullptr);
+int launch_pack_band_slots(vrdd_context* c, const float* d_slots4, int nbricks, const int* row0, int rows, int band_index, int band_rows,
+                           uint32_t* d_frame, uint32_t* d_frame_flag, int iw, int ih, float brightness);
 int launch_pack_frame_slots(vrdd_context* c, const float* d_slots4, int nbricks, const int* row0, int rows, uint32_t* d_out, int iw,
                             int ih, float brightness);
 int launch_compose_alpha_in(vrdd_context* c, const float* d_seg_rows, int gx, int gy, int gz, int qx, int qy, int qz,

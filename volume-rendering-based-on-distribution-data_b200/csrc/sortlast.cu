@@ -26,6 +26,12 @@
 // rank's pass-1 counter of frame k + 1 knows they have finished reading the tables of frame k (stream order there), so
 // frame k + 2 may overwrite them.
 //
+// Band owners (vrdd_render_brick_color_send_bands / vrdd_pack_band_slots): instead of all increments converging on the
+// root (N x 25 MB per 2048^2 frame into one GPU's NVLink port), image rows are dealt out in bands of band_rows rows, band
+// o to rank o.  Pass 2 stores every pixel's increment into the table of the band's owner; each owner sums the slots of
+// its band in brick order, packs to RGBA8 and stores the packed rows (4 B per pixel) into the root's frame.  Every rank
+// then receives 1/N of the increments, and the sum + pack is spread over all GPUs.
+//
 // Fused first segment (direct-send form): where nothing precedes a brick on a ray the incoming alpha is exactly 0, and
 // pass 2 would repeat pass 1's march step for step.  So pass 1 of the direct-send form accumulates colour as well (from
 // alpha 0, with the reference's early exit on its own alpha) and keeps (dR, dG, dB, dA) per pixel in a scratch buffer of
@@ -74,6 +80,7 @@ struct BrickArgs {
     unsigned* flags[VRDD_MAX_PEERS + 1];   // counter next to each table, bumped when the launch is complete
     unsigned* tickets;              // this context's block counter
     int row0, rows;                 // my screen window: only these rows are launched and written
+    int band_rows;                  // pass 2, band owners: > 0 -> dst[o] is slot [brick] of the owner of rows [o * band_rows, (o + 1) * band_rows)
     float4* first4;                 // FUSE: (dR, dG, dB, dA) of the march from alpha 0, float4[rows][iw] (pass 1 writes, pass 2 reads)
 };
 
@@ -278,7 +285,10 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
             }
         }
         if (PASS == 1 && FUSE) A.first4[(size_t)(y - A.row0) * A.iw + x] = make_float4(sr, sg, sb, sa);
-        if (A.n_dst > 0) {                                   // direct send: my window's rows into slot [brick] of the table(s)
+        if (PASS == 2 && A.band_rows > 0) {                  // band owners: this row's increments go to the owner of its band
+            const int o = y / A.band_rows;
+            reinterpret_cast<float4*>(A.dst[o])[(size_t)(y - o * A.band_rows) * A.iw + x] = make_float4(sr, sg, sb, sa - a_in);
+        } else if (A.n_dst > 0) {                            // direct send: my window's rows into slot [brick] of the table(s)
             const size_t wpix = (size_t)(y - A.row0) * A.iw + x;
 #pragma unroll 1
             for (int d = 0; d < A.n_dst; ++d) {
@@ -364,6 +374,36 @@ __global__ void pack_frame_slots_kernel(const float4* __restrict__ slots, int nb
                               ((uint32_t)(__saturatef(c.y * brightness) * 255.0f) << 8) | (uint32_t)(__saturatef(c.x * brightness) * 255.0f);
 }
 
+// band owner: rows [band0, band0 + band_rows) of the frame = sum, in brick order, of the slots whose window holds the row,
+// packed into the (root's, peer-mapped) frame; the last block tells the root
+__global__ void pack_band_slots_kernel(const float4* __restrict__ slots, int nb, const RowWindows Wn, int band0, int band_rows,
+                                       uint32_t* __restrict__ frame, unsigned* frame_flag, unsigned* tickets, int iw, int ih,
+                                       float brightness) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, yb = blockIdx.y, y = band0 + yb;
+    if (x < iw && y < ih) {
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int b = 0; b < nb; ++b) {
+            if ((unsigned)(y - Wn.row0[b]) < (unsigned)Wn.rows) {
+                const float4 v = slots[((size_t)b * band_rows + yb) * iw + x];
+                c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+            }
+        }
+        frame[(size_t)y * iw + x] = ((uint32_t)(__saturatef(c.w * brightness) * 255.0f) << 24) | ((uint32_t)(__saturatef(c.z * brightness) * 255.0f) << 16) |
+                                    ((uint32_t)(__saturatef(c.y * brightness) * 255.0f) << 8) | (uint32_t)(__saturatef(c.x * brightness) * 255.0f);
+    }
+    if (frame_flag) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(tickets, 1u) == gridDim.x * gridDim.y - 1) {
+                *tickets = 0u;
+                __threadfence_system();
+                asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(frame_flag) : "memory");
+            }
+        }
+    }
+}
+
 }  // namespace
 
 int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float* d_out, int iw, int ih,
@@ -411,7 +451,12 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
     A.samples = c->d_samples;
     A.n_dst = 0; A.row0 = 0; A.rows = ih; A.tickets = c->d_tickets;
     for (int d = 0; d <= VRDD_MAX_PEERS; ++d) { A.dst[d] = nullptr; A.flags[d] = nullptr; }
+    A.band_rows = 0;
     if (send) {
+        if (send->band_rows > 0) {
+            if (pass != 2 || (long long)send->band_rows * send->n_dst < ih) return fail(c, VRDD_ERR_INVALID, "render_brick: bands do not cover the frame");
+            A.band_rows = send->band_rows;
+        }
         A.n_dst = send->n_dst; A.row0 = send->row0; A.rows = send->rows;
         for (int d = 0; d < send->n_dst; ++d) { A.dst[d] = send->dst[d]; A.flags[d] = send->flags[d]; }
     }
@@ -497,6 +542,25 @@ int launch_pack_frame_slots(vrdd_context* c, const float* d_slots4, int nbricks,
     for (int b = 0; b < kMaxBricks; ++b) Wn.row0[b] = (b < nbricks) ? row0[b] : 0;
     dim3 grid((iw + 127) / 128, ih);
     pack_frame_slots_kernel<<<grid, 128, 0, c->stream>>>(reinterpret_cast<const float4*>(d_slots4), nbricks, Wn, d_out, iw, ih, brightness);
+    c->launches += 1;
+    VRDD_CUDA(c, cudaGetLastError());
+    return VRDD_OK;
+}
+
+int launch_pack_band_slots(vrdd_context* c, const float* d_slots4, int nbricks, const int* row0, int rows, int band_index, int band_rows,
+                           uint32_t* d_frame, uint32_t* d_frame_flag, int iw, int ih, float brightness) {
+    if (!d_slots4 || !d_frame || !row0 || iw <= 0 || ih <= 0 || nbricks < 1 || nbricks > kMaxBricks || rows < 1 || rows > ih ||
+        band_rows < 1 || band_index < 0)
+        return fail(c, VRDD_ERR_INVALID, "pack_band_slots: bad arguments");
+    RowWindows Wn;
+    Wn.rows = rows;
+    for (int b = 0; b < kMaxBricks; ++b) Wn.row0[b] = (b < nbricks) ? row0[b] : 0;
+    const int band0 = band_index * band_rows;
+    const int nrows = (band0 >= ih) ? 0 : ((band0 + band_rows <= ih) ? band_rows : ih - band0);
+    // an empty band (more ranks than bands) still owes the root its signal: one block, no rows
+    dim3 grid((iw + 127) / 128, nrows > 0 ? nrows : 1);
+    pack_band_slots_kernel<<<grid, 128, 0, c->stream>>>(reinterpret_cast<const float4*>(d_slots4), nbricks, Wn, nrows > 0 ? band0 : ih, band_rows,
+                                                        d_frame, d_frame_flag, c->d_tickets + 2, iw, ih, brightness);
     c->launches += 1;
     VRDD_CUDA(c, cudaGetLastError());
     return VRDD_OK;
