@@ -1175,11 +1175,13 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
             r.set_stream(side_s.cuda_stream)
             if banded:
                 r.stream_wait_flag(direct["band_flag"][s][rank], world * gen)
-                r.pack_band_slots(direct["band"][s][rank], world, row0, rows, rank, band_rows, direct["frame"][s], direct["frame_flag"][s],
+                dst = direct["host_frames"][s] if direct.get("host_frames") else direct["frame"][s]
+                r.pack_band_slots(direct["band"][s][rank], world, row0, rows, rank, band_rows, dst, direct["frame_flag"][s],
                                   fw, fh, params.brightness)
                 if rank == 0:
                     r.stream_wait_flag(direct["frame_flag"][s], world * gen)     # every band is in: the frame is complete
-                    direct["last_frame"] = V.as_torch(direct["frame"][s], (fh, fw), typestr="<i4", device=dev)
+                    if not direct.get("host_frames"):
+                        direct["last_frame"] = V.as_torch(direct["frame"][s], (fh, fw), typestr="<i4", device=dev)
             else:
                 r.stream_wait_flag(direct["slot_flag"][s], world * gen)
                 r.pack_frame_slots(direct["slots"][s], world, row0, rows, frame, fw, fh, params.brightness)
@@ -1264,14 +1266,80 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     samples = sum(counts[k] for k in views)
     # end to end: the packed frame of step k is copied to pinned host memory by a second stream while step k+1 runs
     # (two device frames, two host frames; step k+2 waits for the copy of frame k before it packs into that buffer)
+    # Band owners: no copy at all — the frame lives in POSIX shared memory page-locked and mapped by every rank, and every
+    # owner's pack kernel stores its RGBA8 rows straight into it over its own PCIe link (4 B per pixel, whole lines);
+    # rank 0's stream learns from the frame counter that all bands have landed.
+    e2e_zero_copy = False
+    shm = None
+    if direct and banded:
+        from multiprocessing import shared_memory
+        import numpy as np
+        nbytes = fw * fh * 4
+        shared_ok, host2 = 1, None
+        if rank == 0:
+            try:
+                shm = shared_memory.SharedMemory(create=True, size=2 * nbytes)
+            except Exception:
+                shm = None
+        box_ = [shm.name if shm is not None else None]
+        dist.broadcast_object_list(box_, src=0)
+        try:
+            if box_[0] is None:
+                raise RuntimeError("no shared memory segment")
+            if rank != 0:
+                shm = shared_memory.SharedMemory(name=box_[0])
+                try:
+                    from multiprocessing import resource_tracker
+                    resource_tracker.unregister(shm._name, "shared_memory")
+                except Exception:
+                    pass
+            host2 = np.ndarray((2, fh, fw), dtype=np.int32, buffer=shm.buf)
+            y0, y1 = min(rank * band_rows, fh), min((rank + 1) * band_rows, fh)
+            host2[:, y0:y1] = 0                                   # first touch by the band's owner
+            V.host_register(host2.ctypes.data, 2 * nbytes)
+        except Exception:
+            shared_ok = 0
+        if ctx.all_ok(shared_ok):
+            e2e_zero_copy = True
+            direct["host_frames"] = [host2[0].ctypes.data, host2[1].ctypes.data]
+            barrier()
+            for k in views[:2]:
+                step(k)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for k in views:
+                step(k)
+            torch.cuda.synchronize()                              # rank 0: the last frame counter has been reached
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            # the frame in host memory is the frame the device-side assembly gives
+            last_parity = (direct["frame_no"] - 1) & 1
+            direct["host_frames"] = None
+            step(views[-1])
+            torch.cuda.synchronize()
+            barrier()
+            if rank == 0 and not np.array_equal(direct["last_frame"].cpu().numpy(), host2[last_parity]):
+                raise SystemExit("bench.py: sort-last frame in shared host memory differs from the device-assembled frame")
+            barrier()
+            V.host_unregister(host2.ctypes.data)
+        host2 = None
+        if shm is not None:
+            try:
+                shm.close()
+                if rank == 0:
+                    shm.unlink()
+            except Exception:
+                pass
     host = [torch.empty(fh, fw, dtype=torch.int32).pin_memory() for _ in range(2)]
     frames2 = [frame, torch.zeros_like(frame)]
     copy_stream = torch.cuda.Stream(device=dev)
     copied = [None, None]
     main = torch.cuda.current_stream()
     barrier()
-    t0 = time.perf_counter()
-    for i, k in enumerate(views):
+    if not e2e_zero_copy:
+        t0 = time.perf_counter()
+    for i, k in enumerate([] if e2e_zero_copy else views):
         if copied[i & 1] is not None:
             # root slots: only the pack (second stream) writes the frame; band owners: the other ranks' packs write it, and
             # they follow this rank's pass 2 of the same frame
@@ -1288,7 +1356,8 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
                 copied[i & 1] = torch.cuda.Event(); copied[i & 1].record(copy_stream)
     torch.cuda.synchronize()
     barrier()
-    dt = max_over_ranks(time.perf_counter() - t0)
+    if not e2e_zero_copy:
+        dt = max_over_ranks(time.perf_counter() - t0)
     if direct:
         for qq in direct["opened"]:
             for pp in direct["opened"][qq]:
@@ -1321,7 +1390,11 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
                        "frac_of_hbm_peak": dec_gbs / (hbm_peak * world), "peak_gbs": hbm_peak * world},
             "e2e": {"value": samples / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": 80, "d2h_bytes_per_step": fw * fh * 4,
                     "fps": len(views) / dt,
-                    "call": ("vrdd_render_brick_alpha_send/compose/color_send + vrdd_pack_frame_slots" if direct else
+                    "zero_copy": e2e_zero_copy,
+                    "call": ("vrdd_render_brick_alpha_send/compose/color_send_bands + vrdd_pack_band_slots: every band owner's pack kernel stores "
+                             "its RGBA8 rows straight into the frame in page-locked shared host memory (checked against the device-assembled "
+                             "frame); otherwise: " if e2e_zero_copy else "") +
+                            ("vrdd_render_brick_alpha_send/compose/color_send + vrdd_pack_frame_slots" if direct else
                              "vrdd_render_brick_alpha/compose/color + NCCL + vrdd_pack_frame") + "; the frame of step k is copied to pinned host memory "
                             "by a second stream while step k+1 renders"},
             "gpu_launches": int(launches)}

@@ -229,7 +229,9 @@ int vrdd_render_host_async(vrdd_handle h, uint32_t* h_output, int image_w, int i
  * done; the host does not block.  Put it in front of a per-frame barrier between ranks. */
 int vrdd_render_host_fence(vrdd_handle h, int lag);
 int vrdd_render_host_wait(vrdd_handle h);
-/* cudaHostRegister / cudaHostUnregister for caller memory (e.g. a frame in POSIX shared memory). */
+/* cudaHostRegister (portable, mapped) / cudaHostUnregister for caller memory (e.g. a frame in POSIX shared memory).  Mapped:
+ * under unified addressing the same pointer is valid in kernels, so vrdd_pack_band_slots may be given a frame in registered
+ * host memory as d_frame and stores its rows there directly. */
 int vrdd_host_register(void* p, size_t bytes);
 int vrdd_host_unregister(void* p);
 /* Enables counting of transfer-function lookups (the S of Gsamples/s) in vrdd_render and

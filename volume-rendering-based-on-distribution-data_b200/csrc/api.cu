@@ -794,7 +794,7 @@ int vrdd_render_host_wait(vrdd_handle h) {
 // copies into it are asynchronous and run at full PCIe rate.
 int vrdd_host_register(void* p, size_t bytes) {
     if (!p || !bytes) return VRDD_ERR_INVALID;
-    return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? VRDD_OK : VRDD_ERR_CUDA;
+    return cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess ? VRDD_OK : VRDD_ERR_CUDA;
 }
 
 int vrdd_host_unregister(void* p) {
