@@ -466,6 +466,7 @@ def test_sector_layout_is_chosen_per_view_and_follows_a_new_decode(renderer, ora
     r = renderer
     r.set_volume(*dims)
     r.set_variant("raycast_layout_min_step", "0.3")          # small volume: 0.01 * 48 voxels per step
+    r.set_variant("raycast_layout_min_spacing", "0.5")       # ... and rays 0.96 voxels apart (the default asks for 1.5)
     for seed in (5, 6):
         hist = oracle.synth_histograms(seed, dims)
         r.set_histograms_host(hist)

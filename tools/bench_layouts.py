@@ -24,6 +24,9 @@ ap.add_argument("--persist", default="100")
 ap.add_argument("--gather-tf", default="follow")
 ap.add_argument("--gather-unroll", default="")
 ap.add_argument("--tf", default="")
+ap.add_argument("--cos", default="", help="auto: cosine of the largest angle between view direction and stacking axis for which the copy is used")
+ap.add_argument("--array-blocks", default="", help="resident blocks per SM of the 3-D array kernel (0 = all that fit)")
+ap.add_argument("--tile", type=int, default=0, help="enumerate the 16x16-pixel items tile by tile (TILE x TILE pixels) instead of row by row")
 a = ap.parse_args()
 vol, img = a.vol, a.img
 r = V.Renderer(0); r.set_stream(torch.cuda.current_stream().cuda_stream); r.set_volume(vol, vol, vol)
@@ -34,7 +37,7 @@ for z0 in range(0, vol, slab):
 r.synchronize(); del buf; torch.cuda.empty_cache()
 import vrdd_b200.dist as D
 fw, fh = D.frame_size(img, a.world)
-part = V.TilePartition(D.TILE, D.TILE, 0, a.world) if a.world > 1 else None
+part = V.TilePartition(D.TILE, D.TILE, 0, a.world) if a.world > 1 else (V.TilePartition(a.tile, a.tile, 0, 1) if a.tile else None)
 out = torch.zeros(fh, fw, dtype=torch.int32, device="cuda")
 r.set_variant("raycast_persist_pct", a.persist)
 r.set_variant("raycast_gather_tf", a.gather_tf)
@@ -44,6 +47,10 @@ import math
 ms_ = int(math.ceil(2 * math.sqrt(3.0) / a.tstep)) + 1
 p = V.default_render_params(query_method=1, tstep=a.tstep, max_steps=max(500, ms_))
 r.set_variant("raycast_unroll", a.unroll if a.unroll in ("1", "2", "4", "8") else "4")
+if a.array_blocks:
+    r.set_variant("raycast_array_blocks_per_sm", a.array_blocks)
+if a.cos:
+    r.set_variant("raycast_layout_cos", a.cos)
 if a.gather_unroll:
     r.set_variant("raycast_gather_unroll", a.gather_unroll)
 res = {}

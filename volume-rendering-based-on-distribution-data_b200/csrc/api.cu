@@ -1094,6 +1094,10 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         if (v == "interleaved") c->var_decode_order = 0;
         else if (v == "chunked") c->var_decode_order = 1;
         else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_order is interleaved|chunked");
+    } else if (w == "raycast_array_blocks_per_sm") {
+        const int n = std::atoi(variant);
+        if (n < -1 || n > 8) return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_array_blocks_per_sm is -1 (auto), 0 (all that fit), 1..8");
+        c->var_array_blocks_per_sm = n;
     } else if (w == "raycast_unroll") {
         if (v == "1" || v == "2" || v == "4" || v == "8") c->var_unroll = v[0] - '0';
         else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_unroll is 1|2|4|8");
@@ -1107,6 +1111,10 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         const float f = (float)std::atof(variant);
         if (!(f >= 0.f)) return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_layout_min_step is a number of voxels >= 0");
         c->var_layout_min_step = f;
+    } else if (w == "raycast_layout_min_spacing") {
+        const float f = (float)std::atof(variant);
+        if (!(f >= 0.f)) return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_layout_min_spacing is a number of voxels >= 0");
+        c->var_layout_min_spacing = f;
     } else if (w == "raycast_gather_unroll") {
         if (v == "2" || v == "4") c->var_gather_unroll = v[0] - '0';
         else return fail(c, VRDD_ERR_INVALID, "set_variant: raycast_gather_unroll is 2|4");

@@ -417,11 +417,14 @@ struct vrdd_context {
     int var_gather_unroll = 2;       // march batch of raycast_gather_kernel (2: 48 registers, five blocks per SM — measured faster than 4)
     int var_gather_tf = -1;          // transfer function of raycast_gather_kernel: -1 follow var_tf, 0 texture unit, 1 shared-memory table
     int var_sortlast_fuse = 1;       // direct-send sort-last: pass 1 keeps the colour of the march from alpha 0, pass 2 skips those pixels
+    int var_array_blocks_per_sm = -1; // 3-D array ray kernel: resident 256-thread blocks per SM (-1 = by ray spacing, 0 = as many as fit); at persist_pct 100
+    float var_layout_min_spacing = 1.5f;  // auto: a layered copy only if neighbouring rays are at least this many voxels apart
     int var_persist_pct = 100;       // ray kernels: blocks launched in percent of the resident capacity (0: one block per item)
     int var_layout = 0;              // array the ray caster samples: 0 auto (per view, launch_raycast), 1 the 3-D array (texture unit
                                      // filters), 2 / 3 the layered copy stacked along x / y (tld4 + the unit's integer weights in the kernel)
     float var_layout_min_step = 2.5f;   // auto: a copy only if a ray advances more than this many voxels per step along its stacking axis
-    float var_layout_cos = 0.68f;       // ... and the view direction is within acos(this) of that axis (47 degrees)
+    float var_layout_cos = 0.74f;       // ... and the view direction is within acos(this) of that axis (42 degrees; 47 before the 3-D array
+                                        // kernel ran with two blocks per SM)
     int var_ray_setup = 1;           // 1 "nvcc" (default): the rounding of the reference's own build; 0 "source": the source's uncontracted order (eye_ray above)
     int var_mode7 = 2;               // 2 layered array + tld4 where the volume allows it (default), 0 point-sampled 3-D array, 1 linear plane
     int var_fractal_sink = 1;        // moments2: 1 = the surfaces-only instance where the sink is just the three 3-D arrays; 0 = generic

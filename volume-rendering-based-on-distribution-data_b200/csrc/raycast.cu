@@ -703,8 +703,16 @@ __global__ void build_gather_copy_kernel(cudaSurfaceObject_t src, cudaSurfaceObj
 
 // Persistent launch: as many blocks as the device holds at once (never more than there are items); the blocks share
 // the items through the queue of FrameSignal.
+// Distance between neighbouring rays at the centre of the volume, in voxels: the frame spans 4 world units there (eye 4
+// away, image plane |u| <= 1 at distance 2), the box 2 world units over the volume's longest edge.
+float ray_spacing_voxels(const vrdd_context* c, int iw, int ih) {
+    const int n = c->W > c->H ? (c->W > c->D ? c->W : c->D) : (c->H > c->D ? c->H : c->D);
+    const int m = iw > ih ? iw : ih;
+    return m > 0 ? 2.0f * (float)n / (float)m : 0.0f;
+}
+
 template <class Kernel, class Args>
-void launch_persistent(vrdd_context* c, Kernel kernel, const Args& A, long long items, size_t smem) {
+void launch_persistent(vrdd_context* c, Kernel kernel, const Args& A, long long items, size_t smem, int max_per_sm = 0) {
     static std::map<std::pair<const void*, size_t>, int> per_sm_cache;
     const std::pair<const void*, size_t> key(reinterpret_cast<const void*>(kernel), smem);
     auto it = per_sm_cache.find(key);
@@ -717,14 +725,29 @@ void launch_persistent(vrdd_context* c, Kernel kernel, const Args& A, long long 
     // 0 = one block per item, i.e. the hardware's block scheduler instead of the queue)
     long long cap = (long long)it->second * c->num_sms * c->var_persist_pct / 100;
     if (c->var_persist_pct <= 0 || cap < 1) cap = items;
+    // max_per_sm: fewer resident blocks than fit.  The 3-D array path is fastest with TWO blocks (16 warps) per SM: with
+    // the five that fit, the rays of 1280 pixels march through one SM's L1 at once and evict one another's lines
+    // (profiles/tuning_r2.md: oblique views 0.285 -> 0.259 ms, frontal views unchanged; more blocks under a register cap
+    // are slower still).  The gather path is bound by instruction issue and wants all the warps it can get.
+    if (max_per_sm > 0 && c->var_persist_pct == 100 && (long long)max_per_sm * c->num_sms < cap) cap = (long long)max_per_sm * c->num_sms;
     kernel<<<(unsigned)(items < cap ? items : cap), kBlock, smem, c->stream>>>(A);
 }
 
 template <int SAMPLER, int TFMODE, int U>
 void launch_u(vrdd_context* c, bool count, long long items, const RayArgs& A) {
     const size_t smem = (TFMODE == 1) ? sizeof(float4) * (size_t)A.tf_n : 0;
-    if (count) launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, true, U>, A, items, smem);
-    else launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, false, U>, A, items, smem);
+    // resident blocks per SM of the 3-D array kernel: two where the samples are sparse in the volume — neighbouring rays
+    // about two voxels apart AND steps of several voxels (the headline: every DRAM line the rays cross is fetched, and five
+    // blocks' rays evict one another's lines from L1) —, three otherwise (2048^2 frames, smaller volumes, the
+    // resolution-matched step: the texture pipe is the limit and wants more requests); -1 = this rule, 0 = all that fit
+    int per_sm = 0;
+    if (SAMPLER == 0) {
+        const int n = A.W > A.H ? (A.W > A.D ? A.W : A.D) : (A.H > A.D ? A.H : A.D);
+        const bool sparse = ray_spacing_voxels(c, A.iw, A.ih) >= 1.5f && A.tstep * 0.5f * (float)n >= 2.5f;
+        per_sm = (c->var_array_blocks_per_sm >= 0) ? c->var_array_blocks_per_sm : (sparse ? 2 : 3);
+    }
+    if (count) launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, true, U>, A, items, smem, per_sm);
+    else launch_persistent(c, raycast_kernel<SAMPLER, TFMODE, false, U>, A, items, smem, per_sm);
 }
 
 // The march batch U is a measured knob (vrdd_set_variant("raycast_unroll")) of the default path only: texture
@@ -868,12 +891,16 @@ int ensure_gather_copy(vrdd_context* c, vrdd_decoded_volume& v, int comp, int ax
 // axis on (0.234 against 0.243 ms at 45 degrees, 0.190 against 0.240 ms looking straight along x; 0.245 against 0.213 ms
 // at 39 degrees) — it halves the lines touched when the view is within ~20 degrees of its axis and is no worse in
 // between, where every line of the region the rays cross is touched whatever its shape.  So: the stacking axis the
-// centre ray is most parallel to, if it is within acos(var_layout_cos) = 47 degrees of it and a step advances by more
+// centre ray is most parallel to, if it is within acos(var_layout_cos) = 42 degrees of it and a step advances by more
 // than var_layout_min_step voxels along it (otherwise no slice is ever skipped and the cheaper texture-unit path wins).
-int choose_sector_axis(const vrdd_context* c, const vrdd_render_params& p) {
+int choose_sector_axis(const vrdd_context* c, const vrdd_render_params& p, int iw, int ih) {
     if (c->var_layout == 1) return 0;
     if (c->var_layout == 2) return 1;
     if (c->var_layout == 3) return 2;
+    // Rays one voxel apart or closer (a 2048^2 frame of the 1024^3 volume, the 512^3 volume at 1024^2) share their lines
+    // across the frame whatever the layout: the texture-unit path wins on every view there (side view of 1024^3 at
+    // 2048^2: 0.49 against 0.58 ms; of 512^3 at 1024^2: 0.139 against 0.195 ms).
+    if (ray_spacing_voxels(c, iw, ih) < c->var_layout_min_spacing) return 0;
     const float dir[2] = {std::fabs(c->view[2]), std::fabs(c->view[6])};       // |x|, |y| of the centre ray (third column of M)
     const float adv[2] = {dir[0] * p.tstep * 0.5f * (float)c->W, dir[1] * p.tstep * 0.5f * (float)c->H};
     const int a = dir[0] >= dir[1] ? 0 : 1;
@@ -985,7 +1012,7 @@ int launch_raycast(vrdd_context* c, uint32_t* d_out, int iw, int ih, const vrdd_
     if (sampler == VRDD_SAMPLER_TEXTURE && !A.vol_tex) return fail(c, VRDD_ERR_INVALID, "render: no texture volume");
     if (sampler == VRDD_SAMPLER_BRICKED && !A.vol_brick) return fail(c, VRDD_ERR_INVALID, "render: no bricked volume");
     if (sampler == VRDD_SAMPLER_TEXTURE) {
-        int axis = choose_sector_axis(c, p);
+        int axis = choose_sector_axis(c, p, iw, ih);
         if (axis != 0) {
             const int rc = ensure_gather_copy(c, vol, comp, axis);
             if (rc == VRDD_ERR_UNSUPPORTED && c->var_layout == 0) axis = 0;       // auto: the 3-D array always works
