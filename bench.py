@@ -1058,6 +1058,8 @@ def sortlast_record(args, ctx, V, D, torch, dist, local, dev, hbm_peak, steps, w
     r.set_sampler({"texture": V.SAMPLER_TEXTURE, "linear": V.SAMPLER_LINEAR, "bricked": V.SAMPLER_BRICKED}[args.sortlast_layout])
     r.set_volume(*size)
     r.set_variant("sortlast_fuse", args.sortlast_fuse)
+    if args.sortlast_blocks >= 0:
+        r.set_variant("sortlast_blocks_per_sm", str(args.sortlast_blocks))
     ev = lambda: torch.cuda.Event(enable_timing=True)
     barrier, max_over_ranks = ctx.barrier, ctx.max
     # ---- decode my brick slab by slab -----------------------------------------------------------
@@ -1475,6 +1477,7 @@ def main():
     ap.add_argument("--sortlast-compose", default="auto", choices=["auto", "bands", "root"],
                     help="direct exchange: increments summed + packed by band owners (every rank 1/N of the rows) or all by rank 0; "
                          "auto = bands from 4 ranks on (N = 2: root 1581 fps, bands 1505; N = 8: root 1508, bands 1792)")
+    ap.add_argument("--sortlast-blocks", type=int, default=-1, help="sort-last brick kernel: resident blocks per SM (-1: library default)")
     ap.add_argument("--sortlast-fuse", default="on", choices=["on", "off"],
                     help="direct exchange: pass 1 keeps the colour of the march from alpha 0, pass 2 marches only pixels with incoming alpha")
     ap.add_argument("--sortlast-exchange", default="direct", choices=["direct", "nccl"],

@@ -1077,6 +1077,10 @@ int vrdd_set_variant(vrdd_handle h, const char* what, const char* variant) {
         if (v == "generic") c->var_fractal_sink = 0;
         else if (v == "auto") c->var_fractal_sink = 1;          // the surfaces-only instance where the sink allows it
         else return fail(c, VRDD_ERR_INVALID, "set_variant: decode_fractal_sink is auto|generic");
+    } else if (w == "sortlast_blocks_per_sm") {
+        const int n = std::atoi(variant);
+        if (n < 0 || n > 16) return fail(c, VRDD_ERR_INVALID, "set_variant: sortlast_blocks_per_sm is 0..16");
+        c->var_sortlast_blocks_per_sm = n;
     } else if (w == "sortlast_fuse") {
         if (v == "on") c->var_sortlast_fuse = 1;
         else if (v == "off") c->var_sortlast_fuse = 0;

@@ -416,6 +416,8 @@ struct vrdd_context {
     int var_unroll = 4;              // ray-march batch: steps whose fetches are in flight together (1,2,4,8)
     int var_gather_unroll = 2;       // march batch of raycast_gather_kernel (2: 48 registers, five blocks per SM — measured faster than 4)
     int var_gather_tf = -1;          // transfer function of raycast_gather_kernel: -1 follow var_tf, 0 texture unit, 1 shared-memory table
+    int var_sortlast_blocks_per_sm = 3;   // sort-last brick kernel: resident blocks per SM striding over the 16x16-pixel items (0 = one block
+                                          // per item; N = 2, same box: 0 -> 1432, 2 -> 1413, 3 -> 1562, 4 -> 1559, 5 -> 1370 fps)
     int var_sortlast_fuse = 1;       // direct-send sort-last: pass 1 keeps the colour of the march from alpha 0, pass 2 skips those pixels
     int var_array_blocks_per_sm = -1; // 3-D array ray kernel: resident 256-thread blocks per SM (-1 = by ray spacing, 0 = as many as fit); at persist_pct 100
     float var_layout_min_spacing = 1.5f;  // auto: a layered copy only if neighbouring rays are at least this many voxels apart

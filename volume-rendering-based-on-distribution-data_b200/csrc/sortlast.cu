@@ -80,6 +80,7 @@ struct BrickArgs {
     unsigned* flags[VRDD_MAX_PEERS + 1];   // counter next to each table, bumped when the launch is complete
     unsigned* tickets;              // this context's block counter
     int row0, rows;                 // my screen window: only these rows are launched and written
+    int n_items;                    // 16x16-pixel items of the launch (the window's rows)
     int band_rows;                  // pass 2, band owners: > 0 -> dst[o] is slot [brick] of the owner of rows [o * band_rows, (o + 1) * band_rows)
     float4* first4;                 // FUSE: (dR, dG, dB, dA) of the march from alpha 0, float4[rows][iw] (pass 1 writes, pass 2 reads)
 };
@@ -182,11 +183,13 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
     for (int i = threadIdx.x; i < A.tf_n; i += kBlock) tf_s[i] = A.tf_tab[i];
     __syncthreads();
     const int blocks_x = (A.iw + 15) / 16;
-    const int by = blockIdx.x / blocks_x, bx = blockIdx.x - by * blocks_x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long nsamp = 0;
+    // 16x16-pixel items, block-strided: the launch holds as many blocks as the caller wants resident (launch_brick_pass)
+    for (int item = blockIdx.x; item < A.n_items; item += gridDim.x) {
+    const int by = item / blocks_x, bx = item - by * blocks_x;
     const int x = bx * 16 + (warp & 1) * 8 + (lane & 7);
     const int y = A.row0 + by * 16 + (warp >> 1) * 4 + (lane >> 3);          // row0 = 0, rows = ih without a window
-    unsigned long long nsamp = 0;
     if (x < A.iw && y < A.row0 + A.rows) {
         const size_t pix = (size_t)y * A.iw + x;
         const RaySetup R = make_ray(A.m, x, y, A.iw, A.ih, A.ref_rounding);
@@ -297,6 +300,7 @@ __global__ void __launch_bounds__(kBlock) raycast_brick_kernel(const BrickArgs A
             }
         } else if (PASS == 1) A.alpha_seg[pix] = sa;
         else A.partial[pix] = make_float4(sr, sg, sb, sa - a_in);
+    }
     }
     if (COUNT) {
 #pragma unroll
@@ -460,7 +464,10 @@ int launch_brick_pass(vrdd_context* c, int pass, const float* d_alpha_in, float*
         A.n_dst = send->n_dst; A.row0 = send->row0; A.rows = send->rows;
         for (int d = 0; d < send->n_dst; ++d) { A.dst[d] = send->dst[d]; A.flags[d] = send->flags[d]; }
     }
-    const int grid = ((iw + 15) / 16) * ((A.rows + 15) / 16);      // only the rows of the window are launched
+    A.n_items = ((iw + 15) / 16) * ((A.rows + 15) / 16);           // only the rows of the window are launched
+    // resident blocks: all items at once (0), or var_sortlast_blocks_per_sm per SM striding over the items
+    const long long cap = (long long)c->var_sortlast_blocks_per_sm * c->num_sms;
+    const int grid = (cap > 0 && cap < A.n_items) ? (int)cap : A.n_items;
     const bool count = c->count_samples && pass == 2;
     // Fused first segment: only in the direct-send form (pass 2 is known to follow pass 1 of the same frame), not while
     // samples are counted (the count is taken in pass 2).  The record is tagged with everything the march depends on; a
