@@ -42,6 +42,7 @@ SAMPLE_BYTES = 32                        # 8 fp32 texels per tril
 ORBIT_VIEWS = 64
 HBM_FALLBACK_GBS = 6650.0                # /opt/skills/guides/B200_PROFILING.md
 STRONG_IMAGE = 2048                      # BASELINE.json configs[2]
+L1TEX_FALLBACK_GSAMPLES = 559.1          # profiles/l1tex_peak_r2.txt (tools/l1tex_peak.cu on a B200 of this pool), when not measured live
 
 
 def measured_peaks():
@@ -66,6 +67,36 @@ def ncu_traffic(kernel, bytes_per_launch):
     if t and abs(t["algorithmic_bytes_per_launch"] - bytes_per_launch) < 1e-6 * bytes_per_launch:
         return t["dram_bytes_per_launch"]
     return None
+
+
+def ray_roofline(samples_per_launch, kernel_ms, volume_edge, fw, fh, hbm_peak, peak_src, traffic, tex_peak):
+    """which roofline bounds the ray caster depends on how dense the rays are in the volume.  Rays more than
+    one voxel apart (the headline: 1024^3 at 1024^2, two voxels): every sample brings its own texels, S * 32 B / t against
+    the HBM peak.  Rays one voxel apart or closer (2048^2 frames, the larger frames of N > 1): neighbouring rays share
+    their texels in L1 / L2, DRAM moves a fraction of 32 B per sample, and the 32-byte figure is not a bound (it exceeds
+    the HBM peak); the binding limit is the texture pipe: S / t against its measured fetch rate.  The other figure is kept
+    next to it for information."""
+    spacing = 2.0 * volume_edge / max(fw, fh)
+    gs = samples_per_launch / (kernel_ms * 1e-3) / 1e9
+    hbm = {"achieved": samples_per_launch * SAMPLE_BYTES / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src}
+    hbm["frac"] = hbm["achieved"] / hbm_peak
+    live = bool(tex_peak and "tex3d_linear_l1_gsamples_per_s" in tex_peak)
+    l1_peak = tex_peak["tex3d_linear_l1_gsamples_per_s"] if live else L1TEX_FALLBACK_GSAMPLES
+    l1 = {"achieved": gs, "peak": l1_peak, "unit": "Gsamples/s (one trilinear fp32 fetch each)", "frac": gs / l1_peak,
+          "peak_source": "tools/l1tex_peak.cu, run in this process" if live else "profiles/l1tex_peak_r2.txt (tools/l1tex_peak.cu)"}
+    if live:
+        l1["all"] = tex_peak
+    r = {"launch_ms": kernel_ms, "bytes_per_launch": samples_per_launch * SAMPLE_BYTES, "gsamples_per_s_kernel_only": gs,
+         "ray_spacing_voxels": spacing, "traffic": traffic}
+    if spacing > 1.0:
+        r.update({"bound": "hbm", **hbm, "l1tex": l1})
+    else:
+        r.update({"bound": "l1tex", **l1, "hbm_algorithmic": dict(hbm, note="not a bound at this ray density: neighbouring rays share "
+                                                                            "their texels on chip (see traffic for what DRAM moved)")})
+    if traffic:
+        r["traffic_gbs"] = traffic / (kernel_ms * 1e-3) / 1e9
+        r["traffic_frac"] = r["traffic_gbs"] / hbm_peak
+    return r
 
 
 def l1tex_peak():
@@ -651,6 +682,8 @@ def run_ours(args):
     kernel_ms, _ = F.time(params, views, warm_views, local=True)  # the ray-cast kernel alone, on the SAME views
     kernel_ms /= args.steps
 
+    tex_peak = l1tex_peak() if (rank == 0 and args.l1tex) else None   # the other ranks wait at the next barrier
+
     # ---- strong scaling (BASELINE.json configs[2]): a fixed 2048 x 2048 frame of the same volume at every N --------
     strong = None
     if args.strong:
@@ -666,11 +699,8 @@ def run_ours(args):
                   "value": s_samples / (s_ms * 1e-3) / 1e9, "unit": "Gsamples/s", "ms_per_step": s_ms / args.steps,
                   "fps": args.steps / (s_ms * 1e-3), "samples_per_frame": s_samples / args.steps,
                   "kernel_ms_per_step": sk_ms / args.steps, "gpu_launches": int(s_launches),
-                  "roofline": {"bound": "hbm", "achieved": s_samples / world / args.steps * SAMPLE_BYTES / (sk_ms / args.steps * 1e-3) / 1e9,
-                               "peak": hbm_peak, "unit": "GB/s", "traffic": tr["dram_bytes_per_launch"] if tr else None}}
-        strong["roofline"]["frac"] = strong["roofline"]["achieved"] / hbm_peak
-        if tr:
-            strong["roofline"]["traffic_frac"] = tr["dram_bytes_per_launch"] / (sk_ms / args.steps * 1e-3) / 1e9 / hbm_peak
+                  "roofline": ray_roofline(s_samples / world / args.steps, sk_ms / args.steps, args.volume, STRONG_IMAGE, STRONG_IMAGE,
+                                           hbm_peak, peak_src, tr["dram_bytes_per_launch"] if (tr and args.volume == 1024) else None, tex_peak)}
         if S is not F:
             S.close()
             del S
@@ -935,7 +965,6 @@ def run_ours(args):
 
     clk = clocks.stop()
     total_launches = r.kernel_launches() - launches0
-    tex_peak = l1tex_peak() if (rank == 0 and world == 1 and args.l1tex) else None
 
     # ---- CPU baselines (rank 0, N = 1) ---------------------------------------------------------
     cpu_ray = None
@@ -975,23 +1004,12 @@ def run_ours(args):
         if tj and args.volume == 1024 and args.image == 1024:
             ray_traffic = tj["dram_bytes_per_launch"]
             traffic_what = "mean DRAM bytes of the %d orbit launches under ncu (%s)" % (tj.get("launches", 1), tj.get("source", "profiles/"))
-        roofline = {"kernel": "raycast_kernel / raycast_gather_kernel (per view)", "bound": "hbm",
-                    "achieved": my_samples * SAMPLE_BYTES / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "peak_source": peak_src, "launch_ms": kernel_ms, "bytes_per_launch": my_samples * SAMPLE_BYTES,
-                    "gsamples_per_s_kernel_only": my_samples / (kernel_ms * 1e-3) / 1e9, "traffic": ray_traffic,
-                    "note": "algorithmic bytes = 32 B per trilinear sample (8 fp32 texels) x samples of the average launch; "
+        roofline = ray_roofline(my_samples, kernel_ms, args.volume, fw, fh, hbm_peak, peak_src, ray_traffic, tex_peak)
+        roofline["kernel"] = "raycast_kernel / raycast_gather_kernel (per view)"
+        roofline["note"] = ("algorithmic bytes = 32 B per trilinear sample (8 fp32 texels) x samples of the average launch; "
                             "traffic = " + traffic_what + "; DRAM delivers whole 128-byte lines (8x4x1 texels), so on oblique views "
                             "every line of the region the rays cross is read once: 64 B per sample is compulsory there, 24 B on "
-                            "views along an axis"}
-        roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        if ray_traffic:                                   # what the DRAM actually moved per launch, against the same peak
-            roofline["traffic_gbs"] = ray_traffic / (kernel_ms * 1e-3) / 1e9
-            roofline["traffic_frac"] = roofline["traffic_gbs"] / roofline["peak"]
-        if tex_peak and "tex3d_linear_l1_gsamples_per_s" in tex_peak:
-            l1 = tex_peak["tex3d_linear_l1_gsamples_per_s"]
-            roofline["l1tex"] = {"achieved": my_samples / (kernel_ms * 1e-3) / 1e9, "peak": l1, "unit": "Gsamples/s (one trilinear fp32 fetch each)",
-                                 "frac": my_samples / (kernel_ms * 1e-3) / 1e9 / l1, "peak_source": "tools/l1tex_peak.cu, run in this process",
-                                 "all": tex_peak}
+                            "views along an axis")
         line = {"metric": "raycast_throughput", "value": gsamples, "unit": "Gsamples/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
