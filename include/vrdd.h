@@ -326,7 +326,14 @@ int vrdd_pack_frame(vrdd_handle h, const float* d_sum4, uint32_t* d_output, int 
  *   pass 2   vrdd_render_brick_color_send   stores the increments into slot [brick_index] of the root's table and adds 1 to
  *                                           the root's counter
  *   root     vrdd_stream_wait_flag(counter, nranks * generation), vrdd_pack_frame_slots: the frame is the sum of the
- *                                           slots in brick order, packed to RGBA8. */
+ *                                           slots in brick order, packed to RGBA8.
+ * Fused first segment: vrdd_render_brick_alpha_send also accumulates colour from alpha 0 and keeps (dR, dG, dB, dA) per
+ * pixel in a scratch buffer of the handle; the vrdd_render_brick_color_send* call that follows it for the same view,
+ * parameters, window and brick forwards that record for every pixel whose incoming alpha is exactly 0 (nothing precedes
+ * the brick on that ray: pass 2 would repeat pass 1's march bit for bit) and marches only the others.  The record is
+ * tagged with everything it depends on and dropped when the volume, the transfer function or a variant changes; a pass 2
+ * without a matching record marches every pixel.  Off while samples are counted (vrdd_count_samples) and with
+ * vrdd_set_variant("sortlast_fuse", "off"). */
 int vrdd_render_brick_alpha_send(vrdd_handle h, float* const* d_seg_tables, uint32_t* const* d_flags, int n_tables, int brick_index,
                                  int row0, int rows, int image_w, int image_h, const vrdd_render_params* params,
                                  const vrdd_brick* brick);
