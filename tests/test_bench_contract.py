@@ -51,3 +51,25 @@ def test_timed_views_span_the_orbit_whatever_the_step_count():
     assert v20[0] == 0 and v20[-1] >= 57 and len(set(v20)) == 20
     assert max(b - a for a, b in zip(v20, v20[1:])) <= 4
     assert bench.timed_views(130)[64:70] == [0, 1, 2, 3, 4, 5]
+
+
+def test_roofline_bound_follows_the_ray_density():
+    """SURVEY.md §8d / round-1 verdict: the 32-bytes-per-sample figure is a bound only where every sample brings its own
+    texels.  Rays one voxel apart or closer share them on chip, the figure can exceed the HBM peak there, and the line must
+    then report the texture pipe's roofline as the bound and keep the other figure marked as information."""
+    sys.path.insert(0, ROOT)
+    import bench
+    hbm = 6553.6
+    # the headline: 1024^3 at 1024^2, rays two voxels apart, 24.2 M samples in 0.2 ms
+    r = bench.ray_roofline(24.2e6, 0.2, 1024, 1024, 1024, hbm, "measured", 886e6, None)
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["achieved"] - 24.2e6 * 32 / 0.2e-3 / 1e9) < 1e-6
+    assert 0 < r["frac"] < 1 and r["ray_spacing_voxels"] == 2.0 and 0 < r["traffic_frac"] < 1
+    assert r["l1tex"]["peak"] == bench.L1TEX_FALLBACK_GSAMPLES and "profiles/" in r["l1tex"]["peak_source"]
+    # the fixed 2048^2 frame: one voxel apart, 97 M samples in 0.43 ms -> 7.2 TB/s "algorithmic", not a bound
+    live = {"tex3d_linear_l1_gsamples_per_s": 560.0}
+    s = bench.ray_roofline(97e6, 0.43, 1024, 2048, 2048, hbm, "measured", None, live)
+    assert s["bound"] == "l1tex" and s["peak"] == 560.0 and 0 < s["frac"] < 1 and "run in this process" in s["peak_source"]
+    assert s["hbm_algorithmic"]["frac"] > 1 and "not a bound" in s["hbm_algorithmic"]["note"]
+    assert "traffic_frac" not in s and s["traffic"] is None
+    # N = 8 weak: 4096 x 2048, half a voxel apart
+    assert bench.ray_roofline(24.6e6, 0.118, 1024, 4096, 2048, hbm, "measured", 173e6, live)["bound"] == "l1tex"
