@@ -729,7 +729,10 @@ void launch_persistent(vrdd_context* c, Kernel kernel, const Args& A, long long 
     // the five that fit, the rays of 1280 pixels march through one SM's L1 at once and evict one another's lines
     // (profiles/tuning_r2.md: oblique views 0.285 -> 0.259 ms, frontal views unchanged; more blocks under a register cap
     // are slower still).  The gather path is bound by instruction issue and wants all the warps it can get.
-    if (max_per_sm > 0 && c->var_persist_pct == 100 && (long long)max_per_sm * c->num_sms < cap) cap = (long long)max_per_sm * c->num_sms;
+    // (not for small frames: with fewer than four items per block the tail of the last round costs more than the cap gains —
+    // 512^2 frames: 0.048 ms uncapped, 0.051 ms with three blocks per SM)
+    if (max_per_sm > 0 && c->var_persist_pct == 100 && (long long)max_per_sm * c->num_sms < cap && items >= 4ll * max_per_sm * c->num_sms)
+        cap = (long long)max_per_sm * c->num_sms;
     kernel<<<(unsigned)(items < cap ? items : cap), kBlock, smem, c->stream>>>(A);
 }
 
